@@ -1,0 +1,169 @@
+/*
+ * scoary_b200.h -- C-ABI of libscoary_b200.so, the B200 (sm_100a) engine that
+ * replaces the per-gene statistics / pairwise-comparison / permutation path of
+ * Scoary.
+ *
+ * The reference (pure Python, /root/reference) has no FFI; the seam this
+ * library sits behind is the set of call sites in scoary/methods.py:
+ *   Setup_results(genedic, traitsdic, collapse)        methods.py:278 -> def :757
+ *     Perform_statistics(traits, genes)                methods.py:798 -> def :930
+ *     ss.fisher_exact(obs_table)                       methods.py:854
+ *   PairWiseComparisons((domain, argdict))             methods.py:1094/1105 -> def :1208
+ *     ConvertUPGMAtoPhyloTree(tree, GTC)               methods.py:1247 -> def :1386
+ *       class PhyloTree / Tip                          scoary/classes.py:199-592
+ *     Permute(tree, GTC, permutations, cutoffs)        methods.py:1305 -> def :1314
+ *       PermuteGTC(GTC)                                methods.py:1350 -> def :1371
+ * Each entry point below names the call site it replaces.  INTEGRATION.md shows
+ * the ctypes binding a maintainer would add to the reference.
+ *
+ * Conventions: plain pointers and sizes only; the caller owns every buffer it
+ * passes; the library never frees caller memory.  Every function returns 0 on
+ * success and a negative sb_status on failure; sb_last_error() gives the text.
+ * One context drives one GPU (one process per GPU; gene rows are sharded
+ * across processes by the host).  A context is not re-entrant.  "host" entry
+ * points block until their outputs are valid; "*_device" entry points only
+ * enqueue work on the context's stream.
+ *
+ * There is no CPU fallback: without a CUDA device sb_create fails.
+ */
+#ifndef SCOARY_B200_H
+#define SCOARY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB_VERSION 100          /* 0.1.0 */
+#define SB_MAX_TRAITS 64
+
+typedef struct sb_ctx sb_ctx;
+
+typedef enum {
+    SB_OK = 0,
+    SB_ERR_ARG = -1,            /* bad argument / call order */
+    SB_ERR_CUDA = -2,           /* CUDA runtime error (text in sb_last_error) */
+    SB_ERR_NOMEM = -3,
+    SB_ERR_STATE = -4           /* genes / trait / tree not set */
+} sb_status;
+
+/* Counters since sb_create (or the last sb_stats_reset).  Kernel times are
+ * only accumulated while profiling is on (sb_set_profiling), because they need
+ * a pair of CUDA events around each launch. */
+typedef struct {
+    int64_t kernel_launches;        /* launches of THIS library's kernels */
+    int64_t h2d_bytes;
+    int64_t d2h_bytes;
+    int64_t tests_contingency;      /* (gene, trait) tables built */
+    int64_t tests_walks;            /* (gene, labelling) tree walks, incl. permutations */
+    double ms_pack;                 /* K1 transpose/gather into walk order */
+    double ms_fisher;               /* K2+K3 contingency + Fisher */
+    double ms_shuffle;              /* Fisher-Yates label shuffles */
+    double ms_walk;                 /* K4 unpermuted walks */
+    double ms_permute;              /* K5 permutation walks (dominant kernel) */
+    double ms_reduce;               /* hit-sequence reduction */
+    int64_t launches_permute;       /* launches of the K5 kernel while profiling */
+    int32_t sm_count;
+    int32_t reserved;
+} sb_stats_t;
+
+/* ---- life cycle -------------------------------------------------------- */
+int sb_version(void);
+/* device = CUDA ordinal.  Fails (SB_ERR_CUDA) when no usable GPU exists. */
+int sb_create(int device, sb_ctx **out);
+void sb_destroy(sb_ctx *ctx);
+/* Text of the last error on ctx (ctx == NULL: last sb_create failure). */
+const char *sb_last_error(const sb_ctx *ctx);
+/* Run on a caller-owned cudaStream_t (e.g. torch's current stream); NULL
+ * restores the context's own stream. */
+int sb_set_stream(sb_ctx *ctx, void *cuda_stream);
+int sb_synchronize(sb_ctx *ctx);
+int sb_set_profiling(sb_ctx *ctx, int on);
+int sb_stats(sb_ctx *ctx, sb_stats_t *out);
+int sb_stats_reset(sb_ctx *ctx);
+
+/* ---- inputs ------------------------------------------------------------ */
+/* Gene presence/absence bitset, replaces genedic (methods.py:472-487; a cell
+ * is "present" unless it is "", "0" or "-").  bits: row-major uint64[G][W],
+ * bit (j & 63) of word (j >> 6) of row g = gene g present in isolate column j;
+ * N isolates, W >= ceil(N/64) and W even (16-byte row pitch); bits at
+ * positions >= N must be zero.  The host version copies to the device. */
+int sb_set_genes(sb_ctx *ctx, const uint64_t *bits, int64_t G, int32_t N, int32_t W);
+/* Same, but d_bits already lives in device memory and is borrowed, not copied;
+ * it must stay valid until the next sb_set_genes* or sb_destroy. */
+int sb_set_genes_device(sb_ctx *ctx, const uint64_t *d_bits, int64_t G, int32_t N, int32_t W);
+
+/* Trait t (0 <= t < SB_MAX_TRAITS), replaces traitsdic[trait] (methods.py:546-614):
+ * value bit = trait is "1", mask bit = isolate has a non-missing value for
+ * this trait (missing isolates are never counted, methods.py:580-598).
+ * Host pointers, uint64[W] each. */
+int sb_set_trait(sb_ctx *ctx, int32_t t, const uint64_t *value, const uint64_t *mask);
+
+/* Binary tree for trait t, already pruned of the trait's missing isolates
+ * (PruneForMissing, methods.py:709-739).  n_internal nodes listed children
+ * before parents, root last; child >= 0 is an internal node index, child < 0 is
+ * leaf id ~child (0 .. n_internal); leaf_to_col[leaf id] = isolate column in
+ * the gene bitset.  Replaces the nested-list `tree` argument of
+ * ConvertUPGMAtoPhyloTree (methods.py:1386).  Host pointers. */
+int sb_set_tree(sb_ctx *ctx, int32_t t, const int32_t *left, const int32_t *right,
+                int32_t n_internal, const int32_t *leaf_to_col);
+
+/* ---- the hot path ------------------------------------------------------ */
+/* Setup_results inner loop (methods.py:791-857): for every gene, the 2x2 table
+ * of Perform_statistics (methods.py:930-982) and the two-sided Fisher exact p
+ * of ss.fisher_exact (methods.py:854, SciPy 1.18.1 rule).
+ *   counts int32[G][4] = tpgp, tngp, tpgn, tngn          (bit-exact)
+ *   p      double[G]   two-sided p (<= 1e-10 relative vs SciPy); 1.0 when a
+ *                      margin is zero (the host applies the skip rule of
+ *                      methods.py:804-814 from the counts)
+ *   hash   uint64[G][2] 128-bit hash of the row masked by the trait's mask,
+ *                      for --collapse grouping (methods.py:823-840); may be NULL
+ * Any output pointer may be NULL. */
+int sb_contingency_fisher(sb_ctx *ctx, int32_t t, int32_t *counts, double *p, uint64_t *hash);
+int sb_contingency_fisher_device(sb_ctx *ctx, int32_t t, int32_t *d_counts, double *d_p,
+                                 uint64_t *d_hash);
+
+/* ConvertUPGMAtoPhyloTree (methods.py:1386-1402) for S genes: max contrasting
+ * pairs and, given those, max supporting / opposing pairs (classes.py:199-592).
+ * gene_idx: int64[S] gene rows (NULL = rows 0..S-1).  pairs int32[S][3] =
+ * Total, Pro, Anti -- bit-exact. */
+int sb_pairwise(sb_ctx *ctx, int32_t t, const int64_t *gene_idx, int64_t S, int32_t *pairs);
+int sb_pairwise_device(sb_ctx *ctx, int32_t t, const int64_t *d_gene_idx, int64_t S,
+                       int32_t *d_pairs);
+
+/* Permute (methods.py:1314-1369) for S genes and P label permutations.
+ * Permutation i of trait t is a Fisher-Yates shuffle of the trait's labels
+ * (PermuteGTC, methods.py:1371-1384) driven by Philox4x32-10 keyed by seed with
+ * counter (step/2, i, t, 0x5C0A27) -- see DESIGN.md; the reference's own stream
+ * is an unseeded Mersenne Twister, so agreement with it is distributional.
+ * hit_i = (S_i/Total_i >= S/Total) with S = Pro if Pro >= Anti else Anti
+ * (methods.py:1333-1355), evaluated exactly in integers.
+ *   early_stop = 0: all P permutations count; r = sum of hits, n_done = P.
+ *   early_stop = 1: the reference's sequential rule (methods.py:1360-1363) on
+ *     the ordered hit sequence: first i >= 30 with r_i >= rmin[i] stops,
+ *     n_done = i + 1.  rmin int32[P] is built by the host from the same
+ *     1 - binom.cdf(r, i, 0.1) < 0.05 test.
+ * Empirical p = (r + 1) / (n_done + 1) is formed by the host.
+ *   pairs int32[S][3] unpermuted Total, Pro, Anti (may be NULL);
+ *   r int32[S]; n_done int32[S]. */
+int sb_permute(sb_ctx *ctx, int32_t t, const int64_t *gene_idx, int64_t S, int32_t P,
+               uint64_t seed, int32_t early_stop, const int32_t *rmin, int32_t *pairs,
+               int32_t *r, int32_t *n_done);
+int sb_permute_device(sb_ctx *ctx, int32_t t, const int64_t *d_gene_idx, int64_t S, int32_t P,
+                      uint64_t seed, int32_t early_stop, const int32_t *d_rmin,
+                      int32_t *d_pairs, int32_t *d_r, int32_t *d_n_done);
+
+/* Test hook: the permuted label vectors themselves, by leaf id.
+ * labels uint8[P][n_leaves] (host). */
+int sb_debug_shuffled_labels(sb_ctx *ctx, int32_t t, int32_t P, uint64_t seed, uint8_t *labels);
+
+/* Integer-pipe microbenchmark used for the walk kernels' roofline denominator:
+ * runs `iters` rounds of dependent add/max chains on every SM and returns the
+ * measured int32 add+max operations per second. */
+int sb_int32_peak(sb_ctx *ctx, int32_t iters, double *ops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCOARY_B200_H */

@@ -1,0 +1,930 @@
+// engine.cu -- host side of libscoary_b200.so: context, device memory, the tree
+// compiler and the C-ABI declared in include/scoary_b200.h.
+//
+// Data layout in HBM:
+//   genes     uint64 [G][W]          isolate-column order, 16-byte row pitch
+//   trait t   uint64 [W] value, [W] mask
+//   lut       double2 [N+1]          log k! as (hi, lo)
+//   per tree  uint32 [W32p][Gs]      gene bits in walk order, transposed so the
+//                                    walk kernel's per-thread loads coalesce
+//             uint16 [n_ops]         the compiled stack program
+//             uint32 [P][W32p]       permuted label vectors in walk order
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/scoary_b200.h"
+#include "fisher.cuh"
+#include "walk.cuh"
+
+extern "C" void sb_build_logfact_dd(int32_t n, double *hi_lo);
+
+namespace {
+
+std::string g_create_error;
+
+enum Cat { CAT_PACK = 0, CAT_FISHER, CAT_SHUFFLE, CAT_WALK, CAT_PERMUTE, CAT_REDUCE, CAT_N };
+
+struct TimedEvent {
+    cudaEvent_t start, stop;
+    int cat;
+};
+
+struct TraitSlot {
+    bool has_trait = false;
+    std::vector<uint64_t> h_value, h_mask;
+    uint64_t *d_value = nullptr, *d_mask = nullptr;
+    // tree
+    bool has_tree = false;
+    bool finalized = false;        // labels + genesT built for the current genes/trait/tree
+    int32_t n_leaves = 0, n_internal = 0, W32 = 0, W32p = 0, depth = 0, shift = 0, n_ops = 0;
+    std::vector<int32_t> h_leaf_to_col, h_leaf_of_pos;
+    uint16_t *d_ops = nullptr;
+    int32_t *d_walk_col = nullptr, *d_leaf_of_pos = nullptr;
+    uint32_t *d_labels_leaf = nullptr;   // [W32]  by leaf id
+    uint32_t *d_labels0 = nullptr;       // [W32p] walk order, unpermuted
+    uint32_t *d_genesT = nullptr;        // [W32p][Gs]
+    int64_t Gs = 0;
+};
+
+}  // namespace
+
+struct sb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr, own_stream = nullptr;
+    std::string err;
+    int sm_count = 0;
+    int max_smem_optin = 0;
+    // genes
+    int64_t G = 0;
+    int32_t N = 0, W = 0;
+    uint64_t *d_genes = nullptr;
+    bool own_genes = false;
+    // lut
+    double2 *d_lut = nullptr;
+    int32_t lut_n = -1;
+    TraitSlot traits[SB_MAX_TRAITS];
+    // scratch
+    void *d_scratch[8] = {nullptr};
+    size_t scratch_bytes[8] = {0};
+    // stats / profiling
+    sb_stats_t stats;
+    bool profiling = false;
+    std::vector<TimedEvent> pending;
+    std::vector<TimedEvent> free_events;
+    int *d_peak_out = nullptr;
+};
+
+namespace {
+
+#define SB_CUDA(ctx, call)                                                                      \
+    do {                                                                                        \
+        cudaError_t e_ = (call);                                                                \
+        if (e_ != cudaSuccess) {                                                                \
+            char buf_[512];                                                                     \
+            snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                     __FILE__, __LINE__);                                                       \
+            (ctx)->err = buf_;                                                                  \
+            return SB_ERR_CUDA;                                                                 \
+        }                                                                                       \
+    } while (0)
+
+int fail(sb_ctx *ctx, int code, const char *msg)
+{
+    ctx->err = msg;
+    return code;
+}
+
+int ensure_scratch(sb_ctx *ctx, int slot, size_t bytes)
+{
+    if (bytes <= ctx->scratch_bytes[slot]) return SB_OK;
+    if (ctx->d_scratch[slot]) SB_CUDA(ctx, cudaFree(ctx->d_scratch[slot]));
+    ctx->d_scratch[slot] = nullptr;
+    ctx->scratch_bytes[slot] = 0;
+    size_t cap = bytes + bytes / 8 + 256;
+    SB_CUDA(ctx, cudaMalloc(&ctx->d_scratch[slot], cap));
+    ctx->scratch_bytes[slot] = cap;
+    return SB_OK;
+}
+
+// ---- profiling: a pair of events per launch, resolved lazily in sb_stats
+struct Timed {
+    sb_ctx *ctx;
+    TimedEvent ev;
+    bool on;
+    Timed(sb_ctx *c, int cat) : ctx(c), on(c->profiling)
+    {
+        if (!on) return;
+        if (!ctx->free_events.empty()) {
+            ev = ctx->free_events.back();
+            ctx->free_events.pop_back();
+        } else {
+            cudaEventCreate(&ev.start);
+            cudaEventCreate(&ev.stop);
+        }
+        ev.cat = cat;
+        cudaEventRecord(ev.start, ctx->stream);
+    }
+    ~Timed()
+    {
+        if (!on) return;
+        cudaEventRecord(ev.stop, ctx->stream);
+        ctx->pending.push_back(ev);
+    }
+};
+
+void resolve_events(sb_ctx *ctx)
+{
+    for (auto &e : ctx->pending) {
+        cudaEventSynchronize(e.stop);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e.start, e.stop);
+        switch (e.cat) {
+            case CAT_PACK: ctx->stats.ms_pack += ms; break;
+            case CAT_FISHER: ctx->stats.ms_fisher += ms; break;
+            case CAT_SHUFFLE: ctx->stats.ms_shuffle += ms; break;
+            case CAT_WALK: ctx->stats.ms_walk += ms; break;
+            case CAT_PERMUTE: ctx->stats.ms_permute += ms; ctx->stats.launches_permute += 1; break;
+            case CAT_REDUCE: ctx->stats.ms_reduce += ms; break;
+        }
+        ctx->free_events.push_back(e);
+    }
+    ctx->pending.clear();
+}
+
+void free_tree(TraitSlot &s)
+{
+    cudaFree(s.d_ops); s.d_ops = nullptr;
+    cudaFree(s.d_walk_col); s.d_walk_col = nullptr;
+    cudaFree(s.d_leaf_of_pos); s.d_leaf_of_pos = nullptr;
+    cudaFree(s.d_labels_leaf); s.d_labels_leaf = nullptr;
+    cudaFree(s.d_labels0); s.d_labels0 = nullptr;
+    cudaFree(s.d_genesT); s.d_genesT = nullptr;
+    s.has_tree = false;
+    s.finalized = false;
+}
+
+void free_trait(TraitSlot &s)
+{
+    cudaFree(s.d_value); s.d_value = nullptr;
+    cudaFree(s.d_mask); s.d_mask = nullptr;
+    s.has_trait = false;
+    s.finalized = false;
+}
+
+// ---- tree compiler --------------------------------------------------------
+// Turns the flattened binary tree into the stack program described in walk.cuh.
+struct Program {
+    std::vector<uint16_t> ops;
+    std::vector<int32_t> leaf_of_pos;   // walk position -> leaf id
+    int depth = 0;
+};
+
+bool compile_tree(const int32_t *left, const int32_t *right, int32_t n_internal, Program &out, std::string &err)
+{
+    const int32_t n_leaves = n_internal + 1;
+    std::vector<int32_t> need(n_internal, 0);
+    std::vector<uint8_t> seen_leaf(n_leaves, 0), seen_node(n_internal, 0);
+    for (int32_t v = 0; v < n_internal; ++v) {
+        const int32_t ch[2] = {left[v], right[v]};
+        for (int k = 0; k < 2; ++k) {
+            if (ch[k] >= 0) {
+                if (ch[k] >= v) { err = "tree nodes must list children before parents"; return false; }
+                if (seen_node[ch[k]]) { err = "internal node referenced twice"; return false; }
+                seen_node[ch[k]] = 1;
+            } else {
+                const int32_t leaf = ~ch[k];
+                if (leaf < 0 || leaf >= n_leaves) { err = "leaf id out of range"; return false; }
+                if (seen_leaf[leaf]) { err = "leaf referenced twice"; return false; }
+                seen_leaf[leaf] = 1;
+            }
+        }
+        const bool li = left[v] >= 0, ri = right[v] >= 0;
+        if (li && ri) {
+            const int a = need[left[v]], b = need[right[v]];
+            need[v] = (a == b) ? a + 1 : std::max(a, b);
+        } else if (li) need[v] = need[left[v]];
+        else if (ri) need[v] = need[right[v]];
+        else need[v] = 0;
+    }
+    for (int32_t v = 0; v + 1 < n_internal; ++v)
+        if (!seen_node[v]) { err = "tree is not connected (root must be the last node)"; return false; }
+    for (int32_t k = 0; k < n_leaves; ++k)
+        if (!seen_leaf[k]) { err = "leaf missing from tree"; return false; }
+
+    // raw op list: 0 cherry, 1 leaf, 2 merge
+    std::vector<uint8_t> raw;
+    raw.reserve(n_internal);
+    out.leaf_of_pos.clear();
+    out.leaf_of_pos.reserve(n_leaves);
+    struct Frame { int32_t node; int32_t phase; };
+    std::vector<Frame> st;
+    st.push_back({n_internal - 1, 0});
+    while (!st.empty()) {
+        Frame &f = st.back();
+        const int32_t v = f.node;
+        const bool li = left[v] >= 0, ri = right[v] >= 0;
+        if (!li && !ri) {
+            out.leaf_of_pos.push_back(~left[v]);
+            out.leaf_of_pos.push_back(~right[v]);
+            raw.push_back(0);
+            st.pop_back();
+        } else if (li != ri) {
+            const int32_t inner = li ? left[v] : right[v];
+            const int32_t leaf = li ? ~right[v] : ~left[v];
+            if (f.phase == 0) {
+                f.phase = 1;
+                st.push_back({inner, 0});
+            } else {
+                out.leaf_of_pos.push_back(leaf);
+                raw.push_back(1);
+                st.pop_back();
+            }
+        } else {
+            const bool left_first = need[left[v]] >= need[right[v]];
+            const int32_t first = left_first ? left[v] : right[v];
+            const int32_t second = left_first ? right[v] : left[v];
+            if (f.phase == 0) {
+                f.phase = 1;
+                st.push_back({first, 0});
+            } else if (f.phase == 1) {
+                f.phase = 2;
+                st.push_back({second, 0});
+            } else {
+                raw.push_back(2);
+                st.pop_back();
+            }
+        }
+    }
+    // run-length encode; every cherry after the first pushes the pending accumulator
+    out.ops.clear();
+    int depth = 0, sp = 0;
+    bool first_cherry = true;
+    size_t i = 0;
+    while (i < raw.size()) {
+        if (raw[i] == 0) {
+            if (first_cherry) {
+                out.ops.push_back((uint16_t)sb::OP_CHERRY);
+                first_cherry = false;
+            } else {
+                out.ops.push_back((uint16_t)sb::OP_CHERRY_PUSH);
+                ++sp;
+                depth = std::max(depth, sp);
+            }
+            ++i;
+        } else {
+            const uint8_t kind = raw[i];
+            size_t j = i;
+            while (j < raw.size() && raw[j] == kind) ++j;
+            size_t cnt = j - i;
+            if (kind == 2) sp -= (int)cnt;
+            while (cnt > 0) {
+                const size_t c = std::min<size_t>(cnt, 16383);
+                out.ops.push_back((uint16_t)((c << 2) | (kind == 1 ? sb::OP_LEAF : sb::OP_MERGE)));
+                cnt -= c;
+            }
+            i = j;
+        }
+    }
+    if (sp != 0) { err = "internal error: unbalanced stack program"; return false; }
+    out.depth = depth;
+    return true;
+}
+
+int ensure_lut(sb_ctx *ctx, int32_t n)
+{
+    if (n <= ctx->lut_n) return SB_OK;
+    std::vector<double> h((size_t)(n + 1) * 2);
+    sb_build_logfact_dd(n, h.data());
+    if (ctx->d_lut) SB_CUDA(ctx, cudaFree(ctx->d_lut));
+    ctx->d_lut = nullptr;
+    SB_CUDA(ctx, cudaMalloc(&ctx->d_lut, sizeof(double2) * (size_t)(n + 1)));
+    SB_CUDA(ctx, cudaMemcpyAsync(ctx->d_lut, h.data(), sizeof(double2) * (size_t)(n + 1), cudaMemcpyHostToDevice,
+                                 ctx->stream));
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // h goes out of scope
+    ctx->stats.h2d_bytes += (int64_t)sizeof(double2) * (n + 1);
+    ctx->lut_n = n;
+    return SB_OK;
+}
+
+int set_genes_common(sb_ctx *ctx, int64_t G, int32_t N, int32_t W)
+{
+    if (G <= 0 || N <= 0) return fail(ctx, SB_ERR_ARG, "sb_set_genes: G and N must be positive");
+    if (W < (N + 63) / 64 || (W & 1)) return fail(ctx, SB_ERR_ARG, "sb_set_genes: W must be even and >= ceil(N/64)");
+    if (ctx->own_genes && ctx->d_genes) SB_CUDA(ctx, cudaFree(ctx->d_genes));
+    ctx->d_genes = nullptr;
+    ctx->own_genes = false;
+    if (N != ctx->N || W != ctx->W) {
+        for (auto &s : ctx->traits) { free_trait(s); free_tree(s); }
+    }
+    for (auto &s : ctx->traits) {   // gene-dependent derived data is stale
+        s.finalized = false;
+        cudaFree(s.d_genesT);
+        s.d_genesT = nullptr;
+    }
+    ctx->G = G; ctx->N = N; ctx->W = W;
+    return ensure_lut(ctx, N);
+}
+
+// Build labels (by leaf id and in walk order) and the transposed gene matrix for slot t.
+int finalize_slot(sb_ctx *ctx, int32_t t)
+{
+    TraitSlot &s = ctx->traits[t];
+    if (!ctx->d_genes) return fail(ctx, SB_ERR_STATE, "genes not set (sb_set_genes)");
+    if (!s.has_trait) return fail(ctx, SB_ERR_STATE, "trait not set (sb_set_trait)");
+    if (!s.has_tree) return fail(ctx, SB_ERR_STATE, "tree not set (sb_set_tree)");
+    if (s.finalized) return SB_OK;
+    std::vector<uint32_t> lab_leaf(s.W32, 0u), lab0(s.W32p, 0u);
+    for (int32_t k = 0; k < s.n_leaves; ++k) {
+        const int32_t col = s.h_leaf_to_col[k];
+        if (col < 0 || col >= ctx->N) return fail(ctx, SB_ERR_ARG, "sb_set_tree: leaf_to_col out of range");
+        if (!((s.h_mask[col >> 6] >> (col & 63)) & 1ULL))
+            return fail(ctx, SB_ERR_ARG, "tree has a leaf whose trait value is missing: prune the tree first "
+                                         "(PruneForMissing, scoary/methods.py:709-739)");
+        if ((s.h_value[col >> 6] >> (col & 63)) & 1ULL) lab_leaf[k >> 5] |= (1u << (k & 31));
+    }
+    for (int32_t pos = 0; pos < s.n_leaves; ++pos) {
+        const int32_t leaf = s.h_leaf_of_pos[pos];
+        if ((lab_leaf[leaf >> 5] >> (leaf & 31)) & 1u) lab0[pos >> 5] |= (1u << (pos & 31));
+    }
+    if (!s.d_labels_leaf) SB_CUDA(ctx, cudaMalloc(&s.d_labels_leaf, sizeof(uint32_t) * s.W32));
+    if (!s.d_labels0) SB_CUDA(ctx, cudaMalloc(&s.d_labels0, sizeof(uint32_t) * s.W32p));
+    SB_CUDA(ctx, cudaMemcpyAsync(s.d_labels_leaf, lab_leaf.data(), sizeof(uint32_t) * s.W32, cudaMemcpyHostToDevice,
+                                 ctx->stream));
+    SB_CUDA(ctx, cudaMemcpyAsync(s.d_labels0, lab0.data(), sizeof(uint32_t) * s.W32p, cudaMemcpyHostToDevice,
+                                 ctx->stream));
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stats.h2d_bytes += (int64_t)sizeof(uint32_t) * (s.W32 + s.W32p);
+    if (!s.d_genesT) {
+        s.Gs = (ctx->G + 31) / 32 * 32;
+        SB_CUDA(ctx, cudaMalloc(&s.d_genesT, sizeof(uint32_t) * (size_t)s.W32p * (size_t)s.Gs));
+        const size_t smem = sizeof(uint32_t) * 32 * (size_t)(2 * ctx->W + 1);
+        if (smem > (size_t)ctx->max_smem_optin) return fail(ctx, SB_ERR_ARG, "too many isolates for the pack kernel");
+        SB_CUDA(ctx, cudaFuncSetAttribute(sb::pack_walk_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)smem));
+        Timed tm(ctx, CAT_PACK);
+        const unsigned blocks = (unsigned)((ctx->G + 31) / 32);
+        sb::pack_walk_order_kernel<<<blocks, 256, smem, ctx->stream>>>(ctx->d_genes, ctx->G, ctx->W, s.d_walk_col,
+                                                                       s.n_leaves, s.W32p, s.Gs, s.d_genesT);
+        ctx->stats.kernel_launches += 1;
+        SB_CUDA(ctx, cudaGetLastError());
+    }
+    s.finalized = true;
+    return SB_OK;
+}
+
+int launch_fisher(sb_ctx *ctx, int32_t t, int32_t *d_counts, double *d_p, uint64_t *d_hash)
+{
+    if (t < 0 || t >= SB_MAX_TRAITS) return fail(ctx, SB_ERR_ARG, "trait index out of range");
+    TraitSlot &s = ctx->traits[t];
+    if (!ctx->d_genes) return fail(ctx, SB_ERR_STATE, "genes not set (sb_set_genes)");
+    if (!s.has_trait) return fail(ctx, SB_ERR_STATE, "trait not set (sb_set_trait)");
+    sb::FisherArgs A;
+    A.genes = ctx->d_genes; A.G = ctx->G; A.W = ctx->W; A.Wn = (ctx->N + 63) / 64;
+    A.tvalue = s.d_value; A.tmask = s.d_mask;
+    A.lut = ctx->d_lut; A.lut_n = ctx->lut_n;
+    A.counts = d_counts; A.p = d_p; A.hash = d_hash;
+    const size_t row_bytes = (size_t)ctx->W * 8;
+    const size_t lut_bytes = sizeof(double2) * (size_t)(ctx->lut_n + 1);
+    const size_t fixed = 16 + 2 * row_bytes;
+    const size_t budget = (size_t)ctx->max_smem_optin;
+    bool lut_smem = (fixed + lut_bytes + 2 * 8 * row_bytes) <= budget;
+    size_t avail = budget - fixed - (lut_smem ? lut_bytes : 0);
+    int rows = (int)std::min<size_t>(avail / 2 / row_bytes, std::max<size_t>(8, 32768 / row_bytes));
+    rows = std::max(1, std::min(rows, 512));
+    if ((size_t)rows * row_bytes * 2 + fixed > budget) return fail(ctx, SB_ERR_ARG, "row too long for shared memory");
+    // keep every SM busy: shrink tiles if there would be fewer tiles than SMs
+    while (rows > 16 && (ctx->G + rows - 1) / rows < 2 * ctx->sm_count) rows /= 2;
+    A.rows_per_tile = rows;
+    A.n_tiles = (int32_t)((ctx->G + rows - 1) / rows);
+    const size_t smem = fixed + 2 * (size_t)rows * row_bytes + (lut_smem ? lut_bytes : 0);
+    const int grid = std::min<int>(A.n_tiles, ctx->sm_count);
+    const bool hash = d_hash != nullptr;
+    Timed tm(ctx, CAT_FISHER);
+#define SB_LAUNCH_FISHER(L, H)                                                                                     \
+    do {                                                                                                           \
+        SB_CUDA(ctx, cudaFuncSetAttribute(sb::fisher_kernel<L, H>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                          (int)smem));                                                             \
+        sb::fisher_kernel<L, H><<<grid, sb::FISHER_THREADS, smem, ctx->stream>>>(A);                               \
+    } while (0)
+    if (lut_smem && hash) SB_LAUNCH_FISHER(true, true);
+    else if (lut_smem) SB_LAUNCH_FISHER(true, false);
+    else if (hash) SB_LAUNCH_FISHER(false, true);
+    else SB_LAUNCH_FISHER(false, false);
+#undef SB_LAUNCH_FISHER
+    ctx->stats.kernel_launches += 1;
+    ctx->stats.tests_contingency += ctx->G;
+    SB_CUDA(ctx, cudaGetLastError());
+    return SB_OK;
+}
+
+size_t walk_smem_bytes(const TraitSlot &s, int label_rows)
+{
+    return 16 + sizeof(uint32_t) * (size_t)label_rows * s.W32p + sizeof(int) * 10 * (size_t)std::max(1, s.depth) *
+                                                                     sb::WALK_THREADS;
+}
+
+void fill_walk_args(sb_ctx *ctx, const TraitSlot &s, sb::WalkArgs &A, const int64_t *d_gene_idx, int64_t S)
+{
+    memset(&A, 0, sizeof A);
+    A.genesT = s.d_genesT; A.Gs = s.Gs; A.gene_idx = d_gene_idx; A.S = S;
+    A.W32p = s.W32p; A.ops = s.d_ops; A.n_ops = s.n_ops; A.n_leaves = s.n_leaves; A.shift = s.shift;
+    A.stack_depth = s.depth;
+    (void)ctx;
+}
+
+int launch_pairwise(sb_ctx *ctx, int32_t t, const int64_t *d_gene_idx, int64_t S, int32_t *d_pairs)
+{
+    TraitSlot &s = ctx->traits[t];
+    sb::WalkArgs A;
+    fill_walk_args(ctx, s, A, d_gene_idx, S);
+    A.labelsW = s.d_labels0; A.P = 1; A.perms_per_block = 1; A.n_chunks = 1; A.pairs = d_pairs;
+    const size_t smem = walk_smem_bytes(s, 1);
+    if (smem > (size_t)ctx->max_smem_optin) return fail(ctx, SB_ERR_ARG, "tree too deep for shared memory");
+    SB_CUDA(ctx, cudaFuncSetAttribute(sb::walk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    Timed tm(ctx, CAT_WALK);
+    dim3 grid((unsigned)((S + sb::WALK_THREADS - 1) / sb::WALK_THREADS), 1, 1);
+    sb::walk_kernel<false><<<grid, sb::WALK_THREADS, smem, ctx->stream>>>(A);
+    ctx->stats.kernel_launches += 1;
+    ctx->stats.tests_walks += S;
+    SB_CUDA(ctx, cudaGetLastError());
+    return SB_OK;
+}
+
+int launch_shuffle(sb_ctx *ctx, int32_t t, int32_t P, uint64_t seed, uint32_t *d_labelsW, uint8_t *d_dbg)
+{
+    TraitSlot &s = ctx->traits[t];
+    const size_t smem = sizeof(uint32_t) * (size_t)s.W32 * 64;
+    if (smem > (size_t)ctx->max_smem_optin) return fail(ctx, SB_ERR_ARG, "too many leaves for the shuffle kernel");
+    SB_CUDA(ctx, cudaFuncSetAttribute(sb::shuffle_labels_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    Timed tm(ctx, CAT_SHUFFLE);
+    sb::shuffle_labels_kernel<<<(P + 63) / 64, 64, smem, ctx->stream>>>(s.d_labels_leaf, s.n_leaves, s.W32, s.W32p,
+                                                                       s.d_leaf_of_pos, seed, t, P, d_labelsW, d_dbg);
+    ctx->stats.kernel_launches += 1;
+    SB_CUDA(ctx, cudaGetLastError());
+    return SB_OK;
+}
+
+// d_unperm: [S][3] device (input, already computed); d_r / d_n_done outputs
+int launch_permute(sb_ctx *ctx, int32_t t, const int64_t *d_gene_idx, int64_t S, int32_t P, uint64_t seed,
+                   int32_t early_stop, const int32_t *d_rmin, const int32_t *d_unperm, int32_t *d_r, int32_t *d_n_done)
+{
+    TraitSlot &s = ctx->traits[t];
+    // scratch 0: labelsW [P][W32p]; scratch 1: hitbits [S][n_chunks]
+    int rc = ensure_scratch(ctx, 0, sizeof(uint32_t) * (size_t)P * s.W32p);
+    if (rc) return rc;
+    uint32_t *d_labelsW = (uint32_t *)ctx->d_scratch[0];
+    rc = launch_shuffle(ctx, t, P, seed, d_labelsW, nullptr);
+    if (rc) return rc;
+
+    const int64_t tiles = (S + sb::WALK_THREADS - 1) / sb::WALK_THREADS;
+    // perms per block (<= 32: one word of hit flags): pick the size that keeps the most
+    // warps resident (the per-thread DP stack dominates shared memory), then make sure
+    // there are a few blocks per SM even when only a handful of genes are walked.
+    int ppb = 1;
+    {
+        int best_blocks = -1;
+        for (int cand = sb::PERMS_PER_BLOCK_MAX; cand >= 4; cand /= 2) {
+            const size_t need = walk_smem_bytes(s, cand) + 1024;   // + per-block reservation
+            if (need > (size_t)ctx->max_smem_optin) continue;
+            const int blocks = (int)std::min<size_t>(12, (size_t)(228 * 1024) / need);
+            if (blocks > best_blocks) { best_blocks = blocks; ppb = cand; }
+        }
+        if (best_blocks < 0) {
+            if (walk_smem_bytes(s, 1) > (size_t)ctx->max_smem_optin)
+                return fail(ctx, SB_ERR_ARG, "tree too deep for shared memory");
+            ppb = 1;
+        }
+    }
+    ppb = std::min(ppb, P);
+    const int64_t want_chunks = (4LL * ctx->sm_count + tiles - 1) / tiles;
+    if (want_chunks > 1) ppb = (int)std::max<int64_t>(1, std::min<int64_t>(ppb, P / want_chunks));
+    const int n_chunks = (P + ppb - 1) / ppb;
+    rc = ensure_scratch(ctx, 1, sizeof(uint32_t) * (size_t)S * n_chunks);
+    if (rc) return rc;
+    uint32_t *d_hits = (uint32_t *)ctx->d_scratch[1];
+
+    sb::WalkArgs A;
+    fill_walk_args(ctx, s, A, d_gene_idx, S);
+    A.labelsW = d_labelsW; A.P = P; A.perms_per_block = ppb; A.n_chunks = n_chunks; A.unperm = d_unperm;
+    A.hitbits = d_hits;
+    const size_t smem = walk_smem_bytes(s, ppb);
+    SB_CUDA(ctx, cudaFuncSetAttribute(sb::walk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        Timed tm(ctx, CAT_PERMUTE);
+        dim3 grid((unsigned)tiles, (unsigned)n_chunks, 1);
+        sb::walk_kernel<true><<<grid, sb::WALK_THREADS, smem, ctx->stream>>>(A);
+        ctx->stats.kernel_launches += 1;
+        ctx->stats.tests_walks += S * (int64_t)P;
+        SB_CUDA(ctx, cudaGetLastError());
+    }
+    {
+        Timed tm(ctx, CAT_REDUCE);
+        sb::reduce_hits_kernel<<<(unsigned)((S + 255) / 256), 256, 0, ctx->stream>>>(d_hits, S, n_chunks, ppb, P, early_stop,
+                                                                                    d_rmin, d_r, d_n_done);
+        ctx->stats.kernel_launches += 1;
+        SB_CUDA(ctx, cudaGetLastError());
+    }
+    return SB_OK;
+}
+
+int check_walk_ready(sb_ctx *ctx, int32_t t, int64_t S)
+{
+    if (t < 0 || t >= SB_MAX_TRAITS) return fail(ctx, SB_ERR_ARG, "trait index out of range");
+    if (S <= 0) return fail(ctx, SB_ERR_ARG, "S must be positive");
+    return finalize_slot(ctx, t);
+}
+
+}  // namespace
+
+// ================================================================== C-ABI
+extern "C" {
+
+int sb_version(void) { return SB_VERSION; }
+
+const char *sb_last_error(const sb_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int sb_create(int device, sb_ctx **out)
+{
+    if (!out) { g_create_error = "sb_create: out is NULL"; return SB_ERR_ARG; }
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        g_create_error = std::string("no CUDA device available (libscoary_b200 has no CPU fallback): ") +
+                         cudaGetErrorString(e);
+        return SB_ERR_CUDA;
+    }
+    if (device < 0 || device >= n) { g_create_error = "sb_create: device ordinal out of range"; return SB_ERR_ARG; }
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return SB_ERR_CUDA; }
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return SB_ERR_CUDA; }
+    if (prop.major != 10) {
+        g_create_error = "libscoary_b200 is built for sm_100a (B200) only; found compute capability " +
+                         std::to_string(prop.major) + "." + std::to_string(prop.minor);
+        return SB_ERR_CUDA;
+    }
+    sb_ctx *ctx = new sb_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    memset(&ctx->stats, 0, sizeof ctx->stats);
+    ctx->stats.sm_count = ctx->sm_count;
+    e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return SB_ERR_CUDA; }
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return SB_OK;
+}
+
+void sb_destroy(sb_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    resolve_events(ctx);
+    for (auto &e : ctx->free_events) { cudaEventDestroy(e.start); cudaEventDestroy(e.stop); }
+    for (auto &s : ctx->traits) { free_trait(s); free_tree(s); }
+    if (ctx->own_genes) cudaFree(ctx->d_genes);
+    cudaFree(ctx->d_lut);
+    cudaFree(ctx->d_peak_out);
+    for (auto p : ctx->d_scratch) cudaFree(p);
+    cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+int sb_set_stream(sb_ctx *ctx, void *cuda_stream)
+{
+    if (!ctx) return SB_ERR_ARG;
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return SB_OK;
+}
+
+int sb_synchronize(sb_ctx *ctx)
+{
+    if (!ctx) return SB_ERR_ARG;
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SB_OK;
+}
+
+int sb_set_profiling(sb_ctx *ctx, int on)
+{
+    if (!ctx) return SB_ERR_ARG;
+    ctx->profiling = on != 0;
+    return SB_OK;
+}
+
+int sb_stats(sb_ctx *ctx, sb_stats_t *out)
+{
+    if (!ctx || !out) return SB_ERR_ARG;
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    resolve_events(ctx);
+    *out = ctx->stats;
+    return SB_OK;
+}
+
+int sb_stats_reset(sb_ctx *ctx)
+{
+    if (!ctx) return SB_ERR_ARG;
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    resolve_events(ctx);
+    memset(&ctx->stats, 0, sizeof ctx->stats);
+    ctx->stats.sm_count = ctx->sm_count;
+    return SB_OK;
+}
+
+int sb_set_genes(sb_ctx *ctx, const uint64_t *bits, int64_t G, int32_t N, int32_t W)
+{
+    if (!ctx || !bits) return SB_ERR_ARG;
+    SB_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = set_genes_common(ctx, G, N, W);
+    if (rc) return rc;
+    const size_t bytes = sizeof(uint64_t) * (size_t)G * (size_t)W;
+    SB_CUDA(ctx, cudaMalloc(&ctx->d_genes, bytes));
+    ctx->own_genes = true;
+    SB_CUDA(ctx, cudaMemcpyAsync(ctx->d_genes, bits, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->stats.h2d_bytes += (int64_t)bytes;
+    return SB_OK;
+}
+
+int sb_set_genes_device(sb_ctx *ctx, const uint64_t *d_bits, int64_t G, int32_t N, int32_t W)
+{
+    if (!ctx || !d_bits) return SB_ERR_ARG;
+    SB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (((uintptr_t)d_bits) & 15) return fail(ctx, SB_ERR_ARG, "sb_set_genes_device: pointer must be 16-byte aligned");
+    int rc = set_genes_common(ctx, G, N, W);
+    if (rc) return rc;
+    ctx->d_genes = const_cast<uint64_t *>(d_bits);
+    ctx->own_genes = false;
+    return SB_OK;
+}
+
+int sb_set_trait(sb_ctx *ctx, int32_t t, const uint64_t *value, const uint64_t *mask)
+{
+    if (!ctx || !value || !mask) return SB_ERR_ARG;
+    if (t < 0 || t >= SB_MAX_TRAITS) return fail(ctx, SB_ERR_ARG, "trait index out of range");
+    if (ctx->W == 0) return fail(ctx, SB_ERR_STATE, "call sb_set_genes before sb_set_trait");
+    SB_CUDA(ctx, cudaSetDevice(ctx->device));
+    TraitSlot &s = ctx->traits[t];
+    const int W = ctx->W;
+    s.h_value.assign(value, value + W);
+    s.h_mask.assign(mask, mask + W);
+    for (int w = 0; w < W; ++w) s.h_value[w] &= s.h_mask[w];
+    const int tail = ctx->N & 63;
+    for (int w = 0; w < W; ++w) {   // no bits beyond N
+        uint64_t keep = ~0ULL;
+        if (w > (ctx->N - 1) / 64) keep = 0;
+        else if (w == (ctx->N - 1) / 64 && tail) keep = (1ULL << tail) - 1;
+        s.h_value[w] &= keep;
+        s.h_mask[w] &= keep;
+    }
+    if (!s.d_value) SB_CUDA(ctx, cudaMalloc(&s.d_value, sizeof(uint64_t) * W));
+    if (!s.d_mask) SB_CUDA(ctx, cudaMalloc(&s.d_mask, sizeof(uint64_t) * W));
+    SB_CUDA(ctx, cudaMemcpyAsync(s.d_value, s.h_value.data(), sizeof(uint64_t) * W, cudaMemcpyHostToDevice, ctx->stream));
+    SB_CUDA(ctx, cudaMemcpyAsync(s.d_mask, s.h_mask.data(), sizeof(uint64_t) * W, cudaMemcpyHostToDevice, ctx->stream));
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stats.h2d_bytes += (int64_t)sizeof(uint64_t) * 2 * W;
+    s.has_trait = true;
+    s.finalized = false;   // labels depend on the trait; genesT does not
+    return SB_OK;
+}
+
+int sb_set_tree(sb_ctx *ctx, int32_t t, const int32_t *left, const int32_t *right, int32_t n_internal,
+                const int32_t *leaf_to_col)
+{
+    if (!ctx || !left || !right || !leaf_to_col) return SB_ERR_ARG;
+    if (t < 0 || t >= SB_MAX_TRAITS) return fail(ctx, SB_ERR_ARG, "trait index out of range");
+    if (n_internal < 1) return fail(ctx, SB_ERR_ARG, "sb_set_tree: need at least two leaves");
+    if (n_internal + 1 > 32766) return fail(ctx, SB_ERR_ARG, "sb_set_tree: at most 32766 leaves (32-bit DP keys)");
+    if (ctx->W == 0) return fail(ctx, SB_ERR_STATE, "call sb_set_genes before sb_set_tree");
+    SB_CUDA(ctx, cudaSetDevice(ctx->device));
+    Program prog;
+    std::string err;
+    if (!compile_tree(left, right, n_internal, prog, err)) return fail(ctx, SB_ERR_ARG, err.c_str());
+    TraitSlot &s = ctx->traits[t];
+    free_tree(s);
+    s.n_internal = n_internal;
+    s.n_leaves = n_internal + 1;
+    s.W32 = (s.n_leaves + 31) / 32;
+    s.W32p = (s.W32 + 3) / 4 * 4;
+    s.depth = prog.depth;
+    s.shift = 1;
+    while ((1 << s.shift) <= s.n_leaves / 2) ++s.shift;   // 2^SH > max pairs (= floor(n/2)) >= pro, anti
+    s.n_ops = (int32_t)prog.ops.size();
+    s.h_leaf_to_col.assign(leaf_to_col, leaf_to_col + s.n_leaves);
+    s.h_leaf_of_pos = prog.leaf_of_pos;
+    std::vector<int32_t> walk_col(s.n_leaves);
+    for (int32_t pos = 0; pos < s.n_leaves; ++pos) {
+        const int32_t col = leaf_to_col[prog.leaf_of_pos[pos]];
+        if (col < 0 || col >= ctx->N) return fail(ctx, SB_ERR_ARG, "sb_set_tree: leaf_to_col out of range");
+        walk_col[pos] = col;
+    }
+    SB_CUDA(ctx, cudaMalloc(&s.d_ops, sizeof(uint16_t) * prog.ops.size()));
+    SB_CUDA(ctx, cudaMalloc(&s.d_walk_col, sizeof(int32_t) * s.n_leaves));
+    SB_CUDA(ctx, cudaMalloc(&s.d_leaf_of_pos, sizeof(int32_t) * s.n_leaves));
+    SB_CUDA(ctx, cudaMemcpyAsync(s.d_ops, prog.ops.data(), sizeof(uint16_t) * prog.ops.size(), cudaMemcpyHostToDevice,
+                                 ctx->stream));
+    SB_CUDA(ctx, cudaMemcpyAsync(s.d_walk_col, walk_col.data(), sizeof(int32_t) * s.n_leaves, cudaMemcpyHostToDevice,
+                                 ctx->stream));
+    SB_CUDA(ctx, cudaMemcpyAsync(s.d_leaf_of_pos, prog.leaf_of_pos.data(), sizeof(int32_t) * s.n_leaves,
+                                 cudaMemcpyHostToDevice, ctx->stream));
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stats.h2d_bytes += (int64_t)(sizeof(uint16_t) * prog.ops.size() + 2 * sizeof(int32_t) * s.n_leaves);
+    s.has_tree = true;
+    s.finalized = false;
+    return SB_OK;
+}
+
+int sb_contingency_fisher_device(sb_ctx *ctx, int32_t t, int32_t *d_counts, double *d_p, uint64_t *d_hash)
+{
+    if (!ctx) return SB_ERR_ARG;
+    SB_CUDA(ctx, cudaSetDevice(ctx->device));
+    return launch_fisher(ctx, t, d_counts, d_p, d_hash);
+}
+
+int sb_contingency_fisher(sb_ctx *ctx, int32_t t, int32_t *counts, double *p, uint64_t *hash)
+{
+    if (!ctx) return SB_ERR_ARG;
+    SB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t G = (size_t)ctx->G;
+    if (G == 0) return fail(ctx, SB_ERR_STATE, "genes not set (sb_set_genes)");
+    int rc = ensure_scratch(ctx, 2, G * (16 + 8 + 16));
+    if (rc) return rc;
+    char *base = (char *)ctx->d_scratch[2];
+    int32_t *d_counts = (int32_t *)base;
+    double *d_p = (double *)(base + G * 16);
+    uint64_t *d_hash = (uint64_t *)(base + G * 24);
+    rc = launch_fisher(ctx, t, d_counts, p ? d_p : nullptr, hash ? d_hash : nullptr);
+    if (rc) return rc;
+    if (counts) SB_CUDA(ctx, cudaMemcpyAsync(counts, d_counts, G * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    if (p) SB_CUDA(ctx, cudaMemcpyAsync(p, d_p, G * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (hash) SB_CUDA(ctx, cudaMemcpyAsync(hash, d_hash, G * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stats.d2h_bytes += (int64_t)(G * ((counts ? 16 : 0) + (p ? 8 : 0) + (hash ? 16 : 0)));
+    return SB_OK;
+}
+
+int sb_pairwise_device(sb_ctx *ctx, int32_t t, const int64_t *d_gene_idx, int64_t S, int32_t *d_pairs)
+{
+    if (!ctx || !d_pairs) return SB_ERR_ARG;
+    SB_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = check_walk_ready(ctx, t, S);
+    if (rc) return rc;
+    if (!d_gene_idx && S > ctx->G) return fail(ctx, SB_ERR_ARG, "S exceeds the number of genes");
+    return launch_pairwise(ctx, t, d_gene_idx, S, d_pairs);
+}
+
+static int upload_gene_idx(sb_ctx *ctx, const int64_t *gene_idx, int64_t S, const int64_t **d_out)
+{
+    *d_out = nullptr;
+    if (!gene_idx) {
+        if (S > ctx->G) return fail(ctx, SB_ERR_ARG, "S exceeds the number of genes");
+        return SB_OK;
+    }
+    for (int64_t i = 0; i < S; ++i)
+        if (gene_idx[i] < 0 || gene_idx[i] >= ctx->G) return fail(ctx, SB_ERR_ARG, "gene_idx out of range");
+    int rc = ensure_scratch(ctx, 3, sizeof(int64_t) * (size_t)S);
+    if (rc) return rc;
+    SB_CUDA(ctx, cudaMemcpyAsync(ctx->d_scratch[3], gene_idx, sizeof(int64_t) * (size_t)S, cudaMemcpyHostToDevice,
+                                 ctx->stream));
+    ctx->stats.h2d_bytes += (int64_t)sizeof(int64_t) * S;
+    *d_out = (const int64_t *)ctx->d_scratch[3];
+    return SB_OK;
+}
+
+int sb_pairwise(sb_ctx *ctx, int32_t t, const int64_t *gene_idx, int64_t S, int32_t *pairs)
+{
+    if (!ctx || !pairs) return SB_ERR_ARG;
+    SB_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = check_walk_ready(ctx, t, S);
+    if (rc) return rc;
+    const int64_t *d_idx;
+    rc = upload_gene_idx(ctx, gene_idx, S, &d_idx);
+    if (rc) return rc;
+    rc = ensure_scratch(ctx, 4, sizeof(int32_t) * 3 * (size_t)S);
+    if (rc) return rc;
+    int32_t *d_pairs = (int32_t *)ctx->d_scratch[4];
+    rc = launch_pairwise(ctx, t, d_idx, S, d_pairs);
+    if (rc) return rc;
+    SB_CUDA(ctx, cudaMemcpyAsync(pairs, d_pairs, sizeof(int32_t) * 3 * (size_t)S, cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stats.d2h_bytes += (int64_t)sizeof(int32_t) * 3 * S;
+    return SB_OK;
+}
+
+int sb_permute_device(sb_ctx *ctx, int32_t t, const int64_t *d_gene_idx, int64_t S, int32_t P, uint64_t seed,
+                      int32_t early_stop, const int32_t *d_rmin, int32_t *d_pairs, int32_t *d_r, int32_t *d_n_done)
+{
+    if (!ctx || !d_r || !d_n_done) return SB_ERR_ARG;
+    SB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (P < 1) return fail(ctx, SB_ERR_ARG, "P must be >= 1");
+    if (early_stop && !d_rmin) return fail(ctx, SB_ERR_ARG, "early_stop needs rmin");
+    int rc = check_walk_ready(ctx, t, S);
+    if (rc) return rc;
+    if (!d_gene_idx && S > ctx->G) return fail(ctx, SB_ERR_ARG, "S exceeds the number of genes");
+    int32_t *d_un = d_pairs;
+    if (!d_un) {
+        rc = ensure_scratch(ctx, 4, sizeof(int32_t) * 3 * (size_t)S);
+        if (rc) return rc;
+        d_un = (int32_t *)ctx->d_scratch[4];
+    }
+    rc = launch_pairwise(ctx, t, d_gene_idx, S, d_un);
+    if (rc) return rc;
+    return launch_permute(ctx, t, d_gene_idx, S, P, seed, early_stop, d_rmin, d_un, d_r, d_n_done);
+}
+
+int sb_permute(sb_ctx *ctx, int32_t t, const int64_t *gene_idx, int64_t S, int32_t P, uint64_t seed,
+               int32_t early_stop, const int32_t *rmin, int32_t *pairs, int32_t *r, int32_t *n_done)
+{
+    if (!ctx || !r || !n_done) return SB_ERR_ARG;
+    SB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (P < 1) return fail(ctx, SB_ERR_ARG, "P must be >= 1");
+    if (early_stop && !rmin) return fail(ctx, SB_ERR_ARG, "early_stop needs rmin");
+    int rc = check_walk_ready(ctx, t, S);
+    if (rc) return rc;
+    const int64_t *d_idx;
+    rc = upload_gene_idx(ctx, gene_idx, S, &d_idx);
+    if (rc) return rc;
+    // scratch 4: unperm [S][3]; scratch 5: r [S], n_done [S]; scratch 6: rmin [P]
+    rc = ensure_scratch(ctx, 4, sizeof(int32_t) * 3 * (size_t)S);
+    if (rc) return rc;
+    rc = ensure_scratch(ctx, 5, sizeof(int32_t) * 2 * (size_t)S);
+    if (rc) return rc;
+    int32_t *d_un = (int32_t *)ctx->d_scratch[4];
+    int32_t *d_r = (int32_t *)ctx->d_scratch[5];
+    int32_t *d_nd = d_r + S;
+    const int32_t *d_rmin = nullptr;
+    if (early_stop) {
+        rc = ensure_scratch(ctx, 6, sizeof(int32_t) * (size_t)P);
+        if (rc) return rc;
+        SB_CUDA(ctx, cudaMemcpyAsync(ctx->d_scratch[6], rmin, sizeof(int32_t) * (size_t)P, cudaMemcpyHostToDevice,
+                                     ctx->stream));
+        ctx->stats.h2d_bytes += (int64_t)sizeof(int32_t) * P;
+        d_rmin = (const int32_t *)ctx->d_scratch[6];
+    }
+    rc = launch_pairwise(ctx, t, d_idx, S, d_un);
+    if (rc) return rc;
+    rc = launch_permute(ctx, t, d_idx, S, P, seed, early_stop, d_rmin, d_un, d_r, d_nd);
+    if (rc) return rc;
+    if (pairs) SB_CUDA(ctx, cudaMemcpyAsync(pairs, d_un, sizeof(int32_t) * 3 * (size_t)S, cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(ctx, cudaMemcpyAsync(r, d_r, sizeof(int32_t) * (size_t)S, cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(ctx, cudaMemcpyAsync(n_done, d_nd, sizeof(int32_t) * (size_t)S, cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stats.d2h_bytes += (int64_t)sizeof(int32_t) * S * (pairs ? 5 : 2);
+    return SB_OK;
+}
+
+int sb_debug_shuffled_labels(sb_ctx *ctx, int32_t t, int32_t P, uint64_t seed, uint8_t *labels)
+{
+    if (!ctx || !labels) return SB_ERR_ARG;
+    SB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (P < 1) return fail(ctx, SB_ERR_ARG, "P must be >= 1");
+    int rc = check_walk_ready(ctx, t, 1);
+    if (rc) return rc;
+    TraitSlot &s = ctx->traits[t];
+    rc = ensure_scratch(ctx, 0, sizeof(uint32_t) * (size_t)P * s.W32p);
+    if (rc) return rc;
+    rc = ensure_scratch(ctx, 7, (size_t)P * s.n_leaves);
+    if (rc) return rc;
+    rc = launch_shuffle(ctx, t, P, seed, (uint32_t *)ctx->d_scratch[0], (uint8_t *)ctx->d_scratch[7]);
+    if (rc) return rc;
+    SB_CUDA(ctx, cudaMemcpyAsync(labels, ctx->d_scratch[7], (size_t)P * s.n_leaves, cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SB_OK;
+}
+
+int sb_int32_peak(sb_ctx *ctx, int32_t iters, double *ops_per_s)
+{
+    if (!ctx || !ops_per_s || iters < 1) return SB_ERR_ARG;
+    SB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->d_peak_out) SB_CUDA(ctx, cudaMalloc(&ctx->d_peak_out, sizeof(int)));
+    const int blocks = ctx->sm_count * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    SB_CUDA(ctx, cudaEventCreate(&e0));
+    SB_CUDA(ctx, cudaEventCreate(&e1));
+    sb::int32_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(ctx->d_peak_out, 16, 12345);   // warm-up
+    SB_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+    sb::int32_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(ctx->d_peak_out, iters, 12345);
+    SB_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+    SB_CUDA(ctx, cudaEventSynchronize(e1));
+    ctx->stats.kernel_launches += 2;
+    float ms = 0.f;
+    SB_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    // one VIADDMNMX = one add + one max; 64 of them per thread per iteration
+    const double ops = 2.0 * 64.0 * (double)iters * (double)blocks * (double)threads;
+    *ops_per_s = ops / ((double)ms * 1e-3);
+    return SB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,254 @@
+// fisher.cuh -- K2+K3: per-gene 2x2 contingency table by popcount over the
+// packed bitset rows, then the two-sided Fisher exact p from a double-double
+// log-factorial LUT.
+//
+// Replaces, per (gene, trait): Perform_statistics (scoary/methods.py:930-982)
+// and the ss.fisher_exact call (methods.py:842-857).  The p-value rule is
+// SciPy 1.18.1's (scipy/stats/_stats_py.py, fisher_exact, two-sided):
+//   p = sum_{x on the observed side, from the extreme up to a} pmf(x)
+//     + sum_{x on the other side of the mode with pmf(x) <= pmf(a)(1+1e-14)} pmf(x)
+//   p = 1 when pmf(a) ~= pmf(mode);  p = min(p, 1).
+//
+// Data movement: gene rows are streamed tile-by-tile into shared memory with
+// 1-D TMA bulk copies (cp.async.bulk + mbarrier, double buffered) by a
+// persistent grid; one warp owns one row at a time: 128-bit shared loads,
+// __popcll, warp REDUX, then the warp walks the hypergeometric support.
+#pragma once
+#include "common.cuh"
+
+namespace sb {
+
+constexpr int FISHER_THREADS = 512;
+constexpr double FISHER_TIE_TOL = 1e-12;   // |log pmf ratio| below this is a tie (exact ties give 0)
+
+struct FisherArgs {
+    const uint64_t *genes;   // [G][W]
+    int64_t G;
+    int32_t W;               // words per row (even)
+    int32_t Wn;              // ceil(N/64): words that carry isolates (hash domain)
+    const uint64_t *tvalue;  // [W]
+    const uint64_t *tmask;   // [W]
+    const double2 *lut;      // [lut_n + 1] log k! as (hi, lo)
+    int32_t lut_n;
+    int32_t rows_per_tile;
+    int32_t n_tiles;
+    int32_t *counts;         // [G][4] or null
+    double *p;               // [G] or null
+    uint64_t *hash;          // [G][2] or null
+};
+
+// S(x) = lf[x] + lf[n1-x] + lf[n-x] + lf[n2-n+x]  (the x-dependent part of -log pmf)
+__device__ __forceinline__ dd fisher_S(const double2 *lut, int x, int n1, int n2, int n)
+{
+    dd s = dd_make(lut[x]);
+    s = dd_add(s, dd_make(lut[n1 - x]));
+    s = dd_add(s, dd_make(lut[n - x]));
+    s = dd_add(s, dd_make(lut[n2 - n + x]));
+    return s;
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Sum pmf(x) for x = x0, x0+dir, ..., count terms, terms non-increasing.
+// logp_a = log pmf(a) (dd), S_a = S(a).  Stops once terms are < 2^-80 pmf(a).
+__device__ __forceinline__ double fisher_tail(const double2 *lut, int x0, int dir, int count, int n1, int n2,
+                                              int n, dd logp_a, dd S_a, double pexact, int lane)
+{
+    double acc = 0.0;
+    const double cut = pexact * 8.271806125530277e-25;   // 2^-80
+    for (int base = 0; base < count; base += 32) {
+        int k = base + lane;
+        double term = 0.0;
+        if (k < count) {
+            int x = x0 + dir * k;
+            dd d = dd_sub(S_a, fisher_S(lut, x, n1, n2, n));   // log pmf(x) - log pmf(a)
+            dd L = dd_add(logp_a, d);
+            term = exp(L.hi) * (1.0 + L.lo);
+        }
+        acc += term;
+        double first = __shfl_sync(0xffffffffu, term, 0);
+        if (first < cut) break;
+    }
+    return warp_sum(acc);
+}
+
+// Warp-cooperative two-sided Fisher exact p for [[a, b], [c, d]].
+__device__ __forceinline__ double fisher_two_sided_warp(const double2 *lut, int a, int b, int c, int d, int lane)
+{
+    const int n1 = a + b, n2 = c + d, n = a + c, M = n1 + n2;
+    if (n1 == 0 || n2 == 0 || n == 0 || (b + d) == 0) return 1.0;
+    const int lo = max(0, n - n2), hi = min(n, n1);
+    const int mode = (int)((double)((long long)(n + 1) * (long long)(n1 + 1)) / (double)(M + 2));
+    if (a == mode) return 1.0;
+    // log pmf(a)
+    dd base = dd_make(lut[n1]);
+    base = dd_add(base, dd_make(lut[n2]));
+    base = dd_add(base, dd_make(lut[n]));
+    base = dd_add(base, dd_make(lut[M - n]));
+    base = dd_sub(base, dd_make(lut[M]));
+    const dd S_a = fisher_S(lut, a, n1, n2, n);
+    const dd logp_a = dd_sub(base, S_a);
+    const double pexact = exp(logp_a.hi) * (1.0 + logp_a.lo);
+    {   // pexact ~= pmode  ->  1
+        dd dm = dd_sub(S_a, fisher_S(lut, mode, n1, n2, n));
+        if (fabs(dm.hi + dm.lo) <= FISHER_TIE_TOL) return 1.0;
+    }
+    const int dir_obs = (a < mode) ? -1 : +1;          // away from the mode on the observed side
+    const int cnt_obs = (a < mode) ? (a - lo + 1) : (hi - a + 1);
+    double p = fisher_tail(lut, a, dir_obs, cnt_obs, n1, n2, n, logp_a, S_a, pexact, lane);
+
+    // other side: y_k = mode + dir2 * k, k = 1..K; included iff log pmf(y_k) - log pmf(a) <= tol.
+    // pmf decreases with k, so find the first included k with a 32-ary search.
+    const int dir2 = -dir_obs;
+    const int K = (dir2 > 0) ? (hi - mode) : (mode - lo);
+    int lo_k = 1, hi_k = K + 1;
+    while (hi_k > lo_k) {
+        const int len = hi_k - lo_k;
+        const int stride = (len + 31) >> 5;
+        const int k = lo_k + lane * stride;
+        bool pred = false;
+        if (k < hi_k) {
+            dd dk = dd_sub(S_a, fisher_S(lut, mode + dir2 * k, n1, n2, n));
+            pred = (dk.hi + dk.lo) <= FISHER_TIE_TOL;
+        }
+        const unsigned ball = __ballot_sync(0xffffffffu, pred);
+        if (ball == 0u) {
+            lo_k = lo_k + ((len - 1) / stride) * stride + 1;
+        } else {
+            const int f = __ffs(ball) - 1;
+            hi_k = lo_k + f * stride;
+            lo_k = (f == 0) ? hi_k : (lo_k + (f - 1) * stride + 1);
+        }
+    }
+    const int kstar = lo_k;
+    if (kstar <= K)
+        p += fisher_tail(lut, mode + dir2 * kstar, dir2, K - kstar + 1, n1, n2, n, logp_a, S_a, pexact, lane);
+    return fmin(p, 1.0);
+}
+
+template <bool LUT_SMEM, bool HASH>
+__global__ void __launch_bounds__(FISHER_THREADS) fisher_kernel(const FisherArgs A)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);            // 2 mbarriers (16 B)
+    uint64_t *s_tm = reinterpret_cast<uint64_t *>(smem_raw + 16);       // value & mask  [W]
+    uint64_t *s_m = s_tm + A.W;                                         // mask          [W]
+    uint64_t *s_stage0 = s_m + A.W;
+    const size_t tile_words = (size_t)A.rows_per_tile * A.W;
+    uint64_t *s_stage1 = s_stage0 + tile_words;
+    double2 *s_lut = reinterpret_cast<double2 *>(s_stage1 + tile_words);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = FISHER_THREADS / 32;
+
+    auto issue = [&](int tile, int buf) {
+        const int64_t row0 = (int64_t)tile * A.rows_per_tile;
+        const int rows = (int)min((int64_t)A.rows_per_tile, A.G - row0);
+        const uint32_t bytes = (uint32_t)rows * (uint32_t)A.W * 8u;
+        mbar_arrive_expect_tx(&bars[buf], bytes);
+        tma_bulk_g2s(buf ? s_stage1 : s_stage0, A.genes + row0 * A.W, bytes, &bars[buf]);
+    };
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_barrier_init();
+        int t0 = blockIdx.x, t1 = blockIdx.x + gridDim.x;
+        if (t0 < A.n_tiles) issue(t0, 0);
+        if (t1 < A.n_tiles) issue(t1, 1);
+    }
+    for (int w = tid; w < A.W; w += FISHER_THREADS) {
+        uint64_t m = A.tmask[w];
+        s_m[w] = m;
+        s_tm[w] = A.tvalue[w] & m;
+    }
+    if (LUT_SMEM) {
+        for (int k = tid; k <= A.lut_n; k += FISHER_THREADS) s_lut[k] = A.lut[k];
+    }
+    __syncthreads();
+    const double2 *lut = LUT_SMEM ? s_lut : A.lut;
+
+    // trait totals (every warp computes them redundantly: W is tiny)
+    int n_tp = 0, n_m = 0;
+    for (int w = lane; w < A.W; w += 32) {
+        n_tp += __popcll(s_tm[w]);
+        n_m += __popcll(s_m[w]);
+    }
+    n_tp = __reduce_add_sync(0xffffffffu, n_tp);
+    n_m = __reduce_add_sync(0xffffffffu, n_m);
+
+    const int W2 = A.W >> 1;
+    const ulonglong2 *tm2 = reinterpret_cast<const ulonglong2 *>(s_tm);
+    const ulonglong2 *m2 = reinterpret_cast<const ulonglong2 *>(s_m);
+
+    int it = 0;
+    for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t parity = (it >> 1) & 1;
+        mbar_wait(&bars[buf], parity);
+        const uint64_t *stage = buf ? s_stage1 : s_stage0;
+        const int64_t row0 = (int64_t)tile * A.rows_per_tile;
+        const int rows = (int)min((int64_t)A.rows_per_tile, A.G - row0);
+        for (int r = warp; r < rows; r += NW) {
+            const ulonglong2 *row2 = reinterpret_cast<const ulonglong2 *>(stage + (size_t)r * A.W);
+            int tp = 0, gp = 0;
+            uint64_t h0 = 0, h1 = 0;
+            for (int cidx = lane; cidx < W2; cidx += 32) {
+                const ulonglong2 g = row2[cidx];
+                const ulonglong2 t = tm2[cidx];
+                const ulonglong2 m = m2[cidx];
+                tp += __popcll(g.x & t.x) + __popcll(g.y & t.y);
+                gp += __popcll(g.x & m.x) + __popcll(g.y & m.y);
+                if (HASH) {
+                    const int w0 = 2 * cidx;
+                    if (w0 < A.Wn) {
+                        const uint64_t x = g.x & m.x;
+                        h0 += mix64(x + (uint64_t)(w0 + 1) * 0x9E3779B97F4A7C15ULL);
+                        h1 += mix64((x ^ 0xD6E8FEB86659FD93ULL) + (uint64_t)(w0 + 1) * 0xC2B2AE3D27D4EB4FULL);
+                    }
+                    if (w0 + 1 < A.Wn) {
+                        const uint64_t x = g.y & m.y;
+                        h0 += mix64(x + (uint64_t)(w0 + 2) * 0x9E3779B97F4A7C15ULL);
+                        h1 += mix64((x ^ 0xD6E8FEB86659FD93ULL) + (uint64_t)(w0 + 2) * 0xC2B2AE3D27D4EB4FULL);
+                    }
+                }
+            }
+            tp = __reduce_add_sync(0xffffffffu, tp);
+            gp = __reduce_add_sync(0xffffffffu, gp);
+            const int a = tp;              // tpgp
+            const int c = gp - tp;         // tngp
+            const int b = n_tp - tp;       // tpgn
+            const int d = n_m - n_tp - c;  // tngn
+            const int64_t g_idx = row0 + r;
+            if (HASH) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    h0 += __shfl_xor_sync(0xffffffffu, h0, o);
+                    h1 += __shfl_xor_sync(0xffffffffu, h1, o);
+                }
+                if (lane == 0 && A.hash) {
+                    A.hash[g_idx * 2 + 0] = h0;
+                    A.hash[g_idx * 2 + 1] = h1;
+                }
+            }
+            if (lane == 0 && A.counts)
+                reinterpret_cast<int4 *>(A.counts)[g_idx] = make_int4(a, c, b, d);   // tpgp,tngp,tpgn,tngn
+            if (A.p) {
+                const double pv = fisher_two_sided_warp(lut, a, b, c, d, lane);
+                if (lane == 0) A.p[g_idx] = pv;
+            }
+        }
+        __syncthreads();   // every warp is done with this stage buffer
+        if (tid == 0) {
+            const int nxt = tile + 2 * gridDim.x;
+            if (nxt < A.n_tiles) issue(nxt, buf);
+        }
+    }
+}
+
+}  // namespace sb

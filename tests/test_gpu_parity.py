@@ -1,0 +1,169 @@
+"""GPU parity tests proper: the CUDA path (through the C-ABI) against the CPU
+oracle on the same seeded inputs.  Integer results bit-exact; Fisher p within
+1e-10 relative of SciPy (the tolerance BASELINE.json's north_star states)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from scoary_b200 import engine as eng
+from scoary_b200 import synth
+from scoary_b200 import tree as treemod
+
+pytestmark = pytest.mark.gpu
+
+FISHER_RTOL = 1e-10      # north_star: "within 1e-10 relative for Fisher p-values"
+
+
+def _dataset(G, N, seed, missing=0.0, T=1):
+    traits = synth.make_traits(N, T, seed, missing_frac=missing)
+    bits = synth.make_genes_packed(G, N, seed, traits=traits)
+    return bits, traits
+
+
+def _tree_for(N, seed, trait_vec):
+    nested = synth.make_tree(N, seed)
+    names = synth.isolate_names(N)
+    drop = [names[j] for j in range(N) if trait_vec[j] < 0]
+    nested = treemod.prune(nested, drop)
+    col = {n: j for j, n in enumerate(names)}
+    return nested, col
+
+
+@pytest.mark.parametrize("G,N,missing", [(300, 100, 0.0), (257, 130, 0.05), (2000, 1000, 0.0), (500, 2111, 0.02),
+                                         (64, 5000, 0.0), (33, 64, 0.0), (5, 7, 0.0)])
+def test_contingency_fisher_hash(engine, G, N, missing):
+    bits, traits = _dataset(G, N, 1000 + G + N, missing)
+    engine.set_genes(bits, N)
+    engine.set_trait_vector(0, traits[0])
+    counts, p, h = engine.contingency_fisher(0, want_hash=True)
+    m = synth.unpack_rows(bits, N)
+    ref_counts = O.contingency(m, traits[0])
+    assert np.array_equal(counts, ref_counts)                      # bit-exact
+    assert np.array_equal(h, O.pattern_hash(m, traits[0]))         # bit-exact
+    ref_p = O.fisher_scipy(ref_counts)                             # the reference's own arithmetic (SciPy)
+    ok = ref_p > 1e-290
+    rel = np.abs(p - ref_p) / np.maximum(ref_p, 1e-300)
+    assert rel[ok].max() <= FISHER_RTOL, (rel[ok].max(), ref_counts[int(np.argmax(np.where(ok, rel, 0)))])
+    assert np.all(p[~ok] < 1e-280)
+    # the C oracle agrees too (and is what larger cases use)
+    rel2 = np.abs(p - O.fisher(ref_counts)) / np.maximum(ref_p, 1e-300)
+    assert rel2[ok].max() <= FISHER_RTOL
+
+
+def test_fisher_edge_tables(engine):
+    """all-0 / all-1 genes, genes equal to the trait or its complement, symmetric margins (exact ties)."""
+    N = 200
+    t = np.zeros(N, dtype=np.int8); t[:100] = 1
+    rows = [np.zeros(N), np.ones(N), t == 1, t == 0]
+    rng = np.random.default_rng(5)
+    for k in range(200):
+        r = np.zeros(N); r[rng.choice(N, 100, replace=False)] = 1   # row margin N/2 and col margin N/2 -> ties
+        rows.append(r)
+    m = np.asarray(rows, dtype=np.uint8)
+    engine.set_genes(eng.pack_rows(m), N)
+    engine.set_trait_vector(0, t)
+    counts, p, _ = engine.contingency_fisher(0)
+    ref_counts = O.contingency(m, t)
+    assert np.array_equal(counts, ref_counts)
+    ref_p = O.fisher_scipy(ref_counts)
+    assert p[0] == 1.0 and p[1] == 1.0
+    rel = np.abs(p - ref_p) / ref_p
+    assert rel.max() <= FISHER_RTOL
+
+
+@pytest.mark.parametrize("G,N,missing", [(300, 100, 0.0), (200, 257, 0.06), (150, 1000, 0.0), (40, 3000, 0.01), (7, 2, 0.0),
+                                         (9, 3, 0.0), (130, 33, 0.0)])
+def test_pairwise_bit_exact(engine, G, N, missing):
+    bits, traits = _dataset(G, N, 2000 + G + N, missing)
+    nested, col = _tree_for(N, 77 + N, traits[0])
+    engine.set_genes(bits, N)
+    engine.set_trait_vector(0, traits[0])
+    names = engine.set_tree_nested(0, nested, col)
+    pairs = engine.pairwise(0)
+    left, right, onames = O.flatten_tree(nested)
+    assert onames == names
+    m = synth.unpack_rows(bits, N)
+    cols = np.asarray([col[n] for n in names])
+    labels = traits[0][cols].astype(np.uint8)
+    ref = O.permute(left, right, m[:, cols], labels, P=0)["pairs"]
+    assert np.array_equal(pairs, ref)
+    # a subset through gene_idx, in scrambled order
+    idx = np.random.default_rng(1).permutation(G)[: max(1, G // 3)]
+    assert np.array_equal(engine.pairwise(0, idx), ref[idx])
+
+
+def test_caterpillar_and_balanced_trees(engine):
+    """extreme shapes: a comb (stack depth 0) and a perfectly balanced tree (max stack depth)."""
+    N = 256
+    names = synth.isolate_names(N)
+    comb = names[0]
+    for n in names[1:]:
+        comb = [comb, n]
+    level = list(names)
+    while len(level) > 1:
+        level = [[level[i], level[i + 1]] for i in range(0, len(level), 2)]
+    bal = level[0]
+    bits, traits = _dataset(200, N, 31337)
+    col = {n: j for j, n in enumerate(names)}
+    m = synth.unpack_rows(bits, N)
+    engine.set_genes(bits, N)
+    engine.set_trait_vector(0, traits[0])
+    for nested in (comb, bal):
+        nm = engine.set_tree_nested(0, nested, col)
+        left, right, _ = O.flatten_tree(nested)
+        cols = np.asarray([col[n] for n in nm])
+        ref = O.permute(left, right, m[:, cols], traits[0][cols].astype(np.uint8), P=0)["pairs"]
+        assert np.array_equal(engine.pairwise(0), ref)
+
+
+@pytest.mark.parametrize("N,P", [(100, 40), (257, 33), (1000, 64)])
+def test_shuffles_match_oracle_stream(engine, N, P):
+    bits, traits = _dataset(10, N, 99 + N)
+    nested, col = _tree_for(N, 5 + N, traits[0])
+    engine.set_genes(bits, N)
+    engine.set_trait_vector(0, traits[0])
+    names = engine.set_tree_nested(0, nested, col)
+    cols = np.asarray([col[n] for n in names])
+    labels = traits[0][cols].astype(np.uint8)
+    got = engine.shuffled_labels(0, P, seed=0xC0FFEE12345, n_leaves=len(names))
+    for i in range(P):
+        ref = O.shuffle_labels(0xC0FFEE12345, 0, i, labels)
+        assert np.array_equal(got[i], ref), i
+    assert np.all(got.sum(axis=1) == labels.sum())      # label counts preserved
+
+
+@pytest.mark.parametrize("G,N,P,missing", [(150, 100, 100, 0.0), (60, 300, 64, 0.04), (40, 1000, 37, 0.0)])
+def test_permute_bit_exact(engine, G, N, P, missing):
+    bits, traits = _dataset(G, N, 4000 + G + N, missing)
+    nested, col = _tree_for(N, 11 + N, traits[0])
+    engine.set_genes(bits, N)
+    engine.set_trait_vector(1, traits[0])            # a non-zero trait slot: the RNG counter carries it
+    names = engine.set_tree_nested(1, nested, col)
+    left, right, _ = O.flatten_tree(nested)
+    m = synth.unpack_rows(bits, N)
+    cols = np.asarray([col[n] for n in names])
+    labels = traits[0][cols].astype(np.uint8)
+    seed = 20260924
+    ref = O.permute(left, right, m[:, cols], labels, P=P, seed=seed, trait=1)
+    pairs, r, nd = engine.permute(1, P, seed=seed)
+    assert np.array_equal(pairs, ref["pairs"])
+    assert np.array_equal(r, ref["r"])
+    assert np.all(nd == P)
+    # the reference's sequential early-stop rule on the same hit sequence
+    ref_es = O.permute(left, right, m[:, cols], labels, P=P, seed=seed, trait=1, early_stop=True)
+    _, r2, nd2 = engine.permute(1, P, seed=seed, early_stop=True, rmin=O.rmin_table(P))
+    assert np.array_equal(r2, ref_es["r"])
+    assert np.array_equal(nd2, ref_es["n_done"])
+
+
+def test_errors_are_reported(engine):
+    from scoary_b200.engine import EngineError
+    bits, traits = _dataset(10, 64, 1)
+    engine.set_genes(bits, 64)
+    with pytest.raises(EngineError):
+        engine.contingency_fisher(5)                 # trait 5 never set
+    engine.set_trait_vector(0, traits[0])
+    with pytest.raises(EngineError):
+        engine.pairwise(7)                           # no tree for slot 7
+    with pytest.raises(EngineError):                 # not children-before-parents
+        engine.set_tree(0, [1, ~0], [~1, ~2], [0, 1, 2])
