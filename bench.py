@@ -1,0 +1,430 @@
+#!/usr/bin/env python
+"""bench.py -- gene-trait tests/sec (incl. permutations) of the hot path on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3] [--impl reference]
+
+A "step" is one pass of the whole hot path over one batch of synthetic input
+(SURVEY.md 8(d)): contingency + Fisher for every gene, the unpermuted
+pairwise-comparison walk and P label permutations for every gene
+(-p 1.0, exhaustive mode: no early stop), then -- for N > 1 -- one NCCL
+all-gather of the per-gene records.  tests = G_tested * T * (1 + P).
+
+  value : whole-job tests/s with inputs resident in HBM when the clock starts
+  e2e   : the same through the host-buffer C-ABI calls (pinned host bitsets in,
+          host result arrays out; H2D/D2H inside the timed region)
+  roofline / roofline_int32 : the dominant kernel (K5, permutation walks)
+  cpu_baseline : the oracle's C port on this box's host cores, bounded sample
+
+Default workload = BASELINE.json configs[2] ("c3": 50k genes x 5k isolates x 1
+trait, 1000 permutations + pairwise), the largest single-GPU configuration the
+metric "tests/sec incl. permutations" is quoted on; configs[1] (Fisher only,
+no permutations) is reported alongside as `fisher_pass`.  Under torchrun each
+rank owns its own 50k-gene shard (weak scaling).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+OPS_PER_NODE = 76          # int32 add/max operations per internal node, contract figure
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=["c2", "c3", "c4", "c5", "north_star"])
+    ap.add_argument("--genes", type=int, default=0, help="override genes per GPU")
+    ap.add_argument("--isolates", type=int, default=0)
+    ap.add_argument("--perms", type=int, default=-1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload(a):
+    from scoary_b200 import synth
+    G, N, T, P, seed = synth.CONFIGS[a.workload]
+    if a.workload in ("c4", "c5"):
+        G = G // 8                      # per-GPU shard of the 8-GPU configurations
+    if a.genes:
+        G = a.genes
+    if a.isolates:
+        N = a.isolates
+    if a.perms >= 0:
+        P = a.perms
+    return G, N, T, P, seed
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        load = [s for s in sm if s > 0.5 * max(sm)] or sm
+        return {"sm_mhz": float(np.median(load)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_sample(G, N, T, P, seed, budget_s):
+    """Time the oracle's C port (OpenMP, all host threads) on a bounded sample of the
+    same workload: the first `gs` genes x `ps` permutations (+ unpermuted walk + Fisher)."""
+    from oracle import oracle as O
+    from scoary_b200 import synth
+    threads = os.cpu_count() or O.num_threads()
+    O.set_num_threads(threads)           # torch's import would otherwise cap OpenMP at the physical cores
+    traits = synth.make_traits(N, 1, seed)
+    nested = synth.make_tree(N, seed)
+    left, right, names = O.flatten_tree(nested)
+    col = {n: j for j, n in enumerate(synth.isolate_names(N))}
+    cols = np.asarray([col[n] for n in names])
+    labels = traits[0][cols].astype(np.uint8)
+    # bounded sample: 16 genes per host thread x 32 permutations (a few seconds of wall time;
+    # dynamic scheduling over genes keeps every thread busy)
+    ps = min(P, 32) if P > 0 else 0
+    per_thread = max(1, int(round(16 * budget_s / 6.0)))
+    gs = min(G, per_thread * threads) if P > 0 else min(G, 2000)
+    bits = synth.make_genes_packed(gs, N, seed, traits=traits)
+    m = synth.unpack_rows(bits, N)
+
+    def run():
+        t0 = time.perf_counter()
+        counts = O.contingency(m, traits[0])
+        O.fisher(counts)
+        if P > 0:
+            O.permute(left, right, m[:, cols], labels, P=ps, seed=seed)
+        else:
+            pass
+        return time.perf_counter() - t0
+
+    tests = gs * T * (1 + ps)
+    return run, tests, threads, ("first %d genes x %d of %d permutations (+ unpermuted walk, contingency, Fisher), "
+                                 "%d isolates, exhaustive mode" % (gs, ps, P, N))
+
+
+def run_reference(a):
+    G, N, T, P, seed = workload(a)
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    budget = max(1.0, min(6.0, 100.0 / max(1, a.steps + a.warmup)))
+    run, tests, threads, sample = cpu_sample(G, N, T, P, seed, budget)
+    for _ in range(a.warmup):
+        run()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        run()
+    dt = time.perf_counter() - t0
+    value = tests * a.steps / dt
+    line = {
+        "impl": "reference", "metric": "gene-trait tests/sec (incl. permutations)", "value": value, "unit": "tests/s",
+        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
+        "config": {"workload": "%s: %d genes x %d isolates x %d trait(s), %d permutations + pairwise" %
+                               (a.workload, G, N, T, P)},
+        "cpu_baseline": {"value": value, "unit": "tests/s", "cores": threads, "kind": "port", "sample": sample,
+                         "note": "C restatement of scoary/methods.py + classes.py (oracle/scoary_oracle.c, OpenMP); "
+                                 "the Python reference itself measured 7 walks/s/core at N=5000 (BASELINE.md)"},
+        "e2e": {"value": value, "unit": "tests/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from scoary_b200 import synth
+    from scoary_b200.engine import Engine, words_for
+
+    G, N, T, P, seed = workload(a)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- synthetic inputs: every rank owns its own G-gene shard (weak scaling), same traits / tree
+    traits = synth.make_traits(N, T, seed)
+    bits_np = synth.make_genes_packed(G, N, seed + 1000003 * rank, traits=traits if rank == 0 else None)
+    W = words_for(N)
+    pinned = torch.empty((G, W), dtype=torch.int64, pin_memory=True)
+    pinned.numpy().view(np.uint64)[:] = bits_np
+    nested = synth.make_tree(N, seed)
+    names = synth.isolate_names(N)
+    col = {n: j for j, n in enumerate(names)}
+    from scoary_b200 import tree as treemod
+    left, right, leaf_names = treemod.flatten(nested)
+    leaf_cols = np.asarray([col[n] for n in leaf_names], dtype=np.int32)
+
+    e = Engine(local)
+    # a dedicated (non-default) torch stream: the library launches on it and torch.cuda.Event
+    # timing below sees the same stream (handle 0 would mean "the context's own stream")
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    e.set_stream(stream.cuda_stream)
+    int_peak = e.int32_peak(8192)
+
+    # ---- device-resident state for `value`
+    d_bits = pinned.to(dev, non_blocking=False)
+    e.set_genes_device(d_bits.data_ptr(), G, N, W)
+    for t in range(T):
+        e.set_trait_vector(t, traits[t])
+        e.set_tree(t, left, right, leaf_cols)
+    d_counts = torch.empty((T, G, 4), dtype=torch.int32, device=dev)
+    d_p = torch.empty((T, G), dtype=torch.float64, device=dev)
+    d_pairs = torch.empty((T, G, 3), dtype=torch.int32, device=dev)
+    d_r = torch.zeros((T, G), dtype=torch.int32, device=dev)
+    d_nd = torch.zeros((T, G), dtype=torch.int32, device=dev)
+    rec_w = 4 + 2 + 3 + 2
+    d_rec = torch.empty((T, G, rec_w), dtype=torch.int32, device=dev)
+    d_all = torch.empty((world * T, G, rec_w), dtype=torch.int32, device=dev) if world > 1 else None
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def step_device():
+        for t in range(T):
+            e.contingency_fisher_device(t, d_counts[t].data_ptr(), d_p[t].data_ptr())
+            if P > 0:
+                e.permute_device(t, G, P, seed, d_pairs[t].data_ptr(), d_r[t].data_ptr(), d_nd[t].data_ptr())
+        if world > 1:   # one all-gather of the fixed-size per-gene records
+            d_rec[..., 0:4] = d_counts
+            d_rec[..., 4:6] = d_p.view(torch.int32).view(T, G, 2)
+            d_rec[..., 6:9] = d_pairs
+            d_rec[..., 9] = d_r
+            d_rec[..., 10] = d_nd
+            dist.all_gather_into_tensor(d_all, d_rec)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(max(a.warmup, 3)):
+        step_device()
+    torch.cuda.synchronize()
+    counts_host = d_counts.cpu().numpy()
+    g_tested = int(((counts_host[..., 0] + counts_host[..., 1] > 0) &
+                    (counts_host[..., 2] + counts_host[..., 3] > 0)).sum())
+    tests_per_step_rank = g_tested * (1 + P)
+
+    e.stats_reset()
+    e.set_profiling(True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    barrier()
+    torch.cuda.synchronize()
+    wall0 = time.perf_counter()
+    for k in range(a.steps):
+        flush.zero_()                      # evict L2 between timed iterations (untimed)
+        evs[k][0].record()
+        step_device()
+        evs[k][1].record()
+    torch.cuda.synchronize()
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop() if rank == 0 else None
+    dev_ms = sum(s.elapsed_time(t) for s, t in evs)
+    st = e.stats()
+    e.set_profiling(False)
+    if world > 1:
+        tmax = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dev_ms = float(tmax.item())
+        tt = torch.tensor([tests_per_step_rank], dtype=torch.int64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+        tests_per_step = int(tt.item())
+    else:
+        tests_per_step = tests_per_step_rank
+    value = tests_per_step * a.steps / (dev_ms * 1e-3)
+
+    # ---- e2e: host buffers through the C-ABI, copies inside the timed region
+    counts_h = np.empty((G, 4), dtype=np.int32)
+    bits_host = pinned.numpy().view(np.uint64)
+
+    def step_e2e():
+        h2d = d2h = 0
+        e.set_genes(bits_host, N)
+        h2d += bits_host.nbytes
+        for t in range(T):
+            e.set_trait_vector(t, traits[t])
+            e.set_tree(t, left, right, leaf_cols)
+            h2d += 2 * W * 8 + left.nbytes + right.nbytes + leaf_cols.nbytes
+            c, p, _ = e.contingency_fisher(t)
+            d2h += c.nbytes + p.nbytes
+            if P > 0:
+                pairs, r, nd = e.permute(t, P, seed=seed)
+                d2h += pairs.nbytes + r.nbytes + nd.nbytes
+        return h2d, d2h
+
+    e.set_stream(0)
+    step_e2e()
+    barrier()
+    torch.cuda.synchronize()
+    e0 = time.perf_counter()
+    n_e2e = max(1, min(a.steps, 3))
+    for _ in range(n_e2e):
+        h2d_b, d2h_b = step_e2e()
+    e.synchronize()
+    e2e_s = time.perf_counter() - e0
+    if world > 1:
+        tmax = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        e2e_s = float(tmax.item())
+    e2e_value = tests_per_step * n_e2e / e2e_s
+
+    # ---- Fisher-only pass (BASELINE configs[1] shape of work), device resident
+    e.set_stream(stream.cuda_stream)
+    e.set_genes_device(d_bits.data_ptr(), G, N, W)
+    for t in range(T):
+        e.set_trait_vector(t, traits[t])
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e.contingency_fisher_device(0, d_counts[0].data_ptr(), d_p[0].data_ptr())
+    flush.zero_()
+    f0.record()
+    e.contingency_fisher_device(0, d_counts[0].data_ptr(), d_p[0].data_ptr())
+    f1.record()
+    torch.cuda.synchronize()
+    fisher_ms = f0.elapsed_time(f1)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (K5)
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            peaks = json.load(fh)
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    k5_launches = max(1, int(st["launches_permute"]))
+    k5_ms = st["ms_permute"] / k5_launches
+    n_leaves = N
+    alg_bytes = G * (8 * W + 8)                                  # one gene-row read + one result per gene
+    alg_ops = float(G) * P * (n_leaves - 1) * OPS_PER_NODE
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "k5_dram_bytes.json")
+    if os.path.exists(prof):
+        try:
+            traffic = json.load(open(prof)).get(a.workload)
+        except Exception:
+            traffic = None
+    roofline = {"kernel": "walk_kernel<true> (K5 permutation walks)", "bound": "hbm",
+                "achieved": alg_bytes / (k5_ms * 1e-3) / 1e9 if P > 0 else None, "peak": hbm_peak, "unit": "GB/s",
+                "frac": (alg_bytes / (k5_ms * 1e-3) / 1e9 / hbm_peak) if P > 0 else None, "traffic": traffic,
+                "peak_source": peak_src, "ms_per_launch": k5_ms,
+                "note": "K5 is integer-ALU bound by construction (0.65 B per test): see roofline_int32"}
+    roofline_int = {"kernel": "walk_kernel<true>", "bound": "int32 add/max issue (DPX VIADDMNMX)",
+                    "achieved": alg_ops / (k5_ms * 1e-3) / 1e12 if P > 0 else None, "peak": int_peak / 1e12,
+                    "unit": "Top/s", "frac": (alg_ops / (k5_ms * 1e-3) / int_peak) if P > 0 else None,
+                    "ops_per_node": OPS_PER_NODE,
+                    "peak_source": "sb_int32_peak microbenchmark, this run (VIADDMNMX = 1 add + 1 max)"}
+    fisher_bytes = G * (8 * W + 24)
+    fisher = {"kernel": "fisher_kernel (K2+K3)", "ms": fisher_ms, "tests_per_s": G / (fisher_ms * 1e-3),
+              "bound": "hbm", "achieved": fisher_bytes / (fisher_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+              "frac": fisher_bytes / (fisher_ms * 1e-3) / 1e9 / hbm_peak}
+
+    cpu = None
+    if not a.no_cpu_baseline:
+        run, tests, threads, sample = cpu_sample(G, N, T, P, seed, 6.0)
+        dt = run()
+        cpu = {"value": tests / dt, "unit": "tests/s", "cores": threads, "kind": "port", "sample": sample}
+
+    line = {
+        "metric": "gene-trait tests/sec (incl. permutations)", "value": value, "unit": "tests/s", "n_gpus": world,
+        "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": dev_ms / a.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int32 (walk DP) + f64 (Fisher)", "data": "synthetic",
+        "config": {"workload": "%s: %d genes/GPU x %d isolates x %d trait(s), %d permutations + pairwise, -p 1.0 "
+                               "exhaustive" % (a.workload, G, N, T, P),
+                   "parallelism": "gene-sharded x%d, one all-gather" % world if world > 1 else "single GPU",
+                   "l2": "256 MiB buffer written between timed steps (inputs ~65 MB < 126 MB L2)",
+                   "tests_per_step": tests_per_step, "seed": seed},
+        "e2e": {"value": e2e_value, "unit": "tests/s", "h2d_bytes_per_step": int(h2d_b), "d2h_bytes_per_step": int(d2h_b),
+                "ms_per_step": e2e_s / n_e2e * 1e3},
+        "gpu_launches": int(st["kernel_launches"]),
+        "clocks": clocks,
+        "roofline": roofline, "roofline_int32": roofline_int, "fisher_pass": fisher,
+        "cpu_baseline": cpu,
+        "kernel_ms": {k: st[k] for k in ("ms_fisher", "ms_shuffle", "ms_walk", "ms_permute", "ms_reduce")},
+        "wall_s_timed_region": wall,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,900 @@
+"""Host-side mirror of the reference's interface for the accelerated path.
+
+Same function names, argument meaning, return structures, error behaviour
+(sys.exit(message)) and output files as scoary/methods.py, so the call sites in
+`main` read the same:
+
+    Setup_results(genedic, traitsdic, collapse)            scoary/methods.py:757
+    StoreResults(...) / StoreTraitResult(...)              :987 / :1003
+    PairWiseComparisons((domain, argdict))                 :1208
+    ConvertUPGMAtoPhyloTree(tree, GTC)                     :1386
+    Permute(tree, GTC, permutations, cutoffs)              :1314
+
+but every per-gene number on the path -- 2x2 tables, Fisher p, pair counts,
+permutation hit counts -- comes from libscoary_b200.so on the GPU.  What stays
+on the host is what SURVEY.md 8(b) leaves there: CSV parsing and bit packing,
+collapse grouping, Bonferroni / Benjamini-Hochberg, the two binomial tests per
+reported gene (SciPy, as in the reference), sorting, filtering and CSV writing.
+There is no CPU fallback for the GPU part.
+"""
+import argparse
+import csv
+import logging
+import os
+import sys
+import time
+from collections.abc import Mapping
+
+import numpy as np
+
+from . import __version__
+from . import engine as eng
+from . import tree as treemod
+
+log = logging.getLogger("scoary_b200")
+log.setLevel(logging.DEBUG)
+
+MISSING = ("NA", "-", ".", " ", "")
+_ENGINE = None
+PERMUTATION_SEED = 0x5C0A27B200   # fixed default: runs are repeatable (the reference's are not)
+
+
+def get_engine():
+    """The process-wide engine (one GPU per process: LOCAL_RANK, else device 0)."""
+    global _ENGINE
+    if _ENGINE is None:
+        _ENGINE = eng.Engine(int(os.environ.get("LOCAL_RANK", "0")))
+    return _ENGINE
+
+
+# ============================================================================ inputs
+class GeneTable(Mapping):
+    """Gene presence/absence table: the packed form of the reference's `genedic`
+    (dict gene -> {isolate: 0/1, "Non-unique Gene name", "Annotation", "<col>_name"}).
+    Behaves like that dict for readers, but keeps the matrix as uint8 [G][N]."""
+
+    def __init__(self, names, nugn, annotation, strains, matrix, extra=None):
+        self.names = list(names)
+        self.nugn = list(nugn)
+        self.annotation = list(annotation)
+        self.strains = list(strains)
+        self.matrix = np.ascontiguousarray(matrix, dtype=np.uint8).reshape(len(self.names), len(self.strains))
+        self.extra = extra or {}
+        # the reference's dict keeps the LAST row of a duplicated identifier at the position of
+        # its FIRST occurrence (methods.py:450,462)
+        last, first = {}, {}
+        for i, n in enumerate(self.names):
+            last[n] = i
+            first.setdefault(n, i)
+        if len(last) != len(self.names):
+            order = sorted(last, key=lambda n: first[n])
+            rows = [last[n] for n in order]
+            self.names = order
+            self.nugn = [self.nugn[r] for r in rows]
+            self.annotation = [self.annotation[r] for r in rows]
+            self.matrix = np.ascontiguousarray(self.matrix[rows])
+            self.extra = {k: [v[r] for r in rows] for k, v in self.extra.items()}
+        self.index = {n: i for i, n in enumerate(self.names)}
+        self.col = {s: j for j, s in enumerate(self.strains)}
+
+    @classmethod
+    def from_dict(cls, genedic, strains=None):
+        """Reference-style dict of dicts -> GeneTable."""
+        if isinstance(genedic, GeneTable):
+            return genedic
+        names = list(genedic.keys())
+        if strains is None:
+            first = genedic[names[0]] if names else {}
+            strains = [k for k, v in first.items() if isinstance(v, (int, np.integer)) and not isinstance(v, bool)]
+        m = np.zeros((len(names), len(strains)), dtype=np.uint8)
+        for i, g in enumerate(names):
+            row = genedic[g]
+            m[i] = [row[s] for s in strains]
+        extra = {}
+        if names:
+            for k in genedic[names[0]]:
+                if isinstance(k, str) and k.endswith("_name"):
+                    extra[k] = [str(genedic[g].get(k, "")) for g in names]
+        return cls(names, [genedic[g].get("Non-unique Gene name", "") for g in names],
+                   [genedic[g].get("Annotation", "") for g in names], strains, m, extra)
+
+    def __len__(self):
+        return len(self.names)
+
+    def __iter__(self):
+        return iter(self.names)
+
+    def __getitem__(self, gene):
+        i = self.index[gene]
+        row = {"Non-unique Gene name": self.nugn[i], "Annotation": self.annotation[i]}
+        row.update(zip(self.strains, self.matrix[i].tolist()))
+        for k, v in self.extra.items():
+            row[k] = v[i]
+        return row
+
+
+ROARY_COLUMNS = ["Gene", "Non-unique Gene name", "Annotation", "No. isolates", "No. sequences",
+                 "Avg sequences per isolate", "Genome Fragment", "Order within Fragment", "Accessory Fragment",
+                 "Accessory Order with Fragment", "QC", "Min group size nuc", "Max group size nuc",
+                 "Avg group size nuc", "Order within fragment", "Genome fragment", "Accessory fragment"]
+
+
+def Csv_to_dic_Roary(genefile, delimiter, grabcols, startcol=14, allowed_isolates=None, writereducedset=False,
+                     time="", outdir="./"):
+    """Gene presence/absence CSV -> tables (scoary/methods.py:335-508).
+
+    Returns the reference's keys: "Roarydic" (a GeneTable), "Zero_ones_matrix"
+    (isolates x variable genes, here a uint8 array), "Strains", "Extracols",
+    "Firstcolnames".  A cell counts as present unless it is "", "0" or "-"."""
+    opened = None
+    if writereducedset:
+        opened = open(ReduceSet(genefile, delimiter, grabcols, startcol, allowed_isolates, time, outdir), "r")
+        genefile = opened
+    rdr = csv.reader(genefile, skipinitialspace=True, delimiter=delimiter)
+    header = next(rdr)
+    if grabcols == [-999]:
+        grabcols = list(range(3, len(header)))
+    if startcol >= len(header):
+        sys.exit("The startcol (-s) you have specified does not seem to correspond to any column in your gene "
+                 "presence/absence file.")
+    strains = header[startcol:]
+    extracolstoprint = [header[c] for c in grabcols]
+    roaryfile = header[0:3] == ROARY_COLUMNS[0:3]
+    if roaryfile and strains[0] in ROARY_COLUMNS:
+        guess = next((startcol + c for c in range(len(strains)) if strains[c] not in ROARY_COLUMNS), startcol)
+        log.error("ERROR: Make sure you have set the -s parameter correctly. You are running with -s %s. This "
+                  "correponds to the column %s. If this is not an isolate, Scoary might crash or produce strange "
+                  "results. Scoary thinks you should have run with -s %s instead" % (startcol + 1, strains[0], guess + 1))
+    if roaryfile:
+        before = header[:startcol][::-1]
+        censored = []
+        for name in before:
+            if name not in ROARY_COLUMNS:
+                censored.append(name)
+            else:
+                if censored:
+                    log.error("ERROR: Make sure you have set the -s parameter correctly. You are running with -s %s. "
+                              "Scoary thinks you should have used %s. This excludes the following, which Scoary "
+                              "thinks are isolates: %s" % (startcol + 1, startcol - len(censored) + 1, ", ".join(censored)))
+                break
+    keep_cols = [c for c, s in enumerate(strains) if allowed_isolates is None or s in allowed_isolates]
+    strain_names_allowed = [strains[c] for c in keep_cols]
+    if roaryfile:
+        try:
+            genecol, nugcol, anncol = (header.index("Gene"), header.index("Non-unique Gene name"),
+                                       header.index("Annotation"))
+        except ValueError:
+            log.error("ERROR: Could not properly detect the correct names for all columns in the ROARY table.")
+            genecol, nugcol, anncol = 0, 1, 2
+        firstcolnames = ["Gene", "Non-unique Gene name", "Annotation"]
+    else:
+        genecol, nugcol, anncol = 0, 1, 2
+        firstcolnames = header[0:3]
+    names, nugn, ann, rows = [], [], [], []
+    extra = {header[c] + "_name": [] for c in grabcols}
+    absent = ("", "0", "-")
+    src_cols = [startcol + c for c in keep_cols]
+    for q in rdr:
+        try:
+            ident = q[genecol] if roaryfile else q[genecol] + "_|_" + q[nugcol] + "_|_" + q[anncol]
+            nug, an = q[nugcol], q[anncol]
+            row = np.fromiter((q[c] not in absent for c in src_cols), dtype=np.uint8, count=len(src_cols))
+        except IndexError:
+            sys.exit("CRITICAL: Could not read gene presence absence file. Verify that this file is a proper Roary "
+                     "file using the specified delimiter (default is ',').")
+        names.append(ident)
+        nugn.append(nug)
+        ann.append(an)
+        rows.append(row)
+        for c in grabcols:
+            extra[header[c] + "_name"].append(q[c])
+    if opened:
+        opened.close()
+    matrix = np.vstack(rows) if rows else np.zeros((0, len(src_cols)), dtype=np.uint8)
+    table = GeneTable(names, nugn, ann, strain_names_allowed, matrix, extra)
+    s = matrix.sum(axis=1)                                            # every line counts, duplicates included (:496)
+    variable = (s > 0) & (s < matrix.shape[1])
+    zero_ones = np.ascontiguousarray(matrix[variable].T)              # isolates x variable genes
+    return {"Roarydic": table, "Zero_ones_matrix": zero_ones, "Strains": strain_names_allowed,
+            "Extracols": extracolstoprint, "Firstcolnames": firstcolnames}
+
+
+def ReduceSet(genefile, delimiter, grabcols, startcol=14, allowed_isolates=None, time="", outdir="./"):
+    """-w: write the gene table restricted to the allowed isolates (scoary/methods.py:510-544)."""
+    rdr = csv.reader(genefile, skipinitialspace=True, delimiter=delimiter)
+    header = next(rdr)
+    keep = list(range(startcol)) + [c for c in range(len(header)) if header[c] in allowed_isolates]
+    log.info("Writing gene presence absence file for the reduced set of isolates")
+    fname = "%sgene_presence_absence_reduced%s.csv" % (outdir, time)
+    with open(fname, "w") as out:
+        w = csv.writer(out, delimiter=delimiter)
+        w.writerow([header[a] for a in keep])
+        for r in rdr:
+            w.writerow(tuple(r[a] for a in keep))
+    log.info("Finished writing reduced gene presence absence list to file %s" % fname)
+    return fname
+
+
+def Csv_to_dic(csvfile, delimiter, allowed_isolates, strains):
+    """Traits CSV -> ({trait: {isolate: "0"/"1"}}, Prunedic) (scoary/methods.py:546-614).
+    Missing values are dropped per trait and listed in Prunedic[trait] (+ a trailing None)."""
+    tab = list(zip(*csv.reader(csvfile, delimiter=delimiter)))
+    if len(tab) < 2:
+        sys.exit("Please check that your traits file is formatted properly and contains at least one trait")
+    r, prunedic = {}, {}
+    for k in range(1, len(tab)):
+        p = dict(zip(tab[0], tab[k]))
+        if "" in p:
+            name = p.pop("")
+        elif "Name" in p:
+            name = p.pop("Name")
+        else:
+            sys.exit("Make sure the top-left cell in the traits file is either empty or 'Name'. Do not include "
+                     "empty rows")
+        if allowed_isolates is not None:
+            p = {s: v for s, v in p.items() if s in allowed_isolates}
+        allowed_values = ["0", "1", "NA", ".", "-", " ", ""]
+        if not all(v in allowed_values for v in p.values()):
+            sys.exit("Unrecognized character found in trait file. Allowed values (no commas): %s"
+                     % ",".join(allowed_values))
+        missing = [s for s, v in p.items() if v in MISSING]
+        if missing:
+            log.warning("WARNING: Some isolates have missing values for trait %s. Missing-value isolates will not "
+                        "be counted in association analysis towards this trait." % name)
+        prunedic[name] = list(missing)
+        if not all(s in p for s in strains):
+            log.error("ERROR: Some isolates in your gene presence absence file were not represented in your traits "
+                      "file. These will count as MISSING data and will not be included.")
+            prunedic[name] += [s for s in strains if s not in p and s not in prunedic[name]]
+        r[name] = {s: v for s, v in p.items() if v not in MISSING}
+        prunedic[name] += [None]
+    return r, prunedic
+
+
+# ============================================================================ tree building (host; off the hot path)
+def _morton_key(i, j, bits):
+    key = np.zeros(i.shape, dtype=np.int64)
+    for b in range(bits - 1, -1, -1):
+        key = (key << 2) | (((i >> b) & 1) << 1) | ((j >> b) & 1)
+    return key
+
+
+def upgma_from_matrix(zero_ones_matrix, strainnames):
+    """UPGMA on relative Hamming distances, reproducing the reference's pipeline
+    CreateTriangularDistanceMatrix -> PopulateQuadTreeWithDistances -> upgma
+    (scoary/methods.py:619-707, classes.QuadTree :97-196) including its argmin
+    tie-break: the QuadTree descends from the coarsest level choosing the smallest
+    (value, i, j) in each quad, i.e. the minimum cell with the smallest
+    bit-interleaved (i, j).  Distances: #differing variable genes / #variable genes;
+    the diagonal is 1; retired rows are sys.maxsize; the merged cluster keeps index i
+    and sees retired clusters at distance 1."""
+    m = np.asarray(zero_ones_matrix, dtype=np.float32)
+    n = m.shape[0]
+    if n < 2:
+        sys.exit("Need at least two isolates to build a tree")
+    ngenes = max(m.shape[1], 1)
+    diff = m @ (1.0 - m).T
+    diff = np.rint(diff + diff.T)
+    big = float(sys.maxsize)
+    d = diff.astype(np.float64) / float(ngenes)
+    np.fill_diagonal(d, 1.0)
+    levels, k = 0, n + (n % 2)
+    while k > 1:
+        k += k % 2
+        levels += 1
+        k = (k + 1) // 2
+    cluster = list(strainnames)
+    size = np.ones(n, dtype=np.float64)
+    alive = np.ones(n, dtype=bool)
+    new_cluster = None
+    for _ in range(n - 1):
+        dmin = d.min()
+        ii, jj = np.nonzero(d == dmin)
+        if len(ii) > 1:
+            k = int(np.argmin(_morton_key(ii, jj, levels)))
+            i, j = int(ii[k]), int(jj[k])
+        else:
+            i, j = int(ii[0]), int(jj[0])
+        new_cluster = [cluster[i], cluster[j]]
+        new_size = size[i] + size[j]
+        nd = (d[i] * size[i] + d[j] * size[j]) / new_size
+        nd[~alive] = 1.0
+        nd[i] = big
+        d[i, :] = nd
+        d[:, i] = nd
+        d[j, :] = big
+        d[:, j] = big
+        cluster[i] = new_cluster
+        cluster[j] = None
+        size[i] = new_size
+        size[j] = 0
+        alive[j] = False
+    return new_cluster
+
+
+def PruneForMissing(tree, Prunedic):
+    """scoary/methods.py:709-739"""
+    return treemod.prune(tree, Prunedic)
+
+
+def StoreUPGMAtreeToFile(upgmatree, outdir, time=""):
+    """scoary/methods.py:741-752"""
+    fname = str(outdir + ("Tree%s.nwk" % time))
+    with open(fname, "w") as fh:
+        fh.write(treemod.to_scoary_newick(upgmatree))
+    log.info("Wrote the UPGMA tree to file: %s" % fname)
+
+
+def ReadTreeFromFile(path):
+    """Custom tree (-n).  The reference uses ete3 (scoary/nwkhandler.py), which is
+    not installable here; binary Newick trees with optional branch lengths and
+    quoted or bare names are parsed directly."""
+    with open(path) as fh:
+        nested = treemod.from_scoary_newick(fh.read())
+    return nested, treemod.leaves(nested)
+
+
+# ============================================================================ per-gene statistics (A1-A3)
+class _TraitGTC(Mapping):
+    """GTC[trait]: gene -> {isolate: "AB"|"Ab"|"aB"|"ab"}, materialised on demand
+    (the reference builds all G x N strings up front, methods.py:939-965)."""
+
+    def __init__(self, table, isolates, labels, row_of):
+        self.table, self.isolates, self.labels, self.row_of = table, isolates, labels, row_of
+        self.cols = np.asarray([table.col[s] for s in isolates], dtype=np.int64)
+
+    def __len__(self):
+        return len(self.row_of)
+
+    def __iter__(self):
+        return iter(self.row_of)
+
+    def __getitem__(self, gene):
+        g = self.table.matrix[self.row_of[gene], self.cols]
+        return {s: ("A" if gi else "a") + ("B" if ti else "b") for s, gi, ti in zip(self.isolates, g, self.labels)}
+
+    def gene_bits(self, genes, isolates):
+        cols = np.asarray([self.table.col[s] for s in isolates], dtype=np.int64)
+        rows = np.asarray([self.row_of[g] for g in genes], dtype=np.int64)
+        return self.table.matrix[np.ix_(rows, cols)]
+
+    def trait_bits(self, isolates):
+        lab = dict(zip(self.isolates, self.labels))
+        return np.asarray([lab[s] for s in isolates], dtype=np.uint8)
+
+
+def _trait_vector(table, trait_values):
+    """{isolate: "0"/"1"} -> int8 [N] over the table's columns (-1 = not in the trait)."""
+    vec = np.full(len(table.strains), -1, dtype=np.int8)
+    for s, v in trait_values.items():
+        if s not in table.col:
+            log.critical("CRITICAL: Could not find %s in the genes file." % str(s))
+            sys.exit("Make sure strains are named the same in your traits file as in your gene presence/absence "
+                     "file")
+        if v in ("NA", "-", "."):
+            continue
+        try:
+            iv = int(v)
+        except ValueError:
+            iv = -9
+        if iv not in (0, 1):
+            sys.exit("There was a problem with comparing your traits and gene presence/absence files. Make sure you "
+                     "have formatted the traits file to specification and only use 1s and 0s, as well as NA, - or . "
+                     "for missing data. Also make sure the Roary file contains empty cells for non-present genes and "
+                     "non-empty text cells for present genes.")
+        vec[table.col[s]] = iv
+    return vec
+
+
+def benjamini_hochberg(p_sorted, number_of_tests):
+    """Step-up BH exactly as scoary/methods.py:903-919: the least significant entry keeps
+    its p; an entry tied with its less significant neighbour inherits that neighbour's value."""
+    p = np.asarray(p_sorted, dtype=np.float64)
+    n = len(p)
+    if n == 0:
+        return p
+    vals = (p * number_of_tests) / np.arange(1.0, n + 1.0)
+    vals[-1] = p[-1]
+    tie = np.zeros(n, dtype=bool)
+    tie[:-1] = p[:-1] == p[1:]
+    vals[tie] = np.inf
+    return np.minimum.accumulate(vals[::-1])[::-1]
+
+
+def Setup_results(genedic, traitsdic, collapse):
+    """Counting, Fisher's exact test and multiple-testing adjustment for every trait
+    (scoary/methods.py:757-928); the counting and Fisher part runs on the GPU
+    (sb_contingency_fisher).  Returns {"Results": ..., "Gene_trait_combinations": ...}."""
+    table = GeneTable.from_dict(genedic)
+    e = get_engine()
+    e.set_genes(eng.pack_rows(table.matrix), len(table.strains))
+    all_traits, gtc = {}, {}
+    for t_idx, trait in enumerate(traitsdic):
+        log.info("Gene-wise counting and Fisher's exact tests for trait: %s" % str(trait))
+        vec = _trait_vector(table, traitsdic[trait])
+        slot = t_idx % 64
+        e.set_trait_vector(slot, vec)
+        counts, pvals, hashes = e.contingency_fisher(slot, want_hash=bool(collapse))
+        tpgp, tngp, tpgn, tngn = (counts[:, k].astype(np.int64) for k in range(4))
+        keep = ((tpgp + tngp) > 0) & ((tpgn + tngn) > 0)          # methods.py:804-814
+        number_of_tests = int(keep.sum())
+        num_pos, num_neg = tpgp + tpgn, tngp + tngn
+        with np.errstate(divide="ignore", invalid="ignore"):
+            sens = np.where(num_pos > 0, tpgp.astype(np.float64) / np.maximum(num_pos, 1) * 100, 0.0)
+            spes = np.where(num_neg > 0, tngn.astype(np.float64) / np.maximum(num_neg, 1) * 100, 0.0)
+            odds = np.where((tngp > 0) & (tpgn > 0), (tpgp * tngn) / np.maximum(tngp * tpgn, 1).astype(np.float64),
+                            np.inf)
+        res = {}
+        row_of = {}
+        p_list_names, p_list_vals = [], []
+        owner = {}      # pattern hash -> current (possibly merged) name
+        idx = np.flatnonzero(keep)
+        names = table.names
+        for i in idx.tolist():
+            gene = names[i]
+            entry = {"NUGN": table.nugn[i], "Annotation": table.annotation[i],
+                     "tpgp": int(tpgp[i]), "tngp": int(tngp[i]), "tpgn": int(tpgn[i]), "tngn": int(tngn[i]),
+                     "sens": float(sens[i]), "spes": float(spes[i]), "OR": float(odds[i]), "p_v": float(pvals[i])}
+            if collapse:
+                key = (int(hashes[i, 0]), int(hashes[i, 1]))
+                prev = owner.get(key)
+                if prev is not None:                                   # methods.py:823-835, :874-892
+                    number_of_tests -= 1
+                    newname = prev + "--" + gene
+                    old = res.pop(prev)
+                    entry["NUGN"] = old["NUGN"] + "--" + entry["NUGN"]
+                    entry["Annotation"] = old["Annotation"] + "--" + entry["Annotation"]
+                    row_of.pop(prev)
+                    owner[key] = newname
+                    gene = newname
+                else:
+                    owner[key] = gene
+            res[gene] = entry
+            row_of[gene] = i
+            p_list_names.append(gene)
+            p_list_vals.append(entry["p_v"])
+        log.info("Adding p-values adjusted for testing multiple hypotheses")
+        pv = np.asarray(p_list_vals, dtype=np.float64)
+        order = np.argsort(pv, kind="stable")
+        bh = benjamini_hochberg(pv[order], number_of_tests)
+        bh_by_name = {}
+        for k, o in enumerate(order.tolist()):
+            bh_by_name[p_list_names[o]] = bh[k]
+        for gene, entry in res.items():
+            entry["B_p"] = min(entry["p_v"] * number_of_tests, 1.0)
+            entry["BH_p"] = min(float(bh_by_name[gene]), 1.0)
+        all_traits[trait] = res
+        isolates = list(traitsdic[trait].keys())
+        labels = np.asarray([1 if traitsdic[trait][s] == "1" else 0 for s in isolates], dtype=np.uint8)
+        gtc[trait] = _TraitGTC(table, isolates, labels, row_of)
+    return {"Results": all_traits, "Gene_trait_combinations": gtc}
+
+
+# ============================================================================ pairwise comparisons + permutations (A4-A10)
+_BINOM_CACHE = {}
+
+
+def _binom_two_sided(k, n):
+    """ss.binom_test(k, n, 0.5) (scoary/methods.py:1267-1275); host, memoised, SciPy as in the reference."""
+    key = (int(k), int(n))
+    v = _BINOM_CACHE.get(key)
+    if v is None:
+        from scipy import stats as ss
+        v = float(ss.binomtest(key[0], key[1], 0.5).pvalue) if key[1] > 0 else 1.0
+        _BINOM_CACHE[key] = v
+    return v
+
+
+_RMIN_CACHE = {}
+
+
+def early_stop_table(P):
+    """rmin[i] = least r for which the reference aborts after permutation i:
+    1 - ss.binom.cdf(r, i, 0.1) < 0.05 (scoary/methods.py:1360-1361)."""
+    t = _RMIN_CACHE.get(P)
+    if t is None:
+        from scipy import stats as ss
+        t = np.full(max(P, 1), np.iinfo(np.int32).max, dtype=np.int32)
+        for i in range(30, P):
+            r = np.arange(0, i + 2)
+            t[i] = int(np.argmax((1 - ss.binom.cdf(r, i, 0.1)) < 0.05))
+        _RMIN_CACHE[P] = t
+    return t
+
+
+def _gtc_arrays(GTC, genes, isolates):
+    """gene bits [S][n] and trait bits [n] for `isolates`, from either a lazy GTC or the
+    reference's dict-of-dicts of "AB"/"Ab"/"aB"/"ab" strings."""
+    if isinstance(GTC, _TraitGTC):
+        return GTC.gene_bits(genes, isolates), GTC.trait_bits(isolates)
+    g = np.zeros((len(genes), len(isolates)), dtype=np.uint8)
+    t = None
+    for a, gene in enumerate(genes):
+        row = GTC[gene]
+        try:
+            codes = [row[s] for s in isolates]
+        except KeyError as ex:
+            sys.exit("Isolate %s of the tree has no gene-trait combination" % ex)
+        g[a] = [c[0] == "A" for c in codes]
+        if t is None:
+            t = np.asarray([c[-1] == "B" for c in codes], dtype=np.uint8)
+    return g, t
+
+
+def _walk_setup(tree, GTC, genes):
+    """Load genes x tree-leaves into the engine (trait slot 0) and return the engine."""
+    left, right, names = treemod.flatten(tree)
+    g, t = _gtc_arrays(GTC, genes, names)
+    e = get_engine()
+    e.set_genes(eng.pack_rows(g), len(names))
+    e.set_trait_vector(0, t.astype(np.int8))
+    e.set_tree(0, left, right, np.arange(len(names), dtype=np.int32))
+    return e
+
+
+def ConvertUPGMAtoPhyloTree(tree, GTC):
+    """Max contrasting / supporting / opposing pairs for one gene (scoary/methods.py:1386-1402,
+    classes.PhyloTree); GTC = {isolate: "AB"|...}.  GPU walk (sb_pairwise)."""
+    e = _walk_setup(tree, {"_": GTC}, ["_"])
+    total, pro, anti = (int(x) for x in e.pairwise(0)[0])
+    return {"Total": total, "Pro": pro, "Anti": anti}
+
+
+def Permute(tree, GTC, permutations, cutoffs, seed=PERMUTATION_SEED):
+    """Empirical p by label switching for one gene (scoary/methods.py:1314-1369), with the
+    reference's sequential early stop; GPU (sb_permute)."""
+    if permutations < 10:
+        sys.stdout.write("Number of permutations too few. The absolute minimum is 10.")
+        return None
+    e = _walk_setup(tree, {"_": GTC}, ["_"])
+    _, r, nd = e.permute(0, int(permutations), seed=seed, early_stop=True, rmin=early_stop_table(int(permutations)))
+    return (int(r[0]) + 1.0) / (int(nd[0]) + 1.0)
+
+
+def PairWiseComparisons(nestedlist):
+    """(domain, {"si","tree","GTC","cutoffs","cp","perm","Trait","Threaded"}) -> {gene: {...}}
+    (scoary/methods.py:1208-1312).  All genes of the domain are walked in one launch;
+    the reference's "break at the first gene failing I/B/BH" is applied first, on the host,
+    because those cut-offs do not depend on the walk."""
+    domain, a = nestedlist[0], nestedlist[1]
+    si, tree, GTC, cutoffs, perm, Trait = a["si"], a["tree"], a["GTC"], a["cutoffs"], a["perm"], a["Trait"]
+    genes = []
+    for genenumber in domain:
+        g = si[genenumber]
+        if decideifbreak(cutoffs, Trait[g]):
+            break
+        genes.append(g)
+    out = {}
+    if not genes:
+        return out
+    e = _walk_setup(tree, GTC, genes)
+    if perm >= 10:
+        pairs, r, nd = e.permute(0, int(perm), seed=a.get("seed", PERMUTATION_SEED), early_stop=True,
+                                 rmin=early_stop_table(int(perm)))
+    else:
+        pairs = e.pairwise(0)
+    for k, g in enumerate(genes):
+        total, pro, anti = (int(x) for x in pairs[k])
+        best = _binom_two_sided(pro, total)
+        worst = _binom_two_sided(total - anti, total)
+        if pro < anti:                                   # names swap, methods.py:1259-1265
+            best, worst = worst, best
+        d = {"max_total_pairs": total, "max_propairs": pro, "max_antipairs": anti, "Pbest": best, "Pworst": worst,
+             "Plowest": min(best, worst), "Pboth": max(best, worst),
+             "p_v": Trait[g]["p_v"], "B_p": Trait[g]["B_p"], "BH_p": Trait[g]["BH_p"]}
+        if perm >= 10:
+            d["Empirical_p"] = (int(r[k]) + 1.0) / (int(nd[k]) + 1.0)
+        out[g] = d
+    return out
+
+
+def decideifbreak(cutoffs, currentgene):
+    """scoary/methods.py:1489-1508"""
+    for key, field in (("I", "p_v"), ("B", "B_p"), ("BH", "BH_p")):
+        if key in cutoffs and currentgene[field] > cutoffs[key]:
+            return True
+    return False
+
+
+def SortResultsAndSetKey(genedic, key="p_v"):
+    """rank -> gene, ascending by `key`, ties in dict order (scoary/methods.py:1448-1454)."""
+    return dict(enumerate(sorted(genedic, key=lambda g: genedic[g][key])))
+
+
+def SortResultsAndSetKeyPairwise(genedic, correctionmethod):
+    """scoary/methods.py:1456-1470"""
+    if "EPW" in correctionmethod:
+        return SortResultsAndSetKey(genedic, "Pboth")
+    if "PW" in correctionmethod:
+        return SortResultsAndSetKey(genedic, "Plowest")
+    sys.exit("Something went wrong when using this set of correction methods. Please report this bug")
+
+
+CUT_FIELDS = {"I": "p_v", "B": "B_p", "BH": "BH_p", "PW": "Plowest", "EPW": "Pboth", "P": "Empirical_p"}
+
+
+def StoreResults(Results, max_hits, cutoffs, upgmatree, GTC, Prunedic, outdir, permutations, num_threads,
+                 no_pairwise, genedic, extracolstoprint, firstcolnames, time="", delimiter=","):
+    """scoary/methods.py:987-1001"""
+    for Trait in Results:
+        sys.stdout.write("\n")
+        log.info("Storing results: " + Trait)
+        StoreTraitResult(Results[Trait], Trait, max_hits, cutoffs, upgmatree, GTC, Prunedic, outdir, permutations,
+                         num_threads, no_pairwise, genedic, extracolstoprint, firstcolnames, time, delimiter)
+
+
+def StoreTraitResult(Trait, Traitname, max_hits, cutoffs, upgmatree, GTC, Prunedic, outdir, permutations,
+                     num_threads, no_pairwise, genedic, extracolstoprint, firstcolnames, time="", delimiter=","):
+    """One <Trait>.results.csv (scoary/methods.py:1003-1197): same columns, quoting, ordering
+    and final `<=` filter.  --threads is accepted and ignored: the walk runs on the GPU."""
+    permutations = int(permutations)
+    fname = outdir + Traitname + time + ".results.csv"
+    with open(fname, "w") as outfile:
+        sort_instructions = SortResultsAndSetKey(Trait)
+        if max_hits is None:
+            max_hits = len(Trait)
+        num_results = min(max_hits, len(Trait))
+        columns = list(firstcolnames) + ["Number_pos_present_in", "Number_neg_present_in", "Number_pos_not_present_in",
+                                         "Number_neg_not_present_in", "Sensitivity", "Specificity", "Odds_ratio",
+                                         "Naive_p", "Bonferroni_p", "Benjamini_H_p"]
+        if not no_pairwise:
+            columns += ["Max_Pairwise_comparisons", "Max_supporting_pairs", "Max_opposing_pairs",
+                        "Best_pairwise_comp_p", "Worst_pairwise_comp_p"]
+        if permutations >= 10:
+            columns.append("Empirical_p")
+        columns += list(extracolstoprint)
+        outfile.write(delimiter.join('"' + c + '"' for c in columns) + "\n")
+        if permutations >= 10:
+            log.info("Calculating max number of contrasting pairs for each significant gene and performing %s "
+                     "permutations" % str(permutations))
+        elif no_pairwise:
+            log.info("Skipping population structure-aware analyses.")
+        else:
+            log.info("Calculating max number of contrasting pairs for each nominally significant gene")
+        if not no_pairwise:
+            if len(Prunedic[Traitname]) > 0:
+                upgmatree = PruneForMissing(upgmatree, Prunedic[Traitname])
+            args = {"si": sort_instructions, "tree": upgmatree, "GTC": GTC[Traitname], "cutoffs": cutoffs,
+                    "cp": CUT_FIELDS, "perm": permutations, "Trait": Trait, "Threaded": False}
+            walked = PairWiseComparisons((list(range(num_results)), args))
+            filtered = {}
+            for g, d in walked.items():
+                d.update(Trait[g])
+                filtered[g] = d
+            if ("I" in cutoffs) or ("B" in cutoffs) or ("BH" in cutoffs):
+                sort_instructions = SortResultsAndSetKey(filtered)
+            elif ("PW" in cutoffs) or ("EPW" in cutoffs):
+                sort_instructions = SortResultsAndSetKeyPairwise(filtered, cutoffs)
+            elif "P" in cutoffs:
+                sort_instructions = SortResultsAndSetKey(filtered, key="Empirical_p")
+            else:
+                log.info("No filtration applied")
+        else:
+            filtered = Trait
+            sort_instructions = SortResultsAndSetKey(filtered)
+        log.info("Storing results to file")
+        for x in range(min(num_results, len(filtered))):
+            gene = sort_instructions[x]
+            row = filtered[gene]
+            if not all(row[CUT_FIELDS[m]] <= cutoffs[m] for m in cutoffs):
+                continue
+            first = gene.split("_|_") if "_|_" in gene else [gene, str(row["NUGN"]), str(row["Annotation"])]
+            out = first + [str(row[k]) for k in ("tpgp", "tngp", "tpgn", "tngn", "sens", "spes", "OR", "p_v", "B_p",
+                                                  "BH_p")]
+            if not no_pairwise:
+                out += [str(row[k]) for k in ("max_total_pairs", "max_propairs", "max_antipairs", "Pbest", "Pworst")]
+                if permutations >= 10:
+                    out.append(str(row["Empirical_p"]))
+            for colname in extracolstoprint:
+                parts = gene.split("--") if "--" in gene else [gene]
+                out.append("--".join(str(genedic[g][colname + "_name"]) for g in parts))
+            outfile.write(delimiter.join('"' + c + '"' for c in out) + "\n")
+
+
+# ============================================================================ CLI
+def filtrationoptions(cutoffs, collapse):
+    """scoary/methods.py:1472-1487"""
+    names = {"I": "Individual (Naive)", "B": "Bonferroni", "BH": "Benjamini-Hochberg",
+             "PW": "Pairwise comparison (Best)", "EPW": "Pairwise comparison (Entire range)",
+             "P": "Empirical p-value (permutation-based)"}
+    lines = ["-- Filtration options --"] + [names[k] + ":    " + str(v) for k, v in cutoffs.items()]
+    lines.append("Collapse genes:    " + str(collapse) + "\n\n")
+    return lines
+
+
+def grabcoltype(string):
+    """'4,6,8,16-23' or ALL -> zero-based column list (scoary/methods.py:1510-1549)."""
+    if string == "ALL":
+        return [-999]
+    cols = []
+    try:
+        for part in string.replace(" ", "").split(","):
+            if not part:
+                continue
+            if "-" in part:
+                lo, hi = part.split("-")
+                cols += list(range(int(lo), int(hi) + 1))
+            else:
+                cols.append(int(part))
+    except ValueError:
+        raise argparse.ArgumentTypeError("Could not understand the column specification: %s" % string)
+    return sorted(set(c - 1 for c in cols))
+
+
+def ScoaryArgumentParser(argv=None):
+    """Same flags as scoary/methods.py:1551-1744."""
+    p = argparse.ArgumentParser(description="scoary_b200 %s - Scoary's pan-GWAS screen with the statistics, "
+                                            "pairwise comparisons and permutations on a B200" % __version__)
+    i = p.add_argument_group("Input options")
+    i.add_argument("-t", "--traits", help="trait table (CSV; isolates in rows, traits in columns, 1/0/NA)")
+    i.add_argument("-g", "--genes", help="gene presence/absence table (Roary CSV)")
+    i.add_argument("-n", "--newicktree", default=None, help="custom binary Newick tree instead of the internal UPGMA tree")
+    i.add_argument("-s", "--start_col", default=15, type=int, help="1-based column where isolates start (default 15)")
+    i.add_argument("--delimiter", default=",", type=str, help="cell delimiter of inputs and outputs")
+    i.add_argument("-r", "--restrict_to", help="file with a comma-separated subset of isolates to analyse")
+    o = p.add_argument_group("Output options")
+    o.add_argument("-o", "--outdir", default="./", help="output directory")
+    o.add_argument("-u", "--upgma_tree", default=False, action="store_true", help="write the UPGMA tree to Tree.nwk")
+    o.add_argument("-p", "--p_value_cutoff", nargs="+", default=[0.05], type=float,
+                   help="one cut-off for all correction methods, or one per method in order")
+    choices = ["I", "B", "BH", "PW", "EPW", "P"]
+    o.add_argument("-c", "--correction", choices=choices, nargs="*", default=["I"],
+                   help="filters: I naive, B Bonferroni, BH Benjamini-Hochberg, PW best pairwise, EPW entire pairwise "
+                        "range, P empirical (permutation)")
+    o.add_argument("-m", "--max_hits", type=int, help="report at most this many genes per trait")
+    o.add_argument("--include_input_columns", dest="grabcols", type=grabcoltype, default=[],
+                   help="copy input columns to the output, e.g. 4,6,8,16-23 or ALL")
+    o.add_argument("-w", "--write_reduced", default=False, action="store_true",
+                   help="with -r: also write the reduced gene table")
+    o.add_argument("--no-time", default=False, action="store_true", help="no timestamp in output file names")
+    a = p.add_argument_group("Analysis options")
+    a.add_argument("-e", "--permute", type=int, default=0, help="label-switching permutations per reported gene (>= 10)")
+    a.add_argument("--no_pairwise", default=False, action="store_true", help="population-structure-naive analysis only")
+    a.add_argument("--collapse", default=False, action="store_true", help="merge genes with identical patterns")
+    m = p.add_argument_group("Misc options")
+    m.add_argument("--threads", type=int, default=1, help="accepted for compatibility; the GPU does the work")
+    m.add_argument("--seed", type=int, default=PERMUTATION_SEED, help="seed of the permutation RNG (Philox)")
+    m.add_argument("--test", default=False, action="store_true", help="run on the reference's example data if present")
+    m.add_argument("--citation", default=False, action="store_true", help="show citation information and exit")
+    m.add_argument("--version", action="version", version=__version__)
+    args = p.parse_args(argv)
+    if len(args.p_value_cutoff) == 1:
+        cutoffs = {c: args.p_value_cutoff[0] for c in args.correction}
+    else:
+        cutoffs = dict(zip(args.correction, args.p_value_cutoff))
+    return args, cutoffs
+
+
+CITATION = ("Scoary: Brynildsrud O, Bohlin J, Scheffer L, Eldholm V. Rapid scoring of genes in microbial pan-genome-wide "
+            "association studies with Scoary. Genome Biol. 2016;17:238.  This is scoary_b200, a B200-native engine "
+            "for that method.")
+
+
+def main(**kwargs):
+    """`scoary -g genes.csv -t traits.csv` (scoary/methods.py:49-330) with the same files out."""
+    global PERMUTATION_SEED
+    if "args" in kwargs:
+        args, cutoffs = kwargs["args"], kwargs["cutoffs"]
+    else:
+        args, cutoffs = ScoaryArgumentParser(kwargs.get("argv"))
+    if args.citation:
+        sys.exit(CITATION)
+    if args.test:
+        ex = "/root/reference/scoary/exampledata"
+        args.correction, cutoffs = ["I", "EPW"], {"I": 0.05, "EPW": 0.05}
+        args.delimiter, args.grabcols, args.max_hits, args.newicktree = ",", [], None, None
+        args.genes, args.traits = os.path.join(ex, "Gene_presence_absence.csv"), os.path.join(ex, "Tetracycline_resistance.csv")
+        args.no_pairwise, args.outdir, args.permute, args.p_value_cutoff = False, "./", 0, [0.05, 0.05]
+        args.restrict_to, args.start_col, args.upgma_tree, args.write_reduced = None, 15, True, False
+        args.no_time, args.collapse = False, False
+    PERMUTATION_SEED = getattr(args, "seed", PERMUTATION_SEED)
+    starttime = time.time()
+    currenttime = "" if args.no_time else time.strftime("_%d_%m_%Y_%H%M")
+    if not args.outdir.endswith("/"):
+        args.outdir += "/"
+    os.makedirs(args.outdir, exist_ok=True)
+    console = logging.StreamHandler(sys.stdout)
+    console.setFormatter(logging.Formatter("%(message)s"))
+    console.setLevel(logging.INFO)
+    log.addHandler(console)
+    fileh = logging.FileHandler(os.path.join(args.outdir, "scoary%s.log" % currenttime), mode="w")
+    fileh.setFormatter(logging.Formatter(fmt="%(asctime)s    %(message)s", datefmt="%m/%d/%Y %I:%M:%S %p"))
+    log.addHandler(fileh)
+    log.info("==== Scoary started ====")
+    log.info("Command: " + " ".join(sys.argv))
+    try:
+        if args.traits is None or args.genes is None:
+            sys.exit("The following arguments are required: -t/--traits, -g/--genes")
+        if args.threads <= 0:
+            sys.exit("Number of threads must be positive")
+        if not os.path.isfile(args.traits):
+            sys.exit("Could not find the traits file: %s" % args.traits)
+        if not os.path.isfile(args.genes):
+            sys.exit("Could not find the gene presence absence file: %s" % args.genes)
+        if args.newicktree is not None and not os.path.isfile(args.newicktree):
+            sys.exit("Could not find the custom tree file: %s" % args.newicktree)
+        if not all(0.0 < p <= 1.0 for p in args.p_value_cutoff):
+            sys.exit("P must be between 0.0 and 1.0 or exactly 1.0")
+        if len(args.delimiter) > 1:
+            sys.exit("Delimiter must be a single character string. There is no support for tab.")
+        if len(args.p_value_cutoff) != len(args.correction) and len(args.p_value_cutoff) != 1:
+            sys.exit("You can not use more p-value cutoffs than correction methods. Either provide a single p-value "
+                     "that will be applied to all correction methods, or provide exactly as many as the number of "
+                     "correction methods and in corresponding sequence. e.g. -c I EPW -p 0.1 0.05 will apply an "
+                     "individual p-value cutoff of 0.1 AND a pairwise comparisons p-value cutoff of 0.05.")
+        if "P" in cutoffs and args.permute == 0:
+            sys.exit("Cannot use empirical p-values in filtration without performing permutations. Use "
+                     "'--permute X' where X is a number equal to or larger than 10")
+        if args.permute < 10 and args.permute != 0:
+            sys.exit("The absolute minimum number of permutations is 10 (or 0 to deactivate)")
+        if "P" in cutoffs and cutoffs["P"] < (1.0 / args.permute):
+            sys.exit("Permutation cutoff too low for this number of permutations")
+        if args.no_pairwise:
+            log.info("Performing no pairwise comparisons. Ignoring all tree related options (user tree, population "
+                     "aware-correction, permutations).")
+            args.permute, args.newicktree = 0, None
+            for m in ("PW", "EPW", "P"):
+                cutoffs.pop(m, None)
+        with open(args.genes, "r") as genes, open(args.traits, "r") as traits:
+            if args.restrict_to is not None:
+                allowed = {iso: "all" for line in open(args.restrict_to, "r") for iso in line.rstrip().split(",")}
+            else:
+                allowed = None
+                if args.write_reduced:
+                    sys.exit("You cannot use the -w argument without specifying a subset (-r)")
+            log.info("Reading gene presence absence file")
+            parsed = Csv_to_dic_Roary(genes, args.delimiter, [-999] if args.grabcols == "ALL" else args.grabcols,
+                                      startcol=int(args.start_col) - 1, allowed_isolates=allowed,
+                                      writereducedset=args.write_reduced, time=currenttime, outdir=args.outdir)
+            genedic, strains = parsed["Roarydic"], parsed["Strains"]
+            if args.newicktree is None and not args.no_pairwise:
+                log.info("Creating Hamming distance matrix based on gene presence/absence")
+                log.info("Building UPGMA tree from distance matrix")
+                upgmatree = upgma_from_matrix(parsed["Zero_ones_matrix"], strains)
+            elif args.no_pairwise:
+                log.info("Ignoring relatedness among input sample and performing only population structure-naive "
+                         "analysis.")
+                upgmatree = None
+            else:
+                log.info("Reading custom tree file")
+                upgmatree, members = ReadTreeFromFile(args.newicktree)
+                if sorted(strains) != sorted(members):
+                    if args.restrict_to is None:
+                        sys.exit("CRITICAL: Please make sure that isolates in your custom tree match those in your "
+                                 "gene presence absence file.")
+                    if all(s in members for s in strains):
+                        log.info("Pruning phylogenetic tree to correspond to set of included isolates")
+                        keep = set(strains)
+                        upgmatree = PruneForMissing(upgmatree, [m for m in members if m not in keep])
+                    else:
+                        sys.exit("CRITICAL: Your provided tree file did not contain all the isolates in your gene "
+                                 "presence absence file.")
+            log.info("Reading traits file")
+            traitsdic, Prunedic = Csv_to_dic(traits, args.delimiter, allowed, strains)
+        log.info("Finished loading files into memory.\n\n")
+        log.info("==== Performing statistics ====")
+        for line in filtrationoptions(cutoffs, args.collapse):
+            log.info(line)
+        log.info("Tallying genes and performing statistical analyses")
+        both = Setup_results(genedic, traitsdic, args.collapse)
+        if args.upgma_tree:
+            StoreUPGMAtreeToFile(upgmatree, args.outdir, time=currenttime)
+        StoreResults(both["Results"], args.max_hits, cutoffs, upgmatree, both["Gene_trait_combinations"], Prunedic,
+                     args.outdir, args.permute, args.threads, args.no_pairwise, genedic, parsed["Extracols"],
+                     parsed["Firstcolnames"], time=currenttime, delimiter=args.delimiter)
+        log.info("\n")
+        log.info("==== Finished ====")
+        log.info("Checked a total of %d genes for associations to %d trait(s). Total time used: %d seconds."
+                 % (len(genedic), len(traitsdic), int(time.time() - starttime)))
+    except SystemExit:
+        log.exception("CRITICAL:")
+        log.removeHandler(fileh)
+        log.removeHandler(console)
+        raise
+    log.removeHandler(fileh)
+    log.removeHandler(console)
+    sys.exit(0)
+
+
+if __name__ == "__main__":
+    main()

@@ -140,6 +140,7 @@ def from_scoary_newick(text):
             cur = stack.pop() if stack else None
             if cur is None:
                 root = done
+                break
             i += 1
         elif ch in "'\"":
             j = body.index(ch, i + 1)
@@ -155,7 +156,8 @@ def from_scoary_newick(text):
             if j < n and body[j] == ":":   # skip a branch length
                 while j < n and body[j] not in ",)":
                     j += 1
-            cur.append(name)
+            if name:            # an empty name is the branch length / label of a closed subtree
+                cur.append(name)
             i = j
     if root is None:
         raise ValueError("could not parse tree")

@@ -1,0 +1,139 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures in tests/golden/ by running the UNMODIFIED
+reference (/root/reference, imported through oracle/ref_shim.py) in the build
+container.  The reference cannot travel to the GPU box, so its outputs are
+committed here together with this script.
+
+    python tests/golden/make_golden.py
+
+Fixtures written:
+  inputs/                      the reference's example data (input DATA, gzipped)
+  <scenario>/<Trait>.results.csv[.gz]   full results of the reference CLI
+       default     .travis.yml:18  (-c I -p 0.05)
+       nopairwise  .travis.yml:20  (--no_pairwise)
+       restrict    .travis.yml:22  (-r Restrict_to.csv), all genes (-p 1.0)
+       advanced    .travis.yml:24  (-p 0.01 1E-5 -c B EPW --collapse -m 50 -u; tree built internally)
+       all         every gene, both traits (-p 1.0 -c I)  -> pins counts, p, B_p, BH_p, pairs, binomial p
+       collapse    every gene with --collapse (-p 1.0)
+       perm        -e 200 -c I EPW -p 0.05 0.05 with random.seed(1): Empirical_p (statistical pin only)
+  walks.json       random trees x gene-trait combinations -> reference ConvertUPGMAtoPhyloTree
+  fisher.json      2x2 tables -> scipy.stats.fisher_exact as the reference calls it (methods.py:854)
+  tetrcg_first_row.json   the reference's own CI golden (tests/test_scoary_output.py:12-14)
+"""
+import gzip
+import json
+import os
+import random
+import shutil
+import sys
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_shim  # noqa: E402
+
+EX = os.path.join(ref_shim.REFERENCE_ROOT, "scoary", "exampledata")
+G = os.path.join(EX, "Gene_presence_absence.csv")
+T = os.path.join(EX, "Tetracycline_resistance.csv")
+R = os.path.join(EX, "Restrict_to.csv")
+
+SCENARIOS = {
+    "default": (["-g", G, "-t", T], False),
+    "nopairwise": (["-g", G, "-t", T, "--no_pairwise"], False),
+    "restrict": (["-g", G, "-t", T, "-r", R, "-p", "1.0"], True),
+    "advanced": (["-g", G, "-t", T, "-p", "0.01", "1E-5", "-c", "B", "EPW", "--collapse", "-m", "50", "-u"], False),
+    "all": (["-g", G, "-t", T, "-p", "1.0", "-c", "I"], True),
+    "collapse": (["-g", G, "-t", T, "-p", "1.0", "-c", "I", "--collapse"], True),
+    "perm": (["-g", G, "-t", T, "-e", "200", "-c", "I", "EPW", "-p", "0.05", "0.05"], False),
+}
+
+
+def store(src, dst, gz):
+    os.makedirs(os.path.dirname(dst), exist_ok=True)
+    if gz:
+        with open(src, "rb") as fi, gzip.GzipFile(dst + ".gz", "wb", mtime=0) as fo:
+            shutil.copyfileobj(fi, fo)
+    else:
+        shutil.copyfile(src, dst)
+
+
+def main():
+    m = ref_shim.load()
+    # ---- input data (not code): needed by the GPU-box CLI parity tests
+    for f in ("Gene_presence_absence.csv", "Tetracycline_resistance.csv", "Restrict_to.csv", "ExampleTree.nwk"):
+        store(os.path.join(EX, f), os.path.join(HERE, "inputs", f), gz=f.startswith("Gene"))
+    # ---- CLI scenarios
+    for name, (argv, gz) in SCENARIOS.items():
+        out = tempfile.mkdtemp(prefix="golden_%s_" % name)
+        random.seed(1)
+        rc = ref_shim.run_cli(argv + ["-o", out, "--no-time"])
+        assert rc in (0, None), (name, rc)
+        for f in sorted(os.listdir(out)):
+            if f.endswith(".results.csv") or f.endswith(".nwk"):
+                store(os.path.join(out, f), os.path.join(HERE, name, f), gz and f.endswith(".csv"))
+        shutil.rmtree(out)
+        print("scenario", name, "done")
+    # ---- direct calls: PhyloTree walks
+    rng = random.Random(20260924)
+
+    def rand_tree(names):
+        nodes = list(names)
+        while len(nodes) > 1:
+            a = nodes.pop(rng.randrange(len(nodes)))
+            b = nodes.pop(rng.randrange(len(nodes)))
+            nodes.append([a, b])
+        return nodes[0]
+
+    def comb_tree(names):
+        t = names[0]
+        for n in names[1:]:
+            t = [t, n]
+        return t
+
+    walks = []
+    for it in range(400):
+        n = rng.choice([2, 3, 4, 5, 7, 8, 16, 33, 64, 100, 150])
+        names = ["i%d" % k for k in range(n)]
+        tree = comb_tree(names) if it % 10 == 0 else rand_tree(names)
+        pg, pt = rng.random(), rng.random()
+        gtc = {nm: ("A" if rng.random() < pg else "a") + ("B" if rng.random() < pt else "b") for nm in names}
+        ref = m.ConvertUPGMAtoPhyloTree(tree, gtc)
+        walks.append({"tree": tree, "gtc": gtc, "out": [ref["Total"], ref["Pro"], ref["Anti"]]})
+    with open(os.path.join(HERE, "walks.json"), "w") as fh:
+        json.dump(walks, fh, separators=(",", ":"))
+    # ---- Fisher tables as the reference calls SciPy
+    import numpy as np
+    from scipy import stats as ss
+    npr = np.random.default_rng(20260924)
+    tabs = []
+    for it in range(600):
+        N = int(npr.choice([7, 20, 100, 1000, 5000, 10000]))
+        r1, c1 = int(npr.integers(1, N)), int(npr.integers(1, N))
+        if it % 3 == 0:
+            r1 = N // 2
+        if it % 6 == 0:
+            c1 = N // 2
+        lo, hi = max(0, r1 + c1 - N), min(r1, c1)
+        a = int(npr.integers(lo, hi + 1))
+        if it % 2 == 0:
+            sd = max(r1 * c1 / N * (1 - r1 / N) * (1 - c1 / N), 1.0) ** 0.5
+            a = int(np.clip(round(r1 * c1 / N + npr.normal() * 3 * sd), lo, hi))
+        tpgp, tpgn, tngp, tngn = a, r1 - a, c1 - a, N - r1 - c1 + a
+        odds, p = ss.fisher_exact([[tpgp, tpgn], [tngp, tngn]])
+        tabs.append({"tpgp": tpgp, "tngp": tngp, "tpgn": tpgn, "tngn": tngn, "p": float(p).hex(),
+                     "odds": None if not np.isfinite(odds) else float(odds).hex()})
+    with open(os.path.join(HERE, "fisher.json"), "w") as fh:
+        json.dump({"scipy": __import__("scipy").__version__, "tables": tabs}, fh, separators=(",", ":"))
+    # ---- the reference's own CI golden row
+    with open(os.path.join(HERE, "tetrcg_first_row.json"), "w") as fh:
+        json.dump({"source": "tests/test_scoary_output.py:12-14",
+                   "row": ["TetRCG", "", "A fictitious gene known to cause resistance against tetracycline", 29, 8, 3,
+                           60, 90.625, 88.2352941176, 72.5, 1.08621066108E-014, 6.45209132679E-011,
+                           6.45209132679E-011, 25, 25, 1, 5.96046447754E-008, 1.54972076416E-006]}, fh)
+    print("golden fixtures written to", HERE)
+
+
+if __name__ == "__main__":
+    main()

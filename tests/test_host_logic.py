@@ -1,0 +1,163 @@
+"""Host logic of the reference-interface mirror (parsing, UPGMA, collapse, Bonferroni/BH,
+sorting, filtering, CSV text) checked against the reference's golden result files, with the
+GPU part replaced by the oracle-backed FakeEngine (tests/fake_engine.py).  No GPU needed."""
+import gzip
+import os
+import shutil
+
+import numpy as np
+import pytest
+
+from scoary_b200 import methods as M
+from scoary_b200 import tree as treemod
+from fake_engine import FakeEngine
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture()
+def inputs(tmp_path):
+    g = tmp_path / "Gene_presence_absence.csv"
+    with gzip.open(os.path.join(GOLD, "inputs", "Gene_presence_absence.csv.gz"), "rb") as fi, open(g, "wb") as fo:
+        shutil.copyfileobj(fi, fo)
+    return {"g": str(g), "t": os.path.join(GOLD, "inputs", "Tetracycline_resistance.csv"),
+            "r": os.path.join(GOLD, "inputs", "Restrict_to.csv"), "n": os.path.join(GOLD, "inputs", "ExampleTree.nwk"),
+            "out": str(tmp_path / "out")}
+
+
+@pytest.fixture()
+def fake_engine(monkeypatch):
+    fe = FakeEngine()
+    monkeypatch.setattr(M, "_ENGINE", fe)
+    return fe
+
+
+def _read(path):
+    op = gzip.open if path.endswith(".gz") else open
+    with op(path, "rt") as fh:
+        return fh.read()
+
+
+def _run(argv):
+    with pytest.raises(SystemExit) as ex:
+        M.main(argv=argv)
+    assert ex.value.code == 0
+
+
+SCENARIOS = {
+    "default": [],
+    "nopairwise": ["--no_pairwise"],
+    "advanced": ["-p", "0.01", "1E-5", "-c", "B", "EPW", "--collapse", "-m", "50", "-u"],
+    "all": ["-p", "1.0", "-c", "I"],
+    "collapse": ["-p", "1.0", "-c", "I", "--collapse"],
+}
+
+
+@pytest.mark.parametrize("name", list(SCENARIOS))
+def test_cli_text_identical_to_reference(name, inputs, fake_engine):
+    """Whole result files, byte for byte (header, quoting, row order, float text)."""
+    _run(["-g", inputs["g"], "-t", inputs["t"], "-o", inputs["out"], "--no-time"] + SCENARIOS[name])
+    for trait in ("Tetracycline_resistance", "Bogus_trait"):
+        gold = os.path.join(GOLD, name, trait + ".results.csv")
+        gold = gold if os.path.exists(gold) else gold + ".gz"
+        assert _read(os.path.join(inputs["out"], trait + ".results.csv")) == _read(gold), (name, trait)
+    if name == "advanced":
+        assert _read(os.path.join(inputs["out"], "Tree.nwk")) == _read(os.path.join(GOLD, "advanced", "Tree.nwk"))
+
+
+def test_cli_restrict_and_custom_tree(inputs, fake_engine):
+    _run(["-g", inputs["g"], "-t", inputs["t"], "-o", inputs["out"], "--no-time", "-r", inputs["r"], "-p", "1.0"])
+    for trait in ("Tetracycline_resistance", "Bogus_trait"):
+        assert _read(os.path.join(inputs["out"], trait + ".results.csv")) == \
+            _read(os.path.join(GOLD, "restrict", trait + ".results.csv.gz"))
+    # -n with the reference's own tree file gives the same result as the internal UPGMA tree
+    out2 = inputs["out"] + "2"
+    _run(["-g", inputs["g"], "-t", inputs["t"], "-o", out2, "--no-time", "-n", inputs["n"]])
+    assert _read(os.path.join(out2, "Tetracycline_resistance.results.csv")) == \
+        _read(os.path.join(GOLD, "default", "Tetracycline_resistance.results.csv"))
+
+
+def test_first_row_is_the_reference_ci_golden(inputs, fake_engine):
+    """tests/test_scoary_output.py:12-14 of the reference, same tolerances."""
+    import csv
+    import json
+    ref = json.load(open(os.path.join(GOLD, "tetrcg_first_row.json")))["row"]
+    _run(["-g", inputs["g"], "-t", inputs["t"], "-o", inputs["out"], "--no-time"])
+    with open(os.path.join(inputs["out"], "Tetracycline_resistance.results.csv")) as fh:
+        rows = list(csv.reader(fh))
+    d = rows[1]
+    assert d[0:3] == ref[0:3]
+    assert [int(x) for x in d[3:7]] == ref[3:7]
+    assert abs(float(d[7]) - ref[7]) <= 0.01 and abs(float(d[8]) - ref[8]) <= 0.01 and abs(float(d[9]) - ref[9]) <= 0.1
+    assert abs(float(d[10]) - ref[10]) <= 1e-15 and abs(float(d[11]) - ref[11]) <= 1e-12
+    assert abs(float(d[12]) - ref[12]) <= 1e-12
+    assert [int(x) for x in d[13:16]] == ref[13:16]
+    assert abs(float(d[16]) - ref[16]) <= 1e-9 and abs(float(d[17]) - ref[17]) <= 1e-7
+
+
+def test_upgma_reproduces_example_tree(inputs):
+    with open(inputs["g"]) as fh:
+        parsed = M.Csv_to_dic_Roary(fh, ",", [], startcol=14)
+    tree = M.upgma_from_matrix(parsed["Zero_ones_matrix"], parsed["Strains"])
+    assert treemod.to_scoary_newick(tree) == open(inputs["n"]).read().strip()
+
+
+def test_bh_tie_rule():
+    """methods.py:903-919: ties inherit from the less significant neighbour; last keeps its p."""
+    p = np.array([0.001, 0.01, 0.01, 0.02, 0.5])
+    m = 5
+    bh = M.benjamini_hochberg(p, m)
+    last = p[-1]
+    want = [None] * 5
+    want[4] = last
+    want[3] = min(want[4], p[3] * m / 4.0)
+    want[2] = min(want[3], p[2] * m / 3.0)
+    want[1] = want[2]                         # tied with index 2
+    want[0] = min(want[1], p[0] * m / 1.0)
+    assert np.array_equal(bh, np.array(want))
+
+
+def test_tree_utils_roundtrip_and_prune():
+    t = [[["a", "b"], "c"], [["d", ["e", "f"]], "g"]]
+    left, right, names = treemod.flatten(t)
+    assert names == list("abcdefg") and len(left) == 6
+    assert treemod.from_scoary_newick(treemod.to_scoary_newick(t)) == t
+    assert treemod.prune(t, ["a", "b", None]) == ["c", [["d", ["e", "f"]], "g"]]
+    assert treemod.prune(t, ["c"]) == [["a", "b"], [["d", ["e", "f"]], "g"]]
+    assert treemod.prune(["a", "b"], ["a", "b"]) is None
+    assert treemod.from_scoary_newick("((A:0.1,B:0.2):0.3,C:1);") == [["A", "B"], "C"]
+    with pytest.raises(ValueError):
+        treemod.from_scoary_newick("(A,B,C);")
+
+
+def test_errors_exit_like_the_reference(inputs, fake_engine):
+    for argv, msg in [(["-g", inputs["g"]], "required"),
+                      (["-g", inputs["g"], "-t", inputs["t"], "-e", "5"], "minimum number of permutations"),
+                      (["-g", inputs["g"], "-t", inputs["t"], "-c", "P"], "without performing permutations"),
+                      (["-g", inputs["g"], "-t", "/nonexistent.csv"], "Could not find the traits file"),
+                      (["-g", inputs["g"], "-t", inputs["t"], "-p", "1.5"], "P must be between")]:
+        with pytest.raises(SystemExit) as ex:
+            M.main(argv=argv + ["-o", inputs["out"], "--no-time"])
+        assert msg in str(ex.value.code)
+
+
+def test_reference_style_dict_inputs(fake_engine):
+    """Setup_results / ConvertUPGMAtoPhyloTree / Permute accept the reference's plain dicts."""
+    strains = ["s%d" % i for i in range(12)]
+    rng = np.random.default_rng(3)
+    genedic = {}
+    for g in range(6):
+        row = {"Non-unique Gene name": "", "Annotation": "x"}
+        row.update({s: int(rng.random() < 0.5) for s in strains})
+        genedic["gene%d" % g] = row
+    traitsdic = {"T": {s: str(int(rng.random() < 0.5)) for s in strains}}
+    out = M.Setup_results(genedic, traitsdic, False)
+    res = out["Results"]["T"]
+    assert set(res) <= set(genedic) and all(k in next(iter(res.values())) for k in ("p_v", "B_p", "BH_p", "OR"))
+    gtc = out["Gene_trait_combinations"]["T"][next(iter(res))]
+    assert set(gtc.values()) <= {"AB", "Ab", "aB", "ab"} and list(gtc) == strains
+    tree = [[["s0", "s1"], ["s2", "s3"]], [[["s4", "s5"], ["s6", "s7"]], [["s8", "s9"], ["s10", "s11"]]]]
+    w = M.ConvertUPGMAtoPhyloTree(tree, gtc)
+    assert set(w) == {"Total", "Pro", "Anti"} and w["Total"] >= max(w["Pro"], w["Anti"])
+    emp = M.Permute(tree, gtc, 50, {"I": 0.05})
+    assert 0.0 < emp <= 1.0
