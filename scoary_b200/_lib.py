@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libscoary_b200.so")
+LIB_PATH = os.environ.get("SCOARY_B200_LIB") or os.path.join(_HERE, "libscoary_b200.so")   # override: kernel experiments
 
 c_i32p = ctypes.POINTER(ctypes.c_int32)
 c_i64p = ctypes.POINTER(ctypes.c_int64)

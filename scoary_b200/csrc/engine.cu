@@ -45,7 +45,7 @@ struct TraitSlot {
     bool finalized = false;        // labels + genesT built for the current genes/trait/tree
     int32_t n_leaves = 0, n_internal = 0, W32 = 0, W32p = 0, depth = 0, shift = 0, n_ops = 0;
     std::vector<int32_t> h_leaf_to_col, h_leaf_of_pos;
-    uint16_t *d_ops = nullptr;
+    std::vector<uint16_t> h_ops;
     int32_t *d_walk_col = nullptr, *d_leaf_of_pos = nullptr;
     uint32_t *d_labels_leaf = nullptr;   // [W32]  by leaf id
     uint32_t *d_labels0 = nullptr;       // [W32p] walk order, unpermuted
@@ -160,7 +160,7 @@ void resolve_events(sb_ctx *ctx)
 
 void free_tree(TraitSlot &s)
 {
-    cudaFree(s.d_ops); s.d_ops = nullptr;
+    s.h_ops.clear();
     cudaFree(s.d_walk_col); s.d_walk_col = nullptr;
     cudaFree(s.d_leaf_of_pos); s.d_leaf_of_pos = nullptr;
     cudaFree(s.d_labels_leaf); s.d_labels_leaf = nullptr;
@@ -189,8 +189,14 @@ struct Program {
 bool compile_tree(const int32_t *left, const int32_t *right, int32_t n_internal, Program &out, std::string &err)
 {
     const int32_t n_leaves = n_internal + 1;
-    std::vector<int32_t> need(n_internal, 0);
+    // size[v]  leaves below v;  small[v]  size <= WALK_LIM16 (v is evaluated with packed 16-bit keys)
+    // cat[v]   v is a "caterpillar" (a cherry plus single leaves): needs one accumulator only
+    // need[v]  shared-memory stack units (10 words per gene pair; a 32-bit entry takes 2) used
+    //          while v is evaluated into accumulator A
+    std::vector<int32_t> need(n_internal, 0), size(n_internal, 0);
+    std::vector<uint8_t> cat(n_internal, 0), first_left(n_internal, 1), second_in_b(n_internal, 0);
     std::vector<uint8_t> seen_leaf(n_leaves, 0), seen_node(n_internal, 0);
+    auto small = [&](int32_t v) { return size[v] <= sb::WALK_LIM16; };
     for (int32_t v = 0; v < n_internal; ++v) {
         const int32_t ch[2] = {left[v], right[v]};
         for (int k = 0; k < 2; ++k) {
@@ -206,94 +212,117 @@ bool compile_tree(const int32_t *left, const int32_t *right, int32_t n_internal,
             }
         }
         const bool li = left[v] >= 0, ri = right[v] >= 0;
+        size[v] = (li ? size[left[v]] : 1) + (ri ? size[right[v]] : 1);
         if (li && ri) {
-            const int a = need[left[v]], b = need[right[v]];
-            need[v] = (a == b) ? a + 1 : std::max(a, b);
-        } else if (li) need[v] = need[left[v]];
-        else if (ri) need[v] = need[right[v]];
-        else need[v] = 0;
+            const int32_t a = left[v], b = right[v];
+            auto cost = [&](int32_t f, int32_t s2, bool &in_b) {
+                in_b = cat[s2] && small(s2);
+                return in_b ? need[f] : std::max(need[f], (small(f) ? 1 : 2) + need[s2]);
+            };
+            bool b_ab, b_ba;
+            const int cost_ab = cost(a, b, b_ab), cost_ba = cost(b, a, b_ba);
+            // cheaper stack first; on a tie prefer the order whose second child fits accumulator B
+            const bool a_first = (cost_ab < cost_ba) || (cost_ab == cost_ba && (b_ab || !b_ba));
+            first_left[v] = a_first;
+            second_in_b[v] = a_first ? b_ab : b_ba;
+            need[v] = a_first ? cost_ab : cost_ba;
+        } else if (li) { need[v] = need[left[v]]; cat[v] = cat[left[v]]; }
+        else if (ri) { need[v] = need[right[v]]; cat[v] = cat[right[v]]; }
+        else { need[v] = 0; cat[v] = 1; }
     }
     for (int32_t v = 0; v + 1 < n_internal; ++v)
         if (!seen_node[v]) { err = "tree is not connected (root must be the last node)"; return false; }
     for (int32_t k = 0; k < n_leaves; ++k)
         if (!seen_leaf[k]) { err = "leaf missing from tree"; return false; }
 
-    // raw op list: 0 cherry, 1 leaf, 2 merge
+    // emit one raw op per step (run-length encoded afterwards)
     std::vector<uint8_t> raw;
-    raw.reserve(n_internal);
+    raw.reserve((size_t)n_internal * 2);
     out.leaf_of_pos.clear();
     out.leaf_of_pos.reserve(n_leaves);
-    struct Frame { int32_t node; int32_t phase; };
+    struct Frame { int32_t node; int32_t phase; uint8_t into_b; };
     std::vector<Frame> st;
-    st.push_back({n_internal - 1, 0});
+    st.push_back({n_internal - 1, 0, 0});
     while (!st.empty()) {
         Frame &f = st.back();
         const int32_t v = f.node;
         const bool li = left[v] >= 0, ri = right[v] >= 0;
+        const uint8_t into_b = f.into_b;
         if (!li && !ri) {
             out.leaf_of_pos.push_back(~left[v]);
             out.leaf_of_pos.push_back(~right[v]);
-            raw.push_back(0);
+            raw.push_back(into_b ? sb::OP_CHERRY_B16 : sb::OP_CHERRY_A16);
             st.pop_back();
         } else if (li != ri) {
             const int32_t inner = li ? left[v] : right[v];
             const int32_t leaf = li ? ~right[v] : ~left[v];
             if (f.phase == 0) {
                 f.phase = 1;
-                st.push_back({inner, 0});
+                st.push_back({inner, 0, into_b});
             } else {
                 out.leaf_of_pos.push_back(leaf);
-                raw.push_back(1);
+                if (small(v)) {
+                    raw.push_back(into_b ? sb::OP_LEAF_B16 : sb::OP_LEAF_A16);
+                } else {
+                    if (small(inner)) raw.push_back(sb::OP_WIDEN_A);
+                    raw.push_back(sb::OP_LEAF_A32);
+                }
                 st.pop_back();
             }
         } else {
-            const bool left_first = need[left[v]] >= need[right[v]];
-            const int32_t first = left_first ? left[v] : right[v];
-            const int32_t second = left_first ? right[v] : left[v];
+            const int32_t first = first_left[v] ? left[v] : right[v];
+            const int32_t second = first_left[v] ? right[v] : left[v];
+            const bool in_b = second_in_b[v] != 0;
             if (f.phase == 0) {
                 f.phase = 1;
-                st.push_back({first, 0});
+                st.push_back({first, 0, 0});
             } else if (f.phase == 1) {
                 f.phase = 2;
-                st.push_back({second, 0});
+                if (!in_b) raw.push_back(small(first) ? sb::OP_PUSH16 : sb::OP_PUSH32);
+                st.push_back({second, 0, (uint8_t)(in_b ? 1 : 0)});
             } else {
-                raw.push_back(2);
+                if (in_b) {
+                    if (small(v)) raw.push_back(sb::OP_MERGE_AB16);
+                    else {
+                        if (small(first)) raw.push_back(sb::OP_WIDEN_A);
+                        raw.push_back(sb::OP_MERGE_A32_B16);
+                    }
+                } else if (small(v)) {
+                    raw.push_back(sb::OP_MERGE_POP16);
+                } else {
+                    if (small(second)) raw.push_back(sb::OP_WIDEN_A);
+                    raw.push_back(small(first) ? sb::OP_MERGE_POPW : sb::OP_MERGE_POP32);
+                }
                 st.pop_back();
             }
         }
     }
-    // run-length encode; every cherry after the first pushes the pending accumulator
+    if (small(n_internal - 1)) raw.push_back(sb::OP_WIDEN_A);   // the program always ends in 32-bit mode
     out.ops.clear();
     int depth = 0, sp = 0;
-    bool first_cherry = true;
     size_t i = 0;
     while (i < raw.size()) {
-        if (raw[i] == 0) {
-            if (first_cherry) {
-                out.ops.push_back((uint16_t)sb::OP_CHERRY);
-                first_cherry = false;
-            } else {
-                out.ops.push_back((uint16_t)sb::OP_CHERRY_PUSH);
-                ++sp;
-                depth = std::max(depth, sp);
-            }
-            ++i;
-        } else {
-            const uint8_t kind = raw[i];
-            size_t j = i;
-            while (j < raw.size() && raw[j] == kind) ++j;
-            size_t cnt = j - i;
-            if (kind == 2) sp -= (int)cnt;
-            while (cnt > 0) {
-                const size_t c = std::min<size_t>(cnt, 16383);
-                out.ops.push_back((uint16_t)((c << 2) | (kind == 1 ? sb::OP_LEAF : sb::OP_MERGE)));
-                cnt -= c;
-            }
-            i = j;
+        const uint8_t kind = raw[i];
+        size_t j = i + 1;
+        const bool runs = (kind == sb::OP_LEAF_A16 || kind == sb::OP_LEAF_B16 || kind == sb::OP_LEAF_A32 ||
+                           kind == sb::OP_MERGE_POP16 || kind == sb::OP_MERGE_POP32 || kind == sb::OP_MERGE_POPW);
+        if (runs) while (j < raw.size() && raw[j] == kind) ++j;
+        size_t cnt = j - i;
+        if (kind == sb::OP_PUSH16) sp += 1;
+        if (kind == sb::OP_PUSH32) sp += 2;
+        depth = std::max(depth, sp);
+        if (kind == sb::OP_MERGE_POP16 || kind == sb::OP_MERGE_POPW) sp -= (int)cnt;
+        if (kind == sb::OP_MERGE_POP32) sp -= 2 * (int)cnt;
+        while (cnt > 0) {
+            const size_t c = std::min<size_t>(cnt, (size_t)sb::OP_MAX_COUNT);
+            out.ops.push_back((uint16_t)((c << sb::OP_TYPE_BITS) | kind));
+            cnt -= c;
         }
+        i = j;
     }
+    out.ops.push_back((uint16_t)sb::OP_END);
     if (sp != 0) { err = "internal error: unbalanced stack program"; return false; }
-    out.depth = depth;
+    out.depth = depth;   // stack units of 10 words per gene pair
     return true;
 }
 
@@ -424,33 +453,45 @@ int launch_fisher(sb_ctx *ctx, int32_t t, int32_t *d_counts, double *d_p, uint64
     return SB_OK;
 }
 
-size_t walk_smem_bytes(const TraitSlot &s, int label_rows)
+size_t walk_smem_bytes(const TraitSlot &s)
 {
-    return 16 + sizeof(uint32_t) * (size_t)label_rows * s.W32p + sizeof(int) * 10 * (size_t)std::max(1, s.depth) *
-                                                                     sb::WALK_THREADS;
+    return sizeof(int) * 10 * (size_t)std::max(1, s.depth) * sb::WALK_THREADS * sb::WALK_NPAIR;
 }
 
-void fill_walk_args(sb_ctx *ctx, const TraitSlot &s, sb::WalkArgs &A, const int64_t *d_gene_idx, int64_t S)
+void fill_walk_args(const TraitSlot &s, sb::WalkArgs &A, const int64_t *d_gene_idx, int64_t S)
 {
     memset(&A, 0, sizeof A);
     A.genesT = s.d_genesT; A.Gs = s.Gs; A.gene_idx = d_gene_idx; A.S = S;
-    A.W32p = s.W32p; A.ops = s.d_ops; A.n_ops = s.n_ops; A.n_leaves = s.n_leaves; A.shift = s.shift;
-    A.stack_depth = s.depth;
-    (void)ctx;
+    A.W32p = s.W32p; A.shift = s.shift;
+}
+
+// the compiled program of slot s -> constant memory (stream ordered)
+int upload_program(sb_ctx *ctx, const TraitSlot &s)
+{
+    if ((int)s.h_ops.size() > sb::C_OPS_MAX) return fail(ctx, SB_ERR_ARG, "tree program too long for constant memory");
+    if (s.W32p > sb::C_LABEL_WORDS / sb::PERMS_PER_ITEM) return fail(ctx, SB_ERR_ARG, "too many leaves for constant memory");
+    SB_CUDA(ctx, cudaMemcpyToSymbolAsync(sb::c_ops, s.h_ops.data(), sizeof(uint16_t) * s.h_ops.size(), 0,
+                                         cudaMemcpyHostToDevice, ctx->stream));
+    return SB_OK;
 }
 
 int launch_pairwise(sb_ctx *ctx, int32_t t, const int64_t *d_gene_idx, int64_t S, int32_t *d_pairs)
 {
     TraitSlot &s = ctx->traits[t];
+    int rc = upload_program(ctx, s);
+    if (rc) return rc;
+    SB_CUDA(ctx, cudaMemcpyToSymbolAsync(sb::c_labels, s.d_labels0, sizeof(uint32_t) * s.W32p, 0,
+                                         cudaMemcpyDeviceToDevice, ctx->stream));
     sb::WalkArgs A;
-    fill_walk_args(ctx, s, A, d_gene_idx, S);
-    A.labelsW = s.d_labels0; A.P = 1; A.perms_per_block = 1; A.n_chunks = 1; A.pairs = d_pairs;
-    const size_t smem = walk_smem_bytes(s, 1);
+    fill_walk_args(s, A, d_gene_idx, S);
+    A.pairs = d_pairs;
+    const size_t smem = walk_smem_bytes(s);
     if (smem > (size_t)ctx->max_smem_optin) return fail(ctx, SB_ERR_ARG, "tree too deep for shared memory");
-    SB_CUDA(ctx, cudaFuncSetAttribute(sb::walk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SB_CUDA(ctx, cudaFuncSetAttribute(sb::walk_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     Timed tm(ctx, CAT_WALK);
-    dim3 grid((unsigned)((S + sb::WALK_THREADS - 1) / sb::WALK_THREADS), 1, 1);
-    sb::walk_kernel<false><<<grid, sb::WALK_THREADS, smem, ctx->stream>>>(A);
+    const int64_t per_block = (int64_t)sb::WALK_THREADS * sb::WALK_NP;
+    dim3 grid((unsigned)((S + per_block - 1) / per_block), 1, 1);
+    sb::walk_pairs_kernel<<<grid, sb::WALK_THREADS, smem, ctx->stream>>>(A);
     ctx->stats.kernel_launches += 1;
     ctx->stats.tests_walks += S;
     SB_CUDA(ctx, cudaGetLastError());
@@ -476,58 +517,52 @@ int launch_permute(sb_ctx *ctx, int32_t t, const int64_t *d_gene_idx, int64_t S,
                    int32_t early_stop, const int32_t *d_rmin, const int32_t *d_unperm, int32_t *d_r, int32_t *d_n_done)
 {
     TraitSlot &s = ctx->traits[t];
-    // scratch 0: labelsW [P][W32p]; scratch 1: hitbits [S][n_chunks]
+    // scratch 0: labelsW [P][W32p]; scratch 1: hit bytes [n_chunks][S] + work counters
     int rc = ensure_scratch(ctx, 0, sizeof(uint32_t) * (size_t)P * s.W32p);
     if (rc) return rc;
     uint32_t *d_labelsW = (uint32_t *)ctx->d_scratch[0];
     rc = launch_shuffle(ctx, t, P, seed, d_labelsW, nullptr);
     if (rc) return rc;
-
-    const int64_t tiles = (S + sb::WALK_THREADS - 1) / sb::WALK_THREADS;
-    // perms per block (<= 32: one word of hit flags): pick the size that keeps the most
-    // warps resident (the per-thread DP stack dominates shared memory), then make sure
-    // there are a few blocks per SM even when only a handful of genes are walked.
-    int ppb = 1;
-    {
-        int best_blocks = -1;
-        for (int cand = sb::PERMS_PER_BLOCK_MAX; cand >= 4; cand /= 2) {
-            const size_t need = walk_smem_bytes(s, cand) + 1024;   // + per-block reservation
-            if (need > (size_t)ctx->max_smem_optin) continue;
-            const int blocks = (int)std::min<size_t>(12, (size_t)(228 * 1024) / need);
-            if (blocks > best_blocks) { best_blocks = blocks; ppb = cand; }
-        }
-        if (best_blocks < 0) {
-            if (walk_smem_bytes(s, 1) > (size_t)ctx->max_smem_optin)
-                return fail(ctx, SB_ERR_ARG, "tree too deep for shared memory");
-            ppb = 1;
-        }
-    }
-    ppb = std::min(ppb, P);
-    const int64_t want_chunks = (4LL * ctx->sm_count + tiles - 1) / tiles;
-    if (want_chunks > 1) ppb = (int)std::max<int64_t>(1, std::min<int64_t>(ppb, P / want_chunks));
-    const int n_chunks = (P + ppb - 1) / ppb;
-    rc = ensure_scratch(ctx, 1, sizeof(uint32_t) * (size_t)S * n_chunks);
+    rc = upload_program(ctx, s);
     if (rc) return rc;
-    uint32_t *d_hits = (uint32_t *)ctx->d_scratch[1];
 
-    sb::WalkArgs A;
-    fill_walk_args(ctx, s, A, d_gene_idx, S);
-    A.labelsW = d_labelsW; A.P = P; A.perms_per_block = ppb; A.n_chunks = n_chunks; A.unperm = d_unperm;
-    A.hitbits = d_hits;
-    const size_t smem = walk_smem_bytes(s, ppb);
-    SB_CUDA(ctx, cudaFuncSetAttribute(sb::walk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    {
+    const int ppi = sb::PERMS_PER_ITEM;
+    const int n_chunks = (P + ppi - 1) / ppi;
+    int perms_per_launch = (sb::C_LABEL_WORDS / s.W32p) / ppi * ppi;
+    const int n_launches = (P + perms_per_launch - 1) / perms_per_launch;
+    rc = ensure_scratch(ctx, 1, (size_t)n_chunks * (size_t)S);
+    if (rc) return rc;
+    uint8_t *d_hits = (uint8_t *)ctx->d_scratch[1];
+
+    const size_t smem = walk_smem_bytes(s);
+    if (smem > (size_t)ctx->max_smem_optin) return fail(ctx, SB_ERR_ARG, "tree too deep for shared memory");
+    SB_CUDA(ctx, cudaFuncSetAttribute(sb::walk_permute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t per_block = (int64_t)sb::WALK_THREADS * sb::WALK_NP;
+    const int64_t tiles = (S + per_block - 1) / per_block;
+    for (int l = 0; l < n_launches; ++l) {
+        const int base = l * perms_per_launch;
+        const int n_perms = std::min(perms_per_launch, P - base);
+        SB_CUDA(ctx, cudaMemcpyToSymbolAsync(sb::c_labels, d_labelsW + (size_t)base * s.W32p,
+                                             sizeof(uint32_t) * (size_t)n_perms * s.W32p, 0, cudaMemcpyDeviceToDevice,
+                                             ctx->stream));
+        sb::WalkArgs A;
+        fill_walk_args(s, A, d_gene_idx, S);
+        A.n_perms = n_perms;
+        A.items_per_tile = (n_perms + ppi - 1) / ppi;
+        A.chunk_base = base / ppi;
+        A.unperm = d_unperm;
+        A.hits = d_hits;
+        dim3 grid((unsigned)tiles, (unsigned)A.items_per_tile, 1);
         Timed tm(ctx, CAT_PERMUTE);
-        dim3 grid((unsigned)tiles, (unsigned)n_chunks, 1);
-        sb::walk_kernel<true><<<grid, sb::WALK_THREADS, smem, ctx->stream>>>(A);
+        sb::walk_permute_kernel<<<grid, sb::WALK_THREADS, smem, ctx->stream>>>(A);
         ctx->stats.kernel_launches += 1;
-        ctx->stats.tests_walks += S * (int64_t)P;
         SB_CUDA(ctx, cudaGetLastError());
     }
+    ctx->stats.tests_walks += S * (int64_t)P;
     {
         Timed tm(ctx, CAT_REDUCE);
-        sb::reduce_hits_kernel<<<(unsigned)((S + 255) / 256), 256, 0, ctx->stream>>>(d_hits, S, n_chunks, ppb, P, early_stop,
-                                                                                    d_rmin, d_r, d_n_done);
+        sb::reduce_hits_kernel<<<(unsigned)((S + 255) / 256), 256, 0, ctx->stream>>>(d_hits, S, n_chunks, P, early_stop, d_rmin,
+                                                                                    d_r, d_n_done);
         ctx->stats.kernel_launches += 1;
         SB_CUDA(ctx, cudaGetLastError());
     }
@@ -728,17 +763,15 @@ int sb_set_tree(sb_ctx *ctx, int32_t t, const int32_t *left, const int32_t *righ
         if (col < 0 || col >= ctx->N) return fail(ctx, SB_ERR_ARG, "sb_set_tree: leaf_to_col out of range");
         walk_col[pos] = col;
     }
-    SB_CUDA(ctx, cudaMalloc(&s.d_ops, sizeof(uint16_t) * prog.ops.size()));
+    s.h_ops = prog.ops;
     SB_CUDA(ctx, cudaMalloc(&s.d_walk_col, sizeof(int32_t) * s.n_leaves));
     SB_CUDA(ctx, cudaMalloc(&s.d_leaf_of_pos, sizeof(int32_t) * s.n_leaves));
-    SB_CUDA(ctx, cudaMemcpyAsync(s.d_ops, prog.ops.data(), sizeof(uint16_t) * prog.ops.size(), cudaMemcpyHostToDevice,
-                                 ctx->stream));
     SB_CUDA(ctx, cudaMemcpyAsync(s.d_walk_col, walk_col.data(), sizeof(int32_t) * s.n_leaves, cudaMemcpyHostToDevice,
                                  ctx->stream));
     SB_CUDA(ctx, cudaMemcpyAsync(s.d_leaf_of_pos, prog.leaf_of_pos.data(), sizeof(int32_t) * s.n_leaves,
                                  cudaMemcpyHostToDevice, ctx->stream));
     SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    ctx->stats.h2d_bytes += (int64_t)(sizeof(uint16_t) * prog.ops.size() + 2 * sizeof(int32_t) * s.n_leaves);
+    ctx->stats.h2d_bytes += (int64_t)(2 * sizeof(int32_t) * s.n_leaves);
     s.has_tree = true;
     s.finalized = false;
     return SB_OK;
@@ -924,6 +957,43 @@ int sb_int32_peak(sb_ctx *ctx, int32_t iters, double *ops_per_s)
     // one VIADDMNMX = one add + one max; 64 of them per thread per iteration
     const double ops = 2.0 * 64.0 * (double)iters * (double)blocks * (double)threads;
     *ops_per_s = ops / ((double)ms * 1e-3);
+    return SB_OK;
+}
+
+
+// undocumented design probe: warp-instructions per second for 8 instruction kinds
+int sb_debug_pipe_rates(sb_ctx *ctx, int32_t iters, double *out8)
+{
+    if (!ctx || !out8 || iters < 1) return SB_ERR_ARG;
+    SB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->d_peak_out) SB_CUDA(ctx, cudaMalloc(&ctx->d_peak_out, sizeof(int)));
+    const int blocks = ctx->sm_count * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    SB_CUDA(ctx, cudaEventCreate(&e0));
+    SB_CUDA(ctx, cudaEventCreate(&e1));
+    for (int mode = 0; mode < 8; ++mode) {
+        for (int rep = 0; rep < 2; ++rep) {
+            if (rep) SB_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+            const int it = rep ? iters : 16;
+            switch (mode) {
+                case 0: sb::pipe_rate_kernel<0><<<blocks, threads, 0, ctx->stream>>>(ctx->d_peak_out, it, 12345); break;
+                case 1: sb::pipe_rate_kernel<1><<<blocks, threads, 0, ctx->stream>>>(ctx->d_peak_out, it, 12345); break;
+                case 2: sb::pipe_rate_kernel<2><<<blocks, threads, 0, ctx->stream>>>(ctx->d_peak_out, it, 12345); break;
+                case 3: sb::pipe_rate_kernel<3><<<blocks, threads, 0, ctx->stream>>>(ctx->d_peak_out, it, 12345); break;
+                case 4: sb::pipe_rate_kernel<4><<<blocks, threads, 0, ctx->stream>>>(ctx->d_peak_out, it, 12345); break;
+                case 5: sb::pipe_rate_kernel<5><<<blocks, threads, 0, ctx->stream>>>(ctx->d_peak_out, it, 12345); break;
+                case 6: sb::pipe_rate_kernel<6><<<blocks, threads, 0, ctx->stream>>>(ctx->d_peak_out, it, 12345); break;
+                default: sb::pipe_rate_kernel<7><<<blocks, threads, 0, ctx->stream>>>(ctx->d_peak_out, it, 12345); break;
+            }
+        }
+        SB_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+        SB_CUDA(ctx, cudaEventSynchronize(e1));
+        float ms = 0.f;
+        SB_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+        out8[mode] = 64.0 * (double)iters * (double)blocks * (double)threads / 32.0 / ((double)ms * 1e-3);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
     return SB_OK;
 }
 

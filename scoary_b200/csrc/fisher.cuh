@@ -80,8 +80,20 @@ __device__ __forceinline__ double fisher_tail(const double2 *lut, int x0, int di
 // Warp-cooperative two-sided Fisher exact p for [[a, b], [c, d]].
 __device__ __forceinline__ double fisher_two_sided_warp(const double2 *lut, int a, int b, int c, int d, int lane)
 {
+    if (a + b == 0 || c + d == 0 || a + c == 0 || b + d == 0) return 1.0;
+    // The p-value is invariant under swapping rows, swapping columns and transposing.  Put
+    // the table in a canonical orientation first so that all eight variants run the very
+    // same arithmetic and return bit-identical p (ties stay ties for the BH tie rule and
+    // the p-sort).  Invariant: the unordered pair of unordered pairs {{a,d},{b,c}}.
+    {
+        int d0 = min(a, d), d1 = max(a, d), o0 = min(b, c), o1 = max(b, c);
+        if (o0 < d0 || (o0 == d0 && o1 < d1)) {   // the lexicographically smaller pair goes on the diagonal
+            int t0 = d0, t1 = d1;
+            d0 = o0; d1 = o1; o0 = t0; o1 = t1;
+        }
+        a = d0; d = d1; b = o0; c = o1;
+    }
     const int n1 = a + b, n2 = c + d, n = a + c, M = n1 + n2;
-    if (n1 == 0 || n2 == 0 || n == 0 || (b + d) == 0) return 1.0;
     const int lo = max(0, n - n2), hi = min(n, n1);
     const int mode = (int)((double)((long long)(n + 1) * (long long)(n1 + 1)) / (double)(M + 2));
     if (a == mode) return 1.0;

@@ -15,14 +15,21 @@
 //
 // Because the tree is the same for every (gene, labelling), it is compiled
 // once on the host into a small stack program:
-//   CHERRY        acc <- node of two leaves           (push the old acc first if PUSH)
-//   LEAF  xN      acc <- combine(acc, next leaf)       N times
-//   MERGE xN      acc <- combine(pop(), acc)           N times
-// Children are ordered so the deeper side is evaluated first (Strahler
-// order): the stack never exceeds log2(#cherries) entries, and leaves are
-// consumed strictly left to right, so gene and label bits are read as a
-// stream.  One thread = one (gene, labelling) walk; all threads of a block run
-// the same program on the same labelling, so every branch is uniform.
+//   CHERRY_A / CHERRY_B   A (or B) <- node of two leaves
+//   LEAF_A xN / LEAF_B xN A (or B) <- combine(A (or B), next leaf)      N times
+//   MERGE_AB              A <- combine(A, B)
+//   PUSH                  spill A to the shared-memory stack
+//   MERGE_POP xN          A <- combine(pop(), A)                         N times
+// (each in a packed 16-bit form for subtrees of <= 127 leaves -- two genes per register,
+// .S16x2 DPX instructions -- and a 32-bit form above that, with WIDEN steps in between)
+// A and B are two register-resident accumulators: a second child that is a
+// "caterpillar" (a cherry plus single leaves) is evaluated in B while A stays
+// live, so only second children with real branching touch the shared-memory
+// stack.  Children are ordered to minimise the stack (<= log2(#cherries)
+// entries), and leaves are consumed strictly left to right, so gene and label
+// bits are read as a stream.  One thread = one (gene, labelling) walk; all
+// threads of a block run the same program on the same labelling, so every
+// branch is uniform.
 #pragma once
 #include "common.cuh"
 
@@ -30,8 +37,6 @@ namespace sb {
 
 constexpr int WALK_THREADS = 128;
 constexpr int WALK_NEG = -(1 << 30);   // unreachable; keys stay < 2^28 (n_leaves <= 32766), so inv+inv >= INT_MIN
-constexpr int OP_CHERRY = 0, OP_LEAF = 1, OP_MERGE = 2, OP_CHERRY_PUSH = 3;
-constexpr int PERMS_PER_BLOCK_MAX = 32;
 constexpr uint32_t SHUFFLE_DOMAIN = 0x5C0A27u;
 
 // ---------------------------------------------------------------- K1: gather + transpose
@@ -127,33 +132,47 @@ struct WalkState {
     int a[5];   // anti keys
 };
 
+// The compiled tree program and the label bit-vectors of the current launch live in
+// constant memory: every thread of a block reads the same word at the same time, so
+// the compiler keeps the program counter, the leaf position, the label bits and all
+// the branching on them in the uniform datapath (ULDC / UISETP / BRA.U) and the
+// vector pipes only see the DP arithmetic.
+constexpr int C_OPS_MAX = 12288;           // uint16 ops        (24 KB)
+constexpr int C_LABEL_WORDS = 9728;        // uint32 label words (38 KB)
+__constant__ uint16_t c_ops[C_OPS_MAX];
+__constant__ uint32_t c_labels[C_LABEL_WORDS];
+
+// op = (count << 4) | type.  "16" ops work on the packed accumulators A16 / B16 (two genes
+// per register, 16-bit keys), legal while the subtree has <= WALK_LIM16 leaves; "32" ops work
+// on the per-gene 32-bit accumulator A32.  The host compiler (engine.cu) switches mode with
+// WIDEN_A and the *W merge forms where a subtree outgrows 16 bits.
+constexpr int OP_END = 0, OP_CHERRY_A16 = 1, OP_CHERRY_B16 = 2, OP_LEAF_A16 = 3, OP_LEAF_B16 = 4, OP_MERGE_AB16 = 5,
+              OP_PUSH16 = 6, OP_MERGE_POP16 = 7, OP_WIDEN_A = 8, OP_LEAF_A32 = 9, OP_MERGE_A32_B16 = 10, OP_PUSH32 = 11,
+              OP_MERGE_POP32 = 12, OP_MERGE_POPW = 13;
+constexpr int OP_TYPE_BITS = 4, OP_MAX_COUNT = 4095;
+constexpr int PERMS_PER_ITEM = 4;          // labellings walked per block (one byte of hit flags per gene)
+// 16-bit keys: (pairs << 6) + x with pairs, x <= 63  ->  subtrees of at most 127 leaves.
+// Unreachable = -16384 (+ drift < 4096), so valid + unreachable < 0 and unreachable + unreachable
+// >= -32768 never wraps; both halves of a register follow the same rules as the 32-bit keys.
+constexpr int WALK_LIM16 = 127;
+constexpr int WALK_SH16 = 6;
+constexpr unsigned NEG16x2 = 0xC000C000u;
+constexpr unsigned K16x2 = 0x00400040u;    // one pair
+constexpr unsigned K16P1x2 = 0x00410041u;  // one pair that also counts as pro (or anti)
+
 __device__ __forceinline__ int max5(const int v[5])
 {
     return __vimax3_s32(__vimax3_s32(v[0], v[1], v[2]), v[3], v[4]);
 }
 
-// node with two leaf children (classes.py:580-592 tips combined by :268-572)
-__device__ __forceinline__ void walk_cherry(WalkState &o, int g1, int t1, int g2, int t2, int K)
-{
-    const int s1 = (1 - g1) * 2 + (1 - t1), s2 = (1 - g2) * 2 + (1 - t2);
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        const int v = (s1 == c || s2 == c) ? 0 : WALK_NEG;
-        o.p[c] = v;
-        o.a[c] = v;
-    }
-    const bool comp = (s1 + s2) == 3;
-    const bool propair = (s1 == 0) || (s1 == 3);       // AB/ab pair supports, Ab/aB pair opposes
-    o.p[4] = comp ? (propair ? K + 1 : K) : WALK_NEG;
-    o.a[4] = comp ? (propair ? K : K + 1) : WALK_NEG;
-}
-
-// acc <- combine(acc, leaf (g, t)); t is block-uniform, g is per thread
-__device__ __forceinline__ void walk_leaf(WalkState &s, int g, int t, int K)
+// ---- 32-bit (one gene) node updates
+// acc <- combine(acc, leaf (g, TB)); the trait bit TB is block-uniform (the caller branches
+// on it once for all genes of the thread), the gene bit is per gene
+template <int TB>
+__device__ __forceinline__ void walk_leaf(WalkState &s, bool G1, int K)
 {
     const int Mp = max5(s.p), Ma = max5(s.a);
-    const bool G1 = g != 0;
-    if (t) {   // leaf is AB (g) or aB (!g); its complement is ab (pro pair) or Ab (anti pair)
+    if (TB) {  // leaf is AB (g) or aB (!g); its complement is ab (pro pair) or Ab (anti pair)
         const int np4 = G1 ? s.p[3] + (K + 1) : s.p[1] + K;
         const int na4 = G1 ? s.a[3] + K : s.a[1] + (K + 1);
         s.p[0] = G1 ? Mp : s.p[0];
@@ -185,6 +204,7 @@ __device__ __forceinline__ void merge_pass(const int L[5], const int R[5], int o
     out[4] = max(__vimax3_s32(nf, pp, ap), WALK_NEG);
 }
 
+// acc <- combine(L, acc)
 __device__ __forceinline__ void walk_merge(const WalkState &L, WalkState &acc, int K)
 {
     WalkState o;
@@ -193,88 +213,338 @@ __device__ __forceinline__ void walk_merge(const WalkState &L, WalkState &acc, i
     acc = o;
 }
 
+// ---- packed 16-bit (two genes per register) node updates: the same recurrences with the
+// .S16x2 DPX forms; per-gene choices become bitwise selects under a half-word mask
+struct WalkState16 {
+    unsigned p[5];
+    unsigned a[5];
+};
+
+__device__ __forceinline__ unsigned sel2(unsigned m, unsigned x, unsigned y) { return (x & m) | (y & ~m); }
+
+__device__ __forceinline__ unsigned max5_16(const unsigned v[5])
+{
+    return __vimax3_s16x2(__vimax3_s16x2(v[0], v[1], v[2]), v[3], v[4]);
+}
+
+// m1, m2: half-word masks of the two leaves' gene bits; tt = 2*t1 + t2 (block-uniform)
+__device__ __forceinline__ void walk_cherry16(WalkState16 &o, unsigned m1, unsigned m2, int tt)
+{
+    const unsigned N = NEG16x2;
+    unsigned f0 = N, f1 = N, f2 = N, f3 = N, p4 = N, a4 = N;
+    if (tt == 3) {                  // both trait-positive: leaves in {AB, aB}
+        f0 = N & ~(m1 | m2);
+        f2 = N & (m1 & m2);
+    } else if (tt == 0) {           // both trait-negative: leaves in {Ab, ab}
+        f1 = N & ~(m1 | m2);
+        f3 = N & (m1 & m2);
+    } else {
+        const unsigned mB = (tt == 2) ? m1 : m2;   // gene mask of the trait-positive leaf
+        const unsigned mb = (tt == 2) ? m2 : m1;   // gene mask of the trait-negative leaf
+        f0 = N & ~mB;                   // AB
+        f2 = N & mB;                    // aB
+        f1 = N & ~mb;                   // Ab
+        f3 = N & mb;                    // ab
+        const unsigned pm = mB & ~mb, am = ~mB & mb;   // AB+ab supports, aB+Ab opposes
+        p4 = sel2(pm, K16P1x2, sel2(am, K16x2, N));
+        a4 = sel2(pm, K16x2, sel2(am, K16P1x2, N));
+    }
+    o.p[0] = f0; o.p[1] = f1; o.p[2] = f2; o.p[3] = f3; o.p[4] = p4;
+    o.a[0] = f0; o.a[1] = f1; o.a[2] = f2; o.a[3] = f3; o.a[4] = a4;
+}
+
+template <int TB>
+__device__ __forceinline__ void walk_leaf16(WalkState16 &s, unsigned m)
+{
+    const unsigned Mp = max5_16(s.p), Ma = max5_16(s.a);
+    if (TB) {
+        const unsigned np4 = sel2(m, __vadd2(s.p[3], K16P1x2), __vadd2(s.p[1], K16x2));
+        const unsigned na4 = sel2(m, __vadd2(s.a[3], K16x2), __vadd2(s.a[1], K16P1x2));
+        s.p[0] = sel2(m, Mp, s.p[0]);
+        s.p[2] = sel2(m, s.p[2], Mp);
+        s.a[0] = sel2(m, Ma, s.a[0]);
+        s.a[2] = sel2(m, s.a[2], Ma);
+        s.p[4] = np4;
+        s.a[4] = na4;
+    } else {
+        const unsigned np4 = sel2(m, __vadd2(s.p[2], K16x2), __vadd2(s.p[0], K16P1x2));
+        const unsigned na4 = sel2(m, __vadd2(s.a[2], K16P1x2), __vadd2(s.a[0], K16x2));
+        s.p[1] = sel2(m, Mp, s.p[1]);
+        s.p[3] = sel2(m, s.p[3], Mp);
+        s.a[1] = sel2(m, Ma, s.a[1]);
+        s.a[3] = sel2(m, s.a[3], Ma);
+        s.p[4] = np4;
+        s.a[4] = na4;
+    }
+}
+
+__device__ __forceinline__ void merge_pass16(const unsigned L[5], const unsigned R[5], unsigned out[5], unsigned bpro,
+                                             unsigned banti)
+{
+    const unsigned ML = max5_16(L), MR = max5_16(R);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) out[c] = __viaddmax_s16x2(L[c], MR, __vadd2(ML, R[c]));
+    const unsigned nf = __vadd2(L[4], R[4]);
+    const unsigned pp = __vadd2(__viaddmax_s16x2(L[0], R[3], __vadd2(L[3], R[0])), bpro);
+    const unsigned ap = __vadd2(__viaddmax_s16x2(L[1], R[2], __vadd2(L[2], R[1])), banti);
+    out[4] = __vmaxs2(__vimax3_s16x2(nf, pp, ap), NEG16x2);
+}
+
+// acc <- combine(L, acc)
+__device__ __forceinline__ void walk_merge16(const WalkState16 &L, WalkState16 &acc)
+{
+    WalkState16 o;
+    merge_pass16(L.p, acc.p, o.p, K16P1x2, K16x2);
+    merge_pass16(L.a, acc.a, o.a, K16x2, K16P1x2);
+    acc = o;
+}
+
+// 16-bit key -> 32-bit key of the same (pairs, x); unreachable stays unreachable
+__device__ __forceinline__ int widen_key(int k16, int scale)   // scale = (1 << SH) - 64
+{
+    const int k32 = k16 + (k16 >> WALK_SH16) * scale;
+    return k16 < 0 ? WALK_NEG : k32;
+}
+
+__device__ __forceinline__ void walk_widen(const WalkState16 &s, WalkState &g0, WalkState &g1, int scale)
+{
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+        g0.p[c] = widen_key((int)(short)(s.p[c] & 0xFFFFu), scale);
+        g1.p[c] = widen_key((int)s.p[c] >> 16, scale);
+        g0.a[c] = widen_key((int)(short)(s.a[c] & 0xFFFFu), scale);
+        g1.a[c] = widen_key((int)s.a[c] >> 16, scale);
+    }
+}
+
 struct WalkArgs {
     const uint32_t *genesT;    // [W32p][Gs]
     int64_t Gs;
     const int64_t *gene_idx;   // [S] or null (identity)
     int64_t S;
-    const uint32_t *labelsW;   // [n_label_rows][W32p], walk order
     int32_t W32p;
-    const uint16_t *ops;       // [n_ops]: (count << 2) | type
-    int32_t n_ops;
-    int32_t n_leaves;
     int32_t shift;             // SH
-    int32_t stack_depth;       // max pushes
-    int32_t P;                 // labellings (permute mode)
-    int32_t perms_per_block;
-    int32_t n_chunks;          // ceil(P / perms_per_block)
+    int32_t n_perms;           // labellings in constant memory for this launch (permute mode)
+    int32_t items_per_tile;    // ceil(n_perms / PERMS_PER_ITEM)
+    int32_t chunk_base;        // first hit-byte row of this launch
     const int32_t *unperm;     // [S][3] (permute mode): unpermuted Total, Pro, Anti
     int32_t *pairs;            // [S][3] (pairs mode output)
-    uint32_t *hitbits;         // [S][n_chunks] (permute mode output)
+    uint8_t *hits;             // [n_chunks_total][S] (permute mode output): bit r = perm 4*chunk + r hit
 };
 
-// One full tree walk for this thread's gene under the labelling `lab` (shared
-// memory, walk order).  Returns the root state in acc.
-__device__ __forceinline__ void walk_tree(const WalkArgs &A, const uint32_t *__restrict__ gcol /* genesT + gene */,
-                                          const uint32_t *lab, int *stk, WalkState &acc)
+#ifndef SB_WALK_NPAIR
+#define SB_WALK_NPAIR 1
+#endif
+constexpr int WALK_NPAIR = SB_WALK_NPAIR;   // gene pairs per thread
+constexpr int WALK_NP = 2 * WALK_NPAIR;     // genes per thread
+
+// NP = 2 * NPAIR simultaneous tree walks (this thread's genes, same labelling at
+// c_labels[lab_off ..]).  gcol[k] points at gene k's column of genesT; genes 2q and 2q+1 share
+// the packed accumulators of pair q.  Every branch is on block-uniform data (the program and
+// the label bits); per-gene data only feeds selects.  The program always ends in 32-bit mode.
+template <int NPAIR>
+__device__ __forceinline__ void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR], int lab_off,
+                                          int *stk, WalkState (&acc)[2 * NPAIR])
 {
-    const int K = 1 << A.shift;
+    constexpr int NP = 2 * NPAIR;
     constexpr int T = WALK_THREADS;
-    int pos = 0, sp = 0;
-    uint32_t gw = 0, lw = 0;
-    uint32_t gnext = __ldg(gcol);
-    auto next_bits = [&](int &g, int &t) {
-        if ((pos & 31) == 0) {
-            const int w = pos >> 5;
-            gw = gnext;
-            lw = lab[w];
-            if (w + 1 < A.W32p) gnext = __ldg(gcol + (int64_t)(w + 1) * A.Gs);
+    const int K = 1 << A.shift;
+    const int scale = K - (1 << WALK_SH16);
+    WalkState16 a16[NPAIR], b16[NPAIR];
+    int pos = 0, sp = 0, pc = 0;       // sp counts 32-bit words per thread
+    uint32_t gw[NP], gnext[NP], lw = 0;
+#pragma unroll
+    for (int k = 0; k < NP; ++k) { gw[k] = 0; gnext[k] = __ldg(gcol[k]); }
+    const int W32p = A.W32p;
+    const int64_t Gs = A.Gs;
+    // fetch the next leaf: label bit tv (uniform); gene bits stay in gw[] bit 0 until SB_DROP_BITS
+#define SB_LOAD_BITS(tv)                                                                       \
+    do {                                                                                       \
+        if ((pos & 31) == 0) {                                                                 \
+            const int w_ = pos >> 5;                                                           \
+            lw = c_labels[lab_off + w_];                                                       \
+            _Pragma("unroll") for (int k_ = 0; k_ < NP; ++k_) {                                \
+                gw[k_] = gnext[k_];                                                            \
+                if (w_ + 1 < W32p) gnext[k_] = __ldg(gcol[k_] + (int64_t)(w_ + 1) * Gs);       \
+            }                                                                                  \
+        }                                                                                      \
+        tv = (int)(lw & 1u);                                                                   \
+        lw >>= 1;                                                                              \
+        ++pos;                                                                                 \
+    } while (0)
+#define SB_DROP_BITS()                                                                         \
+    do {                                                                                       \
+        _Pragma("unroll") for (int k_ = 0; k_ < NP; ++k_) gw[k_] >>= 1;                        \
+    } while (0)
+    // half-word mask of pair q's current gene bits: 0xFFFF per half whose gene is present
+#define SB_PAIR_MASK(q) ((((gw[2 * (q)] & 1u) | ((gw[2 * (q) + 1] & 1u) << 16))) * 0xFFFFu)
+    for (;;) {
+        const uint32_t op = c_ops[pc++];
+        const int type = op & 15, cnt = op >> OP_TYPE_BITS;
+        switch (type) {
+        case OP_LEAF_A16:
+            for (int i = 0; i < cnt; ++i) {
+                int t;
+                SB_LOAD_BITS(t);
+                if (t) {
+#pragma unroll
+                    for (int q = 0; q < NPAIR; ++q) walk_leaf16<1>(a16[q], SB_PAIR_MASK(q));
+                } else {
+#pragma unroll
+                    for (int q = 0; q < NPAIR; ++q) walk_leaf16<0>(a16[q], SB_PAIR_MASK(q));
+                }
+                SB_DROP_BITS();
+            }
+            break;
+        case OP_LEAF_B16:
+            for (int i = 0; i < cnt; ++i) {
+                int t;
+                SB_LOAD_BITS(t);
+                if (t) {
+#pragma unroll
+                    for (int q = 0; q < NPAIR; ++q) walk_leaf16<1>(b16[q], SB_PAIR_MASK(q));
+                } else {
+#pragma unroll
+                    for (int q = 0; q < NPAIR; ++q) walk_leaf16<0>(b16[q], SB_PAIR_MASK(q));
+                }
+                SB_DROP_BITS();
+            }
+            break;
+        case OP_CHERRY_A16:
+        case OP_CHERRY_B16: {
+            int t1, t2;
+            unsigned m1[NPAIR], m2[NPAIR];
+            SB_LOAD_BITS(t1);
+#pragma unroll
+            for (int q = 0; q < NPAIR; ++q) m1[q] = SB_PAIR_MASK(q);
+            SB_DROP_BITS();
+            SB_LOAD_BITS(t2);
+#pragma unroll
+            for (int q = 0; q < NPAIR; ++q) m2[q] = SB_PAIR_MASK(q);
+            SB_DROP_BITS();
+            const int tt = t1 * 2 + t2;
+            if (type == OP_CHERRY_A16) {
+#pragma unroll
+                for (int q = 0; q < NPAIR; ++q) walk_cherry16(a16[q], m1[q], m2[q], tt);
+            } else {
+#pragma unroll
+                for (int q = 0; q < NPAIR; ++q) walk_cherry16(b16[q], m1[q], m2[q], tt);
+            }
+            break;
         }
-        g = (int)(gw & 1u);
-        t = (int)(lw & 1u);
-        gw >>= 1;
-        lw >>= 1;
-        ++pos;
-    };
-    uint32_t op_next = __ldg(&A.ops[0]);
-    for (int i = 0; i < A.n_ops; ++i) {
-        const uint32_t op = op_next;
-        if (i + 1 < A.n_ops) op_next = __ldg(&A.ops[i + 1]);
-        const int type = op & 3, cnt = op >> 2;
-        if (type == OP_LEAF) {
-            for (int k = 0; k < cnt; ++k) {
-                int g, t;
-                next_bits(g, t);
-                walk_leaf(acc, g, t, K);
-            }
-        } else if (type == OP_MERGE) {
-            for (int k = 0; k < cnt; ++k) {
-                --sp;
-                WalkState L;
-                const int *s = stk + sp * 10 * T;
+        case OP_MERGE_AB16:
+#pragma unroll
+            for (int q = 0; q < NPAIR; ++q) walk_merge16(b16[q], a16[q]);
+            break;
+        case OP_PUSH16:
+#pragma unroll
+            for (int q = 0; q < NPAIR; ++q) {
+                int *s = stk + (sp + q * 10) * T;
 #pragma unroll
                 for (int c = 0; c < 5; ++c) {
-                    L.p[c] = s[c * T];
-                    L.a[c] = s[(5 + c) * T];
+                    s[c * T] = (int)a16[q].p[c];
+                    s[(5 + c) * T] = (int)a16[q].a[c];
                 }
-                walk_merge(L, acc, K);
             }
-        } else {
-            if (type == OP_CHERRY_PUSH) {
-                int *s = stk + sp * 10 * T;
+            sp += 10 * NPAIR;
+            break;
+        case OP_MERGE_POP16:
+            for (int i = 0; i < cnt; ++i) {
+                sp -= 10 * NPAIR;
+#pragma unroll
+                for (int q = 0; q < NPAIR; ++q) {
+                    WalkState16 L;
+                    const int *s = stk + (sp + q * 10) * T;
+#pragma unroll
+                    for (int c = 0; c < 5; ++c) {
+                        L.p[c] = (unsigned)s[c * T];
+                        L.a[c] = (unsigned)s[(5 + c) * T];
+                    }
+                    walk_merge16(L, a16[q]);
+                }
+            }
+            break;
+        case OP_WIDEN_A:
+#pragma unroll
+            for (int q = 0; q < NPAIR; ++q) walk_widen(a16[q], acc[2 * q], acc[2 * q + 1], scale);
+            break;
+        case OP_LEAF_A32:
+            for (int i = 0; i < cnt; ++i) {
+                int t;
+                SB_LOAD_BITS(t);
+                if (t) {
+#pragma unroll
+                    for (int k = 0; k < NP; ++k) walk_leaf<1>(acc[k], (gw[k] & 1u) != 0, K);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < NP; ++k) walk_leaf<0>(acc[k], (gw[k] & 1u) != 0, K);
+                }
+                SB_DROP_BITS();
+            }
+            break;
+        case OP_MERGE_A32_B16:
+#pragma unroll
+            for (int q = 0; q < NPAIR; ++q) {
+                WalkState r0, r1;
+                walk_widen(b16[q], r0, r1, scale);
+                walk_merge(r0, acc[2 * q], K);
+                walk_merge(r1, acc[2 * q + 1], K);
+            }
+            break;
+        case OP_PUSH32:
+#pragma unroll
+            for (int k = 0; k < NP; ++k) {
+                int *s = stk + (sp + k * 10) * T;
 #pragma unroll
                 for (int c = 0; c < 5; ++c) {
-                    s[c * T] = acc.p[c];
-                    s[(5 + c) * T] = acc.a[c];
+                    s[c * T] = acc[k].p[c];
+                    s[(5 + c) * T] = acc[k].a[c];
                 }
-                ++sp;
             }
-            int g1, t1, g2, t2;
-            next_bits(g1, t1);
-            next_bits(g2, t2);
-            walk_cherry(acc, g1, t1, g2, t2, K);
+            sp += 10 * NP;
+            break;
+        case OP_MERGE_POP32:
+            for (int i = 0; i < cnt; ++i) {
+                sp -= 10 * NP;
+#pragma unroll
+                for (int k = 0; k < NP; ++k) {
+                    WalkState L;
+                    const int *s = stk + (sp + k * 10) * T;
+#pragma unroll
+                    for (int c = 0; c < 5; ++c) {
+                        L.p[c] = s[c * T];
+                        L.a[c] = s[(5 + c) * T];
+                    }
+                    walk_merge(L, acc[k], K);
+                }
+            }
+            break;
+        case OP_MERGE_POPW:
+            for (int i = 0; i < cnt; ++i) {
+                sp -= 10 * NPAIR;
+#pragma unroll
+                for (int q = 0; q < NPAIR; ++q) {
+                    WalkState16 L;
+                    const int *s = stk + (sp + q * 10) * T;
+#pragma unroll
+                    for (int c = 0; c < 5; ++c) {
+                        L.p[c] = (unsigned)s[c * T];
+                        L.a[c] = (unsigned)s[(5 + c) * T];
+                    }
+                    WalkState r0, r1;
+                    walk_widen(L, r0, r1, scale);
+                    walk_merge(r0, acc[2 * q], K);
+                    walk_merge(r1, acc[2 * q + 1], K);
+                }
+            }
+            break;
+        default:   // OP_END
+            return;
         }
     }
+#undef SB_LOAD_BITS
+#undef SB_DROP_BITS
+#undef SB_PAIR_MASK
 }
 
 // root: three independent maxima (classes.py:246-249)
@@ -291,90 +561,103 @@ __device__ __forceinline__ void walk_root(const WalkState &s, int shift, int &to
     }
 }
 
-// PERMUTE = false: K4, one labelling (labelsW row 0), writes pairs[S][3].
-// PERMUTE = true : K5, grid.y = chunks of perms_per_block labellings; each block stages
-//                  its chunk of label vectors with one TMA bulk copy and writes one
-//                  32-bit word of hit flags per gene.
-template <bool PERMUTE>
-__global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs A)
+// gene slots of this thread: (tile * NP + k) * T + tid  (coalesced per k)
+template <int NP>
+__device__ __forceinline__ void walk_slots(const WalkArgs &A, int tile, int64_t (&s_idx)[NP], bool (&active)[NP],
+                                           int64_t (&sc)[NP], const uint32_t *(&gcol)[NP])
 {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
-    uint32_t *s_lab = reinterpret_cast<uint32_t *>(smem_raw + 16);
-    const int n_rows = PERMUTE ? A.perms_per_block : 1;
-    int *stk = reinterpret_cast<int *>(s_lab + (size_t)n_rows * A.W32p) + threadIdx.x;
-
-    const int chunk = PERMUTE ? blockIdx.y : 0;
-    const int perm0 = chunk * A.perms_per_block;
-    const int rows = PERMUTE ? min(A.perms_per_block, A.P - perm0) : 1;
-    if (threadIdx.x == 0) {
-        mbar_init(bar, 1);
-        fence_barrier_init();
-        const uint32_t bytes = (uint32_t)rows * (uint32_t)A.W32p * 4u;
-        mbar_arrive_expect_tx(bar, bytes);
-        tma_bulk_g2s(s_lab, A.labelsW + (int64_t)perm0 * A.W32p, bytes, bar);
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+        s_idx[k] = ((int64_t)tile * NP + k) * WALK_THREADS + threadIdx.x;
+        active[k] = s_idx[k] < A.S;
+        sc[k] = active[k] ? s_idx[k] : (A.S - 1);   // idle slots redo the last gene (no divergence)
+        const int64_t gene = A.gene_idx ? A.gene_idx[sc[k]] : sc[k];
+        gcol[k] = A.genesT + gene;
     }
-    __syncthreads();
-    mbar_wait(bar, 0);
+}
 
-    const int64_t s_idx = (int64_t)blockIdx.x * WALK_THREADS + threadIdx.x;
-    const bool active = s_idx < A.S;
-    const int64_t sc = active ? s_idx : (A.S - 1);   // inactive lanes redo the last gene (no divergence)
-    const int64_t gene = A.gene_idx ? A.gene_idx[sc] : sc;
-    const uint32_t *gcol = A.genesT + gene;
-
-    if (!PERMUTE) {
-        WalkState acc;
-        walk_tree(A, gcol, s_lab, stk, acc);
+// K4: one labelling (c_labels row 0), writes pairs[S][3].
+__global__ void __launch_bounds__(WALK_THREADS) walk_pairs_kernel(const WalkArgs A)
+{
+    extern __shared__ __align__(16) int smem_stack[];
+    int *stk = smem_stack + threadIdx.x;
+    constexpr int NP = WALK_NP;
+    int64_t s_idx[NP], sc[NP]; bool active[NP]; const uint32_t *gcol[NP];
+    walk_slots<NP>(A, blockIdx.x, s_idx, active, sc, gcol);
+    WalkState acc[NP];
+    walk_tree<WALK_NPAIR>(A, gcol, 0, stk, acc);
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
         int total, pro, anti;
-        walk_root(acc, A.shift, total, pro, anti);
-        if (active) {
-            A.pairs[s_idx * 3 + 0] = total;
-            A.pairs[s_idx * 3 + 1] = pro;
-            A.pairs[s_idx * 3 + 2] = anti;
+        walk_root(acc[k], A.shift, total, pro, anti);
+        if (active[k]) {
+            A.pairs[s_idx[k] * 3 + 0] = total;
+            A.pairs[s_idx[k] * 3 + 1] = pro;
+            A.pairs[s_idx[k] * 3 + 2] = anti;
         }
-    } else {
-        const long long u_total = A.unperm[sc * 3 + 0];
-        const int u_pro = A.unperm[sc * 3 + 1], u_anti = A.unperm[sc * 3 + 2];
-        const bool use_pro = u_pro >= u_anti;                 // methods.py:1333-1336
-        const long long u_stat = use_pro ? u_pro : u_anti;
-        uint32_t hits = 0;
-        for (int r = 0; r < rows; ++r) {
-            WalkState acc;
-            walk_tree(A, gcol, s_lab + (size_t)r * A.W32p, stk, acc);
-            int total, pro, anti;
-            walk_root(acc, A.shift, total, pro, anti);
-            const long long si = use_pro ? pro : anti;
-            if (si * u_total >= u_stat * (long long)total) hits |= (1u << r);   // methods.py:1353-1355
-        }
-        if (active) A.hitbits[s_idx * A.n_chunks + chunk] = hits;
     }
+}
+
+// K5: grid = (gene tiles, chunks of PERMS_PER_ITEM labellings).  A thread walks its NP genes
+// under each labelling of the block's chunk and writes one byte of hit flags per gene.
+// Blocks are small work items, so the tail of a launch is short, and blocks that run
+// concurrently read the same few label vectors from the constant cache.
+__global__ void __launch_bounds__(WALK_THREADS) walk_permute_kernel(const WalkArgs A)
+{
+    extern __shared__ __align__(16) int smem_stack[];
+    int *stk = smem_stack + threadIdx.x;
+    constexpr int NP = WALK_NP;
+    const int chunk = blockIdx.y;
+    const int perm0 = chunk * PERMS_PER_ITEM;
+    const int rows = min(PERMS_PER_ITEM, A.n_perms - perm0);
+    int64_t s_idx[NP], sc[NP]; bool active[NP]; const uint32_t *gcol[NP];
+    walk_slots<NP>(A, blockIdx.x, s_idx, active, sc, gcol);
+    long long u_total[NP], u_stat[NP]; bool use_pro[NP]; uint32_t hits[NP];
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+        u_total[k] = A.unperm[sc[k] * 3 + 0];
+        const int u_pro = A.unperm[sc[k] * 3 + 1], u_anti = A.unperm[sc[k] * 3 + 2];
+        use_pro[k] = u_pro >= u_anti;                 // methods.py:1333-1336
+        u_stat[k] = use_pro[k] ? u_pro : u_anti;
+        hits[k] = 0;
+    }
+    for (int r = 0; r < rows; ++r) {
+        WalkState acc[NP];
+        walk_tree<WALK_NPAIR>(A, gcol, (perm0 + r) * A.W32p, stk, acc);
+#pragma unroll
+        for (int k = 0; k < NP; ++k) {
+            int total, pro, anti;
+            walk_root(acc[k], A.shift, total, pro, anti);
+            const long long si = use_pro[k] ? pro : anti;
+            if (si * u_total[k] >= u_stat[k] * (long long)total) hits[k] |= (1u << r);   // methods.py:1353-1355
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NP; ++k)
+        if (active[k]) A.hits[(int64_t)(A.chunk_base + chunk) * A.S + s_idx[k]] = (uint8_t)hits[k];
 }
 
 // ---------------------------------------------------------------- hit-sequence reduction
 // Permute's bookkeeping (methods.py:1348-1365) on the ordered hit flags.
-__global__ void __launch_bounds__(256) reduce_hits_kernel(const uint32_t *__restrict__ hitbits, int64_t S, int n_chunks,
-                                                          int perms_per_block, int P, int early_stop,
-                                                          const int32_t *__restrict__ rmin, int32_t *__restrict__ r_out,
-                                                          int32_t *__restrict__ n_done)
+__global__ void __launch_bounds__(256) reduce_hits_kernel(const uint8_t *__restrict__ hits, int64_t S, int n_chunks,
+                                                          int P, int early_stop, const int32_t *__restrict__ rmin,
+                                                          int32_t *__restrict__ r_out, int32_t *__restrict__ n_done)
 {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
-    const uint32_t *h = hitbits + s * n_chunks;
     int r = 0, done = P;
     if (!early_stop) {
         for (int c = 0; c < n_chunks; ++c) {
-            const int rows = min(perms_per_block, P - c * perms_per_block);
-            const uint32_t m = rows >= 32 ? 0xffffffffu : ((1u << rows) - 1u);
-            r += __popc(h[c] & m);
+            const int rows = min(PERMS_PER_ITEM, P - c * PERMS_PER_ITEM);
+            r += __popc((uint32_t)hits[(int64_t)c * S + s] & ((1u << rows) - 1u));
         }
     } else {
         bool stop = false;
         for (int c = 0; c < n_chunks && !stop; ++c) {
-            const int rows = min(perms_per_block, P - c * perms_per_block);
-            const uint32_t w = h[c];
+            const int rows = min(PERMS_PER_ITEM, P - c * PERMS_PER_ITEM);
+            const uint32_t w = hits[(int64_t)c * S + s];
             for (int b = 0; b < rows; ++b) {
-                const int i = c * perms_per_block + b;
+                const int i = c * PERMS_PER_ITEM + b;
                 r += (w >> b) & 1u;
                 if (i >= 30 && r >= rmin[i]) {   // methods.py:1360-1363
                     done = i + 1;
@@ -407,6 +690,37 @@ __global__ void __launch_bounds__(256) int32_peak_kernel(int *out, int iters, in
 #pragma unroll
     for (int k = 0; k < 8; ++k) s ^= x[k];
     if (s == 0x7fffffff) out[0] = s;
+}
+
+
+// pipe-rate probes for kernel design decisions (sb_debug_pipe_rates)
+template <int MODE>
+__global__ void __launch_bounds__(256) pipe_rate_kernel(int *out, int iters, int seed)
+{
+    unsigned x[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = seed + threadIdx.x * (k + 1);
+    const unsigned a = seed | 0x00010001u, b = 0xC000C000u + seed;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (MODE == 0) x[k] = __viaddmax_s32((int)x[k], (int)a, (int)(b + k));
+                if (MODE == 1) x[k] = __viaddmax_s16x2(x[k], a, b + k);
+                if (MODE == 2) x[k] = __vimax3_s16x2(x[k], a + k, b);
+                if (MODE == 3) x[k] = __vadd2(x[k], a + k);
+                if (MODE == 4) x[k] = (x[k] & a) | (b & ~a) ^ (x[k] >> 1);          // LOP3 + SHF
+                if (MODE == 5) x[k] = __vimax3_s32((int)x[k], (int)(a + k), (int)b);
+                if (MODE == 6) x[k] = (int)x[k] > (int)a ? x[k] + k : b;             // ISETP + SEL(+add)
+                if (MODE == 7) x[k] = x[k] * 3u + a;                                 // IMAD
+            }
+        }
+    }
+    unsigned s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s ^= x[k];
+    if (s == 0x7fffffffu) out[0] = (int)s;
 }
 
 }  // namespace sb

@@ -51,11 +51,8 @@ def _compare(got_path, gold_path):
     assert hdr == ghdr
     assert len(got) == len(gold)
     col = {h: i for i, h in enumerate(hdr)}
-    # p-values that are tied in one implementation and 1 ulp apart in the other may swap
-    # neighbouring rows; compare as sets of genes first, then row by row after aligning by gene
     assert sorted(r[0] for r in got) == sorted(r[0] for r in gold)
     by_gene = {r[0]: r for r in got}
-    swapped = sum(1 for a, b in zip(got, gold) if a[0] != b[0])
     for g in gold:
         r = by_gene[g[0]]
         assert r[1:3] == g[1:3]
@@ -67,6 +64,15 @@ def _compare(got_path, gold_path):
                 a, b = float(r[col[c]]), float(g[col[c]])
                 if b > 1e-290:
                     assert a == b or abs(a - b) <= RTOL * abs(b), (g[0], c, a, b)
+    # Row order: both files are sorted by naive p.  SciPy's own p differs by an ulp between
+    # symmetric variants of one table (row/column swap, transpose), so rows whose p agree to
+    # 1e-10 may come out in a different order; any row that moved must be such a near-tie.
+    ip = col["Naive_p"]
+    swapped = 0
+    for a, b in zip(got, gold):
+        pa, pb = float(a[ip]), float(b[ip])
+        assert pa == pb or abs(pa - pb) <= RTOL * abs(pb), ("sorted p sequence differs", a[0], b[0], pa, pb)
+        swapped += a[0] != b[0]
     return swapped, len(gold)
 
 
@@ -79,8 +85,7 @@ def test_cli_matches_reference_results(name, extra, inputs):
     for trait in ("Tetracycline_resistance", "Bogus_trait"):
         gold = os.path.join(GOLD, name, trait + ".results.csv")
         gold = gold if os.path.exists(gold) else gold + ".gz"
-        swapped, n = _compare(os.path.join(inputs["out"], trait + ".results.csv"), gold)
-        assert swapped <= max(2, n // 50), "row order differs in %d of %d rows" % (swapped, n)
+        _compare(os.path.join(inputs["out"], trait + ".results.csv"), gold)
 
 
 def test_cli_restricted(inputs):
@@ -98,9 +103,11 @@ def test_cli_permutations_statistically_like_reference(inputs):
           "-p", "0.05", "0.05"])
     hdr, got = _rows(os.path.join(inputs["out"], "Tetracycline_resistance.results.csv"))
     ghdr, gold = _rows(os.path.join(GOLD, "perm", "Tetracycline_resistance.results.csv"))
-    assert hdr == ghdr and [r[0] for r in got] == [r[0] for r in gold]
+    assert hdr == ghdr and sorted(r[0] for r in got) == sorted(r[0] for r in gold)
     ie = hdr.index("Empirical_p")
-    for r, g in zip(got, gold):
+    by_gene = {r[0]: r for r in got}
+    for g in gold:
+        r = by_gene[g[0]]
         assert r[:ie][3:7] == g[:ie][3:7] and r[13:16] == g[13:16]
         a, b = float(r[ie]), float(g[ie])
         n = 200
