@@ -262,7 +262,7 @@ bool compile_tree(const int32_t *left, const int32_t *right, int32_t n_internal,
             } else {
                 out.leaf_of_pos.push_back(leaf);
                 if (small(v)) {
-                    raw.push_back(into_b ? sb::OP_LEAF_B16 : sb::OP_LEAF_A16);
+                    raw.push_back(into_b ? sb::RAW_LEAF_B16 : sb::OP_LEAF_A16);
                 } else {
                     if (small(inner)) raw.push_back(sb::OP_WIDEN_A);
                     raw.push_back(sb::OP_LEAF_A32);
@@ -282,7 +282,7 @@ bool compile_tree(const int32_t *left, const int32_t *right, int32_t n_internal,
                 st.push_back({second, 0, (uint8_t)(in_b ? 1 : 0)});
             } else {
                 if (in_b) {
-                    if (small(v)) raw.push_back(sb::OP_MERGE_AB16);
+                    if (small(v)) raw.push_back(sb::RAW_MERGE_AB16);
                     else {
                         if (small(first)) raw.push_back(sb::OP_WIDEN_A);
                         raw.push_back(sb::OP_MERGE_A32_B16);
@@ -298,27 +298,58 @@ bool compile_tree(const int32_t *left, const int32_t *right, int32_t n_internal,
         }
     }
     if (small(n_internal - 1)) raw.push_back(sb::OP_WIDEN_A);   // the program always ends in 32-bit mode
+    // peephole fusion + run-length encoding:
+    //   [PUSH16] CHERRY_A16 LEAF_A16*            -> (PUSH_)CHERRY_A16(n)
+    //   CHERRY_B16 LEAF_B16* [MERGE_AB16]        -> CHERRY_B16(_MERGE)(n)
+    //   LEAF_A16+ / LEAF_A32+ / MERGE_POP*+      -> one op with a count
     out.ops.clear();
     int depth = 0, sp = 0;
+    auto emit = [&](int kind, size_t cnt) {
+        out.ops.push_back((uint16_t)((cnt << sb::OP_TYPE_BITS) | (unsigned)kind));
+    };
     size_t i = 0;
-    while (i < raw.size()) {
+    const size_t n_raw = raw.size();
+    while (i < n_raw) {
         const uint8_t kind = raw[i];
-        size_t j = i + 1;
-        const bool runs = (kind == sb::OP_LEAF_A16 || kind == sb::OP_LEAF_B16 || kind == sb::OP_LEAF_A32 ||
-                           kind == sb::OP_MERGE_POP16 || kind == sb::OP_MERGE_POP32 || kind == sb::OP_MERGE_POPW);
-        if (runs) while (j < raw.size() && raw[j] == kind) ++j;
-        size_t cnt = j - i;
-        if (kind == sb::OP_PUSH16) sp += 1;
-        if (kind == sb::OP_PUSH32) sp += 2;
-        depth = std::max(depth, sp);
-        if (kind == sb::OP_MERGE_POP16 || kind == sb::OP_MERGE_POPW) sp -= (int)cnt;
-        if (kind == sb::OP_MERGE_POP32) sp -= 2 * (int)cnt;
-        while (cnt > 0) {
-            const size_t c = std::min<size_t>(cnt, (size_t)sb::OP_MAX_COUNT);
-            out.ops.push_back((uint16_t)((c << sb::OP_TYPE_BITS) | kind));
-            cnt -= c;
+        if (kind == sb::OP_PUSH16 || kind == sb::OP_CHERRY_A16) {
+            const bool push = kind == sb::OP_PUSH16;
+            if (push) { sp += 1; depth = std::max(depth, sp); }
+            if (push && !(i + 1 < n_raw && raw[i + 1] == sb::OP_CHERRY_A16)) {   // push not followed by a cherry
+                emit(sb::OP_PUSH16, 1);
+                ++i;
+                continue;
+            }
+            size_t j = i + (push ? 2 : 1);
+            size_t leaves = 0;
+            while (j < n_raw && raw[j] == sb::OP_LEAF_A16 && leaves < (size_t)sb::OP_MAX_COUNT) { ++j; ++leaves; }
+            emit(push ? sb::OP_PUSH_CHERRY_A16 : sb::OP_CHERRY_A16, leaves);
+            i = j;
+        } else if (kind == sb::OP_CHERRY_B16) {
+            size_t j = i + 1, leaves = 0;
+            while (j < n_raw && raw[j] == sb::RAW_LEAF_B16 && leaves < (size_t)sb::OP_MAX_COUNT) { ++j; ++leaves; }
+            if (j < n_raw && raw[j] == sb::RAW_LEAF_B16) { err = "caterpillar too long for one op"; return false; }
+            const bool merge = j < n_raw && raw[j] == sb::RAW_MERGE_AB16;
+            emit(merge ? sb::OP_CHERRY_B16_MERGE : sb::OP_CHERRY_B16, leaves);
+            i = j + (merge ? 1 : 0);
+        } else if (kind == sb::RAW_LEAF_B16 || kind == sb::RAW_MERGE_AB16) {
+            err = "internal error: B-accumulator step outside a B evaluation";
+            return false;
+        } else {
+            size_t j = i + 1;
+            const bool runs = (kind == sb::OP_LEAF_A16 || kind == sb::OP_LEAF_A32 || kind == sb::OP_MERGE_POP16 ||
+                               kind == sb::OP_MERGE_POP32 || kind == sb::OP_MERGE_POPW);
+            if (runs) while (j < n_raw && raw[j] == kind) ++j;
+            size_t cnt = j - i;
+            if (kind == sb::OP_PUSH32) { sp += 2; depth = std::max(depth, sp); }
+            if (kind == sb::OP_MERGE_POP16 || kind == sb::OP_MERGE_POPW) sp -= (int)cnt;
+            if (kind == sb::OP_MERGE_POP32) sp -= 2 * (int)cnt;
+            while (cnt > 0) {
+                const size_t c = std::min<size_t>(cnt, (size_t)sb::OP_MAX_COUNT);
+                emit(kind, runs ? c : 1);
+                cnt -= c;
+            }
+            i = j;
         }
-        i = j;
     }
     out.ops.push_back((uint16_t)sb::OP_END);
     if (sp != 0) { err = "internal error: unbalanced stack program"; return false; }

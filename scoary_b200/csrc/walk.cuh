@@ -35,7 +35,13 @@
 
 namespace sb {
 
-constexpr int WALK_THREADS = 128;
+#ifndef SB_WALK_THREADS
+#define SB_WALK_THREADS 128
+#endif
+#ifndef SB_WALK_MINBLOCKS
+#define SB_WALK_MINBLOCKS 6
+#endif
+constexpr int WALK_THREADS = SB_WALK_THREADS;
 constexpr int WALK_NEG = -(1 << 30);   // unreachable; keys stay < 2^28 (n_leaves <= 32766), so inv+inv >= INT_MIN
 constexpr uint32_t SHUFFLE_DOMAIN = 0x5C0A27u;
 
@@ -146,9 +152,15 @@ __constant__ uint32_t c_labels[C_LABEL_WORDS];
 // per register, 16-bit keys), legal while the subtree has <= WALK_LIM16 leaves; "32" ops work
 // on the per-gene 32-bit accumulator A32.  The host compiler (engine.cu) switches mode with
 // WIDEN_A and the *W merge forms where a subtree outgrows 16 bits.
-constexpr int OP_END = 0, OP_CHERRY_A16 = 1, OP_CHERRY_B16 = 2, OP_LEAF_A16 = 3, OP_LEAF_B16 = 4, OP_MERGE_AB16 = 5,
-              OP_PUSH16 = 6, OP_MERGE_POP16 = 7, OP_WIDEN_A = 8, OP_LEAF_A32 = 9, OP_MERGE_A32_B16 = 10, OP_PUSH32 = 11,
-              OP_MERGE_POP32 = 12, OP_MERGE_POPW = 13;
+constexpr int OP_END = 0,
+              OP_CHERRY_A16 = 1,        // A16 <- cherry, then `count` leaf updates
+              OP_PUSH_CHERRY_A16 = 2,   // push A16 first, then as OP_CHERRY_A16
+              OP_CHERRY_B16 = 3,        // B16 <- cherry, then `count` leaf updates
+              OP_CHERRY_B16_MERGE = 4,  // as OP_CHERRY_B16, then A16 <- combine(A16, B16)
+              OP_LEAF_A16 = 5, OP_MERGE_POP16 = 6, OP_WIDEN_A = 7, OP_LEAF_A32 = 8, OP_MERGE_A32_B16 = 9,
+              OP_PUSH32 = 10, OP_MERGE_POP32 = 11, OP_MERGE_POPW = 12, OP_PUSH16 = 13;
+// raw (pre-fusion) steps used only by the host compiler
+constexpr int RAW_LEAF_B16 = 14, RAW_MERGE_AB16 = 15;
 constexpr int OP_TYPE_BITS = 4, OP_MAX_COUNT = 4095;
 constexpr int PERMS_PER_ITEM = 4;          // labellings walked per block (one byte of hit flags per gene)
 // 16-bit keys: (pairs << 6) + x with pairs, x <= 63  ->  subtrees of at most 127 leaves.
@@ -396,7 +408,63 @@ __device__ __forceinline__ void walk_tree(const WalkArgs &A, const uint32_t *con
                 SB_DROP_BITS();
             }
             break;
-        case OP_LEAF_B16:
+        case OP_PUSH16:
+        case OP_PUSH_CHERRY_A16:
+#pragma unroll
+            for (int q = 0; q < NPAIR; ++q) {
+                int *s = stk + (sp + q * 10) * T;
+#pragma unroll
+                for (int c = 0; c < 5; ++c) {
+                    s[c * T] = (int)a16[q].p[c];
+                    s[(5 + c) * T] = (int)a16[q].a[c];
+                }
+            }
+            sp += 10 * NPAIR;
+            if (type == OP_PUSH16) break;
+            // fall through
+        case OP_CHERRY_A16: {
+            int t1, t2;
+            unsigned m1[NPAIR], m2[NPAIR];
+            SB_LOAD_BITS(t1);
+#pragma unroll
+            for (int q = 0; q < NPAIR; ++q) m1[q] = SB_PAIR_MASK(q);
+            SB_DROP_BITS();
+            SB_LOAD_BITS(t2);
+#pragma unroll
+            for (int q = 0; q < NPAIR; ++q) m2[q] = SB_PAIR_MASK(q);
+            SB_DROP_BITS();
+            const int tt = t1 * 2 + t2;
+#pragma unroll
+            for (int q = 0; q < NPAIR; ++q) walk_cherry16(a16[q], m1[q], m2[q], tt);
+            for (int i = 0; i < cnt; ++i) {
+                int t;
+                SB_LOAD_BITS(t);
+                if (t) {
+#pragma unroll
+                    for (int q = 0; q < NPAIR; ++q) walk_leaf16<1>(a16[q], SB_PAIR_MASK(q));
+                } else {
+#pragma unroll
+                    for (int q = 0; q < NPAIR; ++q) walk_leaf16<0>(a16[q], SB_PAIR_MASK(q));
+                }
+                SB_DROP_BITS();
+            }
+            break;
+        }
+        case OP_CHERRY_B16:
+        case OP_CHERRY_B16_MERGE: {
+            int t1, t2;
+            unsigned m1[NPAIR], m2[NPAIR];
+            SB_LOAD_BITS(t1);
+#pragma unroll
+            for (int q = 0; q < NPAIR; ++q) m1[q] = SB_PAIR_MASK(q);
+            SB_DROP_BITS();
+            SB_LOAD_BITS(t2);
+#pragma unroll
+            for (int q = 0; q < NPAIR; ++q) m2[q] = SB_PAIR_MASK(q);
+            SB_DROP_BITS();
+            const int tt = t1 * 2 + t2;
+#pragma unroll
+            for (int q = 0; q < NPAIR; ++q) walk_cherry16(b16[q], m1[q], m2[q], tt);
             for (int i = 0; i < cnt; ++i) {
                 int t;
                 SB_LOAD_BITS(t);
@@ -409,45 +477,12 @@ __device__ __forceinline__ void walk_tree(const WalkArgs &A, const uint32_t *con
                 }
                 SB_DROP_BITS();
             }
-            break;
-        case OP_CHERRY_A16:
-        case OP_CHERRY_B16: {
-            int t1, t2;
-            unsigned m1[NPAIR], m2[NPAIR];
-            SB_LOAD_BITS(t1);
+            if (type == OP_CHERRY_B16_MERGE) {
 #pragma unroll
-            for (int q = 0; q < NPAIR; ++q) m1[q] = SB_PAIR_MASK(q);
-            SB_DROP_BITS();
-            SB_LOAD_BITS(t2);
-#pragma unroll
-            for (int q = 0; q < NPAIR; ++q) m2[q] = SB_PAIR_MASK(q);
-            SB_DROP_BITS();
-            const int tt = t1 * 2 + t2;
-            if (type == OP_CHERRY_A16) {
-#pragma unroll
-                for (int q = 0; q < NPAIR; ++q) walk_cherry16(a16[q], m1[q], m2[q], tt);
-            } else {
-#pragma unroll
-                for (int q = 0; q < NPAIR; ++q) walk_cherry16(b16[q], m1[q], m2[q], tt);
+                for (int q = 0; q < NPAIR; ++q) walk_merge16(b16[q], a16[q]);
             }
             break;
         }
-        case OP_MERGE_AB16:
-#pragma unroll
-            for (int q = 0; q < NPAIR; ++q) walk_merge16(b16[q], a16[q]);
-            break;
-        case OP_PUSH16:
-#pragma unroll
-            for (int q = 0; q < NPAIR; ++q) {
-                int *s = stk + (sp + q * 10) * T;
-#pragma unroll
-                for (int c = 0; c < 5; ++c) {
-                    s[c * T] = (int)a16[q].p[c];
-                    s[(5 + c) * T] = (int)a16[q].a[c];
-                }
-            }
-            sp += 10 * NPAIR;
-            break;
         case OP_MERGE_POP16:
             for (int i = 0; i < cnt; ++i) {
                 sp -= 10 * NPAIR;
@@ -602,7 +637,7 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_pairs_kernel(const WalkArgs
 // under each labelling of the block's chunk and writes one byte of hit flags per gene.
 // Blocks are small work items, so the tail of a launch is short, and blocks that run
 // concurrently read the same few label vectors from the constant cache.
-__global__ void __launch_bounds__(WALK_THREADS) walk_permute_kernel(const WalkArgs A)
+__global__ void __launch_bounds__(WALK_THREADS, SB_WALK_MINBLOCKS) walk_permute_kernel(const WalkArgs A)
 {
     extern __shared__ __align__(16) int smem_stack[];
     int *stk = smem_stack + threadIdx.x;
