@@ -395,6 +395,7 @@ __device__ __forceinline__ void walk_tree(const WalkArgs &A, const uint32_t *con
         const int type = op & 15, cnt = op >> OP_TYPE_BITS;
         switch (type) {
         case OP_LEAF_A16:
+#pragma unroll 1
             for (int i = 0; i < cnt; ++i) {
                 int t;
                 SB_LOAD_BITS(t);
@@ -436,6 +437,7 @@ __device__ __forceinline__ void walk_tree(const WalkArgs &A, const uint32_t *con
             const int tt = t1 * 2 + t2;
 #pragma unroll
             for (int q = 0; q < NPAIR; ++q) walk_cherry16(a16[q], m1[q], m2[q], tt);
+#pragma unroll 1
             for (int i = 0; i < cnt; ++i) {
                 int t;
                 SB_LOAD_BITS(t);
@@ -465,6 +467,7 @@ __device__ __forceinline__ void walk_tree(const WalkArgs &A, const uint32_t *con
             const int tt = t1 * 2 + t2;
 #pragma unroll
             for (int q = 0; q < NPAIR; ++q) walk_cherry16(b16[q], m1[q], m2[q], tt);
+#pragma unroll 1
             for (int i = 0; i < cnt; ++i) {
                 int t;
                 SB_LOAD_BITS(t);
@@ -484,6 +487,7 @@ __device__ __forceinline__ void walk_tree(const WalkArgs &A, const uint32_t *con
             break;
         }
         case OP_MERGE_POP16:
+#pragma unroll 1
             for (int i = 0; i < cnt; ++i) {
                 sp -= 10 * NPAIR;
 #pragma unroll
@@ -504,6 +508,7 @@ __device__ __forceinline__ void walk_tree(const WalkArgs &A, const uint32_t *con
             for (int q = 0; q < NPAIR; ++q) walk_widen(a16[q], acc[2 * q], acc[2 * q + 1], scale);
             break;
         case OP_LEAF_A32:
+#pragma unroll 1
             for (int i = 0; i < cnt; ++i) {
                 int t;
                 SB_LOAD_BITS(t);
@@ -539,6 +544,7 @@ __device__ __forceinline__ void walk_tree(const WalkArgs &A, const uint32_t *con
             sp += 10 * NP;
             break;
         case OP_MERGE_POP32:
+#pragma unroll 1
             for (int i = 0; i < cnt; ++i) {
                 sp -= 10 * NP;
 #pragma unroll
@@ -555,6 +561,7 @@ __device__ __forceinline__ void walk_tree(const WalkArgs &A, const uint32_t *con
             }
             break;
         case OP_MERGE_POPW:
+#pragma unroll 1
             for (int i = 0; i < cnt; ++i) {
                 sp -= 10 * NPAIR;
 #pragma unroll
