@@ -303,19 +303,31 @@ def run_ours(a):
     counts_h = np.empty((G, 4), dtype=np.int32)
     bits_host = pinned.numpy().view(np.uint64)
 
+    e2e_trace = []
+
     def step_e2e():
         h2d = d2h = 0
+        t0 = time.perf_counter()
         e.set_genes(bits_host, N)
         h2d += bits_host.nbytes
+        t1 = time.perf_counter()
+        tf = tp = 0.0
         for t in range(T):
             e.set_trait_vector(t, traits[t])
             e.set_tree(t, left, right, leaf_cols)
             h2d += 2 * W * 8 + left.nbytes + right.nbytes + leaf_cols.nbytes
+            ta = time.perf_counter()
             c, p, _ = e.contingency_fisher(t)
             d2h += c.nbytes + p.nbytes
+            tb = time.perf_counter()
             if P > 0:
                 pairs, r, nd = e.permute(t, P, seed=seed)
                 d2h += pairs.nbytes + r.nbytes + nd.nbytes
+            tc = time.perf_counter()
+            tf += tb - ta
+            tp += tc - tb
+        e2e_trace.append({"set_genes_ms": (t1 - t0) * 1e3, "fisher_ms": tf * 1e3, "permute_ms": tp * 1e3,
+                          "total_ms": (time.perf_counter() - t0) * 1e3})
         return h2d, d2h
 
     e.set_stream(0)
@@ -333,6 +345,37 @@ def run_ours(a):
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         e2e_s = float(tmax.item())
     e2e_value = tests_per_step * n_e2e / e2e_s
+
+    # ---- reference-rule mode (second number): the reference's sequential early stop
+    # (methods.py:1360-1363) applied between growing slices of permutations
+    ref_rule = None
+    if P >= 32:
+        from scoary_b200.methods import early_stop_table
+        e.set_stream(stream.cuda_stream)
+        e.set_genes_device(d_bits.data_ptr(), G, N, W)
+        for t in range(T):
+            e.set_trait_vector(t, traits[t])
+            e.set_tree(t, left, right, leaf_cols)
+        d_rmin = torch.from_numpy(early_stop_table(P)).to(dev)
+        def step_rule():
+            for t in range(T):
+                e.permute_device(t, G, P, seed, d_pairs[t].data_ptr(), d_r[t].data_ptr(), d_nd[t].data_ptr(),
+                                 early_stop=True, rmin_ptr=d_rmin.data_ptr())
+        step_rule()
+        torch.cuda.synchronize()
+        e.stats_reset()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        step_rule()
+        r1.record()
+        torch.cuda.synchronize()
+        rule_ms = r0.elapsed_time(r1)
+        walks = e.stats()["tests_walks"]
+        nd = d_nd.cpu().numpy()
+        ref_rule = {"ms_per_step": rule_ms, "walks_executed": int(walks), "walks_exhaustive": int(G * T * (1 + P)),
+                    "genes_stopped_early": int((nd < P).sum()), "genes": int(G * T),
+                    "equivalent_tests_per_s": G * T * (1 + P) / (rule_ms * 1e-3),
+                    "note": "Permute's early stop on; pairwise walk + permutations only (no Fisher pass)"}
 
     # ---- Fisher-only pass (BASELINE configs[1] shape of work), device resident
     e.set_stream(stream.cuda_stream)
@@ -416,10 +459,10 @@ def run_ours(a):
                    "l2": "256 MiB buffer written between timed steps (inputs ~65 MB < 126 MB L2)",
                    "tests_per_step": tests_per_step, "seed": seed},
         "e2e": {"value": e2e_value, "unit": "tests/s", "h2d_bytes_per_step": int(h2d_b), "d2h_bytes_per_step": int(d2h_b),
-                "ms_per_step": e2e_s / n_e2e * 1e3},
+                "ms_per_step": e2e_s / n_e2e * 1e3, "calls_ms": e2e_trace[-1]},
         "gpu_launches": int(st["kernel_launches"]),
         "clocks": clocks,
-        "roofline": roofline, "roofline_int32": roofline_int, "fisher_pass": fisher,
+        "roofline": roofline, "roofline_int32": roofline_int, "fisher_pass": fisher, "reference_rule_mode": ref_rule,
         "cpu_baseline": cpu,
         "kernel_ms": {k: st[k] for k in ("ms_fisher", "ms_shuffle", "ms_walk", "ms_permute", "ms_reduce")},
         "wall_s_timed_region": wall,

@@ -71,8 +71,9 @@ struct sb_ctx {
     int32_t lut_n = -1;
     TraitSlot traits[SB_MAX_TRAITS];
     // scratch
-    void *d_scratch[8] = {nullptr};
-    size_t scratch_bytes[8] = {0};
+    void *d_scratch[12] = {nullptr};
+    size_t scratch_bytes[12] = {0};
+    int32_t *h_pinned_counter = nullptr;
     // stats / profiling
     sb_stats_t stats;
     bool profiling = false;
@@ -492,7 +493,7 @@ size_t walk_smem_bytes(const TraitSlot &s)
 void fill_walk_args(const TraitSlot &s, sb::WalkArgs &A, const int64_t *d_gene_idx, int64_t S)
 {
     memset(&A, 0, sizeof A);
-    A.genesT = s.d_genesT; A.Gs = s.Gs; A.gene_idx = d_gene_idx; A.S = S;
+    A.genesT = s.d_genesT; A.Gs = s.Gs; A.gene_idx = d_gene_idx; A.S = S; A.S_total = S; A.slot_idx = nullptr;
     A.W32p = s.W32p; A.shift = s.shift;
 }
 
@@ -569,33 +570,72 @@ int launch_permute(sb_ctx *ctx, int32_t t, const int64_t *d_gene_idx, int64_t S,
     if (smem > (size_t)ctx->max_smem_optin) return fail(ctx, SB_ERR_ARG, "tree too deep for shared memory");
     SB_CUDA(ctx, cudaFuncSetAttribute(sb::walk_permute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t per_block = (int64_t)sb::WALK_THREADS * sb::WALK_NP;
-    const int64_t tiles = (S + per_block - 1) / per_block;
-    for (int l = 0; l < n_launches; ++l) {
-        const int base = l * perms_per_launch;
-        const int n_perms = std::min(perms_per_launch, P - base);
+    auto launch_slice = [&](int base, int n_perms, const int32_t *d_list, int64_t n_slots) -> int {
         SB_CUDA(ctx, cudaMemcpyToSymbolAsync(sb::c_labels, d_labelsW + (size_t)base * s.W32p,
                                              sizeof(uint32_t) * (size_t)n_perms * s.W32p, 0, cudaMemcpyDeviceToDevice,
                                              ctx->stream));
         sb::WalkArgs A;
-        fill_walk_args(s, A, d_gene_idx, S);
+        fill_walk_args(s, A, d_gene_idx, n_slots);
+        A.S_total = S;
+        A.slot_idx = d_list;
         A.n_perms = n_perms;
         A.items_per_tile = (n_perms + ppi - 1) / ppi;
         A.chunk_base = base / ppi;
         A.unperm = d_unperm;
         A.hits = d_hits;
+        const int64_t tiles = (n_slots + per_block - 1) / per_block;
         dim3 grid((unsigned)tiles, (unsigned)A.items_per_tile, 1);
         Timed tm(ctx, CAT_PERMUTE);
         sb::walk_permute_kernel<<<grid, sb::WALK_THREADS, smem, ctx->stream>>>(A);
         ctx->stats.kernel_launches += 1;
+        ctx->stats.tests_walks += n_slots * (int64_t)n_perms;
         SB_CUDA(ctx, cudaGetLastError());
-    }
-    ctx->stats.tests_walks += S * (int64_t)P;
-    {
+        return SB_OK;
+    };
+    if (!early_stop) {
+        for (int l = 0; l < n_launches; ++l) {
+            const int base = l * perms_per_launch;
+            rc = launch_slice(base, std::min(perms_per_launch, P - base), nullptr, S);
+            if (rc) return rc;
+        }
         Timed tm(ctx, CAT_REDUCE);
-        sb::reduce_hits_kernel<<<(unsigned)((S + 255) / 256), 256, 0, ctx->stream>>>(d_hits, S, n_chunks, P, early_stop, d_rmin,
-                                                                                    d_r, d_n_done);
+        sb::reduce_hits_kernel<<<(unsigned)((S + 255) / 256), 256, 0, ctx->stream>>>(d_hits, S, n_chunks, P, 0, d_rmin, d_r,
+                                                                                    d_n_done);
         ctx->stats.kernel_launches += 1;
         SB_CUDA(ctx, cudaGetLastError());
+        return SB_OK;
+    }
+    // Reference-rule mode: walk the permutations in growing slices and keep only the genes the
+    // sequential rule has not stopped yet (most null genes stop after 31 permutations).
+    rc = ensure_scratch(ctx, 8, sizeof(int32_t) * (2 * (size_t)S + 4));
+    if (rc) return rc;
+    int32_t *d_list[2] = {(int32_t *)ctx->d_scratch[8], (int32_t *)ctx->d_scratch[8] + S};
+    int32_t *d_counter = (int32_t *)ctx->d_scratch[8] + 2 * S;
+    if (!ctx->h_pinned_counter) SB_CUDA(ctx, cudaMallocHost(&ctx->h_pinned_counter, sizeof(int32_t)));
+    int64_t n_alive = S;
+    const int32_t *cur = nullptr;   // null = identity list
+    int base = 0, round = 0;
+    while (base < P && n_alive > 0) {
+        int n_perms = (round < 2) ? 32 : perms_per_launch;
+        n_perms = std::min(std::min(n_perms, perms_per_launch), P - base);
+        rc = launch_slice(base, n_perms, cur, n_alive);
+        if (rc) return rc;
+        int32_t *out = d_list[round & 1];
+        SB_CUDA(ctx, cudaMemsetAsync(d_counter, 0, sizeof(int32_t), ctx->stream));
+        {
+            Timed tm(ctx, CAT_REDUCE);
+            sb::advance_hits_kernel<<<(unsigned)((n_alive + 255) / 256), 256, 0, ctx->stream>>>(
+                d_hits, S, cur, (int32_t)n_alive, base, n_perms, P, d_rmin, d_r, d_n_done, out, d_counter);
+            ctx->stats.kernel_launches += 1;
+            SB_CUDA(ctx, cudaGetLastError());
+        }
+        SB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned_counter, d_counter, sizeof(int32_t), cudaMemcpyDeviceToHost,
+                                     ctx->stream));
+        SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        n_alive = *ctx->h_pinned_counter;
+        cur = out;
+        base += n_perms;
+        ++round;
     }
     return SB_OK;
 }
@@ -663,6 +703,7 @@ void sb_destroy(sb_ctx *ctx)
     cudaFree(ctx->d_lut);
     cudaFree(ctx->d_peak_out);
     for (auto p : ctx->d_scratch) cudaFree(p);
+    if (ctx->h_pinned_counter) cudaFreeHost(ctx->h_pinned_counter);
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }

@@ -332,8 +332,10 @@ __device__ __forceinline__ void walk_widen(const WalkState16 &s, WalkState &g0, 
 struct WalkArgs {
     const uint32_t *genesT;    // [W32p][Gs]
     int64_t Gs;
-    const int64_t *gene_idx;   // [S] or null (identity)
-    int64_t S;
+    const int64_t *gene_idx;   // [S_total] or null (identity): gene row of result slot s
+    const int32_t *slot_idx;   // [S] or null (identity): result slots still being walked (early-stop rounds)
+    int64_t S;                 // slots walked by this launch
+    int64_t S_total;           // result slots of the call (row stride of `hits`)
     int32_t W32p;
     int32_t shift;             // SH
     int32_t n_perms;           // labellings in constant memory for this launch (permute mode)
@@ -610,9 +612,11 @@ __device__ __forceinline__ void walk_slots(const WalkArgs &A, int tile, int64_t 
 {
 #pragma unroll
     for (int k = 0; k < NP; ++k) {
-        s_idx[k] = ((int64_t)tile * NP + k) * WALK_THREADS + threadIdx.x;
-        active[k] = s_idx[k] < A.S;
-        sc[k] = active[k] ? s_idx[k] : (A.S - 1);   // idle slots redo the last gene (no divergence)
+        const int64_t li = ((int64_t)tile * NP + k) * WALK_THREADS + threadIdx.x;   // position in the work list
+        active[k] = li < A.S;
+        const int64_t lc = active[k] ? li : (A.S - 1);   // idle lanes redo the last entry (no divergence)
+        s_idx[k] = A.slot_idx ? (int64_t)A.slot_idx[lc] : lc;
+        sc[k] = s_idx[k];
         const int64_t gene = A.gene_idx ? A.gene_idx[sc[k]] : sc[k];
         gcol[k] = A.genesT + gene;
     }
@@ -676,7 +680,7 @@ __global__ void __launch_bounds__(WALK_THREADS, SB_WALK_MINBLOCKS) walk_permute_
     }
 #pragma unroll
     for (int k = 0; k < NP; ++k)
-        if (active[k]) A.hits[(int64_t)(A.chunk_base + chunk) * A.S + s_idx[k]] = (uint8_t)hits[k];
+        if (active[k]) A.hits[(int64_t)(A.chunk_base + chunk) * A.S_total + s_idx[k]] = (uint8_t)hits[k];
 }
 
 // ---------------------------------------------------------------- hit-sequence reduction
@@ -711,6 +715,36 @@ __global__ void __launch_bounds__(256) reduce_hits_kernel(const uint8_t *__restr
     }
     r_out[s] = r;
     n_done[s] = done;
+}
+
+// Early-stop rounds: after a slice of permutations [base, base + n) has been walked for the
+// slots in list_in, apply Permute's sequential rule (methods.py:1348-1365) to each of them;
+// slots that neither stopped nor reached P are appended to list_out for the next slice.
+__global__ void __launch_bounds__(256) advance_hits_kernel(const uint8_t *__restrict__ hits, int64_t S_total,
+                                                           const int32_t *__restrict__ list_in, int32_t n_in, int base,
+                                                           int n, int P, const int32_t *__restrict__ rmin,
+                                                           int32_t *__restrict__ r_arr, int32_t *__restrict__ n_done,
+                                                           int32_t *__restrict__ list_out, int32_t *__restrict__ counter)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_in) return;
+    const int slot = list_in ? list_in[e] : e;
+    int r = (base == 0) ? 0 : r_arr[slot];
+    for (int i = base; i < base + n; ++i) {
+        const uint32_t byte = hits[(int64_t)(i / PERMS_PER_ITEM) * S_total + slot];
+        r += (byte >> (i % PERMS_PER_ITEM)) & 1u;
+        if (i >= 30 && r >= rmin[i]) {   // methods.py:1360-1363
+            r_arr[slot] = r;
+            n_done[slot] = i + 1;
+            return;
+        }
+    }
+    r_arr[slot] = r;
+    if (base + n >= P) {
+        n_done[slot] = P;
+    } else {
+        list_out[atomicAdd(counter, 1)] = slot;
+    }
 }
 
 // ---------------------------------------------------------------- int32 pipe microbenchmark

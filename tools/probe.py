@@ -34,3 +34,23 @@ for rep in range(2):
     print("rep %d: fisher wall %.3fs, permute wall %.3fs; K5 %.1f ms -> %.3e walks/s" % (
         rep, t1 - t0, t2 - t1, st["ms_permute"], walks / (st["ms_permute"] * 1e-3)))
 print("pairs head", pairs[:3].tolist(), "r head", r[:12].tolist(), "p head", p[:3].tolist())
+
+# ---- e2e call breakdown (host buffers)
+import time as _t
+def tm(label, fn):
+    t0 = _t.perf_counter(); r = fn(); e.synchronize(); print("  %-28s %8.2f ms" % (label, (_t.perf_counter() - t0) * 1e3)); return r
+from scoary_b200 import tree as treemod
+left, right, leaf_names = treemod.flatten(nested)
+leaf_cols = np.asarray([col[n] for n in leaf_names], dtype=np.int32)
+for rep in range(2):
+    print("e2e breakdown rep", rep)
+    tm("set_genes", lambda: e.set_genes(bits, a.isolates))
+    tm("set_trait_vector", lambda: e.set_trait_vector(0, traits[0]))
+    tm("set_tree", lambda: e.set_tree(0, left, right, leaf_cols))
+    tm("contingency_fisher", lambda: e.contingency_fisher(0))
+    tm("permute(P=%d)" % a.perms, lambda: e.permute(0, a.perms, seed=1))
+    from scoary_b200.methods import early_stop_table
+    rm = early_stop_table(a.perms)
+    e.stats_reset()
+    out = tm("permute early_stop", lambda: e.permute(0, a.perms, seed=1, early_stop=True, rmin=rm))
+    print("   walks executed", e.stats()["tests_walks"], "of", a.genes * (a.perms + 1), "; stopped early:", int((out[2] < a.perms).sum()))
