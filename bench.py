@@ -182,7 +182,7 @@ def run_reference(a):
         "e2e": {"value": value, "unit": "tests/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -393,6 +393,7 @@ def run_ours(a):
 
     if rank != 0:
         if world > 1:
+            dist.barrier()              # stay in the group until rank 0 has printed its line
             dist.destroy_process_group()
         return
 
@@ -467,8 +468,9 @@ def run_ours(a):
         "kernel_ms": {k: st[k] for k in ("ms_fisher", "ms_shuffle", "ms_walk", "ms_permute", "ms_reduce")},
         "wall_s_timed_region": wall,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
