@@ -158,6 +158,15 @@ int sb_permute_device(sb_ctx *ctx, int32_t t, const int64_t *d_gene_idx, int64_t
  * labels uint8[P][n_leaves] (host). */
 int sb_debug_shuffled_labels(sb_ctx *ctx, int32_t t, int32_t P, uint64_t seed, uint8_t *labels);
 
+/* ---- tree construction ------------------------- */
+/* UPGMA tree of the N isolates from the gene bitset set with sb_set_genes*: relative Hamming
+ * distances over the variable genes (CreateTriangularDistanceMatrix, methods.py:619-644),
+ * then upgma (methods.py:667-707) with the QuadTree's argmin tie-break (classes.py:155-196).
+ * merges int32[N-1][2]: step s joins clusters (i, j); the joined cluster keeps index i
+ * (methods.py:700-703), so the host rebuilds the nested list with
+ * cluster[i] = [cluster[i], cluster[j]].  The merge order is identical to the reference's. */
+int sb_upgma(sb_ctx *ctx, int32_t *merges);
+
 /* Integer-pipe microbenchmark used for the walk kernels' roofline denominator:
  * runs `iters` rounds of dependent add/max chains on every SM and returns the
  * measured int32 add+max operations per second. */

@@ -61,6 +61,7 @@ SIGNATURES = {
                                          ctypes.c_uint64, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
                                          ctypes.c_void_p, ctypes.c_void_p]),
     "sb_debug_shuffled_labels": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_uint64, ctypes.c_void_p]),
+    "sb_upgma": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "sb_int32_peak": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_double)]),
 }
 

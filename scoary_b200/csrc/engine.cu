@@ -22,6 +22,7 @@
 #include "../../include/scoary_b200.h"
 #include "fisher.cuh"
 #include "walk.cuh"
+#include "tree_build.cuh"
 
 extern "C" void sb_build_logfact_dd(int32_t n, double *hi_lo);
 
@@ -29,7 +30,7 @@ namespace {
 
 std::string g_create_error;
 
-enum Cat { CAT_PACK = 0, CAT_FISHER, CAT_SHUFFLE, CAT_WALK, CAT_PERMUTE, CAT_REDUCE, CAT_N };
+enum Cat { CAT_PACK = 0, CAT_FISHER, CAT_SHUFFLE, CAT_WALK, CAT_PERMUTE, CAT_REDUCE, CAT_TREE, CAT_N };
 
 struct TimedEvent {
     cudaEvent_t start, stop;
@@ -153,6 +154,7 @@ void resolve_events(sb_ctx *ctx)
             case CAT_WALK: ctx->stats.ms_walk += ms; break;
             case CAT_PERMUTE: ctx->stats.ms_permute += ms; ctx->stats.launches_permute += 1; break;
             case CAT_REDUCE: ctx->stats.ms_reduce += ms; break;
+            case CAT_TREE: ctx->stats.ms_pack += ms; break;   // tree construction is accounted with packing
         }
         ctx->free_events.push_back(e);
     }
@@ -1004,6 +1006,78 @@ int sb_debug_shuffled_labels(sb_ctx *ctx, int32_t t, int32_t P, uint64_t seed, u
     if (rc) return rc;
     SB_CUDA(ctx, cudaMemcpyAsync(labels, ctx->d_scratch[7], (size_t)P * s.n_leaves, cudaMemcpyDeviceToHost, ctx->stream));
     SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SB_OK;
+}
+
+int sb_upgma(sb_ctx *ctx, int32_t *merges)
+{
+    if (!ctx || !merges) return SB_ERR_ARG;
+    SB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->d_genes) return fail(ctx, SB_ERR_STATE, "genes not set (sb_set_genes)");
+    const int N = ctx->N, W = ctx->W;
+    const int64_t G = ctx->G;
+    if (N < 2) return fail(ctx, SB_ERR_ARG, "need at least two isolates to build a tree");
+    if (N > 32766) return fail(ctx, SB_ERR_ARG, "sb_upgma: at most 32766 isolates");
+    const int64_t Gw = (G + 63) / 64;
+    // device buffers (freed on exit; tree building runs once per data set)
+    uint64_t *d_T = nullptr, *d_allowed = nullptr;
+    unsigned long long *d_nvar = nullptr;
+    sb::UpgmaState S;
+    memset(&S, 0, sizeof S);
+    S.N = N;
+    std::vector<uint64_t> h_allowed(W, 0);
+    for (int j = 0; j < N; ++j) h_allowed[j >> 6] |= 1ULL << (j & 63);
+    auto cleanup = [&]() {
+        cudaFree(d_T); cudaFree(d_allowed); cudaFree(d_nvar); cudaFree(S.D); cudaFree(S.rowmin_val); cudaFree(S.rowmin_col);
+        cudaFree(S.size); cudaFree(S.alive); cudaFree(S.redo); cudaFree(S.pick); cudaFree(S.merges);
+    };
+#define SB_TRY(call)                                                \
+    do {                                                            \
+        cudaError_t e__ = (call);                                   \
+        if (e__ != cudaSuccess) {                                   \
+            cleanup();                                              \
+            ctx->err = std::string(#call) + " failed: " + cudaGetErrorString(e__); \
+            return SB_ERR_CUDA;                                     \
+        }                                                           \
+    } while (0)
+    SB_TRY(cudaMalloc(&d_T, sizeof(uint64_t) * (size_t)N * (size_t)Gw));
+    SB_TRY(cudaMalloc(&d_allowed, sizeof(uint64_t) * W));
+    SB_TRY(cudaMalloc(&d_nvar, sizeof(unsigned long long)));
+    SB_TRY(cudaMalloc(&S.D, sizeof(double) * (size_t)N * (size_t)N));
+    SB_TRY(cudaMalloc(&S.rowmin_val, sizeof(double) * N));
+    SB_TRY(cudaMalloc(&S.rowmin_col, sizeof(int) * N));
+    SB_TRY(cudaMalloc(&S.size, sizeof(double) * N));
+    SB_TRY(cudaMalloc(&S.alive, N));
+    SB_TRY(cudaMalloc(&S.redo, N));
+    SB_TRY(cudaMalloc(&S.pick, sizeof(int) * 2));
+    SB_TRY(cudaMalloc(&S.merges, sizeof(int) * 2 * (size_t)(N - 1)));
+    SB_TRY(cudaMemcpyAsync(d_allowed, h_allowed.data(), sizeof(uint64_t) * W, cudaMemcpyHostToDevice, ctx->stream));
+    SB_TRY(cudaMemsetAsync(d_nvar, 0, sizeof(unsigned long long), ctx->stream));
+    std::vector<double> ones(N, 1.0);
+    SB_TRY(cudaMemcpyAsync(S.size, ones.data(), sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
+    SB_TRY(cudaMemsetAsync(S.alive, 1, N, ctx->stream));
+    {
+        Timed tm(ctx, CAT_TREE);
+        dim3 g1((unsigned)Gw, (unsigned)((W + 3) / 4), 1);
+        sb::transpose_variable_kernel<<<g1, 256, 0, ctx->stream>>>(ctx->d_genes, G, W, N, d_allowed, N, Gw, d_T, d_nvar);
+        const unsigned tiles = (unsigned)((N + 31) / 32);
+        sb::hamming_kernel<<<dim3(tiles, tiles, 1), dim3(32, 32, 1), 0, ctx->stream>>>(d_T, N, Gw, d_nvar, d_allowed, S.D);
+        sb::upgma_rowmin_all_kernel<<<N, 256, 0, ctx->stream>>>(S);
+        ctx->stats.kernel_launches += 3;
+        for (int step = 0; step < N - 1; ++step) {
+            sb::upgma_pick_kernel<<<1, 1024, 0, ctx->stream>>>(S, step);
+            sb::upgma_update_kernel<<<(N + 255) / 256, 256, 0, ctx->stream>>>(S);
+            sb::upgma_redo_kernel<<<N, 256, 0, ctx->stream>>>(S);
+            sb::upgma_finish_step_kernel<<<1, 1, 0, ctx->stream>>>(S);
+        }
+        ctx->stats.kernel_launches += 4LL * (N - 1);
+    }
+    SB_TRY(cudaGetLastError());
+    SB_TRY(cudaMemcpyAsync(merges, S.merges, sizeof(int) * 2 * (size_t)(N - 1), cudaMemcpyDeviceToHost, ctx->stream));
+    SB_TRY(cudaStreamSynchronize(ctx->stream));
+#undef SB_TRY
+    ctx->stats.d2h_bytes += (int64_t)sizeof(int) * 2 * (N - 1);
+    cleanup();
     return SB_OK;
 }
 

@@ -154,6 +154,13 @@ class Engine:
         self.set_tree(t, left, right, cols)
         return names
 
+    # -- tree construction
+    def upgma(self):
+        """UPGMA merge list int32 [N-1][2] over the isolates of the current gene bitset."""
+        merges = np.empty((self.N - 1, 2), dtype=np.int32)
+        self._check(self._lib.sb_upgma(self._ctx, _ptr(merges)))
+        return merges
+
     # -- hot path, host buffers
     def contingency_fisher(self, t, want_p=True, want_hash=False):
         G = self.G

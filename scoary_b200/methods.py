@@ -252,64 +252,16 @@ def Csv_to_dic(csvfile, delimiter, allowed_isolates, strains):
 
 
 # ============================================================================ tree building (host; off the hot path)
-def _morton_key(i, j, bits):
-    key = np.zeros(i.shape, dtype=np.int64)
-    for b in range(bits - 1, -1, -1):
-        key = (key << 2) | (((i >> b) & 1) << 1) | ((j >> b) & 1)
-    return key
-
-
-def upgma_from_matrix(zero_ones_matrix, strainnames):
-    """UPGMA on relative Hamming distances, reproducing the reference's pipeline
-    CreateTriangularDistanceMatrix -> PopulateQuadTreeWithDistances -> upgma
-    (scoary/methods.py:619-707, classes.QuadTree :97-196) including its argmin
-    tie-break: the QuadTree descends from the coarsest level choosing the smallest
-    (value, i, j) in each quad, i.e. the minimum cell with the smallest
-    bit-interleaved (i, j).  Distances: #differing variable genes / #variable genes;
-    the diagonal is 1; retired rows are sys.maxsize; the merged cluster keeps index i
-    and sees retired clusters at distance 1."""
-    m = np.asarray(zero_ones_matrix, dtype=np.float32)
-    n = m.shape[0]
-    if n < 2:
+def upgma(table):
+    """UPGMA tree (nested lists of isolate names) of the isolates of a GeneTable, built on the
+    GPU (sb_upgma): relative Hamming distances over the variable genes, then the reference's
+    merge order -- CreateTriangularDistanceMatrix -> PopulateQuadTreeWithDistances -> upgma
+    (scoary/methods.py:619-707) with the QuadTree argmin tie-break (classes.py:155-196)."""
+    if len(table.strains) < 2:
         sys.exit("Need at least two isolates to build a tree")
-    ngenes = max(m.shape[1], 1)
-    diff = m @ (1.0 - m).T
-    diff = np.rint(diff + diff.T)
-    big = float(sys.maxsize)
-    d = diff.astype(np.float64) / float(ngenes)
-    np.fill_diagonal(d, 1.0)
-    levels, k = 0, n + (n % 2)
-    while k > 1:
-        k += k % 2
-        levels += 1
-        k = (k + 1) // 2
-    cluster = list(strainnames)
-    size = np.ones(n, dtype=np.float64)
-    alive = np.ones(n, dtype=bool)
-    new_cluster = None
-    for _ in range(n - 1):
-        dmin = d.min()
-        ii, jj = np.nonzero(d == dmin)
-        if len(ii) > 1:
-            k = int(np.argmin(_morton_key(ii, jj, levels)))
-            i, j = int(ii[k]), int(jj[k])
-        else:
-            i, j = int(ii[0]), int(jj[0])
-        new_cluster = [cluster[i], cluster[j]]
-        new_size = size[i] + size[j]
-        nd = (d[i] * size[i] + d[j] * size[j]) / new_size
-        nd[~alive] = 1.0
-        nd[i] = big
-        d[i, :] = nd
-        d[:, i] = nd
-        d[j, :] = big
-        d[:, j] = big
-        cluster[i] = new_cluster
-        cluster[j] = None
-        size[i] = new_size
-        size[j] = 0
-        alive[j] = False
-    return new_cluster
+    e = get_engine()
+    e.set_genes(eng.pack_rows(table.matrix), len(table.strains))
+    return treemod.from_merges(table.strains, e.upgma())
 
 
 def PruneForMissing(tree, Prunedic):
@@ -850,7 +802,7 @@ def main(**kwargs):
             if args.newicktree is None and not args.no_pairwise:
                 log.info("Creating Hamming distance matrix based on gene presence/absence")
                 log.info("Building UPGMA tree from distance matrix")
-                upgmatree = upgma_from_matrix(parsed["Zero_ones_matrix"], strains)
+                upgmatree = upgma(genedic)
             elif args.no_pairwise:
                 log.info("Ignoring relatedness among input sample and performing only population structure-naive "
                          "analysis.")

@@ -164,6 +164,19 @@ def from_scoary_newick(text):
     return root
 
 
+def from_merges(names, merges):
+    """UPGMA merge list [(i, j), ...] -> nested lists: the joined cluster keeps index i
+    (scoary/methods.py:683,700-703)."""
+    cluster = list(names)
+    new = None
+    for i, j in merges:
+        i, j = int(i), int(j)
+        new = [cluster[i], cluster[j]]
+        cluster[i] = new
+        cluster[j] = None
+    return new
+
+
 def random_join_tree(names, rng):
     """Seeded random-join (coalescent-shaped) binary tree used for the synthetic
     workloads with N >= 2000; rng is a numpy Generator."""

@@ -24,6 +24,9 @@ class FakeEngine:
     def set_tree(self, t, left, right, leaf_to_col):
         self.trees[t] = (np.asarray(left), np.asarray(right), np.asarray(leaf_to_col))
 
+    def upgma(self):
+        return O.upgma_merges(self.m)
+
     def contingency_fisher(self, t, want_p=True, want_hash=False):
         counts = O.contingency(self.m, self.traits[t])
         p = O.fisher_scipy(counts) if want_p else None

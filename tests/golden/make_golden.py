@@ -17,6 +17,7 @@ Fixtures written:
        collapse    every gene with --collapse (-p 1.0)
        perm        -e 200 -c I EPW -p 0.05 0.05 with random.seed(1): Empirical_p (statistical pin only)
   walks.json       random trees x gene-trait combinations -> reference ConvertUPGMAtoPhyloTree
+  upgma.json       random presence matrices -> reference CreateTriangularDistanceMatrix/QuadTree/upgma tree
   fisher.json      2x2 tables -> scipy.stats.fisher_exact as the reference calls it (methods.py:854)
   tetrcg_first_row.json   the reference's own CI golden (tests/test_scoary_output.py:12-14)
 """
@@ -126,6 +127,26 @@ def main():
                      "odds": None if not np.isfinite(odds) else float(odds).hex()})
     with open(os.path.join(HERE, "fisher.json"), "w") as fh:
         json.dump({"scipy": __import__("scipy").__version__, "tables": tabs}, fh, separators=(",", ":"))
+    # ---- tree construction: reference upgma on random matrices (many tied distances)
+    upg = []
+    nrng = np.random.default_rng(77)
+    for it in range(60):
+        n = int(nrng.choice([2, 3, 4, 5, 8, 13, 16, 17, 31, 40]))
+        g = int(nrng.choice([3, 8, 30, 200]))
+        mat = (nrng.random((g, n)) < nrng.uniform(0.1, 0.9)).astype(int)
+        if it % 4 == 0 and n > 3:
+            mat[:, 1] = mat[:, 0]
+            mat[:, n - 1] = mat[:, 0]
+        var = [row for row in mat.tolist() if 0 < sum(row) < n]
+        if not var:
+            continue
+        names = ["s%d" % k for k in range(n)]
+        zom = list(map(list, zip(*var)))                      # isolates x variable genes (methods.py:502)
+        tdm = m.CreateTriangularDistanceMatrix(zom, names)
+        tree = m.upgma(m.PopulateQuadTreeWithDistances(tdm))
+        upg.append({"matrix": mat.tolist(), "tree": tree})
+    with open(os.path.join(HERE, "upgma.json"), "w") as fh:
+        json.dump(upg, fh, separators=(",", ":"))
     # ---- the reference's own CI golden row
     with open(os.path.join(HERE, "tetrcg_first_row.json"), "w") as fh:
         json.dump({"source": "tests/test_scoary_output.py:12-14",

@@ -167,3 +167,40 @@ def test_errors_are_reported(engine):
         engine.pairwise(7)                           # no tree for slot 7
     with pytest.raises(EngineError):                 # not children-before-parents
         engine.set_tree(0, [1, ~0], [~1, ~2], [0, 1, 2])
+
+
+@pytest.mark.parametrize("G,N,seed", [(300, 17, 1), (2000, 100, 2), (5000, 333, 3), (64, 2, 4), (1000, 65, 5)])
+def test_upgma_merge_order_matches_restatement(engine, G, N, seed):
+    """GPU tree construction == the reference's merge order (oracle restatement,
+    itself pinned on ExampleTree.nwk), including ties: small N and few genes give many equal distances."""
+    rng = np.random.default_rng(seed)
+    m = (rng.random((G, N)) < rng.uniform(0.05, 0.95, size=(G, 1))).astype(np.uint8)
+    if seed == 1:
+        m[:, 5] = m[:, 3]          # identical isolates -> distance 0 ties
+        m[:, 9] = m[:, 3]
+    engine.set_genes(eng.pack_rows(m), N)
+    got = engine.upgma()
+    assert np.array_equal(got, O.upgma_merges(m))
+
+
+def test_upgma_example_tree(engine):
+    """the reference's golden tree (exampledata/ExampleTree.nwk), byte for byte, from the GPU"""
+    import gzip, os
+    from scoary_b200 import methods as M
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "inputs")
+    with gzip.open(os.path.join(gold, "Gene_presence_absence.csv.gz"), "rt") as fh:
+        table = M.Csv_to_dic_Roary(fh, ",", [], startcol=14)["Roarydic"]
+    engine.set_genes(eng.pack_rows(table.matrix), len(table.strains))
+    tree = treemod.from_merges(table.strains, engine.upgma())
+    assert treemod.to_scoary_newick(tree) == open(os.path.join(gold, "ExampleTree.nwk")).read().strip()
+
+
+def test_upgma_matches_reference_golden(engine):
+    """GPU tree construction against trees built by the unmodified reference (tests/golden/upgma.json)."""
+    import json, os
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "upgma.json")
+    for u in json.load(open(gold)):
+        mat = np.asarray(u["matrix"], dtype=np.uint8)
+        names = ["s%d" % k for k in range(mat.shape[1])]
+        engine.set_genes(eng.pack_rows(mat), mat.shape[1])
+        assert treemod.from_merges(names, engine.upgma()) == u["tree"]

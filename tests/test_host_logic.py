@@ -95,10 +95,13 @@ def test_first_row_is_the_reference_ci_golden(inputs, fake_engine):
     assert abs(float(d[16]) - ref[16]) <= 1e-9 and abs(float(d[17]) - ref[17]) <= 1e-7
 
 
-def test_upgma_reproduces_example_tree(inputs):
+def test_upgma_restatement_reproduces_example_tree(inputs):
+    """the oracle's UPGMA restatement is pinned by the reference's own ExampleTree.nwk"""
+    from oracle import oracle as O
     with open(inputs["g"]) as fh:
         parsed = M.Csv_to_dic_Roary(fh, ",", [], startcol=14)
-    tree = M.upgma_from_matrix(parsed["Zero_ones_matrix"], parsed["Strains"])
+    table = parsed["Roarydic"]
+    tree = treemod.from_merges(table.strains, O.upgma_merges(table.matrix))
     assert treemod.to_scoary_newick(tree) == open(inputs["n"]).read().strip()
 
 

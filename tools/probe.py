@@ -54,3 +54,9 @@ for rep in range(2):
     e.stats_reset()
     out = tm("permute early_stop", lambda: e.permute(0, a.perms, seed=1, early_stop=True, rmin=rm))
     print("   walks executed", e.stats()["tests_walks"], "of", a.genes * (a.perms + 1), "; stopped early:", int((out[2] < a.perms).sum()))
+
+# ---- GPU tree construction timing
+e.set_genes(bits, a.isolates)
+for rep in range(2):
+    merges = tm("upgma (N=%d, G=%d)" % (a.isolates, a.genes), lambda: e.upgma())
+print("first merges", merges[:3].tolist())
