@@ -487,9 +487,10 @@ int launch_fisher(sb_ctx *ctx, int32_t t, int32_t *d_counts, double *d_p, uint64
     return SB_OK;
 }
 
-size_t walk_smem_bytes(const TraitSlot &s)
+// DP stack: s.depth units per gene pair; a unit is 10 words with both passes (K4), 5 with one (K5)
+size_t walk_smem_bytes(const TraitSlot &s, bool dual)
 {
-    return sizeof(int) * 10 * (size_t)std::max(1, s.depth) * sb::WALK_THREADS * sb::WALK_NPAIR;
+    return sizeof(int) * (dual ? 10 : 5) * (size_t)std::max(1, s.depth) * sb::WALK_THREADS * sb::WALK_NPAIR;
 }
 
 void fill_walk_args(const TraitSlot &s, sb::WalkArgs &A, const int64_t *d_gene_idx, int64_t S)
@@ -519,7 +520,7 @@ int launch_pairwise(sb_ctx *ctx, int32_t t, const int64_t *d_gene_idx, int64_t S
     sb::WalkArgs A;
     fill_walk_args(s, A, d_gene_idx, S);
     A.pairs = d_pairs;
-    const size_t smem = walk_smem_bytes(s);
+    const size_t smem = walk_smem_bytes(s, true);
     if (smem > (size_t)ctx->max_smem_optin) return fail(ctx, SB_ERR_ARG, "tree too deep for shared memory");
     SB_CUDA(ctx, cudaFuncSetAttribute(sb::walk_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     Timed tm(ctx, CAT_WALK);
@@ -568,7 +569,7 @@ int launch_permute(sb_ctx *ctx, int32_t t, const int64_t *d_gene_idx, int64_t S,
     if (rc) return rc;
     uint8_t *d_hits = (uint8_t *)ctx->d_scratch[1];
 
-    const size_t smem = walk_smem_bytes(s);
+    const size_t smem = walk_smem_bytes(s, false);
     if (smem > (size_t)ctx->max_smem_optin) return fail(ctx, SB_ERR_ARG, "tree too deep for shared memory");
     SB_CUDA(ctx, cudaFuncSetAttribute(sb::walk_permute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t per_block = (int64_t)sb::WALK_THREADS * sb::WALK_NP;

@@ -177,52 +177,77 @@ __device__ __forceinline__ int max5(const int v[5])
     return __vimax3_s32(__vimax3_s32(v[0], v[1], v[2]), v[3], v[4]);
 }
 
+// The DP runs one or two "passes".  K4 (DUAL = true) needs Total, Pro and Anti and keeps both key
+// sets: p = (pairs, pro | pairs), a = (pairs, anti | pairs).  The permutation test (K5,
+// DUAL = false) only needs Total and ONE statistic per gene -- Pro if the unpermuted Pro >= Anti,
+// else Anti (methods.py:1333-1338) -- and the two passes differ only in which kind of pair adds
+// the extra +1, so K5 runs a single pass with per-gene pair bonuses: half the state, half the
+// arithmetic, half the stack traffic.
+struct Bonus32 {     // what a supporting (AB+ab) / opposing (Ab+aB) pair adds to the p and a keys
+    int ps, po, as_, ao;
+};
+struct Bonus16 {     // the same, packed for the two genes of a pair
+    unsigned ps, po, as_, ao;
+};
+
 // ---- 32-bit (one gene) node updates
 // acc <- combine(acc, leaf (g, TB)); the trait bit TB is block-uniform (the caller branches
 // on it once for all genes of the thread), the gene bit is per gene
-template <int TB>
-__device__ __forceinline__ void walk_leaf(WalkState &s, bool G1, int K)
+template <int TB, bool DUAL>
+__device__ __forceinline__ void walk_leaf(WalkState &s, bool G1, const Bonus32 &b)
 {
-    const int Mp = max5(s.p), Ma = max5(s.a);
-    if (TB) {  // leaf is AB (g) or aB (!g); its complement is ab (pro pair) or Ab (anti pair)
-        const int np4 = G1 ? s.p[3] + (K + 1) : s.p[1] + K;
-        const int na4 = G1 ? s.a[3] + K : s.a[1] + (K + 1);
+    const int Mp = max5(s.p);
+    if (TB) {  // leaf is AB (g) or aB (!g); its complement is ab (supporting pair) or Ab (opposing pair)
+        const int np4 = G1 ? s.p[3] + b.ps : s.p[1] + b.po;
         s.p[0] = G1 ? Mp : s.p[0];
         s.p[2] = G1 ? s.p[2] : Mp;
-        s.a[0] = G1 ? Ma : s.a[0];
-        s.a[2] = G1 ? s.a[2] : Ma;
         s.p[4] = np4;
-        s.a[4] = na4;
-    } else {   // leaf is Ab (g) or ab (!g); complement aB (anti pair) or AB (pro pair)
-        const int np4 = G1 ? s.p[2] + K : s.p[0] + (K + 1);
-        const int na4 = G1 ? s.a[2] + (K + 1) : s.a[0] + K;
+    } else {   // leaf is Ab (g) or ab (!g); complement aB (opposing) or AB (supporting)
+        const int np4 = G1 ? s.p[2] + b.po : s.p[0] + b.ps;
         s.p[1] = G1 ? Mp : s.p[1];
         s.p[3] = G1 ? s.p[3] : Mp;
-        s.a[1] = G1 ? Ma : s.a[1];
-        s.a[3] = G1 ? s.a[3] : Ma;
         s.p[4] = np4;
-        s.a[4] = na4;
+    }
+    if constexpr (DUAL) {
+        const int Ma = max5(s.a);
+        if (TB) {
+            const int na4 = G1 ? s.a[3] + b.as_ : s.a[1] + b.ao;
+            s.a[0] = G1 ? Ma : s.a[0];
+            s.a[2] = G1 ? s.a[2] : Ma;
+            s.a[4] = na4;
+        } else {
+            const int na4 = G1 ? s.a[2] + b.ao : s.a[0] + b.as_;
+            s.a[1] = G1 ? Ma : s.a[1];
+            s.a[3] = G1 ? s.a[3] : Ma;
+            s.a[4] = na4;
+        }
     }
 }
 
-__device__ __forceinline__ void merge_pass(const int L[5], const int R[5], int out[5], int bpro, int banti)
+__device__ __forceinline__ void merge_pass(const int L[5], const int R[5], int out[5], int bsup, int bopp)
 {
     const int ML = max5(L), MR = max5(R);
 #pragma unroll
     for (int c = 0; c < 4; ++c) out[c] = __viaddmax_s32(L[c], MR, ML + R[c]);
     const int nf = L[4] + R[4];
-    const int pp = __viaddmax_s32(L[0], R[3], L[3] + R[0]) + bpro;
-    const int ap = __viaddmax_s32(L[1], R[2], L[2] + R[1]) + banti;
+    const int pp = __viaddmax_s32(L[0], R[3], L[3] + R[0]) + bsup;
+    const int ap = __viaddmax_s32(L[1], R[2], L[2] + R[1]) + bopp;
     out[4] = max(__vimax3_s32(nf, pp, ap), WALK_NEG);
 }
 
 // acc <- combine(L, acc)
-__device__ __forceinline__ void walk_merge(const WalkState &L, WalkState &acc, int K)
+template <bool DUAL>
+__device__ __forceinline__ void walk_merge(const WalkState &L, WalkState &acc, const Bonus32 &b)
 {
     WalkState o;
-    merge_pass(L.p, acc.p, o.p, K + 1, K);
-    merge_pass(L.a, acc.a, o.a, K, K + 1);
-    acc = o;
+    merge_pass(L.p, acc.p, o.p, b.ps, b.po);
+#pragma unroll
+    for (int c = 0; c < 5; ++c) acc.p[c] = o.p[c];
+    if constexpr (DUAL) {
+        merge_pass(L.a, acc.a, o.a, b.as_, b.ao);
+#pragma unroll
+        for (int c = 0; c < 5; ++c) acc.a[c] = o.a[c];
+    }
 }
 
 // ---- packed 16-bit (two genes per register) node updates: the same recurrences with the
@@ -240,7 +265,8 @@ __device__ __forceinline__ unsigned max5_16(const unsigned v[5])
 }
 
 // m1, m2: half-word masks of the two leaves' gene bits; tt = 2*t1 + t2 (block-uniform)
-__device__ __forceinline__ void walk_cherry16(WalkState16 &o, unsigned m1, unsigned m2, int tt)
+template <bool DUAL>
+__device__ __forceinline__ void walk_cherry16(WalkState16 &o, unsigned m1, unsigned m2, int tt, const Bonus16 &b)
 {
     const unsigned N = NEG16x2;
     unsigned f0 = N, f1 = N, f2 = N, f3 = N, p4 = N, a4 = N;
@@ -258,57 +284,69 @@ __device__ __forceinline__ void walk_cherry16(WalkState16 &o, unsigned m1, unsig
         f1 = N & ~mb;                   // Ab
         f3 = N & mb;                    // ab
         const unsigned pm = mB & ~mb, am = ~mB & mb;   // AB+ab supports, aB+Ab opposes
-        p4 = sel2(pm, K16P1x2, sel2(am, K16x2, N));
-        a4 = sel2(pm, K16x2, sel2(am, K16P1x2, N));
+        p4 = sel2(pm, b.ps, sel2(am, b.po, N));
+        if constexpr (DUAL) a4 = sel2(pm, b.as_, sel2(am, b.ao, N));
     }
     o.p[0] = f0; o.p[1] = f1; o.p[2] = f2; o.p[3] = f3; o.p[4] = p4;
-    o.a[0] = f0; o.a[1] = f1; o.a[2] = f2; o.a[3] = f3; o.a[4] = a4;
+    if constexpr (DUAL) { o.a[0] = f0; o.a[1] = f1; o.a[2] = f2; o.a[3] = f3; o.a[4] = a4; }
 }
 
-template <int TB>
-__device__ __forceinline__ void walk_leaf16(WalkState16 &s, unsigned m)
+template <int TB, bool DUAL>
+__device__ __forceinline__ void walk_leaf16(WalkState16 &s, unsigned m, const Bonus16 &b)
 {
-    const unsigned Mp = max5_16(s.p), Ma = max5_16(s.a);
+    const unsigned Mp = max5_16(s.p);
     if (TB) {
-        const unsigned np4 = sel2(m, __vadd2(s.p[3], K16P1x2), __vadd2(s.p[1], K16x2));
-        const unsigned na4 = sel2(m, __vadd2(s.a[3], K16x2), __vadd2(s.a[1], K16P1x2));
+        const unsigned np4 = sel2(m, __vadd2(s.p[3], b.ps), __vadd2(s.p[1], b.po));
         s.p[0] = sel2(m, Mp, s.p[0]);
         s.p[2] = sel2(m, s.p[2], Mp);
-        s.a[0] = sel2(m, Ma, s.a[0]);
-        s.a[2] = sel2(m, s.a[2], Ma);
         s.p[4] = np4;
-        s.a[4] = na4;
     } else {
-        const unsigned np4 = sel2(m, __vadd2(s.p[2], K16x2), __vadd2(s.p[0], K16P1x2));
-        const unsigned na4 = sel2(m, __vadd2(s.a[2], K16P1x2), __vadd2(s.a[0], K16x2));
+        const unsigned np4 = sel2(m, __vadd2(s.p[2], b.po), __vadd2(s.p[0], b.ps));
         s.p[1] = sel2(m, Mp, s.p[1]);
         s.p[3] = sel2(m, s.p[3], Mp);
-        s.a[1] = sel2(m, Ma, s.a[1]);
-        s.a[3] = sel2(m, s.a[3], Ma);
         s.p[4] = np4;
-        s.a[4] = na4;
+    }
+    if constexpr (DUAL) {
+        const unsigned Ma = max5_16(s.a);
+        if (TB) {
+            const unsigned na4 = sel2(m, __vadd2(s.a[3], b.as_), __vadd2(s.a[1], b.ao));
+            s.a[0] = sel2(m, Ma, s.a[0]);
+            s.a[2] = sel2(m, s.a[2], Ma);
+            s.a[4] = na4;
+        } else {
+            const unsigned na4 = sel2(m, __vadd2(s.a[2], b.ao), __vadd2(s.a[0], b.as_));
+            s.a[1] = sel2(m, Ma, s.a[1]);
+            s.a[3] = sel2(m, s.a[3], Ma);
+            s.a[4] = na4;
+        }
     }
 }
 
-__device__ __forceinline__ void merge_pass16(const unsigned L[5], const unsigned R[5], unsigned out[5], unsigned bpro,
-                                             unsigned banti)
+__device__ __forceinline__ void merge_pass16(const unsigned L[5], const unsigned R[5], unsigned out[5], unsigned bsup,
+                                             unsigned bopp)
 {
     const unsigned ML = max5_16(L), MR = max5_16(R);
 #pragma unroll
     for (int c = 0; c < 4; ++c) out[c] = __viaddmax_s16x2(L[c], MR, __vadd2(ML, R[c]));
     const unsigned nf = __vadd2(L[4], R[4]);
-    const unsigned pp = __vadd2(__viaddmax_s16x2(L[0], R[3], __vadd2(L[3], R[0])), bpro);
-    const unsigned ap = __vadd2(__viaddmax_s16x2(L[1], R[2], __vadd2(L[2], R[1])), banti);
+    const unsigned pp = __vadd2(__viaddmax_s16x2(L[0], R[3], __vadd2(L[3], R[0])), bsup);
+    const unsigned ap = __vadd2(__viaddmax_s16x2(L[1], R[2], __vadd2(L[2], R[1])), bopp);
     out[4] = __vmaxs2(__vimax3_s16x2(nf, pp, ap), NEG16x2);
 }
 
 // acc <- combine(L, acc)
-__device__ __forceinline__ void walk_merge16(const WalkState16 &L, WalkState16 &acc)
+template <bool DUAL>
+__device__ __forceinline__ void walk_merge16(const WalkState16 &L, WalkState16 &acc, const Bonus16 &b)
 {
     WalkState16 o;
-    merge_pass16(L.p, acc.p, o.p, K16P1x2, K16x2);
-    merge_pass16(L.a, acc.a, o.a, K16x2, K16P1x2);
-    acc = o;
+    merge_pass16(L.p, acc.p, o.p, b.ps, b.po);
+#pragma unroll
+    for (int c = 0; c < 5; ++c) acc.p[c] = o.p[c];
+    if constexpr (DUAL) {
+        merge_pass16(L.a, acc.a, o.a, b.as_, b.ao);
+#pragma unroll
+        for (int c = 0; c < 5; ++c) acc.a[c] = o.a[c];
+    }
 }
 
 // 16-bit key -> 32-bit key of the same (pairs, x); unreachable stays unreachable
@@ -318,14 +356,17 @@ __device__ __forceinline__ int widen_key(int k16, int scale)   // scale = (1 << 
     return k16 < 0 ? WALK_NEG : k32;
 }
 
+template <bool DUAL>
 __device__ __forceinline__ void walk_widen(const WalkState16 &s, WalkState &g0, WalkState &g1, int scale)
 {
 #pragma unroll
     for (int c = 0; c < 5; ++c) {
         g0.p[c] = widen_key((int)(short)(s.p[c] & 0xFFFFu), scale);
         g1.p[c] = widen_key((int)s.p[c] >> 16, scale);
-        g0.a[c] = widen_key((int)(short)(s.a[c] & 0xFFFFu), scale);
-        g1.a[c] = widen_key((int)s.a[c] >> 16, scale);
+        if constexpr (DUAL) {
+            g0.a[c] = widen_key((int)(short)(s.a[c] & 0xFFFFu), scale);
+            g1.a[c] = widen_key((int)s.a[c] >> 16, scale);
+        }
     }
 }
 
@@ -356,12 +397,15 @@ constexpr int WALK_NP = 2 * WALK_NPAIR;     // genes per thread
 // c_labels[lab_off ..]).  gcol[k] points at gene k's column of genesT; genes 2q and 2q+1 share
 // the packed accumulators of pair q.  Every branch is on block-uniform data (the program and
 // the label bits); per-gene data only feeds selects.  The program always ends in 32-bit mode.
-template <int NPAIR>
+// Stack entries take EW = 10 (DUAL) or 5 words per gene pair in 16-bit form, twice that in 32-bit form.
+template <int NPAIR, bool DUAL>
 __device__ __forceinline__ void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR], int lab_off,
-                                          int *stk, WalkState (&acc)[2 * NPAIR])
+                                          int *stk, WalkState (&acc)[2 * NPAIR], const Bonus32 (&b32)[2 * NPAIR],
+                                          const Bonus16 (&b16c)[NPAIR])
 {
     constexpr int NP = 2 * NPAIR;
     constexpr int T = WALK_THREADS;
+    constexpr int EW = DUAL ? 10 : 5;
     const int K = 1 << A.shift;
     const int scale = K - (1 << WALK_SH16);
     WalkState16 a16[NPAIR], b16[NPAIR];
@@ -392,122 +436,90 @@ __device__ __forceinline__ void walk_tree(const WalkArgs &A, const uint32_t *con
     } while (0)
     // half-word mask of pair q's current gene bits: 0xFFFF per half whose gene is present
 #define SB_PAIR_MASK(q) ((((gw[2 * (q)] & 1u) | ((gw[2 * (q) + 1] & 1u) << 16))) * 0xFFFFu)
+#define SB_LEAF_RUN16(ACC)                                                                     \
+    _Pragma("unroll 1") for (int i = 0; i < cnt; ++i) {                                        \
+        int t;                                                                                 \
+        SB_LOAD_BITS(t);                                                                       \
+        if (t) {                                                                               \
+            _Pragma("unroll") for (int q = 0; q < NPAIR; ++q)                                  \
+                walk_leaf16<1, DUAL>(ACC[q], SB_PAIR_MASK(q), b16c[q]);                        \
+        } else {                                                                               \
+            _Pragma("unroll") for (int q = 0; q < NPAIR; ++q)                                  \
+                walk_leaf16<0, DUAL>(ACC[q], SB_PAIR_MASK(q), b16c[q]);                        \
+        }                                                                                      \
+        SB_DROP_BITS();                                                                        \
+    }
+#define SB_CHERRY16(ACC)                                                                       \
+    do {                                                                                       \
+        int t1, t2;                                                                            \
+        unsigned m1[NPAIR], m2[NPAIR];                                                         \
+        SB_LOAD_BITS(t1);                                                                      \
+        _Pragma("unroll") for (int q = 0; q < NPAIR; ++q) m1[q] = SB_PAIR_MASK(q);             \
+        SB_DROP_BITS();                                                                        \
+        SB_LOAD_BITS(t2);                                                                      \
+        _Pragma("unroll") for (int q = 0; q < NPAIR; ++q) m2[q] = SB_PAIR_MASK(q);             \
+        SB_DROP_BITS();                                                                        \
+        const int tt = t1 * 2 + t2;                                                            \
+        _Pragma("unroll") for (int q = 0; q < NPAIR; ++q)                                      \
+            walk_cherry16<DUAL>(ACC[q], m1[q], m2[q], tt, b16c[q]);                            \
+    } while (0)
+#define SB_POP16(L, q)                                                                         \
+    do {                                                                                       \
+        const int *s_ = stk + (sp + (q) * EW) * T;                                             \
+        _Pragma("unroll") for (int c = 0; c < 5; ++c) {                                        \
+            L.p[c] = (unsigned)s_[c * T];                                                      \
+            if constexpr (DUAL) L.a[c] = (unsigned)s_[(5 + c) * T];                            \
+        }                                                                                      \
+    } while (0)
     for (;;) {
         const uint32_t op = c_ops[pc++];
         const int type = op & 15, cnt = op >> OP_TYPE_BITS;
         switch (type) {
         case OP_LEAF_A16:
-#pragma unroll 1
-            for (int i = 0; i < cnt; ++i) {
-                int t;
-                SB_LOAD_BITS(t);
-                if (t) {
-#pragma unroll
-                    for (int q = 0; q < NPAIR; ++q) walk_leaf16<1>(a16[q], SB_PAIR_MASK(q));
-                } else {
-#pragma unroll
-                    for (int q = 0; q < NPAIR; ++q) walk_leaf16<0>(a16[q], SB_PAIR_MASK(q));
-                }
-                SB_DROP_BITS();
-            }
+            SB_LEAF_RUN16(a16)
             break;
         case OP_PUSH16:
         case OP_PUSH_CHERRY_A16:
 #pragma unroll
             for (int q = 0; q < NPAIR; ++q) {
-                int *s = stk + (sp + q * 10) * T;
+                int *s = stk + (sp + q * EW) * T;
 #pragma unroll
                 for (int c = 0; c < 5; ++c) {
                     s[c * T] = (int)a16[q].p[c];
-                    s[(5 + c) * T] = (int)a16[q].a[c];
+                    if constexpr (DUAL) s[(5 + c) * T] = (int)a16[q].a[c];
                 }
             }
-            sp += 10 * NPAIR;
+            sp += EW * NPAIR;
             if (type == OP_PUSH16) break;
             // fall through
-        case OP_CHERRY_A16: {
-            int t1, t2;
-            unsigned m1[NPAIR], m2[NPAIR];
-            SB_LOAD_BITS(t1);
-#pragma unroll
-            for (int q = 0; q < NPAIR; ++q) m1[q] = SB_PAIR_MASK(q);
-            SB_DROP_BITS();
-            SB_LOAD_BITS(t2);
-#pragma unroll
-            for (int q = 0; q < NPAIR; ++q) m2[q] = SB_PAIR_MASK(q);
-            SB_DROP_BITS();
-            const int tt = t1 * 2 + t2;
-#pragma unroll
-            for (int q = 0; q < NPAIR; ++q) walk_cherry16(a16[q], m1[q], m2[q], tt);
-#pragma unroll 1
-            for (int i = 0; i < cnt; ++i) {
-                int t;
-                SB_LOAD_BITS(t);
-                if (t) {
-#pragma unroll
-                    for (int q = 0; q < NPAIR; ++q) walk_leaf16<1>(a16[q], SB_PAIR_MASK(q));
-                } else {
-#pragma unroll
-                    for (int q = 0; q < NPAIR; ++q) walk_leaf16<0>(a16[q], SB_PAIR_MASK(q));
-                }
-                SB_DROP_BITS();
-            }
+        case OP_CHERRY_A16:
+            SB_CHERRY16(a16);
+            SB_LEAF_RUN16(a16)
             break;
-        }
         case OP_CHERRY_B16:
-        case OP_CHERRY_B16_MERGE: {
-            int t1, t2;
-            unsigned m1[NPAIR], m2[NPAIR];
-            SB_LOAD_BITS(t1);
-#pragma unroll
-            for (int q = 0; q < NPAIR; ++q) m1[q] = SB_PAIR_MASK(q);
-            SB_DROP_BITS();
-            SB_LOAD_BITS(t2);
-#pragma unroll
-            for (int q = 0; q < NPAIR; ++q) m2[q] = SB_PAIR_MASK(q);
-            SB_DROP_BITS();
-            const int tt = t1 * 2 + t2;
-#pragma unroll
-            for (int q = 0; q < NPAIR; ++q) walk_cherry16(b16[q], m1[q], m2[q], tt);
-#pragma unroll 1
-            for (int i = 0; i < cnt; ++i) {
-                int t;
-                SB_LOAD_BITS(t);
-                if (t) {
-#pragma unroll
-                    for (int q = 0; q < NPAIR; ++q) walk_leaf16<1>(b16[q], SB_PAIR_MASK(q));
-                } else {
-#pragma unroll
-                    for (int q = 0; q < NPAIR; ++q) walk_leaf16<0>(b16[q], SB_PAIR_MASK(q));
-                }
-                SB_DROP_BITS();
-            }
+        case OP_CHERRY_B16_MERGE:
+            SB_CHERRY16(b16);
+            SB_LEAF_RUN16(b16)
             if (type == OP_CHERRY_B16_MERGE) {
 #pragma unroll
-                for (int q = 0; q < NPAIR; ++q) walk_merge16(b16[q], a16[q]);
+                for (int q = 0; q < NPAIR; ++q) walk_merge16<DUAL>(b16[q], a16[q], b16c[q]);
             }
             break;
-        }
         case OP_MERGE_POP16:
 #pragma unroll 1
             for (int i = 0; i < cnt; ++i) {
-                sp -= 10 * NPAIR;
+                sp -= EW * NPAIR;
 #pragma unroll
                 for (int q = 0; q < NPAIR; ++q) {
                     WalkState16 L;
-                    const int *s = stk + (sp + q * 10) * T;
-#pragma unroll
-                    for (int c = 0; c < 5; ++c) {
-                        L.p[c] = (unsigned)s[c * T];
-                        L.a[c] = (unsigned)s[(5 + c) * T];
-                    }
-                    walk_merge16(L, a16[q]);
+                    SB_POP16(L, q);
+                    walk_merge16<DUAL>(L, a16[q], b16c[q]);
                 }
             }
             break;
         case OP_WIDEN_A:
 #pragma unroll
-            for (int q = 0; q < NPAIR; ++q) walk_widen(a16[q], acc[2 * q], acc[2 * q + 1], scale);
+            for (int q = 0; q < NPAIR; ++q) walk_widen<DUAL>(a16[q], acc[2 * q], acc[2 * q + 1], scale);
             break;
         case OP_LEAF_A32:
 #pragma unroll 1
@@ -516,10 +528,10 @@ __device__ __forceinline__ void walk_tree(const WalkArgs &A, const uint32_t *con
                 SB_LOAD_BITS(t);
                 if (t) {
 #pragma unroll
-                    for (int k = 0; k < NP; ++k) walk_leaf<1>(acc[k], (gw[k] & 1u) != 0, K);
+                    for (int k = 0; k < NP; ++k) walk_leaf<1, DUAL>(acc[k], (gw[k] & 1u) != 0, b32[k]);
                 } else {
 #pragma unroll
-                    for (int k = 0; k < NP; ++k) walk_leaf<0>(acc[k], (gw[k] & 1u) != 0, K);
+                    for (int k = 0; k < NP; ++k) walk_leaf<0, DUAL>(acc[k], (gw[k] & 1u) != 0, b32[k]);
                 }
                 SB_DROP_BITS();
             }
@@ -528,57 +540,52 @@ __device__ __forceinline__ void walk_tree(const WalkArgs &A, const uint32_t *con
 #pragma unroll
             for (int q = 0; q < NPAIR; ++q) {
                 WalkState r0, r1;
-                walk_widen(b16[q], r0, r1, scale);
-                walk_merge(r0, acc[2 * q], K);
-                walk_merge(r1, acc[2 * q + 1], K);
+                walk_widen<DUAL>(b16[q], r0, r1, scale);
+                walk_merge<DUAL>(r0, acc[2 * q], b32[2 * q]);
+                walk_merge<DUAL>(r1, acc[2 * q + 1], b32[2 * q + 1]);
             }
             break;
         case OP_PUSH32:
 #pragma unroll
             for (int k = 0; k < NP; ++k) {
-                int *s = stk + (sp + k * 10) * T;
+                int *s = stk + (sp + k * EW) * T;
 #pragma unroll
                 for (int c = 0; c < 5; ++c) {
                     s[c * T] = acc[k].p[c];
-                    s[(5 + c) * T] = acc[k].a[c];
+                    if constexpr (DUAL) s[(5 + c) * T] = acc[k].a[c];
                 }
             }
-            sp += 10 * NP;
+            sp += EW * NP;
             break;
         case OP_MERGE_POP32:
 #pragma unroll 1
             for (int i = 0; i < cnt; ++i) {
-                sp -= 10 * NP;
+                sp -= EW * NP;
 #pragma unroll
                 for (int k = 0; k < NP; ++k) {
                     WalkState L;
-                    const int *s = stk + (sp + k * 10) * T;
+                    const int *s = stk + (sp + k * EW) * T;
 #pragma unroll
                     for (int c = 0; c < 5; ++c) {
                         L.p[c] = s[c * T];
-                        L.a[c] = s[(5 + c) * T];
+                        if constexpr (DUAL) L.a[c] = s[(5 + c) * T];
                     }
-                    walk_merge(L, acc[k], K);
+                    walk_merge<DUAL>(L, acc[k], b32[k]);
                 }
             }
             break;
         case OP_MERGE_POPW:
 #pragma unroll 1
             for (int i = 0; i < cnt; ++i) {
-                sp -= 10 * NPAIR;
+                sp -= EW * NPAIR;
 #pragma unroll
                 for (int q = 0; q < NPAIR; ++q) {
                     WalkState16 L;
-                    const int *s = stk + (sp + q * 10) * T;
-#pragma unroll
-                    for (int c = 0; c < 5; ++c) {
-                        L.p[c] = (unsigned)s[c * T];
-                        L.a[c] = (unsigned)s[(5 + c) * T];
-                    }
+                    SB_POP16(L, q);
                     WalkState r0, r1;
-                    walk_widen(L, r0, r1, scale);
-                    walk_merge(r0, acc[2 * q], K);
-                    walk_merge(r1, acc[2 * q + 1], K);
+                    walk_widen<DUAL>(L, r0, r1, scale);
+                    walk_merge<DUAL>(r0, acc[2 * q], b32[2 * q]);
+                    walk_merge<DUAL>(r1, acc[2 * q + 1], b32[2 * q + 1]);
                 }
             }
             break;
@@ -589,20 +596,9 @@ __device__ __forceinline__ void walk_tree(const WalkArgs &A, const uint32_t *con
 #undef SB_LOAD_BITS
 #undef SB_DROP_BITS
 #undef SB_PAIR_MASK
-}
-
-// root: three independent maxima (classes.py:246-249)
-__device__ __forceinline__ void walk_root(const WalkState &s, int shift, int &total, int &pro, int &anti)
-{
-    const int mask = (1 << shift) - 1;
-    total = max5(s.p) >> shift;
-    pro = -1;
-    anti = -1;
-#pragma unroll
-    for (int c = 0; c < 5; ++c) {
-        if (s.p[c] >= 0) pro = max(pro, s.p[c] & mask);
-        if (s.a[c] >= 0) anti = max(anti, s.a[c] & mask);
-    }
+#undef SB_LEAF_RUN16
+#undef SB_CHERRY16
+#undef SB_POP16
 }
 
 // gene slots of this thread: (tile * NP + k) * T + tid  (coalesced per k)
@@ -622,7 +618,8 @@ __device__ __forceinline__ void walk_slots(const WalkArgs &A, int tile, int64_t 
     }
 }
 
-// K4: one labelling (c_labels row 0), writes pairs[S][3].
+// K4: one labelling (c_labels row 0), both passes; writes pairs[S][3] = Total, Pro, Anti.
+// The root takes three independent maxima (classes.py:246-249).
 __global__ void __launch_bounds__(WALK_THREADS) walk_pairs_kernel(const WalkArgs A)
 {
     extern __shared__ __align__(16) int smem_stack[];
@@ -630,12 +627,25 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_pairs_kernel(const WalkArgs
     constexpr int NP = WALK_NP;
     int64_t s_idx[NP], sc[NP]; bool active[NP]; const uint32_t *gcol[NP];
     walk_slots<NP>(A, blockIdx.x, s_idx, active, sc, gcol);
+    const int K = 1 << A.shift;
+    Bonus32 b32[NP];
+    Bonus16 b16[WALK_NPAIR];
+#pragma unroll
+    for (int k = 0; k < NP; ++k) b32[k] = Bonus32{K + 1, K, K, K + 1};
+#pragma unroll
+    for (int q = 0; q < WALK_NPAIR; ++q) b16[q] = Bonus16{K16P1x2, K16x2, K16x2, K16P1x2};
     WalkState acc[NP];
-    walk_tree<WALK_NPAIR>(A, gcol, 0, stk, acc);
+    walk_tree<WALK_NPAIR, true>(A, gcol, 0, stk, acc, b32, b16);
+    const int mask = K - 1;
 #pragma unroll
     for (int k = 0; k < NP; ++k) {
-        int total, pro, anti;
-        walk_root(acc[k], A.shift, total, pro, anti);
+        const int total = max5(acc[k].p) >> A.shift;
+        int pro = -1, anti = -1;
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+            if (acc[k].p[c] >= 0) pro = max(pro, acc[k].p[c] & mask);
+            if (acc[k].a[c] >= 0) anti = max(anti, acc[k].a[c] & mask);
+        }
         if (active[k]) {
             A.pairs[s_idx[k] * 3 + 0] = total;
             A.pairs[s_idx[k] * 3 + 1] = pro;
@@ -645,9 +655,10 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_pairs_kernel(const WalkArgs
 }
 
 // K5: grid = (gene tiles, chunks of PERMS_PER_ITEM labellings).  A thread walks its NP genes
-// under each labelling of the block's chunk and writes one byte of hit flags per gene.
-// Blocks are small work items, so the tail of a launch is short, and blocks that run
-// concurrently read the same few label vectors from the constant cache.
+// under each labelling of the block's chunk -- a single pass keyed on each gene's own statistic --
+// and writes one byte of hit flags per gene.  Blocks are small work items, so the tail of a
+// launch is short, and concurrently running blocks read the same few label vectors from the
+// constant cache.
 __global__ void __launch_bounds__(WALK_THREADS, SB_WALK_MINBLOCKS) walk_permute_kernel(const WalkArgs A)
 {
     extern __shared__ __align__(16) int smem_stack[];
@@ -658,7 +669,11 @@ __global__ void __launch_bounds__(WALK_THREADS, SB_WALK_MINBLOCKS) walk_permute_
     const int rows = min(PERMS_PER_ITEM, A.n_perms - perm0);
     int64_t s_idx[NP], sc[NP]; bool active[NP]; const uint32_t *gcol[NP];
     walk_slots<NP>(A, blockIdx.x, s_idx, active, sc, gcol);
+    const int K = 1 << A.shift;
+    const int mask = K - 1;
     long long u_total[NP], u_stat[NP]; bool use_pro[NP]; uint32_t hits[NP];
+    Bonus32 b32[NP];
+    Bonus16 b16[WALK_NPAIR];
 #pragma unroll
     for (int k = 0; k < NP; ++k) {
         u_total[k] = A.unperm[sc[k] * 3 + 0];
@@ -666,16 +681,26 @@ __global__ void __launch_bounds__(WALK_THREADS, SB_WALK_MINBLOCKS) walk_permute_
         use_pro[k] = u_pro >= u_anti;                 // methods.py:1333-1336
         u_stat[k] = use_pro[k] ? u_pro : u_anti;
         hits[k] = 0;
+        // the statistic this gene is tested on counts +1 for its own kind of pair
+        b32[k] = Bonus32{use_pro[k] ? K + 1 : K, use_pro[k] ? K : K + 1, 0, 0};
+    }
+#pragma unroll
+    for (int q = 0; q < WALK_NPAIR; ++q) {
+        const unsigned s0 = use_pro[2 * q] ? 65u : 64u, s1 = use_pro[2 * q + 1] ? 65u : 64u;
+        b16[q] = Bonus16{s0 | (s1 << 16), (129u - s0) | ((129u - s1) << 16), 0u, 0u};
     }
     for (int r = 0; r < rows; ++r) {
         WalkState acc[NP];
-        walk_tree<WALK_NPAIR>(A, gcol, (perm0 + r) * A.W32p, stk, acc);
+        walk_tree<WALK_NPAIR, false>(A, gcol, (perm0 + r) * A.W32p, stk, acc, b32, b16);
 #pragma unroll
         for (int k = 0; k < NP; ++k) {
-            int total, pro, anti;
-            walk_root(acc[k], A.shift, total, pro, anti);
-            const long long si = use_pro[k] ? pro : anti;
-            if (si * u_total[k] >= u_stat[k] * (long long)total) hits[k] |= (1u << r);   // methods.py:1353-1355
+            // root: Total and the statistic are independent maxima over the five states (classes.py:246-249)
+            const long long total = max5(acc[k].p) >> A.shift;
+            int stat = -1;
+#pragma unroll
+            for (int c = 0; c < 5; ++c)
+                if (acc[k].p[c] >= 0) stat = max(stat, acc[k].p[c] & mask);
+            if ((long long)stat * u_total[k] >= u_stat[k] * total) hits[k] |= (1u << r);   // methods.py:1353-1355
         }
     }
 #pragma unroll
