@@ -410,20 +410,33 @@ __device__ __forceinline__ void walk_tree(const WalkArgs &A, const uint32_t *con
     const int scale = K - (1 << WALK_SH16);
     WalkState16 a16[NPAIR], b16[NPAIR];
     int pos = 0, sp = 0, pc = 0;       // sp counts 32-bit words per thread
-    uint32_t gw[NP], gnext[NP], lw = 0;
+    // gx[q]: the current 16-leaf window of pair q's two genes (gene 2q in bits 0..15, gene 2q+1 in
+    // bits 16..31, consumed from bit 0 / bit 16); gy[q]: the following 16 leaves; gnext: prefetch
+    uint32_t gx[NPAIR], gy[NPAIR], gnext[NP], lw = 0;
 #pragma unroll
-    for (int k = 0; k < NP; ++k) { gw[k] = 0; gnext[k] = __ldg(gcol[k]); }
+    for (int k = 0; k < NP; ++k) gnext[k] = __ldg(gcol[k]);
+#pragma unroll
+    for (int q = 0; q < NPAIR; ++q) { gx[q] = 0; gy[q] = 0; }
     const int W32p = A.W32p;
     const int64_t Gs = A.Gs;
-    // fetch the next leaf: label bit tv (uniform); gene bits stay in gw[] bit 0 until SB_DROP_BITS
+    // fetch the next leaf: label bit tv (uniform); gene bits stay at bit 0 / bit 16 of gx until SB_DROP_BITS
 #define SB_LOAD_BITS(tv)                                                                       \
     do {                                                                                       \
-        if ((pos & 31) == 0) {                                                                 \
-            const int w_ = pos >> 5;                                                           \
-            lw = c_labels[lab_off + w_];                                                       \
-            _Pragma("unroll") for (int k_ = 0; k_ < NP; ++k_) {                                \
-                gw[k_] = gnext[k_];                                                            \
-                if (w_ + 1 < W32p) gnext[k_] = __ldg(gcol[k_] + (int64_t)(w_ + 1) * Gs);       \
+        if ((pos & 15) == 0) {                                                                 \
+            if ((pos & 31) == 0) {                                                             \
+                const int w_ = pos >> 5;                                                       \
+                lw = c_labels[lab_off + w_];                                                   \
+                _Pragma("unroll") for (int q_ = 0; q_ < NPAIR; ++q_) {                         \
+                    const uint32_t a_ = gnext[2 * q_], b_ = gnext[2 * q_ + 1];                 \
+                    gx[q_] = (a_ & 0xFFFFu) | (b_ << 16);                                      \
+                    gy[q_] = (a_ >> 16) | (b_ & 0xFFFF0000u);                                  \
+                }                                                                              \
+                if (w_ + 1 < W32p) {                                                           \
+                    _Pragma("unroll") for (int k_ = 0; k_ < NP; ++k_)                          \
+                        gnext[k_] = __ldg(gcol[k_] + (int64_t)(w_ + 1) * Gs);                  \
+                }                                                                              \
+            } else {                                                                           \
+                _Pragma("unroll") for (int q_ = 0; q_ < NPAIR; ++q_) gx[q_] = gy[q_];          \
             }                                                                                  \
         }                                                                                      \
         tv = (int)(lw & 1u);                                                                   \
@@ -432,10 +445,11 @@ __device__ __forceinline__ void walk_tree(const WalkArgs &A, const uint32_t *con
     } while (0)
 #define SB_DROP_BITS()                                                                         \
     do {                                                                                       \
-        _Pragma("unroll") for (int k_ = 0; k_ < NP; ++k_) gw[k_] >>= 1;                        \
+        _Pragma("unroll") for (int q_ = 0; q_ < NPAIR; ++q_) gx[q_] >>= 1;                     \
     } while (0)
     // half-word mask of pair q's current gene bits: 0xFFFF per half whose gene is present
-#define SB_PAIR_MASK(q) ((((gw[2 * (q)] & 1u) | ((gw[2 * (q) + 1] & 1u) << 16))) * 0xFFFFu)
+#define SB_PAIR_MASK(q) ((gx[q] & 0x00010001u) * 0xFFFFu)
+#define SB_GENE_BIT(k) (((gx[(k) >> 1] >> (((k) & 1) * 16)) & 1u) != 0)
 #define SB_LEAF_RUN16(ACC)                                                                     \
     _Pragma("unroll 1") for (int i = 0; i < cnt; ++i) {                                        \
         int t;                                                                                 \
@@ -528,10 +542,10 @@ __device__ __forceinline__ void walk_tree(const WalkArgs &A, const uint32_t *con
                 SB_LOAD_BITS(t);
                 if (t) {
 #pragma unroll
-                    for (int k = 0; k < NP; ++k) walk_leaf<1, DUAL>(acc[k], (gw[k] & 1u) != 0, b32[k]);
+                    for (int k = 0; k < NP; ++k) walk_leaf<1, DUAL>(acc[k], SB_GENE_BIT(k), b32[k]);
                 } else {
 #pragma unroll
-                    for (int k = 0; k < NP; ++k) walk_leaf<0, DUAL>(acc[k], (gw[k] & 1u) != 0, b32[k]);
+                    for (int k = 0; k < NP; ++k) walk_leaf<0, DUAL>(acc[k], SB_GENE_BIT(k), b32[k]);
                 }
                 SB_DROP_BITS();
             }
@@ -596,6 +610,7 @@ __device__ __forceinline__ void walk_tree(const WalkArgs &A, const uint32_t *con
 #undef SB_LOAD_BITS
 #undef SB_DROP_BITS
 #undef SB_PAIR_MASK
+#undef SB_GENE_BIT
 #undef SB_LEAF_RUN16
 #undef SB_CHERRY16
 #undef SB_POP16
