@@ -439,6 +439,18 @@ def run_ours(a):
                                    "instruction, same issue rate)",
                     "note": "achieved counts the SURVEY 8(d) contract ops (76 per internal node); the kernel executes "
                             "fewer (cheap leaf/cherry updates, two genes per instruction), so frac can exceed 1"}
+    # issue-slot view of the same kernel: warp instructions actually executed (ncu count, profiles/) per second
+    # against the SM's issue capacity (4 warp instructions per clock per SM) at the clock sampled above
+    try:
+        wi = json.load(open(os.path.join(ROOT, "profiles", "k5_warp_instructions.json"))).get(a.workload)
+    except Exception:
+        wi = None
+    if wi and P > 0 and clocks and clocks.get("sm_mhz"):
+        issued = tests_per_launch / 64.0 * wi / (k5_ms * 1e-3)
+        cap = 4.0 * st["sm_count"] * clocks["sm_mhz"] * 1e6
+        roofline_int["issue"] = {"warp_instr_per_s": issued, "peak": cap, "frac": issued / cap,
+                                 "source": "instruction count from profiles/k5_warp_instructions.json (ncu), time and "
+                                           "clock from this run"}
     fisher_bytes = G * (8 * W + 24)
     fisher = {"kernel": "fisher_kernel (K2+K3)", "ms": fisher_ms, "tests_per_s": G / (fisher_ms * 1e-3),
               "bound": "hbm", "achieved": fisher_bytes / (fisher_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
