@@ -204,3 +204,93 @@ def test_upgma_matches_reference_golden(engine):
         names = ["s%d" % k for k in range(mat.shape[1])]
         engine.set_genes(eng.pack_rows(mat), mat.shape[1])
         assert treemod.from_merges(names, engine.upgma()) == u["tree"]
+
+
+def _comb(names):
+    t = names[0]
+    for n in names[1:]:
+        t = [t, n]
+    return t
+
+
+def _balanced(names):
+    level = list(names)
+    while len(level) > 1:
+        nxt = [[level[i], level[i + 1]] for i in range(0, len(level) - 1, 2)]
+        if len(level) % 2:
+            nxt.append(level[-1])
+        level = nxt
+    return level[0]
+
+
+@pytest.mark.parametrize("N", [126, 127, 128, 129, 130, 254, 255, 256, 257, 383])
+def test_walk_mode_boundaries(engine, N):
+    """subtree sizes around the 16-bit / 32-bit switch (127 leaves), for three tree shapes"""
+    names = synth.isolate_names(N)
+    col = {n: j for j, n in enumerate(names)}
+    bits, traits = _dataset(70, N, 900 + N)
+    m = synth.unpack_rows(bits, N)
+    engine.set_genes(bits, N)
+    engine.set_trait_vector(0, traits[0])
+    for nested in (_comb(names), _balanced(names), synth.make_tree(N, N)):
+        order = engine.set_tree_nested(0, nested, col)
+        left, right, _ = O.flatten_tree(nested)
+        cols = np.asarray([col[n] for n in order])
+        ref = O.permute(left, right, m[:, cols], traits[0][cols].astype(np.uint8), P=9, seed=N, trait=0)
+        pairs, r, nd = engine.permute(0, 9, seed=N)
+        assert np.array_equal(pairs, ref["pairs"]) and np.array_equal(r, ref["r"])
+
+
+@pytest.mark.parametrize("P", [1, 2, 3, 4, 5, 10, 31, 32, 33, 70, 131])
+def test_permutation_counts_and_early_stop_boundaries(engine, P):
+    G, N = 90, 200
+    bits, traits = _dataset(G, N, 4242)
+    nested, col = _tree_for(N, 4242, traits[0])
+    engine.set_genes(bits, N)
+    engine.set_trait_vector(2, traits[0])
+    names = engine.set_tree_nested(2, nested, col)
+    left, right, _ = O.flatten_tree(nested)
+    m = synth.unpack_rows(bits, N)
+    cols = np.asarray([col[n] for n in names])
+    labels = traits[0][cols].astype(np.uint8)
+    idx = np.asarray([5, 5, 0, 89, 17, 3, 44], dtype=np.int64)        # duplicates, arbitrary order, odd count
+    for es in (False, True):
+        ref = O.permute(left, right, m[np.ix_(idx, cols)], labels, P=P, seed=7, trait=2, early_stop=es)
+        pairs, r, nd = engine.permute(2, P, seed=7, gene_idx=idx, early_stop=es, rmin=O.rmin_table(P) if es else None)
+        assert np.array_equal(pairs, ref["pairs"])
+        assert np.array_equal(r, ref["r"]) and np.array_equal(nd, ref["n_done"]), (P, es)
+
+
+def test_device_pointer_entry_points(engine):
+    """the *_device variants (device buffers, caller's stream) agree with the host-buffer calls"""
+    import torch
+    G, N, P = 500, 300, 40
+    bits, traits = _dataset(G, N, 77)
+    nested, col = _tree_for(N, 77, traits[0])
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(stream):
+        d_bits = torch.from_numpy(bits.view(np.int64)).to(dev)
+        engine.set_stream(stream.cuda_stream)
+        try:
+            engine.set_genes_device(d_bits.data_ptr(), G, N, bits.shape[1])
+            engine.set_trait_vector(0, traits[0])
+            engine.set_tree_nested(0, nested, col)
+            d_counts = torch.empty((G, 4), dtype=torch.int32, device=dev)
+            d_p = torch.empty(G, dtype=torch.float64, device=dev)
+            d_pairs = torch.empty((G, 3), dtype=torch.int32, device=dev)
+            d_r = torch.empty(G, dtype=torch.int32, device=dev)
+            d_nd = torch.empty(G, dtype=torch.int32, device=dev)
+            engine.contingency_fisher_device(0, d_counts.data_ptr(), d_p.data_ptr())
+            engine.permute_device(0, G, P, 5, d_pairs.data_ptr(), d_r.data_ptr(), d_nd.data_ptr())
+            stream.synchronize()
+            got = (d_counts.cpu().numpy(), d_p.cpu().numpy(), d_pairs.cpu().numpy(), d_r.cpu().numpy())
+        finally:
+            engine.set_stream(0)
+    engine.set_genes(bits, N)
+    engine.set_trait_vector(0, traits[0])
+    engine.set_tree_nested(0, nested, col)
+    counts, p, _ = engine.contingency_fisher(0)
+    pairs, r, nd = engine.permute(0, P, seed=5)
+    assert np.array_equal(got[0], counts) and np.array_equal(got[1], p)
+    assert np.array_equal(got[2], pairs) and np.array_equal(got[3], r)
