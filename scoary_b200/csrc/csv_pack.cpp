@@ -1,0 +1,177 @@
+// csv_pack.cpp -- SURVEY.md 8(f) rank 2: gene presence/absence CSV -> packed bitset rows, natively.
+//
+// Replaces the per-cell Python loop of Csv_to_dic_Roary (scoary/methods.py:445-497): for every
+// data row, the cells of the selected isolate columns are turned into presence bits ("present"
+// unless the cell is "", "0" or "-", methods.py:476-487) and packed straight into the uint64
+// rows sb_set_genes takes; the byte ranges of a few leading fields (gene name, annotation, ...)
+// are returned so the host can slice them out without parsing the row again.
+//
+// CSV dialect = Python's csv.reader(skipinitialspace=True, delimiter=d) as the reference uses it
+// (methods.py:350-351): excel dialect, '"' quoting recognised at the start of a field (after the
+// skipped spaces), "" inside quotes is a literal quote, rows end at \n, \r\n or \r outside quotes.
+// Host code only (no CUDA); rows are parsed in parallel with OpenMP after a sequential scan for
+// the row starts.
+#include <stdint.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace {
+
+struct Field {
+    int64_t begin, end;   // byte range of the raw field text (quotes included when quoted)
+    bool quoted;
+};
+
+// Parses one row starting at p (end of buffer e).  Calls f(col, begin, end, quoted, needs_unescape)
+// for every field; returns the position after the row terminator.
+template <class F>
+inline const char *parse_row(const char *base, const char *p, const char *e, char delim, F &&f)
+{
+    int col = 0;
+    for (;;) {
+        while (p < e && *p == ' ') ++p;             // skipinitialspace
+        const char *fb = p;
+        bool quoted = false, esc = false;
+        if (p < e && *p == '"') {
+            quoted = true;
+            ++p;
+            fb = p;
+            const char *fe;
+            for (;;) {
+                if (p >= e) { fe = e; break; }
+                if (*p == '"') {
+                    if (p + 1 < e && p[1] == '"') { esc = true; p += 2; continue; }
+                    fe = p;
+                    ++p;
+                    break;
+                }
+                ++p;
+            }
+            // anything between the closing quote and the delimiter belongs to the field in Python's
+            // reader; Roary files never have it: skip to the delimiter
+            const char *tail = p;
+            while (p < e && *p != delim && *p != '\n' && *p != '\r') ++p;
+            if (p != tail) esc = true;              // flag unusual field: host re-parses it
+            f(col, fb - base, (esc ? p : fe) - base, quoted, esc);
+        } else {
+            while (p < e && *p != delim && *p != '\n' && *p != '\r') ++p;
+            f(col, fb - base, p - base, false, false);
+        }
+        ++col;
+        if (p >= e) return e;
+        if (*p == delim) { ++p; continue; }
+        if (*p == '\r') { ++p; if (p < e && *p == '\n') ++p; return p; }
+        if (*p == '\n') return p + 1;
+    }
+}
+
+inline bool is_absent(const char *b, const char *e)
+{
+    const int64_t n = e - b;
+    return n == 0 || (n == 1 && (b[0] == '0' || b[0] == '-'));
+}
+
+}  // namespace
+
+extern "C" {
+
+// Row starts of the data rows (everything after the first row).  row_starts may be NULL to count.
+// Returns the number of data rows (empty trailing lines are ignored), or -1 on error.
+int64_t sb_csv_row_starts(const char *buf, int64_t len, int64_t *row_starts, int64_t max_rows, int64_t *header_end)
+{
+    if (!buf || len < 0) return -1;
+    const char *p = buf, *e = buf + len;
+    bool inq = false;
+    // skip the header row
+    auto next_row = [&](const char *q) {
+        for (; q < e; ++q) {
+            const char c = *q;
+            if (c == '"') inq = !inq;                 // "" toggles twice: still correct for row scanning
+            else if (!inq && c == '\n') return q + 1;
+            else if (!inq && c == '\r') { return (q + 1 < e && q[1] == '\n') ? q + 2 : q + 1; }
+        }
+        return e;
+    };
+    p = next_row(p);
+    if (header_end) *header_end = p - buf;
+    int64_t n = 0;
+    while (p < e) {
+        const char *q = next_row(p);
+        // ignore rows that are empty
+        const char *t = p;
+        while (t < q && (*t == '\n' || *t == '\r')) ++t;
+        if (t < q) {
+            if (row_starts) {
+                if (n >= max_rows) return -1;
+                row_starts[n] = p - buf;
+            }
+            ++n;
+        }
+        p = q;
+    }
+    return n;
+}
+
+// Pack the presence bits of n_rows data rows.
+//   keep_cols  [n_keep] column indices (0-based, ascending) whose cells become bits 0..n_keep-1
+//   bits       uint64 [n_rows][W] (W >= ceil(n_keep / 64)), zero-filled by this call
+//   lead_cols  [n_lead] column indices whose byte ranges are returned in lead_ranges [n_rows][n_lead][2];
+//              a negative begin marks a field the host must re-parse (escaped quotes etc.)
+//   row_fields [n_rows] number of fields found in each row (the host checks it against the header)
+// Returns 0, or -(row + 1) for the first row that has fewer fields than the largest needed column.
+int64_t sb_csv_pack_rows(const char *buf, int64_t len, char delimiter, const int64_t *row_starts, int64_t n_rows,
+                         const int32_t *keep_cols, int32_t n_keep, uint64_t *bits, int32_t W, const int32_t *lead_cols,
+                         int32_t n_lead, int64_t *lead_ranges, int32_t *row_fields)
+{
+    if (!buf || !row_starts || !bits || (n_keep > 0 && !keep_cols)) return -1;
+    const char *e = buf + len;
+    int32_t max_col = -1;
+    for (int32_t i = 0; i < n_keep; ++i) max_col = keep_cols[i] > max_col ? keep_cols[i] : max_col;
+    for (int32_t i = 0; i < n_lead; ++i) max_col = lead_cols[i] > max_col ? lead_cols[i] : max_col;
+    // column -> bit index (or -1) and column -> lead slot (or -1)
+    std::vector<int32_t> bit_of(max_col + 1, -1), lead_of(max_col + 1, -1);
+    for (int32_t i = 0; i < n_keep; ++i) bit_of[keep_cols[i]] = i;
+    for (int32_t i = 0; i < n_lead; ++i) lead_of[lead_cols[i]] = i;
+    int64_t first_bad = 0;
+#pragma omp parallel for schedule(static)
+    for (int64_t r = 0; r < n_rows; ++r) {
+        uint64_t *row = bits + r * (int64_t)W;
+        memset(row, 0, sizeof(uint64_t) * (size_t)W);
+        int32_t nf = 0;
+        parse_row(buf, buf + row_starts[r], e, delimiter,
+                  [&](int col, int64_t b, int64_t en, bool quoted, bool esc) {
+                      nf = col + 1;
+                      if (col > max_col) return;
+                      const int32_t bi = bit_of[col];
+                      if (bi >= 0) {
+                          // escaped / unusual fields are never "", "0" or "-" unless they unescape to that;
+                          // a quoted field with an escaped quote has length >= 1 and contains '"': present
+                          const bool absent = !esc && is_absent(buf + b, buf + en);
+                          if (!absent) row[bi >> 6] |= 1ULL << (bi & 63);
+                      }
+                      const int32_t li = lead_of[col];
+                      if (li >= 0 && lead_ranges) {
+                          int64_t *o = lead_ranges + (r * (int64_t)n_lead + li) * 2;
+                          o[0] = esc ? -(b + 1) : b;
+                          o[1] = en;
+                          (void)quoted;
+                      }
+                  });
+        if (row_fields) row_fields[r] = nf;
+        if (nf <= max_col) {
+#pragma omp critical(sb_csv_bad)
+            {
+                if (first_bad == 0 || r + 1 < first_bad) first_bad = r + 1;
+            }
+        }
+    }
+    return first_bad ? -first_bad : 0;
+}
+
+}  // extern "C"

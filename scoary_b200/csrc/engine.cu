@@ -504,7 +504,7 @@ void fill_walk_args(const TraitSlot &s, sb::WalkArgs &A, const int64_t *d_gene_i
 int upload_program(sb_ctx *ctx, const TraitSlot &s)
 {
     if ((int)s.h_ops.size() > sb::C_OPS_MAX) return fail(ctx, SB_ERR_ARG, "tree program too long for constant memory");
-    if (s.W32p > sb::C_LABEL_WORDS / sb::PERMS_PER_ITEM) return fail(ctx, SB_ERR_ARG, "too many leaves for constant memory");
+    if (s.W32p > sb::C_LABEL_WORDS / sb::PERMS_PER_ITEM_MAX) return fail(ctx, SB_ERR_ARG, "too many leaves for constant memory");
     SB_CUDA(ctx, cudaMemcpyToSymbolAsync(sb::c_ops, s.h_ops.data(), sizeof(uint16_t) * s.h_ops.size(), 0,
                                          cudaMemcpyHostToDevice, ctx->stream));
     return SB_OK;
@@ -561,9 +561,14 @@ int launch_permute(sb_ctx *ctx, int32_t t, const int64_t *d_gene_idx, int64_t S,
     rc = upload_program(ctx, s);
     if (rc) return rc;
 
-    const int ppi = sb::PERMS_PER_ITEM;
+    // labellings per block: as many as 4 (fewer hit bytes), but few enough that one launch still
+    // has a couple of blocks for every resident slot when only few genes are walked
+    const int label_cap = (sb::C_LABEL_WORDS / s.W32p) / sb::PERMS_PER_ITEM_MAX * sb::PERMS_PER_ITEM_MAX;
+    const int64_t tiles_all = (S + (int64_t)sb::WALK_THREADS * sb::WALK_NP - 1) / ((int64_t)sb::WALK_THREADS * sb::WALK_NP);
+    int ppi = sb::PERMS_PER_ITEM_MAX;
+    while (ppi > 1 && tiles_all * ((std::min(label_cap, P) + ppi - 1) / ppi) < 2LL * 7 * ctx->sm_count) ppi /= 2;
     const int n_chunks = (P + ppi - 1) / ppi;
-    int perms_per_launch = (sb::C_LABEL_WORDS / s.W32p) / ppi * ppi;
+    int perms_per_launch = label_cap;
     const int n_launches = (P + perms_per_launch - 1) / perms_per_launch;
     rc = ensure_scratch(ctx, 1, (size_t)n_chunks * (size_t)S);
     if (rc) return rc;
@@ -582,6 +587,7 @@ int launch_permute(sb_ctx *ctx, int32_t t, const int64_t *d_gene_idx, int64_t S,
         A.S_total = S;
         A.slot_idx = d_list;
         A.n_perms = n_perms;
+        A.ppi = ppi;
         A.items_per_tile = (n_perms + ppi - 1) / ppi;
         A.chunk_base = base / ppi;
         A.unperm = d_unperm;
@@ -602,7 +608,7 @@ int launch_permute(sb_ctx *ctx, int32_t t, const int64_t *d_gene_idx, int64_t S,
             if (rc) return rc;
         }
         Timed tm(ctx, CAT_REDUCE);
-        sb::reduce_hits_kernel<<<(unsigned)((S + 255) / 256), 256, 0, ctx->stream>>>(d_hits, S, n_chunks, P, 0, d_rmin, d_r,
+        sb::reduce_hits_kernel<<<(unsigned)((S + 255) / 256), 256, 0, ctx->stream>>>(d_hits, S, n_chunks, ppi, P, 0, d_rmin, d_r,
                                                                                     d_n_done);
         ctx->stats.kernel_launches += 1;
         SB_CUDA(ctx, cudaGetLastError());
@@ -628,7 +634,7 @@ int launch_permute(sb_ctx *ctx, int32_t t, const int64_t *d_gene_idx, int64_t S,
         {
             Timed tm(ctx, CAT_REDUCE);
             sb::advance_hits_kernel<<<(unsigned)((n_alive + 255) / 256), 256, 0, ctx->stream>>>(
-                d_hits, S, cur, (int32_t)n_alive, base, n_perms, P, d_rmin, d_r, d_n_done, out, d_counter);
+                d_hits, S, cur, (int32_t)n_alive, base, n_perms, P, ppi, d_rmin, d_r, d_n_done, out, d_counter);
             ctx->stats.kernel_launches += 1;
             SB_CUDA(ctx, cudaGetLastError());
         }

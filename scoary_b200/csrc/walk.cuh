@@ -162,7 +162,7 @@ constexpr int OP_END = 0,
 // raw (pre-fusion) steps used only by the host compiler
 constexpr int RAW_LEAF_B16 = 14, RAW_MERGE_AB16 = 15;
 constexpr int OP_TYPE_BITS = 4, OP_MAX_COUNT = 4095;
-constexpr int PERMS_PER_ITEM = 4;          // labellings walked per block (one byte of hit flags per gene)
+constexpr int PERMS_PER_ITEM_MAX = 4;      // labellings walked per block: 4, 2 or 1 (one byte of hit flags per gene)
 // 16-bit keys: (pairs << 6) + x with pairs, x <= 63  ->  subtrees of at most 127 leaves.
 // Unreachable = -16384 (+ drift < 4096), so valid + unreachable < 0 and unreachable + unreachable
 // >= -32768 never wraps; both halves of a register follow the same rules as the 32-bit keys.
@@ -380,11 +380,12 @@ struct WalkArgs {
     int32_t W32p;
     int32_t shift;             // SH
     int32_t n_perms;           // labellings in constant memory for this launch (permute mode)
-    int32_t items_per_tile;    // ceil(n_perms / PERMS_PER_ITEM)
+    int32_t ppi;               // labellings per block (PERMS_PER_ITEM_MAX or less when few genes are walked)
+    int32_t items_per_tile;    // ceil(n_perms / ppi)
     int32_t chunk_base;        // first hit-byte row of this launch
     const int32_t *unperm;     // [S][3] (permute mode): unpermuted Total, Pro, Anti
     int32_t *pairs;            // [S][3] (pairs mode output)
-    uint8_t *hits;             // [n_chunks_total][S] (permute mode output): bit r = perm 4*chunk + r hit
+    uint8_t *hits;             // [n_chunks_total][S] (permute mode output): bit r = perm ppi*chunk + r hit
 };
 
 #ifndef SB_WALK_NPAIR
@@ -680,8 +681,8 @@ __global__ void __launch_bounds__(WALK_THREADS, SB_WALK_MINBLOCKS) walk_permute_
     int *stk = smem_stack + threadIdx.x;
     constexpr int NP = WALK_NP;
     const int chunk = blockIdx.y;
-    const int perm0 = chunk * PERMS_PER_ITEM;
-    const int rows = min(PERMS_PER_ITEM, A.n_perms - perm0);
+    const int perm0 = chunk * A.ppi;
+    const int rows = min(A.ppi, A.n_perms - perm0);
     int64_t s_idx[NP], sc[NP]; bool active[NP]; const uint32_t *gcol[NP];
     walk_slots<NP>(A, blockIdx.x, s_idx, active, sc, gcol);
     const int K = 1 << A.shift;
@@ -726,24 +727,25 @@ __global__ void __launch_bounds__(WALK_THREADS, SB_WALK_MINBLOCKS) walk_permute_
 // ---------------------------------------------------------------- hit-sequence reduction
 // Permute's bookkeeping (methods.py:1348-1365) on the ordered hit flags.
 __global__ void __launch_bounds__(256) reduce_hits_kernel(const uint8_t *__restrict__ hits, int64_t S, int n_chunks,
-                                                          int P, int early_stop, const int32_t *__restrict__ rmin,
-                                                          int32_t *__restrict__ r_out, int32_t *__restrict__ n_done)
+                                                          int ppi, int P, int early_stop,
+                                                          const int32_t *__restrict__ rmin, int32_t *__restrict__ r_out,
+                                                          int32_t *__restrict__ n_done)
 {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
     int r = 0, done = P;
     if (!early_stop) {
         for (int c = 0; c < n_chunks; ++c) {
-            const int rows = min(PERMS_PER_ITEM, P - c * PERMS_PER_ITEM);
+            const int rows = min(ppi, P - c * ppi);
             r += __popc((uint32_t)hits[(int64_t)c * S + s] & ((1u << rows) - 1u));
         }
     } else {
         bool stop = false;
         for (int c = 0; c < n_chunks && !stop; ++c) {
-            const int rows = min(PERMS_PER_ITEM, P - c * PERMS_PER_ITEM);
+            const int rows = min(ppi, P - c * ppi);
             const uint32_t w = hits[(int64_t)c * S + s];
             for (int b = 0; b < rows; ++b) {
-                const int i = c * PERMS_PER_ITEM + b;
+                const int i = c * ppi + b;
                 r += (w >> b) & 1u;
                 if (i >= 30 && r >= rmin[i]) {   // methods.py:1360-1363
                     done = i + 1;
@@ -762,7 +764,7 @@ __global__ void __launch_bounds__(256) reduce_hits_kernel(const uint8_t *__restr
 // slots that neither stopped nor reached P are appended to list_out for the next slice.
 __global__ void __launch_bounds__(256) advance_hits_kernel(const uint8_t *__restrict__ hits, int64_t S_total,
                                                            const int32_t *__restrict__ list_in, int32_t n_in, int base,
-                                                           int n, int P, const int32_t *__restrict__ rmin,
+                                                           int n, int P, int ppi, const int32_t *__restrict__ rmin,
                                                            int32_t *__restrict__ r_arr, int32_t *__restrict__ n_done,
                                                            int32_t *__restrict__ list_out, int32_t *__restrict__ counter)
 {
@@ -771,8 +773,8 @@ __global__ void __launch_bounds__(256) advance_hits_kernel(const uint8_t *__rest
     const int slot = list_in ? list_in[e] : e;
     int r = (base == 0) ? 0 : r_arr[slot];
     for (int i = base; i < base + n; ++i) {
-        const uint32_t byte = hits[(int64_t)(i / PERMS_PER_ITEM) * S_total + slot];
-        r += (byte >> (i % PERMS_PER_ITEM)) & 1u;
+        const uint32_t byte = hits[(int64_t)(i / ppi) * S_total + slot];
+        r += (byte >> (i % ppi)) & 1u;
         if (i >= 30 && r >= rmin[i]) {   // methods.py:1360-1363
             r_arr[slot] = r;
             n_done[slot] = i + 1;

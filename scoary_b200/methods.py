@@ -51,15 +51,20 @@ def get_engine():
 class GeneTable(Mapping):
     """Gene presence/absence table: the packed form of the reference's `genedic`
     (dict gene -> {isolate: 0/1, "Non-unique Gene name", "Annotation", "<col>_name"}).
-    Behaves like that dict for readers, but keeps the matrix as uint8 [G][N]."""
+    Behaves like that dict for readers; the data live as uint64 bitset rows [G][W] (what
+    sb_set_genes takes) and are unpacked to uint8 [G][N] only on demand (`.matrix`)."""
 
-    def __init__(self, names, nugn, annotation, strains, matrix, extra=None):
+    def __init__(self, names, nugn, annotation, strains, matrix=None, extra=None, bits=None):
         self.names = list(names)
         self.nugn = list(nugn)
         self.annotation = list(annotation)
         self.strains = list(strains)
-        self.matrix = np.ascontiguousarray(matrix, dtype=np.uint8).reshape(len(self.names), len(self.strains))
         self.extra = extra or {}
+        if bits is None:
+            m = np.ascontiguousarray(matrix, dtype=np.uint8).reshape(len(self.names), len(self.strains))
+            bits = eng.pack_rows(m) if len(self.names) else np.zeros((0, eng.words_for(len(self.strains))), np.uint64)
+        self.bits = np.ascontiguousarray(bits, dtype=np.uint64)
+        self._matrix = None
         # the reference's dict keeps the LAST row of a duplicated identifier at the position of
         # its FIRST occurrence (methods.py:450,462)
         last, first = {}, {}
@@ -72,10 +77,23 @@ class GeneTable(Mapping):
             self.names = order
             self.nugn = [self.nugn[r] for r in rows]
             self.annotation = [self.annotation[r] for r in rows]
-            self.matrix = np.ascontiguousarray(self.matrix[rows])
+            self.bits = np.ascontiguousarray(self.bits[rows])
             self.extra = {k: [v[r] for r in rows] for k, v in self.extra.items()}
         self.index = {n: i for i, n in enumerate(self.names)}
         self.col = {s: j for j, s in enumerate(self.strains)}
+
+    @property
+    def matrix(self):
+        """uint8 [G][N], unpacked on first use"""
+        if self._matrix is None:
+            self._matrix = self.rows_matrix(np.arange(len(self.names)))
+        return self._matrix
+
+    def rows_matrix(self, rows):
+        """uint8 [len(rows)][N] for a subset of gene rows"""
+        b = np.ascontiguousarray(self.bits[np.asarray(rows, dtype=np.int64)])
+        by = b.view(np.uint8).reshape(b.shape[0], -1)
+        return np.unpackbits(by, axis=1, bitorder="little")[:, :len(self.strains)]
 
     @classmethod
     def from_dict(cls, genedic, strains=None):
@@ -107,7 +125,7 @@ class GeneTable(Mapping):
     def __getitem__(self, gene):
         i = self.index[gene]
         row = {"Non-unique Gene name": self.nugn[i], "Annotation": self.annotation[i]}
-        row.update(zip(self.strains, self.matrix[i].tolist()))
+        row.update(zip(self.strains, self.rows_matrix([i])[0].tolist()))
         for k, v in self.extra.items():
             row[k] = v[i]
         return row
@@ -130,6 +148,11 @@ def Csv_to_dic_Roary(genefile, delimiter, grabcols, startcol=14, allowed_isolate
     if writereducedset:
         opened = open(ReduceSet(genefile, delimiter, grabcols, startcol, allowed_isolates, time, outdir), "r")
         genefile = opened
+    import io
+    path = getattr(genefile, "name", None)
+    raw = getattr(getattr(genefile, "buffer", None), "raw", None)
+    native = (isinstance(path, str) and isinstance(raw, io.FileIO) and os.path.isfile(path)     # a plain file on disk
+              and os.environ.get("SCOARY_B200_PY_CSV") != "1")
     rdr = csv.reader(genefile, skipinitialspace=True, delimiter=delimiter)
     header = next(rdr)
     if grabcols == [-999]:
@@ -170,10 +193,22 @@ def Csv_to_dic_Roary(genefile, delimiter, grabcols, startcol=14, allowed_isolate
     else:
         genecol, nugcol, anncol = 0, 1, 2
         firstcolnames = header[0:3]
+    src_cols = [startcol + c for c in keep_cols]
+    if native:
+        table = _native_gene_table(path, delimiter, roaryfile, genecol, nugcol, anncol, grabcols, header, src_cols,
+                                   strain_names_allowed)
+        if opened:
+            opened.close()
+        s = _popcount_rows(table.bits)
+        variable = (s > 0) & (s < len(strain_names_allowed))
+        zero_ones = None
+        if int(variable.sum()) * len(strain_names_allowed) <= 200_000_000:
+            zero_ones = np.ascontiguousarray(table.rows_matrix(np.flatnonzero(variable)).T)
+        return {"Roarydic": table, "Zero_ones_matrix": zero_ones, "Strains": strain_names_allowed,
+                "Extracols": extracolstoprint, "Firstcolnames": firstcolnames}
     names, nugn, ann, rows = [], [], [], []
     extra = {header[c] + "_name": [] for c in grabcols}
     absent = ("", "0", "-")
-    src_cols = [startcol + c for c in keep_cols]
     for q in rdr:
         try:
             ident = q[genecol] if roaryfile else q[genecol] + "_|_" + q[nugcol] + "_|_" + q[anncol]
@@ -197,6 +232,56 @@ def Csv_to_dic_Roary(genefile, delimiter, grabcols, startcol=14, allowed_isolate
     zero_ones = np.ascontiguousarray(matrix[variable].T)              # isolates x variable genes
     return {"Roarydic": table, "Zero_ones_matrix": zero_ones, "Strains": strain_names_allowed,
             "Extracols": extracolstoprint, "Firstcolnames": firstcolnames}
+
+
+def _popcount_rows(bits):
+    b = np.ascontiguousarray(bits).view(np.uint8)
+    return np.unpackbits(b, axis=1).sum(axis=1, dtype=np.int64) if b.size else np.zeros(bits.shape[0], np.int64)
+
+
+def _native_gene_table(path, delimiter, roaryfile, genecol, nugcol, anncol, grabcols, header, src_cols, strains):
+    """The row loop of Csv_to_dic_Roary (methods.py:445-497) through libscoary_b200's native
+    packer (sb_csv_row_starts / sb_csv_pack_rows): presence bits are packed straight into the
+    uint64 rows the GPU takes; only the few text fields are sliced out here."""
+    import ctypes
+    from . import _lib
+    lib = _lib.load()
+    with open(path, "rb") as fh:
+        buf = fh.read()
+    n = lib.sb_csv_row_starts(buf, len(buf), None, 0, None)
+    if n < 0:
+        sys.exit("CRITICAL: Could not read gene presence absence file.")
+    starts = np.empty(max(n, 1), dtype=np.int64)
+    lib.sb_csv_row_starts(buf, len(buf), starts.ctypes.data_as(ctypes.c_void_p), n, None)
+    W = eng.words_for(len(src_cols))
+    bits = np.empty((n, W), dtype=np.uint64)
+    lead = sorted(set([genecol, nugcol, anncol] + list(grabcols)))
+    lead_arr = np.asarray(lead, dtype=np.int32)
+    keep_arr = np.asarray(src_cols, dtype=np.int32)
+    ranges = np.empty((n, len(lead), 2), dtype=np.int64)
+    nfields = np.empty(max(n, 1), dtype=np.int32)
+    rc = lib.sb_csv_pack_rows(buf, len(buf), delimiter.encode()[:1], starts.ctypes.data_as(ctypes.c_void_p), n,
+                              keep_arr.ctypes.data_as(ctypes.c_void_p), len(src_cols),
+                              bits.ctypes.data_as(ctypes.c_void_p), W, lead_arr.ctypes.data_as(ctypes.c_void_p),
+                              len(lead), ranges.ctypes.data_as(ctypes.c_void_p), nfields.ctypes.data_as(ctypes.c_void_p))
+    if rc != 0:
+        sys.exit("CRITICAL: Could not read gene presence absence file. Verify that this file is a proper Roary "
+                 "file using the specified delimiter (default is ',').")
+    slot = {c: k for k, c in enumerate(lead)}
+
+    def field(r, c):
+        b, e = int(ranges[r, slot[c], 0]), int(ranges[r, slot[c], 1])
+        if b < 0:      # escaped quotes or text after a closing quote: let the csv module unescape it
+            raw = buf[-b - 1 - 1:e].decode("utf-8", "replace")
+            return next(csv.reader([raw], skipinitialspace=True, delimiter=delimiter))[0]
+        return buf[b:e].decode("utf-8", "replace")
+
+    gene = [field(r, genecol) for r in range(n)]
+    nug = [field(r, nugcol) for r in range(n)]
+    ann = [field(r, anncol) for r in range(n)]
+    names = gene if roaryfile else [g + "_|_" + u + "_|_" + a for g, u, a in zip(gene, nug, ann)]
+    extra = {header[c] + "_name": [field(r, c) for r in range(n)] for c in grabcols}
+    return GeneTable(names, nug, ann, strains, extra=extra, bits=bits)
 
 
 def ReduceSet(genefile, delimiter, grabcols, startcol=14, allowed_isolates=None, time="", outdir="./"):
@@ -260,7 +345,7 @@ def upgma(table):
     if len(table.strains) < 2:
         sys.exit("Need at least two isolates to build a tree")
     e = get_engine()
-    e.set_genes(eng.pack_rows(table.matrix), len(table.strains))
+    e.set_genes(table.bits, len(table.strains))
     return treemod.from_merges(table.strains, e.upgma())
 
 
@@ -302,13 +387,13 @@ class _TraitGTC(Mapping):
         return iter(self.row_of)
 
     def __getitem__(self, gene):
-        g = self.table.matrix[self.row_of[gene], self.cols]
+        g = self.table.rows_matrix([self.row_of[gene]])[0][self.cols]
         return {s: ("A" if gi else "a") + ("B" if ti else "b") for s, gi, ti in zip(self.isolates, g, self.labels)}
 
     def gene_bits(self, genes, isolates):
         cols = np.asarray([self.table.col[s] for s in isolates], dtype=np.int64)
         rows = np.asarray([self.row_of[g] for g in genes], dtype=np.int64)
-        return self.table.matrix[np.ix_(rows, cols)]
+        return self.table.rows_matrix(rows)[:, cols]
 
     def trait_bits(self, isolates):
         lab = dict(zip(self.isolates, self.labels))
@@ -359,7 +444,7 @@ def Setup_results(genedic, traitsdic, collapse):
     (sb_contingency_fisher).  Returns {"Results": ..., "Gene_trait_combinations": ...}."""
     table = GeneTable.from_dict(genedic)
     e = get_engine()
-    e.set_genes(eng.pack_rows(table.matrix), len(table.strains))
+    e.set_genes(table.bits, len(table.strains))
     all_traits, gtc = {}, {}
     for t_idx, trait in enumerate(traitsdic):
         log.info("Gene-wise counting and Fisher's exact tests for trait: %s" % str(trait))

@@ -164,3 +164,45 @@ def test_reference_style_dict_inputs(fake_engine):
     assert set(w) == {"Total", "Pro", "Anti"} and w["Total"] >= max(w["Pro"], w["Anti"])
     emp = M.Permute(tree, gtc, 50, {"I": 0.05})
     assert 0.0 < emp <= 1.0
+
+
+def _write_tricky_csv(path, G=120, N=70, seed=3):
+    rng = np.random.default_rng(seed)
+    hdr = M.ROARY_COLUMNS[:14] + ["Iso_%03d" % i for i in range(N)]
+    with open(path, "w", newline="") as fh:
+        fh.write(",".join('"%s"' % h for h in hdr) + "\r\n")
+        for g in range(G):
+            pres = rng.random(N) < rng.uniform(0.05, 0.95)
+            cells = ['"locus_%d_%d"' % (g, j) if pres[j] else ['""', '0', '"-"', '', ' ""', '-'][(g + j) % 6] for j in range(N)]
+            ann = '"hypothetical, protein ""%d"" x"' % g if g % 7 == 0 else '"annot %d"' % g
+            fh.write('"gene_%d","nug%d",%s,"1","2","3","4","5","6","7","","8","9","10",' % (g, g, ann) + ",".join(cells)
+                     + ("\r\n" if g % 2 else "\n"))
+
+
+def test_native_csv_packer_equals_python_parser(tmp_path, monkeypatch, inputs):
+    """sb_csv_pack_rows == the csv-module parser (which the golden CLI files pin),
+    on the reference's example data and on a file with quoted commas, escaped quotes, mixed line ends,
+    spaces after delimiters and every spelling of an absent cell."""
+    tricky = str(tmp_path / "tricky.csv")
+    _write_tricky_csv(tricky)
+    for path, grab, allowed in [(inputs["g"], [], None), (tricky, [3, 10], None),
+                                (tricky, [], {"Iso_%03d" % i: "all" for i in range(0, 70, 3)})]:
+        monkeypatch.delenv("SCOARY_B200_PY_CSV", raising=False)
+        with open(path) as fh:
+            a = M.Csv_to_dic_Roary(fh, ",", list(grab), startcol=14, allowed_isolates=allowed)
+        monkeypatch.setenv("SCOARY_B200_PY_CSV", "1")
+        with open(path, newline="") as fh:
+            b = M.Csv_to_dic_Roary(fh, ",", list(grab), startcol=14, allowed_isolates=allowed)
+        ta, tb = a["Roarydic"], b["Roarydic"]
+        assert ta.names == tb.names and ta.nugn == tb.nugn and ta.annotation == tb.annotation
+        assert np.array_equal(ta.bits, tb.bits) and ta.extra == tb.extra and a["Strains"] == b["Strains"]
+        assert np.array_equal(a["Zero_ones_matrix"], b["Zero_ones_matrix"])
+    monkeypatch.delenv("SCOARY_B200_PY_CSV", raising=False)
+    short = str(tmp_path / "short.csv")
+    with open(tricky) as fh:
+        lines = fh.read().splitlines()
+    lines[5] = ",".join(lines[5].split(",")[:20])
+    open(short, "w").write("\n".join(lines) + "\n")
+    with pytest.raises(SystemExit) as ex, open(short) as fh:
+        M.Csv_to_dic_Roary(fh, ",", [], startcol=14)
+    assert "Could not read gene presence absence file" in str(ex.value.code)
