@@ -457,7 +457,7 @@ def run_ours(a):
               "frac": fisher_bytes / (fisher_ms * 1e-3) / 1e9 / hbm_peak}
 
     cpu = None
-    if not a.no_cpu_baseline:
+    if not a.no_cpu_baseline and world == 1:      # rank 0 at N = 1 only
         run, tests, threads, sample = cpu_sample(G, N, T, P, seed, 6.0)
         dt = run()
         cpu = {"value": tests / dt, "unit": "tests/s", "cores": threads, "kind": "port", "sample": sample}

@@ -567,6 +567,7 @@ int launch_permute(sb_ctx *ctx, int32_t t, const int64_t *d_gene_idx, int64_t S,
     const int64_t tiles_all = (S + (int64_t)sb::WALK_THREADS * sb::WALK_NP - 1) / ((int64_t)sb::WALK_THREADS * sb::WALK_NP);
     int ppi = sb::PERMS_PER_ITEM_MAX;
     while (ppi > 1 && tiles_all * ((std::min(label_cap, P) + ppi - 1) / ppi) < 2LL * 7 * ctx->sm_count) ppi /= 2;
+    if (early_stop) ppi = 1;   // later rounds walk few genes: one labelling per block keeps every SM busy
     const int n_chunks = (P + ppi - 1) / ppi;
     int perms_per_launch = label_cap;
     const int n_launches = (P + perms_per_launch - 1) / perms_per_launch;
