@@ -51,6 +51,8 @@ struct TraitSlot {
     uint32_t *d_labels_leaf = nullptr;   // [W32]  by leaf id
     uint32_t *d_labels0 = nullptr;       // [W32p] walk order, unpermuted
     uint32_t *d_genesT = nullptr;        // [W32p][Gs]
+    size_t genesT_cap = 0;               // bytes allocated behind d_genesT (reused when large enough)
+    bool genesT_valid = false;
     int64_t Gs = 0;
 };
 
@@ -67,6 +69,8 @@ struct sb_ctx {
     int32_t N = 0, W = 0;
     uint64_t *d_genes = nullptr;
     bool own_genes = false;
+    uint64_t *d_genes_buf = nullptr;   // the context's own allocation (reused across sb_set_genes calls)
+    size_t genes_cap = 0;
     // lut
     double2 *d_lut = nullptr;
     int32_t lut_n = -1;
@@ -168,9 +172,15 @@ void free_tree(TraitSlot &s)
     cudaFree(s.d_leaf_of_pos); s.d_leaf_of_pos = nullptr;
     cudaFree(s.d_labels_leaf); s.d_labels_leaf = nullptr;
     cudaFree(s.d_labels0); s.d_labels0 = nullptr;
-    cudaFree(s.d_genesT); s.d_genesT = nullptr;
+    s.genesT_valid = false;              // the allocation itself is kept for the next tree
     s.has_tree = false;
     s.finalized = false;
+}
+
+void free_tree_storage(TraitSlot &s)
+{
+    free_tree(s);
+    cudaFree(s.d_genesT); s.d_genesT = nullptr; s.genesT_cap = 0;
 }
 
 void free_trait(TraitSlot &s)
@@ -380,7 +390,6 @@ int set_genes_common(sb_ctx *ctx, int64_t G, int32_t N, int32_t W)
 {
     if (G <= 0 || N <= 0) return fail(ctx, SB_ERR_ARG, "sb_set_genes: G and N must be positive");
     if (W < (N + 63) / 64 || (W & 1)) return fail(ctx, SB_ERR_ARG, "sb_set_genes: W must be even and >= ceil(N/64)");
-    if (ctx->own_genes && ctx->d_genes) SB_CUDA(ctx, cudaFree(ctx->d_genes));
     ctx->d_genes = nullptr;
     ctx->own_genes = false;
     if (N != ctx->N || W != ctx->W) {
@@ -388,8 +397,7 @@ int set_genes_common(sb_ctx *ctx, int64_t G, int32_t N, int32_t W)
     }
     for (auto &s : ctx->traits) {   // gene-dependent derived data is stale
         s.finalized = false;
-        cudaFree(s.d_genesT);
-        s.d_genesT = nullptr;
+        s.genesT_valid = false;
     }
     ctx->G = G; ctx->N = N; ctx->W = W;
     return ensure_lut(ctx, N);
@@ -424,9 +432,15 @@ int finalize_slot(sb_ctx *ctx, int32_t t)
                                  ctx->stream));
     SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->stats.h2d_bytes += (int64_t)sizeof(uint32_t) * (s.W32 + s.W32p);
-    if (!s.d_genesT) {
+    if (!s.genesT_valid) {
         s.Gs = (ctx->G + 31) / 32 * 32;
-        SB_CUDA(ctx, cudaMalloc(&s.d_genesT, sizeof(uint32_t) * (size_t)s.W32p * (size_t)s.Gs));
+        const size_t need = sizeof(uint32_t) * (size_t)s.W32p * (size_t)s.Gs;
+        if (need > s.genesT_cap) {
+            if (s.d_genesT) SB_CUDA(ctx, cudaFree(s.d_genesT));
+            s.d_genesT = nullptr; s.genesT_cap = 0;
+            SB_CUDA(ctx, cudaMalloc(&s.d_genesT, need));
+            s.genesT_cap = need;
+        }
         const size_t smem = sizeof(uint32_t) * 32 * (size_t)(2 * ctx->W + 1);
         if (smem > (size_t)ctx->max_smem_optin) return fail(ctx, SB_ERR_ARG, "too many isolates for the pack kernel");
         SB_CUDA(ctx, cudaFuncSetAttribute(sb::pack_walk_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -437,6 +451,7 @@ int finalize_slot(sb_ctx *ctx, int32_t t)
                                                                        s.n_leaves, s.W32p, s.Gs, s.d_genesT);
         ctx->stats.kernel_launches += 1;
         SB_CUDA(ctx, cudaGetLastError());
+        s.genesT_valid = true;
     }
     s.finalized = true;
     return SB_OK;
@@ -708,8 +723,8 @@ void sb_destroy(sb_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     resolve_events(ctx);
     for (auto &e : ctx->free_events) { cudaEventDestroy(e.start); cudaEventDestroy(e.stop); }
-    for (auto &s : ctx->traits) { free_trait(s); free_tree(s); }
-    if (ctx->own_genes) cudaFree(ctx->d_genes);
+    for (auto &s : ctx->traits) { free_trait(s); free_tree_storage(s); }
+    cudaFree(ctx->d_genes_buf);
     cudaFree(ctx->d_lut);
     cudaFree(ctx->d_peak_out);
     for (auto p : ctx->d_scratch) cudaFree(p);
@@ -766,7 +781,13 @@ int sb_set_genes(sb_ctx *ctx, const uint64_t *bits, int64_t G, int32_t N, int32_
     int rc = set_genes_common(ctx, G, N, W);
     if (rc) return rc;
     const size_t bytes = sizeof(uint64_t) * (size_t)G * (size_t)W;
-    SB_CUDA(ctx, cudaMalloc(&ctx->d_genes, bytes));
+    if (bytes > ctx->genes_cap) {       // grow the context's own buffer; otherwise reuse it
+        if (ctx->d_genes_buf) SB_CUDA(ctx, cudaFree(ctx->d_genes_buf));
+        ctx->d_genes_buf = nullptr; ctx->genes_cap = 0;
+        SB_CUDA(ctx, cudaMalloc(&ctx->d_genes_buf, bytes));
+        ctx->genes_cap = bytes;
+    }
+    ctx->d_genes = ctx->d_genes_buf;
     ctx->own_genes = true;
     SB_CUDA(ctx, cudaMemcpyAsync(ctx->d_genes, bits, bytes, cudaMemcpyHostToDevice, ctx->stream));
     ctx->stats.h2d_bytes += (int64_t)bytes;
