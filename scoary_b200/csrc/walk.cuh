@@ -39,7 +39,7 @@ namespace sb {
 #define SB_WALK_THREADS 128
 #endif
 #ifndef SB_WALK_MINBLOCKS
-#define SB_WALK_MINBLOCKS 6
+#define SB_WALK_MINBLOCKS 5
 #endif
 constexpr int WALK_THREADS = SB_WALK_THREADS;
 constexpr int WALK_NEG = -(1 << 30);   // unreachable; keys stay < 2^28 (n_leaves <= 32766), so inv+inv >= INT_MIN
@@ -389,7 +389,7 @@ struct WalkArgs {
 };
 
 #ifndef SB_WALK_NPAIR
-#define SB_WALK_NPAIR 1
+#define SB_WALK_NPAIR 2
 #endif
 constexpr int WALK_NPAIR = SB_WALK_NPAIR;   // gene pairs per thread
 constexpr int WALK_NP = 2 * WALK_NPAIR;     // genes per thread
