@@ -19,6 +19,7 @@ Fixtures written:
   walks.json       random trees x gene-trait combinations -> reference ConvertUPGMAtoPhyloTree
   upgma.json       random presence matrices -> reference CreateTriangularDistanceMatrix/QuadTree/upgma tree
   fisher.json      2x2 tables -> scipy.stats.fisher_exact as the reference calls it (methods.py:854)
+  vcf/*.csv        reference vcf2scoary output for Example.vcf and a generated multi-allelic VCF
   tetrcg_first_row.json   the reference's own CI golden (tests/test_scoary_output.py:12-14)
 """
 import gzip
@@ -147,6 +148,40 @@ def main():
         upg.append({"matrix": mat.tolist(), "tree": tree})
     with open(os.path.join(HERE, "upgma.json"), "w") as fh:
         json.dump(upg, fh, separators=(",", ":"))
+    # ---- vcf2scoary (scoary/vcf2scoary.py) on its example and on a generated multi-allelic VCF
+    import importlib
+    conv = importlib.import_module("scoary.vcf2scoary")
+    vdir = os.path.join(HERE, "vcf")
+    os.makedirs(vdir, exist_ok=True)
+    shutil.copyfile(os.path.join(EX, "Example.vcf"), os.path.join(vdir, "Example.vcf"))
+    vr = random.Random(5)
+    vl = ["##fileformat=VCFv4.2", '##FORMAT=<ID=GT,Number=1,Type=String,Description="Genotype">',
+          '##FORMAT=<ID=DP,Number=1,Type=Integer,Description="Depth">',
+          '##INFO=<ID=TYPE,Number=A,Type=String,Description="The type of allele.">']
+    samples = ["S%02d" % i for i in range(37)]
+    vl.append("\t".join(["#CHROM", "POS", "ID", "REF", "ALT", "QUAL", "FILTER", "INFO", "FORMAT"] + samples))
+    for k in range(300):
+        nalt = vr.choice([1, 1, 1, 2, 3])
+        alts = ",".join(vr.sample("ACGT", nalt))
+        typ = vr.choice(["snp", "ins", "del", "complex"])
+        cells = []
+        for _ in samples:
+            g = vr.choice(["0", "0", "1", ".", "2" if nalt > 1 else "1", "3" if nalt > 2 else "0"])
+            cells.append(g + ":" + str(vr.randint(1, 99)))
+        vl.append("\t".join(["chr%d" % (k % 3), str(100 + k * 7), "id%d" % k if k % 4 else ".", "A", alts, "99", "PASS",
+                             "TYPE=%s" % typ, "GT:DP"] + cells))
+    with open(os.path.join(vdir, "generated.vcf"), "w") as fh:
+        fh.write("\n".join(vl) + "\n")
+    for vname, vtypes in (("Example", None), ("generated", None), ("generated", "snp,del")):
+        outp = os.path.join(vdir, vname + ("_snp_del" if vtypes else "") + ".csv")
+        old = sys.argv
+        sys.argv = ["vcf2scoary", "--force", "--out", outp] + (["--types", vtypes] if vtypes else []) + \
+                   [os.path.join(vdir, vname + ".vcf")]
+        try:
+            conv.main()
+        except SystemExit:
+            pass
+        sys.argv = old
     # ---- the reference's own CI golden row
     with open(os.path.join(HERE, "tetrcg_first_row.json"), "w") as fh:
         json.dump({"source": "tests/test_scoary_output.py:12-14",

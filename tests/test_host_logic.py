@@ -206,3 +206,31 @@ def test_native_csv_packer_equals_python_parser(tmp_path, monkeypatch, inputs):
     with pytest.raises(SystemExit) as ex, open(short) as fh:
         M.Csv_to_dic_Roary(fh, ",", [], startcol=14)
     assert "Could not read gene presence absence file" in str(ex.value.code)
+
+
+@pytest.mark.parametrize("name,types", [("Example", None), ("generated", None), ("generated", "snp,del")])
+def test_vcf2scoary_matches_reference_converter(name, types, tmp_path):
+    """same output file as scoary/vcf2scoary.py (goldens written by the reference),
+    and the direct VCF -> packed table path equals parsing that file."""
+    from scoary_b200 import vcf2scoary as V
+    gold = os.path.join(GOLD, "vcf")
+    out = str(tmp_path / "out.csv")
+    argv = ["--force", "--out", out] + (["--types", types] if types else []) + [os.path.join(gold, name + ".vcf")]
+    with pytest.raises(SystemExit) as ex:
+        V.main(argv)
+    assert ex.value.code == 0
+    want = os.path.join(gold, name + ("_snp_del" if types else "") + ".csv")
+    assert open(out).read() == open(want).read()
+    table = V.vcf_to_table(os.path.join(gold, name + ".vcf"), types.split(",") if types else "ALL")
+    with open(want, newline="") as fh:
+        ref = M.Csv_to_dic_Roary(fh, ",", [], startcol=10)["Roarydic"]
+    # the reference's dict keeps one row per identifier (last wins): compare after the same de-duplication
+    assert table.names == ref.names and table.strains == ref.strains[0:] and np.array_equal(table.bits, ref.bits)
+
+
+def test_vcf_first_row_is_the_reference_ci_golden():
+    """tests/test_scoary_output.py:16-17,123-136 of the reference"""
+    import csv
+    with open(os.path.join(GOLD, "vcf", "Example.csv")) as fh:
+        rows = list(csv.reader(fh))
+    assert rows[1] == ["NC_000962", "4013", "0", "T", "C", "9999", "0", "TYPE=snp", "GT", "False", "0", "1", "1", "1"]
