@@ -391,6 +391,51 @@ def run_ours(a):
     torch.cuda.synchronize()
     fisher_ms = f0.elapsed_time(f1)
 
+    # ---- BASELINE configs[1] itself (10k genes x 1k isolates, Fisher only, no tree): a second, small line
+    c2 = None
+    if rank == 0 and a.workload != "c2":
+        G2, N2, _, _, seed2 = synth.CONFIGS["c2"]
+        tr2 = synth.make_traits(N2, 1, seed2)
+        bits2 = synth.make_genes_packed(G2, N2, seed2, traits=tr2)
+        W2 = words_for(N2)
+        pin2 = torch.empty((G2, W2), dtype=torch.int64, pin_memory=True)
+        pin2.numpy().view(np.uint64)[:] = bits2
+        d_bits2 = pin2.to(dev)
+        e.set_stream(stream.cuda_stream)
+        e.set_genes_device(d_bits2.data_ptr(), G2, N2, W2)
+        e.set_trait_vector(0, tr2[0])
+        dc2 = torch.empty((G2, 4), dtype=torch.int32, device=dev)
+        dp2 = torch.empty(G2, dtype=torch.float64, device=dev)
+        for _ in range(3):
+            e.contingency_fisher_device(0, dc2.data_ptr(), dp2.data_ptr())
+        reps, tot = 20, 0.0
+        for _ in range(reps):
+            flush.zero_()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            e.contingency_fisher_device(0, dc2.data_ptr(), dp2.data_ptr())
+            c1.record()
+            torch.cuda.synchronize()
+            tot += c0.elapsed_time(c1)
+        ms2 = tot / reps
+        e.set_stream(0)
+        host2 = pin2.numpy().view(np.uint64)
+        e.set_genes(host2, N2); e.set_trait_vector(0, tr2[0]); e.contingency_fisher(0)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            e.set_genes(host2, N2)
+            e.set_trait_vector(0, tr2[0])
+            cc2, pp2, _ = e.contingency_fisher(0)
+        e2e2 = (time.perf_counter() - t0) / reps * 1e3
+        tested2 = int(((cc2[:, 0] + cc2[:, 1] > 0) & (cc2[:, 2] + cc2[:, 3] > 0)).sum())
+        bytes2 = G2 * (8 * W2 + 24)
+        c2 = {"workload": "c2: %d genes x %d isolates x 1 trait, Fisher only" % (G2, N2), "tests_per_step": tested2,
+              "value": tested2 / (ms2 * 1e-3), "unit": "tests/s", "ms_per_step": ms2,
+              "e2e": {"value": tested2 / (e2e2 * 1e-3), "ms_per_step": e2e2, "h2d_bytes_per_step": int(host2.nbytes + 16 * W2),
+                      "d2h_bytes_per_step": int(cc2.nbytes + pp2.nbytes)},
+              "roofline": {"bound": "hbm", "achieved": bytes2 / (ms2 * 1e-3) / 1e9, "unit": "GB/s",
+                           "note": "1.5 MB of input: launch-latency bound, not bandwidth bound"}}
+
     if rank != 0:
         if world > 1:
             dist.barrier()              # stay in the group until rank 0 has printed its line
@@ -476,6 +521,7 @@ def run_ours(a):
         "gpu_launches": int(st["kernel_launches"]),
         "clocks": clocks,
         "roofline": roofline, "roofline_int32": roofline_int, "fisher_pass": fisher, "reference_rule_mode": ref_rule,
+        "config1_fisher_only": c2,
         "cpu_baseline": cpu,
         "kernel_ms": {k: st[k] for k in ("ms_fisher", "ms_shuffle", "ms_walk", "ms_permute", "ms_reduce")},
         "wall_s_timed_region": wall,
