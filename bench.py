@@ -202,6 +202,9 @@ def run_ours(a):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL_DEBUG=VERSION/INFO would put NCCL's banner on stdout in front of the one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "INFO"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- synthetic inputs: every rank owns its own G-gene shard (weak scaling), same traits / tree
