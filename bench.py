@@ -202,9 +202,9 @@ def run_ours(a):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL_DEBUG=VERSION/INFO would put NCCL's banner on stdout in front of the one JSON line
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "INFO"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL writes its version banner (and any NCCL_DEBUG output) to stdout by default: send it to
+        # stderr so that stdout carries exactly the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- synthetic inputs: every rank owns its own G-gene shard (weak scaling), same traits / tree
