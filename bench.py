@@ -182,7 +182,7 @@ def run_reference(a):
         "e2e": {"value": value, "unit": "tests/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -202,9 +202,9 @@ def run_ours(a):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL writes its version banner (and any NCCL_DEBUG output) to stdout by default: send it to
-        # stderr so that stdout carries exactly the one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # the image exports NCCL_DEBUG=VERSION, which makes NCCL print a banner on stdout
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            os.environ.pop("NCCL_DEBUG")
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- synthetic inputs: every rank owns its own G-gene shard (weak scaling), same traits / tree
@@ -529,14 +529,36 @@ def run_ours(a):
         "kernel_ms": {k: st[k] for k in ("ms_fisher", "ms_shuffle", "ms_walk", "ms_permute", "ms_reduce")},
         "wall_s_timed_region": wall,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def _guard_stdout():
+    """Whatever libraries print (NCCL banners, warnings) goes to stderr; the process's real
+    stdout receives exactly the one JSON line (emit())."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
     a = parse_args()
+    _guard_stdout()
     if a.impl == "reference":
         run_reference(a)
     else:
