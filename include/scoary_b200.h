@@ -146,7 +146,9 @@ int sb_pairwise_device(sb_ctx *ctx, int32_t t, const int64_t *d_gene_idx, int64_
  *     1 - binom.cdf(r, i, 0.1) < 0.05 test.
  * Empirical p = (r + 1) / (n_done + 1) is formed by the host.
  *   pairs int32[S][3] unpermuted Total, Pro, Anti (may be NULL);
- *   r int32[S]; n_done int32[S]. */
+ *   r int32[S]; n_done int32[S].
+ * With early_stop = 1 the permutations are walked in rounds and the library waits for each
+ * round's survivor count, so even the *_device variant synchronises the stream internally. */
 int sb_permute(sb_ctx *ctx, int32_t t, const int64_t *gene_idx, int64_t S, int32_t P,
                uint64_t seed, int32_t early_stop, const int32_t *rmin, int32_t *pairs,
                int32_t *r, int32_t *n_done);
