@@ -474,11 +474,11 @@ int launch_fisher(sb_ctx *ctx, int32_t t, int32_t *d_counts, double *d_p, uint64
     const size_t budget = (size_t)ctx->max_smem_optin;
     bool lut_smem = (fixed + lut_bytes + 2 * 8 * row_bytes) <= budget;
     size_t avail = budget - fixed - (lut_smem ? lut_bytes : 0);
-    int rows = (int)std::min<size_t>(avail / 2 / row_bytes, std::max<size_t>(8, 32768 / row_bytes));
+    int rows = (int)std::min<size_t>(avail / 2 / row_bytes, std::max<size_t>(8, 65536 / row_bytes));   // >= one row per warp
     rows = std::max(1, std::min(rows, 512));
     if ((size_t)rows * row_bytes * 2 + fixed > budget) return fail(ctx, SB_ERR_ARG, "row too long for shared memory");
     // keep every SM busy: shrink tiles if there would be fewer tiles than SMs
-    while (rows > 16 && (ctx->G + rows - 1) / rows < 2 * ctx->sm_count) rows /= 2;
+    while (rows > 32 && (ctx->G + rows - 1) / rows < 2 * ctx->sm_count) rows /= 2;
     A.rows_per_tile = rows;
     A.n_tiles = (int32_t)((ctx->G + rows - 1) / rows);
     const size_t smem = fixed + 2 * (size_t)rows * row_bytes + (lut_smem ? lut_bytes : 0);

@@ -18,7 +18,10 @@
 
 namespace sb {
 
-constexpr int FISHER_THREADS = 512;
+#ifndef SB_FISHER_THREADS
+#define SB_FISHER_THREADS 1024
+#endif
+constexpr int FISHER_THREADS = SB_FISHER_THREADS;
 constexpr double FISHER_TIE_TOL = 1e-12;   // |log pmf ratio| below this is a tie (exact ties give 0)
 
 struct FisherArgs {
@@ -55,23 +58,41 @@ __device__ __forceinline__ double warp_sum(double v)
 }
 
 // Sum pmf(x) for x = x0, x0+dir, ..., count terms, terms non-increasing.
-// logp_a = log pmf(a) (dd), S_a = S(a).  Stops once terms are < 2^-80 pmf(a).
+// logp_a = log pmf(a) (dd), S_a = S(a).  Each lane takes FISHER_BLOCK consecutive terms per round:
+// the first from the double-double LUT (one exp), the rest by the hypergeometric ratio
+//   pmf(x+1)/pmf(x) = (n1-x)(n-x) / ((x+1)(n2-n+x+1))       (and its mirror for dir = -1)
+// in plain double (two roundings per step: <= 2e-15 relative after 7 steps).  Stops once a round
+// starts below 2^-80 pmf(a).
+constexpr int FISHER_BLOCK = 8;
+
 __device__ __forceinline__ double fisher_tail(const double2 *lut, int x0, int dir, int count, int n1, int n2,
                                               int n, dd logp_a, dd S_a, double pexact, int lane)
 {
     double acc = 0.0;
     const double cut = pexact * 8.271806125530277e-25;   // 2^-80
-    for (int base = 0; base < count; base += 32) {
-        int k = base + lane;
-        double term = 0.0;
-        if (k < count) {
-            int x = x0 + dir * k;
+    for (int base = 0; base < count; base += 32 * FISHER_BLOCK) {
+        const int kb = base + lane * FISHER_BLOCK;
+        double t = 0.0;
+        if (kb < count) {
+            const int x = x0 + dir * kb;
             dd d = dd_sub(S_a, fisher_S(lut, x, n1, n2, n));   // log pmf(x) - log pmf(a)
             dd L = dd_add(logp_a, d);
-            term = exp(L.hi) * (1.0 + L.lo);
+            t = exp(L.hi) * (1.0 + L.lo);
+            double A, B, C, D;      // pmf(next)/pmf(cur) = (A * B) / (C * D); A, B step down, C, D step up
+            if (dir > 0) { A = (double)(n1 - x); B = (double)(n - x); C = (double)(x + 1); D = (double)(n2 - n + x + 1); }
+            else { A = (double)x; B = (double)(n2 - n + x); C = (double)(n1 - x + 1); D = (double)(n - x + 1); }
+            double tt = t, s = t;
+#pragma unroll
+            for (int j = 1; j < FISHER_BLOCK; ++j) {
+                if (kb + j < count) {
+                    tt = __dmul_rn(tt, __ddiv_rn(__dmul_rn(A, B), __dmul_rn(C, D)));
+                    s += tt;
+                    A -= 1.0; B -= 1.0; C += 1.0; D += 1.0;
+                }
+            }
+            acc += s;
         }
-        acc += term;
-        double first = __shfl_sync(0xffffffffu, term, 0);
+        const double first = __shfl_sync(0xffffffffu, t, 0);
         if (first < cut) break;
     }
     return warp_sum(acc);
