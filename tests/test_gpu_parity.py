@@ -294,3 +294,42 @@ def test_device_pointer_entry_points(engine):
     pairs, r, nd = engine.permute(0, P, seed=5)
     assert np.array_equal(got[0], counts) and np.array_equal(got[1], p)
     assert np.array_equal(got[2], pairs) and np.array_equal(got[3], r)
+
+
+def test_large_isolate_count_paths(engine):
+    """N = 20 000 isolates: the log-factorial LUT no longer fits shared memory (global-memory LUT
+    path of the Fisher kernel), label vectors take 628 words (few permutations per launch), and a
+    comb tree is 19 999 levels deep (pure caterpillar program, widened to 32-bit keys after 127 leaves)."""
+    N, G, P = 20000, 48, 6
+    bits, traits = _dataset(G, N, 31415, 0.01)
+    names = synth.isolate_names(N)
+    col = {n: j for j, n in enumerate(names)}
+    keep = [n for j, n in enumerate(names) if traits[0][j] >= 0]
+    nested = _comb(keep)
+    m = synth.unpack_rows(bits, N)
+    engine.set_genes(bits, N)
+    engine.set_trait_vector(0, traits[0])
+    counts, p, _ = engine.contingency_fisher(0)
+    ref_counts = O.contingency(m, traits[0])
+    assert np.array_equal(counts, ref_counts)
+    ref_p = O.fisher(ref_counts)
+    ok = ref_p > 1e-290
+    assert np.max(np.abs(p - ref_p)[ok] / ref_p[ok]) <= FISHER_RTOL
+    order = engine.set_tree_nested(0, nested, col)
+    left, right, _ = O.flatten_tree(nested)
+    cols = np.asarray([col[n] for n in order])
+    ref = O.permute(left, right, m[:, cols], traits[0][cols].astype(np.uint8), P=P, seed=3, trait=0)
+    pairs, r, nd = engine.permute(0, P, seed=3)
+    assert np.array_equal(pairs, ref["pairs"]) and np.array_equal(r, ref["r"])
+
+
+def test_empty_selections(engine):
+    bits, traits = _dataset(20, 64, 5)
+    nested, col = _tree_for(64, 5, traits[0])
+    engine.set_genes(bits, 64)
+    engine.set_trait_vector(0, traits[0])
+    engine.set_tree_nested(0, nested, col)
+    none = np.zeros(0, dtype=np.int64)
+    assert engine.pairwise(0, none).shape == (0, 3)
+    pairs, r, nd = engine.permute(0, 10, gene_idx=none)
+    assert pairs.shape == (0, 3) and r.shape == (0,) and nd.shape == (0,)
