@@ -188,6 +188,14 @@ int64_t sb_csv_pack_rows(const char *buf, int64_t len, char delimiter, const int
                          int32_t W, const int32_t *lead_cols, int32_t n_lead, int64_t *lead_ranges,
                          int32_t *row_fields);
 
+/* Test hook, host only (no GPU needed): the tree compiler behind sb_set_tree.  Writes the stack
+ * program (uint16 ops: low 4 bits = op type, high 12 bits = count; see csrc/walk.cuh) and the
+ * order in which the program consumes the leaves.  Returns the number of ops or a negative
+ * sb_status (text in sb_last_error(NULL)). */
+int sb_debug_compile_tree(const int32_t *left, const int32_t *right, int32_t n_internal,
+                          uint16_t *ops_out, int32_t max_ops, int32_t *leaf_of_pos,
+                          int32_t *stack_units);
+
 /* Integer-pipe microbenchmark used for the walk kernels' roofline denominator:
  * runs `iters` rounds of dependent add/max chains on every SM and returns the
  * measured int32 add+max operations per second. */

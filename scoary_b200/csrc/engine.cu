@@ -1110,6 +1110,23 @@ int sb_upgma(sb_ctx *ctx, int32_t *merges)
     return SB_OK;
 }
 
+// Host-only test hook (no GPU needed): compile a tree into the K4/K5 stack program.
+// ops_out [max_ops] receives the uint16 program, leaf_of_pos [n_internal + 1] the walk order;
+// returns the number of ops (> 0), or a negative sb_status; *stack_units = DP stack depth.
+int sb_debug_compile_tree(const int32_t *left, const int32_t *right, int32_t n_internal, uint16_t *ops_out,
+                          int32_t max_ops, int32_t *leaf_of_pos, int32_t *stack_units)
+{
+    if (!left || !right || !ops_out || !leaf_of_pos || n_internal < 1) return SB_ERR_ARG;
+    Program prog;
+    std::string err;
+    if (!compile_tree(left, right, n_internal, prog, err)) { g_create_error = err; return SB_ERR_ARG; }
+    if ((int32_t)prog.ops.size() > max_ops) { g_create_error = "program longer than max_ops"; return SB_ERR_ARG; }
+    memcpy(ops_out, prog.ops.data(), sizeof(uint16_t) * prog.ops.size());
+    memcpy(leaf_of_pos, prog.leaf_of_pos.data(), sizeof(int32_t) * (size_t)(n_internal + 1));
+    if (stack_units) *stack_units = prog.depth;
+    return (int)prog.ops.size();
+}
+
 int sb_int32_peak(sb_ctx *ctx, int32_t iters, double *ops_per_s)
 {
     if (!ctx || !ops_per_s || iters < 1) return SB_ERR_ARG;
