@@ -470,19 +470,15 @@ int launch_fisher(sb_ctx *ctx, int32_t t, int32_t *d_counts, double *d_p, uint64
     A.counts = d_counts; A.p = d_p; A.hash = d_hash;
     const size_t row_bytes = (size_t)ctx->W * 8;
     const size_t lut_bytes = sizeof(double2) * (size_t)(ctx->lut_n + 1);
-    const size_t fixed = 16 + 2 * row_bytes;
+    constexpr size_t NW = sb::FISHER_THREADS / 32;
+    // [2 mbarriers per warp][value&mask, mask][2 row buffers per warp][LUT if it fits]
+    const size_t fixed = 16 * NW + 2 * row_bytes + 2 * NW * row_bytes;
     const size_t budget = (size_t)ctx->max_smem_optin;
-    bool lut_smem = (fixed + lut_bytes + 2 * 8 * row_bytes) <= budget;
-    size_t avail = budget - fixed - (lut_smem ? lut_bytes : 0);
-    int rows = (int)std::min<size_t>(avail / 2 / row_bytes, std::max<size_t>(8, 65536 / row_bytes));   // >= one row per warp
-    rows = std::max(1, std::min(rows, 512));
-    if ((size_t)rows * row_bytes * 2 + fixed > budget) return fail(ctx, SB_ERR_ARG, "row too long for shared memory");
-    // keep every SM busy: shrink tiles if there would be fewer tiles than SMs
-    while (rows > 32 && (ctx->G + rows - 1) / rows < 2 * ctx->sm_count) rows /= 2;
-    A.rows_per_tile = rows;
-    A.n_tiles = (int32_t)((ctx->G + rows - 1) / rows);
-    const size_t smem = fixed + 2 * (size_t)rows * row_bytes + (lut_smem ? lut_bytes : 0);
-    const int grid = std::min<int>(A.n_tiles, ctx->sm_count);
+    if (fixed > budget) return fail(ctx, SB_ERR_ARG, "row too long for shared memory");
+    const bool lut_smem = fixed + lut_bytes <= budget;
+    const size_t smem = fixed + (lut_smem ? lut_bytes : 0);
+    const int64_t rows_per_cta = (int64_t)NW;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((ctx->G + rows_per_cta - 1) / rows_per_cta, ctx->sm_count));
     const bool hash = d_hash != nullptr;
     Timed tm(ctx, CAT_FISHER);
 #define SB_LAUNCH_FISHER(L, H)                                                                                     \

@@ -9,10 +9,10 @@
 //     + sum_{x on the other side of the mode with pmf(x) <= pmf(a)(1+1e-14)} pmf(x)
 //   p = 1 when pmf(a) ~= pmf(mode);  p = min(p, 1).
 //
-// Data movement: gene rows are streamed tile-by-tile into shared memory with
-// 1-D TMA bulk copies (cp.async.bulk + mbarrier, double buffered) by a
-// persistent grid; one warp owns one row at a time: 128-bit shared loads,
-// __popcll, warp REDUX, then the warp walks the hypergeometric support.
+// Data movement: a persistent grid; every warp streams its own gene rows into
+// shared memory with 1-D TMA bulk copies (cp.async.bulk + its own pair of
+// mbarriers, double buffered) and owns one row at a time: 128-bit shared
+// loads, __popcll, warp REDUX, then the warp walks the hypergeometric support.
 #pragma once
 #include "common.cuh"
 
@@ -33,8 +33,6 @@ struct FisherArgs {
     const uint64_t *tmask;   // [W]
     const double2 *lut;      // [lut_n + 1] log k! as (hi, lo)
     int32_t lut_n;
-    int32_t rows_per_tile;
-    int32_t n_tiles;
     int32_t *counts;         // [G][4] or null
     double *p;               // [G] or null
     uint64_t *hash;          // [G][2] or null
@@ -167,33 +165,37 @@ __device__ __forceinline__ double fisher_two_sided_warp(const double2 *lut, int 
 template <bool LUT_SMEM, bool HASH>
 __global__ void __launch_bounds__(FISHER_THREADS) fisher_kernel(const FisherArgs A)
 {
+    // Shared memory: [2 mbarriers per warp] [value & mask] [mask] [2 row buffers per warp] [LUT].
+    // Every warp runs its own double-buffered TMA pipeline over its own rows (1-D bulk copies of
+    // one 8*W-byte row, completion on the warp's mbarriers): the rows cost very different amounts
+    // of Fisher work, so there is no block-wide barrier anywhere in the loop.
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);            // 2 mbarriers (16 B)
-    uint64_t *s_tm = reinterpret_cast<uint64_t *>(smem_raw + 16);       // value & mask  [W]
-    uint64_t *s_m = s_tm + A.W;                                         // mask          [W]
-    uint64_t *s_stage0 = s_m + A.W;
-    const size_t tile_words = (size_t)A.rows_per_tile * A.W;
-    uint64_t *s_stage1 = s_stage0 + tile_words;
-    double2 *s_lut = reinterpret_cast<double2 *>(s_stage1 + tile_words);
+    constexpr int NW = FISHER_THREADS / 32;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);                    // [NW][2]
+    uint64_t *s_tm = reinterpret_cast<uint64_t *>(smem_raw + 16 * NW);          // value & mask  [W]
+    uint64_t *s_m = s_tm + A.W;                                                 // mask          [W]
+    uint64_t *s_rows = s_m + A.W;                                               // [NW][2][W]
+    double2 *s_lut = reinterpret_cast<double2 *>(s_rows + (size_t)NW * 2 * A.W);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = FISHER_THREADS / 32;
+    uint64_t *my_bar = bars + warp * 2;
+    uint64_t *my_rows = s_rows + (size_t)warp * 2 * A.W;
+    const uint32_t row_bytes = (uint32_t)A.W * 8u;
+    const int64_t stride = (int64_t)gridDim.x * NW;
+    const int64_t row_first = (int64_t)blockIdx.x * NW + warp;
 
-    auto issue = [&](int tile, int buf) {
-        const int64_t row0 = (int64_t)tile * A.rows_per_tile;
-        const int rows = (int)min((int64_t)A.rows_per_tile, A.G - row0);
-        const uint32_t bytes = (uint32_t)rows * (uint32_t)A.W * 8u;
-        mbar_arrive_expect_tx(&bars[buf], bytes);
-        tma_bulk_g2s(buf ? s_stage1 : s_stage0, A.genes + row0 * A.W, bytes, &bars[buf]);
-    };
-
-    if (tid == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
+    if (lane == 0) {
+        mbar_init(&my_bar[0], 1);
+        mbar_init(&my_bar[1], 1);
         fence_barrier_init();
-        int t0 = blockIdx.x, t1 = blockIdx.x + gridDim.x;
-        if (t0 < A.n_tiles) issue(t0, 0);
-        if (t1 < A.n_tiles) issue(t1, 1);
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const int64_t r = row_first + b * stride;
+            if (r < A.G) {
+                mbar_arrive_expect_tx(&my_bar[b], row_bytes);
+                tma_bulk_g2s(my_rows + (size_t)b * A.W, A.genes + r * A.W, row_bytes, &my_bar[b]);
+            }
+        }
     }
     for (int w = tid; w < A.W; w += FISHER_THREADS) {
         uint64_t m = A.tmask[w];
@@ -203,7 +205,7 @@ __global__ void __launch_bounds__(FISHER_THREADS) fisher_kernel(const FisherArgs
     if (LUT_SMEM) {
         for (int k = tid; k <= A.lut_n; k += FISHER_THREADS) s_lut[k] = A.lut[k];
     }
-    __syncthreads();
+    __syncthreads();   // trait vectors and LUT staged (the only block-wide barrier)
     const double2 *lut = LUT_SMEM ? s_lut : A.lut;
 
     // trait totals (every warp computes them redundantly: W is tiny)
@@ -220,66 +222,62 @@ __global__ void __launch_bounds__(FISHER_THREADS) fisher_kernel(const FisherArgs
     const ulonglong2 *m2 = reinterpret_cast<const ulonglong2 *>(s_m);
 
     int it = 0;
-    for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x, ++it) {
+    for (int64_t g_idx = row_first; g_idx < A.G; g_idx += stride, ++it) {
         const int buf = it & 1;
-        const uint32_t parity = (it >> 1) & 1;
-        mbar_wait(&bars[buf], parity);
-        const uint64_t *stage = buf ? s_stage1 : s_stage0;
-        const int64_t row0 = (int64_t)tile * A.rows_per_tile;
-        const int rows = (int)min((int64_t)A.rows_per_tile, A.G - row0);
-        for (int r = warp; r < rows; r += NW) {
-            const ulonglong2 *row2 = reinterpret_cast<const ulonglong2 *>(stage + (size_t)r * A.W);
-            int tp = 0, gp = 0;
-            uint64_t h0 = 0, h1 = 0;
-            for (int cidx = lane; cidx < W2; cidx += 32) {
-                const ulonglong2 g = row2[cidx];
-                const ulonglong2 t = tm2[cidx];
-                const ulonglong2 m = m2[cidx];
-                tp += __popcll(g.x & t.x) + __popcll(g.y & t.y);
-                gp += __popcll(g.x & m.x) + __popcll(g.y & m.y);
-                if (HASH) {
-                    const int w0 = 2 * cidx;
-                    if (w0 < A.Wn) {
-                        const uint64_t x = g.x & m.x;
-                        h0 += mix64(x + (uint64_t)(w0 + 1) * 0x9E3779B97F4A7C15ULL);
-                        h1 += mix64((x ^ 0xD6E8FEB86659FD93ULL) + (uint64_t)(w0 + 1) * 0xC2B2AE3D27D4EB4FULL);
-                    }
-                    if (w0 + 1 < A.Wn) {
-                        const uint64_t x = g.y & m.y;
-                        h0 += mix64(x + (uint64_t)(w0 + 2) * 0x9E3779B97F4A7C15ULL);
-                        h1 += mix64((x ^ 0xD6E8FEB86659FD93ULL) + (uint64_t)(w0 + 2) * 0xC2B2AE3D27D4EB4FULL);
-                    }
-                }
-            }
-            tp = __reduce_add_sync(0xffffffffu, tp);
-            gp = __reduce_add_sync(0xffffffffu, gp);
-            const int a = tp;              // tpgp
-            const int c = gp - tp;         // tngp
-            const int b = n_tp - tp;       // tpgn
-            const int d = n_m - n_tp - c;  // tngn
-            const int64_t g_idx = row0 + r;
+        mbar_wait(&my_bar[buf], (uint32_t)((it >> 1) & 1));
+        const ulonglong2 *row2 = reinterpret_cast<const ulonglong2 *>(my_rows + (size_t)buf * A.W);
+        int tp = 0, gp = 0;
+        uint64_t h0 = 0, h1 = 0;
+        for (int cidx = lane; cidx < W2; cidx += 32) {
+            const ulonglong2 g = row2[cidx];
+            const ulonglong2 t = tm2[cidx];
+            const ulonglong2 m = m2[cidx];
+            tp += __popcll(g.x & t.x) + __popcll(g.y & t.y);
+            gp += __popcll(g.x & m.x) + __popcll(g.y & m.y);
             if (HASH) {
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    h0 += __shfl_xor_sync(0xffffffffu, h0, o);
-                    h1 += __shfl_xor_sync(0xffffffffu, h1, o);
+                const int w0 = 2 * cidx;
+                if (w0 < A.Wn) {
+                    const uint64_t x = g.x & m.x;
+                    h0 += mix64(x + (uint64_t)(w0 + 1) * 0x9E3779B97F4A7C15ULL);
+                    h1 += mix64((x ^ 0xD6E8FEB86659FD93ULL) + (uint64_t)(w0 + 1) * 0xC2B2AE3D27D4EB4FULL);
                 }
-                if (lane == 0 && A.hash) {
-                    A.hash[g_idx * 2 + 0] = h0;
-                    A.hash[g_idx * 2 + 1] = h1;
+                if (w0 + 1 < A.Wn) {
+                    const uint64_t x = g.y & m.y;
+                    h0 += mix64(x + (uint64_t)(w0 + 2) * 0x9E3779B97F4A7C15ULL);
+                    h1 += mix64((x ^ 0xD6E8FEB86659FD93ULL) + (uint64_t)(w0 + 2) * 0xC2B2AE3D27D4EB4FULL);
                 }
-            }
-            if (lane == 0 && A.counts)
-                reinterpret_cast<int4 *>(A.counts)[g_idx] = make_int4(a, c, b, d);   // tpgp,tngp,tpgn,tngn
-            if (A.p) {
-                const double pv = fisher_two_sided_warp(lut, a, b, c, d, lane);
-                if (lane == 0) A.p[g_idx] = pv;
             }
         }
-        __syncthreads();   // every warp is done with this stage buffer
-        if (tid == 0) {
-            const int nxt = tile + 2 * gridDim.x;
-            if (nxt < A.n_tiles) issue(nxt, buf);
+        __syncwarp();   // every lane has read the row: the buffer can be refilled
+        if (lane == 0) {
+            const int64_t nxt = g_idx + 2 * stride;
+            if (nxt < A.G) {
+                mbar_arrive_expect_tx(&my_bar[buf], row_bytes);
+                tma_bulk_g2s(my_rows + (size_t)buf * A.W, A.genes + nxt * A.W, row_bytes, &my_bar[buf]);
+            }
+        }
+        tp = __reduce_add_sync(0xffffffffu, tp);
+        gp = __reduce_add_sync(0xffffffffu, gp);
+        const int a = tp;              // tpgp
+        const int c = gp - tp;         // tngp
+        const int b = n_tp - tp;       // tpgn
+        const int d = n_m - n_tp - c;  // tngn
+        if (HASH) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                h0 += __shfl_xor_sync(0xffffffffu, h0, o);
+                h1 += __shfl_xor_sync(0xffffffffu, h1, o);
+            }
+            if (lane == 0 && A.hash) {
+                A.hash[g_idx * 2 + 0] = h0;
+                A.hash[g_idx * 2 + 1] = h1;
+            }
+        }
+        if (lane == 0 && A.counts)
+            reinterpret_cast<int4 *>(A.counts)[g_idx] = make_int4(a, c, b, d);   // tpgp,tngp,tpgn,tngn
+        if (A.p) {
+            const double pv = fisher_two_sided_warp(lut, a, b, c, d, lane);
+            if (lane == 0) A.p[g_idx] = pv;
         }
     }
 }
