@@ -57,3 +57,16 @@ def test_oracle_is_not_imported_by_the_product():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src and "libscoary_oracle" not in src, f
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/scoary_b200.h compiles as C and a C program can drive the library."""
+    import subprocess
+    exe = str(tmp_path / "c_abi_smoke")
+    lib_dir = os.path.join(ROOT, "scoary_b200")
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    subprocess.check_call([cc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c_abi_smoke.c"), "-o", exe, "-L", lib_dir, "-lscoary_b200",
+                           "-Wl,-rpath," + lib_dir])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
