@@ -475,7 +475,9 @@ def run_ours(a):
                 "frac": (alg_bytes / (k5_ms * 1e-3) / 1e9 / hbm_peak) if P > 0 else None, "traffic": traffic,
                 "peak_source": peak_src, "ms_per_launch": k5_ms, "launches_per_step": launches_per_step,
                 "note": "K5 is integer-issue bound by construction (%.2f algorithmic bytes per test): the meaningful "
-                        "bound is roofline_int32" % bytes_per_test}
+                        "bound is roofline_int32.  traffic = ncu dram bytes of ONE launch with caches flushed (the 32 MB "
+                        "walk-order gene matrix read once); within a step the %d launches find it in L2 (ncu "
+                        "lts hit rate 96 %%)" % (bytes_per_test, int(round(launches_per_step)))}
     roofline_int = {"kernel": "walk_permute_kernel", "bound": "int32 add/max issue (DPX)",
                     "achieved": alg_ops / (k5_ms * 1e-3) / 1e12 if P > 0 else None, "peak": int_peak / 1e12,
                     "unit": "Top/s", "frac": (alg_ops / (k5_ms * 1e-3) / int_peak) if P > 0 else None,
