@@ -10,6 +10,12 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run on the GPU box with `-m gpu`)")
+    # the shared libraries are build artefacts (git-ignored): build them once if a fresh checkout lacks them
+    lib = os.path.join(ROOT, "scoary_b200", "libscoary_b200.so")
+    ora = os.path.join(ROOT, "oracle", "libscoary_oracle.so")
+    if not (os.path.exists(lib) and os.path.exists(ora)):
+        import __graft_entry__
+        __graft_entry__.build()
 
 
 def _have_gpu():
