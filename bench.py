@@ -133,10 +133,10 @@ def cpu_sample(G, N, T, P, seed, budget_s):
     col = {n: j for j, n in enumerate(synth.isolate_names(N))}
     cols = np.asarray([col[n] for n in names])
     labels = traits[0][cols].astype(np.uint8)
-    # bounded sample: 16 genes per host thread x 32 permutations (a few seconds of wall time;
-    # dynamic scheduling over genes keeps every thread busy)
+    # bounded sample: ~200 genes per host thread x 32 permutations (a few seconds of wall time with the
+    # -O3 port; dynamic scheduling over genes keeps every thread busy)
     ps = min(P, 32) if P > 0 else 0
-    per_thread = max(1, int(round(16 * budget_s / 6.0)))
+    per_thread = max(1, int(round(192 * budget_s / 6.0)))
     gs = min(G, per_thread * threads) if P > 0 else min(G, 2000)
     bits = synth.make_genes_packed(gs, N, seed, traits=traits)
     m = synth.unpack_rows(bits, N)
