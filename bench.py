@@ -120,13 +120,40 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU arm
+def usable_host_threads():
+    """Host threads this process can really use: cpu_count, clipped by the affinity mask and by the
+    container's CPU quota (cgroup cpu.max / cfs_quota).  With a quota of q CPUs, 2q threads measured
+    best (more only thrash: 128 threads on a 16-CPU quota ran 2.5x slower than 32)."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    quota = None
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            quota = float(q) / float(per)
+    except Exception:
+        try:
+            q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / per
+        except Exception:
+            pass
+    if quota:
+        n = min(n, max(1, int(round(2 * quota))))
+    return n, quota
+
+
 def cpu_sample(G, N, T, P, seed, budget_s):
     """Time the oracle's C port (OpenMP, all host threads) on a bounded sample of the
     same workload: the first `gs` genes x `ps` permutations (+ unpermuted walk + Fisher)."""
     from oracle import oracle as O
     from scoary_b200 import synth
-    threads = os.cpu_count() or O.num_threads()
-    O.set_num_threads(threads)           # torch's import would otherwise cap OpenMP at the physical cores
+    threads, quota = usable_host_threads()
+    O.set_num_threads(threads)           # (torch's import / torchrun would otherwise pin OpenMP to fewer threads)
     traits = synth.make_traits(N, 1, seed)
     nested = synth.make_tree(N, seed)
     left, right, names = O.flatten_tree(nested)
@@ -158,8 +185,9 @@ def cpu_sample(G, N, T, P, seed, budget_s):
         return T * (1 + P) / (T * per_gene)
 
     sample = ("first %d genes x %d of %d permutations (+ unpermuted walk, contingency, Fisher), %d isolates, "
-              "exhaustive mode; per-gene and per-walk costs combined at the full %d permutations per gene"
-              % (gs, ps, P, N, P))
+              "exhaustive mode; per-gene and per-walk costs combined at the full %d permutations per gene; %d OpenMP "
+              "threads (os.cpu_count() = %s, container CPU quota = %s)"
+              % (gs, ps, P, N, P, threads, os.cpu_count(), ("%.0f CPUs" % quota) if quota else "none"))
     return run, rate, threads, sample
 
 
