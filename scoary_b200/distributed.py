@@ -47,3 +47,93 @@ def all_gather_records(rec_tensor, n_total, bounds):
     full = torch.cat(parts, dim=0)
     assert full.shape[0] == n_total
     return full
+
+
+# ---------------------------------------------------------------------------- the CLI's N > 1 flow
+# `torchrun --nproc-per-node N -m scoary_b200.methods ...` (two-phase):
+#   phase 1  contiguous gene shards -> counts / Fisher p / pattern hash -> ONE all-gather ->
+#            every rank runs the same deterministic host code (skip rule, collapse, Bonferroni/BH, sort,
+#            cut-offs), so every rank knows the surviving genes without a second exchange;
+#   phase 2  the survivors are dealt out again, strided like the reference's worker domains
+#            (range(t, num_results, threads), scoary/methods.py:1077) so that early-stopping and
+#            full-length permutation runs mix evenly -> walks + permutations -> ONE all-gather.
+# Rank 0 writes the files.  Host arrays in, host arrays out; NCCL when GPUs are there, gloo on CPU.
+_OWN_GROUP = False
+
+
+def init_from_env():
+    """Join the process group torchrun describes (WORLD_SIZE > 1); no-op otherwise."""
+    global _OWN_GROUP
+    import os
+    if int(os.environ.get("WORLD_SIZE", "1")) <= 1:
+        return False
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        cuda = torch.cuda.is_available()
+        if cuda:
+            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group("nccl" if cuda else "gloo")
+        _OWN_GROUP = True
+    return True
+
+
+def finish():
+    global _OWN_GROUP
+    if _OWN_GROUP:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+        _OWN_GROUP = False
+
+
+def world_rank():
+    """(world, rank) of the initialised process group, (1, 0) without one."""
+    try:
+        import sys
+        if "torch" not in sys.modules:
+            return 1, 0
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_world_size(), dist.get_rank()
+    except ImportError:
+        pass
+    return 1, 0
+
+
+def _gather_padded(rows, n_max):
+    """int32 [n_r][W] per rank -> numpy int32 [world][n_max][W] (one all-gather of padded blocks)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size()
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    rows = np.ascontiguousarray(rows, dtype=np.int32)
+    W = rows.shape[1]
+    pad = torch.zeros((n_max, W), dtype=torch.int32, device=dev)
+    if len(rows):
+        pad[: len(rows)] = torch.from_numpy(rows).to(dev)
+    flat = torch.empty((world * n_max, W), dtype=torch.int32, device=dev)
+    dist.all_gather_into_tensor(flat, pad)
+    return flat.view(world, n_max, W).cpu().numpy()
+
+
+def gather_blocks(rows, n_total):
+    """Rank r holds rows shard_bounds(n_total, world)[r] -> every rank gets all n_total rows in order."""
+    world, _ = world_rank()
+    bounds = shard_bounds(n_total, world)
+    parts = _gather_padded(rows, max(hi - lo for lo, hi in bounds))
+    return np.concatenate([parts[r][: bounds[r][1] - bounds[r][0]] for r in range(world)], axis=0)
+
+
+def gather_strided(rows, n_total):
+    """Rank r holds rows r, r + world, r + 2 world, ... -> every rank gets all n_total rows in order."""
+    world, _ = world_rank()
+    rows = np.ascontiguousarray(rows, dtype=np.int32)
+    out = np.zeros((n_total, rows.shape[1]), dtype=np.int32)
+    if n_total == 0:
+        return out
+    parts = _gather_padded(rows, -(-n_total // world))
+    for r in range(world):
+        n_r = len(range(r, n_total, world))
+        out[r::world] = parts[r][:n_r]
+    return out

@@ -28,6 +28,7 @@ from collections.abc import Mapping
 import numpy as np
 
 from . import __version__
+from . import distributed as dist
 from . import engine as eng
 from . import tree as treemod
 
@@ -444,7 +445,10 @@ def Setup_results(genedic, traitsdic, collapse):
     (sb_contingency_fisher).  Returns {"Results": ..., "Gene_trait_combinations": ...}."""
     table = GeneTable.from_dict(genedic)
     e = get_engine()
-    e.set_genes(table.bits, len(table.strains))
+    world, rank = dist.world_rank()
+    G = table.bits.shape[0]
+    lo, hi = dist.shard_bounds(G, world)[rank]           # N > 1: this rank's contiguous block of genes
+    e.set_genes(table.bits[lo:hi], len(table.strains))
     all_traits, gtc = {}, {}
     for t_idx, trait in enumerate(traitsdic):
         log.info("Gene-wise counting and Fisher's exact tests for trait: %s" % str(trait))
@@ -452,6 +456,16 @@ def Setup_results(genedic, traitsdic, collapse):
         slot = t_idx % 64
         e.set_trait_vector(slot, vec)
         counts, pvals, hashes = e.contingency_fisher(slot, want_hash=bool(collapse))
+        if world > 1:                                     # one all-gather; the rest is the same on every rank
+            rec = np.zeros((hi - lo, 10), dtype=np.int32)
+            rec[:, 0:4] = counts
+            rec[:, 4:6] = np.ascontiguousarray(pvals, dtype=np.float64).view(np.int32).reshape(-1, 2)
+            if collapse:
+                rec[:, 6:10] = np.ascontiguousarray(hashes, dtype=np.uint64).view(np.int32).reshape(-1, 4)
+            rec = dist.gather_blocks(rec, G)
+            counts = rec[:, 0:4]
+            pvals = np.ascontiguousarray(rec[:, 4:6]).view(np.float64).reshape(-1)
+            hashes = np.ascontiguousarray(rec[:, 6:10]).view(np.uint64).reshape(-1, 2)
         tpgp, tngp, tpgn, tngn = (counts[:, k].astype(np.int64) for k in range(4))
         keep = ((tpgp + tngp) > 0) & ((tpgn + tngn) > 0)          # methods.py:804-814
         number_of_tests = int(keep.sum())
@@ -604,12 +618,23 @@ def PairWiseComparisons(nestedlist):
     out = {}
     if not genes:
         return out
-    e = _walk_setup(tree, GTC, genes)
-    if perm >= 10:
-        pairs, r, nd = e.permute(0, int(perm), seed=a.get("seed", PERMUTATION_SEED), early_stop=True,
-                                 rmin=early_stop_table(int(perm)))
-    else:
-        pairs = e.pairwise(0)
+    world, rank = dist.world_rank()
+    mine = genes[rank::world]                            # N > 1: strided, as the reference deals out its domains
+    pairs, r, nd = np.zeros((0, 3), np.int32), np.zeros(0, np.int32), np.zeros(0, np.int32)
+    if mine:
+        e = _walk_setup(tree, GTC, mine)
+        if perm >= 10:
+            pairs, r, nd = e.permute(0, int(perm), seed=a.get("seed", PERMUTATION_SEED), early_stop=True,
+                                     rmin=early_stop_table(int(perm)))
+        else:
+            pairs = e.pairwise(0)
+    if world > 1:
+        rec = np.zeros((len(mine), 5), dtype=np.int32)
+        rec[:, 0:3] = pairs
+        if perm >= 10:
+            rec[:, 3], rec[:, 4] = r, nd
+        rec = dist.gather_strided(rec, len(genes))
+        pairs, r, nd = rec[:, 0:3], rec[:, 3], rec[:, 4]
     for k, g in enumerate(genes):
         total, pro, anti = (int(x) for x in pairs[k])
         best = _binom_two_sided(pro, total)
@@ -807,6 +832,17 @@ CITATION = ("Scoary: Brynildsrud O, Bohlin J, Scheffer L, Eldholm V. Rapid scori
             "for that method.")
 
 
+def _close_run(fileh, console, scratch, ok):
+    log.removeHandler(fileh)
+    log.removeHandler(console)
+    fileh.close()
+    if ok:
+        dist.finish()              # barrier + leave the process group (no-op on one GPU)
+    if scratch is not None:
+        import shutil
+        shutil.rmtree(scratch, ignore_errors=True)
+
+
 def main(**kwargs):
     """`scoary -g genes.csv -t traits.csv` (scoary/methods.py:49-330) with the same files out."""
     global PERMUTATION_SEED
@@ -827,10 +863,17 @@ def main(**kwargs):
     PERMUTATION_SEED = getattr(args, "seed", PERMUTATION_SEED)
     starttime = time.time()
     currenttime = "" if args.no_time else time.strftime("_%d_%m_%Y_%H%M")
+    scratch = None
+    if dist.init_from_env() and dist.world_rank()[1] != 0:
+        # one process per GPU (torchrun): every rank runs the same host code, rank 0 owns the output
+        # directory; the others write their (identical) files to a scratch directory that is removed
+        import tempfile
+        scratch = tempfile.mkdtemp(prefix="scoary_b200_rank%d_" % dist.world_rank()[1])
+        args.outdir = scratch
     if not args.outdir.endswith("/"):
         args.outdir += "/"
     os.makedirs(args.outdir, exist_ok=True)
-    console = logging.StreamHandler(sys.stdout)
+    console = logging.StreamHandler(sys.stdout if scratch is None else open(os.devnull, "w"))
     console.setFormatter(logging.Formatter("%(message)s"))
     console.setLevel(logging.INFO)
     log.addHandler(console)
@@ -925,11 +968,9 @@ def main(**kwargs):
                  % (len(genedic), len(traitsdic), int(time.time() - starttime)))
     except SystemExit:
         log.exception("CRITICAL:")
-        log.removeHandler(fileh)
-        log.removeHandler(console)
+        _close_run(fileh, console, scratch, ok=False)
         raise
-    log.removeHandler(fileh)
-    log.removeHandler(console)
+    _close_run(fileh, console, scratch, ok=True)
     sys.exit(0)
 
 

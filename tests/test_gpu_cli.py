@@ -127,3 +127,29 @@ def test_permute_and_walk_mirror_functions():
     w = next(x for x in walks if len(x["gtc"]) >= 64 and x["out"][0] > 3)
     emp = M.Permute(w["tree"], w["gtc"], 100, {"I": 0.05})
     assert 0.0 < emp <= 1.0
+
+
+def test_cli_two_gpus_matches_reference_results(inputs):
+    """The N > 1 flow of the CLI on real GPUs (torchrun, NCCL).  Needs two GPUs: skipped on a one-GPU box
+    (the same flow runs under gloo in tests/test_distributed_cpu.py)."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", str(29900 + os.getpid() % 90), "-m", "scoary_b200.methods", "-g", inputs["g"],
+           "-t", inputs["t"], "-o", inputs["out"], "--no-time", "-p", "1.0", "-c", "I", "-e", "50"]
+    res = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    for trait in ("Tetracycline_resistance", "Bogus_trait"):
+        got = os.path.join(inputs["out"], trait + ".results.csv")
+        hdr, rows = _rows(got)
+        ghdr, gold = _rows(os.path.join(GOLD, "all", trait + ".results.csv.gz"))
+        assert hdr[:len(ghdr)] == ghdr and hdr[-1] == "Empirical_p" and len(rows) == len(gold)
+        col = {h: i for i, h in enumerate(hdr)}
+        by_gene = {r[0]: r for r in rows}
+        for g in gold:
+            for c in INT_COLS:
+                assert by_gene[g[0]][col[c]] == g[col[c]], (trait, g[0], c)
