@@ -37,6 +37,9 @@ def engine():
 
 
 def pytest_collection_modifyitems(config, items):
+    # the full-size runs (BASELINE.json's shapes, seconds each) go last: `-x` reaches them only after every
+    # small parity test has passed
+    items.sort(key=lambda it: "test_gpu_full_size" in it.nodeid)
     if _have_gpu():
         return
     skip = pytest.mark.skip(reason="no GPU in this container")
