@@ -20,6 +20,7 @@ There is no CPU fallback for the GPU part.
 import argparse
 import csv
 import logging
+import operator
 import os
 import sys
 import time
@@ -477,16 +478,31 @@ def Setup_results(genedic, traitsdic, collapse):
                             np.inf)
         res = {}
         row_of = {}
-        p_list_names, p_list_vals = [], []
-        owner = {}      # pattern hash -> current (possibly merged) name
         idx = np.flatnonzero(keep)
         names = table.names
-        for i in idx.tolist():
-            gene = names[i]
-            entry = {"NUGN": table.nugn[i], "Annotation": table.annotation[i],
-                     "tpgp": int(tpgp[i]), "tngp": int(tngp[i]), "tpgn": int(tpgn[i]), "tngn": int(tngn[i]),
-                     "sens": float(sens[i]), "spes": float(spes[i]), "OR": float(odds[i]), "p_v": float(pvals[i])}
-            if collapse:
+        cols = [x[idx].tolist() for x in (tpgp, tngp, tpgn, tngn, sens, spes, odds, np.asarray(pvals, np.float64))]
+        if not collapse:
+            # every tested gene is its own row: the adjusted p-values are array operations (methods.py:900-925)
+            pv = np.asarray(cols[7], dtype=np.float64)
+            order = np.argsort(pv, kind="stable")
+            bh = np.empty(len(pv), dtype=np.float64)
+            bh[order] = np.minimum(benjamini_hochberg(pv[order], number_of_tests), 1.0)
+            log.info("Adding p-values adjusted for testing multiple hypotheses")
+            nugn, annotation = table.nugn, table.annotation
+            for i, a, b, c, d, se, sp, od, p_v, b_p, bh_p in zip(idx.tolist(), *cols,
+                                                                 np.minimum(pv * number_of_tests, 1.0).tolist(),
+                                                                 bh.tolist()):
+                gene = names[i]
+                res[gene] = {"NUGN": nugn[i], "Annotation": annotation[i], "tpgp": a, "tngp": b, "tpgn": c, "tngn": d,
+                             "sens": se, "spes": sp, "OR": od, "p_v": p_v, "B_p": b_p, "BH_p": bh_p}
+                row_of[gene] = i
+        else:
+            p_list_names, p_list_vals = [], []
+            owner = {}      # pattern hash -> current (possibly merged) name
+            for i, a, b, c, d, se, sp, od, p_v in zip(idx.tolist(), *cols):
+                gene = names[i]
+                entry = {"NUGN": table.nugn[i], "Annotation": table.annotation[i], "tpgp": a, "tngp": b, "tpgn": c,
+                         "tngn": d, "sens": se, "spes": sp, "OR": od, "p_v": p_v}
                 key = (int(hashes[i, 0]), int(hashes[i, 1]))
                 prev = owner.get(key)
                 if prev is not None:                                   # methods.py:823-835, :874-892
@@ -500,20 +516,20 @@ def Setup_results(genedic, traitsdic, collapse):
                     gene = newname
                 else:
                     owner[key] = gene
-            res[gene] = entry
-            row_of[gene] = i
-            p_list_names.append(gene)
-            p_list_vals.append(entry["p_v"])
-        log.info("Adding p-values adjusted for testing multiple hypotheses")
-        pv = np.asarray(p_list_vals, dtype=np.float64)
-        order = np.argsort(pv, kind="stable")
-        bh = benjamini_hochberg(pv[order], number_of_tests)
-        bh_by_name = {}
-        for k, o in enumerate(order.tolist()):
-            bh_by_name[p_list_names[o]] = bh[k]
-        for gene, entry in res.items():
-            entry["B_p"] = min(entry["p_v"] * number_of_tests, 1.0)
-            entry["BH_p"] = min(float(bh_by_name[gene]), 1.0)
+                res[gene] = entry
+                row_of[gene] = i
+                p_list_names.append(gene)
+                p_list_vals.append(p_v)
+            log.info("Adding p-values adjusted for testing multiple hypotheses")
+            pv = np.asarray(p_list_vals, dtype=np.float64)
+            order = np.argsort(pv, kind="stable")
+            bh = benjamini_hochberg(pv[order], number_of_tests)
+            bh_by_name = {}
+            for k, o in enumerate(order.tolist()):
+                bh_by_name[p_list_names[o]] = bh[k]
+            for gene, entry in res.items():
+                entry["B_p"] = min(entry["p_v"] * number_of_tests, 1.0)
+                entry["BH_p"] = min(float(bh_by_name[gene]), 1.0)
         all_traits[trait] = res
         isolates = list(traitsdic[trait].keys())
         labels = np.asarray([1 if traitsdic[trait][s] == "1" else 0 for s in isolates], dtype=np.uint8)
@@ -732,25 +748,32 @@ def StoreTraitResult(Trait, Traitname, max_hits, cutoffs, upgmatree, GTC, Pruned
             else:
                 log.info("No filtration applied")
         else:
-            filtered = Trait
-            sort_instructions = SortResultsAndSetKey(filtered)
+            filtered = Trait                             # same genes, same key: the ranking above stands
         log.info("Storing results to file")
+        keys = ["tpgp", "tngp", "tpgn", "tngn", "sens", "spes", "OR", "p_v", "B_p", "BH_p"]
+        if not no_pairwise:
+            keys += ["max_total_pairs", "max_propairs", "max_antipairs", "Pbest", "Pworst"]
+            if permutations >= 10:
+                keys.append("Empirical_p")
+        stats_of = operator.itemgetter(*keys)
+        cuts = [(CUT_FIELDS[m], cutoffs[m]) for m in cutoffs]
+        sep = '"' + delimiter + '"'                       # every cell double-quoted (methods.py:1159-1197)
+        lines = []
         for x in range(min(num_results, len(filtered))):
             gene = sort_instructions[x]
             row = filtered[gene]
-            if not all(row[CUT_FIELDS[m]] <= cutoffs[m] for m in cutoffs):
+            if not all(row[f] <= c for f, c in cuts):
                 continue
-            first = gene.split("_|_") if "_|_" in gene else [gene, str(row["NUGN"]), str(row["Annotation"])]
-            out = first + [str(row[k]) for k in ("tpgp", "tngp", "tpgn", "tngn", "sens", "spes", "OR", "p_v", "B_p",
-                                                  "BH_p")]
-            if not no_pairwise:
-                out += [str(row[k]) for k in ("max_total_pairs", "max_propairs", "max_antipairs", "Pbest", "Pworst")]
-                if permutations >= 10:
-                    out.append(str(row["Empirical_p"]))
+            out = gene.split("_|_") if "_|_" in gene else [gene, str(row["NUGN"]), str(row["Annotation"])]
+            out += map(str, stats_of(row))
             for colname in extracolstoprint:
                 parts = gene.split("--") if "--" in gene else [gene]
                 out.append("--".join(str(genedic[g][colname + "_name"]) for g in parts))
-            outfile.write(delimiter.join('"' + c + '"' for c in out) + "\n")
+            lines.append('"' + sep.join(out) + '"\n')
+            if len(lines) >= 65536:
+                outfile.writelines(lines)
+                lines = []
+        outfile.writelines(lines)
 
 
 # ============================================================================ CLI
