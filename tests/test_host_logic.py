@@ -234,3 +234,19 @@ def test_vcf_first_row_is_the_reference_ci_golden():
     with open(os.path.join(GOLD, "vcf", "Example.csv")) as fh:
         rows = list(csv.reader(fh))
     assert rows[1] == ["NC_000962", "4013", "0", "T", "C", "9999", "0", "TYPE=snp", "GT", "False", "0", "1", "1", "1"]
+
+
+def test_vectorised_binomial_test_is_bitwise_the_scalar_scipy_call():
+    """PairWiseComparisons evaluates ss.binom_test(k, n, 0.5) (scoary/methods.py:1267-1275) for all genes in one
+    vectorised SciPy call; the columns must not change by a bit."""
+    from scipy import stats as ss
+    rng = np.random.default_rng(3)
+    pairs = [(k, n) for n in range(1, 40) for k in range(n + 1)]
+    for n in rng.integers(40, 5001, 60).tolist():
+        pairs += [(int(k), n) for k in set(rng.integers(0, n + 1, 4).tolist() + [0, n, n // 2, (n + 1) // 2])]
+    k = np.array([p[0] for p in pairs] + [0]), np.array([p[1] for p in pairs] + [0])
+    M._BINOM_CACHE.clear()
+    got = M._binom_two_sided_many(*k)
+    want = np.array([float(ss.binomtest(a, b, 0.5).pvalue) for a, b in pairs] + [1.0])
+    assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
+    assert np.array_equal(M._binom_two_sided_many(*k).view(np.uint64), want.view(np.uint64))      # from the cache
