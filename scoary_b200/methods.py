@@ -576,14 +576,31 @@ _RMIN_CACHE = {}
 
 def early_stop_table(P):
     """rmin[i] = least r for which the reference aborts after permutation i:
-    1 - ss.binom.cdf(r, i, 0.1) < 0.05 (scoary/methods.py:1360-1361)."""
+    1 - ss.binom.cdf(r, i, 0.1) < 0.05 (scoary/methods.py:1360-1361).  Same SciPy expression as the
+    reference evaluates, but only around the boundary (started from the normal approximation and
+    walked down/up to the first r that satisfies it) and for all i at once."""
     t = _RMIN_CACHE.get(P)
     if t is None:
         from scipy import stats as ss
         t = np.full(max(P, 1), np.iinfo(np.int32).max, dtype=np.int32)
-        for i in range(30, P):
-            r = np.arange(0, i + 2)
-            t[i] = int(np.argmax((1 - ss.binom.cdf(r, i, 0.1)) < 0.05))
+        if P > 30:
+            i = np.arange(30, P, dtype=np.int64)
+
+            def stops(r):
+                return (1 - ss.binom.cdf(r, i, 0.1)) < 0.05
+
+            r = np.clip(np.floor(0.1 * i + 1.645 * np.sqrt(0.09 * i)).astype(np.int64), 0, i + 1)
+            for _ in range(64):                          # down while the smaller r already stops
+                down = (r > 0) & stops(np.maximum(r - 1, 0))
+                if not down.any():
+                    break
+                r[down] -= 1
+            for _ in range(64):                          # up to the first r that stops
+                up = ~stops(r)
+                if not up.any():
+                    break
+                r[up] += 1
+            t[30:P] = r
         _RMIN_CACHE[P] = t
     return t
 

@@ -250,3 +250,17 @@ def test_vectorised_binomial_test_is_bitwise_the_scalar_scipy_call():
     want = np.array([float(ss.binomtest(a, b, 0.5).pvalue) for a, b in pairs] + [1.0])
     assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
     assert np.array_equal(M._binom_two_sided_many(*k).view(np.uint64), want.view(np.uint64))      # from the cache
+
+
+def test_early_stop_table_is_the_reference_expression():
+    """rmin[i] found around the boundary must equal the first r of the reference's own test
+    1 - ss.binom.cdf(r, i, 0.1) < 0.05 (scoary/methods.py:1360-1361) scanned from r = 0."""
+    from scipy import stats as ss
+    P = 700
+    M._RMIN_CACHE.clear()
+    got = M.early_stop_table(P)
+    for i in range(30, P):
+        r = np.arange(0, i + 2)
+        assert got[i] == int(np.argmax((1 - ss.binom.cdf(r, i, 0.1)) < 0.05)), i
+    assert np.all(got[:30] == np.iinfo(np.int32).max)
+    assert [int(M.early_stop_table(10000)[i]) for i in (30, 50, 100, 1000, 9999)] == [6, 9, 15, 116, 1049]
