@@ -188,6 +188,31 @@ int64_t sb_csv_pack_rows(const char *buf, int64_t len, char delimiter, const int
                          int32_t W, const int32_t *lead_cols, int32_t n_lead, int64_t *lead_ranges,
                          int32_t *row_fields);
 
+/* ---- VCF input (host code, no GPU needed) ---- */
+/* scoary/vcf2scoary.py:50-218 followed by the cell loop of Csv_to_dic_Roary (methods.py:445-497),
+ * done natively on the raw bytes of a VCF 4.x file: one output row per ALT allele, genotype = the
+ * sample cell up to its first ':', single-ALT lines present unless "", "0" or "-", multi-ALT
+ * lines present where int(genotype) is the allele's number ("." = absent), optional TYPE= filter.
+ * sb_vcf_line_starts: byte offsets of the non-empty lines from the "#CHROM" header on (the "##"
+ *   lines before it are skipped); line_starts = NULL to count.  *needs_python = 1 if the header
+ *   or a variant line holds a '"' or a byte >= 0x80 (csv quoting / Unicode rules could matter:
+ *   use the Python parser).
+ * sb_vcf_count_rows: rows_per_line[i] for the variant lines (not the header); `types` is a
+ *   '\n'-separated list of wanted TYPE values or NULL for all.  Returns the total number of rows,
+ *   or -(line + 1) for a line with fewer than nine fields.
+ * sb_vcf_pack_rows: bits uint64[n_rows][W]; keep[n_samples] = bit index of each sample column or
+ *   -1 to drop it; ranges[n_rows][3][2] = byte ranges of CHROM, POS, ID; line_of[n_rows] = source
+ *   line.  Returns 0, or -(line + 1) for the first line that must go to the Python parser (sample
+ *   count differs from the header, or a multi-ALT genotype that is neither "." nor plain digits). */
+int64_t sb_vcf_line_starts(const char *buf, int64_t len, int64_t *line_starts, int64_t max_lines,
+                           int32_t *needs_python);
+int64_t sb_vcf_count_rows(const char *buf, int64_t len, const int64_t *line_starts, int64_t n_lines,
+                          const char *types, int64_t types_len, int32_t *rows_per_line);
+int64_t sb_vcf_pack_rows(const char *buf, int64_t len, const int64_t *line_starts, int64_t n_lines,
+                         const int32_t *rows_per_line, const int64_t *row_offset, const char *types,
+                         int64_t types_len, const int32_t *keep, int32_t n_samples, uint64_t *bits,
+                         int32_t W, int64_t *ranges, int64_t *line_of);
+
 /* Test hook, host only (no GPU needed): the tree compiler behind sb_set_tree.  Writes the stack
  * program (uint16 ops: low 4 bits = op type, high 12 bits = count; see csrc/walk.cuh) and the
  * order in which the program consumes the leaves.  Returns the number of ops or a negative

@@ -66,6 +66,7 @@ class GeneTable(Mapping):
             m = np.ascontiguousarray(matrix, dtype=np.uint8).reshape(len(self.names), len(self.strains))
             bits = eng.pack_rows(m) if len(self.names) else np.zeros((0, eng.words_for(len(self.strains))), np.uint64)
         self.bits = np.ascontiguousarray(bits, dtype=np.uint64)
+        self.all_bits = self.bits        # every line of the file, duplicates included: what the tree is built from
         self._matrix = None
         # the reference's dict keeps the LAST row of a duplicated identifier at the position of
         # its FIRST occurrence (methods.py:450,462)
@@ -347,7 +348,9 @@ def upgma(table):
     if len(table.strains) < 2:
         sys.exit("Need at least two isolates to build a tree")
     e = get_engine()
-    e.set_genes(table.bits, len(table.strains))
+    # the reference's distance matrix counts every line of the file, also those a later line with the same
+    # identifier replaces in the gene dictionary (methods.py:496 vs :458-463)
+    e.set_genes(table.all_bits, len(table.strains))
     return treemod.from_merges(table.strains, e.upgma())
 
 
@@ -1000,10 +1003,22 @@ def main(**kwargs):
                 allowed = None
                 if args.write_reduced:
                     sys.exit("You cannot use the -w argument without specifying a subset (-r)")
-            log.info("Reading gene presence absence file")
-            parsed = Csv_to_dic_Roary(genes, args.delimiter, [-999] if args.grabcols == "ALL" else args.grabcols,
-                                      startcol=int(args.start_col) - 1, allowed_isolates=allowed,
-                                      writereducedset=args.write_reduced, time=currenttime, outdir=args.outdir)
+            if args.genes.lower().endswith(".vcf"):
+                # a VCF goes straight to the packed table: what vcf2scoary followed by
+                # `-s 11` gives, without writing and re-reading the converted CSV
+                if args.grabcols or args.write_reduced:
+                    sys.exit("--include_input_columns and -w need a converted table: run vcf2scoary first")
+                log.info("Reading variants from the VCF file")
+                from . import vcf2scoary
+                table = vcf2scoary.vcf_to_table(args.genes, "ALL", allowed)
+                parsed = {"Roarydic": table, "Zero_ones_matrix": None, "Strains": table.strains, "Extracols": [],
+                          "Firstcolnames": ["#CHROM", "POS", "ID"]}
+            else:
+                log.info("Reading gene presence absence file")
+                parsed = Csv_to_dic_Roary(genes, args.delimiter, [-999] if args.grabcols == "ALL" else args.grabcols,
+                                          startcol=int(args.start_col) - 1, allowed_isolates=allowed,
+                                          writereducedset=args.write_reduced, time=currenttime,
+                                          outdir=args.outdir)
             genedic, strains = parsed["Roarydic"], parsed["Strains"]
             if args.newicktree is None and not args.no_pairwise:
                 log.info("Creating Hamming distance matrix based on gene presence/absence")

@@ -96,15 +96,75 @@ def convert(vcf_path, out_path, types="ALL"):
     print("Reached the end of the file")
 
 
-def vcf_to_table(vcf_path, types="ALL"):
-    """VCF -> GeneTable, equal to Csv_to_dic_Roary(converted CSV, startcol=10)["Roarydic"]."""
+def _native_table(vcf_path, types, keep):
+    """The packed table through sb_vcf_* (csrc/vcf_pack.cpp), or None when the file needs the Python
+    parser (quotes, non-ASCII bytes, ragged lines, unusual genotypes) -- then the caller runs it."""
+    import ctypes
+    import io
+    from . import _lib
     from . import engine as eng
     from .methods import GeneTable
+    lib = _lib.load()
+    with open(vcf_path, "rb") as fh:
+        buf = fh.read()
+    odd = ctypes.c_int32(0)
+    n = lib.sb_vcf_line_starts(buf, len(buf), None, 0, ctypes.byref(odd))
+    if odd.value or n < 1:
+        return None
+    starts = np.empty(n, dtype=np.int64)
+    lib.sb_vcf_line_starts(buf, len(buf), starts.ctypes.data_as(ctypes.c_void_p), n, None)
+    head_end = int(starts[1]) if n > 1 else len(buf)
+    rows = csv.reader(io.StringIO(buf[:head_end].decode("utf-8"), newline=None), delimiter="\t", quotechar='"')
+    meta, formats, header = _read_meta_and_header(rows)
+    _check(meta, formats)
+    strains = header[9:]
+    keep_idx = np.full(len(strains), -1, dtype=np.int32)
+    kept = [j for j, s in enumerate(strains) if keep is None or s in keep]
+    keep_idx[kept] = np.arange(len(kept), dtype=np.int32)
+    kept_names = [strains[j] for j in kept]
+    tl = None if types == "ALL" else "\n".join(types).encode("ascii", "replace")
+    n_lines = n - 1
+    vstarts = np.ascontiguousarray(starts[1:])
+    per_line = np.zeros(max(n_lines, 1), dtype=np.int32)
+    total = lib.sb_vcf_count_rows(buf, len(buf), vstarts.ctypes.data_as(ctypes.c_void_p), n_lines, tl,
+                                  len(tl) if tl is not None else 0, per_line.ctypes.data_as(ctypes.c_void_p))
+    if total < 0:
+        return None
+    W = eng.words_for(len(kept))
+    offs = np.zeros(max(n_lines, 1), dtype=np.int64)
+    np.cumsum(per_line[:n_lines - 1], out=offs[1:n_lines]) if n_lines > 1 else None
+    bits = np.zeros((total, W), dtype=np.uint64)
+    ranges = np.zeros((max(total, 1), 3, 2), dtype=np.int64)
+    rc = lib.sb_vcf_pack_rows(buf, len(buf), vstarts.ctypes.data_as(ctypes.c_void_p), n_lines,
+                              per_line.ctypes.data_as(ctypes.c_void_p), offs.ctypes.data_as(ctypes.c_void_p), tl,
+                              len(tl) if tl is not None else 0, keep_idx.ctypes.data_as(ctypes.c_void_p), len(strains),
+                              bits.ctypes.data_as(ctypes.c_void_p), W, ranges.ctypes.data_as(ctypes.c_void_p), None)
+    if rc != 0:
+        return None
+    rg = ranges[:total].tolist()
+    chrom = [buf[b:e].decode("ascii") for (b, e), _, _ in rg]
+    pos = [buf[b:e].decode("ascii") for _, (b, e), _ in rg]
+    vid = [buf[b:e].decode("ascii") for _, _, (b, e) in rg]
+    names = [c + "_|_" + p + "_|_" + i for c, p, i in zip(chrom, pos, vid)]
+    return GeneTable(names, pos, vid, kept_names, bits=bits)
+
+
+def vcf_to_table(vcf_path, types="ALL", allowed_isolates=None):
+    """VCF -> GeneTable, equal to Csv_to_dic_Roary(converted CSV, startcol=10)["Roarydic"]
+    (restricted to `allowed_isolates` like its allowed_isolates argument).  Parsed natively
+    (sb_vcf_*); files the native parser is not sure about go through the Python csv module."""
+    from . import engine as eng
+    from .methods import GeneTable
+    if os.environ.get("SCOARY_B200_PY_CSV") != "1":
+        table = _native_table(vcf_path, types, allowed_isolates)
+        if table is not None:
+            return table
     with open(vcf_path, "r") as fh:
         rows = csv.reader(fh, delimiter="\t", quotechar='"')
         meta, formats, header = _read_meta_and_header(rows)
         _check(meta, formats)
         strains = header[9:]
+        kept = [j for j, s in enumerate(strains) if allowed_isolates is None or s in allowed_isolates]
         names, nug, ann, packed = [], [], [], []
         absent = ("", "0", "-")
         chunk = []
@@ -112,15 +172,15 @@ def vcf_to_table(vcf_path, types="ALL"):
             names.append(head[0] + "_|_" + head[1] + "_|_" + head[2])
             nug.append(head[1])
             ann.append(head[2])
-            chunk.append([c not in absent for c in cells])
+            chunk.append([cells[j] not in absent for j in kept])
             if len(chunk) == 4096:
-                packed.append(eng.pack_rows(np.asarray(chunk, dtype=np.uint8)))
+                packed.append(eng.pack_rows(np.asarray(chunk, dtype=np.uint8).reshape(len(chunk), len(kept))))
                 chunk = []
         if chunk:
-            packed.append(eng.pack_rows(np.asarray(chunk, dtype=np.uint8)))
-    W = eng.words_for(len(strains))
+            packed.append(eng.pack_rows(np.asarray(chunk, dtype=np.uint8).reshape(len(chunk), len(kept))))
+    W = eng.words_for(len(kept))
     bits = np.concatenate(packed, axis=0) if packed else np.zeros((0, W), dtype=np.uint64)
-    return GeneTable(names, nug, ann, strains, bits=bits)
+    return GeneTable(names, nug, ann, [strains[j] for j in kept], bits=bits)
 
 
 def main(argv=None):

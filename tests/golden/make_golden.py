@@ -182,6 +182,21 @@ def main():
         except SystemExit:
             pass
         sys.argv = old
+    # ---- the reference CLI on the converted tables (-s 11): golden for reading a VCF directly (-g x.vcf)
+    with open(os.path.join(vdir, "generated_traits.csv"), "w") as fh:
+        fh.write(",resistant,with_missing\n")
+        for i, smp in enumerate(samples):
+            fh.write("%s,%d,%s\n" % (smp, vr.randint(0, 1), "NA" if i % 9 == 4 else str(vr.randint(0, 1))))
+    shutil.copyfile(os.path.join(EX, "ExampleVCFTrait.csv"), os.path.join(vdir, "ExampleVCFTrait.csv"))
+    for vname, tname in (("generated", "generated_traits.csv"), ("Example", "ExampleVCFTrait.csv")):
+        out = tempfile.mkdtemp(prefix="golden_vcfcli_")
+        rc = ref_shim.run_cli(["-g", os.path.join(vdir, vname + ".csv"), "-t", os.path.join(vdir, tname), "-s", "11",
+                               "-p", "1.0", "-c", "I", "-o", out, "--no-time"])
+        assert rc in (0, None), rc
+        for f in sorted(os.listdir(out)):
+            if f.endswith(".results.csv"):
+                store(os.path.join(out, f), os.path.join(vdir, "cli_" + vname, f), False)
+        shutil.rmtree(out)
     # ---- the reference's own CI golden row
     with open(os.path.join(HERE, "tetrcg_first_row.json"), "w") as fh:
         json.dump({"source": "tests/test_scoary_output.py:12-14",

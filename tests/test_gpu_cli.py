@@ -45,16 +45,17 @@ def _run(argv):
     assert isinstance(M._ENGINE, Engine)
 
 
-def _compare(got_path, gold_path):
+def _compare(got_path, gold_path, key_cols=1):
     hdr, got = _rows(got_path)
     ghdr, gold = _rows(gold_path)
     assert hdr == ghdr
     assert len(got) == len(gold)
     col = {h: i for i, h in enumerate(hdr)}
-    assert sorted(r[0] for r in got) == sorted(r[0] for r in gold)
-    by_gene = {r[0]: r for r in got}
+    assert sorted(tuple(r[:key_cols]) for r in got) == sorted(tuple(r[:key_cols]) for r in gold)
+    by_gene = {tuple(r[:key_cols]): r for r in got}
+    assert len(by_gene) == len(got)
     for g in gold:
-        r = by_gene[g[0]]
+        r = by_gene[tuple(g[:key_cols])]
         assert r[1:3] == g[1:3]
         for c in INT_COLS:
             if c in col:
@@ -72,7 +73,7 @@ def _compare(got_path, gold_path):
     for a, b in zip(got, gold):
         pa, pb = float(a[ip]), float(b[ip])
         assert pa == pb or abs(pa - pb) <= RTOL * abs(pb), ("sorted p sequence differs", a[0], b[0], pa, pb)
-        swapped += a[0] != b[0]
+        swapped += a[:key_cols] != b[:key_cols]
     return swapped, len(gold)
 
 
@@ -153,3 +154,14 @@ def test_cli_two_gpus_matches_reference_results(inputs):
         for g in gold:
             for c in INT_COLS:
                 assert by_gene[g[0]][col[c]] == g[col[c]], (trait, g[0], c)
+
+
+def test_cli_reads_a_vcf_directly(tmp_path):
+    """`-g x.vcf` on the GPU against the reference CLI run on the vcf2scoary-converted table (-s 11)."""
+    vdir = os.path.join(GOLD, "vcf")
+    out = str(tmp_path / "out")
+    _run(["-g", os.path.join(vdir, "generated.vcf"), "-t", os.path.join(vdir, "generated_traits.csv"), "-p", "1.0", "-c",
+          "I", "-o", out, "--no-time"])
+    for t in ("resistant", "with_missing"):
+        _compare(os.path.join(out, t + ".results.csv"), os.path.join(vdir, "cli_generated", t + ".results.csv"),
+                 key_cols=3)

@@ -264,3 +264,85 @@ def test_early_stop_table_is_the_reference_expression():
         assert got[i] == int(np.argmax((1 - ss.binom.cdf(r, i, 0.1)) < 0.05)), i
     assert np.all(got[:30] == np.iinfo(np.int32).max)
     assert [int(M.early_stop_table(10000)[i]) for i in (30, 50, 100, 1000, 9999)] == [6, 9, 15, 116, 1049]
+
+
+@pytest.mark.parametrize("vname,tname,traits", [("generated", "generated_traits.csv", ["resistant", "with_missing"]),
+                                                ("Example", "ExampleVCFTrait.csv", ["ExampleVCFtrait"])])
+def test_cli_reads_a_vcf_directly(vname, tname, traits, tmp_path, fake_engine):
+    """`-g x.vcf` = the reference's vcf2scoary followed by `scoary -g converted.csv -s 11` (goldens written
+    by the reference that way), without the CSV round trip."""
+    vdir = os.path.join(GOLD, "vcf")
+    out = str(tmp_path / "out")
+    _run(["-g", os.path.join(vdir, vname + ".vcf"), "-t", os.path.join(vdir, tname), "-p", "1.0", "-c", "I", "-o", out,
+          "--no-time"])
+    for t in traits:
+        assert _read(os.path.join(out, t + ".results.csv")) == \
+            _read(os.path.join(vdir, "cli_" + vname, t + ".results.csv")), t
+
+
+def test_native_vcf_packer_equals_python_parser(tmp_path, monkeypatch):
+    """csrc/vcf_pack.cpp against the csv-module parser on generated files: line endings, empty lines,
+    multi-allelic sites with multi-digit and zero-padded alleles, '.', TYPE= filters, -r subsets, and
+    lines only the Python parser may judge (then the native path must step aside)."""
+    import random
+    from scoary_b200 import vcf2scoary as V
+    rng = random.Random(7)
+    used = 0
+    for it in range(40):
+        ns = rng.choice([0, 1, 5, 63, 64, 65, 130])
+        samples = ["S%03d" % i for i in range(ns)]
+        lines = ["##fileformat=VCFv4.2", '##FORMAT=<ID=GT,Number=1,Type=String,Description="Genotype">', "",
+                 "\t".join(["#CHROM", "POS", "ID", "REF", "ALT", "QUAL", "FILTER", "INFO", "FORMAT"] + samples)]
+        for k in range(rng.choice([0, 1, 7, 60])):
+            nalt = rng.choice([1, 1, 1, 2, 3, 12])
+            info = rng.choice(["TYPE=snp", "DP=3;TYPE=ins", "SUBTYPE=del;X=1", "TYPE=;TYPE=complex", "NOTYPE", "TYPE=snp_x;Q"])
+            cells = [rng.choice(["0", "0", "1", ".", "2", "3", "12", "01", "-", "", "10"]) +
+                     rng.choice(["", ":35", ":1:2", ":"]) for _ in samples]
+            if it % 8 == 7 and k == 3 and cells:
+                cells[0] = "1/1"
+            if rng.random() < 0.05:
+                lines.append("")
+            lines.append("\t".join(["chr%d" % (k % 3), str(100 + k * 7), rng.choice(["id%d" % k, ".", ""]), "A",
+                                    ",".join("ACGT"[a % 4] * (1 + a // 4) for a in range(nalt)), "99", "PASS", info,
+                                    "GT:DP"] + cells))
+        path = str(tmp_path / ("f%d.vcf" % it))
+        eol = rng.choice(["\n", "\r\n", "\r"])
+        with open(path, "w", newline="") as fh:
+            fh.write(eol.join(lines) + (eol if it % 3 else ""))
+        types = rng.choice(["ALL", ["snp"], ["snp", "ins", "complex"], ["del"], ["snp_x"]])
+        keep = rng.choice([None, set(samples[::2])])
+
+        def run(py):
+            if py:
+                monkeypatch.setenv("SCOARY_B200_PY_CSV", "1")
+            else:
+                monkeypatch.delenv("SCOARY_B200_PY_CSV", raising=False)
+            try:
+                return V.vcf_to_table(path, types, keep)
+            except SystemExit as ex:
+                return "exit %r" % (ex.code,)
+        monkeypatch.delenv("SCOARY_B200_PY_CSV", raising=False)
+        try:
+            used += V._native_table(path, types, keep) is not None
+        except SystemExit:
+            pass
+        a, b = run(False), run(True)
+        if isinstance(a, str) or isinstance(b, str):
+            assert a == b, (it, a, b)
+            continue
+        assert (a.names, a.nugn, a.annotation, a.strains) == (b.names, b.nugn, b.annotation, b.strains), it
+        assert a.bits.shape == b.bits.shape and np.array_equal(a.bits, b.bits), it
+    assert used >= 20
+
+
+def test_duplicate_identifiers_count_in_the_tree_but_not_in_the_table(tmp_path, fake_engine):
+    """A converted VCF table repeats CHROM_|_POS_|_ID for every allele of a multi-allelic site: the reference's
+    gene dictionary keeps the last such line (methods.py:458-463) while its distance matrix is built from every
+    line (:496).  Golden = the reference CLI on the same CSV."""
+    vdir = os.path.join(GOLD, "vcf")
+    out = str(tmp_path / "out")
+    _run(["-g", os.path.join(vdir, "generated.csv"), "-s", "11", "-t", os.path.join(vdir, "generated_traits.csv"),
+          "-p", "1.0", "-c", "I", "-o", out, "--no-time"])
+    for t in ("resistant", "with_missing"):
+        assert _read(os.path.join(out, t + ".results.csv")) == \
+            _read(os.path.join(vdir, "cli_generated", t + ".results.csv")), t
