@@ -846,22 +846,30 @@ def filtrationoptions(cutoffs, collapse):
 
 
 def grabcoltype(string):
-    """'4,6,8,16-23' or ALL -> zero-based column list (scoary/methods.py:1510-1549)."""
+    """--include_input_columns: '4,6-8' or ALL -> zero-based columns (scoary/methods.py:1510-1549).
+    As in the reference a range a-b needs b > a and stops BEFORE b, the three identifier columns are
+    dropped, and the result is list(set(...)) -- the column order of the output follows from that."""
     if string == "ALL":
         return [-999]
+    if string == "":
+        return []
     cols = []
-    try:
-        for part in string.replace(" ", "").split(","):
-            if not part:
-                continue
-            if "-" in part:
-                lo, hi = part.split("-")
-                cols += list(range(int(lo), int(hi) + 1))
-            else:
-                cols.append(int(part))
-    except ValueError:
-        raise argparse.ArgumentTypeError("Could not understand the column specification: %s" % string)
-    return sorted(set(c - 1 for c in cols))
+    for part in string.split(","):
+        if "-" in part:
+            try:
+                lo, hi = (int(x) for x in part.split("-")[:2])
+                if not hi > lo:
+                    raise ValueError(part)
+            except (ValueError, IndexError):
+                sys.exit("Could not understand --include_input_columns argument %s" % part)
+            cols += list(range(lo, hi))
+        else:
+            cols.append(int(part))
+    cols = [c - 1 for c in cols if c - 1 not in (0, 1, 2)]
+    if not all(c > 1 for c in cols):
+        sys.exit("Could not understand --include_input_columns argument. Make sure all numbers are positive and "
+                 "real.")
+    return list(set(cols))
 
 
 def ScoaryArgumentParser(argv=None):

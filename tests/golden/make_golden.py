@@ -49,6 +49,11 @@ SCENARIOS = {
     "all": (["-g", G, "-t", T, "-p", "1.0", "-c", "I"], True),
     "collapse": (["-g", G, "-t", T, "-p", "1.0", "-c", "I", "--collapse"], True),
     "perm": (["-g", G, "-t", T, "-e", "200", "-c", "I", "EPW", "-p", "0.05", "0.05"], False),
+    # behaviours the Travis scenarios do not reach
+    # (-n needs ete3, which this container does not have: custom trees are checked against the UPGMA run instead)
+    "bh_pw": (["-g", G, "-t", T, "-c", "I", "BH", "PW", "-p", "0.05", "0.2", "0.05", "-m", "40"], False),
+    "grabcols": (["-g", G, "-t", T, "--include_input_columns", "4,6-8", "-p", "0.01"], False),
+    "reduced": (["-g", G, "-t", T, "-r", R, "-w", "-p", "0.01", "--no_pairwise"], False),
 }
 
 
@@ -73,10 +78,31 @@ def main():
         rc = ref_shim.run_cli(argv + ["-o", out, "--no-time"])
         assert rc in (0, None), (name, rc)
         for f in sorted(os.listdir(out)):
-            if f.endswith(".results.csv") or f.endswith(".nwk"):
-                store(os.path.join(out, f), os.path.join(HERE, name, f), gz and f.endswith(".csv"))
+            if f.endswith(".results.csv") or f.endswith(".nwk") or f.startswith("gene_presence_absence_reduced"):
+                store(os.path.join(out, f), os.path.join(HERE, name, f),
+                      (gz and f.endswith(".csv")) or f.startswith("gene_presence_absence_reduced"))
         shutil.rmtree(out)
         print("scenario", name, "done")
+    # ---- --delimiter ';' : the example files rewritten with semicolons (inputs stored gzipped), results from the reference
+    import csv
+    sdir = os.path.join(HERE, "semicolon")
+    os.makedirs(sdir, exist_ok=True)
+    tmpd = tempfile.mkdtemp(prefix="golden_semi_")
+    for src, dst in ((G, "genes_semicolon.csv"), (T, "traits_semicolon.csv")):
+        with open(src, newline="") as fi, open(os.path.join(tmpd, dst), "w", newline="") as fo:
+            w = csv.writer(fo, delimiter=";", lineterminator="\n")
+            for k, row in enumerate(csv.reader(fi, skipinitialspace=True)):
+                w.writerow(row if (k < 1200 or dst.startswith("traits")) else row)
+        store(os.path.join(tmpd, dst), os.path.join(sdir, dst), gz=dst.startswith("genes"))
+    out = tempfile.mkdtemp(prefix="golden_semi_out_")
+    rc = ref_shim.run_cli(["-g", os.path.join(tmpd, "genes_semicolon.csv"), "-t", os.path.join(tmpd, "traits_semicolon.csv"),
+                           "--delimiter", ";", "-p", "0.05", "-o", out, "--no-time"])
+    assert rc in (0, None), rc
+    for f in sorted(os.listdir(out)):
+        if f.endswith(".results.csv"):
+            store(os.path.join(out, f), os.path.join(sdir, f), False)
+    shutil.rmtree(out)
+    shutil.rmtree(tmpd)
     # ---- direct calls: PhyloTree walks
     rng = random.Random(20260924)
 

@@ -346,3 +346,42 @@ def test_duplicate_identifiers_count_in_the_tree_but_not_in_the_table(tmp_path, 
     for t in ("resistant", "with_missing"):
         assert _read(os.path.join(out, t + ".results.csv")) == \
             _read(os.path.join(vdir, "cli_generated", t + ".results.csv")), t
+
+
+MORE_SCENARIOS = {
+    "bh_pw": ["-c", "I", "BH", "PW", "-p", "0.05", "0.2", "0.05", "-m", "40"],
+    "grabcols": ["--include_input_columns", "4,6-8", "-p", "0.01"],
+}
+
+
+@pytest.mark.parametrize("name", list(MORE_SCENARIOS))
+def test_cli_more_reference_scenarios(name, inputs, fake_engine):
+    """BH + pairwise cut-offs with -m, and --include_input_columns: text-identical to the reference."""
+    _run(["-g", inputs["g"], "-t", inputs["t"], "-o", inputs["out"], "--no-time"] + MORE_SCENARIOS[name])
+    for trait in ("Tetracycline_resistance", "Bogus_trait"):
+        assert _read(os.path.join(inputs["out"], trait + ".results.csv")) == \
+            _read(os.path.join(GOLD, name, trait + ".results.csv")), (name, trait)
+
+
+def test_cli_writes_the_reduced_gene_table(inputs, fake_engine):
+    """-r with -w: the reduced presence/absence file and the results computed from it (methods.py:510-544)."""
+    _run(["-g", inputs["g"], "-t", inputs["t"], "-o", inputs["out"], "--no-time", "-r", inputs["r"], "-w", "-p", "0.01",
+          "--no_pairwise"])
+    assert _read(os.path.join(inputs["out"], "gene_presence_absence_reduced.csv")) == \
+        _read(os.path.join(GOLD, "reduced", "gene_presence_absence_reduced.csv.gz"))
+    for trait in ("Tetracycline_resistance", "Bogus_trait"):
+        assert _read(os.path.join(inputs["out"], trait + ".results.csv")) == \
+            _read(os.path.join(GOLD, "reduced", trait + ".results.csv"))
+
+
+def test_cli_semicolon_delimiter(tmp_path, fake_engine):
+    """--delimiter ';' applies to both inputs and to the result files (methods.py:350-351, :1159-1197)."""
+    sdir = os.path.join(GOLD, "semicolon")
+    g = tmp_path / "genes_semicolon.csv"
+    with gzip.open(os.path.join(sdir, "genes_semicolon.csv.gz"), "rb") as fi, open(g, "wb") as fo:
+        shutil.copyfileobj(fi, fo)
+    out = str(tmp_path / "out")
+    _run(["-g", str(g), "-t", os.path.join(sdir, "traits_semicolon.csv"), "--delimiter", ";", "-p", "0.05", "-o", out,
+          "--no-time"])
+    for trait in ("Tetracycline_resistance", "Bogus_trait"):
+        assert _read(os.path.join(out, trait + ".results.csv")) == _read(os.path.join(sdir, trait + ".results.csv"))
