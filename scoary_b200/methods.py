@@ -479,6 +479,9 @@ def Setup_results(genedic, traitsdic, collapse):
             spes = np.where(num_neg > 0, tngn.astype(np.float64) / np.maximum(num_neg, 1) * 100, 0.0)
             odds = np.where((tngp > 0) & (tpgn > 0), (tpgp * tngn) / np.maximum(tngp * tpgn, 1).astype(np.float64),
                             np.inf)
+            # a table with an empty row or column has no odds ratio in SciPy (nan, p = 1): only the trait margins
+            # can be empty here, genes present in all or no isolates were skipped above
+            odds = np.where((num_pos == 0) | (num_neg == 0), np.nan, odds)
         res = {}
         row_of = {}
         idx = np.flatnonzero(keep)
@@ -553,7 +556,7 @@ def _binom_two_sided_many(k, n):
     key = k * (int(n.max(initial=0)) + 1) + n
     uniq, first, inverse = np.unique(key, return_index=True, return_inverse=True)
     uk, un = k[first], n[first]
-    vals = np.ones(len(uniq), dtype=np.float64)
+    vals = np.full(len(uniq), np.nan)                   # n = 0 (no contrasting pair): binomtest has no answer -> nan
     todo = [i for i in range(len(uniq)) if un[i] > 0 and (int(uk[i]), int(un[i])) not in _BINOM_CACHE]
     if todo:
         from scipy import stats as ss

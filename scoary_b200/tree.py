@@ -62,16 +62,18 @@ def leaves(tree):
 def prune(tree, drop):
     """PruneForMissing (scoary/methods.py:709-739): remove the isolates in `drop`;
     a node left with one child is replaced by that child.  Returns None when
-    nothing is left (the reference's bare `return`)."""
+    nothing is left (the reference's bare `return`).
+
+    The reference's UPGMA can leave a None where a cluster should be (when real distances tie
+    with the 1 it assigns to dead clusters, methods.py:685-686); its Prunedic always ends with
+    None (:612), so this pass is also what removes those: None children are dropped here."""
     drop = set(x for x in drop if x is not None)
-    if not drop:
-        return tree
     # post-order, iterative
     result = {}
     stack = [(tree, False)]
     while stack:
         node, done = stack.pop()
-        if isinstance(node, str):
+        if isinstance(node, str) or node is None:
             continue
         if not done:
             stack.append((node, True))
@@ -82,6 +84,8 @@ def prune(tree, drop):
             for ch in node:
                 if isinstance(ch, str):
                     kids.append(None if ch in drop else ch)
+                elif ch is None:
+                    kids.append(None)
                 else:
                     kids.append(result.pop(id(ch)))
             if kids[0] is None and kids[1] is None:
@@ -92,8 +96,8 @@ def prune(tree, drop):
                 result[id(node)] = kids[0]
             else:
                 result[id(node)] = [kids[0], kids[1]]
-    if isinstance(tree, str):
-        return None if tree in drop else tree
+    if isinstance(tree, str) or tree is None:
+        return None if (tree is None or tree in drop) else tree
     return result[id(tree)]
 
 
@@ -106,7 +110,7 @@ def to_scoary_newick(tree):
         n = stack.pop()
         if isinstance(n, tuple):       # literal text
             parts.append(n[0])
-        elif isinstance(n, str):
+        elif isinstance(n, str) or n is None:
             parts.append(repr(n))
         else:
             stack.append(("]",))

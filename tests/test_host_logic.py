@@ -247,9 +247,10 @@ def test_vectorised_binomial_test_is_bitwise_the_scalar_scipy_call():
     k = np.array([p[0] for p in pairs] + [0]), np.array([p[1] for p in pairs] + [0])
     M._BINOM_CACHE.clear()
     got = M._binom_two_sided_many(*k)
-    want = np.array([float(ss.binomtest(a, b, 0.5).pvalue) for a, b in pairs] + [1.0])
-    assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
-    assert np.array_equal(M._binom_two_sided_many(*k).view(np.uint64), want.view(np.uint64))      # from the cache
+    want = np.array([float(ss.binomtest(a, b, 0.5).pvalue) for a, b in pairs])
+    assert np.array_equal(got[:-1].view(np.uint64), want.view(np.uint64))
+    assert np.isnan(got[-1])                 # (0, 0): nan, as the reference prints with this SciPy
+    assert np.array_equal(M._binom_two_sided_many(*k)[:-1].view(np.uint64), want.view(np.uint64))      # from the cache
 
 
 def test_early_stop_table_is_the_reference_expression():
@@ -385,3 +386,13 @@ def test_cli_semicolon_delimiter(tmp_path, fake_engine):
           "--no-time"])
     for trait in ("Tetracycline_resistance", "Bogus_trait"):
         assert _read(os.path.join(out, trait + ".results.csv")) == _read(os.path.join(sdir, trait + ".results.csv"))
+
+
+def test_prune_removes_the_none_clusters_of_a_degenerate_upgma():
+    """With tied distances the reference's upgma can return a tree with None in place of a cluster
+    (methods.py:685-686); Prunedic always ends with None (:612) and PruneForMissing (:709-739) removes it."""
+    broken = [[[["a", "b"], "c"], "d"], None]
+    assert treemod.prune(broken, [None]) == [[["a", "b"], "c"], "d"]
+    assert treemod.prune(broken, ["d", None]) == [["a", "b"], "c"]
+    assert treemod.prune([["a", None], [None, None]], [None]) == "a"
+    assert treemod.to_scoary_newick(broken) == "(((('a', 'b'), 'c'), 'd'), None);"
