@@ -37,9 +37,9 @@ def engine():
 
 
 def pytest_collection_modifyitems(config, items):
-    # the full-size runs (BASELINE.json's shapes, seconds each) go last: `-x` reaches them only after every
-    # small parity test has passed
-    items.sort(key=lambda it: "test_gpu_full_size" in it.nodeid)
+    # the newest GPU checks and the full-size runs (BASELINE.json's shapes, seconds each) go last: `-x` reaches
+    # them only after every earlier parity test has passed
+    items.sort(key=lambda it: 2 if "test_gpu_full_size" in it.nodeid else 1 if "test_gpu_cli_more" in it.nodeid else 0)
     if _have_gpu():
         return
     skip = pytest.mark.skip(reason="no GPU in this container")

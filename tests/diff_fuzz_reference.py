@@ -47,24 +47,28 @@ def make_case(rng, d):
         bits = [(c if mode < 0.3 else (rng.random() < f)) for c in clade]
         if mode < 0.3 and rng.random() < 0.5:
             bits = [b ^ (rng.random() < 0.1) for b in bits]
-        if k and rng.random() < 0.1:
+        if k and rng.random() < 0.15:
             bits = prev                                    # identical pattern (collapse)
+        elif k and rng.random() < 0.05:
+            bits = [not x for x in prev]                   # complementary pattern
         prev = bits
         name = "gene%d" % k if not (names and rng.random() < 0.05) else rng.choice(names)    # repeated identifier
         names.append(name)
-        cells = [rng.choice(["x_%d" % k, "1", "a b", "0.0"]) if b else rng.choice(["", "", "0", "-"]) for b in bits]
+        cells = [rng.choice(["x_%d" % k, "1", "a b", "0.0", "--", "00", 'q""q', "x%sy" % delim]) if b
+                 else rng.choice(["", "", "0", "-"]) for b in bits]
         if roary:
-            lead = [name, rng.choice(["", "nug%d" % k]), rng.choice(["hypothetical protein", "a, b", ""])] + \
+            lead = [name, rng.choice(["", "nug%d" % k]), rng.choice(["hypothetical protein", "a, b", "", 'said ""hi""'])] + \
                    [str(rng.randint(1, 9)) for _ in head[3:]]
         else:
             lead = ["chr%d" % (k % 2), str(10 * k), rng.choice([".", "v%d" % k])] + ["A", "C", "9", "PASS", "TYPE=snp", "GT",
                                                                                    rng.choice(["True", "False"])]
-        lines.append(delim.join(q(c) for c in lead + cells))
+        sep = delim + (" " if rng.random() < 0.1 else "")          # skipinitialspace
+        lines.append(sep.join((q(c) if (rng.random() < 0.9 or delim in c or '"' in c) else c) for c in lead + cells))
     gpath = os.path.join(d, "genes.csv")
     with open(gpath, "w") as fh:
         fh.write("\n".join(lines) + "\n")
     nt = rng.choice([1, 1, 2, 3])
-    tl = [delim.join([""] + ["trait%d" % t for t in range(nt)])]
+    tl = [delim.join([rng.choice(["", "", "Name"])] + ["trait%d" % t for t in range(nt)])]
     order = list(range(n))
     if rng.random() < 0.5:
         rng.shuffle(order)

@@ -83,6 +83,34 @@ def main():
                       (gz and f.endswith(".csv")) or f.startswith("gene_presence_absence_reduced"))
         shutil.rmtree(out)
         print("scenario", name, "done")
+    # ---- edge cases found by tests/diff_fuzz_reference.py, pinned as a fixed scenario:
+    #      one variable gene (tied distances: the reference's upgma leaves a None cluster, PruneForMissing removes it),
+    #      a trait that is all zeros (SciPy: odds ratio nan, p 1), a gene/trait pair without contrasting pairs
+    #      (binomial p nan), missing values, an identifier used twice
+    edir = os.path.join(HERE, "edge")
+    os.makedirs(edir, exist_ok=True)
+    iso = ["iso%02d" % j for j in range(8)]
+    roary = ["Gene", "Non-unique Gene name", "Annotation", "No. isolates", "No. sequences", "Avg sequences per isolate",
+             "Genome Fragment", "Order within Fragment", "Accessory Fragment", "Accessory Order with Fragment", "QC",
+             "Min group size nuc", "Max group size nuc", "Avg group size nuc"]
+    rows = [("geneA", "00010111"), ("core", "11111111"), ("absent", "00000000")]
+    with open(os.path.join(edir, "genes.csv"), "w") as fh:
+        fh.write(",".join('"%s"' % c for c in roary + iso) + "\n")
+        for name, bitsx in rows:
+            fh.write(",".join('"%s"' % c for c in [name, "", "edge case"] + ["1"] * 11 +
+                              [("x" if ch == "1" else "") for ch in bitsx]) + "\n")
+    with open(os.path.join(edir, "traits.csv"), "w") as fh:
+        fh.write(",perfect,allzero,withNA,mixed\n")
+        for j, nm in enumerate(iso):
+            fh.write("%s,%s,0,%s,%s\n" % (nm, "00010111"[j], "NA" if j in (1, 6) else "01010011"[j], "10010110"[j]))
+    out = tempfile.mkdtemp(prefix="golden_edge_")
+    rc = ref_shim.run_cli(["-g", os.path.join(edir, "genes.csv"), "-t", os.path.join(edir, "traits.csv"), "-p", "1.0",
+                           "-c", "I", "-u", "-o", out, "--no-time"])
+    assert rc in (0, None), rc
+    for f in sorted(os.listdir(out)):
+        if f.endswith(".results.csv") or f.endswith(".nwk"):
+            store(os.path.join(out, f), os.path.join(edir, f), False)
+    shutil.rmtree(out)
     # ---- --delimiter ';' : the example files rewritten with semicolons (inputs stored gzipped), results from the reference
     import csv
     sdir = os.path.join(HERE, "semicolon")

@@ -396,3 +396,16 @@ def test_prune_removes_the_none_clusters_of_a_degenerate_upgma():
     assert treemod.prune(broken, ["d", None]) == [["a", "b"], "c"]
     assert treemod.prune([["a", None], [None, None]], [None]) == "a"
     assert treemod.to_scoary_newick(broken) == "(((('a', 'b'), 'c'), 'd'), None);"
+
+
+def test_cli_edge_cases_found_by_the_fuzzer(tmp_path, fake_engine):
+    """tests/golden/edge: one variable gene (the reference's upgma leaves a None cluster that PruneForMissing
+    removes; Tree.nwk still shows it), an all-zero trait (odds ratio nan), no contrasting pairs (binomial p nan),
+    missing values.  Text-identical to the reference."""
+    edir = os.path.join(GOLD, "edge")
+    out = str(tmp_path / "out")
+    _run(["-g", os.path.join(edir, "genes.csv"), "-t", os.path.join(edir, "traits.csv"), "-p", "1.0", "-c", "I", "-u",
+          "-o", out, "--no-time"])
+    for f in ("perfect", "allzero", "withNA", "mixed"):
+        assert _read(os.path.join(out, f + ".results.csv")) == _read(os.path.join(edir, f + ".results.csv")), f
+    assert _read(os.path.join(out, "Tree.nwk")) == _read(os.path.join(edir, "Tree.nwk"))
