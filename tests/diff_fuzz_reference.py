@@ -112,6 +112,57 @@ def make_case(rng, d):
     return argv
 
 
+def make_vcf_case(rng, d):
+    """A random VCF; the reference converts it (vcf2scoary) and reads the CSV with -s 11, ours reads the VCF."""
+    n = rng.choice([4, 6, 9, 20, 66])
+    samples = ["S%02d" % j for j in range(n)]
+    clade = [rng.random() < 0.5 for _ in samples]
+    vl = ["##fileformat=VCFv4.2", '##FORMAT=<ID=GT,Number=1,Type=String,Description="Genotype">',
+          '##INFO=<ID=TYPE,Number=A,Type=String,Description="The type of allele.">',
+          "\t".join(["#CHROM", "POS", "ID", "REF", "ALT", "QUAL", "FILTER", "INFO", "FORMAT"] + samples)]
+    for k in range(rng.choice([1, 5, 40, 120])):
+        nalt = rng.choice([1, 1, 1, 2, 3])
+        cells = []
+        for j in range(n):
+            if rng.random() < 0.4:
+                g = str(rng.randint(1, nalt)) if (clade[j] ^ (rng.random() < 0.15)) else "0"
+            else:
+                g = rng.choice(["0", "0", "1", ".", str(rng.randint(0, nalt))])
+            cells.append(g + rng.choice(["", ":%d" % rng.randint(1, 99)]))
+        vl.append("\t".join(["chr%d" % (k % 2), str(100 + 3 * k), rng.choice([".", "id%d" % k]), "A",
+                             ",".join(rng.sample("CGT", nalt)), "50", "PASS", "TYPE=" + rng.choice(["snp", "ins", "del"]),
+                             "GT:DP"] + cells))
+    vpath = os.path.join(d, "variants.vcf")
+    with open(vpath, "w") as fh:
+        fh.write("\n".join(vl) + "\n")
+    tpath = os.path.join(d, "traits.csv")
+    with open(tpath, "w") as fh:
+        fh.write(",t0,t1\n")
+        for j, smp in enumerate(samples):
+            fh.write("%s,%d,%s\n" % (smp, clade[j] ^ (rng.random() < 0.2), rng.choice(["0", "1", "1", "NA"])))
+    common = ["-t", tpath, "-c", "I", "-p", rng.choice(["1.0", "0.3"])]
+    if rng.random() < 0.3:
+        common.append("--collapse")
+    if rng.random() < 0.3:
+        common.append("--no_pairwise")
+    return vpath, common
+
+
+def convert_with_reference(vpath, cpath):
+    import importlib
+    ref_shim.load()
+    conv = importlib.import_module("scoary.vcf2scoary")
+    old = sys.argv
+    sys.argv = ["vcf2scoary", "--force", "--out", cpath, vpath]
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            conv.main()
+    except SystemExit:
+        pass
+    finally:
+        sys.argv = old
+
+
 def run_reference(argv, out):
     with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
         try:
@@ -148,9 +199,17 @@ def one(seed, keep=False):
     rng = random.Random(seed)
     d = tempfile.mkdtemp(prefix="scoary_fuzz_%d_" % seed)
     try:
-        argv = make_case(rng, d)
-        a = run_reference(argv, os.path.join(d, "ref"))
-        b = run_ours(argv, os.path.join(d, "ours"))
+        if rng.random() < 0.2:
+            vpath, common = make_vcf_case(rng, d)
+            cpath = os.path.join(d, "converted.csv")
+            convert_with_reference(vpath, cpath)
+            argv = ["-g", vpath, "-s", "11"] + common
+            a = run_reference(["-g", cpath, "-s", "11"] + common, os.path.join(d, "ref"))
+            b = run_ours(["-g", vpath] + common, os.path.join(d, "ours"))
+        else:
+            argv = make_case(rng, d)
+            a = run_reference(argv, os.path.join(d, "ref"))
+            b = run_ours(argv, os.path.join(d, "ours"))
         fa, fb = files(os.path.join(d, "ref")), files(os.path.join(d, "ours"))
         ok_exit = (a in (0, None)) == (b in (0, None))
         problems = []
