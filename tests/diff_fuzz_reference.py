@@ -95,6 +95,16 @@ def make_case(rng, d):
     argv += ["-c"] + corr + ["-p"] + pv
     if rng.random() < 0.3:
         argv.append("--collapse")
+    if rng.random() < 0.3 and not nopw:
+        # permutations: the reference's RNG is unseeded, so both sides get the same stand-in for the label
+        # shuffling (see fake_hits) and everything around it -- columns, sorting, the P cut-off -- is compared
+        argv += ["-e", str(rng.choice([10, 50, 400]))]
+        if rng.random() < 0.5:
+            i = argv.index("-c")
+            argv.insert(i + 1 + len(corr), "P")
+            j = argv.index("-p")
+            if len(pv) > 1:
+                argv.insert(j + 1 + len(pv), rng.choice(["1.0", "0.5", "0.11"]))
     if rng.random() < 0.3:
         argv += ["-m", str(rng.choice([1, 3, 10, 1000]))]
     if rng.random() < 0.3 and not nopw:
@@ -163,7 +173,19 @@ def convert_with_reference(vpath, cpath):
         sys.argv = old
 
 
+def fake_hits(n_ab, n_aB_, n_Ab, n_ab_, P):
+    """Deterministic stand-in for the number of permutations that beat the observed statistic."""
+    return (n_ab * 7 + n_aB_ * 13 + n_Ab * 31 + n_ab_ * 3) % (P + 1)
+
+
+def _ref_permute(tree, GTC, permutations, cutoffs):
+    from collections import Counter
+    c = Counter(GTC.values())
+    return (fake_hits(c["AB"], c["aB"], c["Ab"], c["ab"], permutations) + 1.0) / (permutations + 1.0)
+
+
 def run_reference(argv, out):
+    ref_shim.load().Permute = _ref_permute
     with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
         try:
             return ref_shim.run_cli(argv + ["-o", out, "--no-time"])
@@ -172,9 +194,20 @@ def run_reference(argv, out):
 
 
 def run_ours(argv, out):
+    import numpy as np
     from fake_engine import FakeEngine
     from scoary_b200 import methods as M
-    M._ENGINE = FakeEngine()
+
+    class Engine(FakeEngine):
+        def permute(self, t, P, seed=0, gene_idx=None, early_stop=False, rmin=None):
+            left, right, g, lab = self._walk_inputs(t, gene_idx)
+            g, lab = g.astype(np.int64), lab.astype(np.int64)
+            ab = g @ lab
+            r = [fake_hits(int(ab[k]), int(lab.sum() - ab[k]), int(g[k].sum() - ab[k]),
+                           int(len(lab) - lab.sum() - g[k].sum() + ab[k]), P) for k in range(len(g))]
+            return self.pairwise(t, gene_idx), np.asarray(r, dtype=np.int32), np.full(len(g), P, dtype=np.int32)
+
+    M._ENGINE = Engine()
     with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
         try:
             M.main(argv=argv + ["-o", out, "--no-time"])
