@@ -43,3 +43,30 @@ def test_reference_main_with_our_functions(name, extra, tmp_path, monkeypatch):
         with op(gold, "rt") as fh:
             want = fh.read()
         assert open(os.path.join(out, trait + ".results.csv")).read() == want, (name, trait)
+
+
+@pytest.mark.parametrize("name,extra", [("default", []), ("all", ["-p", "1.0", "-c", "I"])])
+def test_reference_main_with_our_pairwise_comparisons(name, extra, tmp_path, monkeypatch):
+    """The other seam of SURVEY 8(b): the reference's own Setup_results and StoreTraitResult, with
+    PairWiseComparisons((domain, argdict)) (call site methods.py:1105, def :1208) swapped for this repo's.
+    Its GTC argument is then the reference's dict of "AB"/"Ab"/"aB"/"ab" strings."""
+    ref = ref_shim.load()
+    monkeypatch.setattr(M, "_ENGINE", FakeEngine())
+    monkeypatch.setattr(ref, "PairWiseComparisons", M.PairWiseComparisons)
+    g = tmp_path / "Gene_presence_absence.csv"
+    with gzip.open(os.path.join(GOLD, "inputs", "Gene_presence_absence.csv.gz"), "rb") as fi, open(g, "wb") as fo:
+        shutil.copyfileobj(fi, fo)
+    out = str(tmp_path / "out")
+    argv = ["-g", str(g), "-t", os.path.join(GOLD, "inputs", "Tetracycline_resistance.csv"), "-o", out, "--no-time"] + extra
+    monkeypatch.setattr(sys, "argv", ["scoary"] + argv)
+    with pytest.raises(SystemExit) as ex:
+        ref.main()
+    assert ex.value.code == 0
+    for trait in ("Tetracycline_resistance", "Bogus_trait"):
+        gold = os.path.join(GOLD, name, trait + ".results.csv")
+        op = open
+        if not os.path.exists(gold):
+            gold, op = gold + ".gz", gzip.open
+        with op(gold, "rt") as fh:
+            want = fh.read()
+        assert open(os.path.join(out, trait + ".results.csv")).read() == want, (name, trait)
