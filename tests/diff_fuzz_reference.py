@@ -173,15 +173,15 @@ def convert_with_reference(vpath, cpath):
         sys.argv = old
 
 
-def fake_hits(n_ab, n_aB_, n_Ab, n_ab_, P):
-    """Deterministic stand-in for the number of permutations that beat the observed statistic."""
-    return (n_ab * 7 + n_aB_ * 13 + n_Ab * 31 + n_ab_ * 3) % (P + 1)
+def fake_hits(total, pro, anti, P):
+    """Deterministic stand-in for the number of permutations that beat the observed statistic (a function of
+    the unpermuted walk, which both sides compute on the same tree)."""
+    return (total * 7 + pro * 13 + anti * 31 + 3) % (P + 1)
 
 
 def _ref_permute(tree, GTC, permutations, cutoffs):
-    from collections import Counter
-    c = Counter(GTC.values())
-    return (fake_hits(c["AB"], c["aB"], c["Ab"], c["ab"], permutations) + 1.0) / (permutations + 1.0)
+    w = ref_shim.load().ConvertUPGMAtoPhyloTree(tree, GTC)
+    return (fake_hits(w["Total"], w["Pro"], w["Anti"], permutations) + 1.0) / (permutations + 1.0)
 
 
 def run_reference(argv, out):
@@ -200,12 +200,9 @@ def run_ours(argv, out):
 
     class Engine(FakeEngine):
         def permute(self, t, P, seed=0, gene_idx=None, early_stop=False, rmin=None):
-            left, right, g, lab = self._walk_inputs(t, gene_idx)
-            g, lab = g.astype(np.int64), lab.astype(np.int64)
-            ab = g @ lab
-            r = [fake_hits(int(ab[k]), int(lab.sum() - ab[k]), int(g[k].sum() - ab[k]),
-                           int(len(lab) - lab.sum() - g[k].sum() + ab[k]), P) for k in range(len(g))]
-            return self.pairwise(t, gene_idx), np.asarray(r, dtype=np.int32), np.full(len(g), P, dtype=np.int32)
+            pairs = self.pairwise(t, gene_idx)
+            r = [fake_hits(int(a), int(b), int(c), P) for a, b, c in pairs]
+            return pairs, np.asarray(r, dtype=np.int32), np.full(len(r), P, dtype=np.int32)
 
     M._ENGINE = Engine()
     with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
