@@ -35,6 +35,39 @@
 
 namespace sb {
 
+// The per-thread walk code is also compiled for the HOST by tests/host_emul (nvcc -DSB_HOST_EMUL, one
+// simulated thread at a time), so the CPU test tier runs the very same DP arithmetic against the oracle.
+// In a device build the macros below expand to exactly the CUDA spellings they stand for.
+#ifdef SB_HOST_EMUL
+struct EmulIdx { int x, y, z; };
+static thread_local EmulIdx threadIdx, blockIdx;        // set by the emulation driver before each call
+static thread_local int *sb_emul_shared = nullptr;      // the block's dynamic shared memory
+#define SB_DEV inline
+#define SB_CONST static
+#define SB_LDG(p) (*(p))
+#define SB_KERNEL(bounds) inline void
+#define SB_SHARED_STACK(name) int *name = sb_emul_shared
+static inline unsigned sb_emul_vadd2(unsigned a, unsigned b)
+{
+    return (((a & 0xFFFFu) + (b & 0xFFFFu)) & 0xFFFFu) | (((a >> 16) + (b >> 16)) << 16);
+}
+static inline unsigned sb_emul_vmaxs2(unsigned a, unsigned b)
+{
+    const short al = (short)(a & 0xFFFFu), bl = (short)(b & 0xFFFFu), ah = (short)(a >> 16), bh = (short)(b >> 16);
+    return (unsigned)(unsigned short)(al > bl ? al : bl) | ((unsigned)(unsigned short)(ah > bh ? ah : bh) << 16);
+}
+#define SB_VADD2(a, b) sb_emul_vadd2(a, b)
+#define SB_VMAXS2(a, b) sb_emul_vmaxs2(a, b)
+#else
+#define SB_DEV __device__ __forceinline__
+#define SB_CONST __constant__
+#define SB_LDG(p) __ldg(p)
+#define SB_KERNEL(bounds) __global__ void bounds
+#define SB_SHARED_STACK(name) extern __shared__ __align__(16) int name[]
+#define SB_VADD2(a, b) __vadd2(a, b)
+#define SB_VMAXS2(a, b) __vmaxs2(a, b)
+#endif
+
 #ifndef SB_WALK_THREADS
 #define SB_WALK_THREADS 128
 #endif
@@ -45,6 +78,7 @@ constexpr int WALK_THREADS = SB_WALK_THREADS;
 constexpr int WALK_NEG = -(1 << 30);   // unreachable; keys stay < 2^28 (n_leaves <= 32766), so inv+inv >= INT_MIN
 constexpr uint32_t SHUFFLE_DOMAIN = 0x5C0A27u;
 
+#ifndef SB_HOST_EMUL   // device-only kernels (packing, shuffling): not part of the host emulation
 // ---------------------------------------------------------------- K1: gather + transpose
 // genes [G][W] uint64 (isolate columns)  ->  genesT [W32p][Gs] uint32 where bit b
 // of word w of gene g = gene g at the leaf consumed at walk position 32 w + b.
@@ -131,6 +165,8 @@ __global__ void __launch_bounds__(64) shuffle_labels_kernel(const uint32_t *__re
     }
 }
 
+#endif  // !SB_HOST_EMUL
+
 // ---------------------------------------------------------------- the DP
 // state index: 0 AB (g=1,t=1), 1 Ab (g=1,t=0), 2 aB (g=0,t=1), 3 ab (g=0,t=0), 4 no free path
 struct WalkState {
@@ -145,8 +181,8 @@ struct WalkState {
 // vector pipes only see the DP arithmetic.
 constexpr int C_OPS_MAX = 12288;           // uint16 ops        (24 KB)
 constexpr int C_LABEL_WORDS = 9728;        // uint32 label words (38 KB)
-__constant__ uint16_t c_ops[C_OPS_MAX];
-__constant__ uint32_t c_labels[C_LABEL_WORDS];
+SB_CONST uint16_t c_ops[C_OPS_MAX];
+SB_CONST uint32_t c_labels[C_LABEL_WORDS];
 
 // op = (count << 4) | type.  "16" ops work on the packed accumulators A16 / B16 (two genes
 // per register, 16-bit keys), legal while the subtree has <= WALK_LIM16 leaves; "32" ops work
@@ -172,7 +208,7 @@ constexpr unsigned NEG16x2 = 0xC000C000u;
 constexpr unsigned K16x2 = 0x00400040u;    // one pair
 constexpr unsigned K16P1x2 = 0x00410041u;  // one pair that also counts as pro (or anti)
 
-__device__ __forceinline__ int max5(const int v[5])
+SB_DEV int max5(const int v[5])
 {
     return __vimax3_s32(__vimax3_s32(v[0], v[1], v[2]), v[3], v[4]);
 }
@@ -194,7 +230,7 @@ struct Bonus16 {     // the same, packed for the two genes of a pair
 // acc <- combine(acc, leaf (g, TB)); the trait bit TB is block-uniform (the caller branches
 // on it once for all genes of the thread), the gene bit is per gene
 template <int TB, bool DUAL>
-__device__ __forceinline__ void walk_leaf(WalkState &s, bool G1, const Bonus32 &b)
+SB_DEV void walk_leaf(WalkState &s, bool G1, const Bonus32 &b)
 {
     const int Mp = max5(s.p);
     if (TB) {  // leaf is AB (g) or aB (!g); its complement is ab (supporting pair) or Ab (opposing pair)
@@ -224,7 +260,7 @@ __device__ __forceinline__ void walk_leaf(WalkState &s, bool G1, const Bonus32 &
     }
 }
 
-__device__ __forceinline__ void merge_pass(const int L[5], const int R[5], int out[5], int bsup, int bopp)
+SB_DEV void merge_pass(const int L[5], const int R[5], int out[5], int bsup, int bopp)
 {
     const int ML = max5(L), MR = max5(R);
 #pragma unroll
@@ -237,7 +273,7 @@ __device__ __forceinline__ void merge_pass(const int L[5], const int R[5], int o
 
 // acc <- combine(L, acc)
 template <bool DUAL>
-__device__ __forceinline__ void walk_merge(const WalkState &L, WalkState &acc, const Bonus32 &b)
+SB_DEV void walk_merge(const WalkState &L, WalkState &acc, const Bonus32 &b)
 {
     WalkState o;
     merge_pass(L.p, acc.p, o.p, b.ps, b.po);
@@ -257,16 +293,16 @@ struct WalkState16 {
     unsigned a[5];
 };
 
-__device__ __forceinline__ unsigned sel2(unsigned m, unsigned x, unsigned y) { return (x & m) | (y & ~m); }
+SB_DEV unsigned sel2(unsigned m, unsigned x, unsigned y) { return (x & m) | (y & ~m); }
 
-__device__ __forceinline__ unsigned max5_16(const unsigned v[5])
+SB_DEV unsigned max5_16(const unsigned v[5])
 {
     return __vimax3_s16x2(__vimax3_s16x2(v[0], v[1], v[2]), v[3], v[4]);
 }
 
 // m1, m2: half-word masks of the two leaves' gene bits; tt = 2*t1 + t2 (block-uniform)
 template <bool DUAL>
-__device__ __forceinline__ void walk_cherry16(WalkState16 &o, unsigned m1, unsigned m2, int tt, const Bonus16 &b)
+SB_DEV void walk_cherry16(WalkState16 &o, unsigned m1, unsigned m2, int tt, const Bonus16 &b)
 {
     const unsigned N = NEG16x2;
     unsigned f0 = N, f1 = N, f2 = N, f3 = N, p4 = N, a4 = N;
@@ -292,16 +328,16 @@ __device__ __forceinline__ void walk_cherry16(WalkState16 &o, unsigned m1, unsig
 }
 
 template <int TB, bool DUAL>
-__device__ __forceinline__ void walk_leaf16(WalkState16 &s, unsigned m, const Bonus16 &b)
+SB_DEV void walk_leaf16(WalkState16 &s, unsigned m, const Bonus16 &b)
 {
     const unsigned Mp = max5_16(s.p);
     if (TB) {
-        const unsigned np4 = sel2(m, __vadd2(s.p[3], b.ps), __vadd2(s.p[1], b.po));
+        const unsigned np4 = sel2(m, SB_VADD2(s.p[3], b.ps), SB_VADD2(s.p[1], b.po));
         s.p[0] = sel2(m, Mp, s.p[0]);
         s.p[2] = sel2(m, s.p[2], Mp);
         s.p[4] = np4;
     } else {
-        const unsigned np4 = sel2(m, __vadd2(s.p[2], b.po), __vadd2(s.p[0], b.ps));
+        const unsigned np4 = sel2(m, SB_VADD2(s.p[2], b.po), SB_VADD2(s.p[0], b.ps));
         s.p[1] = sel2(m, Mp, s.p[1]);
         s.p[3] = sel2(m, s.p[3], Mp);
         s.p[4] = np4;
@@ -309,12 +345,12 @@ __device__ __forceinline__ void walk_leaf16(WalkState16 &s, unsigned m, const Bo
     if constexpr (DUAL) {
         const unsigned Ma = max5_16(s.a);
         if (TB) {
-            const unsigned na4 = sel2(m, __vadd2(s.a[3], b.as_), __vadd2(s.a[1], b.ao));
+            const unsigned na4 = sel2(m, SB_VADD2(s.a[3], b.as_), SB_VADD2(s.a[1], b.ao));
             s.a[0] = sel2(m, Ma, s.a[0]);
             s.a[2] = sel2(m, s.a[2], Ma);
             s.a[4] = na4;
         } else {
-            const unsigned na4 = sel2(m, __vadd2(s.a[2], b.ao), __vadd2(s.a[0], b.as_));
+            const unsigned na4 = sel2(m, SB_VADD2(s.a[2], b.ao), SB_VADD2(s.a[0], b.as_));
             s.a[1] = sel2(m, Ma, s.a[1]);
             s.a[3] = sel2(m, s.a[3], Ma);
             s.a[4] = na4;
@@ -322,21 +358,21 @@ __device__ __forceinline__ void walk_leaf16(WalkState16 &s, unsigned m, const Bo
     }
 }
 
-__device__ __forceinline__ void merge_pass16(const unsigned L[5], const unsigned R[5], unsigned out[5], unsigned bsup,
+SB_DEV void merge_pass16(const unsigned L[5], const unsigned R[5], unsigned out[5], unsigned bsup,
                                              unsigned bopp)
 {
     const unsigned ML = max5_16(L), MR = max5_16(R);
 #pragma unroll
-    for (int c = 0; c < 4; ++c) out[c] = __viaddmax_s16x2(L[c], MR, __vadd2(ML, R[c]));
-    const unsigned nf = __vadd2(L[4], R[4]);
-    const unsigned pp = __vadd2(__viaddmax_s16x2(L[0], R[3], __vadd2(L[3], R[0])), bsup);
-    const unsigned ap = __vadd2(__viaddmax_s16x2(L[1], R[2], __vadd2(L[2], R[1])), bopp);
-    out[4] = __vmaxs2(__vimax3_s16x2(nf, pp, ap), NEG16x2);
+    for (int c = 0; c < 4; ++c) out[c] = __viaddmax_s16x2(L[c], MR, SB_VADD2(ML, R[c]));
+    const unsigned nf = SB_VADD2(L[4], R[4]);
+    const unsigned pp = SB_VADD2(__viaddmax_s16x2(L[0], R[3], SB_VADD2(L[3], R[0])), bsup);
+    const unsigned ap = SB_VADD2(__viaddmax_s16x2(L[1], R[2], SB_VADD2(L[2], R[1])), bopp);
+    out[4] = SB_VMAXS2(__vimax3_s16x2(nf, pp, ap), NEG16x2);
 }
 
 // acc <- combine(L, acc)
 template <bool DUAL>
-__device__ __forceinline__ void walk_merge16(const WalkState16 &L, WalkState16 &acc, const Bonus16 &b)
+SB_DEV void walk_merge16(const WalkState16 &L, WalkState16 &acc, const Bonus16 &b)
 {
     WalkState16 o;
     merge_pass16(L.p, acc.p, o.p, b.ps, b.po);
@@ -350,14 +386,14 @@ __device__ __forceinline__ void walk_merge16(const WalkState16 &L, WalkState16 &
 }
 
 // 16-bit key -> 32-bit key of the same (pairs, x); unreachable stays unreachable
-__device__ __forceinline__ int widen_key(int k16, int scale)   // scale = (1 << SH) - 64
+SB_DEV int widen_key(int k16, int scale)   // scale = (1 << SH) - 64
 {
     const int k32 = k16 + (k16 >> WALK_SH16) * scale;
     return k16 < 0 ? WALK_NEG : k32;
 }
 
 template <bool DUAL>
-__device__ __forceinline__ void walk_widen(const WalkState16 &s, WalkState &g0, WalkState &g1, int scale)
+SB_DEV void walk_widen(const WalkState16 &s, WalkState &g0, WalkState &g1, int scale)
 {
 #pragma unroll
     for (int c = 0; c < 5; ++c) {
@@ -400,7 +436,7 @@ constexpr int WALK_NP = 2 * WALK_NPAIR;     // genes per thread
 // the label bits); per-gene data only feeds selects.  The program always ends in 32-bit mode.
 // Stack entries take EW = 10 (DUAL) or 5 words per gene pair in 16-bit form, twice that in 32-bit form.
 template <int NPAIR, bool DUAL>
-__device__ __forceinline__ void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR], int lab_off,
+SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR], int lab_off,
                                           int *stk, WalkState (&acc)[2 * NPAIR], const Bonus32 (&b32)[2 * NPAIR],
                                           const Bonus16 (&b16c)[NPAIR])
 {
@@ -415,7 +451,7 @@ __device__ __forceinline__ void walk_tree(const WalkArgs &A, const uint32_t *con
     // bits 16..31, consumed from bit 0 / bit 16); gy[q]: the following 16 leaves; gnext: prefetch
     uint32_t gx[NPAIR], gy[NPAIR], gnext[NP], lw = 0;
 #pragma unroll
-    for (int k = 0; k < NP; ++k) gnext[k] = __ldg(gcol[k]);
+    for (int k = 0; k < NP; ++k) gnext[k] = SB_LDG(gcol[k]);
 #pragma unroll
     for (int q = 0; q < NPAIR; ++q) { gx[q] = 0; gy[q] = 0; }
     const int W32p = A.W32p;
@@ -434,7 +470,7 @@ __device__ __forceinline__ void walk_tree(const WalkArgs &A, const uint32_t *con
                 }                                                                              \
                 if (w_ + 1 < W32p) {                                                           \
                     _Pragma("unroll") for (int k_ = 0; k_ < NP; ++k_)                          \
-                        gnext[k_] = __ldg(gcol[k_] + (int64_t)(w_ + 1) * Gs);                  \
+                        gnext[k_] = SB_LDG(gcol[k_] + (int64_t)(w_ + 1) * Gs);                \
                 }                                                                              \
             } else {                                                                           \
                 _Pragma("unroll") for (int q_ = 0; q_ < NPAIR; ++q_) gx[q_] = gy[q_];          \
@@ -619,7 +655,7 @@ __device__ __forceinline__ void walk_tree(const WalkArgs &A, const uint32_t *con
 
 // gene slots of this thread: (tile * NP + k) * T + tid  (coalesced per k)
 template <int NP>
-__device__ __forceinline__ void walk_slots(const WalkArgs &A, int tile, int64_t (&s_idx)[NP], bool (&active)[NP],
+SB_DEV void walk_slots(const WalkArgs &A, int tile, int64_t (&s_idx)[NP], bool (&active)[NP],
                                            int64_t (&sc)[NP], const uint32_t *(&gcol)[NP])
 {
 #pragma unroll
@@ -636,9 +672,9 @@ __device__ __forceinline__ void walk_slots(const WalkArgs &A, int tile, int64_t 
 
 // K4: one labelling (c_labels row 0), both passes; writes pairs[S][3] = Total, Pro, Anti.
 // The root takes three independent maxima (classes.py:246-249).
-__global__ void __launch_bounds__(WALK_THREADS) walk_pairs_kernel(const WalkArgs A)
+SB_KERNEL(__launch_bounds__(WALK_THREADS)) walk_pairs_kernel(const WalkArgs A)
 {
-    extern __shared__ __align__(16) int smem_stack[];
+    SB_SHARED_STACK(smem_stack);
     int *stk = smem_stack + threadIdx.x;
     constexpr int NP = WALK_NP;
     int64_t s_idx[NP], sc[NP]; bool active[NP]; const uint32_t *gcol[NP];
@@ -675,9 +711,9 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_pairs_kernel(const WalkArgs
 // and writes one byte of hit flags per gene.  Blocks are small work items, so the tail of a
 // launch is short, and concurrently running blocks read the same few label vectors from the
 // constant cache.
-__global__ void __launch_bounds__(WALK_THREADS, SB_WALK_MINBLOCKS) walk_permute_kernel(const WalkArgs A)
+SB_KERNEL(__launch_bounds__(WALK_THREADS, SB_WALK_MINBLOCKS)) walk_permute_kernel(const WalkArgs A)
 {
-    extern __shared__ __align__(16) int smem_stack[];
+    SB_SHARED_STACK(smem_stack);
     int *stk = smem_stack + threadIdx.x;
     constexpr int NP = WALK_NP;
     const int chunk = blockIdx.y;
@@ -724,6 +760,7 @@ __global__ void __launch_bounds__(WALK_THREADS, SB_WALK_MINBLOCKS) walk_permute_
         if (active[k]) A.hits[(int64_t)(A.chunk_base + chunk) * A.S_total + s_idx[k]] = (uint8_t)hits[k];
 }
 
+#ifndef SB_HOST_EMUL   // device-only kernels below
 // ---------------------------------------------------------------- hit-sequence reduction
 // Permute's bookkeeping (methods.py:1348-1365) on the ordered hit flags.
 __global__ void __launch_bounds__(256) reduce_hits_kernel(const uint8_t *__restrict__ hits, int64_t S, int n_chunks,
@@ -827,7 +864,7 @@ __global__ void __launch_bounds__(256) pipe_rate_kernel(int *out, int iters, int
                 if (MODE == 0) x[k] = __viaddmax_s32((int)x[k], (int)a, (int)(b + k));
                 if (MODE == 1) x[k] = __viaddmax_s16x2(x[k], a, b + k);
                 if (MODE == 2) x[k] = __vimax3_s16x2(x[k], a + k, b);
-                if (MODE == 3) x[k] = __vadd2(x[k], a + k);
+                if (MODE == 3) x[k] = SB_VADD2(x[k], a + k);
                 if (MODE == 4) x[k] = (x[k] & a) | (b & ~a) ^ (x[k] >> 1);          // LOP3 + SHF
                 if (MODE == 5) x[k] = __vimax3_s32((int)x[k], (int)(a + k), (int)b);
                 if (MODE == 6) x[k] = (int)x[k] > (int)a ? x[k] + k : b;             // ISETP + SEL(+add)
@@ -840,5 +877,7 @@ __global__ void __launch_bounds__(256) pipe_rate_kernel(int *out, int iters, int
     for (int k = 0; k < 8; ++k) s ^= x[k];
     if (s == 0x7fffffffu) out[0] = (int)s;
 }
+
+#endif  // !SB_HOST_EMUL
 
 }  // namespace sb

@@ -1,0 +1,91 @@
+// TEST INFRASTRUCTURE: the walk kernels of scoary_b200/csrc/walk.cuh compiled for the HOST.
+//
+// walk.cuh is included with SB_HOST_EMUL: __device__ functions become plain inline functions, the
+// __constant__ program / label arrays become host arrays, threadIdx / blockIdx become variables this
+// driver sets, and the two kernels (walk_pairs_kernel, walk_permute_kernel) become functions that are
+// called once per simulated thread.  Threads of a block only share the layout of the DP stack
+// ([slot][field][thread]), never data, so running them one after the other is exact.  The DPX
+// intrinsics (__viaddmax_s32, __vimax3_s16x2, ...) have host implementations in the CUDA headers;
+// __vadd2 / __vmaxs2 do not and are spelled out in walk.cuh's emulation block.
+//
+// Built by tests/test_host_emul.py with `nvcc -DSB_HOST_EMUL -shared` (no device code is generated
+// for these functions); nothing here is product code.
+#define SB_HOST_EMUL 1
+#include <stdint.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../scoary_b200/csrc/walk.cuh"
+
+namespace {
+
+void fill(sb::WalkArgs &A, const uint32_t *genesT, int64_t Gs, int64_t S, int W32p, int shift)
+{
+    memset(&A, 0, sizeof A);
+    A.genesT = genesT; A.Gs = Gs; A.gene_idx = nullptr; A.slot_idx = nullptr; A.S = S; A.S_total = S;
+    A.W32p = W32p; A.shift = shift;
+}
+
+int load_program(const uint16_t *ops, int n_ops)
+{
+    if (n_ops > sb::C_OPS_MAX) return -1;
+    memcpy(sb::c_ops, ops, sizeof(uint16_t) * (size_t)n_ops);
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int emul_walk_threads(void) { return sb::WALK_THREADS; }
+int emul_walk_genes_per_thread(void) { return sb::WALK_NP; }
+
+// K4: pairs[S][3] for the labelling `labels` (walk order, W32p words)
+int emul_pairs(const uint16_t *ops, int n_ops, const uint32_t *labels, const uint32_t *genesT, int64_t Gs, int64_t S,
+               int W32p, int shift, int stack_units, int32_t *pairs)
+{
+    if (load_program(ops, n_ops) || W32p > sb::C_LABEL_WORDS) return -1;
+    memcpy(sb::c_labels, labels, sizeof(uint32_t) * (size_t)W32p);
+    sb::WalkArgs A;
+    fill(A, genesT, Gs, S, W32p, shift);
+    A.pairs = pairs;
+    const int T = sb::WALK_THREADS;
+    std::vector<int> smem((size_t)10 * (stack_units > 0 ? stack_units : 1) * T * sb::WALK_NPAIR);
+    const int64_t per_block = (int64_t)T * sb::WALK_NP;
+    for (int64_t tile = 0; tile < (S + per_block - 1) / per_block; ++tile)
+        for (int tid = 0; tid < T; ++tid) {
+            sb::blockIdx = {(int)tile, 0, 0};
+            sb::threadIdx = {tid, 0, 0};
+            sb::sb_emul_shared = smem.data();
+            sb::walk_pairs_kernel(A);
+        }
+    return 0;
+}
+
+// K5: hits[ceil(P / ppi)][S] for the labellings labelsW[P][W32p] (walk order)
+int emul_permute(const uint16_t *ops, int n_ops, const uint32_t *labelsW, int P, int ppi, const uint32_t *genesT,
+                 int64_t Gs, int64_t S, int W32p, int shift, int stack_units, const int32_t *unperm, uint8_t *hits)
+{
+    if (load_program(ops, n_ops) || (int64_t)P * W32p > sb::C_LABEL_WORDS || ppi < 1 || ppi > sb::PERMS_PER_ITEM_MAX)
+        return -1;
+    memcpy(sb::c_labels, labelsW, sizeof(uint32_t) * (size_t)P * W32p);
+    sb::WalkArgs A;
+    fill(A, genesT, Gs, S, W32p, shift);
+    A.n_perms = P; A.ppi = ppi; A.items_per_tile = (P + ppi - 1) / ppi; A.chunk_base = 0;
+    A.unperm = unperm; A.hits = hits;
+    const int T = sb::WALK_THREADS;
+    std::vector<int> smem((size_t)5 * (stack_units > 0 ? stack_units : 1) * T * sb::WALK_NPAIR);
+    const int64_t per_block = (int64_t)T * sb::WALK_NP;
+    for (int64_t tile = 0; tile < (S + per_block - 1) / per_block; ++tile)
+        for (int chunk = 0; chunk < A.items_per_tile; ++chunk)
+            for (int tid = 0; tid < T; ++tid) {
+                sb::blockIdx = {(int)tile, chunk, 0};
+                sb::threadIdx = {tid, 0, 0};
+                sb::sb_emul_shared = smem.data();
+                sb::walk_permute_kernel(A);
+            }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,120 @@
+"""The CUDA walk kernels' own source (scoary_b200/csrc/walk.cuh), compiled for the HOST by
+tests/host_emul/walk_emul.cu and run one simulated thread at a time, against the oracle: the CPU tier
+then covers the real DP arithmetic (packed 16-bit mode, widening, fused ops, per-gene bonuses, the hit
+test), not only a Python model of it.  Needs nvcc (cross-compiles without a GPU); skipped without it."""
+import ctypes
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from scoary_b200 import synth
+from scoary_b200 import tree as treemod
+from test_tree_program import compile_tree
+
+HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_emul")
+SRC = os.path.join(HERE, "walk_emul.cu")
+LIB = os.path.join(HERE, "libwalk_emul.so")
+CSRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scoary_b200", "csrc")
+
+
+@pytest.fixture(scope="module")
+def emul():
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    deps = [SRC, os.path.join(CSRC, "walk.cuh"), os.path.join(CSRC, "common.cuh")]
+    if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(d) for d in deps):
+        cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "-Xcompiler", "-fPIC",
+                        "-ccbin", cxx, "-shared", "-o", LIB, SRC], check=True)
+    lib = ctypes.CDLL(LIB)
+    lib.emul_pairs.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                               ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    lib.emul_permute.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                 ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                 ctypes.c_void_p, ctypes.c_void_p]
+    return lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _pack_walk_order(bits_by_leaf, order, W32p):
+    """uint8 [R][n_leaves] (leaf-id order) -> uint32 [R][W32p], bit b of word w = the leaf consumed at position 32w+b"""
+    walk = np.zeros((bits_by_leaf.shape[0], W32p * 32), dtype=np.uint8)
+    walk[:, :len(order)] = bits_by_leaf[:, order]
+    return np.ascontiguousarray(np.packbits(walk, axis=1, bitorder="little")).view(np.uint32).reshape(-1, W32p)
+
+
+def _setup(n, G, seed, comb=False):
+    rng = np.random.default_rng(seed)
+    names = synth.isolate_names(n)
+    if comb:
+        nested = names[0]
+        for nm in names[1:]:
+            nested = [nested, nm]
+    else:
+        nested = synth.make_tree(n, seed)
+    ops, order, units, leaves = compile_tree(nested)
+    left, right, _ = treemod.flatten(nested)
+    f = rng.uniform(0.02, 0.98, size=G)
+    m = (rng.random((G, n)) < f[:, None]).astype(np.uint8)
+    lab = (rng.random(n) < 0.4).astype(np.uint8)
+    m[0] = lab                                            # a perfectly associated gene
+    if G > 1:
+        m[1] = 1 - lab
+    W32 = (n + 31) // 32
+    W32p = (W32 + 3) // 4 * 4
+    shift = 1
+    while (1 << shift) <= n // 2:
+        shift += 1
+    Gs = (G + 31) // 32 * 32
+    gw = _pack_walk_order(m, order, W32p)                 # [G][W32p]
+    genesT = np.zeros((W32p, Gs), dtype=np.uint32)
+    genesT[:, :G] = gw.T
+    return dict(ops=np.ascontiguousarray(ops), order=order, units=units, left=left, right=right, m=m, lab=lab,
+                W32p=W32p, shift=shift, Gs=Gs, genesT=np.ascontiguousarray(genesT), G=G, n=n)
+
+
+CASES = [(2, 5, False), (3, 9, False), (5, 40, False), (16, 70, False), (100, 130, False), (127, 33, False),
+         (128, 33, False), (129, 600, False), (300, 70, False), (1000, 20, False), (400, 12, True), (150, 520, True)]
+
+
+@pytest.mark.parametrize("n,G,comb", CASES)
+def test_pairs_kernel_source_on_the_host(emul, n, G, comb):
+    c = _setup(n, G, 100 + n, comb)
+    lab0 = _pack_walk_order(c["lab"][None, :], c["order"], c["W32p"])[0]
+    pairs = np.full((G, 3), -7, dtype=np.int32)
+    rc = emul.emul_pairs(_ptr(c["ops"]), len(c["ops"]), _ptr(lab0), _ptr(c["genesT"]), c["Gs"], G, c["W32p"], c["shift"],
+                         c["units"], _ptr(pairs))
+    assert rc == 0
+    ref = O.permute(c["left"], c["right"], c["m"], c["lab"], P=0)["pairs"]
+    assert np.array_equal(pairs, ref)
+
+
+@pytest.mark.parametrize("n,G,comb", CASES)
+@pytest.mark.parametrize("ppi", [1, 2, 4])
+def test_permute_kernel_source_on_the_host(emul, n, G, comb, ppi):
+    if ppi != 4 and n > 200:
+        pytest.skip("one ppi is enough for the large trees")
+    c = _setup(n, G, 200 + n, comb)
+    P, seed = 9, 77
+    ref = O.permute(c["left"], c["right"], c["m"], c["lab"], P=P, seed=seed, trait=0, want_hits=True)
+    labs = np.stack([O.shuffle_labels(seed, 0, p, c["lab"]) for p in range(P)])
+    labelsW = np.ascontiguousarray(_pack_walk_order(labs, c["order"], c["W32p"]))
+    n_chunks = (P + ppi - 1) // ppi
+    hits = np.zeros((n_chunks, G), dtype=np.uint8)
+    unperm = np.ascontiguousarray(ref["pairs"], dtype=np.int32)
+    rc = emul.emul_permute(_ptr(c["ops"]), len(c["ops"]), _ptr(labelsW), P, ppi, _ptr(c["genesT"]), c["Gs"], G, c["W32p"],
+                           c["shift"], c["units"], _ptr(unperm), _ptr(hits))
+    assert rc == 0
+    got = np.zeros((G, P), dtype=np.uint8)
+    for p in range(P):
+        got[:, p] = (hits[p // ppi] >> (p % ppi)) & 1
+    assert np.array_equal(got, ref["hits"])
+    assert np.array_equal(got.sum(axis=1), ref["r"])
