@@ -82,7 +82,8 @@ def _setup(n, G, seed, comb=False):
 
 
 CASES = [(2, 5, False), (3, 9, False), (5, 40, False), (16, 70, False), (100, 130, False), (127, 33, False),
-         (128, 33, False), (129, 600, False), (300, 70, False), (1000, 20, False), (400, 12, True), (150, 520, True)]
+         (128, 33, False), (129, 600, False), (300, 70, False), (1000, 20, False), (400, 12, True), (150, 520, True),
+         (5000, 40, False), (10000, 6, False), (20000, 5, True)]      # C3 / C4 isolate counts, a 19 999-level comb
 
 
 @pytest.mark.parametrize("n,G,comb", CASES)
