@@ -6,7 +6,6 @@ import gzip
 import os
 import shutil
 
-import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
