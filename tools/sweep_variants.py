@@ -1,0 +1,76 @@
+#!/usr/bin/env python
+"""Build and time kernel variants side by side (one `gpurun` call for a whole sweep).
+
+  python tools/sweep_variants.py build      # here (no GPU): nvcc builds variants/<name>.so for every entry of VARIANTS
+  python tools/sweep_variants.py run        # on the GPU box: times K5 / Fisher for each library on the C3 shape and
+                                            # checks that pair counts, hit counts and Fisher p equal the product library's
+
+The product library is variant "base".  Variants differ only in -D switches the kernels already honour
+(threads per block, genes per thread, resident blocks, Fisher block size); results must be identical."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+VDIR = os.path.join(ROOT, "variants")
+VARIANTS = {
+    "minblocks4": "-DSB_WALK_MINBLOCKS=4",
+    "minblocks6": "-DSB_WALK_MINBLOCKS=6",
+    "threads96_mb6": "-DSB_WALK_THREADS=96 -DSB_WALK_MINBLOCKS=6",
+    "threads64_mb10": "-DSB_WALK_THREADS=64 -DSB_WALK_MINBLOCKS=10",
+    "threads256_mb2": "-DSB_WALK_THREADS=256 -DSB_WALK_MINBLOCKS=2",
+    "npair1_mb8": "-DSB_WALK_NPAIR=1 -DSB_WALK_MINBLOCKS=8",
+    "npair3_mb3": "-DSB_WALK_NPAIR=3 -DSB_WALK_MINBLOCKS=3",
+    "fisher512": "-DSB_FISHER_THREADS=512",
+    "fisher256": "-DSB_FISHER_THREADS=256",
+}
+
+
+def build():
+    os.makedirs(VDIR, exist_ok=True)
+    for name, flags in VARIANTS.items():
+        out = os.path.join(VDIR, name + ".so")
+        subprocess.run(["make", "-B", "-C", os.path.join(ROOT, "scoary_b200", "csrc"), "OUT=" + out, "EXTRA=" + flags],
+                       check=True, stdout=subprocess.DEVNULL)
+        print("built", out)
+
+
+CHILD = r'''
+import json, sys, os, zlib
+sys.path.insert(0, %(root)r)
+import numpy as np
+from scoary_b200 import synth
+from scoary_b200.engine import Engine
+G, N, P, seed = 50000, 5000, 240, 20260903
+traits = synth.make_traits(N, 1, seed); bits = synth.make_genes_packed(G, N, seed, traits=traits)
+col = {n: j for j, n in enumerate(synth.isolate_names(N))}
+e = Engine(0); e.set_profiling(True); e.set_genes(bits, N); e.set_trait_vector(0, traits[0]); e.set_tree_nested(0, synth.make_tree(N, seed), col)
+best = {}
+for rep in range(3):
+    e.stats_reset(); c, p, _ = e.contingency_fisher(0); pairs, r, nd = e.permute(0, P, seed=1); st = e.stats()
+    for k in ("ms_fisher", "ms_permute", "ms_walk"): best[k] = min(best.get(k, 1e30), st[k])
+crc = zlib.crc32(pairs.tobytes() + r.tobytes() + c.tobytes() + p.tobytes())
+print(json.dumps({"walks_per_s": G * P / (best["ms_permute"] * 1e-3), "crc": crc, **best}))
+'''
+
+
+def run():
+    libs = [("base", os.path.join(ROOT, "scoary_b200", "libscoary_b200.so"))]
+    libs += [(n, os.path.join(VDIR, n + ".so")) for n in VARIANTS if os.path.exists(os.path.join(VDIR, n + ".so"))]
+    base = None
+    for name, path in libs:
+        env = dict(os.environ, SCOARY_B200_LIB=path)
+        res = subprocess.run([sys.executable, "-c", CHILD % {"root": ROOT}], env=env, capture_output=True, text=True)
+        if res.returncode != 0:
+            print("%-16s FAILED: %s" % (name, res.stderr.strip().splitlines()[-1] if res.stderr.strip() else "?"))
+            continue
+        d = json.loads(res.stdout.strip().splitlines()[-1])
+        base = base or d
+        print("%-16s K5 %.3e walks/s (%.2fx)  fisher %.3f ms  results %s" % (
+            name, d["walks_per_s"], d["walks_per_s"] / base["walks_per_s"], d["ms_fisher"],
+            "identical" if d["crc"] == base["crc"] else "DIFFER"))
+
+
+if __name__ == "__main__":
+    {"build": build, "run": run}[sys.argv[1] if len(sys.argv) > 1 else "build"]()
