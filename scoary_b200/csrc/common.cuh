@@ -5,8 +5,18 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// Host emulation (tests/host_emul, nvcc -DSB_HOST_EMUL): the arithmetic helpers and the kernels' per-thread /
+// per-warp functions are also compiled as plain host functions so the CPU test tier can run the same source
+// against the oracle.  In a device build SB_DEV is exactly `__device__ __forceinline__`.
+#ifdef SB_HOST_EMUL
+#define SB_DEV inline
+#else
+#define SB_DEV __device__ __forceinline__
+#endif
+
 namespace sb {
 
+#ifndef SB_HOST_EMUL   // device-only: mbarrier / TMA bulk copies, Philox (the oracle has the host Philox)
 // ---------------------------------------------------------------- mbarrier / TMA bulk
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
@@ -76,14 +86,16 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
+#endif  // !SB_HOST_EMUL
+
 // ---------------------------------------------------------------- double-double
 struct dd {
     double hi, lo;
 };
 
-__device__ __forceinline__ dd dd_make(double2 v) { return dd{v.x, v.y}; }
+SB_DEV dd dd_make(double2 v) { return dd{v.x, v.y}; }
 
-__device__ __forceinline__ dd dd_add(dd x, dd y)
+SB_DEV dd dd_add(dd x, dd y)
 {
     double s = x.hi + y.hi;
     double bb = s - x.hi;
@@ -94,10 +106,10 @@ __device__ __forceinline__ dd dd_add(dd x, dd y)
     return dd{hi, lo};
 }
 
-__device__ __forceinline__ dd dd_neg(dd x) { return dd{-x.hi, -x.lo}; }
-__device__ __forceinline__ dd dd_sub(dd x, dd y) { return dd_add(x, dd_neg(y)); }
+SB_DEV dd dd_neg(dd x) { return dd{-x.hi, -x.lo}; }
+SB_DEV dd dd_sub(dd x, dd y) { return dd_add(x, dd_neg(y)); }
 
-__device__ __forceinline__ uint64_t mix64(uint64_t z)
+SB_DEV uint64_t mix64(uint64_t z)
 {
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;

@@ -16,6 +16,24 @@
 #pragma once
 #include "common.cuh"
 
+// Warp collectives and rounding intrinsics of the Fisher code: CUDA spellings in a device build, the emulation
+// driver's versions (32 host threads in lockstep) under SB_HOST_EMUL.
+#ifdef SB_HOST_EMUL
+#define SB_SHFL_XOR(v, o) sb_emul_shfl_xor(v, o)
+#define SB_SHFL(v, src) sb_emul_shfl(v, src)
+#define SB_BALLOT(pred) sb_emul_ballot(pred)
+#define SB_FFS(x) __builtin_ffs((int)(x))
+#define SB_DMUL(a, b) sb_emul_mul(a, b)
+#define SB_DDIV(a, b) sb_emul_div(a, b)
+#else
+#define SB_SHFL_XOR(v, o) __shfl_xor_sync(0xffffffffu, v, o)
+#define SB_SHFL(v, src) __shfl_sync(0xffffffffu, v, src)
+#define SB_BALLOT(pred) __ballot_sync(0xffffffffu, pred)
+#define SB_FFS(x) __ffs(x)
+#define SB_DMUL(a, b) __dmul_rn(a, b)
+#define SB_DDIV(a, b) __ddiv_rn(a, b)
+#endif
+
 namespace sb {
 
 #ifndef SB_FISHER_THREADS
@@ -39,7 +57,7 @@ struct FisherArgs {
 };
 
 // S(x) = lf[x] + lf[n1-x] + lf[n-x] + lf[n2-n+x]  (the x-dependent part of -log pmf)
-__device__ __forceinline__ dd fisher_S(const double2 *lut, int x, int n1, int n2, int n)
+SB_DEV dd fisher_S(const double2 *lut, int x, int n1, int n2, int n)
 {
     dd s = dd_make(lut[x]);
     s = dd_add(s, dd_make(lut[n1 - x]));
@@ -48,10 +66,10 @@ __device__ __forceinline__ dd fisher_S(const double2 *lut, int x, int n1, int n2
     return s;
 }
 
-__device__ __forceinline__ double warp_sum(double v)
+SB_DEV double warp_sum(double v)
 {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    for (int o = 16; o > 0; o >>= 1) v += SB_SHFL_XOR(v, o);
     return v;
 }
 
@@ -63,7 +81,7 @@ __device__ __forceinline__ double warp_sum(double v)
 // starts below 2^-80 pmf(a).
 constexpr int FISHER_BLOCK = 8;
 
-__device__ __forceinline__ double fisher_tail(const double2 *lut, int x0, int dir, int count, int n1, int n2,
+SB_DEV double fisher_tail(const double2 *lut, int x0, int dir, int count, int n1, int n2,
                                               int n, dd logp_a, dd S_a, double pexact, int lane)
 {
     double acc = 0.0;
@@ -83,21 +101,21 @@ __device__ __forceinline__ double fisher_tail(const double2 *lut, int x0, int di
 #pragma unroll
             for (int j = 1; j < FISHER_BLOCK; ++j) {
                 if (kb + j < count) {
-                    tt = __dmul_rn(tt, __ddiv_rn(__dmul_rn(A, B), __dmul_rn(C, D)));
+                    tt = SB_DMUL(tt, SB_DDIV(SB_DMUL(A, B), SB_DMUL(C, D)));
                     s += tt;
                     A -= 1.0; B -= 1.0; C += 1.0; D += 1.0;
                 }
             }
             acc += s;
         }
-        const double first = __shfl_sync(0xffffffffu, t, 0);
+        const double first = SB_SHFL(t, 0);
         if (first < cut) break;
     }
     return warp_sum(acc);
 }
 
 // Warp-cooperative two-sided Fisher exact p for [[a, b], [c, d]].
-__device__ __forceinline__ double fisher_two_sided_warp(const double2 *lut, int a, int b, int c, int d, int lane)
+SB_DEV double fisher_two_sided_warp(const double2 *lut, int a, int b, int c, int d, int lane)
 {
     if (a + b == 0 || c + d == 0 || a + c == 0 || b + d == 0) return 1.0;
     // The p-value is invariant under swapping rows, swapping columns and transposing.  Put
@@ -147,11 +165,11 @@ __device__ __forceinline__ double fisher_two_sided_warp(const double2 *lut, int 
             dd dk = dd_sub(S_a, fisher_S(lut, mode + dir2 * k, n1, n2, n));
             pred = (dk.hi + dk.lo) <= FISHER_TIE_TOL;
         }
-        const unsigned ball = __ballot_sync(0xffffffffu, pred);
+        const unsigned ball = SB_BALLOT(pred);
         if (ball == 0u) {
             lo_k = lo_k + ((len - 1) / stride) * stride + 1;
         } else {
-            const int f = __ffs(ball) - 1;
+            const int f = SB_FFS(ball) - 1;
             hi_k = lo_k + f * stride;
             lo_k = (f == 0) ? hi_k : (lo_k + (f - 1) * stride + 1);
         }
@@ -162,6 +180,7 @@ __device__ __forceinline__ double fisher_two_sided_warp(const double2 *lut, int 
     return fmin(p, 1.0);
 }
 
+#ifndef SB_HOST_EMUL   // the kernel itself (TMA pipeline, popcounts) is device-only
 template <bool LUT_SMEM, bool HASH>
 __global__ void __launch_bounds__(FISHER_THREADS) fisher_kernel(const FisherArgs A)
 {
@@ -281,5 +300,7 @@ __global__ void __launch_bounds__(FISHER_THREADS) fisher_kernel(const FisherArgs
         }
     }
 }
+
+#endif  // !SB_HOST_EMUL
 
 }  // namespace sb

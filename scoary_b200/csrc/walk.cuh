@@ -42,7 +42,6 @@ namespace sb {
 struct EmulIdx { int x, y, z; };
 static thread_local EmulIdx threadIdx, blockIdx;        // set by the emulation driver before each call
 static thread_local int *sb_emul_shared = nullptr;      // the block's dynamic shared memory
-#define SB_DEV inline
 #define SB_CONST static
 #define SB_LDG(p) (*(p))
 #define SB_KERNEL(bounds) inline void
@@ -59,7 +58,6 @@ static inline unsigned sb_emul_vmaxs2(unsigned a, unsigned b)
 #define SB_VADD2(a, b) sb_emul_vadd2(a, b)
 #define SB_VMAXS2(a, b) sb_emul_vmaxs2(a, b)
 #else
-#define SB_DEV __device__ __forceinline__
 #define SB_CONST __constant__
 #define SB_LDG(p) __ldg(p)
 #define SB_KERNEL(bounds) __global__ void bounds

@@ -119,3 +119,73 @@ def test_permute_kernel_source_on_the_host(emul, n, G, comb, ppi):
         got[:, p] = (hits[p // ppi] >> (p % ppi)) & 1
     assert np.array_equal(got, ref["hits"])
     assert np.array_equal(got.sum(axis=1), ref["r"])
+
+
+# ---------------------------------------------------------------------------- Fisher (csrc/fisher.cuh) on the host
+FLIB = os.path.join(HERE, "libfisher_emul.so")
+FSRC = os.path.join(HERE, "fisher_emul.cu")
+FISHER_RTOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def femul():
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    deps = [FSRC, os.path.join(CSRC, "fisher.cuh"), os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "lut.cpp")]
+    if not os.path.exists(FLIB) or os.path.getmtime(FLIB) < max(os.path.getmtime(d) for d in deps):
+        cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "-Xcompiler",
+                        "-fPIC,-ffp-contract=off", "-ccbin", cxx, "-shared", "-o", FLIB, FSRC,
+                        os.path.join(CSRC, "lut.cpp"), "-lquadmath", "-lpthread"], check=True)
+    lib = ctypes.CDLL(FLIB)
+    lib.emul_fisher.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
+
+    def run(tables):
+        """tables int [n][4] in the oracle's / C-ABI's order (tpgp, tngp, tpgn, tngn) -> p [n]"""
+        t = np.ascontiguousarray(np.asarray(tables, dtype=np.int32)[:, [0, 2, 1, 3]])     # kernel order a, b, c, d
+        p = np.zeros(len(t), dtype=np.float64)
+        assert lib.emul_fisher(_ptr(t), len(t), _ptr(p)) == 0
+        return p
+    return run
+
+
+def test_fisher_source_on_the_host_matches_scipy_goldens(femul):
+    """The 600 SciPy tables the oracle is pinned on (tests/golden/fisher.json), through the kernel's own
+    warp-cooperative code: same tolerance as the GPU parity tests (1e-10 relative)."""
+    import json
+    gold = json.load(open(os.path.join(os.path.dirname(HERE), "golden", "fisher.json")))["tables"]
+    tabs = np.array([[g["tpgp"], g["tngp"], g["tpgn"], g["tngn"]] for g in gold], dtype=np.int32)
+    want = np.array([float.fromhex(g["p"]) for g in gold])
+    got = femul(tabs)
+    ok = want > 1e-290
+    assert np.max(np.abs(got[ok] - want[ok]) / want[ok]) <= FISHER_RTOL
+    assert np.all(got[~ok] <= 2e-290)
+
+
+def test_fisher_source_on_the_host_large_tables_and_symmetry(femul):
+    """N up to 20 000 against the oracle (binary128), and the canonical orientation: the eight symmetric
+    variants of a table (row swap, column swap, transpose) must give bit-identical p."""
+    rng = np.random.default_rng(5)
+    tabs = []
+    for N in (40, 1000, 5000, 10000, 20000):
+        for _ in range(40):
+            r1, c1 = int(rng.integers(1, N)), int(rng.integers(1, N))
+            if rng.random() < 0.3:
+                r1 = N // 2
+            lo, hi = max(0, r1 + c1 - N), min(r1, c1)
+            sd = max(r1 * c1 / N * (1 - r1 / N) * (1 - c1 / N), 1.0) ** 0.5
+            a = int(np.clip(round(r1 * c1 / N + rng.normal() * 3 * sd), lo, hi))
+            tabs.append([a, c1 - a, r1 - a, N - r1 - c1 + a])          # tpgp, tngp, tpgn, tngn
+    tabs = np.array(tabs, dtype=np.int32)
+    got = femul(tabs)
+    want = O.fisher(tabs)
+    ok = want > 1e-290
+    assert np.max(np.abs(got[ok] - want[ok]) / want[ok]) <= FISHER_RTOL
+    variants = []
+    for a, c, b, d in tabs[:60]:                                      # [[a, b], [c, d]]
+        for (w, x, y, z) in ((a, b, c, d), (c, d, a, b), (b, a, d, c), (d, c, b, a), (a, c, b, d), (b, d, a, c),
+                             (c, a, d, b), (d, b, c, a)):
+            variants.append([w, y, x, z])                             # back to tpgp, tngp, tpgn, tngn
+    pv = femul(np.array(variants, dtype=np.int32)).reshape(-1, 8)
+    assert np.all(pv.view(np.uint64) == pv.view(np.uint64)[:, :1])
