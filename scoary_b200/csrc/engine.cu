@@ -21,6 +21,12 @@
 
 #include "../../include/scoary_b200.h"
 #include "fisher.cuh"
+#ifndef SB_FISHER_V2
+#define SB_FISHER_V2 0   // 1: the experimental four-genes-per-warp kernel of fisher2.cuh (not measured yet)
+#endif
+#if SB_FISHER_V2
+#include "fisher2.cuh"
+#endif
 #include "walk.cuh"
 #include "tree_build.cuh"
 
@@ -470,28 +476,40 @@ int launch_fisher(sb_ctx *ctx, int32_t t, int32_t *d_counts, double *d_p, uint64
     A.counts = d_counts; A.p = d_p; A.hash = d_hash;
     const size_t row_bytes = (size_t)ctx->W * 8;
     const size_t lut_bytes = sizeof(double2) * (size_t)(ctx->lut_n + 1);
-    constexpr size_t NW = sb::FISHER_THREADS / 32;
-    // [2 mbarriers per warp][value&mask, mask][2 row buffers per warp][LUT if it fits]
-    const size_t fixed = 16 * NW + 2 * row_bytes + 2 * NW * row_bytes;
+#if SB_FISHER_V2
+    constexpr size_t NW = sb::FISHER2_THREADS / 32, ROWS_PER_WARP = sb::F2_GENES;
+    constexpr int FTHREADS = sb::FISHER2_THREADS;
+#else
+    constexpr size_t NW = sb::FISHER_THREADS / 32, ROWS_PER_WARP = 1;
+    constexpr int FTHREADS = sb::FISHER_THREADS;
+#endif
+    // [2 mbarriers per warp][value&mask, mask][2 row buffers (of ROWS_PER_WARP rows) per warp][LUT if it fits]
+    const size_t fixed = 16 * NW + 2 * row_bytes + 2 * NW * ROWS_PER_WARP * row_bytes;
     const size_t budget = (size_t)ctx->max_smem_optin;
     if (fixed > budget) return fail(ctx, SB_ERR_ARG, "row too long for shared memory");
     const bool lut_smem = fixed + lut_bytes <= budget;
     const size_t smem = fixed + (lut_smem ? lut_bytes : 0);
-    const int64_t rows_per_cta = (int64_t)NW;
+    const int64_t rows_per_cta = (int64_t)(NW * ROWS_PER_WARP);
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((ctx->G + rows_per_cta - 1) / rows_per_cta, ctx->sm_count));
     const bool hash = d_hash != nullptr;
     Timed tm(ctx, CAT_FISHER);
+#if SB_FISHER_V2
+#define SB_FISHER_KERNEL sb::fisher2_kernel
+#else
+#define SB_FISHER_KERNEL sb::fisher_kernel
+#endif
 #define SB_LAUNCH_FISHER(L, H)                                                                                     \
     do {                                                                                                           \
-        SB_CUDA(ctx, cudaFuncSetAttribute(sb::fisher_kernel<L, H>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+        SB_CUDA(ctx, cudaFuncSetAttribute(SB_FISHER_KERNEL<L, H>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                                           (int)smem));                                                             \
-        sb::fisher_kernel<L, H><<<grid, sb::FISHER_THREADS, smem, ctx->stream>>>(A);                               \
+        SB_FISHER_KERNEL<L, H><<<grid, FTHREADS, smem, ctx->stream>>>(A);                                          \
     } while (0)
     if (lut_smem && hash) SB_LAUNCH_FISHER(true, true);
     else if (lut_smem) SB_LAUNCH_FISHER(true, false);
     else if (hash) SB_LAUNCH_FISHER(false, true);
     else SB_LAUNCH_FISHER(false, false);
 #undef SB_LAUNCH_FISHER
+#undef SB_FISHER_KERNEL
     ctx->stats.kernel_launches += 1;
     ctx->stats.tests_contingency += ctx->G;
     SB_CUDA(ctx, cudaGetLastError());

@@ -45,11 +45,12 @@ static inline unsigned sb_emul_ballot(bool pred)
     pthread_barrier_wait(&g_bar);
     return m;
 }
+static inline bool sb_emul_any(bool pred) { return sb_emul_ballot(pred) != 0u; }
 // __dmul_rn / __ddiv_rn: one correctly rounded operation each, never contracted into an FMA
 static inline double sb_emul_mul(double a, double b) { volatile double r = a * b; return r; }
 static inline double sb_emul_div(double a, double b) { volatile double r = a / b; return r; }
 
-#include "../../scoary_b200/csrc/fisher.cuh"
+#include "../../scoary_b200/csrc/fisher2.cuh"   // includes fisher.cuh
 
 extern "C" void sb_build_logfact_dd(int32_t n, double *hi_lo);
 
@@ -61,6 +62,20 @@ struct Job {
     double *p;
     int lane;
 };
+
+void *lane_main2(void *arg)      // version 2: four tables per warp, eight lanes each
+{
+    const Job *j = static_cast<const Job *>(arg);
+    t_lane = j->lane;
+    const int grp = j->lane >> 3;
+    for (int64_t i = 0; i < j->n; i += 4) {
+        const bool valid = i + grp < j->n;
+        const int32_t *t = j->tables + 4 * (valid ? i + grp : 0);
+        const double pv = sb::fisher2_two_sided(j->lut, t[0], t[1], t[2], t[3], valid, j->lane);
+        if (valid && (j->lane & 7) == 0) j->p[i + grp] = pv;
+    }
+    return nullptr;
+}
 
 void *lane_main(void *arg)
 {
@@ -78,7 +93,12 @@ void *lane_main(void *arg)
 extern "C" {
 
 // tables[n][4] = a, b, c, d of [[a, b], [c, d]] as the kernel passes them (tpgp, tpgn, tngp, tngn)
-int emul_fisher(const int32_t *tables, int64_t n, double *p)
+static int run_fisher(const int32_t *tables, int64_t n, double *p, void *(*fn)(void *));
+
+int emul_fisher(const int32_t *tables, int64_t n, double *p) { return run_fisher(tables, n, p, lane_main); }
+int emul_fisher2(const int32_t *tables, int64_t n, double *p) { return run_fisher(tables, n, p, lane_main2); }
+
+static int run_fisher(const int32_t *tables, int64_t n, double *p, void *(*fn)(void *))
 {
     int32_t lut_n = 1;
     for (int64_t i = 0; i < n; ++i) {
@@ -93,7 +113,7 @@ int emul_fisher(const int32_t *tables, int64_t n, double *p)
     Job jobs[32];
     for (int l = 0; l < 32; ++l) {
         jobs[l] = Job{tables, n, lut, p, l};
-        pthread_create(&th[l], nullptr, lane_main, &jobs[l]);
+        pthread_create(&th[l], nullptr, fn, &jobs[l]);
     }
     for (int l = 0; l < 32; ++l) pthread_join(th[l], nullptr);
     pthread_barrier_destroy(&g_bar);

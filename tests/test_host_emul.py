@@ -139,31 +139,37 @@ def femul():
                         "-fPIC,-ffp-contract=off", "-ccbin", cxx, "-shared", "-o", FLIB, FSRC,
                         os.path.join(CSRC, "lut.cpp"), "-lquadmath", "-lpthread"], check=True)
     lib = ctypes.CDLL(FLIB)
-    lib.emul_fisher.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
+    lib.emul_fisher.argtypes = lib.emul_fisher2.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
 
-    def run(tables):
-        """tables int [n][4] in the oracle's / C-ABI's order (tpgp, tngp, tpgn, tngn) -> p [n]"""
+    def run(tables, version=1):
+        """tables int [n][4] in the oracle's / C-ABI's order (tpgp, tngp, tpgn, tngn) -> p [n];
+        version 1 = fisher.cuh (the product kernel), 2 = fisher2.cuh (experimental, four tables per warp)"""
         t = np.ascontiguousarray(np.asarray(tables, dtype=np.int32)[:, [0, 2, 1, 3]])     # kernel order a, b, c, d
-        p = np.zeros(len(t), dtype=np.float64)
-        assert lib.emul_fisher(_ptr(t), len(t), _ptr(p)) == 0
+        p = np.full(len(t), -1.0, dtype=np.float64)
+        assert (lib.emul_fisher if version == 1 else lib.emul_fisher2)(_ptr(t), len(t), _ptr(p)) == 0
         return p
     return run
 
 
-def test_fisher_source_on_the_host_matches_scipy_goldens(femul):
+@pytest.mark.parametrize("version", [1, 2])
+def test_fisher_source_on_the_host_matches_scipy_goldens(femul, version):
     """The 600 SciPy tables the oracle is pinned on (tests/golden/fisher.json), through the kernel's own
     warp-cooperative code: same tolerance as the GPU parity tests (1e-10 relative)."""
     import json
     gold = json.load(open(os.path.join(os.path.dirname(HERE), "golden", "fisher.json")))["tables"]
     tabs = np.array([[g["tpgp"], g["tngp"], g["tpgn"], g["tngn"]] for g in gold], dtype=np.int32)
     want = np.array([float.fromhex(g["p"]) for g in gold])
-    got = femul(tabs)
+    got = femul(tabs, version)
     ok = want > 1e-290
     assert np.max(np.abs(got[ok] - want[ok]) / want[ok]) <= FISHER_RTOL
     assert np.all(got[~ok] <= 2e-290)
+    if version == 2:        # a batch that does not fill the last warp, in another order: same values per table
+        perm = np.random.default_rng(1).permutation(len(tabs))[:-3]
+        assert np.array_equal(femul(tabs[perm], 2).view(np.uint64), got[perm].view(np.uint64))
 
 
-def test_fisher_source_on_the_host_large_tables_and_symmetry(femul):
+@pytest.mark.parametrize("version", [1, 2])
+def test_fisher_source_on_the_host_large_tables_and_symmetry(femul, version):
     """N up to 20 000 against the oracle (binary128), and the canonical orientation: the eight symmetric
     variants of a table (row swap, column swap, transpose) must give bit-identical p."""
     rng = np.random.default_rng(5)
@@ -177,8 +183,10 @@ def test_fisher_source_on_the_host_large_tables_and_symmetry(femul):
             sd = max(r1 * c1 / N * (1 - r1 / N) * (1 - c1 / N), 1.0) ** 0.5
             a = int(np.clip(round(r1 * c1 / N + rng.normal() * 3 * sd), lo, hi))
             tabs.append([a, c1 - a, r1 - a, N - r1 - c1 + a])          # tpgp, tngp, tpgn, tngn
+    for t in ([0, 0, 3, 5], [4, 0, 0, 6], [0, 7, 0, 2], [1, 0, 0, 0], [1, 1, 1, 1], [0, 1, 1, 0], [2, 0, 0, 1]):
+        tabs.append(t)                                                 # empty margins, tiny tables
     tabs = np.array(tabs, dtype=np.int32)
-    got = femul(tabs)
+    got = femul(tabs, version)
     want = O.fisher(tabs)
     ok = want > 1e-290
     assert np.max(np.abs(got[ok] - want[ok]) / want[ok]) <= FISHER_RTOL
@@ -187,5 +195,5 @@ def test_fisher_source_on_the_host_large_tables_and_symmetry(femul):
         for (w, x, y, z) in ((a, b, c, d), (c, d, a, b), (b, a, d, c), (d, c, b, a), (a, c, b, d), (b, d, a, c),
                              (c, a, d, b), (d, b, c, a)):
             variants.append([w, y, x, z])                             # back to tpgp, tngp, tpgn, tngn
-    pv = femul(np.array(variants, dtype=np.int32)).reshape(-1, 8)
+    pv = femul(np.array(variants, dtype=np.int32), version).reshape(-1, 8)
     assert np.all(pv.view(np.uint64) == pv.view(np.uint64)[:, :1])

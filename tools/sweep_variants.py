@@ -22,6 +22,9 @@ VARIANTS = {
     "threads256_mb2": "-DSB_WALK_THREADS=256 -DSB_WALK_MINBLOCKS=2",
     "npair1_mb8": "-DSB_WALK_NPAIR=1 -DSB_WALK_MINBLOCKS=8",
     "npair3_mb3": "-DSB_WALK_NPAIR=3 -DSB_WALK_MINBLOCKS=3",
+    "fisher_v2_512": "-DSB_FISHER_V2=1 -DSB_FISHER2_THREADS=512",     # csrc/fisher2.cuh: four genes per warp
+    "fisher_v2_768": "-DSB_FISHER_V2=1 -DSB_FISHER2_THREADS=768",
+    "fisher_v2_256": "-DSB_FISHER_V2=1 -DSB_FISHER2_THREADS=256",
     "fisher512": "-DSB_FISHER_THREADS=512",
     "fisher256": "-DSB_FISHER_THREADS=256",
 }
@@ -50,26 +53,34 @@ best = {}
 for rep in range(3):
     e.stats_reset(); c, p, _ = e.contingency_fisher(0); pairs, r, nd = e.permute(0, P, seed=1); st = e.stats()
     for k in ("ms_fisher", "ms_permute", "ms_walk"): best[k] = min(best.get(k, 1e30), st[k])
-crc = zlib.crc32(pairs.tobytes() + r.tobytes() + c.tobytes() + p.tobytes())
+crc = zlib.crc32(pairs.tobytes() + r.tobytes() + c.tobytes())
+np.save(os.environ["SB_SWEEP_P"], p)
 print(json.dumps({"walks_per_s": G * P / (best["ms_permute"] * 1e-3), "crc": crc, **best}))
 '''
 
 
 def run():
+    os.makedirs(VDIR, exist_ok=True)
     libs = [("base", os.path.join(ROOT, "scoary_b200", "libscoary_b200.so"))]
     libs += [(n, os.path.join(VDIR, n + ".so")) for n in VARIANTS if os.path.exists(os.path.join(VDIR, n + ".so"))]
-    base = None
+    import numpy as np
+    base = base_p = None
     for name, path in libs:
-        env = dict(os.environ, SCOARY_B200_LIB=path)
+        pfile = os.path.join(VDIR, name + ".p.npy")
+        env = dict(os.environ, SCOARY_B200_LIB=path, SB_SWEEP_P=pfile)
         res = subprocess.run([sys.executable, "-c", CHILD % {"root": ROOT}], env=env, capture_output=True, text=True)
         if res.returncode != 0:
             print("%-16s FAILED: %s" % (name, res.stderr.strip().splitlines()[-1] if res.stderr.strip() else "?"))
             continue
         d = json.loads(res.stdout.strip().splitlines()[-1])
-        base = base or d
-        print("%-16s K5 %.3e walks/s (%.2fx)  fisher %.3f ms  results %s" % (
-            name, d["walks_per_s"], d["walks_per_s"] / base["walks_per_s"], d["ms_fisher"],
-            "identical" if d["crc"] == base["crc"] else "DIFFER"))
+        p = np.load(pfile)
+        if base is None:
+            base, base_p = d, p
+        ok = base_p > 1e-290
+        perr = float(np.max(np.abs(p[ok] - base_p[ok]) / base_p[ok]))      # a new Fisher kernel may differ in the last bits
+        print("%-16s K5 %.3e walks/s (%.2fx)  fisher %.3f ms (%.2fx)  integers %s  p max rel diff %.1e" % (
+            name, d["walks_per_s"], d["walks_per_s"] / base["walks_per_s"], d["ms_fisher"], base["ms_fisher"] / d["ms_fisher"],
+            "identical" if d["crc"] == base["crc"] else "DIFFER", perr))
 
 
 if __name__ == "__main__":
