@@ -298,31 +298,53 @@ SB_DEV unsigned max5_16(const unsigned v[5])
     return __vimax3_s16x2(__vimax3_s16x2(v[0], v[1], v[2]), v[3], v[4]);
 }
 
-// m1, m2: half-word masks of the two leaves' gene bits; tt = 2*t1 + t2 (block-uniform)
-template <bool DUAL>
-SB_DEV void walk_cherry16(WalkState16 &o, unsigned m1, unsigned m2, int tt, const Bonus16 &b)
+// o[q] <- node of two leaves, for every gene pair q of the thread.  m1, m2: half-word masks of the two
+// leaves' gene bits; t12 = t1 + 2*t2, the leaves' trait bits (block-uniform: one branch for all pairs)
+template <int NPAIR, bool DUAL>
+SB_DEV void walk_cherry16(WalkState16 (&o)[NPAIR], const unsigned (&m1)[NPAIR], const unsigned (&m2)[NPAIR],
+                          unsigned t12, const Bonus16 (&b)[NPAIR])
 {
     const unsigned N = NEG16x2;
-    unsigned f0 = N, f1 = N, f2 = N, f3 = N, p4 = N, a4 = N;
-    if (tt == 3) {                  // both trait-positive: leaves in {AB, aB}
-        f0 = N & ~(m1 | m2);
-        f2 = N & (m1 & m2);
-    } else if (tt == 0) {           // both trait-negative: leaves in {Ab, ab}
-        f1 = N & ~(m1 | m2);
-        f3 = N & (m1 & m2);
+    if (t12 == 3u) {                // both trait-positive: leaves in {AB, aB}
+#pragma unroll
+        for (int q = 0; q < NPAIR; ++q) {
+            o[q].p[0] = N & ~(m1[q] | m2[q]);
+            o[q].p[1] = N;
+            o[q].p[2] = N & (m1[q] & m2[q]);
+            o[q].p[3] = N;
+            o[q].p[4] = N;
+        }
+    } else if (t12 == 0u) {         // both trait-negative: leaves in {Ab, ab}
+#pragma unroll
+        for (int q = 0; q < NPAIR; ++q) {
+            o[q].p[0] = N;
+            o[q].p[1] = N & ~(m1[q] | m2[q]);
+            o[q].p[2] = N;
+            o[q].p[3] = N & (m1[q] & m2[q]);
+            o[q].p[4] = N;
+        }
     } else {
-        const unsigned mB = (tt == 2) ? m1 : m2;   // gene mask of the trait-positive leaf
-        const unsigned mb = (tt == 2) ? m2 : m1;   // gene mask of the trait-negative leaf
-        f0 = N & ~mB;                   // AB
-        f2 = N & mB;                    // aB
-        f1 = N & ~mb;                   // Ab
-        f3 = N & mb;                    // ab
-        const unsigned pm = mB & ~mb, am = ~mB & mb;   // AB+ab supports, aB+Ab opposes
-        p4 = sel2(pm, b.ps, sel2(am, b.po, N));
-        if constexpr (DUAL) a4 = sel2(pm, b.as_, sel2(am, b.ao, N));
+#pragma unroll
+        for (int q = 0; q < NPAIR; ++q) {
+            const unsigned mB = (t12 == 1u) ? m1[q] : m2[q];   // gene mask of the trait-positive leaf
+            const unsigned mb = (t12 == 1u) ? m2[q] : m1[q];   // gene mask of the trait-negative leaf
+            o[q].p[0] = N & ~mB;            // AB
+            o[q].p[1] = N & ~mb;            // Ab
+            o[q].p[2] = N & mB;             // aB
+            o[q].p[3] = N & mb;             // ab
+            const unsigned pm = mB & ~mb, am = ~mB & mb;       // AB+ab supports, aB+Ab opposes
+            o[q].p[4] = sel2(pm, b[q].ps, sel2(am, b[q].po, N));
+            if constexpr (DUAL) o[q].a[4] = sel2(pm, b[q].as_, sel2(am, b[q].ao, N));
+        }
     }
-    o.p[0] = f0; o.p[1] = f1; o.p[2] = f2; o.p[3] = f3; o.p[4] = p4;
-    if constexpr (DUAL) { o.a[0] = f0; o.a[1] = f1; o.a[2] = f2; o.a[3] = f3; o.a[4] = a4; }
+    if constexpr (DUAL) {
+#pragma unroll
+        for (int q = 0; q < NPAIR; ++q) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) o[q].a[c] = o[q].p[c];
+            if (t12 == 3u || t12 == 0u) o[q].a[4] = N;
+        }
+    }
 }
 
 template <int TB, bool DUAL>
@@ -444,7 +466,8 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR
     const int K = 1 << A.shift;
     const int scale = K - (1 << WALK_SH16);
     WalkState16 a16[NPAIR], b16[NPAIR];
-    int pos = 0, sp = 0, pc = 0;       // sp counts 32-bit words per thread
+    int sp = 0, pc = 0;                // sp counts 32-bit words per thread
+    int room = 0, win = 0;             // leaves left in the current 16-leaf window; windows opened so far
     // gx[q]: the current 16-leaf window of pair q's two genes (gene 2q in bits 0..15, gene 2q+1 in
     // bits 16..31, consumed from bit 0 / bit 16); gy[q]: the following 16 leaves; gnext: prefetch
     uint32_t gx[NPAIR], gy[NPAIR], gnext[NP], lw = 0;
@@ -454,63 +477,115 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR
     for (int q = 0; q < NPAIR; ++q) { gx[q] = 0; gy[q] = 0; }
     const int W32p = A.W32p;
     const int64_t Gs = A.Gs;
-    // fetch the next leaf: label bit tv (uniform); gene bits stay at bit 0 / bit 16 of gx until SB_DROP_BITS
-#define SB_LOAD_BITS(tv)                                                                       \
+    // The leaf stream.  lw holds the label bits from the next leaf on (bit 0 = the next leaf) and gx[q] the
+    // gene bits of pair q up to the end of its 16-leaf window (bit 0 / bit 16 = the next leaf); `room`
+    // leaves of the window are left.  An op whose leaves all lie in the window (the usual case: one
+    // block-uniform test per op) consumes them without any per-leaf test; an op that crosses into the
+    // next window takes the general path, which opens a window wherever room == 0.
+#define SB_OPEN_WINDOW()                                                                       \
     do {                                                                                       \
-        if ((pos & 15) == 0) {                                                                 \
-            if ((pos & 31) == 0) {                                                             \
-                const int w_ = pos >> 5;                                                       \
-                lw = c_labels[lab_off + w_];                                                   \
-                _Pragma("unroll") for (int q_ = 0; q_ < NPAIR; ++q_) {                         \
-                    const uint32_t a_ = gnext[2 * q_], b_ = gnext[2 * q_ + 1];                 \
-                    gx[q_] = (a_ & 0xFFFFu) | (b_ << 16);                                      \
-                    gy[q_] = (a_ >> 16) | (b_ & 0xFFFF0000u);                                  \
-                }                                                                              \
-                if (w_ + 1 < W32p) {                                                           \
-                    _Pragma("unroll") for (int k_ = 0; k_ < NP; ++k_)                          \
-                        gnext[k_] = SB_LDG(gcol[k_] + (int64_t)(w_ + 1) * Gs);                \
-                }                                                                              \
-            } else {                                                                           \
-                _Pragma("unroll") for (int q_ = 0; q_ < NPAIR; ++q_) gx[q_] = gy[q_];          \
+        if ((win & 1) == 0) {                                                                  \
+            const int w_ = win >> 1;                                                           \
+            lw = c_labels[lab_off + w_];                                                       \
+            _Pragma("unroll") for (int q_ = 0; q_ < NPAIR; ++q_) {                             \
+                const uint32_t a_ = gnext[2 * q_], b_ = gnext[2 * q_ + 1];                     \
+                gx[q_] = (a_ & 0xFFFFu) | (b_ << 16);                                          \
+                gy[q_] = (a_ >> 16) | (b_ & 0xFFFF0000u);                                      \
             }                                                                                  \
+            if (w_ + 1 < W32p) {                                                               \
+                _Pragma("unroll") for (int k_ = 0; k_ < NP; ++k_)                              \
+                    gnext[k_] = SB_LDG(gcol[k_] + (int64_t)(w_ + 1) * Gs);                    \
+            }                                                                                  \
+        } else {                                                                               \
+            _Pragma("unroll") for (int q_ = 0; q_ < NPAIR; ++q_) gx[q_] = gy[q_];              \
         }                                                                                      \
-        tv = (int)(lw & 1u);                                                                   \
-        lw >>= 1;                                                                              \
-        ++pos;                                                                                 \
+        ++win;                                                                                 \
+        room = 16;                                                                             \
     } while (0)
-#define SB_DROP_BITS()                                                                         \
-    do {                                                                                       \
-        _Pragma("unroll") for (int q_ = 0; q_ < NPAIR; ++q_) gx[q_] >>= 1;                     \
-    } while (0)
-    // half-word mask of pair q's current gene bits: 0xFFFF per half whose gene is present
-#define SB_PAIR_MASK(q) ((gx[q] & 0x00010001u) * 0xFFFFu)
+    // half-word mask of pair q's gene bits at stream offset o (0 = the next leaf): 0xFFFF per half whose gene is present
+#define SB_PAIR_MASK(q, o) (((gx[q] >> (o)) & 0x00010001u) * 0xFFFFu)
 #define SB_GENE_BIT(k) (((gx[(k) >> 1] >> (((k) & 1) * 16)) & 1u) != 0)
-#define SB_LEAF_RUN16(ACC)                                                                     \
-    _Pragma("unroll 1") for (int i = 0; i < cnt; ++i) {                                        \
-        int t;                                                                                 \
-        SB_LOAD_BITS(t);                                                                       \
-        if (t) {                                                                               \
+    // one leaf update of the packed / the 32-bit accumulators; `room` is the caller's business
+#define SB_LEAF_STEP16(ACC)                                                                    \
+    do {                                                                                       \
+        const uint32_t t_ = lw & 1u;                                                           \
+        lw >>= 1;                                                                              \
+        if (t_) {                                                                              \
             _Pragma("unroll") for (int q = 0; q < NPAIR; ++q)                                  \
-                walk_leaf16<1, DUAL>(ACC[q], SB_PAIR_MASK(q), b16c[q]);                        \
+                walk_leaf16<1, DUAL>(ACC[q], SB_PAIR_MASK(q, 0), b16c[q]);                     \
         } else {                                                                               \
             _Pragma("unroll") for (int q = 0; q < NPAIR; ++q)                                  \
-                walk_leaf16<0, DUAL>(ACC[q], SB_PAIR_MASK(q), b16c[q]);                        \
+                walk_leaf16<0, DUAL>(ACC[q], SB_PAIR_MASK(q, 0), b16c[q]);                     \
         }                                                                                      \
-        SB_DROP_BITS();                                                                        \
-    }
-#define SB_CHERRY16(ACC)                                                                       \
+        _Pragma("unroll") for (int q = 0; q < NPAIR; ++q) gx[q] >>= 1;                         \
+    } while (0)
+#define SB_LEAF_STEP32()                                                                       \
     do {                                                                                       \
-        int t1, t2;                                                                            \
+        const uint32_t t_ = lw & 1u;                                                           \
+        lw >>= 1;                                                                              \
+        if (t_) {                                                                              \
+            _Pragma("unroll") for (int k = 0; k < NP; ++k)                                     \
+                walk_leaf<1, DUAL>(acc[k], SB_GENE_BIT(k), b32[k]);                            \
+        } else {                                                                               \
+            _Pragma("unroll") for (int k = 0; k < NP; ++k)                                     \
+                walk_leaf<0, DUAL>(acc[k], SB_GENE_BIT(k), b32[k]);                            \
+        }                                                                                      \
+        _Pragma("unroll") for (int q = 0; q < NPAIR; ++q) gx[q] >>= 1;                         \
+    } while (0)
+    // `cnt` leaf updates
+#define SB_LEAF_RUN(STEP)                                                                      \
+    do {                                                                                       \
+        if (__builtin_expect(cnt <= room, 1)) {                                                \
+            room -= cnt;                                                                       \
+            _Pragma("unroll 1") for (int i = 0; i < cnt; ++i) { STEP; }                        \
+        } else {                                                                               \
+            _Pragma("unroll 1") for (int i = 0; i < cnt; ++i) {                                \
+                if (room == 0) SB_OPEN_WINDOW();                                               \
+                STEP;                                                                          \
+                --room;                                                                        \
+            }                                                                                  \
+        }                                                                                      \
+    } while (0)
+    // ACC <- node of the next two leaves (t12: label of the first in bit 0, of the second in bit 1), then
+    // `cnt` leaf updates of ACC
+#define SB_CHERRY_RUN16(ACC)                                                                   \
+    do {                                                                                       \
+        uint32_t t12;                                                                          \
         unsigned m1[NPAIR], m2[NPAIR];                                                         \
-        SB_LOAD_BITS(t1);                                                                      \
-        _Pragma("unroll") for (int q = 0; q < NPAIR; ++q) m1[q] = SB_PAIR_MASK(q);             \
-        SB_DROP_BITS();                                                                        \
-        SB_LOAD_BITS(t2);                                                                      \
-        _Pragma("unroll") for (int q = 0; q < NPAIR; ++q) m2[q] = SB_PAIR_MASK(q);             \
-        SB_DROP_BITS();                                                                        \
-        const int tt = t1 * 2 + t2;                                                            \
-        _Pragma("unroll") for (int q = 0; q < NPAIR; ++q)                                      \
-            walk_cherry16<DUAL>(ACC[q], m1[q], m2[q], tt, b16c[q]);                            \
+        if (__builtin_expect(cnt + 2 <= room, 1)) {                                            \
+            room -= cnt + 2;                                                                   \
+            t12 = lw & 3u;                                                                     \
+            lw >>= 2;                                                                          \
+            _Pragma("unroll") for (int q = 0; q < NPAIR; ++q) {                                \
+                m1[q] = SB_PAIR_MASK(q, 0);                                                    \
+                m2[q] = SB_PAIR_MASK(q, 1);                                                    \
+                gx[q] >>= 2;                                                                   \
+            }                                                                                  \
+            walk_cherry16<NPAIR, DUAL>(ACC, m1, m2, t12, b16c);                                \
+            _Pragma("unroll 1") for (int i = 0; i < cnt; ++i) { SB_LEAF_STEP16(ACC); }         \
+        } else {                                                                               \
+            if (room == 0) SB_OPEN_WINDOW();                                                   \
+            t12 = lw & 1u;                                                                     \
+            lw >>= 1;                                                                          \
+            _Pragma("unroll") for (int q = 0; q < NPAIR; ++q) {                                \
+                m1[q] = SB_PAIR_MASK(q, 0);                                                    \
+                gx[q] >>= 1;                                                                   \
+            }                                                                                  \
+            if (--room == 0) SB_OPEN_WINDOW();                                                 \
+            t12 |= (lw & 1u) << 1;                                                             \
+            lw >>= 1;                                                                          \
+            _Pragma("unroll") for (int q = 0; q < NPAIR; ++q) {                                \
+                m2[q] = SB_PAIR_MASK(q, 0);                                                    \
+                gx[q] >>= 1;                                                                   \
+            }                                                                                  \
+            --room;                                                                            \
+            walk_cherry16<NPAIR, DUAL>(ACC, m1, m2, t12, b16c);                                \
+            _Pragma("unroll 1") for (int i = 0; i < cnt; ++i) {                                \
+                if (room == 0) SB_OPEN_WINDOW();                                               \
+                SB_LEAF_STEP16(ACC);                                                           \
+                --room;                                                                        \
+            }                                                                                  \
+        }                                                                                      \
     } while (0)
 #define SB_POP16(L, q)                                                                         \
     do {                                                                                       \
@@ -525,7 +600,7 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR
         const int type = op & 15, cnt = op >> OP_TYPE_BITS;
         switch (type) {
         case OP_LEAF_A16:
-            SB_LEAF_RUN16(a16)
+            SB_LEAF_RUN(SB_LEAF_STEP16(a16));
             break;
         case OP_PUSH16:
         case OP_PUSH_CHERRY_A16:
@@ -542,13 +617,11 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR
             if (type == OP_PUSH16) break;
             // fall through
         case OP_CHERRY_A16:
-            SB_CHERRY16(a16);
-            SB_LEAF_RUN16(a16)
+            SB_CHERRY_RUN16(a16);
             break;
         case OP_CHERRY_B16:
         case OP_CHERRY_B16_MERGE:
-            SB_CHERRY16(b16);
-            SB_LEAF_RUN16(b16)
+            SB_CHERRY_RUN16(b16);
             if (type == OP_CHERRY_B16_MERGE) {
 #pragma unroll
                 for (int q = 0; q < NPAIR; ++q) walk_merge16<DUAL>(b16[q], a16[q], b16c[q]);
@@ -571,19 +644,7 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR
             for (int q = 0; q < NPAIR; ++q) walk_widen<DUAL>(a16[q], acc[2 * q], acc[2 * q + 1], scale);
             break;
         case OP_LEAF_A32:
-#pragma unroll 1
-            for (int i = 0; i < cnt; ++i) {
-                int t;
-                SB_LOAD_BITS(t);
-                if (t) {
-#pragma unroll
-                    for (int k = 0; k < NP; ++k) walk_leaf<1, DUAL>(acc[k], SB_GENE_BIT(k), b32[k]);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < NP; ++k) walk_leaf<0, DUAL>(acc[k], SB_GENE_BIT(k), b32[k]);
-                }
-                SB_DROP_BITS();
-            }
+            SB_LEAF_RUN(SB_LEAF_STEP32());
             break;
         case OP_MERGE_A32_B16:
 #pragma unroll
@@ -642,12 +703,13 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR
             return;
         }
     }
-#undef SB_LOAD_BITS
-#undef SB_DROP_BITS
+#undef SB_OPEN_WINDOW
 #undef SB_PAIR_MASK
 #undef SB_GENE_BIT
-#undef SB_LEAF_RUN16
-#undef SB_CHERRY16
+#undef SB_LEAF_STEP16
+#undef SB_LEAF_STEP32
+#undef SB_LEAF_RUN
+#undef SB_CHERRY_RUN16
 #undef SB_POP16
 }
 

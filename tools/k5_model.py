@@ -1,0 +1,117 @@
+#!/usr/bin/env python
+"""Warp instructions per walk of walk_permute_kernel (K5), computed here (no GPU) by running the
+kernel's SASS control flow (tools/sass_emul.py) on the real tree program and the real label vectors.
+
+  python tools/k5_model.py [--lib scoary_b200/libscoary_b200.so] [--isolates 5000] [--seed 20260903]
+                           [--perms 60] [--ppi 2] [--chunks 0,7,15] [--json out.json]
+
+Prints the executed warp instructions of one block-warp per chunk of `ppi` labellings and the average
+per 64 (gene, labelling) walks -- the unit of profiles/k5_warp_instructions.json (ncu:
+smsp__inst_executed.sum / (genes x permutations / 64)).  The labellings are the ones the engine draws
+for `sb_permute(seed=1)` (same Philox stream as the oracle), so for the profiled launch the count can be
+compared with ncu directly."""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+sys.setrecursionlimit(1_000_000)
+
+import numpy as np  # noqa: E402
+
+import sass_emul  # noqa: E402
+
+C_OPS_BYTES = 2 * 12288          # csrc/walk.cuh: c_ops, then c_labels, in constant bank 3
+
+
+def workload(n_isolates, seed, n_perms, perm_seed):
+    """tree program + label vectors in walk order, exactly as sb_set_tree / sb_permute stage them"""
+    from oracle import oracle as O
+    from scoary_b200 import synth
+    from scoary_b200 import tree as treemod
+    from test_tree_program import compile_tree
+    nested = synth.make_tree(n_isolates, seed)
+    ops, order, units, names = compile_tree(nested)
+    col = {n: j for j, n in enumerate(synth.isolate_names(n_isolates))}
+    traits = synth.make_traits(n_isolates, 1, seed)
+    lab = (traits[0][np.asarray([col[n] for n in names])] == 1).astype(np.uint8)      # by leaf id
+    W32 = (n_isolates + 31) // 32
+    W32p = (W32 + 3) // 4 * 4
+    labs = np.stack([O.shuffle_labels(perm_seed, 0, p, lab) for p in range(n_perms)])
+    walk = np.zeros((n_perms, W32p * 32), dtype=np.uint8)
+    walk[:, :n_isolates] = labs[:, order[:n_isolates]]
+    labelsW = np.ascontiguousarray(np.packbits(walk, axis=1, bitorder="little")).view(np.uint32).reshape(n_perms, W32p)
+    shift = 1
+    while (1 << shift) <= n_isolates // 2:
+        shift += 1
+    return np.ascontiguousarray(ops), labelsW, W32p, shift
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--lib", default=os.path.join(ROOT, "scoary_b200", "libscoary_b200.so"))
+    ap.add_argument("--kernel", default="walk_permute_kernel")
+    ap.add_argument("--isolates", type=int, default=5000)
+    ap.add_argument("--genes", type=int, default=50000)
+    ap.add_argument("--seed", type=int, default=20260903)
+    ap.add_argument("--perm-seed", type=int, default=1)
+    ap.add_argument("--perms", type=int, default=60, help="labellings staged for the launch")
+    ap.add_argument("--ppi", type=int, default=2, help="labellings per block")
+    ap.add_argument("--chunks", default="all")
+    ap.add_argument("--genes-per-thread", type=int, default=4)
+    ap.add_argument("--threads", type=int, default=128)
+    ap.add_argument("--json")
+    ap.add_argument("--profile", type=int, default=0, help="print the N basic blocks with the most executed instructions")
+    a = ap.parse_args()
+
+    ops, labelsW, W32p, shift = workload(a.isolates, a.seed, a.perms, a.perm_seed)
+    const3 = bytearray(C_OPS_BYTES + 4 * labelsW.size)
+    const3[:2 * len(ops)] = ops.astype("<u2").tobytes()
+    const3[C_OPS_BYTES:] = labelsW.astype("<u4").tobytes()
+    instrs, labels, const2 = sass_emul.extract(a.lib, a.kernel)
+    Gs = (a.genes + 31) // 32 * 32
+    params = sass_emul.walk_args(Gs, a.genes, a.genes, W32p, shift, a.perms, a.ppi)
+    n_chunks = (a.perms + a.ppi - 1) // a.ppi
+    chunks = range(n_chunks) if a.chunks == "all" else [int(c) for c in a.chunks.split(",")]
+    per_chunk = {}
+    dyn = [0] * len(instrs)
+    for c in chunks:
+        m = sass_emul.Machine(instrs, labels, const2, params, bytes(const3), tid=0, ctaid=(0, c, 0))
+        per_chunk[c] = m.run()
+        dyn = [x + y for x, y in zip(dyn, m.counts)]
+        if m.assumed:
+            print("   per-thread branches assumed not taken:", {hex(k): v for k, v in m.assumed.items()})
+        print("chunk %3d: %d warp instructions for %d labellings" % (c, per_chunk[c], min(a.ppi, a.perms - c * a.ppi)))
+    walks_per_warp = 32 * a.genes_per_thread
+    total_instr = sum(per_chunk.values())
+    total_walks = sum(min(a.ppi, a.perms - c * a.ppi) for c in chunks) * walks_per_warp
+    per64 = total_instr / total_walks * 64
+    print("static instructions in the kernel: %d" % len(instrs))
+    print("warp instructions per 64 walks: %.0f   (per internal node and 4-gene thread: %.1f)" % (
+        per64, per64 * 2 / max(a.isolates - 1, 1)))
+    if a.profile:
+        import sass_blocks
+        count_at = {ins.addr: n for ins, n in zip(instrs, dyn)}
+        rows = []
+        for b in sass_blocks.blocks(sass_blocks.disassemble(a.lib, a.kernel)):
+            ins = [r for r in b if r[0] is not None]
+            if ins:
+                lines = sorted(set(r[1] for r in ins if r[1]))
+                rows.append((sum(count_at.get(r[0], 0) for r in ins), ins[0][0], len(ins), count_at.get(ins[0][0], 0), lines))
+        total = sum(r[0] for r in rows)
+        print("  share  executed  block  (instructions x entries)  walk.cuh lines")
+        for r in sorted(rows, reverse=True)[:a.profile]:
+            print("  %5.1f%% %9d  %06x  (%3d x %6d)  %s" % (100.0 * r[0] / total, r[0], r[1], r[2], r[3], r[4][:8]))
+    if a.json:
+        with open(a.json, "w") as f:
+            json.dump({"lib": os.path.relpath(a.lib, ROOT), "kernel": a.kernel, "isolates": a.isolates, "perms": a.perms,
+                       "ppi": a.ppi, "chunks": {str(k): v for k, v in per_chunk.items()}, "per_64_walks": per64}, f)
+    return per64
+
+
+if __name__ == "__main__":
+    main()

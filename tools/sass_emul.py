@@ -1,0 +1,457 @@
+#!/usr/bin/env python
+"""Dynamic instruction count of the walk kernels WITHOUT a GPU: a small interpreter for the control flow
+of their SASS.
+
+Every branch of walk_permute_kernel / walk_pairs_kernel depends on block-uniform data only (the tree
+program and the label bits in constant memory, the kernel arguments), and nvcc keeps that data in the
+uniform datapath (UR registers, UP predicates, BRA.U / BRX).  This module parses `nvdisasm` output and
+executes exactly those instructions -- the uniform ALU ops, constant loads, and the handful of vector
+ops that feed a BRX or a predicated BRA from uniform values -- for one thread; every other instruction
+is only counted (its destination becomes "unknown").  A branch on an unknown value is an error, so a
+count that comes out is the count the hardware executes for that warp (smsp__inst_executed counts
+predicated-off instructions too).
+
+Validated against ncu: see tools/k5_model.py and profiles/r1_k5_instruction_model.md.
+"""
+import os
+import re
+import struct
+import subprocess
+import tempfile
+
+M32 = 0xFFFFFFFF
+
+
+def s32(x):
+    x &= M32
+    return x - (1 << 32) if x & 0x80000000 else x
+
+
+class Instr:
+    __slots__ = ("addr", "guard", "op", "mods", "args", "text")
+
+
+def extract(lib, kernel):
+    """(instructions, label -> address, constant bank 2 bytes) of `kernel` in shared library `lib`."""
+    with tempfile.TemporaryDirectory() as d:
+        subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=d, check=True, stdout=subprocess.DEVNULL)
+        cubins = sorted((os.path.getsize(os.path.join(d, f)), f) for f in os.listdir(d) if f.endswith(".cubin"))
+        text = subprocess.run(["nvdisasm", os.path.join(d, cubins[-1][1])], check=True, capture_output=True, text=True).stdout
+    instrs, labels, const2 = [], {}, bytearray()
+    section, pending = None, []
+    for line in text.splitlines():
+        m = re.match(r"\s*\.section\s+(\S+?),", line)
+        if m:
+            section = m.group(1)
+            continue
+        if section is None or kernel not in section:
+            continue
+        if section.startswith(".nv.constant2."):
+            m = re.match(r"\s+/\*[0-9a-f]+\*/\s+\.byte\s+(.*)", line)
+            if m:
+                const2 += bytes(int(b, 16) for b in m.group(1).split(","))
+            continue
+        if not section.startswith(".text."):
+            continue
+        m = re.match(r"(\.L_x_\d+):", line)
+        if m:
+            pending.append(m.group(1))
+            continue
+        m = re.match(r"\s+/\*([0-9a-f]{4,6})\*/\s+(.*?);", line)
+        if not m:
+            continue
+        ins = Instr()
+        ins.addr = int(m.group(1), 16)
+        body = m.group(2).strip()
+        ins.text = body
+        g = re.match(r"@(!?U?P\w+)\s+(.*)", body)
+        ins.guard = g.group(1) if g else None
+        body = g.group(2) if g else body
+        parts = body.split(None, 1)
+        name = parts[0].split(".")
+        ins.op, ins.mods = name[0], name[1:]
+        rest = re.sub(r"\(\*.*", "", parts[1]) if len(parts) > 1 else ""
+        ins.args = [a.strip() for a in split_args(rest)]
+        for lab in pending:
+            labels[lab] = ins.addr
+        pending = []
+        instrs.append(ins)
+    return instrs, labels, bytes(const2)
+
+
+def split_args(s):
+    out, depth, cur = [], 0, ""
+    for ch in s:
+        if ch == "[":
+            depth += 1
+        elif ch == "]":
+            depth -= 1
+        if ch == "," and depth == 0:
+            out.append(cur)
+            cur = ""
+        else:
+            cur += ch
+    if cur.strip():
+        out.append(cur)
+    return out
+
+
+class Unknown(Exception):
+    """an input value is unknown: the destinations become unknown"""
+
+
+class Unsupported(Exception):
+    """the interpreter does not model this instruction form"""
+
+
+class Machine:
+    """State of one thread.  Register values are ints (mod 2^32) or None (unknown)."""
+
+    def __init__(self, instrs, labels, const2, params, const3, tid=0, ctaid=(0, 0, 0), param_base=0x380):
+        self.instrs = instrs
+        self.index = {ins.addr: i for i, ins in enumerate(instrs)}
+        self.labels = labels
+        self.const2, self.const3 = const2, const3
+        self.params, self.param_base = params, param_base
+        self.tid, self.ctaid = tid, ctaid
+        self.R, self.UR, self.P, self.UP = {}, {}, {}, {}
+        self.local = {}               # spill slots, keyed by the address text ([R1+0x18])
+        self.counts = [0] * len(instrs)
+        self.assumed = {}             # address -> times a per-thread (non-uniform) branch was assumed not taken
+
+    # ---- operand access
+    def const(self, bank, off, size=4):
+        if bank == 0:
+            o = off - self.param_base
+            if 0 <= o and o + size <= len(self.params):
+                raw = self.params[o:o + size]
+            else:
+                return None          # driver-filled words (stack base, memory descriptors): never steer a branch
+        elif bank == 2:
+            raw = self.const2[off:off + size]
+        elif bank == 3:
+            raw = self.const3[off:off + size]
+        else:
+            return None
+        if len(raw) < size:
+            raw = raw + b"\0" * (size - len(raw))
+        return int.from_bytes(raw, "little")
+
+    def val(self, a):
+        """32-bit value of a source operand (None = unknown)."""
+        a = a.replace(".reuse", "")
+        neg = inv = False
+        if a.startswith("-"):
+            neg, a = True, a[1:]
+        if a.startswith("~"):
+            inv, a = True, a[1:]
+        if a.startswith("|") and a.endswith("|"):
+            raise Unsupported("abs operand " + a)
+        if a in ("RZ", "URZ"):
+            v = 0
+        elif re.fullmatch(r"UR\d+", a):
+            v = self.UR.get(a)
+        elif re.fullmatch(r"R\d+", a):
+            v = self.R.get(a)
+        elif re.fullmatch(r"0x[0-9a-f]+|\d+", a):
+            v = int(a, 0)
+        elif a.startswith("c["):
+            m = re.fullmatch(r"c\[(0x[0-9a-f]+)\]\[(.+)\]", a)
+            bank, inner = int(m.group(1), 16), m.group(2)
+            off = 0
+            for term in inner.split("+"):
+                t = self.val(term.strip())
+                if t is None:
+                    return None
+                off += t
+            v = self.const(bank, off)
+        else:
+            raise Unsupported("operand " + a)
+        if v is None:
+            return None
+        if inv:
+            v = ~v
+        if neg:
+            v = -v
+        return v & M32
+
+    def pred(self, a):
+        negate = a.startswith("!")
+        a = a.lstrip("!")
+        if a in ("PT", "UPT"):
+            v = True
+        elif a.startswith("UP"):
+            v = self.UP.get(a)
+        else:
+            v = self.P.get(a)
+        if v is None:
+            return None
+        return (not v) if negate else v
+
+    def setp(self, a, v):
+        if a in ("PT", "UPT"):
+            return
+        (self.UP if a.startswith("UP") else self.P)[a] = v
+
+    def setr(self, a, v):
+        a = a.replace(".reuse", "")
+        if a in ("RZ", "URZ"):
+            return
+        (self.UR if a.startswith("UR") else self.R)[a] = None if v is None else v & M32
+
+    def pair(self, a):
+        """64-bit value of register pair a (low register named)."""
+        a = a.replace(".reuse", "")
+        if a in ("RZ", "URZ"):
+            return 0
+        m = re.fullmatch(r"(U?R)(\d+)", a)
+        lo = self.val(a)
+        hi = self.val("%s%d" % (m.group(1), int(m.group(2)) + 1))
+        return None if lo is None or hi is None else lo | (hi << 32)
+
+    def setpair(self, a, v):
+        m = re.fullmatch(r"(U?R)(\d+)", a.replace(".reuse", ""))
+        if not m:
+            return
+        self.setr(a, None if v is None else v & M32)
+        self.setr("%s%d" % (m.group(1), int(m.group(2)) + 1), None if v is None else (v >> 32) & M32)
+
+    # ---- execution
+    @staticmethod
+    def compare(cmp, a, b, unsigned):
+        if not unsigned:
+            a, b = s32(a), s32(b)
+        return {"EQ": a == b, "NE": a != b, "LT": a < b, "LE": a <= b, "GT": a > b, "GE": a >= b}[cmp]
+
+    @staticmethod
+    def lut3(a, b, c, lut):
+        r = 0
+        for i in range(8):
+            if lut >> i & 1:
+                ta = a if i & 4 else ~a
+                tb = b if i & 2 else ~b
+                tc = c if i & 1 else ~c
+                r |= ta & tb & tc
+        return r & M32
+
+    def step(self, i):
+        """execute instruction i; return the index of the next one (None = exit)"""
+        ins = self.instrs[i]
+        self.counts[i] += 1
+        op, mods, a = ins.op, ins.mods, ins.args
+        on = True
+        if ins.guard:
+            on = self.pred(ins.guard)
+        if op in ("BRA", "BRX", "EXIT", "RET"):
+            if on is None:
+                if ins.guard.lstrip("!").startswith("UP") or op == "BRX":
+                    raise Unknown("branch on unknown predicate at %x: %s" % (ins.addr, ins.text))
+                # a per-thread predicate (the `active` lane flags around the result stores): the warp runs the
+                # guarded block whenever any lane is active, so count it as executed; reported by the caller
+                self.assumed[ins.addr] = self.assumed.get(ins.addr, 0) + 1
+                return i + 1
+            if not on:
+                return i + 1
+            if op == "EXIT":
+                return None
+            if op == "BRA":
+                tgt = a[-1]
+                if len(a) == 2:                       # BRA.U UP0, target  /  BRA.U !UP0, target
+                    c = self.pred(a[0])
+                    if c is None:
+                        raise Unknown("BRA.U on unknown predicate at %x" % ins.addr)
+                    if not c:
+                        return i + 1
+                m = re.search(r"\((\.L_x_\d+)\)", tgt)
+                return self.index[self.labels[m.group(1)]]
+            if op == "BRX":
+                m = re.fullmatch(r"(R\d+)\s+(-?0x[0-9a-f]+)", a[0].strip())
+                base = self.val(m.group(1))
+                if base is None:
+                    raise Unknown("BRX on unknown register at %x" % ins.addr)
+                return self.index[(base + int(m.group(2), 16) + self.instrs[i + 1].addr) & M32]
+            raise Unknown(op)
+        if on is False:
+            return i + 1                              # predicated off: counted, no effect
+        if on is None:
+            self.clobber(ins)
+            return i + 1
+        try:
+            self.execute(ins)
+        except Unknown:
+            self.clobber(ins)
+        except Unsupported:
+            if ins.op.startswith("U") or ins.op == "PLOP3":
+                raise Unsupported("uniform instruction not modelled at %x: %s" % (ins.addr, ins.text))
+            self.clobber(ins)
+        return i + 1
+
+    def clobber(self, ins):
+        """unknown effect: destinations become unknown"""
+        if ins.op in ("STS", "STG", "BSSY", "BSYNC", "NOP", "BAR", "WARPSYNC", "DEPBAR", "ST"):
+            return
+        wide = "WIDE" in ins.mods or "64" in ins.mods
+        seen_reg = False
+        for arg in ins.args:
+            arg = arg.replace(".reuse", "")
+            if re.fullmatch(r"U?R\d+", arg) and not seen_reg:
+                (self.setpair if wide else self.setr)(arg, None)
+                seen_reg = True
+                if ins.op not in ("IADD3", "LEA", "LOP3", "UIADD3"):
+                    break
+            elif re.fullmatch(r"U?P\d+", arg) and (not seen_reg or ins.op in ("IADD3", "LEA", "UIADD3")):
+                self.setp(arg, None)
+            elif seen_reg:
+                break
+
+    def execute(self, ins):
+        op, mods, a = ins.op, ins.mods, ins.args
+        V = self.val
+
+        def need(*xs):
+            if any(x is None for x in xs):
+                raise Unknown("unknown input")
+            return xs
+
+        if op in ("UMOV", "MOV"):
+            self.setr(a[0], V(a[1]))
+        elif op == "STL":
+            self.local[a[0]] = V(a[1])
+        elif op == "LDL":
+            self.setr(a[0], self.local.get(a[1]))
+        elif op in ("S2R", "S2UR"):
+            sr = {"SR_TID.X": self.tid, "SR_TID.Y": 0, "SR_TID.Z": 0, "SR_CTAID.X": self.ctaid[0],
+                  "SR_CTAID.Y": self.ctaid[1], "SR_CTAID.Z": self.ctaid[2]}
+            self.setr(a[0], sr.get(a[1]))          # anything else (SR_CgaCtaId: shared-memory window) stays unknown
+        elif op in ("LDCU", "LDC"):
+            m = re.fullmatch(r"c\[(0x[0-9a-f]+)\]\[(.+)\]", a[1])
+            bank = int(m.group(1), 16)
+            off = 0
+            for term in m.group(2).split("+"):
+                t = V(term.strip())
+                need(t)
+                off += t
+            if "64" in mods:
+                self.setpair(a[0], self.const(bank, off, 8))
+            elif "U16" in mods:
+                self.setr(a[0], self.const(bank, off, 2))
+            elif "U8" in mods:
+                self.setr(a[0], self.const(bank, off, 1))
+            else:
+                self.setr(a[0], self.const(bank, off, 4))
+        elif op in ("UIADD3", "IADD3"):
+            if "X" in mods:
+                x, y, z = need(V(a[3]), V(a[4]), V(a[5]))
+                c1, c2 = need(self.pred(a[6]), self.pred(a[7]))
+                tot = x + y + z + int(c1) + int(c2)
+            else:
+                x, y, z = need(V(a[3]), V(a[4]), V(a[5]))
+                tot = x + y + z
+            self.setr(a[0], tot)
+            self.setp(a[1], bool((tot >> 32) & 1))
+            self.setp(a[2], bool((tot >> 33) & 1))
+        elif op in ("UIMAD", "IMAD"):
+            if "MOV" in mods:
+                self.setr(a[0], V(a[3]))
+            elif "WIDE" in mods:
+                x, y = need(V(a[1]), V(a[2]))
+                z = self.pair(a[3])
+                need(z)
+                if "U32" not in mods:
+                    x, y = s32(x), s32(y)
+                self.setpair(a[0], (x * y + z) & 0xFFFFFFFFFFFFFFFF)
+            elif "SHL" in mods:                      # the immediate is the multiplier (1 << shift)
+                x, y = need(V(a[1]), V(a[2]))
+                self.setr(a[0], x * y)
+            elif "IADD" in mods:
+                x, z = need(V(a[1]), V(a[3]))
+                self.setr(a[0], x + z)
+            elif "X" in mods or "HI" in mods:
+                raise Unsupported("IMAD." + ".".join(mods))
+            else:
+                x, y, z = need(V(a[1]), V(a[2]), V(a[3]))
+                self.setr(a[0], x * y + z)
+        elif op in ("ULOP3", "LOP3"):
+            if re.fullmatch(r"U?P\w+", a[0]):          # predicate output form: Pd, Rd, a, b, c, lut, Pin
+                x, y, z = need(V(a[2]), V(a[3]), V(a[4]))
+                r = self.lut3(x, y, z, int(a[5], 16))
+                self.setp(a[0], r != 0)
+                self.setr(a[1], r)
+            else:
+                x, y, z = need(V(a[1]), V(a[2]), V(a[3]))
+                self.setr(a[0], self.lut3(x, y, z, int(a[4], 16)))
+        elif op in ("UISETP", "ISETP"):
+            cmp = mods[0]
+            unsigned = "U32" in mods
+            x, y = need(V(a[2]), V(a[3]))
+            c = self.pred(a[4])
+            need(c)
+            if "EX" in mods:
+                # high word of a 64-bit compare: a[5] carries the low-word result
+                lo = self.pred(a[5])
+                need(lo)
+                xs, ys = (x, y) if unsigned else (s32(x), s32(y))
+                r = (xs > ys) if cmp in ("GT", "GE") else (xs < ys) if cmp in ("LT", "LE") else None
+                if cmp in ("EQ", "NE"):
+                    r = (x == y and lo) if cmp == "EQ" else (x != y or lo)
+                else:
+                    r = r or (xs == ys and lo)
+            else:
+                r = self.compare(cmp, x, y, unsigned)
+            bop = [m for m in mods if m in ("AND", "OR", "XOR")][0]
+            r = (r and c) if bop == "AND" else (r or c) if bop == "OR" else (r != c)
+            self.setp(a[0], r)
+            self.setp(a[1], None)
+        elif op in ("USHF", "SHF"):
+            lo, sh, hi = need(V(a[1]), V(a[2]), V(a[3]))
+            sh &= 63 if "U64" in mods or "S64" in mods else 31
+            if "L" in mods:
+                if "HI" in mods:
+                    self.setr(a[0], (((hi << 32) | lo) << sh) >> 32)
+                else:
+                    self.setr(a[0], lo << sh)
+            else:
+                if "HI" in mods:
+                    v = s32(hi) >> sh if "S32" in mods else hi >> sh
+                    self.setr(a[0], v)
+                else:
+                    self.setr(a[0], ((hi << 32) | lo) >> sh)
+        elif op in ("ULEA", "LEA"):
+            if "HI" in mods or re.fullmatch(r"U?P\w+", a[1]):
+                raise Unsupported("LEA form")
+            x, y, sh = need(V(a[1]), V(a[2]), V(a[3]))
+            self.setr(a[0], (x << sh) + y)
+        elif op in ("USEL", "SEL"):
+            x, y = V(a[1]), V(a[2])
+            c = self.pred(a[3])
+            need(c)
+            self.setr(a[0], x if c else y)
+        elif op == "PLOP3":
+            x, y, z = need(self.pred(a[2]), self.pred(a[3]), self.pred(a[4]))
+            lut = int(a[5], 16)
+            self.setp(a[0], bool(lut >> ((4 if x else 0) | (2 if y else 0) | (1 if z else 0)) & 1))
+            self.setp(a[1], None)
+        elif op == "VIADDMNMX" and "U32" in mods:
+            x, y, z = need(V(a[1]), V(a[2]), V(a[3]))
+            s = (x + y) & M32
+            self.setr(a[0], min(s, z) if self.pred(a[4]) else max(s, z))
+        elif op == "VIADD" and not mods:
+            x, y = need(V(a[1]), V(a[2]))
+            self.setr(a[0], x + y)
+        else:
+            raise Unsupported(op)
+
+    def run(self, max_steps=50_000_000):
+        i, n = 0, 0
+        while i is not None:
+            i = self.step(i)
+            n += 1
+            if n > max_steps:
+                raise RuntimeError("instruction limit reached")
+        return n
+
+
+def walk_args(Gs, S, S_total, W32p, shift, n_perms, ppi, chunk_base=0, gene_idx=0, slot_idx=0):
+    """struct WalkArgs (csrc/walk.cuh) as the kernel-parameter bytes; pointers only need to be non-null"""
+    return struct.pack("<QqQQqqiiiiiiQQQ", 0x7000_0000_0000, Gs, gene_idx, slot_idx, S, S_total, W32p, shift, n_perms, ppi,
+                       (n_perms + ppi - 1) // ppi, chunk_base, 0x7100_0000_0000, 0x7200_0000_0000, 0x7300_0000_0000)
