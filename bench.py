@@ -530,15 +530,17 @@ def run_ours(a):
     # issue-slot view of the same kernel: warp instructions actually executed (ncu count, profiles/) per second
     # against the SM's issue capacity (4 warp instructions per clock per SM) at the clock sampled above
     try:
-        wi = json.load(open(os.path.join(ROOT, "profiles", "k5_warp_instructions.json"))).get(a.workload)
+        wi_file = json.load(open(os.path.join(ROOT, "profiles", "k5_warp_instructions.json")))
+        wi, wi_src = wi_file.get(a.workload), wi_file.get("source", "ncu")
     except Exception:
-        wi = None
+        wi = wi_src = None
     if wi and P > 0 and clocks and clocks.get("sm_mhz"):
         issued = tests_per_launch / 64.0 * wi / (k5_ms * 1e-3)
         cap = 4.0 * st["sm_count"] * clocks["sm_mhz"] * 1e6
         roofline_int["issue"] = {"warp_instr_per_s": issued, "peak": cap, "frac": issued / cap,
-                                 "source": "instruction count from profiles/k5_warp_instructions.json (ncu), time and "
-                                           "clock from this run"}
+                                 "warp_instr_per_64_walks": wi,
+                                 "source": "instruction count from profiles/k5_warp_instructions.json (%s); time and "
+                                           "clock from this run" % wi_src}
     fisher_bytes = G * (8 * W + 24)
     fisher = {"kernel": "fisher_kernel (K2+K3)", "ms": fisher_ms, "tests_per_s": G / (fisher_ms * 1e-3),
               "bound": "hbm", "achieved": fisher_bytes / (fisher_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",

@@ -57,6 +57,20 @@ static inline unsigned sb_emul_vmaxs2(unsigned a, unsigned b)
 }
 #define SB_VADD2(a, b) sb_emul_vadd2(a, b)
 #define SB_VMAXS2(a, b) sb_emul_vmaxs2(a, b)
+static inline unsigned sb_emul_brev(unsigned x)
+{
+    unsigned r = 0;
+    for (int i = 0; i < 32; ++i) r |= ((x >> i) & 1u) << (31 - i);
+    return r;
+}
+// prmt.b32 d, x, 0, 0xBB99 (PTX ISA, generic mode: selector msb = replicate the sign of the selected byte):
+// bytes 0-1 <- sign of byte 1 (bit 15), bytes 2-3 <- sign of byte 3 (bit 31)
+static inline unsigned sb_emul_sign_mask2(unsigned x)
+{
+    return ((x >> 15) & 1u ? 0x0000FFFFu : 0u) | ((x >> 31) & 1u ? 0xFFFF0000u : 0u);
+}
+#define SB_BREV(x) sb_emul_brev(x)
+#define SB_SIGN_MASK2(x) sb_emul_sign_mask2(x)
 #else
 #define SB_CONST __constant__
 #define SB_LDG(p) __ldg(p)
@@ -64,6 +78,15 @@ static inline unsigned sb_emul_vmaxs2(unsigned a, unsigned b)
 #define SB_SHARED_STACK(name) extern __shared__ __align__(16) int name[]
 #define SB_VADD2(a, b) __vadd2(a, b)
 #define SB_VMAXS2(a, b) __vmaxs2(a, b)
+#define SB_BREV(x) __brev(x)
+// not __byte_perm: it keeps only 3 bits of each selector nibble (the SASS showed PRMT 0x3311, plain byte copies)
+__device__ __forceinline__ unsigned sb_sign_mask2(unsigned x)
+{
+    unsigned d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(0u), "r"(0xBB99u));
+    return d;
+}
+#define SB_SIGN_MASK2(x) sb_sign_mask2(x)
 #endif
 
 #ifndef SB_WALK_THREADS
@@ -71,6 +94,12 @@ static inline unsigned sb_emul_vmaxs2(unsigned a, unsigned b)
 #endif
 #ifndef SB_WALK_MINBLOCKS
 #define SB_WALK_MINBLOCKS 5
+#endif
+// Experimental (tools/sweep_variants.py, not measured yet): gene windows kept bit-reversed, so that the
+// next leaf sits in bit 15 / bit 31 and its half-word mask is ONE PRMT (sign replication) instead of
+// LOP3 + IMAD; a consumed leaf is a left shift.  Same results; verified through the host emulation.
+#ifndef SB_WALK_PRMT
+#define SB_WALK_PRMT 0
 #endif
 constexpr int WALK_THREADS = SB_WALK_THREADS;
 constexpr int WALK_NEG = -(1 << 30);   // unreachable; keys stay < 2^28 (n_leaves <= 32766), so inv+inv >= INT_MIN
@@ -186,15 +215,21 @@ SB_CONST uint32_t c_labels[C_LABEL_WORDS];
 // per register, 16-bit keys), legal while the subtree has <= WALK_LIM16 leaves; "32" ops work
 // on the per-gene 32-bit accumulator A32.  The host compiler (engine.cu) switches mode with
 // WIDEN_A and the *W merge forms where a subtree outgrows 16 bits.
+// The most frequent ops of a typical tree are numbered so that the interpreter recognises each with
+// one bit test on the op word before it falls back to a jump table: B cherries = 2 | merge,
+// A pushes / cherries = 4 | push | 2 * cherry.
 constexpr int OP_END = 0,
-              OP_CHERRY_A16 = 1,        // A16 <- cherry, then `count` leaf updates
-              OP_PUSH_CHERRY_A16 = 2,   // push A16 first, then as OP_CHERRY_A16
-              OP_CHERRY_B16 = 3,        // B16 <- cherry, then `count` leaf updates
-              OP_CHERRY_B16_MERGE = 4,  // as OP_CHERRY_B16, then A16 <- combine(A16, B16)
-              OP_LEAF_A16 = 5, OP_MERGE_POP16 = 6, OP_WIDEN_A = 7, OP_LEAF_A32 = 8, OP_MERGE_A32_B16 = 9,
-              OP_PUSH32 = 10, OP_MERGE_POP32 = 11, OP_MERGE_POPW = 12, OP_PUSH16 = 13;
-// raw (pre-fusion) steps used only by the host compiler
-constexpr int RAW_LEAF_B16 = 14, RAW_MERGE_AB16 = 15;
+              OP_LEAF_A16 = 1,
+              OP_CHERRY_B16 = 2,        // B16 <- cherry, then `count` leaf updates
+              OP_CHERRY_B16_MERGE = 3,  // as OP_CHERRY_B16, then A16 <- combine(A16, B16)
+              OP_PUSH16 = 5,            // spill A16 to the stack
+              OP_CHERRY_A16 = 6,        // A16 <- cherry, then `count` leaf updates
+              OP_PUSH_CHERRY_A16 = 7,   // push A16 first, then as OP_CHERRY_A16
+              OP_MERGE_POP16 = 8,
+              OP_WIDEN_A = 9, OP_LEAF_A32 = 10, OP_MERGE_A32_B16 = 11, OP_PUSH32 = 12, OP_MERGE_POP32 = 13,
+              OP_MERGE_POPW = 14;
+// raw (pre-fusion) steps used only by the host compiler (never stored in a program)
+constexpr int RAW_LEAF_B16 = 16, RAW_MERGE_AB16 = 17;
 constexpr int OP_TYPE_BITS = 4, OP_MAX_COUNT = 4095;
 constexpr int PERMS_PER_ITEM_MAX = 4;      // labellings walked per block: 4, 2 or 1 (one byte of hit flags per gene)
 // 16-bit keys: (pairs << 6) + x with pairs, x <= 63  ->  subtrees of at most 127 leaves.
@@ -298,6 +333,20 @@ SB_DEV unsigned max5_16(const unsigned v[5])
     return __vimax3_s16x2(__vimax3_s16x2(v[0], v[1], v[2]), v[3], v[4]);
 }
 
+// node of a trait-positive leaf (gene mask mB) and a trait-negative leaf (gene mask mb)
+template <bool DUAL>
+SB_DEV void walk_cherry16_mixed(WalkState16 &o, unsigned mB, unsigned mb, const Bonus16 &b)
+{
+    const unsigned N = NEG16x2;
+    o.p[0] = N & ~mB;               // AB
+    o.p[1] = N & ~mb;               // Ab
+    o.p[2] = N & mB;                // aB
+    o.p[3] = N & mb;                // ab
+    const unsigned pm = mB & ~mb, am = ~mB & mb;   // AB+ab supports, aB+Ab opposes
+    o.p[4] = sel2(pm, b.ps, sel2(am, b.po, N));
+    if constexpr (DUAL) o.a[4] = sel2(pm, b.as_, sel2(am, b.ao, N));
+}
+
 // o[q] <- node of two leaves, for every gene pair q of the thread.  m1, m2: half-word masks of the two
 // leaves' gene bits; t12 = t1 + 2*t2, the leaves' trait bits (block-uniform: one branch for all pairs)
 template <int NPAIR, bool DUAL>
@@ -323,19 +372,12 @@ SB_DEV void walk_cherry16(WalkState16 (&o)[NPAIR], const unsigned (&m1)[NPAIR], 
             o[q].p[3] = N & (m1[q] & m2[q]);
             o[q].p[4] = N;
         }
+    } else if (t12 == 1u) {         // first leaf trait-positive, second trait-negative
+#pragma unroll
+        for (int q = 0; q < NPAIR; ++q) walk_cherry16_mixed<DUAL>(o[q], m1[q], m2[q], b[q]);
     } else {
 #pragma unroll
-        for (int q = 0; q < NPAIR; ++q) {
-            const unsigned mB = (t12 == 1u) ? m1[q] : m2[q];   // gene mask of the trait-positive leaf
-            const unsigned mb = (t12 == 1u) ? m2[q] : m1[q];   // gene mask of the trait-negative leaf
-            o[q].p[0] = N & ~mB;            // AB
-            o[q].p[1] = N & ~mb;            // Ab
-            o[q].p[2] = N & mB;             // aB
-            o[q].p[3] = N & mb;             // ab
-            const unsigned pm = mB & ~mb, am = ~mB & mb;       // AB+ab supports, aB+Ab opposes
-            o[q].p[4] = sel2(pm, b[q].ps, sel2(am, b[q].po, N));
-            if constexpr (DUAL) o[q].a[4] = sel2(pm, b[q].as_, sel2(am, b[q].ao, N));
-        }
+        for (int q = 0; q < NPAIR; ++q) walk_cherry16_mixed<DUAL>(o[q], m2[q], m1[q], b[q]);
     }
     if constexpr (DUAL) {
 #pragma unroll
@@ -489,8 +531,8 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR
             lw = c_labels[lab_off + w_];                                                       \
             _Pragma("unroll") for (int q_ = 0; q_ < NPAIR; ++q_) {                             \
                 const uint32_t a_ = gnext[2 * q_], b_ = gnext[2 * q_ + 1];                     \
-                gx[q_] = (a_ & 0xFFFFu) | (b_ << 16);                                          \
-                gy[q_] = (a_ >> 16) | (b_ & 0xFFFF0000u);                                      \
+                gx[q_] = SB_WINDOW_X(a_, b_);                                                  \
+                gy[q_] = SB_WINDOW_Y(a_, b_);                                                  \
             }                                                                                  \
             if (w_ + 1 < W32p) {                                                               \
                 _Pragma("unroll") for (int k_ = 0; k_ < NP; ++k_)                              \
@@ -502,9 +544,21 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR
         ++win;                                                                                 \
         room = 16;                                                                             \
     } while (0)
-    // half-word mask of pair q's gene bits at stream offset o (0 = the next leaf): 0xFFFF per half whose gene is present
+    // SB_PAIR_MASK: half-word mask of pair q's gene bits at stream offset o (0 = the next leaf), 0xFFFF per
+    // half whose gene is present; SB_CONSUME: drop n leaves from pair q's window
+#if SB_WALK_PRMT
+#define SB_WINDOW_X(a_, b_) ((SB_BREV(a_) >> 16) | (SB_BREV(b_) & 0xFFFF0000u))
+#define SB_WINDOW_Y(a_, b_) ((SB_BREV(a_) & 0xFFFFu) | (SB_BREV(b_) << 16))
+#define SB_PAIR_MASK(q, o) SB_SIGN_MASK2(gx[q] << (o))
+#define SB_GENE_BIT(k) (((gx[(k) >> 1] >> (((k) & 1) * 16 + 15)) & 1u) != 0)
+#define SB_CONSUME(q, n) gx[q] <<= (n)
+#else
+#define SB_WINDOW_X(a_, b_) (((a_) & 0xFFFFu) | ((b_) << 16))
+#define SB_WINDOW_Y(a_, b_) (((a_) >> 16) | ((b_) & 0xFFFF0000u))
 #define SB_PAIR_MASK(q, o) (((gx[q] >> (o)) & 0x00010001u) * 0xFFFFu)
 #define SB_GENE_BIT(k) (((gx[(k) >> 1] >> (((k) & 1) * 16)) & 1u) != 0)
+#define SB_CONSUME(q, n) gx[q] >>= (n)
+#endif
     // one leaf update of the packed / the 32-bit accumulators; `room` is the caller's business
 #define SB_LEAF_STEP16(ACC)                                                                    \
     do {                                                                                       \
@@ -517,7 +571,7 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR
             _Pragma("unroll") for (int q = 0; q < NPAIR; ++q)                                  \
                 walk_leaf16<0, DUAL>(ACC[q], SB_PAIR_MASK(q, 0), b16c[q]);                     \
         }                                                                                      \
-        _Pragma("unroll") for (int q = 0; q < NPAIR; ++q) gx[q] >>= 1;                         \
+        _Pragma("unroll") for (int q = 0; q < NPAIR; ++q) SB_CONSUME(q, 1);                    \
     } while (0)
 #define SB_LEAF_STEP32()                                                                       \
     do {                                                                                       \
@@ -530,7 +584,7 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR
             _Pragma("unroll") for (int k = 0; k < NP; ++k)                                     \
                 walk_leaf<0, DUAL>(acc[k], SB_GENE_BIT(k), b32[k]);                            \
         }                                                                                      \
-        _Pragma("unroll") for (int q = 0; q < NPAIR; ++q) gx[q] >>= 1;                         \
+        _Pragma("unroll") for (int q = 0; q < NPAIR; ++q) SB_CONSUME(q, 1);                    \
     } while (0)
     // `cnt` leaf updates
 #define SB_LEAF_RUN(STEP)                                                                      \
@@ -559,7 +613,7 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR
             _Pragma("unroll") for (int q = 0; q < NPAIR; ++q) {                                \
                 m1[q] = SB_PAIR_MASK(q, 0);                                                    \
                 m2[q] = SB_PAIR_MASK(q, 1);                                                    \
-                gx[q] >>= 2;                                                                   \
+                SB_CONSUME(q, 2);                                                              \
             }                                                                                  \
             walk_cherry16<NPAIR, DUAL>(ACC, m1, m2, t12, b16c);                                \
             _Pragma("unroll 1") for (int i = 0; i < cnt; ++i) { SB_LEAF_STEP16(ACC); }         \
@@ -569,14 +623,14 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR
             lw >>= 1;                                                                          \
             _Pragma("unroll") for (int q = 0; q < NPAIR; ++q) {                                \
                 m1[q] = SB_PAIR_MASK(q, 0);                                                    \
-                gx[q] >>= 1;                                                                   \
+                SB_CONSUME(q, 1);                                                              \
             }                                                                                  \
             if (--room == 0) SB_OPEN_WINDOW();                                                 \
             t12 |= (lw & 1u) << 1;                                                             \
             lw >>= 1;                                                                          \
             _Pragma("unroll") for (int q = 0; q < NPAIR; ++q) {                                \
                 m2[q] = SB_PAIR_MASK(q, 0);                                                    \
-                gx[q] >>= 1;                                                                   \
+                SB_CONSUME(q, 1);                                                              \
             }                                                                                  \
             --room;                                                                            \
             walk_cherry16<NPAIR, DUAL>(ACC, m1, m2, t12, b16c);                                \
@@ -598,36 +652,31 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR
     for (;;) {
         const uint32_t op = c_ops[pc++];
         const int type = op & 15, cnt = op >> OP_TYPE_BITS;
-        switch (type) {
-        case OP_LEAF_A16:
-            SB_LEAF_RUN(SB_LEAF_STEP16(a16));
-            break;
-        case OP_PUSH16:
-        case OP_PUSH_CHERRY_A16:
-#pragma unroll
-            for (int q = 0; q < NPAIR; ++q) {
-                int *s = stk + (sp + q * EW) * T;
-#pragma unroll
-                for (int c = 0; c < 5; ++c) {
-                    s[c * T] = (int)a16[q].p[c];
-                    if constexpr (DUAL) s[(5 + c) * T] = (int)a16[q].a[c];
-                }
-            }
-            sp += EW * NPAIR;
-            if (type == OP_PUSH16) break;
-            // fall through
-        case OP_CHERRY_A16:
-            SB_CHERRY_RUN16(a16);
-            break;
-        case OP_CHERRY_B16:
-        case OP_CHERRY_B16_MERGE:
+        if (((op ^ (uint32_t)OP_CHERRY_B16) & 14u) == 0) {
             SB_CHERRY_RUN16(b16);
-            if (type == OP_CHERRY_B16_MERGE) {
+            if (op & 1u) {
 #pragma unroll
                 for (int q = 0; q < NPAIR; ++q) walk_merge16<DUAL>(b16[q], a16[q], b16c[q]);
             }
-            break;
-        case OP_MERGE_POP16:
+            continue;
+        }
+        if ((op & 12u) == 4u) {
+            if (op & 1u) {
+#pragma unroll
+                for (int q = 0; q < NPAIR; ++q) {
+                    int *s = stk + (sp + q * EW) * T;
+#pragma unroll
+                    for (int c = 0; c < 5; ++c) {
+                        s[c * T] = (int)a16[q].p[c];
+                        if constexpr (DUAL) s[(5 + c) * T] = (int)a16[q].a[c];
+                    }
+                }
+                sp += EW * NPAIR;
+            }
+            if (op & 2u) SB_CHERRY_RUN16(a16);
+            continue;
+        }
+        if (type == OP_MERGE_POP16) {
 #pragma unroll 1
             for (int i = 0; i < cnt; ++i) {
                 sp -= EW * NPAIR;
@@ -638,7 +687,13 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR
                     walk_merge16<DUAL>(L, a16[q], b16c[q]);
                 }
             }
-            break;
+            continue;
+        }
+        if (type == OP_LEAF_A16) {
+            SB_LEAF_RUN(SB_LEAF_STEP16(a16));
+            continue;
+        }
+        switch (type) {
         case OP_WIDEN_A:
 #pragma unroll
             for (int q = 0; q < NPAIR; ++q) walk_widen<DUAL>(a16[q], acc[2 * q], acc[2 * q + 1], scale);
@@ -704,8 +759,11 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR
         }
     }
 #undef SB_OPEN_WINDOW
+#undef SB_WINDOW_X
+#undef SB_WINDOW_Y
 #undef SB_PAIR_MASK
 #undef SB_GENE_BIT
+#undef SB_CONSUME
 #undef SB_LEAF_STEP16
 #undef SB_LEAF_STEP32
 #undef SB_LEAF_RUN

@@ -21,23 +21,34 @@ LIB = os.path.join(HERE, "libwalk_emul.so")
 CSRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scoary_b200", "csrc")
 
 
-@pytest.fixture(scope="module")
-def emul():
+def _build_walk_emul(lib_path, extra=()):
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         pytest.skip("nvcc not available")
     deps = [SRC, os.path.join(CSRC, "walk.cuh"), os.path.join(CSRC, "common.cuh")]
-    if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(d) for d in deps):
+    if not os.path.exists(lib_path) or os.path.getmtime(lib_path) < max(os.path.getmtime(d) for d in deps):
         cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
         subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "-Xcompiler", "-fPIC",
-                        "-ccbin", cxx, "-shared", "-o", LIB, SRC], check=True)
-    lib = ctypes.CDLL(LIB)
+                        "-ccbin", cxx, *extra, "-shared", "-o", lib_path, SRC], check=True)
+    lib = ctypes.CDLL(lib_path)
     lib.emul_pairs.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
                                ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
     lib.emul_permute.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                                  ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                  ctypes.c_void_p, ctypes.c_void_p]
     return lib
+
+
+@pytest.fixture(scope="module")
+def emul():
+    return _build_walk_emul(LIB)
+
+
+@pytest.fixture(scope="module")
+def emul_prmt():
+    """the experimental -DSB_WALK_PRMT=1 build of the same source (bit-reversed gene windows, masks by PRMT sign
+    replication -- emulated here from the PTX definition of prmt.b32)"""
+    return _build_walk_emul(os.path.join(HERE, "libwalk_emul_prmt.so"), ("-DSB_WALK_PRMT=1",))
 
 
 def _ptr(a):
@@ -86,23 +97,18 @@ CASES = [(2, 5, False), (3, 9, False), (5, 40, False), (16, 70, False), (100, 13
          (5000, 40, False), (10000, 6, False), (20000, 5, True)]      # C3 / C4 isolate counts, a 19 999-level comb
 
 
-@pytest.mark.parametrize("n,G,comb", CASES)
-def test_pairs_kernel_source_on_the_host(emul, n, G, comb):
+def _check_pairs(lib, n, G, comb):
     c = _setup(n, G, 100 + n, comb)
     lab0 = _pack_walk_order(c["lab"][None, :], c["order"], c["W32p"])[0]
     pairs = np.full((G, 3), -7, dtype=np.int32)
-    rc = emul.emul_pairs(_ptr(c["ops"]), len(c["ops"]), _ptr(lab0), _ptr(c["genesT"]), c["Gs"], G, c["W32p"], c["shift"],
-                         c["units"], _ptr(pairs))
+    rc = lib.emul_pairs(_ptr(c["ops"]), len(c["ops"]), _ptr(lab0), _ptr(c["genesT"]), c["Gs"], G, c["W32p"], c["shift"],
+                        c["units"], _ptr(pairs))
     assert rc == 0
     ref = O.permute(c["left"], c["right"], c["m"], c["lab"], P=0)["pairs"]
     assert np.array_equal(pairs, ref)
 
 
-@pytest.mark.parametrize("n,G,comb", CASES)
-@pytest.mark.parametrize("ppi", [1, 2, 4])
-def test_permute_kernel_source_on_the_host(emul, n, G, comb, ppi):
-    if ppi != 4 and n > 200:
-        pytest.skip("one ppi is enough for the large trees")
+def _check_permute(lib, n, G, comb, ppi):
     c = _setup(n, G, 200 + n, comb)
     P, seed = 9, 77
     ref = O.permute(c["left"], c["right"], c["m"], c["lab"], P=P, seed=seed, trait=0, want_hits=True)
@@ -111,14 +117,34 @@ def test_permute_kernel_source_on_the_host(emul, n, G, comb, ppi):
     n_chunks = (P + ppi - 1) // ppi
     hits = np.zeros((n_chunks, G), dtype=np.uint8)
     unperm = np.ascontiguousarray(ref["pairs"], dtype=np.int32)
-    rc = emul.emul_permute(_ptr(c["ops"]), len(c["ops"]), _ptr(labelsW), P, ppi, _ptr(c["genesT"]), c["Gs"], G, c["W32p"],
-                           c["shift"], c["units"], _ptr(unperm), _ptr(hits))
+    rc = lib.emul_permute(_ptr(c["ops"]), len(c["ops"]), _ptr(labelsW), P, ppi, _ptr(c["genesT"]), c["Gs"], G, c["W32p"],
+                          c["shift"], c["units"], _ptr(unperm), _ptr(hits))
     assert rc == 0
     got = np.zeros((G, P), dtype=np.uint8)
     for p in range(P):
         got[:, p] = (hits[p // ppi] >> (p % ppi)) & 1
     assert np.array_equal(got, ref["hits"])
     assert np.array_equal(got.sum(axis=1), ref["r"])
+
+
+@pytest.mark.parametrize("n,G,comb", CASES)
+def test_pairs_kernel_source_on_the_host(emul, n, G, comb):
+    _check_pairs(emul, n, G, comb)
+
+
+@pytest.mark.parametrize("n,G,comb", CASES)
+@pytest.mark.parametrize("ppi", [1, 2, 4])
+def test_permute_kernel_source_on_the_host(emul, n, G, comb, ppi):
+    if ppi != 4 and n > 200:
+        pytest.skip("one ppi is enough for the large trees")
+    _check_permute(emul, n, G, comb, ppi)
+
+
+@pytest.mark.parametrize("n,G,comb", [(5, 40, False), (129, 600, False), (150, 520, True), (1000, 20, False),
+                                      (5000, 12, False)])
+def test_prmt_variant_of_the_walk_kernels_on_the_host(emul_prmt, n, G, comb):
+    _check_pairs(emul_prmt, n, G, comb)
+    _check_permute(emul_prmt, n, G, comb, 4)
 
 
 # ---------------------------------------------------------------------------- Fisher (csrc/fisher.cuh) on the host

@@ -11,9 +11,9 @@ from oracle import oracle as O
 from scoary_b200 import _lib, synth
 from scoary_b200 import tree as treemod
 
-OPS = {0: "END", 1: "CHERRY_A16", 2: "PUSH_CHERRY_A16", 3: "CHERRY_B16", 4: "CHERRY_B16_MERGE", 5: "LEAF_A16",
-       6: "MERGE_POP16", 7: "WIDEN_A", 8: "LEAF_A32", 9: "MERGE_A32_B16", 10: "PUSH32", 11: "MERGE_POP32",
-       12: "MERGE_POPW", 13: "PUSH16"}
+OPS = {0: "END", 1: "LEAF_A16", 2: "CHERRY_B16", 3: "CHERRY_B16_MERGE", 5: "PUSH16", 6: "CHERRY_A16",
+       7: "PUSH_CHERRY_A16", 8: "MERGE_POP16", 9: "WIDEN_A", 10: "LEAF_A32", 11: "MERGE_A32_B16", 12: "PUSH32",
+       13: "MERGE_POP32", 14: "MERGE_POPW"}      # csrc/walk.cuh
 NEG = -(1 << 30)
 
 

@@ -67,6 +67,7 @@ def main():
     ap.add_argument("--json")
     ap.add_argument("--profile", type=int, default=0, help="print the N basic blocks with the most executed instructions")
     a = ap.parse_args()
+    os.environ["SCOARY_B200_LIB"] = os.path.abspath(a.lib)      # the tree compiler of the library being modelled
 
     ops, labelsW, W32p, shift = workload(a.isolates, a.seed, a.perms, a.perm_seed)
     const3 = bytearray(C_OPS_BYTES + 4 * labelsW.size)

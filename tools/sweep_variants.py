@@ -14,7 +14,11 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VDIR = os.path.join(ROOT, "variants")
+# name: compiler switches, or (git revision, switches) to build the kernels as they were at that revision
 VARIANTS = {
+    "r1_profiled": ("5af1521", ""),           # the K5 that profiles/r1_ncu_walk_permute.txt was captured on
+    "prmt": "-DSB_WALK_PRMT=1",               # gene-bit masks by PRMT sign replication (tools/k5_model.py: -3.4 % instructions)
+    "prmt_npair3_mb3": "-DSB_WALK_PRMT=1 -DSB_WALK_NPAIR=3 -DSB_WALK_MINBLOCKS=3",
     "minblocks4": "-DSB_WALK_MINBLOCKS=4",
     "minblocks6": "-DSB_WALK_MINBLOCKS=6",
     "threads96_mb6": "-DSB_WALK_THREADS=96 -DSB_WALK_MINBLOCKS=6",
@@ -31,11 +35,19 @@ VARIANTS = {
 
 
 def build():
+    import tempfile
     os.makedirs(VDIR, exist_ok=True)
-    for name, flags in VARIANTS.items():
+    for name, spec in VARIANTS.items():
         out = os.path.join(VDIR, name + ".so")
-        subprocess.run(["make", "-B", "-C", os.path.join(ROOT, "scoary_b200", "csrc"), "OUT=" + out, "EXTRA=" + flags],
-                       check=True, stdout=subprocess.DEVNULL)
+        rev, flags = spec if isinstance(spec, tuple) else (None, spec)
+        with tempfile.TemporaryDirectory() as tmp:
+            src = os.path.join(ROOT, "scoary_b200", "csrc")
+            if rev:                                   # the sources of that revision, built out of tree
+                tar = subprocess.run(["git", "-C", ROOT, "archive", rev, "scoary_b200/csrc", "include"], check=True,
+                                     capture_output=True).stdout
+                subprocess.run(["tar", "-x", "-C", tmp], input=tar, check=True)
+                src = os.path.join(tmp, "scoary_b200", "csrc")
+            subprocess.run(["make", "-B", "-C", src, "OUT=" + out, "EXTRA=" + flags], check=True, stdout=subprocess.DEVNULL)
         print("built", out)
 
 
