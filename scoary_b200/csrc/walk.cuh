@@ -508,7 +508,7 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR
     const int K = 1 << A.shift;
     const int scale = K - (1 << WALK_SH16);
     WalkState16 a16[NPAIR], b16[NPAIR];
-    int sp = 0, pc = 0;                // sp counts 32-bit words per thread
+    int sp = 0, pc = 0;                // sp counts 32-bit words per thread; pc is a BYTE offset into c_ops
     int room = 0, win = 0;             // leaves left in the current 16-leaf window; windows opened so far
     // gx[q]: the current 16-leaf window of pair q's two genes (gene 2q in bits 0..15, gene 2q+1 in
     // bits 16..31, consumed from bit 0 / bit 16); gy[q]: the following 16 leaves; gnext: prefetch
@@ -650,7 +650,8 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR
         }                                                                                      \
     } while (0)
     for (;;) {
-        const uint32_t op = c_ops[pc++];
+        const uint32_t op = *reinterpret_cast<const uint16_t *>(reinterpret_cast<const char *>(c_ops) + pc);
+        pc += 2;
         const int type = op & 15, cnt = op >> OP_TYPE_BITS;
         if (((op ^ (uint32_t)OP_CHERRY_B16) & 14u) == 0) {
             SB_CHERRY_RUN16(b16);

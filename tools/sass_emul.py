@@ -118,6 +118,7 @@ class Machine:
         self.local = {}               # spill slots, keyed by the address text ([R1+0x18])
         self.counts = [0] * len(instrs)
         self.assumed = {}             # address -> times a per-thread (non-uniform) branch was assumed not taken
+        self.max_assumed = 8          # per address: the result stores run once per walk row, never in a hot loop
 
     # ---- operand access
     def const(self, bank, off, size=4):
@@ -249,6 +250,9 @@ class Machine:
                 # a per-thread predicate (the `active` lane flags around the result stores): the warp runs the
                 # guarded block whenever any lane is active, so count it as executed; reported by the caller
                 self.assumed[ins.addr] = self.assumed.get(ins.addr, 0) + 1
+                if self.assumed[ins.addr] > self.max_assumed:
+                    raise Unknown("branch at %x keeps depending on a value the interpreter does not track: %s" % (
+                        ins.addr, ins.text))
                 return i + 1
             if not on:
                 return i + 1
