@@ -119,6 +119,8 @@ class Machine:
         self.counts = [0] * len(instrs)
         self.assumed = {}             # address -> times a per-thread (non-uniform) branch was assumed not taken
         self.max_assumed = 8          # per address: the result stores run once per walk row, never in a hot loop
+        self.why = {}                 # register / predicate -> the instruction that made it unknown (diagnostics)
+        self.cur = None
 
     # ---- operand access
     def const(self, bank, off, size=4):
@@ -192,12 +194,16 @@ class Machine:
     def setp(self, a, v):
         if a in ("PT", "UPT"):
             return
+        if v is None and self.cur is not None:
+            self.why[a] = "%x: %s" % (self.cur.addr, self.cur.text)
         (self.UP if a.startswith("UP") else self.P)[a] = v
 
     def setr(self, a, v):
         a = a.replace(".reuse", "")
         if a in ("RZ", "URZ"):
             return
+        if v is None and self.cur is not None:
+            self.why[a] = "%x: %s" % (self.cur.addr, self.cur.text)
         (self.UR if a.startswith("UR") else self.R)[a] = None if v is None else v & M32
 
     def pair(self, a):
@@ -238,6 +244,7 @@ class Machine:
     def step(self, i):
         """execute instruction i; return the index of the next one (None = exit)"""
         ins = self.instrs[i]
+        self.cur = ins
         self.counts[i] += 1
         op, mods, a = ins.op, ins.mods, ins.args
         on = True
@@ -251,8 +258,8 @@ class Machine:
                 # guarded block whenever any lane is active, so count it as executed; reported by the caller
                 self.assumed[ins.addr] = self.assumed.get(ins.addr, 0) + 1
                 if self.assumed[ins.addr] > self.max_assumed:
-                    raise Unknown("branch at %x keeps depending on a value the interpreter does not track: %s" % (
-                        ins.addr, ins.text))
+                    raise Unknown("branch at %x keeps depending on a value the interpreter does not track: %s\n  %s" % (
+                        ins.addr, ins.text, self.explain(ins.guard.lstrip("!"))))
                 return i + 1
             if not on:
                 return i + 1
@@ -295,6 +302,10 @@ class Machine:
         if ins.op in ("STS", "STG", "BSSY", "BSYNC", "NOP", "BAR", "WARPSYNC", "DEPBAR", "ST"):
             return
         wide = "WIDE" in ins.mods or "64" in ins.mods
+        if ins.op in ("ISETP", "UISETP", "PLOP3", "FSETP", "DSETP", "UPLOP3"):     # predicate destinations only
+            self.setp(ins.args[0], None)
+            self.setp(ins.args[1], None)
+            return
         seen_reg = False
         for arg in ins.args:
             arg = arg.replace(".reuse", "")
@@ -319,6 +330,10 @@ class Machine:
 
         if op in ("UMOV", "MOV"):
             self.setr(a[0], V(a[1]))
+        elif op == "CS2R":
+            if a[1] != "SRZ":
+                raise Unsupported("CS2R " + a[1])
+            (self.setr if "32" in mods else self.setpair)(a[0], 0)
         elif op == "STL":
             self.local[a[0]] = V(a[1])
         elif op == "LDL":
@@ -444,6 +459,19 @@ class Machine:
             self.setr(a[0], x + y)
         else:
             raise Unsupported(op)
+
+    def explain(self, name, depth=6):
+        """why `name` is unknown: the chain of instructions that lost track of it"""
+        out = []
+        while depth and name in self.why:
+            out.append("%s <- %s" % (name, self.why[name]))
+            regs = [r.replace(".reuse", "").lstrip("-~!") for r in re.findall(r"!?U?[RP]\d+(?:\.reuse)?", self.why[name].split(":", 1)[1])]
+            nxt = [r for r in regs[1:] if r != name and (self.R.get(r, 0) is None or self.UR.get(r, 0) is None or
+                                                          self.P.get(r, 0) is None or self.UP.get(r, 0) is None)]
+            if not nxt:
+                break
+            name, depth = nxt[0], depth - 1
+        return "\n  ".join(out)
 
     def run(self, max_steps=50_000_000):
         i, n = 0, 0
