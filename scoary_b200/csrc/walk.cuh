@@ -616,7 +616,10 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR
                 SB_CONSUME(q, 2);                                                              \
             }                                                                                  \
             walk_cherry16<NPAIR, DUAL>(ACC, m1, m2, t12, b16c);                                \
-            _Pragma("unroll 1") for (int i = 0; i < cnt; ++i) { SB_LEAF_STEP16(ACC); }         \
+            if (cnt) {                                                                         \
+                int i = cnt;                                                                   \
+                _Pragma("unroll 1") do { SB_LEAF_STEP16(ACC); } while (--i);                   \
+            }                                                                                  \
         } else {                                                                               \
             if (room == 0) SB_OPEN_WINDOW();                                                   \
             t12 = lw & 1u;                                                                     \

@@ -24,6 +24,7 @@ VARIANTS = {
     "threads96_mb6": "-DSB_WALK_THREADS=96 -DSB_WALK_MINBLOCKS=6",
     "threads64_mb10": "-DSB_WALK_THREADS=64 -DSB_WALK_MINBLOCKS=10",
     "threads256_mb2": "-DSB_WALK_THREADS=256 -DSB_WALK_MINBLOCKS=2",
+    "threads320_mb2": "-DSB_WALK_THREADS=320 -DSB_WALK_MINBLOCKS=2",   # 2 x 10 warps: fewer program positions per SM (L0 I-cache)
     "npair1_mb8": "-DSB_WALK_NPAIR=1 -DSB_WALK_MINBLOCKS=8",
     "npair3_mb3": "-DSB_WALK_NPAIR=3 -DSB_WALK_MINBLOCKS=3",
     "fisher_v2_512": "-DSB_FISHER_V2=1 -DSB_FISHER2_THREADS=512",     # csrc/fisher2.cuh: four genes per warp
