@@ -1,0 +1,41 @@
+#!/usr/bin/env bash
+# One GPU call that answers everything a kernel change needs answered (run under gpurun, one GPU):
+#
+#   python tools/sweep_variants.py build                      # here, no GPU: variants/*.so travel with the snapshot
+#   gpurun --timeout 1500 -- 'bash tools/gpu_session.sh r2a'  # tag names the artefacts under gpurun_out/
+#
+# 1. pytest -m gpu                    parity first: nothing below matters if it is red
+# 2. tools/sweep_variants.py run      every variant library on the C3 shape, with a checksum against the product library
+# 3. ncu launch list                  of `bench.py --steps 2 --warmup 3` (kernel shares of a step)
+# 4. ncu --set full                   one walk_permute_kernel launch and one fisher_kernel launch of tools/probe.py
+# 5. bench.py                         the number itself (never taken under a profiler), clocks sampled by bench.py
+# Each step has its own timeout so a hang cannot eat the box; later steps still run when an earlier one fails.
+set -u
+tag="${1:-session}"
+out="gpurun_out/${tag}"
+mkdir -p "$out"
+cd "$(dirname "$0")/.."
+
+step() {   # step <seconds> <log> <command...>
+    local t="$1" log="$2"; shift 2
+    echo "== $* (limit ${t}s)" | tee -a "$out/session.log"
+    timeout "$t" "$@" > "$out/$log" 2>&1
+    echo "   exit $? ; tail:" | tee -a "$out/session.log"
+    tail -n 6 "$out/$log" | tee -a "$out/session.log"
+}
+
+step 900 pytest_gpu.log python -m pytest tests -m gpu -x -q
+step 600 sweep.log python tools/sweep_variants.py run
+step 300 launches.log ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
+    --log-file "$out/launches.csv" python bench.py --steps 2 --warmup 3 --no-cpu-baseline
+step 420 ncu_walk.log ncu --set full --clock-control none --import-source on -k regex:walk_permute -c 1 \
+    -o "$out/prof_walk" -f python tools/probe.py --perms 60
+step 300 ncu_fisher.log ncu --set full --clock-control none --import-source on -k regex:fisher_kernel -c 1 \
+    -o "$out/prof_fisher" -f python tools/probe.py --perms 4
+for rep in "$out"/prof_walk.ncu-rep "$out"/prof_fisher.ncu-rep; do
+    [ -f "$rep" ] && ncu -i "$rep" --page raw --csv > "${rep%.ncu-rep}.raw.csv" 2>/dev/null
+done
+step 600 bench.log python bench.py
+step 300 bench_north_star.log python bench.py --workload north_star --steps 2 --no-cpu-baseline
+grep -h '^{' "$out/bench.log" "$out/bench_north_star.log" > "$out/bench_lines.json" 2>/dev/null
+echo "== done" | tee -a "$out/session.log"
