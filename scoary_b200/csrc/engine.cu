@@ -516,10 +516,12 @@ int launch_fisher(sb_ctx *ctx, int32_t t, int32_t *d_counts, double *d_p, uint64
     return SB_OK;
 }
 
-// DP stack: s.depth units per gene pair; a unit is 10 words with both passes (K4), 5 with one (K5)
+// DP stack: s.depth units per gene pair (and per labelling walked in lockstep, K5 only); a unit is 10 words
+// with both passes (K4), 5 with one (K5)
 size_t walk_smem_bytes(const TraitSlot &s, bool dual)
 {
-    return sizeof(int) * (dual ? 10 : 5) * (size_t)std::max(1, s.depth) * sb::WALK_THREADS * sb::WALK_NPAIR;
+    return sizeof(int) * (dual ? 10 : 5) * (size_t)std::max(1, s.depth) * sb::WALK_THREADS * sb::WALK_NPAIR *
+           (dual ? 1 : sb::WALK_NLAB);
 }
 
 void fill_walk_args(const TraitSlot &s, sb::WalkArgs &A, const int64_t *d_gene_idx, int64_t S)
@@ -595,8 +597,8 @@ int launch_permute(sb_ctx *ctx, int32_t t, const int64_t *d_gene_idx, int64_t S,
     const int label_cap = (sb::C_LABEL_WORDS / s.W32p) / sb::PERMS_PER_ITEM_MAX * sb::PERMS_PER_ITEM_MAX;
     const int64_t tiles_all = (S + (int64_t)sb::WALK_THREADS * sb::WALK_NP - 1) / ((int64_t)sb::WALK_THREADS * sb::WALK_NP);
     int ppi = sb::PERMS_PER_ITEM_MAX;
-    while (ppi > 1 && tiles_all * ((std::min(label_cap, P) + ppi - 1) / ppi) < 2LL * 7 * ctx->sm_count) ppi /= 2;
-    if (early_stop) ppi = 1;   // later rounds walk few genes: one labelling per block keeps every SM busy
+    while (ppi > sb::WALK_NLAB && tiles_all * ((std::min(label_cap, P) + ppi - 1) / ppi) < 2LL * 7 * ctx->sm_count) ppi /= 2;
+    if (early_stop) ppi = sb::WALK_NLAB;   // later rounds walk few genes: the fewest labellings per block keep every SM busy
     const int n_chunks = (P + ppi - 1) / ppi;
     int perms_per_launch = label_cap;
     const int n_launches = (P + perms_per_launch - 1) / perms_per_launch;

@@ -350,7 +350,7 @@ SB_DEV void walk_cherry16_mixed(WalkState16 &o, unsigned mB, unsigned mb, const 
 // o[q] <- node of two leaves, for every gene pair q of the thread.  m1, m2: half-word masks of the two
 // leaves' gene bits; t12 = t1 + 2*t2, the leaves' trait bits (block-uniform: one branch for all pairs)
 template <int NPAIR, bool DUAL>
-SB_DEV void walk_cherry16(WalkState16 (&o)[NPAIR], const unsigned (&m1)[NPAIR], const unsigned (&m2)[NPAIR],
+SB_DEV void walk_cherry16(WalkState16 *o, const unsigned (&m1)[NPAIR], const unsigned (&m2)[NPAIR],
                           unsigned t12, const Bonus16 (&b)[NPAIR])
 {
     const unsigned N = NEG16x2;
@@ -491,28 +491,38 @@ struct WalkArgs {
 #endif
 constexpr int WALK_NPAIR = SB_WALK_NPAIR;   // gene pairs per thread
 constexpr int WALK_NP = 2 * WALK_NPAIR;     // genes per thread
+// Experimental (tools/sweep_variants.py, not measured yet): K5 walks SB_WALK_NLAB labellings of its genes in
+// lockstep.  The program decode, the leaf-stream bookkeeping and the gene-bit masks are then shared by the
+// labellings; only the DP arithmetic is per labelling (tools/k5_model.py counts the instructions).
+#ifndef SB_WALK_NLAB
+#define SB_WALK_NLAB 1
+#endif
+constexpr int WALK_NLAB = SB_WALK_NLAB;
 
-// NP = 2 * NPAIR simultaneous tree walks (this thread's genes, same labelling at
-// c_labels[lab_off ..]).  gcol[k] points at gene k's column of genesT; genes 2q and 2q+1 share
-// the packed accumulators of pair q.  Every branch is on block-uniform data (the program and
+// NP = 2 * NPAIR genes x NLAB labellings: simultaneous tree walks of this thread's genes under the
+// labellings at c_labels[lab_off[l] ..].  gcol[k] points at gene k's column of genesT; genes 2q and 2q+1
+// share the packed accumulators of pair q; state index s = l * NPAIR + q (32-bit: l * NP + k).  Every branch is on block-uniform data (the program and
 // the label bits); per-gene data only feeds selects.  The program always ends in 32-bit mode.
 // Stack entries take EW = 10 (DUAL) or 5 words per gene pair in 16-bit form, twice that in 32-bit form.
-template <int NPAIR, bool DUAL>
-SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR], int lab_off,
-                                          int *stk, WalkState (&acc)[2 * NPAIR], const Bonus32 (&b32)[2 * NPAIR],
-                                          const Bonus16 (&b16c)[NPAIR])
+template <int NPAIR, int NLAB, bool DUAL>
+SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR], const int (&lab_off)[NLAB],
+                                          int *stk, WalkState (&acc)[NLAB * 2 * NPAIR],
+                                          const Bonus32 (&b32)[2 * NPAIR], const Bonus16 (&b16c)[NPAIR])
 {
     constexpr int NP = 2 * NPAIR;
+    constexpr int NS = NLAB * NPAIR;   // packed states
     constexpr int T = WALK_THREADS;
     constexpr int EW = DUAL ? 10 : 5;
     const int K = 1 << A.shift;
     const int scale = K - (1 << WALK_SH16);
-    WalkState16 a16[NPAIR], b16[NPAIR];
+    WalkState16 a16[NS], b16[NS];
     int sp = 0, pc = 0;                // sp counts 32-bit words per thread; pc is a BYTE offset into c_ops
     int room = 0, win = 0;             // leaves left in the current 16-leaf window; windows opened so far
     // gx[q]: the current 16-leaf window of pair q's two genes (gene 2q in bits 0..15, gene 2q+1 in
     // bits 16..31, consumed from bit 0 / bit 16); gy[q]: the following 16 leaves; gnext: prefetch
-    uint32_t gx[NPAIR], gy[NPAIR], gnext[NP], lw = 0;
+    uint32_t gx[NPAIR], gy[NPAIR], gnext[NP], lw[NLAB];
+#pragma unroll
+    for (int l = 0; l < NLAB; ++l) lw[l] = 0;
 #pragma unroll
     for (int k = 0; k < NP; ++k) gnext[k] = SB_LDG(gcol[k]);
 #pragma unroll
@@ -528,7 +538,7 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR
     do {                                                                                       \
         if ((win & 1) == 0) {                                                                  \
             const int w_ = win >> 1;                                                           \
-            lw = c_labels[lab_off + w_];                                                       \
+            _Pragma("unroll") for (int l_ = 0; l_ < NLAB; ++l_) lw[l_] = c_labels[lab_off[l_] + w_]; \
             _Pragma("unroll") for (int q_ = 0; q_ < NPAIR; ++q_) {                             \
                 const uint32_t a_ = gnext[2 * q_], b_ = gnext[2 * q_ + 1];                     \
                 gx[q_] = SB_WINDOW_X(a_, b_);                                                  \
@@ -562,27 +572,33 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR
     // one leaf update of the packed / the 32-bit accumulators; `room` is the caller's business
 #define SB_LEAF_STEP16(ACC)                                                                    \
     do {                                                                                       \
-        const uint32_t t_ = lw & 1u;                                                           \
-        lw >>= 1;                                                                              \
-        if (t_) {                                                                              \
-            _Pragma("unroll") for (int q = 0; q < NPAIR; ++q)                                  \
-                walk_leaf16<1, DUAL>(ACC[q], SB_PAIR_MASK(q, 0), b16c[q]);                     \
-        } else {                                                                               \
-            _Pragma("unroll") for (int q = 0; q < NPAIR; ++q)                                  \
-                walk_leaf16<0, DUAL>(ACC[q], SB_PAIR_MASK(q, 0), b16c[q]);                     \
+        unsigned mk_[NPAIR];                                                                   \
+        _Pragma("unroll") for (int q = 0; q < NPAIR; ++q) mk_[q] = SB_PAIR_MASK(q, 0);         \
+        _Pragma("unroll") for (int l = 0; l < NLAB; ++l) {                                     \
+            const uint32_t t_ = lw[l] & 1u;                                                    \
+            lw[l] >>= 1;                                                                       \
+            if (t_) {                                                                          \
+                _Pragma("unroll") for (int q = 0; q < NPAIR; ++q)                              \
+                    walk_leaf16<1, DUAL>(ACC[l * NPAIR + q], mk_[q], b16c[q]);                 \
+            } else {                                                                           \
+                _Pragma("unroll") for (int q = 0; q < NPAIR; ++q)                              \
+                    walk_leaf16<0, DUAL>(ACC[l * NPAIR + q], mk_[q], b16c[q]);                 \
+            }                                                                                  \
         }                                                                                      \
         _Pragma("unroll") for (int q = 0; q < NPAIR; ++q) SB_CONSUME(q, 1);                    \
     } while (0)
 #define SB_LEAF_STEP32()                                                                       \
     do {                                                                                       \
-        const uint32_t t_ = lw & 1u;                                                           \
-        lw >>= 1;                                                                              \
-        if (t_) {                                                                              \
-            _Pragma("unroll") for (int k = 0; k < NP; ++k)                                     \
-                walk_leaf<1, DUAL>(acc[k], SB_GENE_BIT(k), b32[k]);                            \
-        } else {                                                                               \
-            _Pragma("unroll") for (int k = 0; k < NP; ++k)                                     \
-                walk_leaf<0, DUAL>(acc[k], SB_GENE_BIT(k), b32[k]);                            \
+        _Pragma("unroll") for (int l = 0; l < NLAB; ++l) {                                     \
+            const uint32_t t_ = lw[l] & 1u;                                                    \
+            lw[l] >>= 1;                                                                       \
+            if (t_) {                                                                          \
+                _Pragma("unroll") for (int k = 0; k < NP; ++k)                                 \
+                    walk_leaf<1, DUAL>(acc[l * NP + k], SB_GENE_BIT(k), b32[k]);               \
+            } else {                                                                           \
+                _Pragma("unroll") for (int k = 0; k < NP; ++k)                                 \
+                    walk_leaf<0, DUAL>(acc[l * NP + k], SB_GENE_BIT(k), b32[k]);               \
+            }                                                                                  \
         }                                                                                      \
         _Pragma("unroll") for (int q = 0; q < NPAIR; ++q) SB_CONSUME(q, 1);                    \
     } while (0)
@@ -604,39 +620,47 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR
     // `cnt` leaf updates of ACC
 #define SB_CHERRY_RUN16(ACC)                                                                   \
     do {                                                                                       \
-        uint32_t t12;                                                                          \
+        uint32_t t12[NLAB];                                                                    \
         unsigned m1[NPAIR], m2[NPAIR];                                                         \
         if (__builtin_expect(cnt + 2 <= room, 1)) {                                            \
             room -= cnt + 2;                                                                   \
-            t12 = lw & 3u;                                                                     \
-            lw >>= 2;                                                                          \
+            _Pragma("unroll") for (int l = 0; l < NLAB; ++l) {                                 \
+                t12[l] = lw[l] & 3u;                                                           \
+                lw[l] >>= 2;                                                                   \
+            }                                                                                  \
             _Pragma("unroll") for (int q = 0; q < NPAIR; ++q) {                                \
                 m1[q] = SB_PAIR_MASK(q, 0);                                                    \
                 m2[q] = SB_PAIR_MASK(q, 1);                                                    \
                 SB_CONSUME(q, 2);                                                              \
             }                                                                                  \
-            walk_cherry16<NPAIR, DUAL>(ACC, m1, m2, t12, b16c);                                \
+            _Pragma("unroll") for (int l = 0; l < NLAB; ++l)                                   \
+                walk_cherry16<NPAIR, DUAL>(ACC + l * NPAIR, m1, m2, t12[l], b16c);             \
             if (cnt) {                                                                         \
                 int i = cnt;                                                                   \
                 _Pragma("unroll 1") do { SB_LEAF_STEP16(ACC); } while (--i);                   \
             }                                                                                  \
         } else {                                                                               \
             if (room == 0) SB_OPEN_WINDOW();                                                   \
-            t12 = lw & 1u;                                                                     \
-            lw >>= 1;                                                                          \
+            _Pragma("unroll") for (int l = 0; l < NLAB; ++l) {                                 \
+                t12[l] = lw[l] & 1u;                                                           \
+                lw[l] >>= 1;                                                                   \
+            }                                                                                  \
             _Pragma("unroll") for (int q = 0; q < NPAIR; ++q) {                                \
                 m1[q] = SB_PAIR_MASK(q, 0);                                                    \
                 SB_CONSUME(q, 1);                                                              \
             }                                                                                  \
             if (--room == 0) SB_OPEN_WINDOW();                                                 \
-            t12 |= (lw & 1u) << 1;                                                             \
-            lw >>= 1;                                                                          \
+            _Pragma("unroll") for (int l = 0; l < NLAB; ++l) {                                 \
+                t12[l] |= (lw[l] & 1u) << 1;                                                   \
+                lw[l] >>= 1;                                                                   \
+            }                                                                                  \
             _Pragma("unroll") for (int q = 0; q < NPAIR; ++q) {                                \
                 m2[q] = SB_PAIR_MASK(q, 0);                                                    \
                 SB_CONSUME(q, 1);                                                              \
             }                                                                                  \
             --room;                                                                            \
-            walk_cherry16<NPAIR, DUAL>(ACC, m1, m2, t12, b16c);                                \
+            _Pragma("unroll") for (int l = 0; l < NLAB; ++l)                                   \
+                walk_cherry16<NPAIR, DUAL>(ACC + l * NPAIR, m1, m2, t12[l], b16c);             \
             _Pragma("unroll 1") for (int i = 0; i < cnt; ++i) {                                \
                 if (room == 0) SB_OPEN_WINDOW();                                               \
                 SB_LEAF_STEP16(ACC);                                                           \
@@ -660,14 +684,14 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR
             SB_CHERRY_RUN16(b16);
             if (op & 1u) {
 #pragma unroll
-                for (int q = 0; q < NPAIR; ++q) walk_merge16<DUAL>(b16[q], a16[q], b16c[q]);
+                for (int s = 0; s < NS; ++s) walk_merge16<DUAL>(b16[s], a16[s], b16c[s % NPAIR]);
             }
             continue;
         }
         if ((op & 12u) == 4u) {
             if (op & 1u) {
 #pragma unroll
-                for (int q = 0; q < NPAIR; ++q) {
+                for (int q = 0; q < NS; ++q) {
                     int *s = stk + (sp + q * EW) * T;
 #pragma unroll
                     for (int c = 0; c < 5; ++c) {
@@ -675,7 +699,7 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR
                         if constexpr (DUAL) s[(5 + c) * T] = (int)a16[q].a[c];
                     }
                 }
-                sp += EW * NPAIR;
+                sp += EW * NS;
             }
             if (op & 2u) SB_CHERRY_RUN16(a16);
             continue;
@@ -683,12 +707,12 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR
         if (type == OP_MERGE_POP16) {
 #pragma unroll 1
             for (int i = 0; i < cnt; ++i) {
-                sp -= EW * NPAIR;
+                sp -= EW * NS;
 #pragma unroll
-                for (int q = 0; q < NPAIR; ++q) {
+                for (int q = 0; q < NS; ++q) {
                     WalkState16 L;
                     SB_POP16(L, q);
-                    walk_merge16<DUAL>(L, a16[q], b16c[q]);
+                    walk_merge16<DUAL>(L, a16[q], b16c[q % NPAIR]);
                 }
             }
             continue;
@@ -700,23 +724,23 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR
         switch (type) {
         case OP_WIDEN_A:
 #pragma unroll
-            for (int q = 0; q < NPAIR; ++q) walk_widen<DUAL>(a16[q], acc[2 * q], acc[2 * q + 1], scale);
+            for (int q = 0; q < NS; ++q) walk_widen<DUAL>(a16[q], acc[2 * q], acc[2 * q + 1], scale);
             break;
         case OP_LEAF_A32:
             SB_LEAF_RUN(SB_LEAF_STEP32());
             break;
         case OP_MERGE_A32_B16:
 #pragma unroll
-            for (int q = 0; q < NPAIR; ++q) {
+            for (int q = 0; q < NS; ++q) {
                 WalkState r0, r1;
                 walk_widen<DUAL>(b16[q], r0, r1, scale);
-                walk_merge<DUAL>(r0, acc[2 * q], b32[2 * q]);
-                walk_merge<DUAL>(r1, acc[2 * q + 1], b32[2 * q + 1]);
+                walk_merge<DUAL>(r0, acc[2 * q], b32[(2 * q) % NP]);
+                walk_merge<DUAL>(r1, acc[2 * q + 1], b32[(2 * q + 1) % NP]);
             }
             break;
         case OP_PUSH32:
 #pragma unroll
-            for (int k = 0; k < NP; ++k) {
+            for (int k = 0; k < NLAB * NP; ++k) {
                 int *s = stk + (sp + k * EW) * T;
 #pragma unroll
                 for (int c = 0; c < 5; ++c) {
@@ -724,14 +748,14 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR
                     if constexpr (DUAL) s[(5 + c) * T] = acc[k].a[c];
                 }
             }
-            sp += EW * NP;
+            sp += EW * NLAB * NP;
             break;
         case OP_MERGE_POP32:
 #pragma unroll 1
             for (int i = 0; i < cnt; ++i) {
-                sp -= EW * NP;
+                sp -= EW * NLAB * NP;
 #pragma unroll
-                for (int k = 0; k < NP; ++k) {
+                for (int k = 0; k < NLAB * NP; ++k) {
                     WalkState L;
                     const int *s = stk + (sp + k * EW) * T;
 #pragma unroll
@@ -739,22 +763,22 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR
                         L.p[c] = s[c * T];
                         if constexpr (DUAL) L.a[c] = s[(5 + c) * T];
                     }
-                    walk_merge<DUAL>(L, acc[k], b32[k]);
+                    walk_merge<DUAL>(L, acc[k], b32[k % NP]);
                 }
             }
             break;
         case OP_MERGE_POPW:
 #pragma unroll 1
             for (int i = 0; i < cnt; ++i) {
-                sp -= EW * NPAIR;
+                sp -= EW * NS;
 #pragma unroll
-                for (int q = 0; q < NPAIR; ++q) {
+                for (int q = 0; q < NS; ++q) {
                     WalkState16 L;
                     SB_POP16(L, q);
                     WalkState r0, r1;
                     walk_widen<DUAL>(L, r0, r1, scale);
-                    walk_merge<DUAL>(r0, acc[2 * q], b32[2 * q]);
-                    walk_merge<DUAL>(r1, acc[2 * q + 1], b32[2 * q + 1]);
+                    walk_merge<DUAL>(r0, acc[2 * q], b32[(2 * q) % NP]);
+                    walk_merge<DUAL>(r1, acc[2 * q + 1], b32[(2 * q + 1) % NP]);
                 }
             }
             break;
@@ -809,7 +833,8 @@ SB_KERNEL(__launch_bounds__(WALK_THREADS)) walk_pairs_kernel(const WalkArgs A)
 #pragma unroll
     for (int q = 0; q < WALK_NPAIR; ++q) b16[q] = Bonus16{K16P1x2, K16x2, K16x2, K16P1x2};
     WalkState acc[NP];
-    walk_tree<WALK_NPAIR, true>(A, gcol, 0, stk, acc, b32, b16);
+    const int lab_off[1] = {0};
+    walk_tree<WALK_NPAIR, 1, true>(A, gcol, lab_off, stk, acc, b32, b16);
     const int mask = K - 1;
 #pragma unroll
     for (int k = 0; k < NP; ++k) {
@@ -863,18 +888,26 @@ SB_KERNEL(__launch_bounds__(WALK_THREADS, SB_WALK_MINBLOCKS)) walk_permute_kerne
         const unsigned s0 = use_pro[2 * q] ? 65u : 64u, s1 = use_pro[2 * q + 1] ? 65u : 64u;
         b16[q] = Bonus16{s0 | (s1 << 16), (129u - s0) | ((129u - s1) << 16), 0u, 0u};
     }
-    for (int r = 0; r < rows; ++r) {
-        WalkState acc[NP];
-        walk_tree<WALK_NPAIR, false>(A, gcol, (perm0 + r) * A.W32p, stk, acc, b32, b16);
+    constexpr int NLAB = WALK_NLAB;
+    for (int r = 0; r < rows; r += NLAB) {
+        WalkState acc[NLAB * NP];
+        int lab_off[NLAB];
 #pragma unroll
-        for (int k = 0; k < NP; ++k) {
-            // root: Total and the statistic are independent maxima over the five states (classes.py:246-249)
-            const long long total = max5(acc[k].p) >> A.shift;
-            int stat = -1;
+        for (int l = 0; l < NLAB; ++l) lab_off[l] = (perm0 + min(r + l, rows - 1)) * A.W32p;   // an odd tail walks its last labelling twice
+        walk_tree<WALK_NPAIR, NLAB, false>(A, gcol, lab_off, stk, acc, b32, b16);
 #pragma unroll
-            for (int c = 0; c < 5; ++c)
-                if (acc[k].p[c] >= 0) stat = max(stat, acc[k].p[c] & mask);
-            if ((long long)stat * u_total[k] >= u_stat[k] * total) hits[k] |= (1u << r);   // methods.py:1353-1355
+        for (int l = 0; l < NLAB; ++l) {
+            if (r + l >= rows) break;
+#pragma unroll
+            for (int k = 0; k < NP; ++k) {
+                // root: Total and the statistic are independent maxima over the five states (classes.py:246-249)
+                const long long total = max5(acc[l * NP + k].p) >> A.shift;
+                int stat = -1;
+#pragma unroll
+                for (int c = 0; c < 5; ++c)
+                    if (acc[l * NP + k].p[c] >= 0) stat = max(stat, acc[l * NP + k].p[c] & mask);
+                if ((long long)stat * u_total[k] >= u_stat[k] * total) hits[k] |= (1u << (r + l));   // methods.py:1353-1355
+            }
         }
     }
 #pragma unroll

@@ -75,7 +75,7 @@ int emul_permute(const uint16_t *ops, int n_ops, const uint32_t *labelsW, int P,
     A.n_perms = P; A.ppi = ppi; A.items_per_tile = (P + ppi - 1) / ppi; A.chunk_base = 0;
     A.unperm = unperm; A.hits = hits;
     const int T = sb::WALK_THREADS;
-    std::vector<int> smem((size_t)5 * (stack_units > 0 ? stack_units : 1) * T * sb::WALK_NPAIR);
+    std::vector<int> smem((size_t)5 * (stack_units > 0 ? stack_units : 1) * T * sb::WALK_NPAIR * sb::WALK_NLAB);
     const int64_t per_block = (int64_t)T * sb::WALK_NP;
     for (int64_t tile = 0; tile < (S + per_block - 1) / per_block; ++tile)
         for (int chunk = 0; chunk < A.items_per_tile; ++chunk)

@@ -140,11 +140,27 @@ def test_permute_kernel_source_on_the_host(emul, n, G, comb, ppi):
     _check_permute(emul, n, G, comb, ppi)
 
 
-@pytest.mark.parametrize("n,G,comb", [(5, 40, False), (129, 600, False), (150, 520, True), (1000, 20, False),
-                                      (5000, 12, False)])
+VARIANT_CASES = [(5, 40, False), (129, 600, False), (150, 520, True), (1000, 20, False), (5000, 12, False)]
+
+
+@pytest.mark.parametrize("n,G,comb", VARIANT_CASES)
 def test_prmt_variant_of_the_walk_kernels_on_the_host(emul_prmt, n, G, comb):
     _check_pairs(emul_prmt, n, G, comb)
     _check_permute(emul_prmt, n, G, comb, 4)
+
+
+@pytest.fixture(scope="module")
+def emul_nlab2():
+    """the experimental -DSB_WALK_NLAB=2 build: K5 walks two labellings of its genes in lockstep"""
+    return _build_walk_emul(os.path.join(HERE, "libwalk_emul_nlab2.so"), ("-DSB_WALK_NLAB=2",))
+
+
+@pytest.mark.parametrize("n,G,comb", VARIANT_CASES)
+@pytest.mark.parametrize("ppi", [2, 4])
+def test_lockstep_variant_of_the_permutation_kernel_on_the_host(emul_nlab2, n, G, comb, ppi):
+    """9 labellings in blocks of 2 or 4: the odd tail walks its last labelling twice and reports it once"""
+    _check_pairs(emul_nlab2, n, G, comb)
+    _check_permute(emul_nlab2, n, G, comb, ppi)
 
 
 # ---------------------------------------------------------------------------- Fisher (csrc/fisher.cuh) on the host
