@@ -51,6 +51,23 @@ def workload(n_isolates, seed, n_perms, perm_seed):
     return np.ascontiguousarray(ops), labelsW, W32p, shift
 
 
+def pipe_of(op):
+    """issue pipe of a SASS opcode as ncu groups them (sm__inst_executed_pipe_alu / fma / uniform / lsu / ...)"""
+    if op.startswith("U") or op in ("R2UR", "S2UR"):
+        return "uniform"
+    if op in ("IMAD", "FFMA", "FMUL", "FADD", "HFMA2", "IMUL"):
+        return "fma"
+    if op in ("LDS", "STS", "LDG", "STG", "LDL", "STL", "LD", "ST", "ATOM", "RED"):
+        return "lsu"
+    if op in ("BRA", "BRX", "EXIT", "BSSY", "BSYNC", "RET", "CALL", "WARPSYNC", "NOP", "BAR"):
+        return "branch/control"
+    if op in ("LDC", "S2R", "CS2R"):
+        return "other (LDC, S2R)"
+    if op in ("BREV", "POPC", "FLO", "MUFU"):
+        return "xu"
+    return "alu"          # LOP3, SHF, SEL, PRMT, ISETP, IADD3, LEA, VIADD, VIADDMNMX, VIMNMX(3), PLOP3, MOV
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--lib", default=os.path.join(ROOT, "scoary_b200", "libscoary_b200.so"))
@@ -94,6 +111,12 @@ def main():
     print("static instructions in the kernel: %d" % len(instrs))
     print("warp instructions per 64 walks: %.0f   (per internal node and 4-gene thread: %.1f)" % (
         per64, per64 * 2 / max(a.isolates - 1, 1)))
+    # executed instructions by issue pipe (ncu: sm__inst_executed_pipe_*), same unit as per64
+    pipes = {}
+    for ins, n in zip(instrs, dyn):
+        pipes[pipe_of(ins.op)] = pipes.get(pipe_of(ins.op), 0) + n
+    scale = 64.0 / total_walks
+    print("by pipe, per 64 walks: " + ", ".join("%s %.0f" % (k, v * scale) for k, v in sorted(pipes.items(), key=lambda kv: -kv[1])))
     if a.profile:
         import sass_blocks
         count_at = {ins.addr: n for ins, n in zip(instrs, dyn)}
