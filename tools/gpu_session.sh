@@ -34,6 +34,8 @@ step 300 ncu_fisher.log ncu --set full --clock-control none --import-source on -
     -o "$out/prof_fisher" -f python tools/probe.py --perms 4
 for rep in "$out"/prof_walk.ncu-rep "$out"/prof_fisher.ncu-rep; do
     [ -f "$rep" ] && ncu -i "$rep" --page raw --csv > "${rep%.ncu-rep}.raw.csv" 2>/dev/null
+    # per-instruction executed counts and stall samples (SASS view): settles the pipe assignment of each opcode
+    [ -f "$rep" ] && ncu -i "$rep" --page source --csv --print-source sass > "${rep%.ncu-rep}.source.csv" 2>/dev/null
 done
 step 600 bench.log python bench.py
 step 300 bench_north_star.log python bench.py --workload north_star --steps 2 --no-cpu-baseline
