@@ -57,6 +57,15 @@ static inline unsigned sb_emul_vmaxs2(unsigned a, unsigned b)
 }
 #define SB_VADD2(a, b) sb_emul_vadd2(a, b)
 #define SB_VMAXS2(a, b) sb_emul_vmaxs2(a, b)
+// SB_ADD2_NC on the host: the lane-wise sum, and a count of every call whose low lane would have carried into
+// the high lane (the device build uses one 32-bit add there); tests/test_host_emul.py requires the count to stay 0
+static long long sb_emul_carry_violations = 0;
+static inline unsigned sb_emul_add2_nc(unsigned a, unsigned b)
+{
+    if ((a & 0xFFFFu) + (b & 0xFFFFu) > 0xFFFFu) ++sb_emul_carry_violations;
+    return sb_emul_vadd2(a, b);
+}
+#define SB_ADD2_NC(a, b) sb_emul_add2_nc(a, b)
 static inline unsigned sb_emul_brev(unsigned x)
 {
     unsigned r = 0;
@@ -78,6 +87,11 @@ static inline unsigned sb_emul_sign_mask2(unsigned x)
 #define SB_SHARED_STACK(name) extern __shared__ __align__(16) int name[]
 #define SB_VADD2(a, b) __vadd2(a, b)
 #define SB_VMAXS2(a, b) __vmaxs2(a, b)
+// Packed 16-bit add where the low lane provably cannot carry: one operand is a reachable key (0 .. 4095) or a pair
+// bonus (64 / 65) and the other is a stored state value (reachable, or unreachable = 0xC000 + drift <= 0xD081 as an
+// unsigned lane; even a sum of two unreachable values, >= 0x8000, stays below 0xFFFF - 65).  A plain 32-bit add is
+// then lane-exact, and unlike VIADD.16x2 (ALU pipe only) the compiler may issue it on the FMA pipe (IMAD.IADD).
+#define SB_ADD2_NC(a, b) ((a) + (b))
 #define SB_BREV(x) __brev(x)
 // not __byte_perm: it keeps only 3 bits of each selector nibble (the SASS showed PRMT 0x3311, plain byte copies)
 __device__ __forceinline__ unsigned sb_sign_mask2(unsigned x)
@@ -394,12 +408,12 @@ SB_DEV void walk_leaf16(WalkState16 &s, unsigned m, const Bonus16 &b)
 {
     const unsigned Mp = max5_16(s.p);
     if (TB) {
-        const unsigned np4 = sel2(m, SB_VADD2(s.p[3], b.ps), SB_VADD2(s.p[1], b.po));
+        const unsigned np4 = sel2(m, SB_ADD2_NC(s.p[3], b.ps), SB_ADD2_NC(s.p[1], b.po));
         s.p[0] = sel2(m, Mp, s.p[0]);
         s.p[2] = sel2(m, s.p[2], Mp);
         s.p[4] = np4;
     } else {
-        const unsigned np4 = sel2(m, SB_VADD2(s.p[2], b.po), SB_VADD2(s.p[0], b.ps));
+        const unsigned np4 = sel2(m, SB_ADD2_NC(s.p[2], b.po), SB_ADD2_NC(s.p[0], b.ps));
         s.p[1] = sel2(m, Mp, s.p[1]);
         s.p[3] = sel2(m, s.p[3], Mp);
         s.p[4] = np4;
@@ -407,12 +421,12 @@ SB_DEV void walk_leaf16(WalkState16 &s, unsigned m, const Bonus16 &b)
     if constexpr (DUAL) {
         const unsigned Ma = max5_16(s.a);
         if (TB) {
-            const unsigned na4 = sel2(m, SB_VADD2(s.a[3], b.as_), SB_VADD2(s.a[1], b.ao));
+            const unsigned na4 = sel2(m, SB_ADD2_NC(s.a[3], b.as_), SB_ADD2_NC(s.a[1], b.ao));
             s.a[0] = sel2(m, Ma, s.a[0]);
             s.a[2] = sel2(m, s.a[2], Ma);
             s.a[4] = na4;
         } else {
-            const unsigned na4 = sel2(m, SB_VADD2(s.a[2], b.ao), SB_VADD2(s.a[0], b.as_));
+            const unsigned na4 = sel2(m, SB_ADD2_NC(s.a[2], b.ao), SB_ADD2_NC(s.a[0], b.as_));
             s.a[1] = sel2(m, Ma, s.a[1]);
             s.a[3] = sel2(m, s.a[3], Ma);
             s.a[4] = na4;
@@ -425,10 +439,10 @@ SB_DEV void merge_pass16(const unsigned L[5], const unsigned R[5], unsigned out[
 {
     const unsigned ML = max5_16(L), MR = max5_16(R);
 #pragma unroll
-    for (int c = 0; c < 4; ++c) out[c] = __viaddmax_s16x2(L[c], MR, SB_VADD2(ML, R[c]));
+    for (int c = 0; c < 4; ++c) out[c] = __viaddmax_s16x2(L[c], MR, SB_ADD2_NC(ML, R[c]));   // ML is reachable
     const unsigned nf = SB_VADD2(L[4], R[4]);
-    const unsigned pp = SB_VADD2(__viaddmax_s16x2(L[0], R[3], SB_VADD2(L[3], R[0])), bsup);
-    const unsigned ap = SB_VADD2(__viaddmax_s16x2(L[1], R[2], SB_VADD2(L[2], R[1])), bopp);
+    const unsigned pp = SB_ADD2_NC(__viaddmax_s16x2(L[0], R[3], SB_VADD2(L[3], R[0])), bsup);
+    const unsigned ap = SB_ADD2_NC(__viaddmax_s16x2(L[1], R[2], SB_VADD2(L[2], R[1])), bopp);
     out[4] = SB_VMAXS2(__vimax3_s16x2(nf, pp, ap), NEG16x2);
 }
 

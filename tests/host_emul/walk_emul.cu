@@ -39,6 +39,7 @@ int load_program(const uint16_t *ops, int n_ops)
 extern "C" {
 
 int emul_walk_threads(void) { return sb::WALK_THREADS; }
+long long emul_carry_violations(void) { return sb::sb_emul_carry_violations; }
 int emul_walk_genes_per_thread(void) { return sb::WALK_NP; }
 
 // K4: pairs[S][3] for the labelling `labels` (walk order, W32p words)

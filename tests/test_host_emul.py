@@ -106,6 +106,7 @@ def _check_pairs(lib, n, G, comb):
     assert rc == 0
     ref = O.permute(c["left"], c["right"], c["m"], c["lab"], P=0)["pairs"]
     assert np.array_equal(pairs, ref)
+    _no_carries(lib)
 
 
 def _check_permute(lib, n, G, comb, ppi):
@@ -125,6 +126,13 @@ def _check_permute(lib, n, G, comb, ppi):
         got[:, p] = (hits[p // ppi] >> (p % ppi)) & 1
     assert np.array_equal(got, ref["hits"])
     assert np.array_equal(got.sum(axis=1), ref["r"])
+    _no_carries(lib)
+
+
+def _no_carries(lib):
+    """SB_ADD2_NC (walk.cuh) is a plain 32-bit add on the device: its low 16-bit lane must never carry"""
+    lib.emul_carry_violations.restype = ctypes.c_longlong
+    assert lib.emul_carry_violations() == 0
 
 
 @pytest.mark.parametrize("n,G,comb", CASES)
