@@ -148,6 +148,44 @@ def test_permute_kernel_source_on_the_host(emul, n, G, comb, ppi):
     _check_permute(emul, n, G, comb, ppi)
 
 
+@pytest.mark.parametrize("n,comb", [(127, True), (127, False), (126, True), (254, True), (255, False), (1000, False)])
+def test_extreme_keys_stay_inside_their_16_bit_lane(emul, n, comb):
+    """Labels alternating along the walk and genes that follow / oppose them give the most pairs a subtree can hold
+    (63 pairs and 63 pro or anti pairs in 127 leaves: key 4095, the largest drift an unreachable state can pick up).
+    Results must equal the oracle's and SB_ADD2_NC must never see a low-lane carry."""
+    c = _setup(n, 8, 900 + n, comb)
+    pos_of_leaf = np.empty(n, dtype=np.int64)
+    pos_of_leaf[c["order"][:n]] = np.arange(n)
+    lab = (pos_of_leaf % 2).astype(np.uint8)                      # by leaf id: alternating in walk order
+    m = np.stack([lab, 1 - lab, (pos_of_leaf // 2 % 2).astype(np.uint8), 1 - (pos_of_leaf // 2 % 2).astype(np.uint8),
+                  np.ones(n, np.uint8), np.zeros(n, np.uint8), (pos_of_leaf % 3 == 0).astype(np.uint8),
+                  (pos_of_leaf % 4 < 3).astype(np.uint8)])
+    gw = _pack_walk_order(m, c["order"], c["W32p"])
+    genesT = np.zeros((c["W32p"], c["Gs"]), dtype=np.uint32)
+    genesT[:, :8] = gw.T
+    lab0 = _pack_walk_order(lab[None, :], c["order"], c["W32p"])[0]
+    pairs = np.full((8, 3), -7, dtype=np.int32)
+    assert emul.emul_pairs(_ptr(c["ops"]), len(c["ops"]), _ptr(lab0), _ptr(genesT), c["Gs"], 8, c["W32p"], c["shift"],
+                           c["units"], _ptr(pairs)) == 0
+    ref = O.permute(c["left"], c["right"], m, lab, P=0)["pairs"]
+    assert np.array_equal(pairs, ref)
+    P = 4
+    labs = np.stack([lab, 1 - lab, np.roll(lab, 1), (pos_of_leaf % 2 == 0).astype(np.uint8)])
+    labelsW = np.ascontiguousarray(_pack_walk_order(labs, c["order"], c["W32p"]))
+    hits = np.zeros((1, 8), dtype=np.uint8)
+    unperm = np.ascontiguousarray(ref, dtype=np.int32)
+    assert emul.emul_permute(_ptr(c["ops"]), len(c["ops"]), _ptr(labelsW), P, 4, _ptr(genesT), c["Gs"], 8, c["W32p"],
+                             c["shift"], c["units"], _ptr(unperm), _ptr(hits)) == 0
+    for p in range(P):                                            # the oracle, labelling by labelling
+        want = O.permute(c["left"], c["right"], m, labs[p], P=0)["pairs"].astype(np.int64)
+        side = np.where(ref[:, 1] >= ref[:, 2], 1, 2)             # methods.py:1333-1336
+        stat, u_stat = want[np.arange(8), side], ref[np.arange(8), side].astype(np.int64)
+        hit = stat * ref[:, 0].astype(np.int64) >= u_stat * want[:, 0]
+        assert np.array_equal((hits[0] >> p) & 1, hit.astype(np.uint8)), p
+    _no_carries(emul)
+    assert ref[:, 0].max() >= (n // 2) - 1                        # the construction does reach the maximum
+
+
 VARIANT_CASES = [(5, 40, False), (129, 600, False), (150, 520, True), (1000, 20, False), (5000, 12, False)]
 
 
