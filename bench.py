@@ -541,6 +541,13 @@ def run_ours(a):
                                  "warp_instr_per_64_walks": wi,
                                  "source": "instruction count from profiles/k5_warp_instructions.json (%s); time and "
                                            "clock from this run" % wi_src}
+        alu = (wi_file.get("by_pipe_c3") or {}).get("alu_class")
+        if alu:      # ALU-class instructions (DPX, LOP3, SHF, SEL ...) issue at 2 per clock per SM: the tighter pipe bound
+            roofline_int["issue"]["alu_class"] = {
+                "warp_instr_per_64_walks": alu, "peak_per_clock_per_sm": 2.0,
+                "frac": tests_per_launch / 64.0 * alu / (k5_ms * 1e-3) / (2.0 * st["sm_count"] * clocks["sm_mhz"] * 1e6),
+                "note": "upper estimate: assumes the DPX forms share the ALU pipe (ncu pipe_alu read 59.9 % where this "
+                        "count gave 77 % on the profiled kernel)"}
     fisher_bytes = G * (8 * W + 24)
     fisher = {"kernel": "fisher_kernel (K2+K3)", "ms": fisher_ms, "tests_per_s": G / (fisher_ms * 1e-3),
               "bound": "hbm", "achieved": fisher_bytes / (fisher_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
