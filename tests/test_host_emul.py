@@ -209,6 +209,62 @@ def test_lockstep_variant_of_the_permutation_kernel_on_the_host(emul_nlab2, n, G
     _check_permute(emul_nlab2, n, G, comb, ppi)
 
 
+def _balanced(names):
+    if len(names) == 1:
+        return names[0]
+    h = len(names) // 2
+    return [_balanced(names[:h]), _balanced(names[h:])]
+
+
+def test_random_campaign_over_tree_shapes_and_window_offsets(emul, emul_prmt, emul_nlab2):
+    """40 random configurations (isolate counts around every 16 / 32 / 127-leaf boundary; random-join, comb and
+    balanced trees; gene frequencies from 0 to 1) through the three builds: pairs, per-permutation hit flags, no carry."""
+    rng = np.random.default_rng(20261017)
+    sizes = [2, 3, 4, 5, 7, 15, 16, 17, 31, 32, 33, 47, 48, 49, 63, 64, 65, 100, 126, 127, 128, 129, 130, 200, 255, 256, 257,
+             300, 511, 513]
+    for _ in range(40):
+        n, G, kind = int(rng.choice(sizes)), int(rng.integers(1, 24)), int(rng.integers(3))
+        names = synth.isolate_names(n)
+        if kind == 0:
+            nested = synth.make_tree(n, int(rng.integers(1 << 30)))
+        elif kind == 1:
+            nested = names[0]
+            for nm in names[1:]:
+                nested = [nested, nm]
+        else:
+            nested = _balanced(names)
+        ops, order, units, _ = compile_tree(nested)
+        left, right, _ = treemod.flatten(nested)
+        m = (rng.random((G, n)) < rng.uniform(0.0, 1.0, size=G)[:, None]).astype(np.uint8)
+        lab = (rng.random(n) < rng.uniform(0.05, 0.95)).astype(np.uint8)
+        m[0] = lab
+        W32p = ((n + 31) // 32 + 3) // 4 * 4
+        shift = 1
+        while (1 << shift) <= n // 2:
+            shift += 1
+        Gs = (G + 31) // 32 * 32
+        genesT = np.zeros((W32p, Gs), dtype=np.uint32)
+        genesT[:, :G] = _pack_walk_order(m, order, W32p).T
+        genesT, ops = np.ascontiguousarray(genesT), np.ascontiguousarray(ops)
+        P, seed = int(rng.integers(1, 10)), int(rng.integers(1 << 30))
+        ref = O.permute(left, right, m, lab, P=P, seed=seed, trait=0, want_hits=True)
+        labs = np.stack([O.shuffle_labels(seed, 0, p, lab) for p in range(P)])
+        labelsW = np.ascontiguousarray(_pack_walk_order(labs, order, W32p))
+        unperm = np.ascontiguousarray(ref["pairs"], dtype=np.int32)
+        lab0 = _pack_walk_order(lab[None, :], order, W32p)[0]
+        for lib, ppis in ((emul, (1, 2, 4)), (emul_nlab2, (2, 4)), (emul_prmt, (4,))):
+            pairs = np.full((G, 3), -7, dtype=np.int32)
+            assert lib.emul_pairs(_ptr(ops), len(ops), _ptr(lab0), _ptr(genesT), Gs, G, W32p, shift, units, _ptr(pairs)) == 0
+            assert np.array_equal(pairs, ref["pairs"]), (n, G, kind)
+            for ppi in ppis:
+                hits = np.zeros(((P + ppi - 1) // ppi, G), dtype=np.uint8)
+                assert lib.emul_permute(_ptr(ops), len(ops), _ptr(labelsW), P, ppi, _ptr(genesT), Gs, G, W32p, shift, units,
+                                        _ptr(unperm), _ptr(hits)) == 0
+                got = np.stack([(hits[p // ppi] >> (p % ppi)) & 1 for p in range(P)], axis=1)
+                assert np.array_equal(got, ref["hits"]), (n, G, kind, ppi, P)
+            _no_carries(lib)
+
+
 # ---------------------------------------------------------------------------- Fisher (csrc/fisher.cuh) on the host
 FLIB = os.path.join(HERE, "libfisher_emul.so")
 FSRC = os.path.join(HERE, "fisher_emul.cu")
