@@ -117,6 +117,17 @@ def main():
         pipes[pipe_of(ins.op)] = pipes.get(pipe_of(ins.op), 0) + n
     scale = 64.0 / total_walks
     print("by pipe, per 64 walks: " + ", ".join("%s %.0f" % (k, v * scale) for k, v in sorted(pipes.items(), key=lambda kv: -kv[1])))
+    # dynamic instruction footprint: bytes of 128-byte I-cache lines that cover a share of the executed instructions
+    lines = {}
+    for ins, n in zip(instrs, dyn):
+        lines[ins.addr // 128] = lines.get(ins.addr // 128, 0) + n
+    acc, cover, want = 0, {}, [0.5, 0.8, 0.9, 0.99]
+    for k, n in enumerate(sorted(lines.values(), reverse=True)):
+        acc += n
+        while want and acc >= want[0] * total_instr:
+            cover[want.pop(0)] = (k + 1) * 128
+    print("code bytes covering 50 / 80 / 90 / 99 %% of the executed instructions: %s (static %d)" % (
+        " / ".join(str(cover.get(q, 0)) for q in (0.5, 0.8, 0.9, 0.99)), 16 * len(instrs)))
     if a.profile:
         import sass_blocks
         count_at = {ins.addr: n for ins, n in zip(instrs, dyn)}
