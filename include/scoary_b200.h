@@ -221,6 +221,13 @@ int sb_debug_compile_tree(const int32_t *left, const int32_t *right, int32_t n_i
                           uint16_t *ops_out, int32_t max_ops, int32_t *leaf_of_pos,
                           int32_t *stack_units);
 
+/* The same hook for builds that pad the leaf stream (-DSB_WALK_PADDED=1, an experimental kernel variant):
+ * leaf_of_pos [max_pos] receives the stream, -1 marking a pad position, and *n_pos its length
+ * (= n_internal + 1 in the default build). */
+int sb_debug_compile_tree2(const int32_t *left, const int32_t *right, int32_t n_internal,
+                           uint16_t *ops_out, int32_t max_ops, int32_t *leaf_of_pos, int32_t max_pos,
+                           int32_t *n_pos, int32_t *stack_units);
+
 /* Integer-pipe microbenchmark used for the walk kernels' roofline denominator:
  * runs `iters` rounds of dependent add/max chains on every SM and returns the
  * measured int32 add+max operations per second. */

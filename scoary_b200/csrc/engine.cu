@@ -205,6 +205,55 @@ struct Program {
     int depth = 0;
 };
 
+// SB_WALK_PADDED: give every leaf-consuming op a place inside ONE leaf window.  Leaf runs are split at the window
+// boundaries; a cherry op (2 + count leaves, no continuation) that does not fit the rest of its window starts the
+// next one, and the positions it skips become padding (leaf_of_pos = -1: gene bit 0, no label).  The kernels apply
+// the same rule ("does not fit -> open the next window"), so no flag is stored in the program.
+bool pad_stream(Program &prog, std::string &err)
+{
+    const int W = sb::WALK_WINDOW;
+    std::vector<uint16_t> ops;
+    std::vector<int32_t> pos_leaf;
+    ops.reserve(prog.ops.size() + prog.ops.size() / 4);
+    pos_leaf.reserve(prog.leaf_of_pos.size() + prog.leaf_of_pos.size() / 4);
+    size_t next = 0;          // next entry of the unpadded leaf order
+    int room = 0;             // leaves left in the current window, as the kernel counts them
+    auto take = [&](int n) {
+        for (int k = 0; k < n; ++k) pos_leaf.push_back(prog.leaf_of_pos[next++]);
+        room -= n;
+    };
+    for (const uint16_t op : prog.ops) {
+        const int type = op & 15, cnt = op >> sb::OP_TYPE_BITS;
+        const bool cherry = type == sb::OP_CHERRY_A16 || type == sb::OP_PUSH_CHERRY_A16 || type == sb::OP_CHERRY_B16 ||
+                            type == sb::OP_CHERRY_B16_MERGE;
+        if (cherry) {
+            const int n = cnt + 2;
+            if (n > W) { err = "internal error: cherry op longer than a leaf window"; return false; }
+            if (n > room) {
+                for (int k = 0; k < room; ++k) pos_leaf.push_back(-1);
+                room = W;
+            }
+            take(n);
+            ops.push_back(op);
+        } else if (type == sb::OP_LEAF_A16 || type == sb::OP_LEAF_A32) {
+            int left_ = cnt;
+            while (left_ > 0) {
+                if (room == 0) room = W;
+                const int n = std::min(left_, room);
+                take(n);
+                ops.push_back((uint16_t)((n << sb::OP_TYPE_BITS) | type));
+                left_ -= n;
+            }
+        } else {
+            ops.push_back(op);
+        }
+    }
+    if (next != prog.leaf_of_pos.size()) { err = "internal error: leaf stream and program disagree"; return false; }
+    prog.ops.swap(ops);
+    prog.leaf_of_pos.swap(pos_leaf);
+    return true;
+}
+
 bool compile_tree(const int32_t *left, const int32_t *right, int32_t n_internal, Program &out, std::string &err)
 {
     const int32_t n_leaves = n_internal + 1;
@@ -235,7 +284,8 @@ bool compile_tree(const int32_t *left, const int32_t *right, int32_t n_internal,
         if (li && ri) {
             const int32_t a = left[v], b = right[v];
             auto cost = [&](int32_t f, int32_t s2, bool &in_b) {
-                in_b = cat[s2] && small(s2);
+                // padded streams: a B caterpillar must fit one leaf window (it has no continuation op)
+                in_b = cat[s2] && small(s2) && (!sb::WALK_PADDED || size[s2] <= sb::WALK_WINDOW);
                 return in_b ? need[f] : std::max(need[f], (small(f) ? 1 : 2) + need[s2]);
             };
             bool b_ab, b_ba;
@@ -340,7 +390,8 @@ bool compile_tree(const int32_t *left, const int32_t *right, int32_t n_internal,
             }
             size_t j = i + (push ? 2 : 1);
             size_t leaves = 0;
-            while (j < n_raw && raw[j] == sb::OP_LEAF_A16 && leaves < (size_t)sb::OP_MAX_COUNT) { ++j; ++leaves; }
+            const size_t cap = sb::WALK_PADDED ? (size_t)(sb::WALK_WINDOW - 2) : (size_t)sb::OP_MAX_COUNT;
+            while (j < n_raw && raw[j] == sb::OP_LEAF_A16 && leaves < cap) { ++j; ++leaves; }
             emit(push ? sb::OP_PUSH_CHERRY_A16 : sb::OP_CHERRY_A16, leaves);
             i = j;
         } else if (kind == sb::OP_CHERRY_B16) {
@@ -373,6 +424,7 @@ bool compile_tree(const int32_t *left, const int32_t *right, int32_t n_internal,
     out.ops.push_back((uint16_t)sb::OP_END);
     if (sp != 0) { err = "internal error: unbalanced stack program"; return false; }
     out.depth = depth;   // stack units of 10 words per gene pair
+    if (sb::WALK_PADDED && !pad_stream(out, err)) return false;
     return true;
 }
 
@@ -426,8 +478,9 @@ int finalize_slot(sb_ctx *ctx, int32_t t)
                                          "(PruneForMissing, scoary/methods.py:709-739)");
         if ((s.h_value[col >> 6] >> (col & 63)) & 1ULL) lab_leaf[k >> 5] |= (1u << (k & 31));
     }
-    for (int32_t pos = 0; pos < s.n_leaves; ++pos) {
+    for (int32_t pos = 0; pos < (int32_t)s.h_leaf_of_pos.size(); ++pos) {
         const int32_t leaf = s.h_leaf_of_pos[pos];
+        if (leaf < 0) continue;      // pad position (SB_WALK_PADDED)
         if ((lab_leaf[leaf >> 5] >> (leaf & 31)) & 1u) lab0[pos >> 5] |= (1u << (pos & 31));
     }
     if (!s.d_labels_leaf) SB_CUDA(ctx, cudaMalloc(&s.d_labels_leaf, sizeof(uint32_t) * s.W32));
@@ -454,7 +507,8 @@ int finalize_slot(sb_ctx *ctx, int32_t t)
         Timed tm(ctx, CAT_PACK);
         const unsigned blocks = (unsigned)((ctx->G + 31) / 32);
         sb::pack_walk_order_kernel<<<blocks, 256, smem, ctx->stream>>>(ctx->d_genes, ctx->G, ctx->W, s.d_walk_col,
-                                                                       s.n_leaves, s.W32p, s.Gs, s.d_genesT);
+                                                                       (int)s.h_leaf_of_pos.size(), s.W32p, s.Gs,
+                                                                       s.d_genesT);
         ctx->stats.kernel_launches += 1;
         SB_CUDA(ctx, cudaGetLastError());
         s.genesT_valid = true;
@@ -875,22 +929,31 @@ int sb_set_tree(sb_ctx *ctx, int32_t t, const int32_t *left, const int32_t *righ
     while ((1 << s.shift) <= s.n_leaves / 2) ++s.shift;   // 2^SH > max pairs (= floor(n/2)) >= pro, anti
     s.n_ops = (int32_t)prog.ops.size();
     s.h_leaf_to_col.assign(leaf_to_col, leaf_to_col + s.n_leaves);
+    // stream positions: the leaves in walk order; with SB_WALK_PADDED also pad positions (-1), and the label /
+    // gene words in walk order (W32p) are counted over positions.  The device copies are filled up with -1 to
+    // W32p * 32 entries so that the kernels need no separate position count.
+    int32_t n_pos = (int32_t)prog.leaf_of_pos.size();
+    if (sb::WALK_PADDED) s.W32p = ((n_pos + 31) / 32 + 3) / 4 * 4;
+    const int32_t n_alloc = sb::WALK_PADDED ? s.W32p * 32 : s.n_leaves;
     s.h_leaf_of_pos = prog.leaf_of_pos;
-    std::vector<int32_t> walk_col(s.n_leaves);
-    for (int32_t pos = 0; pos < s.n_leaves; ++pos) {
-        const int32_t col = leaf_to_col[prog.leaf_of_pos[pos]];
+    std::vector<int32_t> walk_col((size_t)n_alloc, -1), pos_leaf((size_t)n_alloc, -1);
+    for (int32_t pos = 0; pos < n_pos; ++pos) {
+        const int32_t leaf = prog.leaf_of_pos[pos];
+        if (leaf < 0) continue;      // pad position
+        const int32_t col = leaf_to_col[leaf];
         if (col < 0 || col >= ctx->N) return fail(ctx, SB_ERR_ARG, "sb_set_tree: leaf_to_col out of range");
         walk_col[pos] = col;
+        pos_leaf[pos] = leaf;
     }
     s.h_ops = prog.ops;
-    SB_CUDA(ctx, cudaMalloc(&s.d_walk_col, sizeof(int32_t) * s.n_leaves));
-    SB_CUDA(ctx, cudaMalloc(&s.d_leaf_of_pos, sizeof(int32_t) * s.n_leaves));
-    SB_CUDA(ctx, cudaMemcpyAsync(s.d_walk_col, walk_col.data(), sizeof(int32_t) * s.n_leaves, cudaMemcpyHostToDevice,
+    SB_CUDA(ctx, cudaMalloc(&s.d_walk_col, sizeof(int32_t) * n_alloc));
+    SB_CUDA(ctx, cudaMalloc(&s.d_leaf_of_pos, sizeof(int32_t) * n_alloc));
+    SB_CUDA(ctx, cudaMemcpyAsync(s.d_walk_col, walk_col.data(), sizeof(int32_t) * n_alloc, cudaMemcpyHostToDevice,
                                  ctx->stream));
-    SB_CUDA(ctx, cudaMemcpyAsync(s.d_leaf_of_pos, prog.leaf_of_pos.data(), sizeof(int32_t) * s.n_leaves,
+    SB_CUDA(ctx, cudaMemcpyAsync(s.d_leaf_of_pos, pos_leaf.data(), sizeof(int32_t) * n_alloc,
                                  cudaMemcpyHostToDevice, ctx->stream));
     SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    ctx->stats.h2d_bytes += (int64_t)(2 * sizeof(int32_t) * s.n_leaves);
+    ctx->stats.h2d_bytes += (int64_t)(2 * sizeof(int32_t) * n_alloc);
     s.has_tree = true;
     s.finalized = false;
     return SB_OK;
@@ -1137,8 +1200,31 @@ int sb_debug_compile_tree(const int32_t *left, const int32_t *right, int32_t n_i
     std::string err;
     if (!compile_tree(left, right, n_internal, prog, err)) { g_create_error = err; return SB_ERR_ARG; }
     if ((int32_t)prog.ops.size() > max_ops) { g_create_error = "program longer than max_ops"; return SB_ERR_ARG; }
+    if ((int32_t)prog.leaf_of_pos.size() != n_internal + 1) {
+        g_create_error = "this build pads the leaf stream: use sb_debug_compile_tree2";
+        return SB_ERR_STATE;
+    }
     memcpy(ops_out, prog.ops.data(), sizeof(uint16_t) * prog.ops.size());
     memcpy(leaf_of_pos, prog.leaf_of_pos.data(), sizeof(int32_t) * (size_t)(n_internal + 1));
+    if (stack_units) *stack_units = prog.depth;
+    return (int)prog.ops.size();
+}
+
+// As sb_debug_compile_tree, for builds whose stream may hold pad positions (SB_WALK_PADDED): leaf_of_pos
+// [max_pos] receives the stream (leaf id, or -1 for a pad position) and *n_pos its length.
+int sb_debug_compile_tree2(const int32_t *left, const int32_t *right, int32_t n_internal, uint16_t *ops_out,
+                           int32_t max_ops, int32_t *leaf_of_pos, int32_t max_pos, int32_t *n_pos,
+                           int32_t *stack_units)
+{
+    if (!left || !right || !ops_out || !leaf_of_pos || !n_pos || n_internal < 1) return SB_ERR_ARG;
+    Program prog;
+    std::string err;
+    if (!compile_tree(left, right, n_internal, prog, err)) { g_create_error = err; return SB_ERR_ARG; }
+    if ((int32_t)prog.ops.size() > max_ops) { g_create_error = "program longer than max_ops"; return SB_ERR_ARG; }
+    if ((int32_t)prog.leaf_of_pos.size() > max_pos) { g_create_error = "stream longer than max_pos"; return SB_ERR_ARG; }
+    memcpy(ops_out, prog.ops.data(), sizeof(uint16_t) * prog.ops.size());
+    memcpy(leaf_of_pos, prog.leaf_of_pos.data(), sizeof(int32_t) * prog.leaf_of_pos.size());
+    *n_pos = (int32_t)prog.leaf_of_pos.size();
     if (stack_units) *stack_units = prog.depth;
     return (int)prog.ops.size();
 }

@@ -115,7 +115,16 @@ __device__ __forceinline__ unsigned sb_sign_mask2(unsigned x)
 #ifndef SB_WALK_PRMT
 #define SB_WALK_PRMT 0
 #endif
+// Experimental (tools/sweep_variants.py, not measured yet): the host compiler pads the leaf stream so that no op
+// ever crosses a 16-leaf window (pad positions carry gene bit 0 and no label; long leaf runs are split at the
+// boundaries).  The kernels then have no general path: an op that does not fit the rest of the window simply opens
+// the next one.  Changes the stream layout, so engine.cu (compile_tree, sb_set_tree) honours the same switch.
+#ifndef SB_WALK_PADDED
+#define SB_WALK_PADDED 0
+#endif
 constexpr int WALK_THREADS = SB_WALK_THREADS;
+constexpr bool WALK_PADDED = SB_WALK_PADDED != 0;
+constexpr int WALK_WINDOW = 16;           // leaves per gene window (two genes per 32-bit register)
 constexpr int WALK_NEG = -(1 << 30);   // unreachable; keys stay < 2^28 (n_leaves <= 32766), so inv+inv >= INT_MIN
 constexpr uint32_t SHUFFLE_DOMAIN = 0x5C0A27u;
 
@@ -147,9 +156,9 @@ __global__ void __launch_bounds__(256) pack_walk_order_kernel(const uint64_t *__
 #pragma unroll 4
         for (int b = 0; b < 32; ++b) {
             const int pos = base + b;
-            if (pos < n_leaves) {
+            if (pos < n_leaves) {   // padded streams: n_leaves counts positions, pad positions have column -1
                 const int col = __ldg(&walk_col[pos]);
-                word |= ((s_rows[gl * pitch + (col >> 5)] >> (col & 31)) & 1u) << b;
+                if (!WALK_PADDED || col >= 0) word |= ((s_rows[gl * pitch + (col >> 5)] >> (col & 31)) & 1u) << b;
             }
         }
         if (g < G) genesT[(int64_t)w * Gs + g] = word;
@@ -193,7 +202,10 @@ __global__ void __launch_bounds__(64) shuffle_labels_kernel(const uint32_t *__re
         uint32_t word = 0;
         for (int b = 0; b < 32; ++b) {
             const int pos = w * 32 + b;
-            if (pos < n_leaves) {
+            if (WALK_PADDED) {      // leaf_of_pos has W32p * 32 entries, -1 = pad position or past the end
+                const int leaf = __ldg(&leaf_of_pos[pos]);
+                if (leaf >= 0) word |= ((s_lab[(leaf >> 5) * T + tid] >> (leaf & 31)) & 1u) << b;
+            } else if (pos < n_leaves) {
                 const int leaf = __ldg(&leaf_of_pos[pos]);
                 word |= ((s_lab[(leaf >> 5) * T + tid] >> (leaf & 31)) & 1u) << b;
             }
@@ -564,9 +576,13 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR
             }                                                                                  \
         } else {                                                                               \
             _Pragma("unroll") for (int q_ = 0; q_ < NPAIR; ++q_) gx[q_] = gy[q_];              \
+            if (WALK_PADDED) {   /* skipped pad positions: the label word is not where the shifts left it */ \
+                _Pragma("unroll") for (int l_ = 0; l_ < NLAB; ++l_)                            \
+                    lw[l_] = c_labels[lab_off[l_] + (win >> 1)] >> 16;                         \
+            }                                                                                  \
         }                                                                                      \
         ++win;                                                                                 \
-        room = 16;                                                                             \
+        room = WALK_WINDOW;                                                                    \
     } while (0)
     // SB_PAIR_MASK: half-word mask of pair q's gene bits at stream offset o (0 = the next leaf), 0xFFFF per
     // half whose gene is present; SB_CONSUME: drop n leaves from pair q's window
@@ -619,7 +635,11 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR
     // `cnt` leaf updates
 #define SB_LEAF_RUN(STEP)                                                                      \
     do {                                                                                       \
-        if (__builtin_expect(cnt <= room, 1)) {                                                \
+        if (WALK_PADDED) {   /* the compiler never lets a run cross a window: what is left is padding */ \
+            if (cnt > room) SB_OPEN_WINDOW();                                                  \
+            room -= cnt;                                                                       \
+            _Pragma("unroll 1") for (int i = 0; i < cnt; ++i) { STEP; }                        \
+        } else if (__builtin_expect(cnt <= room, 1)) {                                         \
             room -= cnt;                                                                       \
             _Pragma("unroll 1") for (int i = 0; i < cnt; ++i) { STEP; }                        \
         } else {                                                                               \
@@ -636,7 +656,8 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR
     do {                                                                                       \
         uint32_t t12[NLAB];                                                                    \
         unsigned m1[NPAIR], m2[NPAIR];                                                         \
-        if (__builtin_expect(cnt + 2 <= room, 1)) {                                            \
+        if (WALK_PADDED && cnt + 2 > room) SB_OPEN_WINDOW();   /* the rest of the window is padding */ \
+        if (WALK_PADDED || __builtin_expect(cnt + 2 <= room, 1)) {                             \
             room -= cnt + 2;                                                                   \
             _Pragma("unroll") for (int l = 0; l < NLAB; ++l) {                                 \
                 t12[l] = lw[l] & 3u;                                                           \

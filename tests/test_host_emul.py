@@ -209,6 +209,117 @@ def test_lockstep_variant_of_the_permutation_kernel_on_the_host(emul_nlab2, n, G
     _check_permute(emul_nlab2, n, G, comb, ppi)
 
 
+# ---------------------------------------------------------------------------- padded leaf stream (-DSB_WALK_PADDED=1)
+@pytest.fixture(scope="module")
+def padded():
+    """(tree compiler of a -DSB_WALK_PADDED=1 build of the product library, walk kernels of the same build on the host)"""
+    so = os.path.join(HERE, "libscoary_b200_padded.so")
+    deps = [os.path.join(CSRC, f) for f in ("engine.cu", "walk.cuh", "common.cuh")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
+        env = dict(os.environ)
+        env.pop("CC", None)
+        subprocess.run(["make", "-B", "-C", CSRC, "OUT=" + so, "EXTRA=-DSB_WALK_PADDED=1"], check=True, env=env,
+                       stdout=subprocess.DEVNULL)
+    lib = ctypes.CDLL(so)
+    lib.sb_debug_compile_tree2.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int32,
+                                           ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]
+    return lib, _build_walk_emul(os.path.join(HERE, "libwalk_emul_padded.so"), ("-DSB_WALK_PADDED=1",))
+
+
+def _compile_padded(lib, nested):
+    left, right, names = treemod.flatten(nested)
+    n = len(left)
+    ops = np.zeros(6 * n + 64, dtype=np.uint16)
+    order = np.full(3 * n + 64, -9, dtype=np.int32)
+    n_pos, depth = ctypes.c_int32(), ctypes.c_int32()
+    k = lib.sb_debug_compile_tree2(_ptr(left), _ptr(right), n, _ptr(ops), len(ops), _ptr(order), len(order),
+                                   ctypes.byref(n_pos), ctypes.byref(depth))
+    assert k > 0
+    return ops[:k].copy(), order[:n_pos.value].copy(), depth.value, left, right
+
+
+def _pack_stream(bits_by_leaf, order, W32p):
+    """as _pack_walk_order, for a stream with pad positions (leaf id -1 -> bit 0)"""
+    walk = np.zeros((bits_by_leaf.shape[0], W32p * 32), dtype=np.uint8)
+    real = order >= 0
+    walk[:, np.nonzero(real)[0]] = bits_by_leaf[:, order[real]]
+    return np.ascontiguousarray(np.packbits(walk, axis=1, bitorder="little")).view(np.uint32).reshape(-1, W32p)
+
+
+def test_padded_stream_program_never_crosses_a_window(padded):
+    """Every leaf-consuming op of a padded program lies inside one 16-leaf window under the kernels' rule (an op
+    that does not fit opens the next window), every leaf appears exactly once, pads cost at most ~25 % positions."""
+    lib, _ = padded
+    for n, comb in ((2, False), (17, False), (127, True), (300, True), (1000, False), (5000, False)):
+        names = synth.isolate_names(n)
+        nested = names[0]
+        if comb:
+            for nm in names[1:]:
+                nested = [nested, nm]
+        else:
+            nested = synth.make_tree(n, 31 + n)
+        ops, order, _, left, _ = _compile_padded(lib, nested)
+        assert sorted(order[order >= 0].tolist()) == list(range(n))
+        assert len(order) <= 1.25 * n + 16
+        room, pos = 0, 0
+        for op in ops:
+            kind, cnt = int(op) & 15, int(op) >> 4
+            leaves = cnt + 2 if kind in (2, 3, 6, 7) else cnt if kind in (1, 10) else 0      # csrc/walk.cuh op numbers
+            if leaves == 0:
+                continue
+            assert leaves <= 16
+            if leaves > room:
+                assert np.all(order[pos:pos + room] == -1)       # what the kernel skips is padding
+                pos += room
+                room = 16
+            assert np.all(order[pos:pos + leaves] >= 0)
+            pos += leaves
+            room -= leaves
+        assert pos == len(order)
+
+
+@pytest.mark.parametrize("n,G,comb", [(5, 40, False), (33, 9, False), (129, 300, False), (150, 260, True), (1000, 20, False),
+                                      (5000, 12, False)])
+def test_padded_variant_of_the_walk_kernels_on_the_host(padded, n, G, comb):
+    lib, emul_p = padded
+    rng = np.random.default_rng(700 + n)
+    names = synth.isolate_names(n)
+    nested = names[0]
+    if comb:
+        for nm in names[1:]:
+            nested = [nested, nm]
+    else:
+        nested = synth.make_tree(n, 700 + n)
+    ops, order, units, left, right = _compile_padded(lib, nested)
+    m = (rng.random((G, n)) < rng.uniform(0.02, 0.98, size=G)[:, None]).astype(np.uint8)
+    lab = (rng.random(n) < 0.4).astype(np.uint8)
+    m[0] = lab
+    W32p = ((len(order) + 31) // 32 + 3) // 4 * 4
+    shift = 1
+    while (1 << shift) <= n // 2:
+        shift += 1
+    Gs = (G + 31) // 32 * 32
+    genesT = np.zeros((W32p, Gs), dtype=np.uint32)
+    genesT[:, :G] = _pack_stream(m, order, W32p).T
+    genesT, ops = np.ascontiguousarray(genesT), np.ascontiguousarray(ops)
+    P, seed = 9, 5
+    ref = O.permute(left, right, m, lab, P=P, seed=seed, trait=0, want_hits=True)
+    pairs = np.full((G, 3), -7, dtype=np.int32)
+    lab0 = _pack_stream(lab[None, :], order, W32p)[0]
+    assert emul_p.emul_pairs(_ptr(ops), len(ops), _ptr(lab0), _ptr(genesT), Gs, G, W32p, shift, units, _ptr(pairs)) == 0
+    assert np.array_equal(pairs, ref["pairs"])
+    labs = np.stack([O.shuffle_labels(seed, 0, p, lab) for p in range(P)])
+    labelsW = np.ascontiguousarray(_pack_stream(labs, order, W32p))
+    unperm = np.ascontiguousarray(ref["pairs"], dtype=np.int32)
+    for ppi in (1, 4):
+        hits = np.zeros(((P + ppi - 1) // ppi, G), dtype=np.uint8)
+        assert emul_p.emul_permute(_ptr(ops), len(ops), _ptr(labelsW), P, ppi, _ptr(genesT), Gs, G, W32p, shift, units,
+                                   _ptr(unperm), _ptr(hits)) == 0
+        got = np.stack([(hits[p // ppi] >> (p % ppi)) & 1 for p in range(P)], axis=1)
+        assert np.array_equal(got, ref["hits"])
+    _no_carries(emul_p)
+
+
 def _balanced(names):
     if len(names) == 1:
         return names[0]

@@ -29,21 +29,32 @@ C_OPS_BYTES = 2 * 12288          # csrc/walk.cuh: c_ops, then c_labels, in const
 
 
 def workload(n_isolates, seed, n_perms, perm_seed):
-    """tree program + label vectors in walk order, exactly as sb_set_tree / sb_permute stage them"""
+    """tree program + label vectors in walk order, exactly as sb_set_tree / sb_permute stage them
+    (the tree compiler is the one of the library named by SCOARY_B200_LIB, so variants get their own program)"""
+    import ctypes
     from oracle import oracle as O
-    from scoary_b200 import synth
+    from scoary_b200 import _lib, synth
     from scoary_b200 import tree as treemod
-    from test_tree_program import compile_tree
     nested = synth.make_tree(n_isolates, seed)
-    ops, order, units, names = compile_tree(nested)
-    col = {n: j for j, n in enumerate(synth.isolate_names(n_isolates))}
+    left, right, names = treemod.flatten(nested)
+    lib = _lib.load()
+    n = len(left)
+    ops = np.zeros(6 * n + 64, dtype=np.uint16)
+    order = np.full(3 * n + 64, -9, dtype=np.int32)
+    n_pos, depth = ctypes.c_int32(), ctypes.c_int32()
+    ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p)      # noqa: E731
+    k = lib.sb_debug_compile_tree2(ptr(left), ptr(right), n, ptr(ops), len(ops), ptr(order), len(order),
+                                   ctypes.byref(n_pos), ctypes.byref(depth))
+    assert k > 0, lib.sb_last_error(None)
+    ops, order = ops[:k], order[:n_pos.value]              # order: leaf id per stream position, -1 = pad position
+    col = {nm: j for j, nm in enumerate(synth.isolate_names(n_isolates))}
     traits = synth.make_traits(n_isolates, 1, seed)
-    lab = (traits[0][np.asarray([col[n] for n in names])] == 1).astype(np.uint8)      # by leaf id
-    W32 = (n_isolates + 31) // 32
-    W32p = (W32 + 3) // 4 * 4
+    lab = (traits[0][np.asarray([col[nm] for nm in names])] == 1).astype(np.uint8)      # by leaf id
+    W32p = ((len(order) + 31) // 32 + 3) // 4 * 4
     labs = np.stack([O.shuffle_labels(perm_seed, 0, p, lab) for p in range(n_perms)])
     walk = np.zeros((n_perms, W32p * 32), dtype=np.uint8)
-    walk[:, :n_isolates] = labs[:, order[:n_isolates]]
+    real = order >= 0
+    walk[:, np.nonzero(real)[0]] = labs[:, order[real]]
     labelsW = np.ascontiguousarray(np.packbits(walk, axis=1, bitorder="little")).view(np.uint32).reshape(n_perms, W32p)
     shift = 1
     while (1 << shift) <= n_isolates // 2:
