@@ -25,7 +25,7 @@ step() {   # step <seconds> <log> <command...>
 }
 
 step 900 pytest_gpu.log python -m pytest tests -m gpu -x -q
-step 600 sweep.log python tools/sweep_variants.py run
+step 1200 sweep.log python tools/sweep_variants.py run
 step 300 launches.log ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
     --log-file "$out/launches.csv" python bench.py --steps 2 --warmup 3 --no-cpu-baseline
 step 420 ncu_walk.log ncu --set full --clock-control none --import-source on -k regex:walk_permute -c 1 \

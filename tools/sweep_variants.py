@@ -70,7 +70,12 @@ import numpy as np
 from scoary_b200 import synth
 from scoary_b200.engine import Engine
 G, N, P, seed = 50000, 5000, 240, 20260903
-traits = synth.make_traits(N, 1, seed); bits = synth.make_genes_packed(G, N, seed, traits=traits)
+traits = synth.make_traits(N, 1, seed)
+cache = "/tmp/sb_sweep_bits_%d_%d_%d.npy" % (G, N, seed)          # the same matrix for every variant: generate once
+if os.path.exists(cache):
+    bits = np.load(cache)
+else:
+    bits = synth.make_genes_packed(G, N, seed, traits=traits); np.save(cache, bits)
 col = {n: j for j, n in enumerate(synth.isolate_names(N))}
 e = Engine(0); e.set_profiling(True); e.set_genes(bits, N); e.set_trait_vector(0, traits[0]); e.set_tree_nested(0, synth.make_tree(N, seed), col)
 best = {}
