@@ -71,7 +71,7 @@ from scoary_b200 import synth
 from scoary_b200.engine import Engine
 G, N, P, seed = 50000, 5000, 240, 20260903
 traits = synth.make_traits(N, 1, seed)
-cache = "/tmp/sb_sweep_bits_%d_%d_%d.npy" % (G, N, seed)          # the same matrix for every variant: generate once
+cache = "/tmp/sb_sweep_bits_{}_{}_{}.npy".format(G, N, seed)          # the same matrix for every variant: generate once
 if os.path.exists(cache):
     bits = np.load(cache)
 else:
