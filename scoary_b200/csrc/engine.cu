@@ -202,7 +202,8 @@ void free_trait(TraitSlot &s)
 struct Program {
     std::vector<uint16_t> ops;
     std::vector<int32_t> leaf_of_pos;   // walk position -> leaf id
-    int depth = 0;
+    int depth = 0;                      // packed 16-bit entries pending at most (shared-memory stack units)
+    int depth32 = 0;                    // 32-bit entries pending at most (per-thread local memory, <= WALK_STACK32)
 };
 
 // SB_WALK_PADDED: give every leaf-consuming op a place inside ONE leaf window.  Leaf runs are split at the window
@@ -372,7 +373,7 @@ bool compile_tree(const int32_t *left, const int32_t *right, int32_t n_internal,
     //   CHERRY_B16 LEAF_B16* [MERGE_AB16]        -> CHERRY_B16(_MERGE)(n)
     //   LEAF_A16+ / LEAF_A32+ / MERGE_POP*+      -> one op with a count
     out.ops.clear();
-    int depth = 0, sp = 0;
+    int depth = 0, sp = 0, depth32 = 0, sp32 = 0;   // the two stacks of walk.cuh: 16-bit entries, 32-bit entries
     auto emit = [&](int kind, size_t cnt) {
         out.ops.push_back((uint16_t)((cnt << sb::OP_TYPE_BITS) | (unsigned)kind));
     };
@@ -410,9 +411,9 @@ bool compile_tree(const int32_t *left, const int32_t *right, int32_t n_internal,
                                kind == sb::OP_MERGE_POP32 || kind == sb::OP_MERGE_POPW);
             if (runs) while (j < n_raw && raw[j] == kind) ++j;
             size_t cnt = j - i;
-            if (kind == sb::OP_PUSH32) { sp += 2; depth = std::max(depth, sp); }
+            if (kind == sb::OP_PUSH32) { sp32 += 1; depth32 = std::max(depth32, sp32); }
             if (kind == sb::OP_MERGE_POP16 || kind == sb::OP_MERGE_POPW) sp -= (int)cnt;
-            if (kind == sb::OP_MERGE_POP32) sp -= 2 * (int)cnt;
+            if (kind == sb::OP_MERGE_POP32) sp32 -= (int)cnt;
             while (cnt > 0) {
                 const size_t c = std::min<size_t>(cnt, (size_t)sb::OP_MAX_COUNT);
                 emit(kind, runs ? c : 1);
@@ -422,8 +423,10 @@ bool compile_tree(const int32_t *left, const int32_t *right, int32_t n_internal,
         }
     }
     out.ops.push_back((uint16_t)sb::OP_END);
-    if (sp != 0) { err = "internal error: unbalanced stack program"; return false; }
+    if (sp != 0 || sp32 != 0) { err = "internal error: unbalanced stack program"; return false; }
+    if (depth32 > sb::WALK_STACK32) { err = "tree too deep for the 32-bit DP stack"; return false; }
     out.depth = depth;   // stack units of 10 words per gene pair
+    out.depth32 = depth32;
     if (sb::WALK_PADDED && !pad_stream(out, err)) return false;
     return true;
 }

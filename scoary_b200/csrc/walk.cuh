@@ -125,6 +125,12 @@ __device__ __forceinline__ unsigned sb_sign_mask2(unsigned x)
 constexpr int WALK_THREADS = SB_WALK_THREADS;
 constexpr bool WALK_PADDED = SB_WALK_PADDED != 0;
 constexpr int WALK_WINDOW = 16;           // leaves per gene window (two genes per 32-bit register)
+// The DP stack is split.  Packed 16-bit entries (subtrees of <= 127 leaves: at most 4-5 pending at any time, pushed
+// and popped all the time) live in shared memory; 32-bit entries (the few large subtrees along the spine of the tree:
+// ~46 pushes per walk at 5 000 leaves, long-lived) live in per-thread local memory.  Before the split the long-lived
+// 32-bit entries sat UNDER the hot 16-bit ones and doubled the shared memory a block needs (8 units at 5 000 leaves,
+// 11 at 10 000, against 4 now).
+constexpr int WALK_STACK32 = 10;          // 32-bit entries a thread can hold (a balanced 32 766-leaf tree needs 9)
 constexpr int WALK_NEG = -(1 << 30);   // unreachable; keys stay < 2^28 (n_leaves <= 32766), so inv+inv >= INT_MIN
 constexpr uint32_t SHUFFLE_DOMAIN = 0x5C0A27u;
 
@@ -543,6 +549,8 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR
     const int scale = K - (1 << WALK_SH16);
     WalkState16 a16[NS], b16[NS];
     int sp = 0, pc = 0;                // sp counts 32-bit words per thread; pc is a BYTE offset into c_ops
+    int sp32 = 0;                      // 32-bit entries held in stk32
+    int stk32[WALK_STACK32 * EW * NLAB * NP];   // local memory: touched by PUSH32 / MERGE_POP32 only
     int room = 0, win = 0;             // leaves left in the current 16-leaf window; windows opened so far
     // gx[q]: the current 16-leaf window of pair q's two genes (gene 2q in bits 0..15, gene 2q+1 in
     // bits 16..31, consumed from bit 0 / bit 16); gy[q]: the following 16 leaves; gnext: prefetch
@@ -773,30 +781,31 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR
                 walk_merge<DUAL>(r1, acc[2 * q + 1], b32[(2 * q + 1) % NP]);
             }
             break;
-        case OP_PUSH32:
+        case OP_PUSH32: {
+            int *s = stk32 + sp32 * (EW * NLAB * NP);
 #pragma unroll
             for (int k = 0; k < NLAB * NP; ++k) {
-                int *s = stk + (sp + k * EW) * T;
 #pragma unroll
                 for (int c = 0; c < 5; ++c) {
-                    s[c * T] = acc[k].p[c];
-                    if constexpr (DUAL) s[(5 + c) * T] = acc[k].a[c];
+                    s[k * EW + c] = acc[k].p[c];
+                    if constexpr (DUAL) s[k * EW + 5 + c] = acc[k].a[c];
                 }
             }
-            sp += EW * NLAB * NP;
+            ++sp32;
             break;
+        }
         case OP_MERGE_POP32:
 #pragma unroll 1
             for (int i = 0; i < cnt; ++i) {
-                sp -= EW * NLAB * NP;
+                --sp32;
+                const int *s = stk32 + sp32 * (EW * NLAB * NP);
 #pragma unroll
                 for (int k = 0; k < NLAB * NP; ++k) {
                     WalkState L;
-                    const int *s = stk + (sp + k * EW) * T;
 #pragma unroll
                     for (int c = 0; c < 5; ++c) {
-                        L.p[c] = s[c * T];
-                        if constexpr (DUAL) L.a[c] = s[(5 + c) * T];
+                        L.p[c] = s[k * EW + c];
+                        if constexpr (DUAL) L.a[c] = s[k * EW + 5 + c];
                     }
                     walk_merge<DUAL>(L, acc[k], b32[k % NP]);
                 }

@@ -27,6 +27,18 @@ void fill(sb::WalkArgs &A, const uint32_t *genesT, int64_t Gs, int64_t S, int W3
     A.W32p = W32p; A.shift = shift;
 }
 
+// the simulated shared memory is followed by guard words: a kernel that needs more stack than the compiler
+// reported (stack_units) tramples them and the call fails
+constexpr size_t GUARD = 4096;
+constexpr int CANARY = 0x5CA7A11;
+
+bool guard_intact(const std::vector<int> &smem, size_t words)
+{
+    for (size_t i = words; i < smem.size(); ++i)
+        if (smem[i] != CANARY) return false;
+    return true;
+}
+
 int load_program(const uint16_t *ops, int n_ops)
 {
     if (n_ops > sb::C_OPS_MAX) return -1;
@@ -52,7 +64,8 @@ int emul_pairs(const uint16_t *ops, int n_ops, const uint32_t *labels, const uin
     fill(A, genesT, Gs, S, W32p, shift);
     A.pairs = pairs;
     const int T = sb::WALK_THREADS;
-    std::vector<int> smem((size_t)10 * (stack_units > 0 ? stack_units : 1) * T * sb::WALK_NPAIR);
+    const size_t words = (size_t)10 * (stack_units > 0 ? stack_units : 1) * T * sb::WALK_NPAIR;
+    std::vector<int> smem(words + GUARD, CANARY);
     const int64_t per_block = (int64_t)T * sb::WALK_NP;
     for (int64_t tile = 0; tile < (S + per_block - 1) / per_block; ++tile)
         for (int tid = 0; tid < T; ++tid) {
@@ -61,7 +74,7 @@ int emul_pairs(const uint16_t *ops, int n_ops, const uint32_t *labels, const uin
             sb::sb_emul_shared = smem.data();
             sb::walk_pairs_kernel(A);
         }
-    return 0;
+    return guard_intact(smem, words) ? 0 : -2;
 }
 
 // K5: hits[ceil(P / ppi)][S] for the labellings labelsW[P][W32p] (walk order)
@@ -76,7 +89,8 @@ int emul_permute(const uint16_t *ops, int n_ops, const uint32_t *labelsW, int P,
     A.n_perms = P; A.ppi = ppi; A.items_per_tile = (P + ppi - 1) / ppi; A.chunk_base = 0;
     A.unperm = unperm; A.hits = hits;
     const int T = sb::WALK_THREADS;
-    std::vector<int> smem((size_t)5 * (stack_units > 0 ? stack_units : 1) * T * sb::WALK_NPAIR * sb::WALK_NLAB);
+    const size_t words = (size_t)5 * (stack_units > 0 ? stack_units : 1) * T * sb::WALK_NPAIR * sb::WALK_NLAB;
+    std::vector<int> smem(words + GUARD, CANARY);
     const int64_t per_block = (int64_t)T * sb::WALK_NP;
     for (int64_t tile = 0; tile < (S + per_block - 1) / per_block; ++tile)
         for (int chunk = 0; chunk < A.items_per_tile; ++chunk)
@@ -86,7 +100,7 @@ int emul_permute(const uint16_t *ops, int n_ops, const uint32_t *labelsW, int P,
                 sb::sb_emul_shared = smem.data();
                 sb::walk_permute_kernel(A);
             }
-    return 0;
+    return guard_intact(smem, words) ? 0 : -2;
 }
 
 }  // extern "C"

@@ -129,6 +129,18 @@ def _check_permute(lib, n, G, comb, ppi):
     _no_carries(lib)
 
 
+def test_shared_stack_size_reported_by_the_compiler_is_tight(emul):
+    """The emulated shared memory ends in guard words: with the compiler's stack_units the kernels stay inside
+    (every other test checks rc == 0); with one unit less a 1000-leaf tree tramples the guard (rc == -2)."""
+    c = _setup(1000, 20, 4242, False)
+    lab0 = _pack_walk_order(c["lab"][None, :], c["order"], c["W32p"])[0]
+    pairs = np.full((20, 3), -7, dtype=np.int32)
+    args = (_ptr(c["ops"]), len(c["ops"]), _ptr(lab0), _ptr(c["genesT"]), c["Gs"], 20, c["W32p"], c["shift"])
+    assert c["units"] >= 2
+    assert emul.emul_pairs(*args, c["units"], _ptr(pairs)) == 0
+    assert emul.emul_pairs(*args, c["units"] - 1, _ptr(pairs)) == -2
+
+
 def _no_carries(lib):
     """SB_ADD2_NC (walk.cuh) is a plain 32-bit add on the device: its low 16-bit lane must never carry"""
     lib.emul_carry_violations.restype = ctypes.c_longlong
