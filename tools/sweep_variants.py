@@ -20,16 +20,17 @@ VARIANTS = {
     "prmt": "-DSB_WALK_PRMT=1",               # gene-bit masks by PRMT sign replication (tools/k5_model.py: -3.4 % instructions)
     "prmt_npair3_mb3": "-DSB_WALK_PRMT=1 -DSB_WALK_NPAIR=3 -DSB_WALK_MINBLOCKS=3",
     # two labellings in lockstep per thread (shares program decode, stream bookkeeping and gene masks: -20 % instructions
-    # per walk by tools/k5_model.py); the DP stack doubles, so 64-thread blocks keep 10 warps per SM
-    "nlab2_t64_mb5": "-DSB_WALK_NLAB=2 -DSB_WALK_THREADS=64 -DSB_WALK_MINBLOCKS=5",
-    "nlab2_t128_mb2": "-DSB_WALK_NLAB=2 -DSB_WALK_MINBLOCKS=2",
-    "nlab2_prmt_t64_mb5": "-DSB_WALK_NLAB=2 -DSB_WALK_PRMT=1 -DSB_WALK_THREADS=64 -DSB_WALK_MINBLOCKS=5",
+    # per walk by tools/k5_model.py); 165 registers: 12 warps per SM
+    "nlab2_t64_mb6": "-DSB_WALK_NLAB=2 -DSB_WALK_THREADS=64 -DSB_WALK_MINBLOCKS=6",
+    "nlab2_t128_mb3": "-DSB_WALK_NLAB=2 -DSB_WALK_MINBLOCKS=3",
+    "nlab2_prmt_t64_mb6": "-DSB_WALK_NLAB=2 -DSB_WALK_PRMT=1 -DSB_WALK_THREADS=64 -DSB_WALK_MINBLOCKS=6",
     # leaf stream padded by the host compiler so that no op crosses a window: no general path in the kernels
     # (static code 42 -> 33 KB, 80 % of the executed instructions inside 5.6 KB, -1.7 % instructions)
     "padded": "-DSB_WALK_PADDED=1",
     "padded_prmt": "-DSB_WALK_PADDED=1 -DSB_WALK_PRMT=1",
-    "padded_nlab2_t64_mb5": "-DSB_WALK_PADDED=1 -DSB_WALK_NLAB=2 -DSB_WALK_THREADS=64 -DSB_WALK_MINBLOCKS=5",
-    "padded_nlab2_prmt_t64_mb5": "-DSB_WALK_PADDED=1 -DSB_WALK_NLAB=2 -DSB_WALK_PRMT=1 -DSB_WALK_THREADS=64 -DSB_WALK_MINBLOCKS=5",
+    "padded_nlab2_t64_mb6": "-DSB_WALK_PADDED=1 -DSB_WALK_NLAB=2 -DSB_WALK_THREADS=64 -DSB_WALK_MINBLOCKS=6",
+    "padded_nlab2_prmt_t64_mb6": "-DSB_WALK_PADDED=1 -DSB_WALK_NLAB=2 -DSB_WALK_PRMT=1 -DSB_WALK_THREADS=64 -DSB_WALK_MINBLOCKS=6",
+    "padded_mb6": "-DSB_WALK_PADDED=1 -DSB_WALK_MINBLOCKS=6",
     "minblocks4": "-DSB_WALK_MINBLOCKS=4",
     "minblocks6": "-DSB_WALK_MINBLOCKS=6",
     "threads96_mb6": "-DSB_WALK_THREADS=96 -DSB_WALK_MINBLOCKS=6",
