@@ -330,10 +330,12 @@ SB_DEV void merge_pass(const int L[5], const int R[5], int out[5], int bsup, int
     const int ML = max5(L), MR = max5(R);
 #pragma unroll
     for (int c = 0; c < 4; ++c) out[c] = __viaddmax_s32(L[c], MR, ML + R[c]);
-    const int nf = L[4] + R[4];
-    const int pp = __viaddmax_s32(L[0], R[3], L[3] + R[0]) + bsup;
-    const int ap = __viaddmax_s32(L[1], R[2], L[2] + R[1]) + bopp;
-    out[4] = max(__vimax3_s32(nf, pp, ap), WALK_NEG);
+    // out[4] = max(L4 + R4, pp + bsup, ap + bopp, unreachable) as a chain of fused add-max steps: the clamp rides on
+    // the first one and the pair bonuses on the last two (7 instructions instead of 9)
+    const int nf = __viaddmax_s32(L[4], R[4], WALK_NEG);
+    const int pp = __viaddmax_s32(L[0], R[3], L[3] + R[0]);
+    const int ap = __viaddmax_s32(L[1], R[2], L[2] + R[1]);
+    out[4] = __viaddmax_s32(ap, bopp, __viaddmax_s32(pp, bsup, nf));
 }
 
 // acc <- combine(L, acc)
@@ -458,10 +460,11 @@ SB_DEV void merge_pass16(const unsigned L[5], const unsigned R[5], unsigned out[
     const unsigned ML = max5_16(L), MR = max5_16(R);
 #pragma unroll
     for (int c = 0; c < 4; ++c) out[c] = __viaddmax_s16x2(L[c], MR, SB_ADD2_NC(ML, R[c]));   // ML is reachable
-    const unsigned nf = SB_VADD2(L[4], R[4]);
-    const unsigned pp = SB_ADD2_NC(__viaddmax_s16x2(L[0], R[3], SB_VADD2(L[3], R[0])), bsup);
-    const unsigned ap = SB_ADD2_NC(__viaddmax_s16x2(L[1], R[2], SB_VADD2(L[2], R[1])), bopp);
-    out[4] = SB_VMAXS2(__vimax3_s16x2(nf, pp, ap), NEG16x2);
+    // out[4] as in merge_pass: clamp and pair bonuses ride on fused add-max steps
+    const unsigned nf = __viaddmax_s16x2(L[4], R[4], NEG16x2);
+    const unsigned pp = __viaddmax_s16x2(L[0], R[3], SB_VADD2(L[3], R[0]));
+    const unsigned ap = __viaddmax_s16x2(L[1], R[2], SB_VADD2(L[2], R[1]));
+    out[4] = __viaddmax_s16x2(ap, bopp, __viaddmax_s16x2(pp, bsup, nf));
 }
 
 // acc <- combine(L, acc)
