@@ -130,7 +130,7 @@ constexpr int WALK_WINDOW = 16;           // leaves per gene window (two genes p
 // ~46 pushes per walk at 5 000 leaves, long-lived) live in per-thread local memory.  Before the split the long-lived
 // 32-bit entries sat UNDER the hot 16-bit ones and doubled the shared memory a block needs (8 units at 5 000 leaves,
 // 11 at 10 000, against 4 now).
-constexpr int WALK_STACK32 = 10;          // 32-bit entries a thread can hold (a balanced 32 766-leaf tree needs 9)
+constexpr int WALK_STACK32 = 8;           // 32-bit entries a thread can hold (a balanced 32 766-leaf tree needs 7)
 constexpr int WALK_NEG = -(1 << 30);   // unreachable; keys stay < 2^28 (n_leaves <= 32766), so inv+inv >= INT_MIN
 constexpr uint32_t SHUFFLE_DOMAIN = 0x5C0A27u;
 
