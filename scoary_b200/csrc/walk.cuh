@@ -18,7 +18,7 @@
 //   CHERRY_A / CHERRY_B   A (or B) <- node of two leaves
 //   LEAF_A xN / LEAF_B xN A (or B) <- combine(A (or B), next leaf)      N times
 //   MERGE_AB              A <- combine(A, B)
-//   PUSH                  spill A to the shared-memory stack
+//   PUSH                  spill A to the DP stack (packed entries: shared memory; 32-bit entries: local memory)
 //   MERGE_POP xN          A <- combine(pop(), A)                         N times
 // (each in a packed 16-bit form for subtrees of <= 127 leaves -- two genes per register,
 // .S16x2 DPX instructions -- and a 32-bit form above that, with WIDEN steps in between)
@@ -538,7 +538,8 @@ constexpr int WALK_NLAB = SB_WALK_NLAB;
 // labellings at c_labels[lab_off[l] ..].  gcol[k] points at gene k's column of genesT; genes 2q and 2q+1
 // share the packed accumulators of pair q; state index s = l * NPAIR + q (32-bit: l * NP + k).  Every branch is on block-uniform data (the program and
 // the label bits); per-gene data only feeds selects.  The program always ends in 32-bit mode.
-// Stack entries take EW = 10 (DUAL) or 5 words per gene pair in 16-bit form, twice that in 32-bit form.
+// Stack entries take EW = 10 (DUAL) or 5 words: per gene pair in the packed shared-memory stack, per gene in the
+// 32-bit local-memory stack (WALK_STACK32).
 template <int NPAIR, int NLAB, bool DUAL>
 SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR], const int (&lab_off)[NLAB],
                                           int *stk, WalkState (&acc)[NLAB * 2 * NPAIR],
