@@ -28,6 +28,11 @@ step 900 pytest_gpu.log python -m pytest tests -m gpu -x -q
 step 1200 sweep.log python tools/sweep_variants.py run
 step 300 launches.log ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
     --log-file "$out/launches.csv" python bench.py --steps 2 --warmup 3 --no-cpu-baseline
+# the same command without ncu's cache flush between kernels: DRAM bytes and executed instructions of every launch as
+# they are inside a running step (the --set full capture below is cold-cache: its dram bytes re-read the gene matrix)
+step 300 step_dram.log ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum,gpu__time_duration.sum \
+    --cache-control none --clock-control none -c 400 --csv \
+    --log-file "$out/step_dram.csv" python bench.py --steps 2 --warmup 3 --no-cpu-baseline
 step 420 ncu_walk.log ncu --set full --clock-control none --import-source on -k regex:walk_permute -c 1 \
     -o "$out/prof_walk" -f python tools/probe.py --perms 60
 step 300 ncu_fisher.log ncu --set full --clock-control none --import-source on -k regex:fisher_kernel -c 1 \
