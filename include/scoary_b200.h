@@ -174,15 +174,16 @@ int sb_upgma(sb_ctx *ctx, int32_t *merges);
  * the gene presence/absence file.  Dialect: csv.reader(skipinitialspace=True, delimiter=d) as
  * the reference opens it (methods.py:350-351).
  * sb_csv_row_starts: byte offsets of the data rows (all rows after the header row); pass
- *   row_starts = NULL to count.  Returns the number of data rows or -1.
+ *   row_starts = NULL to count.  Returns the number of data rows or -1.  A '"' opens a quoted
+ *   field only at the start of a field (csv.reader's rule): `5" nuclease` is plain text.
  * sb_csv_pack_rows: for each data row, bit i of the output row = cell of column keep_cols[i] is
  *   present (not "", "0" or "-", methods.py:476-487); bits uint64[n_rows][W].  lead_ranges
  *   [n_rows][n_lead][2] receives the byte range of the fields lead_cols[] (identifier,
  *   annotation, ...); begin < 0 marks a field with escaped quotes that the host must unescape
  *   (its range starts at -begin - 1).  row_fields[n_rows] = number of fields in the row.
  *   Returns 0, or -(row + 1) of the first row too short for the requested columns. */
-int64_t sb_csv_row_starts(const char *buf, int64_t len, int64_t *row_starts, int64_t max_rows,
-                          int64_t *header_end);
+int64_t sb_csv_row_starts(const char *buf, int64_t len, char delimiter, int64_t *row_starts,
+                          int64_t max_rows, int64_t *header_end);
 int64_t sb_csv_pack_rows(const char *buf, int64_t len, char delimiter, const int64_t *row_starts,
                          int64_t n_rows, const int32_t *keep_cols, int32_t n_keep, uint64_t *bits,
                          int32_t W, const int32_t *lead_cols, int32_t n_lead, int64_t *lead_ranges,

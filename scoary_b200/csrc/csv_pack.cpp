@@ -83,22 +83,37 @@ extern "C" {
 
 // Row starts of the data rows (everything after the first row).  row_starts may be NULL to count.
 // Returns the number of data rows (empty trailing lines are ignored), or -1 on error.
-int64_t sb_csv_row_starts(const char *buf, int64_t len, int64_t *row_starts, int64_t max_rows, int64_t *header_end)
+int64_t sb_csv_row_starts(const char *buf, int64_t len, char delimiter, int64_t *row_starts, int64_t max_rows,
+                          int64_t *header_end)
 {
     if (!buf || len < 0) return -1;
     const char *p = buf, *e = buf + len;
-    bool inq = false;
-    // skip the header row
+    // The reader's state machine (Python's _csv.c, excel dialect, skipinitialspace, non-strict): a '"' opens a quoted
+    // field only as the first character of a field (after the skipped spaces); anywhere else it is a literal, so an
+    // unquoted cell such as `5" nuclease` does not swallow the row terminator.  Inside a quoted field "" is a literal
+    // quote and newlines belong to the field; after the closing quote the rest up to the delimiter is plain text.
+    enum { START_FIELD, IN_FIELD, IN_QUOTED, QUOTE_IN_QUOTED };
     auto next_row = [&](const char *q) {
+        int st = START_FIELD;
         for (; q < e; ++q) {
             const char c = *q;
-            if (c == '"') inq = !inq;                 // "" toggles twice: still correct for row scanning
-            else if (!inq && c == '\n') return q + 1;
-            else if (!inq && c == '\r') { return (q + 1 < e && q[1] == '\n') ? q + 2 : q + 1; }
+            if (st == IN_QUOTED) {
+                if (c == '"') st = QUOTE_IN_QUOTED;
+                continue;
+            }
+            if (c == '\n') return q + 1;
+            if (c == '\r') return (q + 1 < e && q[1] == '\n') ? q + 2 : q + 1;
+            if (c == delimiter) { st = START_FIELD; continue; }
+            if (st == START_FIELD) {
+                if (c == ' ') continue;
+                st = (c == '"') ? IN_QUOTED : IN_FIELD;
+            } else if (st == QUOTE_IN_QUOTED) {
+                st = (c == '"') ? IN_QUOTED : IN_FIELD;
+            }
         }
         return e;
     };
-    p = next_row(p);
+    p = next_row(p);   // skip the header row
     if (header_end) *header_end = p - buf;
     int64_t n = 0;
     while (p < e) {

@@ -197,9 +197,11 @@ def Csv_to_dic_Roary(genefile, delimiter, grabcols, startcol=14, allowed_isolate
         genecol, nugcol, anncol = 0, 1, 2
         firstcolnames = header[0:3]
     src_cols = [startcol + c for c in keep_cols]
+    table = None
     if native:
         table = _native_gene_table(path, delimiter, roaryfile, genecol, nugcol, anncol, grabcols, header, src_cols,
                                    strain_names_allowed)
+    if table is not None:        # None: ragged rows -- the csv-module loop below is the semantic reference for those
         if opened:
             opened.close()
         s = _popcount_rows(table.bits)
@@ -251,11 +253,12 @@ def _native_gene_table(path, delimiter, roaryfile, genecol, nugcol, anncol, grab
     lib = _lib.load()
     with open(path, "rb") as fh:
         buf = fh.read()
-    n = lib.sb_csv_row_starts(buf, len(buf), None, 0, None)
+    delim = delimiter.encode()[:1]
+    n = lib.sb_csv_row_starts(buf, len(buf), delim, None, 0, None)
     if n < 0:
         sys.exit("CRITICAL: Could not read gene presence absence file.")
     starts = np.empty(max(n, 1), dtype=np.int64)
-    lib.sb_csv_row_starts(buf, len(buf), starts.ctypes.data_as(ctypes.c_void_p), n, None)
+    lib.sb_csv_row_starts(buf, len(buf), delim, starts.ctypes.data_as(ctypes.c_void_p), n, None)
     W = eng.words_for(len(src_cols))
     bits = np.empty((n, W), dtype=np.uint64)
     lead = sorted(set([genecol, nugcol, anncol] + list(grabcols)))
@@ -263,13 +266,15 @@ def _native_gene_table(path, delimiter, roaryfile, genecol, nugcol, anncol, grab
     keep_arr = np.asarray(src_cols, dtype=np.int32)
     ranges = np.empty((n, len(lead), 2), dtype=np.int64)
     nfields = np.empty(max(n, 1), dtype=np.int32)
-    rc = lib.sb_csv_pack_rows(buf, len(buf), delimiter.encode()[:1], starts.ctypes.data_as(ctypes.c_void_p), n,
+    rc = lib.sb_csv_pack_rows(buf, len(buf), delim, starts.ctypes.data_as(ctypes.c_void_p), n,
                               keep_arr.ctypes.data_as(ctypes.c_void_p), len(src_cols),
                               bits.ctypes.data_as(ctypes.c_void_p), W, lead_arr.ctypes.data_as(ctypes.c_void_p),
                               len(lead), ranges.ctypes.data_as(ctypes.c_void_p), nfields.ctypes.data_as(ctypes.c_void_p))
     if rc != 0:
         sys.exit("CRITICAL: Could not read gene presence absence file. Verify that this file is a proper Roary "
                  "file using the specified delimiter (default is ',').")
+    if n and np.any(nfields[:n] != len(header)):
+        return None              # rows wider or narrower than the header: leave them to the csv module
     slot = {c: k for k, c in enumerate(lead)}
 
     def field(r, c):
@@ -368,11 +373,14 @@ def StoreUPGMAtreeToFile(upgmatree, outdir, time=""):
 
 
 def ReadTreeFromFile(path):
-    """Custom tree (-n).  The reference uses ete3 (scoary/nwkhandler.py), which is
-    not installable here; binary Newick trees with optional branch lengths and
-    quoted or bare names are parsed directly."""
-    with open(path) as fh:
-        nested = treemod.from_scoary_newick(fh.read())
+    """Custom tree (-n), nwkhandler.ReadTreeFromFile (scoary/nwkhandler.py:10-22).  The reference uses ete3, which is
+    not installable here; treemod.from_newick reads the same files (branch lengths, support values / internal labels,
+    quoted or bare names) and resolves polytomies the way ete3's resolve_polytomy(recursive=True) does."""
+    try:
+        with open(path) as fh:
+            nested = treemod.from_newick(fh.read())
+    except (OSError, ValueError) as e:
+        sys.exit("Corrupted or non-existing custom tree file? %s" % e)
     return nested, treemod.leaves(nested)
 
 

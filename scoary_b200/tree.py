@@ -7,8 +7,6 @@ the same tree flattened into child-index arrays (include/scoary_b200.h,
 sb_set_tree).  Everything here is iterative: UPGMA trees on real data are deep
 (height ~N/8) and recursion would hit Python's limit long before N = 10 000.
 """
-import ast
-
 import numpy as np
 
 
@@ -121,51 +119,94 @@ def to_scoary_newick(tree):
     return "".join(parts).replace("[", "(").replace("]", ")") + ";"
 
 
-def from_scoary_newick(text):
-    """Inverse of to_scoary_newick for files Scoary wrote itself (quoted names,
-    no branch lengths), e.g. exampledata/ExampleTree.nwk."""
-    body = text.strip().rstrip(";").strip()
-    # iterative parse of the restricted grammar: ( item , item ) with quoted leaves
-    stack, cur, i, n = [], None, 0, len(body)
-    root = None
+def _resolve_polytomy(children):
+    """ete3's TreeNode.resolve_polytomy(recursive=True), which the reference applies to every custom tree
+    (scoary/nwkhandler.py:19): a node with children c0 .. c(k-1), k > 2, becomes the ladder
+    [[...[[c(k-2), c(k-1)], c(k-3)] ..., c1], c0].  A node with one child is that child."""
+    if len(children) == 1:
+        return children[0]
+    node = [children[-2], children[-1]]
+    for ch in reversed(children[:-2]):
+        node = [node, ch]
+    return node
+
+
+def from_newick(text):
+    """Newick text -> nested 2-lists of leaf names, as nwkhandler.ReadTreeFromFile / RecTree2List build them
+    (scoary/nwkhandler.py:10-40): branch lengths, internal node labels / support values and [comments] are
+    discarded, quotes around leaf names are stripped, polytomies (e.g. the trifurcating root of an unrooted ML
+    tree) are resolved like ete3 does.  Also reads the files Scoary writes itself (to_scoary_newick: quoted names,
+    no lengths).  Iterative: UPGMA trees are deep.  Raises ValueError on malformed input."""
+    body = text.strip()
+    n = len(body)
+    seps = ",();"
+
+    def skip_meta(i):       # label, ':length', [comment] after a name or a ')': up to the next structural character
+        while i < n and body[i] not in seps:
+            if body[i] == "[":
+                j = body.find("]", i + 1)
+                if j < 0:
+                    raise ValueError("unterminated [comment]")
+                i = j + 1
+            elif body[i] in "'\"":      # a quoted internal label
+                j = body.find(body[i], i + 1)
+                if j < 0:
+                    raise ValueError("unterminated quoted name")
+                i = j + 1
+            else:
+                i += 1
+        return i
+
+    stack, root, i = [], None, 0
     while i < n:
         ch = body[i]
         if ch == "(":
-            new = []
-            if cur is not None:
-                cur.append(new)
-                stack.append(cur)
-            cur = new
+            stack.append([])
             i += 1
         elif ch == ")":
-            if len(cur) != 2:
-                raise ValueError("tree is not binary (resolve polytomies first)")
-            done = cur
-            cur = stack.pop() if stack else None
-            if cur is None:
-                root = done
+            if not stack:
+                raise ValueError("unbalanced parentheses")
+            kids = stack.pop()
+            if not kids:
+                raise ValueError("empty node")
+            node = _resolve_polytomy(kids)
+            i = skip_meta(i + 1)
+            if stack:
+                stack[-1].append(node)
+            else:
+                root = node
                 break
-            i += 1
-        elif ch in "'\"":
-            j = body.index(ch, i + 1)
-            cur.append(ast.literal_eval(body[i:j + 1]))
-            i = j + 1
         elif ch in ", \t\r\n":
             i += 1
-        else:   # unquoted name up to , ) or :
-            j = i
-            while j < n and body[j] not in ",():":
-                j += 1
-            name = body[i:j].strip()
-            if j < n and body[j] == ":":   # skip a branch length
-                while j < n and body[j] not in ",)":
+        elif ch == ";":
+            break
+        elif ch == "[":
+            i = skip_meta(i)
+        else:
+            if ch in "'\"":
+                j = body.find(ch, i + 1)
+                if j < 0:
+                    raise ValueError("unterminated quoted name")
+                name, i = body[i + 1:j], j + 1
+            else:           # bare name up to : , ( ) ; [
+                j = i
+                while j < n and body[j] not in ",():;[":
                     j += 1
-            if name:            # an empty name is the branch length / label of a closed subtree
-                cur.append(name)
-            i = j
-    if root is None:
-        raise ValueError("could not parse tree")
+                name, i = body[i:j].strip(), j
+            i = skip_meta(i)
+            if not stack:
+                raise ValueError("a tree needs at least two leaves")
+            stack[-1].append(name.lstrip("'\"").rstrip("'\""))     # nwkhandler.py:33
+    if root is None or stack:
+        raise ValueError("unbalanced parentheses")
+    if body[i:].strip().lstrip(";").strip():
+        raise ValueError("text after the end of the tree")
+    if isinstance(root, str):
+        raise ValueError("a tree needs at least two leaves")
     return root
+
+
+from_scoary_newick = from_newick
 
 
 def from_merges(names, merges):

@@ -12,7 +12,7 @@ int main(void)
     /* native CSV packer on a tiny table: 2 data rows, isolate columns 3..5 */
     const char *csv = "\"Gene\",\"x\",\"y\",\"i1\",\"i2\",\"i3\"\n\"g1\",\"a\",\"b\",\"locus\",\"\",\"0\"\n\"g2\",\"c\",\"d\",\"-\",\"q\",\"r\"\n";
     int64_t starts[4], hdr_end = 0;
-    int64_t n = sb_csv_row_starts(csv, (int64_t)strlen(csv), starts, 4, &hdr_end);
+    int64_t n = sb_csv_row_starts(csv, (int64_t)strlen(csv), ',', starts, 4, &hdr_end);
     if (n != 2) { printf("row count %lld\n", (long long)n); return 2; }
     int32_t keep[3] = {3, 4, 5}, lead[1] = {0}, nf[2];
     uint64_t bits[2 * 2];

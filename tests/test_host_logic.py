@@ -129,8 +129,28 @@ def test_tree_utils_roundtrip_and_prune():
     assert treemod.prune(t, ["c"]) == [["a", "b"], [["d", ["e", "f"]], "g"]]
     assert treemod.prune(["a", "b"], ["a", "b"]) is None
     assert treemod.from_scoary_newick("((A:0.1,B:0.2):0.3,C:1);") == [["A", "B"], "C"]
-    with pytest.raises(ValueError):
-        treemod.from_scoary_newick("(A,B,C);")
+    # support values / internal labels are discarded, polytomies resolved like ete3's
+    # resolve_polytomy(recursive=True) (scoary/nwkhandler.py:19): [[..[[c(k-2), c(k-1)], c(k-3)].., c1], c0]
+    assert treemod.from_newick("((a:0.1,b:0.2)0.95:0.3,(c:1,d:1)node7:0.5)root;") == [["a", "b"], ["c", "d"]]
+    assert treemod.from_newick("(A,B,C);") == [["B", "C"], "A"]
+    assert treemod.from_newick("(A:1,B:2,(C:1,D:1)100:3,E:0.5):0.0;") == [[[["C", "D"], "E"], "B"], "A"]
+    assert treemod.from_newick("('it s'[&&NHX:x=1]:1,(\"q r\":2,(x)):3);") == ["it s", ["q r", "x"]]
+    for bad in ["", "A;", "((A,B);", "(A,B));", "(A,'B);"]:
+        with pytest.raises(ValueError):
+            treemod.from_newick(bad)
+
+
+def test_custom_tree_errors_exit_like_the_reference(tmp_path):
+    """nwkhandler.py:16-17: sys.exit("Corrupted or non-existing custom tree file? ...")"""
+    bad = tmp_path / "bad.nwk"
+    bad.write_text("((A,B);")
+    for path in (str(bad), str(tmp_path / "missing.nwk")):
+        with pytest.raises(SystemExit) as ex:
+            M.ReadTreeFromFile(path)
+        assert "Corrupted or non-existing custom tree file?" in str(ex.value.code)
+    ok = tmp_path / "ok.nwk"
+    ok.write_text("((a:0.1,b:0.2)0.95:0.3,c:1,d:2);\n")
+    assert M.ReadTreeFromFile(str(ok)) == ([["c", "d"], ["a", "b"]], ["c", "d", "a", "b"])
 
 
 def test_errors_exit_like_the_reference(inputs, fake_engine):
@@ -206,6 +226,42 @@ def test_native_csv_packer_equals_python_parser(tmp_path, monkeypatch, inputs):
     with pytest.raises(SystemExit) as ex, open(short) as fh:
         M.Csv_to_dic_Roary(fh, ",", [], startcol=14)
     assert "Could not read gene presence absence file" in str(ex.value.code)
+
+
+def test_native_csv_packer_embedded_quotes_and_ragged_rows(tmp_path, monkeypatch):
+    """a '"' inside an unquoted cell (`5" nuclease`) is a literal for csv.reader -- it must not swallow the
+    row terminator in the native row scanner -- and rows wider than the header are left to the csv module."""
+    import random
+    rnd = random.Random(11)
+    N = 9
+    header = ",".join('"%s"' % c for c in M.ROARY_COLUMNS[:14]) + "," + ",".join("I%d" % j for j in range(N))
+    tricky_ann = ['5" nuclease', 'x "quoted" y', '"starts quoted" tail"', '"a ""b"" c"', 'odd " count', '"multi\nline, cell"',
+                  ' "after space"', 'plain', '3\'-5" exo"nuclease"', '""']
+    for trial, wide_row in [(0, None), (1, 3)]:
+        lines = [header]
+        for g in range(40):
+            ann = tricky_ann[g % len(tricky_ann)] if g % 2 == 0 else rnd.choice(tricky_ann)
+            cells = [rnd.choice(['"l_%d"' % g, "l%d" % g, '', '0', '-', '""', 'a"b', '"-"']) for _ in range(N)]
+            row = 'g%d,nug %d"x,%s,1,2,3,4,5,6,7,8,9,10,11,%s' % (g, g, ann, ",".join(cells))
+            if wide_row is not None and g == wide_row:
+                row += ",extra"
+            lines.append(row)
+        path = str(tmp_path / ("quotes%d.csv" % trial))
+        with open(path, "w", newline="") as fh:
+            fh.write("\r\n".join(lines[:20]) + "\n" + "\n".join(lines[20:]) + "\n")
+        monkeypatch.delenv("SCOARY_B200_PY_CSV", raising=False)
+        with open(path) as fh:
+            a = M.Csv_to_dic_Roary(fh, ",", [3], startcol=14)
+        monkeypatch.setenv("SCOARY_B200_PY_CSV", "1")
+        with open(path, newline="") as fh:
+            b = M.Csv_to_dic_Roary(fh, ",", [3], startcol=14)
+        with open(path, newline="") as fh:
+            want = [r[0] for r in __import__("csv").reader(fh, skipinitialspace=True)][1:]
+        ta, tb = a["Roarydic"], b["Roarydic"]
+        assert len(want) == 40 and tb.names == [w for w in dict.fromkeys(want)]
+        assert ta.names == tb.names and ta.nugn == tb.nugn and ta.annotation == tb.annotation
+        assert np.array_equal(ta.bits, tb.bits) and ta.extra == tb.extra
+    monkeypatch.delenv("SCOARY_B200_PY_CSV", raising=False)
 
 
 @pytest.mark.parametrize("name,types", [("Example", None), ("generated", None), ("generated", "snp,del")])
