@@ -66,6 +66,8 @@ typedef struct {
     int64_t launches_permute;       /* launches of the K5 kernel while profiling */
     int32_t sm_count;
     int32_t reserved;
+    int64_t calls_transposed;       /* sb_permute calls that ran threads = labellings (few genes, many permutations) */
+    double ms_epilogue;             /* device epilogue: sort, Bonferroni / Benjamini-Hochberg, binomial tests */
 } sb_stats_t;
 
 /* ---- life cycle -------------------------------------------------------- */
@@ -80,6 +82,11 @@ const char *sb_last_error(const sb_ctx *ctx);
 int sb_set_stream(sb_ctx *ctx, void *cuda_stream);
 int sb_synchronize(sb_ctx *ctx);
 int sb_set_profiling(sb_ctx *ctx, int on);
+/* K5 launch shape of sb_permute: 0 = chosen per call (default), 1 = threads are genes, 2 = threads are labellings
+ * (the "few genes x many permutations" shape left after decideifbreak, scoary/methods.py:1022-1024, :1295-1310:
+ * the DP is symmetric in the gene and the trait bit of a leaf, so the same walk runs with the roles exchanged).
+ * Results are identical in every mode. */
+int sb_set_permute_mode(sb_ctx *ctx, int mode);
 int sb_stats(sb_ctx *ctx, sb_stats_t *out);
 int sb_stats_reset(sb_ctx *ctx);
 
@@ -123,6 +130,15 @@ int sb_set_tree(sb_ctx *ctx, int32_t t, const int32_t *left, const int32_t *righ
 int sb_contingency_fisher(sb_ctx *ctx, int32_t t, int32_t *counts, double *p, uint64_t *hash);
 int sb_contingency_fisher_device(sb_ctx *ctx, int32_t t, int32_t *d_counts, double *d_p,
                                  uint64_t *d_hash);
+/* The same for the traits in slots t0 .. t0 + n_traits - 1 in ONE pass over the gene rows: the
+ * reference loops traits outside genes (methods.py:771, :791) and so reads every gene once per
+ * trait; here the trait vectors are staged in shared memory and each row is read once (C4: 340
+ * instead of 1 288 bytes per test).  Outputs are trait-major: counts int32[n_traits][G][4],
+ * p double[n_traits][G], hash uint64[n_traits][G][2]; same values as n_traits single calls. */
+int sb_contingency_fisher_multi(sb_ctx *ctx, int32_t t0, int32_t n_traits, int32_t *counts, double *p,
+                                uint64_t *hash);
+int sb_contingency_fisher_multi_device(sb_ctx *ctx, int32_t t0, int32_t n_traits, int32_t *d_counts,
+                                       double *d_p, uint64_t *d_hash);
 
 /* ConvertUPGMAtoPhyloTree (methods.py:1386-1402) for S genes: max contrasting
  * pairs and, given those, max supporting / opposing pairs (classes.py:199-592).

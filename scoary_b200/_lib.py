@@ -32,6 +32,8 @@ class SbStats(ctypes.Structure):
         ("launches_permute", ctypes.c_int64),
         ("sm_count", ctypes.c_int32),
         ("reserved", ctypes.c_int32),
+        ("calls_transposed", ctypes.c_int64),
+        ("ms_epilogue", ctypes.c_double),
     ]
 
 
@@ -44,6 +46,7 @@ SIGNATURES = {
     "sb_set_stream": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "sb_synchronize": (ctypes.c_int, [ctypes.c_void_p]),
     "sb_set_profiling": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "sb_set_permute_mode": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "sb_stats": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(SbStats)]),
     "sb_stats_reset": (ctypes.c_int, [ctypes.c_void_p]),
     "sb_set_genes": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32]),
@@ -52,6 +55,10 @@ SIGNATURES = {
     "sb_set_tree": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p]),
     "sb_contingency_fisher": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "sb_contingency_fisher_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "sb_contingency_fisher_multi": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
+                                                   ctypes.c_void_p, ctypes.c_void_p]),
+    "sb_contingency_fisher_multi_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
+                                                          ctypes.c_void_p, ctypes.c_void_p]),
     "sb_pairwise": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
     "sb_pairwise_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
     "sb_permute": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32,

@@ -21,12 +21,6 @@
 
 #include "../../include/scoary_b200.h"
 #include "fisher.cuh"
-#ifndef SB_FISHER_V2
-#define SB_FISHER_V2 0   // 1: the experimental four-genes-per-warp kernel of fisher2.cuh (not measured yet)
-#endif
-#if SB_FISHER_V2
-#include "fisher2.cuh"
-#endif
 #include "walk.cuh"
 #include "tree_build.cuh"
 
@@ -46,11 +40,12 @@ struct TimedEvent {
 struct TraitSlot {
     bool has_trait = false;
     std::vector<uint64_t> h_value, h_mask;
-    uint64_t *d_value = nullptr, *d_mask = nullptr;
+    uint64_t *d_value = nullptr, *d_mask = nullptr;   // into the context's trait arena (not owned)
     // tree
     bool has_tree = false;
     bool finalized = false;        // labels + genesT built for the current genes/trait/tree
     int32_t n_leaves = 0, n_internal = 0, W32 = 0, W32p = 0, depth = 0, shift = 0, n_ops = 0;
+    int32_t lab_base = 0;                // first label word behind the program in the constant pool (walk.cuh)
     std::vector<int32_t> h_leaf_to_col, h_leaf_of_pos;
     std::vector<uint16_t> h_ops;
     int32_t *d_walk_col = nullptr, *d_leaf_of_pos = nullptr;
@@ -77,6 +72,8 @@ struct sb_ctx {
     bool own_genes = false;
     uint64_t *d_genes_buf = nullptr;   // the context's own allocation (reused across sb_set_genes calls)
     size_t genes_cap = 0;
+    uint64_t *d_trait_arena = nullptr;  // [SB_MAX_TRAITS][2][W]: value, mask of every trait slot, so that a Fisher launch
+                                        // finds the vectors of consecutive traits in one block
     // lut
     double2 *d_lut = nullptr;
     int32_t lut_n = -1;
@@ -85,6 +82,8 @@ struct sb_ctx {
     void *d_scratch[12] = {nullptr};
     size_t scratch_bytes[12] = {0};
     int32_t *h_pinned_counter = nullptr;
+    unsigned long long *d_walks = nullptr;   // walks of rounds whose slot count lives on the device
+    int permute_mode = 0;                    // 0 auto, 1 threads = genes, 2 threads = labellings (sb_set_permute_mode)
     // stats / profiling
     sb_stats_t stats;
     bool profiling = false;
@@ -191,8 +190,8 @@ void free_tree_storage(TraitSlot &s)
 
 void free_trait(TraitSlot &s)
 {
-    cudaFree(s.d_value); s.d_value = nullptr;
-    cudaFree(s.d_mask); s.d_mask = nullptr;
+    s.d_value = nullptr;
+    s.d_mask = nullptr;
     s.has_trait = false;
     s.finalized = false;
 }
@@ -453,8 +452,11 @@ int set_genes_common(sb_ctx *ctx, int64_t G, int32_t N, int32_t W)
     if (W < (N + 63) / 64 || (W & 1)) return fail(ctx, SB_ERR_ARG, "sb_set_genes: W must be even and >= ceil(N/64)");
     ctx->d_genes = nullptr;
     ctx->own_genes = false;
-    if (N != ctx->N || W != ctx->W) {
+    if (N != ctx->N || W != ctx->W || !ctx->d_trait_arena) {
         for (auto &s : ctx->traits) { free_trait(s); free_tree(s); }
+        if (ctx->d_trait_arena) SB_CUDA(ctx, cudaFree(ctx->d_trait_arena));
+        ctx->d_trait_arena = nullptr;
+        SB_CUDA(ctx, cudaMalloc(&ctx->d_trait_arena, sizeof(uint64_t) * SB_MAX_TRAITS * 2 * (size_t)W));
     }
     for (auto &s : ctx->traits) {   // gene-dependent derived data is stale
         s.finalized = false;
@@ -520,56 +522,52 @@ int finalize_slot(sb_ctx *ctx, int32_t t)
     return SB_OK;
 }
 
-int launch_fisher(sb_ctx *ctx, int32_t t, int32_t *d_counts, double *d_p, uint64_t *d_hash)
+// Contingency tables + Fisher p for traits t0 .. t0 + nT - 1, every gene row read once per launch of up to
+// FISHER_MAX_TRAITS traits.  Outputs are trait-major: counts [nT][G][4], p [nT][G], hash [nT][G][2].
+int launch_fisher(sb_ctx *ctx, int32_t t0, int32_t nT, int32_t *d_counts, double *d_p, uint64_t *d_hash)
 {
-    if (t < 0 || t >= SB_MAX_TRAITS) return fail(ctx, SB_ERR_ARG, "trait index out of range");
-    TraitSlot &s = ctx->traits[t];
+    if (nT < 1 || t0 < 0 || t0 + nT > SB_MAX_TRAITS) return fail(ctx, SB_ERR_ARG, "trait index out of range");
     if (!ctx->d_genes) return fail(ctx, SB_ERR_STATE, "genes not set (sb_set_genes)");
-    if (!s.has_trait) return fail(ctx, SB_ERR_STATE, "trait not set (sb_set_trait)");
-    sb::FisherArgs A;
-    A.genes = ctx->d_genes; A.G = ctx->G; A.W = ctx->W; A.Wn = (ctx->N + 63) / 64;
-    A.tvalue = s.d_value; A.tmask = s.d_mask;
-    A.lut = ctx->d_lut; A.lut_n = ctx->lut_n;
-    A.counts = d_counts; A.p = d_p; A.hash = d_hash;
+    for (int32_t t = t0; t < t0 + nT; ++t)
+        if (!ctx->traits[t].has_trait) return fail(ctx, SB_ERR_STATE, "trait not set (sb_set_trait)");
     const size_t row_bytes = (size_t)ctx->W * 8;
     const size_t lut_bytes = sizeof(double2) * (size_t)(ctx->lut_n + 1);
-#if SB_FISHER_V2
-    constexpr size_t NW = sb::FISHER2_THREADS / 32, ROWS_PER_WARP = sb::F2_GENES;
-    constexpr int FTHREADS = sb::FISHER2_THREADS;
-#else
-    constexpr size_t NW = sb::FISHER_THREADS / 32, ROWS_PER_WARP = 1;
-    constexpr int FTHREADS = sb::FISHER_THREADS;
-#endif
-    // [2 mbarriers per warp][value&mask, mask][2 row buffers (of ROWS_PER_WARP rows) per warp][LUT if it fits]
-    const size_t fixed = 16 * NW + 2 * row_bytes + 2 * NW * ROWS_PER_WARP * row_bytes;
-    const size_t budget = (size_t)ctx->max_smem_optin;
-    if (fixed > budget) return fail(ctx, SB_ERR_ARG, "row too long for shared memory");
-    const bool lut_smem = fixed + lut_bytes <= budget;
-    const size_t smem = fixed + (lut_smem ? lut_bytes : 0);
-    const int64_t rows_per_cta = (int64_t)(NW * ROWS_PER_WARP);
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((ctx->G + rows_per_cta - 1) / rows_per_cta, ctx->sm_count));
+    constexpr size_t NW = sb::FISHER_THREADS / 32, ROWS_PER_WARP = sb::F_GENES;
     const bool hash = d_hash != nullptr;
-    Timed tm(ctx, CAT_FISHER);
-#if SB_FISHER_V2
-#define SB_FISHER_KERNEL sb::fisher2_kernel
-#else
-#define SB_FISHER_KERNEL sb::fisher_kernel
-#endif
+    const int64_t G = ctx->G;
+    for (int32_t c0 = 0; c0 < nT; c0 += sb::FISHER_MAX_TRAITS) {
+        const int32_t n = std::min<int32_t>(sb::FISHER_MAX_TRAITS, nT - c0);
+        sb::FisherArgs A;
+        A.genes = ctx->d_genes; A.G = G; A.W = ctx->W; A.Wn = (ctx->N + 63) / 64;
+        A.traits = ctx->d_trait_arena + (size_t)(t0 + c0) * 2 * ctx->W; A.n_traits = n;
+        A.lut = ctx->d_lut; A.lut_n = ctx->lut_n;
+        A.counts = d_counts ? d_counts + (size_t)c0 * G * 4 : nullptr;
+        A.p = d_p ? d_p + (size_t)c0 * G : nullptr;
+        A.hash = d_hash ? d_hash + (size_t)c0 * G * 2 : nullptr;
+        // [2 mbarriers per warp][per trait: value & mask, mask][2 buffers of 4 rows per warp][LUT if it fits]
+        const size_t fixed = 16 * NW + 2 * row_bytes * n + 2 * NW * ROWS_PER_WARP * row_bytes;
+        const size_t budget = (size_t)ctx->max_smem_optin - 256;     // minus the kernel's static shared memory
+        if (fixed > budget) return fail(ctx, SB_ERR_ARG, "row too long for shared memory");
+        const bool lut_smem = fixed + lut_bytes <= budget;
+        const size_t smem = fixed + (lut_smem ? lut_bytes : 0);
+        const int64_t rows_per_cta = (int64_t)(NW * ROWS_PER_WARP);
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((G + rows_per_cta - 1) / rows_per_cta, ctx->sm_count));
+        Timed tm(ctx, CAT_FISHER);
 #define SB_LAUNCH_FISHER(L, H)                                                                                     \
     do {                                                                                                           \
-        SB_CUDA(ctx, cudaFuncSetAttribute(SB_FISHER_KERNEL<L, H>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+        SB_CUDA(ctx, cudaFuncSetAttribute(sb::fisher_kernel<L, H>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                                           (int)smem));                                                             \
-        SB_FISHER_KERNEL<L, H><<<grid, FTHREADS, smem, ctx->stream>>>(A);                                          \
+        sb::fisher_kernel<L, H><<<grid, sb::FISHER_THREADS, smem, ctx->stream>>>(A);                               \
     } while (0)
-    if (lut_smem && hash) SB_LAUNCH_FISHER(true, true);
-    else if (lut_smem) SB_LAUNCH_FISHER(true, false);
-    else if (hash) SB_LAUNCH_FISHER(false, true);
-    else SB_LAUNCH_FISHER(false, false);
+        if (lut_smem && hash) SB_LAUNCH_FISHER(true, true);
+        else if (lut_smem) SB_LAUNCH_FISHER(true, false);
+        else if (hash) SB_LAUNCH_FISHER(false, true);
+        else SB_LAUNCH_FISHER(false, false);
 #undef SB_LAUNCH_FISHER
-#undef SB_FISHER_KERNEL
-    ctx->stats.kernel_launches += 1;
-    ctx->stats.tests_contingency += ctx->G;
-    SB_CUDA(ctx, cudaGetLastError());
+        ctx->stats.kernel_launches += 1;
+        ctx->stats.tests_contingency += G * n;
+        SB_CUDA(ctx, cudaGetLastError());
+    }
     return SB_OK;
 }
 
@@ -585,16 +583,25 @@ void fill_walk_args(const TraitSlot &s, sb::WalkArgs &A, const int64_t *d_gene_i
 {
     memset(&A, 0, sizeof A);
     A.genesT = s.d_genesT; A.Gs = s.Gs; A.gene_idx = d_gene_idx; A.S = S; A.S_total = S; A.slot_idx = nullptr;
-    A.W32p = s.W32p; A.shift = s.shift;
+    A.W32p = s.W32p; A.shift = s.shift; A.lab_base = s.lab_base;
 }
 
-// the compiled program of slot s -> constant memory (stream ordered)
+// label vectors (or, in transposed launches, gene rows) that fit behind the program of slot s
+int label_capacity(const TraitSlot &s) { return (sb::C_POOL_WORDS - s.lab_base) / s.W32p; }
+
+// the compiled program of slot s -> the start of the constant pool (stream ordered; sb_set_tree checked the size)
 int upload_program(sb_ctx *ctx, const TraitSlot &s)
 {
-    if ((int)s.h_ops.size() > sb::C_OPS_MAX) return fail(ctx, SB_ERR_ARG, "tree program too long for constant memory");
-    if (s.W32p > sb::C_LABEL_WORDS / sb::PERMS_PER_ITEM_MAX) return fail(ctx, SB_ERR_ARG, "too many leaves for constant memory");
-    SB_CUDA(ctx, cudaMemcpyToSymbolAsync(sb::c_ops, s.h_ops.data(), sizeof(uint16_t) * s.h_ops.size(), 0,
+    SB_CUDA(ctx, cudaMemcpyToSymbolAsync(sb::c_pool, s.h_ops.data(), sizeof(uint16_t) * s.h_ops.size(), 0,
                                          cudaMemcpyHostToDevice, ctx->stream));
+    return SB_OK;
+}
+
+// n vectors of W32p words (device memory) -> the label area of the constant pool
+int upload_labels(sb_ctx *ctx, const TraitSlot &s, const uint32_t *d_src, int n)
+{
+    SB_CUDA(ctx, cudaMemcpyToSymbolAsync(sb::c_pool, d_src, sizeof(uint32_t) * (size_t)n * s.W32p,
+                                         sizeof(uint32_t) * (size_t)s.lab_base, cudaMemcpyDeviceToDevice, ctx->stream));
     return SB_OK;
 }
 
@@ -603,8 +610,8 @@ int launch_pairwise(sb_ctx *ctx, int32_t t, const int64_t *d_gene_idx, int64_t S
     TraitSlot &s = ctx->traits[t];
     int rc = upload_program(ctx, s);
     if (rc) return rc;
-    SB_CUDA(ctx, cudaMemcpyToSymbolAsync(sb::c_labels, s.d_labels0, sizeof(uint32_t) * s.W32p, 0,
-                                         cudaMemcpyDeviceToDevice, ctx->stream));
+    rc = upload_labels(ctx, s, s.d_labels0, 1);
+    if (rc) return rc;
     sb::WalkArgs A;
     fill_walk_args(s, A, d_gene_idx, S);
     A.pairs = d_pairs;
@@ -635,12 +642,115 @@ int launch_shuffle(sb_ctx *ctx, int32_t t, int32_t P, uint64_t seed, uint32_t *d
     return SB_OK;
 }
 
+// ---- K5 launch plans ---------------------------------------------------------
+// How well a launch shape fills the GPU: lanes that carry a walk x resident block slots that get a block.
+double fill_fraction(int64_t threads_domain, int64_t blocks_y, int slots)
+{
+    const int64_t per_block = (int64_t)sb::WALK_THREADS * sb::WALK_NP;
+    const int64_t tiles = (threads_domain + per_block - 1) / per_block;
+    const double lanes = (double)threads_domain / (double)(tiles * per_block);
+    const double blocks = (double)(tiles * blocks_y);
+    return lanes * std::min(1.0, blocks / (double)slots);
+}
+
+// Transposed launches (walk.cuh): threads = labellings, constant rows = the genes of result slots list[e] / e.
+// Walks labellings [perm_lo, perm_hi) for n_rows genes; hit bytes go to d_hits [slot][Ps].
+int launch_rows(sb_ctx *ctx, const TraitSlot &s, const uint32_t *d_labelsT, int64_t Ps, int perm_lo, int perm_hi,
+                const int64_t *d_gene_idx, const int32_t *d_list, int64_t n_rows, const int32_t *d_unperm,
+                uint8_t *d_hits, uint32_t *d_rowsW)
+{
+    if (n_rows <= 0 || perm_hi <= perm_lo) return SB_OK;
+    {
+        const int64_t n = n_rows * s.W32p;
+        sb::gather_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(s.d_genesT, s.Gs, s.W32p, d_gene_idx,
+                                                                                    d_list, (int)n_rows, d_rowsW);
+        ctx->stats.kernel_launches += 1;
+        SB_CUDA(ctx, cudaGetLastError());
+    }
+    const int cap = label_capacity(s);
+    const int64_t Pn = perm_hi - perm_lo;
+    const int64_t per_block = (int64_t)sb::WALK_THREADS * sb::WALK_NP;
+    const int64_t tiles = (Pn + per_block - 1) / per_block;
+    int ppi = sb::PERMS_PER_ITEM_MAX;      // rows per block: fewer when that is what it takes to give every SM work
+    while (ppi > 1 && tiles * ((std::min<int64_t>(cap, n_rows) + ppi - 1) / ppi) < 2LL * 7 * ctx->sm_count) ppi /= 2;
+    const size_t smem = sizeof(int) * 5 * (size_t)std::max(1, s.depth) * sb::WALK_THREADS * sb::WALK_NPAIR;
+    SB_CUDA(ctx, cudaFuncSetAttribute(sb::walk_permute_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int64_t base = 0; base < n_rows; base += cap) {
+        const int n = (int)std::min<int64_t>(cap, n_rows - base);
+        int rc = upload_labels(ctx, s, d_rowsW + (size_t)base * s.W32p, n);
+        if (rc) return rc;
+        sb::WalkArgs A;
+        memset(&A, 0, sizeof A);
+        A.genesT = d_labelsT + perm_lo; A.Gs = Ps; A.S = Pn; A.S_total = Ps;
+        A.slot_idx = d_list; A.row_base = (int32_t)base;
+        A.W32p = s.W32p; A.shift = s.shift; A.lab_base = s.lab_base;
+        A.n_perms = n; A.ppi = ppi; A.items_per_tile = (n + ppi - 1) / ppi;
+        A.unperm = d_unperm; A.hits = d_hits + perm_lo;
+        dim3 grid((unsigned)tiles, (unsigned)A.items_per_tile, 1);
+        Timed tm(ctx, CAT_PERMUTE);
+        sb::walk_permute_kernel<true><<<grid, sb::WALK_THREADS, smem, ctx->stream>>>(A);
+        ctx->stats.kernel_launches += 1;
+        ctx->stats.tests_walks += (int64_t)n * Pn;
+        SB_CUDA(ctx, cudaGetLastError());
+    }
+    return SB_OK;
+}
+
+int launch_permute_transposed(sb_ctx *ctx, TraitSlot &s, const int64_t *d_gene_idx, int64_t S, int32_t P,
+                              int32_t early_stop, const int32_t *d_rmin, const int32_t *d_unperm,
+                              const uint32_t *d_labelsW, int32_t *d_r, int32_t *d_n_done)
+{
+    const int64_t Ps = ((int64_t)P + 31) / 32 * 32;
+    int rc = ensure_scratch(ctx, 9, sizeof(uint32_t) * (size_t)s.W32p * (size_t)Ps);
+    if (rc) return rc;
+    rc = ensure_scratch(ctx, 10, sizeof(uint32_t) * (size_t)s.W32p * (size_t)S);
+    if (rc) return rc;
+    rc = ensure_scratch(ctx, 1, (size_t)S * (size_t)Ps);
+    if (rc) return rc;
+    rc = ensure_scratch(ctx, 8, sizeof(int32_t) * ((size_t)S + 4));
+    if (rc) return rc;
+    uint32_t *d_labelsT = (uint32_t *)ctx->d_scratch[9], *d_rowsW = (uint32_t *)ctx->d_scratch[10];
+    uint8_t *d_hits = (uint8_t *)ctx->d_scratch[1];
+    int32_t *d_list = (int32_t *)ctx->d_scratch[8], *d_counter = d_list + S;
+    {
+        Timed tm(ctx, CAT_SHUFFLE);
+        dim3 grid((unsigned)((P + 31) / 32), (unsigned)((s.W32p + 31) / 32), 1);
+        sb::transpose_labels_kernel<<<grid, 256, 0, ctx->stream>>>(d_labelsW, P, s.W32p, Ps, d_labelsT);
+        ctx->stats.kernel_launches += 1;
+        SB_CUDA(ctx, cudaGetLastError());
+    }
+    auto reduce = [&](const int32_t *list, int64_t n, int n_avail) -> int {
+        Timed tm(ctx, CAT_REDUCE);
+        sb::reduce_hit_rows_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, ctx->stream>>>(
+            d_hits, Ps, list, (int)n, n_avail, P, early_stop, d_rmin, d_r, d_n_done, d_list, d_counter);
+        ctx->stats.kernel_launches += 1;
+        SB_CUDA(ctx, cudaGetLastError());
+        return SB_OK;
+    };
+    // Reference-rule mode: most genes stop within the first few dozen labellings (methods.py:1360-1363), so the
+    // first tile of labellings is walked for everything and only the genes still running see the rest.
+    const int first = early_stop ? (int)std::min<int64_t>(P, (int64_t)sb::WALK_THREADS * sb::WALK_NP) : P;
+    rc = launch_rows(ctx, s, d_labelsT, Ps, 0, first, d_gene_idx, nullptr, S, d_unperm, d_hits, d_rowsW);
+    if (rc) return rc;
+    SB_CUDA(ctx, cudaMemsetAsync(d_counter, 0, sizeof(int32_t), ctx->stream));
+    rc = reduce(nullptr, S, first);
+    if (rc || first >= P) return rc;
+    if (!ctx->h_pinned_counter) SB_CUDA(ctx, cudaMallocHost(&ctx->h_pinned_counter, sizeof(int32_t)));
+    SB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned_counter, d_counter, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const int64_t n_alive = *ctx->h_pinned_counter;
+    if (n_alive == 0) return SB_OK;
+    rc = launch_rows(ctx, s, d_labelsT, Ps, first, P, d_gene_idx, d_list, n_alive, d_unperm, d_hits, d_rowsW);
+    if (rc) return rc;
+    return reduce(d_list, n_alive, P);   // appends nothing: n_avail == P
+}
+
 // d_unperm: [S][3] device (input, already computed); d_r / d_n_done outputs
 int launch_permute(sb_ctx *ctx, int32_t t, const int64_t *d_gene_idx, int64_t S, int32_t P, uint64_t seed,
                    int32_t early_stop, const int32_t *d_rmin, const int32_t *d_unperm, int32_t *d_r, int32_t *d_n_done)
 {
     TraitSlot &s = ctx->traits[t];
-    // scratch 0: labelsW [P][W32p]; scratch 1: hit bytes [n_chunks][S] + work counters
+    // scratch 0: labelsW [P][W32p]; scratch 1: hit bytes of one slice; scratch 8: work lists + counters
     int rc = ensure_scratch(ctx, 0, sizeof(uint32_t) * (size_t)P * s.W32p);
     if (rc) return rc;
     uint32_t *d_labelsW = (uint32_t *)ctx->d_scratch[0];
@@ -649,89 +759,107 @@ int launch_permute(sb_ctx *ctx, int32_t t, const int64_t *d_gene_idx, int64_t S,
     rc = upload_program(ctx, s);
     if (rc) return rc;
 
+    const int slots = 7 * ctx->sm_count;                   // resident K5 blocks, roughly (5-6 per SM)
+    int label_cap = label_capacity(s);
+    if (label_cap >= sb::PERMS_PER_ITEM_MAX) label_cap = label_cap / sb::PERMS_PER_ITEM_MAX * sb::PERMS_PER_ITEM_MAX;
+    // threads = genes (the default) or threads = labellings: whichever shape fills the GPU better
+    bool transposed = false;
+    if (sb::WALK_NLAB == 1 && !sb::WALK_PADDED && ctx->permute_mode != 1) {
+        const double f_genes = fill_fraction(S, std::min(label_cap, P), slots);
+        const double f_perms = fill_fraction(early_stop ? std::min<int64_t>(P, (int64_t)sb::WALK_THREADS * sb::WALK_NP) : P,
+                                             std::min<int64_t>(label_cap, S), slots);
+        transposed = ctx->permute_mode == 2 || f_perms > (early_stop ? 3.0 : 1.5) * f_genes;
+    }
+    ctx->stats.calls_transposed += transposed ? 1 : 0;
+    if (transposed)
+        return launch_permute_transposed(ctx, s, d_gene_idx, S, P, early_stop, d_rmin, d_unperm, d_labelsW, d_r, d_n_done);
+
     // labellings per block: as many as 4 (fewer hit bytes), but few enough that one launch still
     // has a couple of blocks for every resident slot when only few genes are walked
-    const int label_cap = (sb::C_LABEL_WORDS / s.W32p) / sb::PERMS_PER_ITEM_MAX * sb::PERMS_PER_ITEM_MAX;
     const int64_t tiles_all = (S + (int64_t)sb::WALK_THREADS * sb::WALK_NP - 1) / ((int64_t)sb::WALK_THREADS * sb::WALK_NP);
     int ppi = sb::PERMS_PER_ITEM_MAX;
-    while (ppi > sb::WALK_NLAB && tiles_all * ((std::min(label_cap, P) + ppi - 1) / ppi) < 2LL * 7 * ctx->sm_count) ppi /= 2;
+    while (ppi > sb::WALK_NLAB && tiles_all * ((std::min(label_cap, P) + ppi - 1) / ppi) < 2LL * slots) ppi /= 2;
     if (early_stop) ppi = sb::WALK_NLAB;   // later rounds walk few genes: the fewest labellings per block keep every SM busy
-    const int n_chunks = (P + ppi - 1) / ppi;
-    int perms_per_launch = label_cap;
-    const int n_launches = (P + perms_per_launch - 1) / perms_per_launch;
-    rc = ensure_scratch(ctx, 1, (size_t)n_chunks * (size_t)S);
+    const int rows_max = (std::min(label_cap, P) + ppi - 1) / ppi;
+    rc = ensure_scratch(ctx, 1, (size_t)rows_max * (size_t)S);
     if (rc) return rc;
     uint8_t *d_hits = (uint8_t *)ctx->d_scratch[1];
 
     const size_t smem = walk_smem_bytes(s, false);
     if (smem > (size_t)ctx->max_smem_optin) return fail(ctx, SB_ERR_ARG, "tree too deep for shared memory");
-    SB_CUDA(ctx, cudaFuncSetAttribute(sb::walk_permute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SB_CUDA(ctx, cudaFuncSetAttribute(sb::walk_permute_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t per_block = (int64_t)sb::WALK_THREADS * sb::WALK_NP;
-    auto launch_slice = [&](int base, int n_perms, const int32_t *d_list, int64_t n_slots) -> int {
-        SB_CUDA(ctx, cudaMemcpyToSymbolAsync(sb::c_labels, d_labelsW + (size_t)base * s.W32p,
-                                             sizeof(uint32_t) * (size_t)n_perms * s.W32p, 0, cudaMemcpyDeviceToDevice,
-                                             ctx->stream));
+    // one slice: labellings [base, base + n_perms) for the slots of d_list (n_bound of them at most; the exact
+    // count is n_bound itself or, for rounds enqueued without a host round trip, *d_count), then the bookkeeping
+    auto slice = [&](int base, int n_perms, const int32_t *d_list, int64_t n_bound, const int32_t *d_count,
+                     int32_t *d_list_out, int32_t *d_count_out) -> int {
+        int rc2 = upload_labels(ctx, s, d_labelsW + (size_t)base * s.W32p, n_perms);
+        if (rc2) return rc2;
         sb::WalkArgs A;
-        fill_walk_args(s, A, d_gene_idx, n_slots);
+        fill_walk_args(s, A, d_gene_idx, n_bound);
         A.S_total = S;
+        A.S_dev = d_count;
         A.slot_idx = d_list;
         A.n_perms = n_perms;
         A.ppi = ppi;
         A.items_per_tile = (n_perms + ppi - 1) / ppi;
-        A.chunk_base = base / ppi;
+        A.chunk_base = 0;
         A.unperm = d_unperm;
         A.hits = d_hits;
-        const int64_t tiles = (n_slots + per_block - 1) / per_block;
+        const int64_t tiles = (n_bound + per_block - 1) / per_block;
         dim3 grid((unsigned)tiles, (unsigned)A.items_per_tile, 1);
-        Timed tm(ctx, CAT_PERMUTE);
-        sb::walk_permute_kernel<<<grid, sb::WALK_THREADS, smem, ctx->stream>>>(A);
+        {
+            Timed tm(ctx, CAT_PERMUTE);
+            sb::walk_permute_kernel<false><<<grid, sb::WALK_THREADS, smem, ctx->stream>>>(A);
+            ctx->stats.kernel_launches += 1;
+            if (!d_count) ctx->stats.tests_walks += n_bound * (int64_t)n_perms;   // else the device counts (d_walks)
+            SB_CUDA(ctx, cudaGetLastError());
+        }
+        Timed tm(ctx, CAT_REDUCE);
+        sb::accumulate_hits_kernel<<<(unsigned)((n_bound + 255) / 256), 256, 0, ctx->stream>>>(
+            d_hits, S, d_list, (int32_t)n_bound, d_count, base, n_perms, P, ppi, early_stop, d_rmin, d_r, d_n_done,
+            d_list_out, d_count_out, d_count ? ctx->d_walks : nullptr);
         ctx->stats.kernel_launches += 1;
-        ctx->stats.tests_walks += n_slots * (int64_t)n_perms;
         SB_CUDA(ctx, cudaGetLastError());
         return SB_OK;
     };
     if (!early_stop) {
-        for (int l = 0; l < n_launches; ++l) {
-            const int base = l * perms_per_launch;
-            rc = launch_slice(base, std::min(perms_per_launch, P - base), nullptr, S);
+        for (int base = 0; base < P; base += label_cap) {
+            rc = slice(base, std::min(label_cap, P - base), nullptr, S, nullptr, nullptr, nullptr);
             if (rc) return rc;
         }
-        Timed tm(ctx, CAT_REDUCE);
-        sb::reduce_hits_kernel<<<(unsigned)((S + 255) / 256), 256, 0, ctx->stream>>>(d_hits, S, n_chunks, ppi, P, 0, d_rmin, d_r,
-                                                                                    d_n_done);
-        ctx->stats.kernel_launches += 1;
-        SB_CUDA(ctx, cudaGetLastError());
         return SB_OK;
     }
-    // Reference-rule mode: walk the permutations in growing slices and keep only the genes the
-    // sequential rule has not stopped yet (most null genes stop after 31 permutations).
-    rc = ensure_scratch(ctx, 8, sizeof(int32_t) * (2 * (size_t)S + 4));
+    // Reference-rule mode: walk the permutations in growing slices and keep only the genes the sequential rule has
+    // not stopped yet.  The rule cannot fire before permutation 31 (methods.py:1360: i >= 30) and most null genes
+    // stop right there, so the first slice is 31 labellings; the survivors of the first two slices (the host reads
+    // their number, which bounds every later grid) then run slice after slice without a host round trip: each
+    // round's list length stays on the device (S_dev) and blocks past the end exit at once.
+    const int n_rounds_max = 4 + (P + label_cap - 1) / label_cap;
+    rc = ensure_scratch(ctx, 8, sizeof(int32_t) * (2 * (size_t)S + (size_t)n_rounds_max + 4));
     if (rc) return rc;
     int32_t *d_list[2] = {(int32_t *)ctx->d_scratch[8], (int32_t *)ctx->d_scratch[8] + S};
-    int32_t *d_counter = (int32_t *)ctx->d_scratch[8] + 2 * S;
+    int32_t *d_counters = (int32_t *)ctx->d_scratch[8] + 2 * S;     // one per round
+    SB_CUDA(ctx, cudaMemsetAsync(d_counters, 0, sizeof(int32_t) * (size_t)n_rounds_max, ctx->stream));
     if (!ctx->h_pinned_counter) SB_CUDA(ctx, cudaMallocHost(&ctx->h_pinned_counter, sizeof(int32_t)));
-    int64_t n_alive = S;
-    const int32_t *cur = nullptr;   // null = identity list
+    int64_t n_bound = S;
+    const int32_t *cur = nullptr, *cur_count = nullptr;   // null = identity list of S slots
     int base = 0, round = 0;
-    while (base < P && n_alive > 0) {
-        int n_perms = (round < 2) ? 32 : perms_per_launch;
-        n_perms = std::min(std::min(n_perms, perms_per_launch), P - base);
-        rc = launch_slice(base, n_perms, cur, n_alive);
-        if (rc) return rc;
+    while (base < P && n_bound > 0) {
+        int n_perms = round == 0 ? 31 : (round == 1 ? 33 : label_cap);
+        n_perms = std::min(std::min(n_perms, label_cap), P - base);
         int32_t *out = d_list[round & 1];
-        SB_CUDA(ctx, cudaMemsetAsync(d_counter, 0, sizeof(int32_t), ctx->stream));
-        {
-            Timed tm(ctx, CAT_REDUCE);
-            sb::advance_hits_kernel<<<(unsigned)((n_alive + 255) / 256), 256, 0, ctx->stream>>>(
-                d_hits, S, cur, (int32_t)n_alive, base, n_perms, P, ppi, d_rmin, d_r, d_n_done, out, d_counter);
-            ctx->stats.kernel_launches += 1;
-            SB_CUDA(ctx, cudaGetLastError());
-        }
-        SB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned_counter, d_counter, sizeof(int32_t), cudaMemcpyDeviceToHost,
-                                     ctx->stream));
-        SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        n_alive = *ctx->h_pinned_counter;
+        rc = slice(base, n_perms, cur, n_bound, cur_count, out, d_counters + round);
+        if (rc) return rc;
         cur = out;
+        cur_count = d_counters + round;
+        if (round < 2) {       // the two rounds that remove most genes: read the survivor count
+            SB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned_counter, cur_count, sizeof(int32_t), cudaMemcpyDeviceToHost,
+                                         ctx->stream));
+            SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            n_bound = *ctx->h_pinned_counter;
+            cur_count = nullptr;     // exact on the host from here
+        }
         base += n_perms;
         ++round;
     }
@@ -784,6 +912,9 @@ int sb_create(int device, sb_ctx **out)
     ctx->stats.sm_count = ctx->sm_count;
     e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return SB_ERR_CUDA; }
+    e = cudaMalloc(&ctx->d_walks, sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(ctx->d_walks, 0, sizeof(unsigned long long));
+    if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); cudaStreamDestroy(ctx->own_stream); delete ctx; return SB_ERR_CUDA; }
     ctx->stream = ctx->own_stream;
     *out = ctx;
     return SB_OK;
@@ -798,8 +929,10 @@ void sb_destroy(sb_ctx *ctx)
     for (auto &e : ctx->free_events) { cudaEventDestroy(e.start); cudaEventDestroy(e.stop); }
     for (auto &s : ctx->traits) { free_trait(s); free_tree_storage(s); }
     cudaFree(ctx->d_genes_buf);
+    cudaFree(ctx->d_trait_arena);
     cudaFree(ctx->d_lut);
     cudaFree(ctx->d_peak_out);
+    cudaFree(ctx->d_walks);
     for (auto p : ctx->d_scratch) cudaFree(p);
     if (ctx->h_pinned_counter) cudaFreeHost(ctx->h_pinned_counter);
     cudaStreamDestroy(ctx->own_stream);
@@ -821,6 +954,13 @@ int sb_synchronize(sb_ctx *ctx)
     return SB_OK;
 }
 
+int sb_set_permute_mode(sb_ctx *ctx, int mode)
+{
+    if (!ctx || mode < 0 || mode > 2) return SB_ERR_ARG;
+    ctx->permute_mode = mode;
+    return SB_OK;
+}
+
 int sb_set_profiling(sb_ctx *ctx, int on)
 {
     if (!ctx) return SB_ERR_ARG;
@@ -833,7 +973,10 @@ int sb_stats(sb_ctx *ctx, sb_stats_t *out)
     if (!ctx || !out) return SB_ERR_ARG;
     SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     resolve_events(ctx);
+    unsigned long long dev_walks = 0;
+    SB_CUDA(ctx, cudaMemcpy(&dev_walks, ctx->d_walks, sizeof dev_walks, cudaMemcpyDeviceToHost));
     *out = ctx->stats;
+    out->tests_walks += (int64_t)dev_walks;
     return SB_OK;
 }
 
@@ -844,6 +987,7 @@ int sb_stats_reset(sb_ctx *ctx)
     resolve_events(ctx);
     memset(&ctx->stats, 0, sizeof ctx->stats);
     ctx->stats.sm_count = ctx->sm_count;
+    SB_CUDA(ctx, cudaMemset(ctx->d_walks, 0, sizeof(unsigned long long)));
     return SB_OK;
 }
 
@@ -898,8 +1042,8 @@ int sb_set_trait(sb_ctx *ctx, int32_t t, const uint64_t *value, const uint64_t *
         s.h_value[w] &= keep;
         s.h_mask[w] &= keep;
     }
-    if (!s.d_value) SB_CUDA(ctx, cudaMalloc(&s.d_value, sizeof(uint64_t) * W));
-    if (!s.d_mask) SB_CUDA(ctx, cudaMalloc(&s.d_mask, sizeof(uint64_t) * W));
+    s.d_value = ctx->d_trait_arena + (size_t)t * 2 * W;
+    s.d_mask = s.d_value + W;
     SB_CUDA(ctx, cudaMemcpyAsync(s.d_value, s.h_value.data(), sizeof(uint64_t) * W, cudaMemcpyHostToDevice, ctx->stream));
     SB_CUDA(ctx, cudaMemcpyAsync(s.d_mask, s.h_mask.data(), sizeof(uint64_t) * W, cudaMemcpyHostToDevice, ctx->stream));
     SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -921,6 +1065,19 @@ int sb_set_tree(sb_ctx *ctx, int32_t t, const int32_t *left, const int32_t *righ
     Program prog;
     std::string err;
     if (!compile_tree(left, right, n_internal, prog, err)) return fail(ctx, SB_ERR_ARG, err.c_str());
+    {   // the program and at least one label vector must fit the constant pool (walk.cuh): reject the tree HERE,
+        // not at the first walk.  Every binary tree of <= 32 766 leaves passes (the longest program, a balanced
+        // tree's 21 374 ops, leaves room for 5 vectors); the check guards builds with a padded leaf stream.
+        const int64_t n_pos = (int64_t)prog.leaf_of_pos.size();
+        const int64_t w32p = ((n_pos + 31) / 32 + 3) / 4 * 4;
+        const int64_t need = sb::walk_label_base((int)prog.ops.size()) + w32p * std::max(1, sb::WALK_NLAB);
+        if (need > sb::C_POOL_WORDS) {
+            char buf[200];
+            snprintf(buf, sizeof buf, "sb_set_tree: tree program (%d ops) and one label vector (%lld words) exceed the "
+                     "%d-word constant pool", (int)prog.ops.size(), (long long)w32p, sb::C_POOL_WORDS);
+            return fail(ctx, SB_ERR_ARG, buf);
+        }
+    }
     TraitSlot &s = ctx->traits[t];
     free_tree(s);
     s.n_internal = n_internal;
@@ -931,6 +1088,7 @@ int sb_set_tree(sb_ctx *ctx, int32_t t, const int32_t *left, const int32_t *righ
     s.shift = 1;
     while ((1 << s.shift) <= s.n_leaves / 2) ++s.shift;   // 2^SH > max pairs (= floor(n/2)) >= pro, anti
     s.n_ops = (int32_t)prog.ops.size();
+    s.lab_base = sb::walk_label_base(s.n_ops);
     s.h_leaf_to_col.assign(leaf_to_col, leaf_to_col + s.n_leaves);
     // stream positions: the leaves in walk order; with SB_WALK_PADDED also pad positions (-1), and the label /
     // gene words in walk order (W32p) are counted over positions.  The device copies are filled up with -1 to
@@ -966,29 +1124,44 @@ int sb_contingency_fisher_device(sb_ctx *ctx, int32_t t, int32_t *d_counts, doub
 {
     if (!ctx) return SB_ERR_ARG;
     SB_CUDA(ctx, cudaSetDevice(ctx->device));
-    return launch_fisher(ctx, t, d_counts, d_p, d_hash);
+    return launch_fisher(ctx, t, 1, d_counts, d_p, d_hash);
 }
 
-int sb_contingency_fisher(sb_ctx *ctx, int32_t t, int32_t *counts, double *p, uint64_t *hash)
+int sb_contingency_fisher_multi_device(sb_ctx *ctx, int32_t t0, int32_t n_traits, int32_t *d_counts, double *d_p,
+                                       uint64_t *d_hash)
+{
+    if (!ctx) return SB_ERR_ARG;
+    SB_CUDA(ctx, cudaSetDevice(ctx->device));
+    return launch_fisher(ctx, t0, n_traits, d_counts, d_p, d_hash);
+}
+
+int sb_contingency_fisher_multi(sb_ctx *ctx, int32_t t0, int32_t n_traits, int32_t *counts, double *p, uint64_t *hash)
 {
     if (!ctx) return SB_ERR_ARG;
     SB_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t G = (size_t)ctx->G;
     if (G == 0) return fail(ctx, SB_ERR_STATE, "genes not set (sb_set_genes)");
-    int rc = ensure_scratch(ctx, 2, G * (16 + 8 + 16));
+    if (n_traits < 1 || t0 < 0 || t0 + n_traits > SB_MAX_TRAITS) return fail(ctx, SB_ERR_ARG, "trait index out of range");
+    const size_t GT = G * (size_t)n_traits;
+    int rc = ensure_scratch(ctx, 2, GT * (16 + 8 + 16));
     if (rc) return rc;
     char *base = (char *)ctx->d_scratch[2];
     int32_t *d_counts = (int32_t *)base;
-    double *d_p = (double *)(base + G * 16);
-    uint64_t *d_hash = (uint64_t *)(base + G * 24);
-    rc = launch_fisher(ctx, t, d_counts, p ? d_p : nullptr, hash ? d_hash : nullptr);
+    double *d_p = (double *)(base + GT * 16);
+    uint64_t *d_hash = (uint64_t *)(base + GT * 24);
+    rc = launch_fisher(ctx, t0, n_traits, d_counts, p ? d_p : nullptr, hash ? d_hash : nullptr);
     if (rc) return rc;
-    if (counts) SB_CUDA(ctx, cudaMemcpyAsync(counts, d_counts, G * 16, cudaMemcpyDeviceToHost, ctx->stream));
-    if (p) SB_CUDA(ctx, cudaMemcpyAsync(p, d_p, G * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    if (hash) SB_CUDA(ctx, cudaMemcpyAsync(hash, d_hash, G * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    if (counts) SB_CUDA(ctx, cudaMemcpyAsync(counts, d_counts, GT * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    if (p) SB_CUDA(ctx, cudaMemcpyAsync(p, d_p, GT * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (hash) SB_CUDA(ctx, cudaMemcpyAsync(hash, d_hash, GT * 16, cudaMemcpyDeviceToHost, ctx->stream));
     SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    ctx->stats.d2h_bytes += (int64_t)(G * ((counts ? 16 : 0) + (p ? 8 : 0) + (hash ? 16 : 0)));
+    ctx->stats.d2h_bytes += (int64_t)(GT * ((counts ? 16 : 0) + (p ? 8 : 0) + (hash ? 16 : 0)));
     return SB_OK;
+}
+
+int sb_contingency_fisher(sb_ctx *ctx, int32_t t, int32_t *counts, double *p, uint64_t *hash)
+{
+    return sb_contingency_fisher_multi(ctx, t, 1, counts, p, hash);
 }
 
 int sb_pairwise_device(sb_ctx *ctx, int32_t t, const int64_t *d_gene_idx, int64_t S, int32_t *d_pairs)

@@ -238,10 +238,13 @@ struct WalkState {
 // the compiler keeps the program counter, the leaf position, the label bits and all
 // the branching on them in the uniform datapath (ULDC / UISETP / BRA.U) and the
 // vector pipes only see the DP arithmetic.
-constexpr int C_OPS_MAX = 12288;           // uint16 ops        (24 KB)
-constexpr int C_LABEL_WORDS = 9728;        // uint32 label words (38 KB)
-SB_CONST uint16_t c_ops[C_OPS_MAX];
-SB_CONST uint32_t c_labels[C_LABEL_WORDS];
+// One 62 KB pool, split per tree: the uint16 program at the start, the label vectors of the current launch
+// from word WalkArgs::lab_base on.  A 5 000-leaf tree (~2 500 ops, 5 KB) leaves room for 91 labellings per launch;
+// a balanced 32 766-leaf tree (21 374 ops, 43 KB) still fits with 5.
+constexpr int C_POOL_WORDS = 15872;
+SB_CONST uint32_t c_pool[C_POOL_WORDS];
+// first label word behind a program of n_ops ops (16-byte aligned)
+constexpr int walk_label_base(int n_ops) { return ((n_ops + 1) / 2 + 3) / 4 * 4; }
 
 // op = (count << 4) | type.  "16" ops work on the packed accumulators A16 / B16 (two genes
 // per register, 16-bit keys), legal while the subtree has <= WALK_LIM16 leaves; "32" ops work
@@ -519,6 +522,11 @@ struct WalkArgs {
     const int32_t *unperm;     // [S][3] (permute mode): unpermuted Total, Pro, Anti
     int32_t *pairs;            // [S][3] (pairs mode output)
     uint8_t *hits;             // [n_chunks_total][S] (permute mode output): bit r = perm ppi*chunk + r hit
+                               // transposed launches: [rows][S_total] bytes, 1 = the row's gene hit under labelling s
+    const int32_t *S_dev;      // if set: the number of slots to walk is read from device memory (early-stop rounds
+                               // are enqueued without a host round trip; blocks past the end exit at once)
+    int32_t lab_base;          // first word of the launch's label vectors in c_pool
+    int32_t row_base;          // transposed launches: position (in slot_idx, or the slot itself) of constant row 0
 };
 
 #ifndef SB_WALK_NPAIR
@@ -535,7 +543,7 @@ constexpr int WALK_NP = 2 * WALK_NPAIR;     // genes per thread
 constexpr int WALK_NLAB = SB_WALK_NLAB;
 
 // NP = 2 * NPAIR genes x NLAB labellings: simultaneous tree walks of this thread's genes under the
-// labellings at c_labels[lab_off[l] ..].  gcol[k] points at gene k's column of genesT; genes 2q and 2q+1
+// labellings at c_pool[lab_off[l] ..].  gcol[k] points at gene k's column of genesT; genes 2q and 2q+1
 // share the packed accumulators of pair q; state index s = l * NPAIR + q (32-bit: l * NP + k).  Every branch is on block-uniform data (the program and
 // the label bits); per-gene data only feeds selects.  The program always ends in 32-bit mode.
 // Stack entries take EW = 10 (DUAL) or 5 words: per gene pair in the packed shared-memory stack, per gene in the
@@ -552,7 +560,7 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR
     const int K = 1 << A.shift;
     const int scale = K - (1 << WALK_SH16);
     WalkState16 a16[NS], b16[NS];
-    int sp = 0, pc = 0;                // sp counts 32-bit words per thread; pc is a BYTE offset into c_ops
+    int sp = 0, pc = 0;                // sp counts 32-bit words per thread; pc is a BYTE offset into c_pool
     int sp32 = 0;                      // 32-bit entries held in stk32
     int stk32[WALK_STACK32 * EW * NLAB * NP];   // local memory: touched by PUSH32 / MERGE_POP32 only
     int room = 0, win = 0;             // leaves left in the current 16-leaf window; windows opened so far
@@ -576,7 +584,7 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR
     do {                                                                                       \
         if ((win & 1) == 0) {                                                                  \
             const int w_ = win >> 1;                                                           \
-            _Pragma("unroll") for (int l_ = 0; l_ < NLAB; ++l_) lw[l_] = c_labels[lab_off[l_] + w_]; \
+            _Pragma("unroll") for (int l_ = 0; l_ < NLAB; ++l_) lw[l_] = c_pool[lab_off[l_] + w_]; \
             _Pragma("unroll") for (int q_ = 0; q_ < NPAIR; ++q_) {                             \
                 const uint32_t a_ = gnext[2 * q_], b_ = gnext[2 * q_ + 1];                     \
                 gx[q_] = SB_WINDOW_X(a_, b_);                                                  \
@@ -590,7 +598,7 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR
             _Pragma("unroll") for (int q_ = 0; q_ < NPAIR; ++q_) gx[q_] = gy[q_];              \
             if (WALK_PADDED) {   /* skipped pad positions: the label word is not where the shifts left it */ \
                 _Pragma("unroll") for (int l_ = 0; l_ < NLAB; ++l_)                            \
-                    lw[l_] = c_labels[lab_off[l_] + (win >> 1)] >> 16;                         \
+                    lw[l_] = c_pool[lab_off[l_] + (win >> 1)] >> 16;                           \
             }                                                                                  \
         }                                                                                      \
         ++win;                                                                                 \
@@ -724,7 +732,7 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR
         }                                                                                      \
     } while (0)
     for (;;) {
-        const uint32_t op = *reinterpret_cast<const uint16_t *>(reinterpret_cast<const char *>(c_ops) + pc);
+        const uint32_t op = *reinterpret_cast<const uint16_t *>(reinterpret_cast<const char *>(c_pool) + pc);
         pc += 2;
         const int type = op & 15, cnt = op >> OP_TYPE_BITS;
         if (((op ^ (uint32_t)OP_CHERRY_B16) & 14u) == 0) {
@@ -849,22 +857,23 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR
 
 // gene slots of this thread: (tile * NP + k) * T + tid  (coalesced per k)
 template <int NP>
-SB_DEV void walk_slots(const WalkArgs &A, int tile, int64_t (&s_idx)[NP], bool (&active)[NP],
+SB_DEV void walk_slots(const WalkArgs &A, const int32_t *list, int tile, int64_t (&s_idx)[NP], bool (&active)[NP],
                                            int64_t (&sc)[NP], const uint32_t *(&gcol)[NP])
 {
+    const int64_t S = A.S_dev ? (int64_t)*A.S_dev : A.S;
 #pragma unroll
     for (int k = 0; k < NP; ++k) {
         const int64_t li = ((int64_t)tile * NP + k) * WALK_THREADS + threadIdx.x;   // position in the work list
-        active[k] = li < A.S;
-        const int64_t lc = active[k] ? li : (A.S - 1);   // idle lanes redo the last entry (no divergence)
-        s_idx[k] = A.slot_idx ? (int64_t)A.slot_idx[lc] : lc;
+        active[k] = li < S;
+        const int64_t lc = active[k] ? li : (S - 1);   // idle lanes redo the last entry (no divergence)
+        s_idx[k] = list ? (int64_t)list[lc] : lc;
         sc[k] = s_idx[k];
         const int64_t gene = A.gene_idx ? A.gene_idx[sc[k]] : sc[k];
         gcol[k] = A.genesT + gene;
     }
 }
 
-// K4: one labelling (c_labels row 0), both passes; writes pairs[S][3] = Total, Pro, Anti.
+// K4: one labelling (the first row behind lab_base), both passes; writes pairs[S][3] = Total, Pro, Anti.
 // The root takes three independent maxima (classes.py:246-249).
 SB_KERNEL(__launch_bounds__(WALK_THREADS)) walk_pairs_kernel(const WalkArgs A)
 {
@@ -872,7 +881,7 @@ SB_KERNEL(__launch_bounds__(WALK_THREADS)) walk_pairs_kernel(const WalkArgs A)
     int *stk = smem_stack + threadIdx.x;
     constexpr int NP = WALK_NP;
     int64_t s_idx[NP], sc[NP]; bool active[NP]; const uint32_t *gcol[NP];
-    walk_slots<NP>(A, blockIdx.x, s_idx, active, sc, gcol);
+    walk_slots<NP>(A, A.slot_idx, blockIdx.x, s_idx, active, sc, gcol);
     const int K = 1 << A.shift;
     Bonus32 b32[NP];
     Bonus16 b16[WALK_NPAIR];
@@ -881,7 +890,7 @@ SB_KERNEL(__launch_bounds__(WALK_THREADS)) walk_pairs_kernel(const WalkArgs A)
 #pragma unroll
     for (int q = 0; q < WALK_NPAIR; ++q) b16[q] = Bonus16{K16P1x2, K16x2, K16x2, K16P1x2};
     WalkState acc[NP];
-    const int lab_off[1] = {0};
+    const int lab_off[1] = {A.lab_base};
     walk_tree<WALK_NPAIR, 1, true>(A, gcol, lab_off, stk, acc, b32, b16);
     const int mask = K - 1;
 #pragma unroll
@@ -906,42 +915,67 @@ SB_KERNEL(__launch_bounds__(WALK_THREADS)) walk_pairs_kernel(const WalkArgs A)
 // and writes one byte of hit flags per gene.  Blocks are small work items, so the tail of a
 // launch is short, and concurrently running blocks read the same few label vectors from the
 // constant cache.
+//
+// TRANSPOSED launches serve the usual command-line case after filtering -- a few dozen genes, thousands of
+// permutations (methods.py:1022-1024, :1295-1310) -- where threads = genes would leave most of every block idle.
+// The DP is symmetric in the gene bit and the trait bit of a leaf (swapping them exchanges the states Ab and aB,
+// and AB+ab / Ab+aB pairs keep their kind, classes.py:459-572), so the same walk runs with the roles exchanged:
+// a thread's "gene" columns are labellings (genesT = the label vectors transposed, [W32p][Ps]), the constant rows
+// are the walk-order bits of up to ppi genes, and the tested side / unpermuted counts belong to the row.
+template <bool TRANSPOSED>
 SB_KERNEL(__launch_bounds__(WALK_THREADS, SB_WALK_MINBLOCKS)) walk_permute_kernel(const WalkArgs A)
 {
     SB_SHARED_STACK(smem_stack);
     int *stk = smem_stack + threadIdx.x;
     constexpr int NP = WALK_NP;
+    constexpr int NLAB = TRANSPOSED ? 1 : WALK_NLAB;
     const int chunk = blockIdx.y;
     const int perm0 = chunk * A.ppi;
     const int rows = min(A.ppi, A.n_perms - perm0);
+    if (A.S_dev && (int64_t)blockIdx.x * NP * WALK_THREADS >= (int64_t)*A.S_dev) return;   // grid sized for an upper bound
     int64_t s_idx[NP], sc[NP]; bool active[NP]; const uint32_t *gcol[NP];
-    walk_slots<NP>(A, blockIdx.x, s_idx, active, sc, gcol);
+    walk_slots<NP>(A, TRANSPOSED ? nullptr : A.slot_idx, blockIdx.x, s_idx, active, sc, gcol);   // transposed: slot_idx lists the rows
     const int K = 1 << A.shift;
     const int mask = K - 1;
     long long u_total[NP], u_stat[NP]; bool use_pro[NP]; uint32_t hits[NP];
     Bonus32 b32[NP];
     Bonus16 b16[WALK_NPAIR];
-#pragma unroll
-    for (int k = 0; k < NP; ++k) {
-        u_total[k] = A.unperm[sc[k] * 3 + 0];
-        const int u_pro = A.unperm[sc[k] * 3 + 1], u_anti = A.unperm[sc[k] * 3 + 2];
-        use_pro[k] = u_pro >= u_anti;                 // methods.py:1333-1336
-        u_stat[k] = use_pro[k] ? u_pro : u_anti;
-        hits[k] = 0;
-        // the statistic this gene is tested on counts +1 for its own kind of pair
+    // tested side and pair bonuses of "gene" k from the unpermuted counts at un: the statistic a gene is tested on
+    // counts +1 for its own kind of pair (methods.py:1333-1336)
+    auto side = [&](int k, const int32_t *un) {
+        u_total[k] = un[0];
+        use_pro[k] = un[1] >= un[2];
+        u_stat[k] = use_pro[k] ? un[1] : un[2];
         b32[k] = Bonus32{use_pro[k] ? K + 1 : K, use_pro[k] ? K : K + 1, 0, 0};
-    }
+    };
+    auto pack_bonus = [&]() {
 #pragma unroll
-    for (int q = 0; q < WALK_NPAIR; ++q) {
-        const unsigned s0 = use_pro[2 * q] ? 65u : 64u, s1 = use_pro[2 * q + 1] ? 65u : 64u;
-        b16[q] = Bonus16{s0 | (s1 << 16), (129u - s0) | ((129u - s1) << 16), 0u, 0u};
+        for (int q = 0; q < WALK_NPAIR; ++q) {
+            const unsigned s0 = use_pro[2 * q] ? 65u : 64u, s1 = use_pro[2 * q + 1] ? 65u : 64u;
+            b16[q] = Bonus16{s0 | (s1 << 16), (129u - s0) | ((129u - s1) << 16), 0u, 0u};
+        }
+    };
+#pragma unroll
+    for (int k = 0; k < NP; ++k) hits[k] = 0;
+    if constexpr (!TRANSPOSED) {
+#pragma unroll
+        for (int k = 0; k < NP; ++k) side(k, A.unperm + sc[k] * 3);
+        pack_bonus();
     }
-    constexpr int NLAB = WALK_NLAB;
     for (int r = 0; r < rows; r += NLAB) {
+        int64_t row_slot = 0;
+        if constexpr (TRANSPOSED) {   // the row's gene decides the tested side for every labelling of the thread
+            const int64_t e = (int64_t)A.row_base + perm0 + r;
+            row_slot = A.slot_idx ? (int64_t)A.slot_idx[e] : e;
+#pragma unroll
+            for (int k = 0; k < NP; ++k) side(k, A.unperm + row_slot * 3);
+            pack_bonus();
+        }
         WalkState acc[NLAB * NP];
         int lab_off[NLAB];
 #pragma unroll
-        for (int l = 0; l < NLAB; ++l) lab_off[l] = (perm0 + min(r + l, rows - 1)) * A.W32p;   // an odd tail walks its last labelling twice
+        for (int l = 0; l < NLAB; ++l)   // an odd tail walks its last labelling twice
+            lab_off[l] = A.lab_base + (perm0 + min(r + l, rows - 1)) * A.W32p;
         walk_tree<WALK_NPAIR, NLAB, false>(A, gcol, lab_off, stk, acc, b32, b16);
 #pragma unroll
         for (int l = 0; l < NLAB; ++l) {
@@ -954,79 +988,135 @@ SB_KERNEL(__launch_bounds__(WALK_THREADS, SB_WALK_MINBLOCKS)) walk_permute_kerne
 #pragma unroll
                 for (int c = 0; c < 5; ++c)
                     if (acc[l * NP + k].p[c] >= 0) stat = max(stat, acc[l * NP + k].p[c] & mask);
-                if ((long long)stat * u_total[k] >= u_stat[k] * total) hits[k] |= (1u << (r + l));   // methods.py:1353-1355
-            }
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < NP; ++k)
-        if (active[k]) A.hits[(int64_t)(A.chunk_base + chunk) * A.S_total + s_idx[k]] = (uint8_t)hits[k];
-}
-
-#ifndef SB_HOST_EMUL   // device-only kernels below
-// ---------------------------------------------------------------- hit-sequence reduction
-// Permute's bookkeeping (methods.py:1348-1365) on the ordered hit flags.
-__global__ void __launch_bounds__(256) reduce_hits_kernel(const uint8_t *__restrict__ hits, int64_t S, int n_chunks,
-                                                          int ppi, int P, int early_stop,
-                                                          const int32_t *__restrict__ rmin, int32_t *__restrict__ r_out,
-                                                          int32_t *__restrict__ n_done)
-{
-    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= S) return;
-    int r = 0, done = P;
-    if (!early_stop) {
-        for (int c = 0; c < n_chunks; ++c) {
-            const int rows = min(ppi, P - c * ppi);
-            r += __popc((uint32_t)hits[(int64_t)c * S + s] & ((1u << rows) - 1u));
-        }
-    } else {
-        bool stop = false;
-        for (int c = 0; c < n_chunks && !stop; ++c) {
-            const int rows = min(ppi, P - c * ppi);
-            const uint32_t w = hits[(int64_t)c * S + s];
-            for (int b = 0; b < rows; ++b) {
-                const int i = c * ppi + b;
-                r += (w >> b) & 1u;
-                if (i >= 30 && r >= rmin[i]) {   // methods.py:1360-1363
-                    done = i + 1;
-                    stop = true;
-                    break;
+                const bool hit = (long long)stat * u_total[k] >= u_stat[k] * total;   // methods.py:1353-1355
+                if constexpr (TRANSPOSED) {
+                    if (active[k]) A.hits[row_slot * A.S_total + s_idx[k]] = (uint8_t)hit;
+                } else {
+                    if (hit) hits[k] |= (1u << (r + l));
                 }
             }
         }
     }
-    r_out[s] = r;
-    n_done[s] = done;
+    if constexpr (!TRANSPOSED) {
+#pragma unroll
+        for (int k = 0; k < NP; ++k)
+            if (active[k]) A.hits[(int64_t)(A.chunk_base + chunk) * A.S_total + s_idx[k]] = (uint8_t)hits[k];
+    }
 }
 
-// Early-stop rounds: after a slice of permutations [base, base + n) has been walked for the
-// slots in list_in, apply Permute's sequential rule (methods.py:1348-1365) to each of them;
-// slots that neither stopped nor reached P are appended to list_out for the next slice.
-__global__ void __launch_bounds__(256) advance_hits_kernel(const uint8_t *__restrict__ hits, int64_t S_total,
-                                                           const int32_t *__restrict__ list_in, int32_t n_in, int base,
-                                                           int n, int P, int ppi, const int32_t *__restrict__ rmin,
-                                                           int32_t *__restrict__ r_arr, int32_t *__restrict__ n_done,
-                                                           int32_t *__restrict__ list_out, int32_t *__restrict__ counter)
+#ifndef SB_HOST_EMUL   // device-only kernels below
+// ---------------------------------------------------------------- hit-sequence reduction
+// Permute's bookkeeping (methods.py:1348-1365), slice by slice.  `hits` holds the flags of the slice of
+// permutations [base, base + n) just walked for the slots in list_in (row c, bit b = permutation base + ppi*c + b).
+// Exhaustive mode adds the hits up; reference-rule mode applies the sequential stop rule (:1360-1363), and slots
+// that neither stopped nor reached P are appended to list_out for the next slice.  n_in_dev: the length of
+// list_in in device memory (rounds are enqueued without a host round trip), else n_in; `walks` (optional)
+// accumulates the walks such a round really did, for sb_stats.
+__global__ void __launch_bounds__(256) accumulate_hits_kernel(const uint8_t *__restrict__ hits, int64_t S_total,
+                                                              const int32_t *__restrict__ list_in, int32_t n_in,
+                                                              const int32_t *__restrict__ n_in_dev, int base, int n,
+                                                              int P, int ppi, int early_stop,
+                                                              const int32_t *__restrict__ rmin, int32_t *__restrict__ r_arr,
+                                                              int32_t *__restrict__ n_done, int32_t *__restrict__ list_out,
+                                                              int32_t *__restrict__ counter,
+                                                              unsigned long long *__restrict__ walks)
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n_in) return;
+    if (e == 0 && walks) atomicAdd(walks, (unsigned long long)(n_in_dev ? *n_in_dev : n_in) * (unsigned long long)n);
+    if (e >= (n_in_dev ? *n_in_dev : n_in)) return;
     const int slot = list_in ? list_in[e] : e;
     int r = (base == 0) ? 0 : r_arr[slot];
-    for (int i = base; i < base + n; ++i) {
-        const uint32_t byte = hits[(int64_t)(i / ppi) * S_total + slot];
-        r += (byte >> (i % ppi)) & 1u;
-        if (i >= 30 && r >= rmin[i]) {   // methods.py:1360-1363
+    if (!early_stop) {
+        for (int c = 0; c * ppi < n; ++c)
+            r += __popc((uint32_t)hits[(int64_t)c * S_total + slot] & ((1u << min(ppi, n - c * ppi)) - 1u));
+        r_arr[slot] = r;
+        if (base + n >= P) n_done[slot] = P;
+        return;
+    }
+    for (int k = 0; k < n; ++k) {
+        const int i = base + k;
+        r += (hits[(int64_t)(k / ppi) * S_total + slot] >> (k % ppi)) & 1u;
+        if (i >= 30 && r >= rmin[i]) {
             r_arr[slot] = r;
             n_done[slot] = i + 1;
             return;
         }
     }
     r_arr[slot] = r;
-    if (base + n >= P) {
-        n_done[slot] = P;
-    } else {
-        list_out[atomicAdd(counter, 1)] = slot;
+    if (base + n >= P) n_done[slot] = P;
+    else list_out[atomicAdd(counter, 1)] = slot;
+}
+
+// ---------------------------------------------------------------- transposed launches (few genes x many permutations)
+// labelsW [P][W32p] -> labelsT [W32p][Ps]: the label vectors become the per-thread columns of a transposed K5 launch
+__global__ void __launch_bounds__(256) transpose_labels_kernel(const uint32_t *__restrict__ labelsW, int P, int W32p,
+                                                               int64_t Ps, uint32_t *__restrict__ labelsT)
+{
+    __shared__ uint32_t tile[32][33];
+    const int p0 = blockIdx.x * 32, w0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    for (int j = ty; j < 32; j += 8) {
+        const int p = p0 + j, w = w0 + tx;
+        tile[j][tx] = (p < P && w < W32p) ? labelsW[(int64_t)p * W32p + w] : 0u;
     }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        const int w = w0 + j, p = p0 + tx;
+        if (w < W32p && p < Ps) labelsT[(int64_t)w * Ps + p] = tile[tx][j];
+    }
+}
+
+// rowsW [n][W32p]: the walk-order bits of the genes in result slots list[e] (or e), gathered out of genesT [W32p][Gs]
+__global__ void __launch_bounds__(256) gather_rows_kernel(const uint32_t *__restrict__ genesT, int64_t Gs, int W32p,
+                                                          const int64_t *__restrict__ gene_idx,
+                                                          const int32_t *__restrict__ list, int n,
+                                                          uint32_t *__restrict__ rowsW)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)n * W32p) return;
+    const int e = (int)(i / W32p), w = (int)(i - (int64_t)e * W32p);
+    const int64_t slot = list ? list[e] : e;
+    const int64_t gene = gene_idx ? gene_idx[slot] : slot;
+    rowsW[i] = genesT[(int64_t)w * Gs + gene];
+}
+
+// Permute's bookkeeping (methods.py:1348-1365) on hit rows [slot][Pp] (one byte per labelling), one warp per gene.
+// n_avail labellings have been walked so far: a gene that neither stopped nor reached P goes to list_out.
+__global__ void __launch_bounds__(256) reduce_hit_rows_kernel(const uint8_t *__restrict__ hits, int64_t Pp,
+                                                              const int32_t *__restrict__ list, int n, int n_avail,
+                                                              int P, int early_stop, const int32_t *__restrict__ rmin,
+                                                              int32_t *__restrict__ r_out, int32_t *__restrict__ n_done,
+                                                              int32_t *__restrict__ list_out, int32_t *__restrict__ counter)
+{
+    const int e = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (e >= n) return;
+    const int slot = list ? list[e] : e;
+    const uint8_t *row = hits + (int64_t)slot * Pp;
+    int r = 0, done = -1;
+    for (int base = 0; base < n_avail; base += 32) {
+        const int i = base + lane;
+        const bool bit = i < n_avail && row[i] != 0;
+        const unsigned m = __ballot_sync(0xffffffffu, bit);
+        if (early_stop) {
+            const int cum = r + __popc(m & (0xffffffffu >> (31 - lane)));
+            const bool stop = i < n_avail && i >= 30 && cum >= rmin[i];     // methods.py:1360-1363
+            const unsigned sm = __ballot_sync(0xffffffffu, stop);
+            if (sm) {
+                const int first = __ffs(sm) - 1;
+                r += __popc(m & (0xffffffffu >> (31 - first)));
+                done = base + first + 1;
+                break;
+            }
+        }
+        r += __popc(m);
+    }
+    if (lane) return;
+    if (done < 0 && n_avail < P) {
+        list_out[atomicAdd(counter, 1)] = slot;
+        return;
+    }
+    r_out[slot] = r;
+    n_done[slot] = done < 0 ? P : done;
 }
 
 // ---------------------------------------------------------------- int32 pipe microbenchmark

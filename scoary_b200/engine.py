@@ -170,6 +170,20 @@ class Engine:
         self._check(self._lib.sb_contingency_fisher(self._ctx, int(t), _ptr(counts), _ptr(p), _ptr(h)))
         return counts, p, h
 
+    def contingency_fisher_multi(self, t0, n_traits, want_p=True, want_hash=False):
+        """Traits t0 .. t0 + n_traits - 1 in one pass over the gene rows (every row is read once for all of them):
+        counts [T][G][4], p [T][G], hash [T][G][2]."""
+        G, T = self.G, int(n_traits)
+        counts = np.empty((T, G, 4), dtype=np.int32)
+        p = np.empty((T, G), dtype=np.float64) if want_p else None
+        h = np.empty((T, G, 2), dtype=np.uint64) if want_hash else None
+        self._check(self._lib.sb_contingency_fisher_multi(self._ctx, int(t0), T, _ptr(counts), _ptr(p), _ptr(h)))
+        return counts, p, h
+
+    def set_permute_mode(self, mode):
+        """K5 launch shape: 0 chosen per call, 1 threads = genes, 2 threads = labellings (same results)."""
+        self._check(self._lib.sb_set_permute_mode(self._ctx, int(mode)))
+
     def pairwise(self, t, gene_idx=None):
         idx = None if gene_idx is None else np.ascontiguousarray(gene_idx, dtype=np.int64)
         S = self.G if idx is None else len(idx)
@@ -208,6 +222,12 @@ class Engine:
         self._check(self._lib.sb_contingency_fisher_device(self._ctx, int(t), ctypes.c_void_p(int(counts_ptr) or None),
                                                            ctypes.c_void_p(int(p_ptr) or None),
                                                            ctypes.c_void_p(int(hash_ptr) or None)))
+
+    def contingency_fisher_multi_device(self, t0, n_traits, counts_ptr, p_ptr, hash_ptr=0):
+        self._check(self._lib.sb_contingency_fisher_multi_device(self._ctx, int(t0), int(n_traits),
+                                                                 ctypes.c_void_p(int(counts_ptr) or None),
+                                                                 ctypes.c_void_p(int(p_ptr) or None),
+                                                                 ctypes.c_void_p(int(hash_ptr) or None)))
 
     def pairwise_device(self, t, S, pairs_ptr, gene_idx_ptr=0):
         self._check(self._lib.sb_pairwise_device(self._ctx, int(t), ctypes.c_void_p(int(gene_idx_ptr) or None), int(S),

@@ -460,14 +460,26 @@ def Setup_results(genedic, traitsdic, collapse):
     world, rank = dist.world_rank()
     G = table.bits.shape[0]
     lo, hi = dist.shard_bounds(G, world)[rank]           # N > 1: this rank's contiguous block of genes
-    e.set_genes(table.bits[lo:hi], len(table.strains))
+    if hi > lo:
+        e.set_genes(table.bits[lo:hi], len(table.strains))
     all_traits, gtc = {}, {}
-    for t_idx, trait in enumerate(traitsdic):
+    trait_names = list(traitsdic)
+    TRAITS_PER_PASS = 8       # sb_contingency_fisher_multi reads every gene row once for this many traits
+    staged = {}               # trait -> (counts, p, hashes) of the pass it was computed in
+    for t_idx, trait in enumerate(trait_names):
+        if trait not in staged:
+            chunk = trait_names[t_idx:t_idx + TRAITS_PER_PASS]
+            if hi > lo:       # a rank without genes (fewer genes than GPUs) only takes part in the gather
+                for slot, name in enumerate(chunk):
+                    e.set_trait_vector(slot, _trait_vector(table, traitsdic[name]))
+                c_all, p_all, h_all = e.contingency_fisher_multi(0, len(chunk), want_hash=bool(collapse))
+            else:
+                c_all = np.zeros((len(chunk), 0, 4), np.int32)
+                p_all = np.zeros((len(chunk), 0), np.float64)
+                h_all = np.zeros((len(chunk), 0, 2), np.uint64) if collapse else None
+            staged = {name: (c_all[k], p_all[k], h_all[k] if collapse else None) for k, name in enumerate(chunk)}
         log.info("Gene-wise counting and Fisher's exact tests for trait: %s" % str(trait))
-        vec = _trait_vector(table, traitsdic[trait])
-        slot = t_idx % 64
-        e.set_trait_vector(slot, vec)
-        counts, pvals, hashes = e.contingency_fisher(slot, want_hash=bool(collapse))
+        counts, pvals, hashes = staged[trait]
         if world > 1:                                     # one all-gather; the rest is the same on every rank
             rec = np.zeros((hi - lo, 10), dtype=np.int32)
             rec[:, 0:4] = counts

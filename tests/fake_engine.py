@@ -33,6 +33,14 @@ class FakeEngine:
         h = O.pattern_hash(self.m, self.traits[t]) if want_hash else None
         return counts, p, h
 
+    def contingency_fisher_multi(self, t0, n_traits, want_p=True, want_hash=False):
+        outs = [self.contingency_fisher(t0 + k, want_p, want_hash) for k in range(n_traits)]
+        return (np.stack([o[0] for o in outs]), np.stack([o[1] for o in outs]) if want_p else None,
+                np.stack([o[2] for o in outs]) if want_hash else None)
+
+    def set_permute_mode(self, mode):
+        pass
+
     def _walk_inputs(self, t, gene_idx):
         left, right, cols = self.trees[t]
         rows = np.arange(self.G) if gene_idx is None else np.asarray(gene_idx)

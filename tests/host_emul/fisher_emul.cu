@@ -1,7 +1,7 @@
 // TEST INFRASTRUCTURE: the Fisher code of scoary_b200/csrc/fisher.cuh compiled for the HOST.
 //
-// fisher_two_sided_warp() is a warp-cooperative function (lanes split the hypergeometric support,
-// shuffles sum the lanes, a ballot drives the 32-ary search).  Here a "warp" is 32 host threads that
+// fisher_two_sided() is a warp-cooperative function (four tables per warp, eight lanes each: lanes split the
+// hypergeometric support, shuffles sum the lanes, a ballot drives the boundary search).  Here a "warp" is 32 host threads that
 // meet at a pthread barrier inside every collective, so the very same source runs with the same
 // lane-to-term assignment and the same summation order as on the GPU.  Differences to the device:
 // exp() comes from the host libm (<= 1 ulp), everything else is IEEE double in the same order.
@@ -50,7 +50,7 @@ static inline bool sb_emul_any(bool pred) { return sb_emul_ballot(pred) != 0u; }
 static inline double sb_emul_mul(double a, double b) { volatile double r = a * b; return r; }
 static inline double sb_emul_div(double a, double b) { volatile double r = a / b; return r; }
 
-#include "../../scoary_b200/csrc/fisher2.cuh"   // includes fisher.cuh
+#include "../../scoary_b200/csrc/fisher.cuh"
 
 extern "C" void sb_build_logfact_dd(int32_t n, double *hi_lo);
 
@@ -63,7 +63,7 @@ struct Job {
     int lane;
 };
 
-void *lane_main2(void *arg)      // version 2: four tables per warp, eight lanes each
+void *lane_main(void *arg)      // four tables per warp, eight lanes each
 {
     const Job *j = static_cast<const Job *>(arg);
     t_lane = j->lane;
@@ -71,20 +71,8 @@ void *lane_main2(void *arg)      // version 2: four tables per warp, eight lanes
     for (int64_t i = 0; i < j->n; i += 4) {
         const bool valid = i + grp < j->n;
         const int32_t *t = j->tables + 4 * (valid ? i + grp : 0);
-        const double pv = sb::fisher2_two_sided(j->lut, t[0], t[1], t[2], t[3], valid, j->lane);
+        const double pv = sb::fisher_two_sided(j->lut, t[0], t[1], t[2], t[3], valid, j->lane);
         if (valid && (j->lane & 7) == 0) j->p[i + grp] = pv;
-    }
-    return nullptr;
-}
-
-void *lane_main(void *arg)
-{
-    const Job *j = static_cast<const Job *>(arg);
-    t_lane = j->lane;
-    for (int64_t i = 0; i < j->n; ++i) {
-        const int32_t *t = j->tables + 4 * i;
-        const double pv = sb::fisher_two_sided_warp(j->lut, t[0], t[1], t[2], t[3], j->lane);
-        if (j->lane == 0) j->p[i] = pv;
     }
     return nullptr;
 }
@@ -96,7 +84,6 @@ extern "C" {
 static int run_fisher(const int32_t *tables, int64_t n, double *p, void *(*fn)(void *));
 
 int emul_fisher(const int32_t *tables, int64_t n, double *p) { return run_fisher(tables, n, p, lane_main); }
-int emul_fisher2(const int32_t *tables, int64_t n, double *p) { return run_fisher(tables, n, p, lane_main2); }
 
 static int run_fisher(const int32_t *tables, int64_t n, double *p, void *(*fn)(void *))
 {

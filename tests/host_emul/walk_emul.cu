@@ -39,11 +39,15 @@ bool guard_intact(const std::vector<int> &smem, size_t words)
     return true;
 }
 
-int load_program(const uint16_t *ops, int n_ops)
+// program at the start of the constant pool, n_vec label vectors behind it (as engine.cu lays them out);
+// returns the label base, or -1 if they do not fit
+int load_pool(const uint16_t *ops, int n_ops, const uint32_t *labels, int64_t n_vec, int W32p)
 {
-    if (n_ops > sb::C_OPS_MAX) return -1;
-    memcpy(sb::c_ops, ops, sizeof(uint16_t) * (size_t)n_ops);
-    return 0;
+    const int base = sb::walk_label_base(n_ops);
+    if ((int64_t)base + n_vec * W32p > sb::C_POOL_WORDS) return -1;
+    memcpy(sb::c_pool, ops, sizeof(uint16_t) * (size_t)n_ops);
+    memcpy(sb::c_pool + base, labels, sizeof(uint32_t) * (size_t)n_vec * W32p);
+    return base;
 }
 
 }  // namespace
@@ -58,11 +62,11 @@ int emul_walk_genes_per_thread(void) { return sb::WALK_NP; }
 int emul_pairs(const uint16_t *ops, int n_ops, const uint32_t *labels, const uint32_t *genesT, int64_t Gs, int64_t S,
                int W32p, int shift, int stack_units, int32_t *pairs)
 {
-    if (load_program(ops, n_ops) || W32p > sb::C_LABEL_WORDS) return -1;
-    memcpy(sb::c_labels, labels, sizeof(uint32_t) * (size_t)W32p);
+    const int base = load_pool(ops, n_ops, labels, 1, W32p);
+    if (base < 0) return -1;
     sb::WalkArgs A;
     fill(A, genesT, Gs, S, W32p, shift);
-    A.pairs = pairs;
+    A.pairs = pairs; A.lab_base = base;
     const int T = sb::WALK_THREADS;
     const size_t words = (size_t)10 * (stack_units > 0 ? stack_units : 1) * T * sb::WALK_NPAIR;
     std::vector<int> smem(words + GUARD, CANARY);
@@ -81,11 +85,11 @@ int emul_pairs(const uint16_t *ops, int n_ops, const uint32_t *labels, const uin
 int emul_permute(const uint16_t *ops, int n_ops, const uint32_t *labelsW, int P, int ppi, const uint32_t *genesT,
                  int64_t Gs, int64_t S, int W32p, int shift, int stack_units, const int32_t *unperm, uint8_t *hits)
 {
-    if (load_program(ops, n_ops) || (int64_t)P * W32p > sb::C_LABEL_WORDS || ppi < 1 || ppi > sb::PERMS_PER_ITEM_MAX)
-        return -1;
-    memcpy(sb::c_labels, labelsW, sizeof(uint32_t) * (size_t)P * W32p);
+    const int base = load_pool(ops, n_ops, labelsW, P, W32p);
+    if (base < 0 || ppi < 1 || ppi > sb::PERMS_PER_ITEM_MAX) return -1;
     sb::WalkArgs A;
     fill(A, genesT, Gs, S, W32p, shift);
+    A.lab_base = base;
     A.n_perms = P; A.ppi = ppi; A.items_per_tile = (P + ppi - 1) / ppi; A.chunk_base = 0;
     A.unperm = unperm; A.hits = hits;
     const int T = sb::WALK_THREADS;
@@ -98,7 +102,35 @@ int emul_permute(const uint16_t *ops, int n_ops, const uint32_t *labelsW, int P,
                 sb::blockIdx = {(int)tile, chunk, 0};
                 sb::threadIdx = {tid, 0, 0};
                 sb::sb_emul_shared = smem.data();
-                sb::walk_permute_kernel(A);
+                sb::walk_permute_kernel<false>(A);
+            }
+    return guard_intact(smem, words) ? 0 : -2;
+}
+
+// K5, transposed launch: threads = labellings (labelsT [W32p][Ps], the label vectors transposed), constant rows =
+// the walk-order bits of n_rows genes (rowsW [n_rows][W32p]); hits [n_rows][Ps] bytes, unperm [n_rows][3]
+int emul_permute_transposed(const uint16_t *ops, int n_ops, const uint32_t *rowsW, int n_rows, int ppi,
+                            const uint32_t *labelsT, int64_t Ps, int64_t P, int W32p, int shift, int stack_units,
+                            const int32_t *unperm, uint8_t *hits)
+{
+    const int base = load_pool(ops, n_ops, rowsW, n_rows, W32p);
+    if (base < 0 || ppi < 1 || ppi > sb::PERMS_PER_ITEM_MAX) return -1;
+    sb::WalkArgs A;
+    fill(A, labelsT, Ps, P, W32p, shift);
+    A.S_total = Ps; A.lab_base = base; A.row_base = 0;
+    A.n_perms = n_rows; A.ppi = ppi; A.items_per_tile = (n_rows + ppi - 1) / ppi;
+    A.unperm = unperm; A.hits = hits;
+    const int T = sb::WALK_THREADS;
+    const size_t words = (size_t)5 * (stack_units > 0 ? stack_units : 1) * T * sb::WALK_NPAIR;
+    std::vector<int> smem(words + GUARD, CANARY);
+    const int64_t per_block = (int64_t)T * sb::WALK_NP;
+    for (int64_t tile = 0; tile < (P + per_block - 1) / per_block; ++tile)
+        for (int chunk = 0; chunk < A.items_per_tile; ++chunk)
+            for (int tid = 0; tid < T; ++tid) {
+                sb::blockIdx = {(int)tile, chunk, 0};
+                sb::threadIdx = {tid, 0, 0};
+                sb::sb_emul_shared = smem.data();
+                sb::walk_permute_kernel<true>(A);
             }
     return guard_intact(smem, words) ? 0 : -2;
 }

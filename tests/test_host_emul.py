@@ -36,6 +36,10 @@ def _build_walk_emul(lib_path, extra=()):
     lib.emul_permute.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                                  ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                  ctypes.c_void_p, ctypes.c_void_p]
+    if hasattr(lib, "emul_permute_transposed"):
+        lib.emul_permute_transposed.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                                ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+                                                ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
     return lib
 
 
@@ -127,6 +131,38 @@ def _check_permute(lib, n, G, comb, ppi):
     assert np.array_equal(got, ref["hits"])
     assert np.array_equal(got.sum(axis=1), ref["r"])
     _no_carries(lib)
+
+
+def _check_permute_transposed(lib, n, G, comb, ppi, P=41):
+    """the transposed launch (threads = labellings, constant rows = genes): the same hit flags as the oracle's
+    Permute -- the DP is symmetric in the gene and the trait bit of a leaf"""
+    c = _setup(n, G, 300 + n, comb)
+    seed = 78
+    ref = O.permute(c["left"], c["right"], c["m"], c["lab"], P=P, seed=seed, trait=0, want_hits=True)
+    labs = np.stack([O.shuffle_labels(seed, 0, p, c["lab"]) for p in range(P)])
+    labelsW = _pack_walk_order(labs, c["order"], c["W32p"])                 # [P][W32p]
+    Ps = (P + 31) // 32 * 32
+    labelsT = np.zeros((c["W32p"], Ps), dtype=np.uint32)
+    labelsT[:, :P] = labelsW.T
+    rowsW = np.ascontiguousarray(c["genesT"][:, :G].T)                      # [G][W32p]
+    hits = np.full((G, Ps), 9, dtype=np.uint8)
+    unperm = np.ascontiguousarray(ref["pairs"], dtype=np.int32)
+    rc = lib.emul_permute_transposed(_ptr(c["ops"]), len(c["ops"]), _ptr(rowsW), G, ppi, _ptr(np.ascontiguousarray(labelsT)),
+                                     Ps, P, c["W32p"], c["shift"], c["units"], _ptr(unperm), _ptr(hits))
+    assert rc == 0
+    assert np.array_equal(hits[:, :P], ref["hits"])
+    assert np.all(hits[:, P:] == 9)                                         # nothing written past the labellings
+    _no_carries(lib)
+
+
+@pytest.mark.parametrize("n,G,comb", [(2, 5, False), (5, 9, False), (16, 7, False), (100, 13, False), (127, 6, False),
+                                      (129, 30, False), (300, 12, False), (150, 8, True), (1000, 5, False),
+                                      (5000, 3, False)])
+@pytest.mark.parametrize("ppi", [1, 4])
+def test_transposed_permute_kernel_source_on_the_host(emul, n, G, comb, ppi):
+    if ppi != 4 and n > 200:
+        pytest.skip("one ppi is enough for the large trees")
+    _check_permute_transposed(emul, n, G, comb, ppi, P=41 if n < 2000 else 9)
 
 
 def test_shared_stack_size_reported_by_the_compiler_is_tight(emul):
@@ -406,37 +442,35 @@ def femul():
                         "-fPIC,-ffp-contract=off", "-ccbin", cxx, "-shared", "-o", FLIB, FSRC,
                         os.path.join(CSRC, "lut.cpp"), "-lquadmath", "-lpthread"], check=True)
     lib = ctypes.CDLL(FLIB)
-    lib.emul_fisher.argtypes = lib.emul_fisher2.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
+    lib.emul_fisher.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
 
-    def run(tables, version=1):
-        """tables int [n][4] in the oracle's / C-ABI's order (tpgp, tngp, tpgn, tngn) -> p [n];
-        version 1 = fisher.cuh (the product kernel), 2 = fisher2.cuh (experimental, four tables per warp)"""
+    def run(tables):
+        """tables int [n][4] in the oracle's / C-ABI's order (tpgp, tngp, tpgn, tngn) -> p [n]"""
         t = np.ascontiguousarray(np.asarray(tables, dtype=np.int32)[:, [0, 2, 1, 3]])     # kernel order a, b, c, d
         p = np.full(len(t), -1.0, dtype=np.float64)
-        assert (lib.emul_fisher if version == 1 else lib.emul_fisher2)(_ptr(t), len(t), _ptr(p)) == 0
+        assert lib.emul_fisher(_ptr(t), len(t), _ptr(p)) == 0
         return p
     return run
 
 
-@pytest.mark.parametrize("version", [1, 2])
-def test_fisher_source_on_the_host_matches_scipy_goldens(femul, version):
+def test_fisher_source_on_the_host_matches_scipy_goldens(femul):
     """The 600 SciPy tables the oracle is pinned on (tests/golden/fisher.json), through the kernel's own
     warp-cooperative code: same tolerance as the GPU parity tests (1e-10 relative)."""
     import json
     gold = json.load(open(os.path.join(os.path.dirname(HERE), "golden", "fisher.json")))["tables"]
     tabs = np.array([[g["tpgp"], g["tngp"], g["tpgn"], g["tngn"]] for g in gold], dtype=np.int32)
     want = np.array([float.fromhex(g["p"]) for g in gold])
-    got = femul(tabs, version)
+    got = femul(tabs)
     ok = want > 1e-290
+    print("max rel err vs SciPy", np.max(np.abs(got[ok] - want[ok]) / want[ok]))
     assert np.max(np.abs(got[ok] - want[ok]) / want[ok]) <= FISHER_RTOL
     assert np.all(got[~ok] <= 2e-290)
-    if version == 2:        # a batch that does not fill the last warp, in another order: same values per table
-        perm = np.random.default_rng(1).permutation(len(tabs))[:-3]
-        assert np.array_equal(femul(tabs[perm], 2).view(np.uint64), got[perm].view(np.uint64))
+    # a batch that does not fill the last warp, in another order: same values per table
+    perm = np.random.default_rng(1).permutation(len(tabs))[:-3]
+    assert np.array_equal(femul(tabs[perm]).view(np.uint64), got[perm].view(np.uint64))
 
 
-@pytest.mark.parametrize("version", [1, 2])
-def test_fisher_source_on_the_host_large_tables_and_symmetry(femul, version):
+def test_fisher_source_on_the_host_large_tables_and_symmetry(femul):
     """N up to 20 000 against the oracle (binary128), and the canonical orientation: the eight symmetric
     variants of a table (row swap, column swap, transpose) must give bit-identical p."""
     rng = np.random.default_rng(5)
@@ -453,14 +487,41 @@ def test_fisher_source_on_the_host_large_tables_and_symmetry(femul, version):
     for t in ([0, 0, 3, 5], [4, 0, 0, 6], [0, 7, 0, 2], [1, 0, 0, 0], [1, 1, 1, 1], [0, 1, 1, 0], [2, 0, 0, 1]):
         tabs.append(t)                                                 # empty margins, tiny tables
     tabs = np.array(tabs, dtype=np.int32)
-    got = femul(tabs, version)
+    got = femul(tabs)
     want = O.fisher(tabs)
     ok = want > 1e-290
+    print("max rel err vs binary128", np.max(np.abs(got[ok] - want[ok]) / want[ok]))
     assert np.max(np.abs(got[ok] - want[ok]) / want[ok]) <= FISHER_RTOL
     variants = []
     for a, c, b, d in tabs[:60]:                                      # [[a, b], [c, d]]
         for (w, x, y, z) in ((a, b, c, d), (c, d, a, b), (b, a, d, c), (d, c, b, a), (a, c, b, d), (b, d, a, c),
                              (c, a, d, b), (d, b, c, a)):
             variants.append([w, y, x, z])                             # back to tpgp, tngp, tpgn, tngn
-    pv = femul(np.array(variants, dtype=np.int32), version).reshape(-1, 8)
+    pv = femul(np.array(variants, dtype=np.int32)).reshape(-1, 8)
     assert np.all(pv.view(np.uint64) == pv.view(np.uint64)[:, :1])
+
+
+def test_fisher_near_mode_complement_path_accuracy(femul):
+    """Tables whose observed cell lies within a few standard deviations of the mode take the complement path of
+    fisher.cuh (p = 1 - the terms between a and the far-side boundary, kept for p >= 0.01): 3 000 such tables at
+    the BASELINE isolate counts against the oracle's binary128 sums -- the switch between the two paths (p around
+    0.01, |z| around 2.5) must not be visible at 1e-10."""
+    rng = np.random.default_rng(17)
+    tabs = []
+    for N in (100, 1000, 2000, 5000, 10000):
+        for _ in range(600):
+            r1 = int(rng.integers(max(2, N // 50), N - 1))
+            c1 = int(rng.integers(max(2, N // 50), N - 1)) if rng.random() < 0.7 else int(0.35 * N)
+            lo, hi = max(0, r1 + c1 - N), min(r1, c1)
+            sd = max(r1 * c1 / N * (1 - r1 / N) * (1 - c1 / N), 0.25) ** 0.5
+            z = rng.uniform(-3.2, 3.2)
+            a = int(np.clip(round(r1 * c1 / N + z * sd), lo, hi))
+            tabs.append([a, c1 - a, r1 - a, N - r1 - c1 + a])          # tpgp, tngp, tpgn, tngn
+    tabs = np.array(tabs, dtype=np.int32)
+    got = femul(tabs)
+    want = O.fisher(tabs)
+    rel = np.abs(got - want) / want
+    print("near-mode tables: max rel err %.2e; p range %.2e .. 1; %d tables with 0.005 < p < 0.02" % (
+        rel.max(), want.min(), int(((want > 0.005) & (want < 0.02)).sum())))
+    assert rel.max() <= 1e-11
+    assert ((want > 0.005) & (want < 0.02)).sum() >= 50

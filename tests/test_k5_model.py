@@ -19,19 +19,20 @@ def _count(kernel, n_isolates, perms, ppi, chunk):
     import sass_emul
     lib = os.path.join(ROOT, "scoary_b200", "libscoary_b200.so")
     ops, labelsW, W32p, shift = k5_model.workload(n_isolates, 4242, perms, 7)
-    const3 = bytearray(k5_model.C_OPS_BYTES + 4 * labelsW.size)
+    base = k5_model.label_base(len(ops))
+    const3 = bytearray(4 * base + 4 * labelsW.size)
     const3[:2 * len(ops)] = ops.astype("<u2").tobytes()
-    const3[k5_model.C_OPS_BYTES:] = labelsW.astype("<u4").tobytes()
+    const3[4 * base:] = labelsW.astype("<u4").tobytes()
     instrs, labels, const2 = sass_emul.extract(lib, kernel)
-    params = sass_emul.walk_args(1024, 1000, 1000, W32p, shift, perms, ppi)
+    params = sass_emul.walk_args(1024, 1000, 1000, W32p, shift, perms, ppi, lab_base=base)
     m = sass_emul.Machine(instrs, labels, const2, params, bytes(const3), tid=0, ctaid=(0, chunk, 0))
     return m.run(max_steps=2_000_000), m, instrs
 
 
 def test_interpreter_follows_the_permutation_kernel_to_its_exit():
     """every branch of K5 resolves from block-uniform data; the count scales with the labellings walked"""
-    one, m1, _ = _count("walk_permute_kernel", 300, 4, 1, 0)
-    two, m2, instrs = _count("walk_permute_kernel", 300, 4, 2, 1)
+    one, m1, _ = _count("walk_permute_kernelILb0", 300, 4, 1, 0)
+    two, m2, instrs = _count("walk_permute_kernelILb0", 300, 4, 2, 1)
     assert len(m1.assumed) <= 4 and all(v == 1 for v in m1.assumed.values())      # the four guarded result stores
     per_walk = two - one                                                          # second labelling of the block
     assert 299 * 25 < per_walk < 299 * 90                                         # 4 genes per thread: ~55 per node

@@ -25,7 +25,9 @@ import numpy as np  # noqa: E402
 
 import sass_emul  # noqa: E402
 
-C_OPS_BYTES = 2 * 12288          # csrc/walk.cuh: c_ops, then c_labels, in constant bank 3
+def label_base(n_ops):
+    """csrc/walk.cuh walk_label_base: first label word behind the program in the constant pool (bank 3)"""
+    return ((n_ops + 1) // 2 + 3) // 4 * 4
 
 
 def workload(n_isolates, seed, n_perms, perm_seed):
@@ -82,7 +84,7 @@ def pipe_of(op):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--lib", default=os.path.join(ROOT, "scoary_b200", "libscoary_b200.so"))
-    ap.add_argument("--kernel", default="walk_permute_kernel")
+    ap.add_argument("--kernel", default="walk_permute_kernelILb0")
     ap.add_argument("--isolates", type=int, default=5000)
     ap.add_argument("--genes", type=int, default=50000)
     ap.add_argument("--seed", type=int, default=20260903)
@@ -98,12 +100,13 @@ def main():
     os.environ["SCOARY_B200_LIB"] = os.path.abspath(a.lib)      # the tree compiler of the library being modelled
 
     ops, labelsW, W32p, shift = workload(a.isolates, a.seed, a.perms, a.perm_seed)
-    const3 = bytearray(C_OPS_BYTES + 4 * labelsW.size)
+    base = label_base(len(ops))
+    const3 = bytearray(4 * base + 4 * labelsW.size)
     const3[:2 * len(ops)] = ops.astype("<u2").tobytes()
-    const3[C_OPS_BYTES:] = labelsW.astype("<u4").tobytes()
+    const3[4 * base:] = labelsW.astype("<u4").tobytes()
     instrs, labels, const2 = sass_emul.extract(a.lib, a.kernel)
     Gs = (a.genes + 31) // 32 * 32
-    params = sass_emul.walk_args(Gs, a.genes, a.genes, W32p, shift, a.perms, a.ppi)
+    params = sass_emul.walk_args(Gs, a.genes, a.genes, W32p, shift, a.perms, a.ppi, lab_base=base)
     n_chunks = (a.perms + a.ppi - 1) // a.ppi
     chunks = range(n_chunks) if a.chunks == "all" else [int(c) for c in a.chunks.split(",")]
     per_chunk = {}

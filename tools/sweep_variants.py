@@ -16,34 +16,18 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VDIR = os.path.join(ROOT, "variants")
 # name: compiler switches, or (git revision, switches) to build the kernels as they were at that revision
 VARIANTS = {
-    "r1_profiled": ("5af1521", ""),           # the K5 that profiles/r1_ncu_walk_permute.txt was captured on
-    "prmt": "-DSB_WALK_PRMT=1",               # gene-bit masks by PRMT sign replication (tools/k5_model.py: -3.4 % instructions)
-    "prmt_npair3_mb3": "-DSB_WALK_PRMT=1 -DSB_WALK_NPAIR=3 -DSB_WALK_MINBLOCKS=3",
-    # two labellings in lockstep per thread (shares program decode, stream bookkeeping and gene masks: -20 % instructions
-    # per walk by tools/k5_model.py); 165 registers: 12 warps per SM
-    "nlab2_t64_mb6": "-DSB_WALK_NLAB=2 -DSB_WALK_THREADS=64 -DSB_WALK_MINBLOCKS=6",
-    "nlab2_t128_mb3": "-DSB_WALK_NLAB=2 -DSB_WALK_MINBLOCKS=3",
-    "nlab2_prmt_t64_mb6": "-DSB_WALK_NLAB=2 -DSB_WALK_PRMT=1 -DSB_WALK_THREADS=64 -DSB_WALK_MINBLOCKS=6",
-    # leaf stream padded by the host compiler so that no op crosses a window: no general path in the kernels
-    # (static code 42 -> 33 KB, 80 % of the executed instructions inside 5.6 KB, -1.7 % instructions)
-    "padded": "-DSB_WALK_PADDED=1",
-    "padded_prmt": "-DSB_WALK_PADDED=1 -DSB_WALK_PRMT=1",
-    "padded_nlab2_t64_mb6": "-DSB_WALK_PADDED=1 -DSB_WALK_NLAB=2 -DSB_WALK_THREADS=64 -DSB_WALK_MINBLOCKS=6",
-    "padded_nlab2_prmt_t64_mb6": "-DSB_WALK_PADDED=1 -DSB_WALK_NLAB=2 -DSB_WALK_PRMT=1 -DSB_WALK_THREADS=64 -DSB_WALK_MINBLOCKS=6",
-    "padded_mb6": "-DSB_WALK_PADDED=1 -DSB_WALK_MINBLOCKS=6",
-    "minblocks4": "-DSB_WALK_MINBLOCKS=4",
-    "minblocks6": "-DSB_WALK_MINBLOCKS=6",
-    "threads96_mb6": "-DSB_WALK_THREADS=96 -DSB_WALK_MINBLOCKS=6",
-    "threads64_mb10": "-DSB_WALK_THREADS=64 -DSB_WALK_MINBLOCKS=10",
-    "threads256_mb2": "-DSB_WALK_THREADS=256 -DSB_WALK_MINBLOCKS=2",
-    "threads320_mb2": "-DSB_WALK_THREADS=320 -DSB_WALK_MINBLOCKS=2",   # 2 x 10 warps: fewer program positions per SM (L0 I-cache)
-    "npair1_mb8": "-DSB_WALK_NPAIR=1 -DSB_WALK_MINBLOCKS=8",
-    "npair3_mb3": "-DSB_WALK_NPAIR=3 -DSB_WALK_MINBLOCKS=3",
-    "fisher_v2_512": "-DSB_FISHER_V2=1 -DSB_FISHER2_THREADS=512",     # csrc/fisher2.cuh: four genes per warp
-    "fisher_v2_768": "-DSB_FISHER_V2=1 -DSB_FISHER2_THREADS=768",
-    "fisher_v2_256": "-DSB_FISHER_V2=1 -DSB_FISHER2_THREADS=256",
+    # round-2 session r2a (profiles/r2_sweep_a.txt): prmt 1.03x, minblocks6 1.03x, everything else <= 1.00x
+    # (two labellings in lockstep 0.88-0.97x despite -20 % instructions: 12 warps per SM do not hide the ALU latency)
+    "prmt": "-DSB_WALK_PRMT=1",               # gene-bit masks by PRMT sign replication
+    "minblocks6": "-DSB_WALK_MINBLOCKS=6",    # 80 registers: 24 warps per SM
+    "prmt_mb6": "-DSB_WALK_PRMT=1 -DSB_WALK_MINBLOCKS=6",
+    "prmt_mb7": "-DSB_WALK_PRMT=1 -DSB_WALK_MINBLOCKS=7",
+    "prmt_t96_mb8": "-DSB_WALK_PRMT=1 -DSB_WALK_THREADS=96 -DSB_WALK_MINBLOCKS=8",
+    "prmt_t160_mb5": "-DSB_WALK_PRMT=1 -DSB_WALK_THREADS=160 -DSB_WALK_MINBLOCKS=5",
+    "prmt_t192_mb4": "-DSB_WALK_PRMT=1 -DSB_WALK_THREADS=192 -DSB_WALK_MINBLOCKS=4",
     "fisher512": "-DSB_FISHER_THREADS=512",
-    "fisher256": "-DSB_FISHER_THREADS=256",
+    "fisher1024": "-DSB_FISHER_THREADS=1024",
+    "fisher640": "-DSB_FISHER_THREADS=640",
 }
 
 
