@@ -532,7 +532,7 @@ int launch_fisher(sb_ctx *ctx, int32_t t0, int32_t nT, int32_t *d_counts, double
         if (!ctx->traits[t].has_trait) return fail(ctx, SB_ERR_STATE, "trait not set (sb_set_trait)");
     const size_t row_bytes = (size_t)ctx->W * 8;
     const size_t lut_bytes = sizeof(double2) * (size_t)(ctx->lut_n + 1);
-    constexpr size_t NW = sb::FISHER_THREADS / 32, ROWS_PER_WARP = sb::F_GENES;
+    constexpr size_t ROWS_PER_WARP = sb::F_GENES;
     const bool hash = d_hash != nullptr;
     const int64_t G = ctx->G;
     for (int32_t c0 = 0; c0 < nT; c0 += sb::FISHER_MAX_TRAITS) {
@@ -544,10 +544,13 @@ int launch_fisher(sb_ctx *ctx, int32_t t0, int32_t nT, int32_t *d_counts, double
         A.counts = d_counts ? d_counts + (size_t)c0 * G * 4 : nullptr;
         A.p = d_p ? d_p + (size_t)c0 * G : nullptr;
         A.hash = d_hash ? d_hash + (size_t)c0 * G * 2 : nullptr;
-        // [2 mbarriers per warp][per trait: value & mask, mask][2 buffers of 4 rows per warp][LUT if it fits]
-        const size_t fixed = 16 * NW + 2 * row_bytes * n + 2 * NW * ROWS_PER_WARP * row_bytes;
+        // [2 mbarriers per warp][per trait: value & mask, mask][2 buffers of 4 rows per warp][LUT if it fits];
+        // long rows leave room for fewer warps (N = 32 766: 4 KB rows, 6 warps)
         const size_t budget = (size_t)ctx->max_smem_optin - 256;     // minus the kernel's static shared memory
-        if (fixed > budget) return fail(ctx, SB_ERR_ARG, "row too long for shared memory");
+        const size_t per_warp = 16 + 2 * ROWS_PER_WARP * row_bytes, traits_bytes = 2 * row_bytes * n;
+        if (traits_bytes + per_warp > budget) return fail(ctx, SB_ERR_ARG, "row too long for shared memory");
+        const size_t NW = std::min<size_t>(sb::FISHER_THREADS / 32, (budget - traits_bytes) / per_warp);
+        const size_t fixed = 16 * NW + traits_bytes + 2 * NW * ROWS_PER_WARP * row_bytes;
         const bool lut_smem = fixed + lut_bytes <= budget;
         const size_t smem = fixed + (lut_smem ? lut_bytes : 0);
         const int64_t rows_per_cta = (int64_t)(NW * ROWS_PER_WARP);
@@ -557,7 +560,7 @@ int launch_fisher(sb_ctx *ctx, int32_t t0, int32_t nT, int32_t *d_counts, double
     do {                                                                                                           \
         SB_CUDA(ctx, cudaFuncSetAttribute(sb::fisher_kernel<L, H>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                                           (int)smem));                                                             \
-        sb::fisher_kernel<L, H><<<grid, sb::FISHER_THREADS, smem, ctx->stream>>>(A);                               \
+        sb::fisher_kernel<L, H><<<grid, (unsigned)(NW * 32), smem, ctx->stream>>>(A);                              \
     } while (0)
         if (lut_smem && hash) SB_LAUNCH_FISHER(true, true);
         else if (lut_smem) SB_LAUNCH_FISHER(true, false);
@@ -631,11 +634,13 @@ int launch_pairwise(sb_ctx *ctx, int32_t t, const int64_t *d_gene_idx, int64_t S
 int launch_shuffle(sb_ctx *ctx, int32_t t, int32_t P, uint64_t seed, uint32_t *d_labelsW, uint8_t *d_dbg)
 {
     TraitSlot &s = ctx->traits[t];
-    const size_t smem = sizeof(uint32_t) * (size_t)s.W32 * 64;
+    int T = 64;       // permutations (threads) per block: 64 label vectors in shared memory, 32 above ~28 000 leaves
+    while (T > 8 && sizeof(uint32_t) * (size_t)s.W32 * T > (size_t)ctx->max_smem_optin) T /= 2;
+    const size_t smem = sizeof(uint32_t) * (size_t)s.W32 * T;
     if (smem > (size_t)ctx->max_smem_optin) return fail(ctx, SB_ERR_ARG, "too many leaves for the shuffle kernel");
     SB_CUDA(ctx, cudaFuncSetAttribute(sb::shuffle_labels_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     Timed tm(ctx, CAT_SHUFFLE);
-    sb::shuffle_labels_kernel<<<(P + 63) / 64, 64, smem, ctx->stream>>>(s.d_labels_leaf, s.n_leaves, s.W32, s.W32p,
+    sb::shuffle_labels_kernel<<<(P + T - 1) / T, T, smem, ctx->stream>>>(s.d_labels_leaf, s.n_leaves, s.W32, s.W32p,
                                                                        s.d_leaf_of_pos, seed, t, P, d_labelsW, d_dbg);
     ctx->stats.kernel_launches += 1;
     SB_CUDA(ctx, cudaGetLastError());

@@ -242,8 +242,10 @@ template <bool LUT_SMEM, bool HASH>
 __global__ void __launch_bounds__(FISHER_THREADS) fisher_kernel(const FisherArgs A)
 {
     // Shared memory: [2 mbarriers per warp] [per trait: value & mask, mask] [2 x 4 row buffers per warp] [LUT]
+    // The block may be launched with fewer than FISHER_THREADS threads: long rows (N > ~7 000 isolates) leave
+    // room for fewer warps' row buffers.
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int NW = FISHER_THREADS / 32;
+    const int NW = (int)blockDim.x >> 5, NT = (int)blockDim.x;
     __shared__ int s_tot[FISHER_MAX_TRAITS][2];      // per trait: positives, non-missing
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
     uint64_t *s_tr = reinterpret_cast<uint64_t *>(smem_raw + 16 * NW);          // [n_traits][2][W]: value & mask, mask
@@ -276,25 +278,25 @@ __global__ void __launch_bounds__(FISHER_THREADS) fisher_kernel(const FisherArgs
             if (bt < n_batches) issue(bt, bf);
         }
     }
-    for (int i = tid; i < nT * A.W; i += FISHER_THREADS) {
+    for (int i = tid; i < nT * A.W; i += NT) {
         const int t = i / A.W, w = i - t * A.W;
         const uint64_t m = A.traits[((size_t)t * 2 + 1) * A.W + w];
         s_tr[((size_t)t * 2 + 1) * A.W + w] = m;
         s_tr[((size_t)t * 2) * A.W + w] = A.traits[((size_t)t * 2) * A.W + w] & m;
     }
     if (LUT_SMEM) {
-        for (int k = tid; k <= A.lut_n; k += FISHER_THREADS) s_lut[k] = A.lut[k];
+        for (int k = tid; k <= A.lut_n; k += NT) s_lut[k] = A.lut[k];
     }
     __syncthreads();
-    if (warp < nT) {       // trait totals, one warp per trait
+    for (int t = warp; t < nT; t += NW) {       // trait totals, one warp per trait
         int n_tp = 0, n_m = 0;
         for (int w = lane; w < A.W; w += 32) {
-            n_tp += __popcll(s_tr[((size_t)warp * 2) * A.W + w]);
-            n_m += __popcll(s_tr[((size_t)warp * 2 + 1) * A.W + w]);
+            n_tp += __popcll(s_tr[((size_t)t * 2) * A.W + w]);
+            n_m += __popcll(s_tr[((size_t)t * 2 + 1) * A.W + w]);
         }
         n_tp = __reduce_add_sync(0xffffffffu, n_tp);
         n_m = __reduce_add_sync(0xffffffffu, n_m);
-        if (lane == 0) { s_tot[warp][0] = n_tp; s_tot[warp][1] = n_m; }
+        if (lane == 0) { s_tot[t][0] = n_tp; s_tot[t][1] = n_m; }
     }
     __syncthreads();   // trait vectors, totals and LUT staged (the only block-wide barriers)
     const double2 *lut = LUT_SMEM ? s_lut : A.lut;

@@ -184,8 +184,8 @@ __global__ void __launch_bounds__(64) shuffle_labels_kernel(const uint32_t *__re
                                                             int trait, int P, uint32_t *__restrict__ labelsW,
                                                             uint8_t *__restrict__ dbg_leaf /* [P][n_leaves] or null */)
 {
-    extern __shared__ uint32_t s_lab[];   // [W32][64]
-    const int T = 64, tid = threadIdx.x;
+    extern __shared__ uint32_t s_lab[];   // [W32][T]
+    const int T = (int)blockDim.x, tid = threadIdx.x;
     const int perm = blockIdx.x * T + tid;
     for (int w = 0; w < W32; ++w) s_lab[w * T + tid] = labels_leaf[w];
     if (perm >= P) return;   // no block-wide sync below

@@ -29,10 +29,29 @@ def _popcount_rows(words):
     return np.bitwise_count(words).sum(axis=1).astype(np.int64)
 
 
-def check(engine, G, N, P, seed, missing=0.0, n_oracle=8, n_subset=1000):
-    traits = synth.make_traits(N, 1, seed, missing_frac=missing)
-    vec = traits[0]
+def check(engine, G, N, P, seed, missing=0.0, n_oracle=8, n_subset=1000, T=1):
+    """T > 1: the job has T traits (BASELINE C4 has four).  The Fisher pass of all of them runs as ONE multi-trait call
+    and must equal the single-trait calls bit for bit; the walk / permutation properties are then checked for every
+    trait in turn (its own mask, pruned tree and labellings)."""
+    traits = synth.make_traits(N, T, seed, missing_frac=missing)
     bits = synth.make_genes_packed(G, N, seed, traits=traits)
+    out = None
+    if T > 1:
+        engine.set_genes(bits, N)
+        for t in range(T):
+            engine.set_trait_vector(t, traits[t])
+        c_all, p_all, h_all = engine.contingency_fisher_multi(0, T, want_hash=True)
+        for t in range(T):
+            c1, p1, h1 = engine.contingency_fisher(t, want_hash=True)
+            assert np.array_equal(c_all[t], c1) and np.array_equal(h_all[t], h1)
+            assert np.array_equal(p_all[t].view(np.uint64), p1.view(np.uint64))
+    for t in range(T):
+        res = _check_trait(engine, bits, traits[t], t, G, N, P, seed, n_oracle, n_subset)
+        out = res if out is None else {k: out[k] + res[k] for k in out}
+    return out
+
+
+def _check_trait(engine, bits, vec, trait_index, G, N, P, seed, n_oracle, n_subset):
     value, mask = eng.pack_trait(vec)
     names = synth.isolate_names(N)
     nested = treemod.prune(synth.make_tree(N, seed), [names[j] for j in range(N) if vec[j] < 0])
@@ -42,9 +61,9 @@ def check(engine, G, N, P, seed, missing=0.0, n_oracle=8, n_subset=1000):
     n_mask, n_pos = int(np.bitwise_count(mask).sum()), int(np.bitwise_count(value & mask).sum())
 
     engine.set_genes(bits, N)
-    engine.set_trait_vector(0, vec)
-    engine.set_tree(0, left, right, cols)
-    counts, p, _ = engine.contingency_fisher(0)
+    engine.set_trait_vector(trait_index, vec)
+    engine.set_tree(trait_index, left, right, cols)
+    counts, p, _ = engine.contingency_fisher(trait_index)
     # ---- counts
     pc = _popcount_rows(bits & mask)
     pct = _popcount_rows(bits & (value & mask))
@@ -53,7 +72,7 @@ def check(engine, G, N, P, seed, missing=0.0, n_oracle=8, n_subset=1000):
     tested = (pc > 0) & (pc < n_mask)
     assert np.all((p[tested] >= 0) & (p[tested] <= 1.0))      # planted genes underflow to 0 at N = 5000, as in SciPy
     # ---- exhaustive permutations
-    pairs, r, nd = engine.permute(0, P, seed=seed)
+    pairs, r, nd = engine.permute(trait_index, P, seed=seed)
     assert np.all(nd == P) and np.all((r >= 0) & (r <= P))
     total, pro, anti = pairs[:, 0].astype(np.int64), pairs[:, 1].astype(np.int64), pairs[:, 2].astype(np.int64)
     assert np.all((pro >= 0) & (anti >= 0) & (pro <= total) & (anti <= total))
@@ -66,25 +85,25 @@ def check(engine, G, N, P, seed, missing=0.0, n_oracle=8, n_subset=1000):
         full[w] = np.uint64((1 << nb) - 1) if nb < 64 else np.uint64(0xFFFFFFFFFFFFFFFF)
     bits_c = bits ^ full
     engine.set_genes(bits_c, N)
-    counts_c, p_c, _ = engine.contingency_fisher(0)
+    counts_c, p_c, _ = engine.contingency_fisher(trait_index)
     assert np.array_equal(counts_c[:, [2, 3, 0, 1]], counts)
     assert np.array_equal(np.isfinite(p), np.isfinite(p_c))
     both = np.isfinite(p) & np.isfinite(p_c) & (p > 1e-290)
     assert np.max(np.abs(p_c[both] - p[both]) / p[both], initial=0.0) <= FISHER_RTOL
     tiny = np.isfinite(p) & (p <= 1e-290)
     assert np.all(p_c[tiny] <= 2e-290)
-    pairs_c, r_c, nd_c = engine.permute(0, P, seed=seed)
+    pairs_c, r_c, nd_c = engine.permute(trait_index, P, seed=seed)
     assert np.array_equal(pairs_c[:, [0, 2, 1]], pairs) and np.all(nd_c == P)
     strict = pro != anti
     assert np.array_equal(r_c[strict], r[strict])
     # ---- any subset of genes gives the rows of the full run
     rng = np.random.default_rng(seed)
     idx = np.sort(rng.choice(G, size=min(n_subset, G), replace=False)).astype(np.int64)
-    pairs_s, r_s, nd_s = engine.permute(0, P, seed=seed, gene_idx=idx)
+    pairs_s, r_s, nd_s = engine.permute(trait_index, P, seed=seed, gene_idx=idx)
     assert np.array_equal(pairs_s, pairs_c[idx]) and np.array_equal(r_s, r_c[idx]) and np.all(nd_s == P)
-    assert np.array_equal(engine.pairwise(0, idx), pairs_c[idx])
+    assert np.array_equal(engine.pairwise(trait_index, idx), pairs_c[idx])
     # a different seed gives different labellings (some hit count changes) but the same unpermuted walk
-    pairs_o, r_o, _ = engine.permute(0, P, seed=seed + 1, gene_idx=idx)
+    pairs_o, r_o, _ = engine.permute(trait_index, P, seed=seed + 1, gene_idx=idx)
     assert np.array_equal(pairs_o, pairs_s)
     if P >= 10 and len(idx) >= 20:
         assert not np.array_equal(r_o, r_s)
@@ -97,6 +116,6 @@ def check(engine, G, N, P, seed, missing=0.0, n_oracle=8, n_subset=1000):
     ref_p = O.fisher(ref_counts)
     ok = np.isfinite(ref_p) & (ref_p > 1e-290)
     assert np.max(np.abs(p[pick][ok] - ref_p[ok]) / ref_p[ok], initial=0.0) <= FISHER_RTOL
-    ref = O.permute(left, right, m[:, cols], vec[cols].astype(np.uint8), P=P, seed=seed, trait=0)
+    ref = O.permute(left, right, m[:, cols], vec[cols].astype(np.uint8), P=P, seed=seed, trait=trait_index)
     assert np.array_equal(pairs[pick], ref["pairs"]) and np.array_equal(r[pick], ref["r"])
     return {"tested": int(tested.sum()), "strict": int(strict.sum()), "oracle_genes": len(pick)}

@@ -333,3 +333,117 @@ def test_empty_selections(engine):
     assert engine.pairwise(0, none).shape == (0, 3)
     pairs, r, nd = engine.permute(0, 10, gene_idx=none)
     assert pairs.shape == (0, 3) and r.shape == (0,) and nd.shape == (0,)
+
+
+@pytest.mark.parametrize("G,N,P,S", [(400, 300, 700, 3), (400, 300, 1100, 41), (200, 1000, 600, 130), (64, 5000, 1500, 64),
+                                     (50, 129, 513, 1)])
+def test_transposed_launches_match_oracle_and_default_shape(engine, G, N, P, S):
+    """Few genes x many permutations (what is left after decideifbreak, methods.py:1022-1024, :1295-1310): K5 runs
+    with threads = labellings (sb_set_permute_mode 2).  Same r / n_done as the oracle's Permute and as the
+    threads = genes shape, exhaustive and with the reference's early stop; the automatic choice picks it here."""
+    bits, traits = _dataset(G, N, 6000 + G + N, 0.02)
+    nested, col = _tree_for(N, 21 + N, traits[0])
+    engine.set_genes(bits, N)
+    engine.set_trait_vector(3, traits[0])
+    names = engine.set_tree_nested(3, nested, col)
+    left, right, _ = O.flatten_tree(nested)
+    m = synth.unpack_rows(bits, N)
+    cols = np.asarray([col[n] for n in names])
+    labels = traits[0][cols].astype(np.uint8)
+    idx = np.random.default_rng(S).choice(G, size=S, replace=False).astype(np.int64)
+    idx[0] = 0                                                    # a planted gene: never stops early
+    rmin = O.rmin_table(P)
+    try:
+        for es in (False, True):
+            ref = O.permute(left, right, m[np.ix_(idx, cols)], labels, P=P, seed=99, trait=3, early_stop=es)
+            out = {}
+            for mode in (1, 2, 0):
+                engine.set_permute_mode(mode)
+                engine.stats_reset()
+                pairs, r, nd = engine.permute(3, P, seed=99, gene_idx=idx, early_stop=es, rmin=rmin if es else None)
+                out[mode] = engine.stats()["calls_transposed"]
+                assert np.array_equal(pairs, ref["pairs"]), (mode, es)
+                assert np.array_equal(r, ref["r"]) and np.array_equal(nd, ref["n_done"]), (mode, es)
+            assert out[1] == 0 and out[2] == 1
+            if not es and S * 8 <= P:
+                assert out[0] == 1                                # auto: the transposed shape fills the GPU better
+    finally:
+        engine.set_permute_mode(0)
+
+
+@pytest.mark.parametrize("G,N,T,missing", [(300, 100, 2, 0.0), (1000, 1000, 4, 0.03), (257, 5000, 3, 0.01), (64, 333, 11, 0.05)])
+def test_multi_trait_fisher_pass_equals_single_calls(engine, G, N, T, missing):
+    """sb_contingency_fisher_multi: every gene row read once for all traits (the reference loops traits outside
+    genes, methods.py:771, :791).  Bit-identical to T single-trait calls -- counts, hashes and p -- and the counts
+    equal the oracle's; T = 11 exceeds the 8 traits one launch stages (two launches)."""
+    bits, traits = _dataset(G, N, 7000 + G + N, missing, T=T)
+    engine.set_genes(bits, N)
+    for t in range(T):
+        engine.set_trait_vector(5 + t, traits[t])                 # slots 5 ..: consecutive slots, not from 0
+    c_all, p_all, h_all = engine.contingency_fisher_multi(5, T, want_hash=True)
+    m = synth.unpack_rows(bits, N)
+    for t in range(T):
+        c1, p1, h1 = engine.contingency_fisher(5 + t, want_hash=True)
+        assert np.array_equal(c_all[t], c1) and np.array_equal(h_all[t], h1)
+        assert np.array_equal(p_all[t].view(np.uint64), p1.view(np.uint64))
+        ref_counts = O.contingency(m, traits[t])
+        assert np.array_equal(c1, ref_counts)
+        ref_p = O.fisher(ref_counts)
+        ok = ref_p > 1e-290
+        assert np.max(np.abs(p1 - ref_p)[ok] / ref_p[ok]) <= FISHER_RTOL
+
+
+def test_fisher_near_mode_and_tail_paths(engine):
+    """The Fisher kernel sums the complement for tables near the mode (p >= 0.01) and the two tails otherwise:
+    6 000 tables built to straddle the switch (|z| up to 3.5 at N = 5 000), against SciPy itself."""
+    N, G = 5000, 6000
+    rng = np.random.default_rng(123)
+    t = (rng.random(N) < 0.35).astype(np.int8)
+    n_pos = int(t.sum())
+    rows = np.zeros((G, N), dtype=np.uint8)
+    pos, neg = np.flatnonzero(t == 1), np.flatnonzero(t == 0)
+    for g in range(G):
+        r1 = int(rng.integers(100, N - 100))
+        mean = r1 * n_pos / N
+        sd = (mean * (1 - r1 / N) * (1 - n_pos / N)) ** 0.5
+        a = int(np.clip(round(mean + rng.uniform(-3.5, 3.5) * sd), max(0, r1 - len(neg)), min(r1, n_pos)))
+        rows[g, rng.choice(pos, a, replace=False)] = 1
+        rows[g, rng.choice(neg, r1 - a, replace=False)] = 1
+    engine.set_genes(eng.pack_rows(rows), N)
+    engine.set_trait_vector(0, t)
+    counts, p, _ = engine.contingency_fisher(0)
+    ref_counts = O.contingency(rows, t)
+    assert np.array_equal(counts, ref_counts)
+    ref_p = O.fisher(ref_counts)
+    rel = np.abs(p - ref_p) / ref_p
+    assert rel.max() <= FISHER_RTOL, rel.max()
+    pick = np.argsort(np.abs(ref_p - 0.01))[:300]                   # around the switch: SciPy's own arithmetic
+    sp = O.fisher_scipy(ref_counts[pick])
+    assert np.max(np.abs(p[pick] - sp) / sp) <= FISHER_RTOL
+
+
+@pytest.mark.parametrize("shape", ["random", "balanced"])
+def test_maximum_tree_size(engine, shape):
+    """32 766 isolates, the limit include/scoary_b200.h states, for the two shapes with the longest programs
+    (a random-join tree compiles to ~16 400 ops, a balanced one to ~21 400 -- both beyond the 12 288
+    ops round 1 could hold).  Pair counts and permutation hit counts against the oracle."""
+    N, G, P = 32766, 12, 5
+    bits, traits = _dataset(G, N, 27182)
+    names = synth.isolate_names(N)
+    col = {n: j for j, n in enumerate(names)}
+    nested = synth.make_tree(N, 99) if shape == "random" else _balanced(names)
+    m = synth.unpack_rows(bits, N)
+    engine.set_genes(bits, N)
+    engine.set_trait_vector(0, traits[0])
+    order = engine.set_tree_nested(0, nested, col)
+    left, right, _ = O.flatten_tree(nested)
+    cols = np.asarray([col[n] for n in order])
+    ref = O.permute(left, right, m[:, cols], traits[0][cols].astype(np.uint8), P=P, seed=4, trait=0)
+    pairs, r, nd = engine.permute(0, P, seed=4)
+    assert np.array_equal(pairs, ref["pairs"]) and np.array_equal(r, ref["r"]) and np.all(nd == P)
+    from scoary_b200.engine import EngineError
+    with pytest.raises(EngineError):                               # one leaf more is refused by sb_set_tree itself
+        big = synth.isolate_names(N + 1)
+        engine.set_genes(np.zeros((2, eng.words_for(N + 1)), dtype=np.uint64), N + 1)
+        engine.set_trait_vector(0, np.zeros(N + 1, dtype=np.int8))
+        engine.set_tree_nested(0, _comb(big), {n: j for j, n in enumerate(big)})
