@@ -1,25 +1,26 @@
 #!/usr/bin/env python
 """bench.py -- gene-trait tests/sec (incl. permutations) of the hot path on B200.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload north_star|c3|c4|c5|c2] [--impl reference]
 
-A "step" is one pass of the whole hot path over one batch of synthetic input
-(SURVEY.md 8(d)): contingency + Fisher for every gene, the unpermuted
-pairwise-comparison walk and P label permutations for every gene
-(-p 1.0, exhaustive mode: no early stop), then -- for N > 1 -- one NCCL
-all-gather of the per-gene records.  tests = G_tested * T * (1 + P).
+A "step" is one pass of the whole hot path over one batch of synthetic input: contingency + Fisher
+for every (gene, trait) -- every gene row read once for all traits --, the unpermuted pairwise-comparison walk and P
+label permutations for every gene (-p 1.0, exhaustive mode: no early stop), then -- for N > 1 -- the one NCCL
+all-gather of the per-gene records (scoary_b200.distributed).  tests = G_tested * T * (1 + P).
 
-  value : whole-job tests/s with inputs resident in HBM when the clock starts
-  e2e   : the same through the host-buffer C-ABI calls (pinned host bitsets in,
-          host result arrays out; H2D/D2H inside the timed region)
-  roofline / roofline_int32 : the dominant kernel (K5, permutation walks)
-  cpu_baseline : the oracle's C port on this box's host cores, bounded sample
+The job is FIXED and N GPUs split its genes into contiguous shards ("scaling": "strong"): the default workload is
+BASELINE.json's north_star target, 50 000 genes x 5 000 isolates x 10 000 permutations, at 1 / 2 / 4 / 8 GPUs;
+--workload c3 / c4 / c5 are configs[2..4] (c4 and c5 are the 8-GPU configurations; they also fit one GPU).
 
-Default workload = BASELINE.json configs[2] ("c3": 50k genes x 5k isolates x 1
-trait, 1000 permutations + pairwise), the largest single-GPU configuration the
-metric "tests/sec incl. permutations" is quoted on; configs[1] (Fisher only,
-no permutations) is reported alongside as `fisher_pass`.  Under torchrun each
-rank owns its own 50k-gene shard (weak scaling).
+  value : whole-job tests/s with inputs resident in HBM when the clock starts (CUDA events, max over ranks)
+  e2e   : the same through the host-buffer C-ABI calls (pinned host bitsets in, host result arrays out, H2D/D2H
+          inside the timed region), the product's gather and rank 0's adjusted p-values + sort; all --steps steps
+  roofline : the dominant kernel (K5, permutation walks): the HBM fraction the contract asks for (meaningless for a
+          kernel that needs 0.07 bytes per test) and `issue`, its real utilisation (executed warp instructions from
+          ncu / issue slots); contract_int32 is the SURVEY 8(d) op-count ratio, labelled as not a bound
+  fisher_pass, config1_fisher_only, config2_c3, reference_rule_mode : the other kernels / configs, one GPU only
+  cpu_baseline : the oracle's C port on this box's host cores, bounded sample (+ the Python reference's own timing,
+          measured in the build container: it cannot travel to the GPU box)
 """
 import argparse
 import json
@@ -44,8 +45,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c3", choices=["c2", "c3", "c4", "c5", "north_star"])
-    ap.add_argument("--genes", type=int, default=0, help="override genes per GPU")
+    ap.add_argument("--workload", default="north_star", choices=["c2", "c3", "c4", "c5", "north_star"])
+    ap.add_argument("--genes", type=int, default=0, help="override the job's gene count")
     ap.add_argument("--isolates", type=int, default=0)
     ap.add_argument("--perms", type=int, default=-1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -54,9 +55,7 @@ def parse_args():
 
 def workload(a):
     from scoary_b200 import synth
-    G, N, T, P, seed = synth.CONFIGS[a.workload]
-    if a.workload in ("c4", "c5"):
-        G = G // 8                      # per-GPU shard of the 8-GPU configurations
+    G, N, T, P, seed = synth.CONFIGS[a.workload]       # the whole job; N GPUs split its genes (strong scaling)
     if a.genes:
         G = a.genes
     if a.isolates:
@@ -64,6 +63,11 @@ def workload(a):
     if a.perms >= 0:
         P = a.perms
     return G, N, T, P, seed
+
+
+def workload_string(name, G, N, T, P):
+    """config.workload -- the same text in both arms"""
+    return "%s: %d genes x %d isolates x %d trait(s), %d permutations + pairwise, -p 1.0 exhaustive" % (name, G, N, T, P)
 
 
 class ClockSampler:
@@ -211,12 +215,12 @@ def run_reference(a):
     line = {
         "impl": "reference", "metric": "gene-trait tests/sec (incl. permutations)", "value": value, "unit": "tests/s",
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
-        "config": {"workload": "%s: %d genes x %d isolates x %d trait(s), %d permutations + pairwise" %
-                               (a.workload, G, N, T, P)},
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
+        "config": {"workload": workload_string(a.workload, G, N, T, P)},
         "cpu_baseline": {"value": value, "unit": "tests/s", "cores": threads, "kind": "port", "sample": sample,
-                         "note": "C restatement of scoary/methods.py + classes.py (oracle/scoary_oracle.c, OpenMP); "
-                                 "the Python reference itself measured 7 walks/s/core at N=5000 (BASELINE.md)"},
+                         "note": "C restatement of scoary/methods.py + classes.py (oracle/scoary_oracle.c, -O3, OpenMP); "
+                                 "the Python reference itself: python_reference",
+                         "python_reference": _profile_json("python_reference_timing.json") or None},
         "e2e": {"value": value, "unit": "tests/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -224,10 +228,22 @@ def run_reference(a):
 
 
 # ----------------------------------------------------------------------------- GPU arm
+def rank0_epilogue(e, p, counts, device_min=100000):
+    """What rank 0 does with the gathered vector before results can be written: skip rule, Bonferroni,
+    Benjamini-Hochberg, p-sort (methods.py:804-814, :900-925, :1448-1454) -- the product's own code path
+    (scoary_b200.methods.adjust_pvalues: device epilogue for large vectors, NumPy below)."""
+    from scoary_b200 import methods as M
+    keep = ((counts[:, 0] + counts[:, 1]) > 0) & ((counts[:, 2] + counts[:, 3]) > 0)
+    order, bonf, bh = M.adjust_pvalues(e, p, keep, device_min=device_min)
+    return order, bonf, bh
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
+    from scoary_b200 import distributed as sbd
     from scoary_b200 import synth
+    from scoary_b200 import tree as treemod
     from scoary_b200.engine import Engine, words_for
 
     G, N, T, P, seed = workload(a)
@@ -245,16 +261,20 @@ def run_ours(a):
             os.environ.pop("NCCL_DEBUG")
         dist.init_process_group("nccl", device_id=dev)
 
-    # ---- synthetic inputs: every rank owns its own G-gene shard (weak scaling), same traits / tree
+    # ---- synthetic inputs: ONE fixed job (G genes), split into contiguous gene shards (strong scaling);
+    # traits and tree are replicated
+    bounds = sbd.shard_bounds(G, world)
+    lo, hi = bounds[rank]
+    g_loc = hi - lo
     traits = synth.make_traits(N, T, seed)
-    bits_np = synth.make_genes_packed(G, N, seed + 1000003 * rank, traits=traits if rank == 0 else None)
+    bits_np = synth.make_genes_rows(lo, hi, G, N, seed, traits=traits)
     W = words_for(N)
-    pinned = torch.empty((G, W), dtype=torch.int64, pin_memory=True)
-    pinned.numpy().view(np.uint64)[:] = bits_np
+    pinned = torch.empty((max(g_loc, 1), W), dtype=torch.int64, pin_memory=True)
+    pinned.numpy().view(np.uint64)[:g_loc] = bits_np
+    del bits_np
     nested = synth.make_tree(N, seed)
     names = synth.isolate_names(N)
     col = {n: j for j, n in enumerate(names)}
-    from scoary_b200 import tree as treemod
     left, right, leaf_names = treemod.flatten(nested)
     leaf_cols = np.asarray([col[n] for n in leaf_names], dtype=np.int32)
 
@@ -269,32 +289,34 @@ def run_ours(a):
 
     # ---- device-resident state for `value`
     d_bits = pinned.to(dev, non_blocking=False)
-    e.set_genes_device(d_bits.data_ptr(), G, N, W)
+    e.set_genes_device(d_bits.data_ptr(), g_loc, N, W)
     for t in range(T):
         e.set_trait_vector(t, traits[t])
         e.set_tree(t, left, right, leaf_cols)
-    d_counts = torch.empty((T, G, 4), dtype=torch.int32, device=dev)
-    d_p = torch.empty((T, G), dtype=torch.float64, device=dev)
-    d_pairs = torch.empty((T, G, 3), dtype=torch.int32, device=dev)
-    d_r = torch.zeros((T, G), dtype=torch.int32, device=dev)
-    d_nd = torch.zeros((T, G), dtype=torch.int32, device=dev)
-    rec_w = 4 + 2 + 3 + 2
-    d_rec = torch.empty((T, G, rec_w), dtype=torch.int32, device=dev)
-    d_all = torch.empty((world * T, G, rec_w), dtype=torch.int32, device=dev) if world > 1 else None
+    d_counts = torch.empty((T, g_loc, 4), dtype=torch.int32, device=dev)
+    d_p = torch.empty((T, g_loc), dtype=torch.float64, device=dev)
+    d_pairs = torch.zeros((T, g_loc, 3), dtype=torch.int32, device=dev)
+    d_r = torch.zeros((T, g_loc), dtype=torch.int32, device=dev)
+    d_nd = torch.zeros((T, g_loc), dtype=torch.int32, device=dev)
+    RW = sbd.RECORD_WORDS
+    d_rec = torch.empty((g_loc, T * RW), dtype=torch.int32, device=dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > 126 MB L2
+    full_rec = [None]
 
     def step_device():
-        for t in range(T):
-            e.contingency_fisher_device(t, d_counts[t].data_ptr(), d_p[t].data_ptr())
-            if P > 0:
-                e.permute_device(t, G, P, seed, d_pairs[t].data_ptr(), d_r[t].data_ptr(), d_nd[t].data_ptr())
-        if world > 1:   # one all-gather of the fixed-size per-gene records
-            d_rec[..., 0:4] = d_counts
-            d_rec[..., 4:6] = d_p.view(torch.int32).view(T, G, 2)
-            d_rec[..., 6:9] = d_pairs
-            d_rec[..., 9] = d_r
-            d_rec[..., 10] = d_nd
-            dist.all_gather_into_tensor(d_all, d_rec)
+        # every gene row is read ONCE for all T traits (sb_contingency_fisher_multi), then walks + permutations
+        e.contingency_fisher_multi_device(0, T, d_counts.data_ptr(), d_p.data_ptr())
+        if P > 0:
+            for t in range(T):
+                e.permute_device(t, g_loc, P, seed, d_pairs[t].data_ptr(), d_r[t].data_ptr(), d_nd[t].data_ptr())
+        if world > 1:   # the one collective of the path: an all-gather of fixed-size per-gene records (NCCL)
+            for t in range(T):
+                d_rec[:, t * RW + 0:t * RW + 4] = d_counts[t]
+                d_rec[:, t * RW + 4:t * RW + 6] = d_p[t].view(torch.int32).view(g_loc, 2)
+                d_rec[:, t * RW + 6:t * RW + 9] = d_pairs[t]
+                d_rec[:, t * RW + 9] = d_r[t]
+                d_rec[:, t * RW + 10] = d_nd[t]
+            full_rec[0] = sbd.all_gather_records(d_rec, G, bounds)
 
     def barrier():
         if world > 1:
@@ -340,10 +362,9 @@ def run_ours(a):
         tests_per_step = tests_per_step_rank
     value = tests_per_step * a.steps / (dev_ms * 1e-3)
 
-    # ---- e2e: host buffers through the C-ABI, copies inside the timed region
-    counts_h = np.empty((G, 4), dtype=np.int32)
-    bits_host = pinned.numpy().view(np.uint64)
-
+    # ---- e2e: the calls a user of the C-ABI makes, host buffers in and out (copies inside the timed region), the
+    # product's own gather (scoary_b200.distributed, NCCL) and rank 0's epilogue (adjusted p-values + sort)
+    bits_host = pinned.numpy().view(np.uint64)[:g_loc]
     e2e_trace = []
 
     def step_e2e():
@@ -351,24 +372,35 @@ def run_ours(a):
         t0 = time.perf_counter()
         e.set_genes(bits_host, N)
         h2d += bits_host.nbytes
-        t1 = time.perf_counter()
-        tf = tp = 0.0
         for t in range(T):
             e.set_trait_vector(t, traits[t])
             e.set_tree(t, left, right, leaf_cols)
             h2d += 2 * W * 8 + left.nbytes + right.nbytes + leaf_cols.nbytes
-            ta = time.perf_counter()
-            c, p, _ = e.contingency_fisher(t)
-            d2h += c.nbytes + p.nbytes
-            tb = time.perf_counter()
+        t1 = time.perf_counter()
+        c, p, _ = e.contingency_fisher_multi(0, T)
+        d2h += c.nbytes + p.nbytes
+        t2 = time.perf_counter()
+        rec = np.zeros((g_loc, T * RW), dtype=np.int32)
+        for t in range(T):
+            pairs = r = nd = 0
             if P > 0:
                 pairs, r, nd = e.permute(t, P, seed=seed)
                 d2h += pairs.nbytes + r.nbytes + nd.nbytes
-            tc = time.perf_counter()
-            tf += tb - ta
-            tp += tc - tb
-        e2e_trace.append({"set_genes_ms": (t1 - t0) * 1e3, "fisher_ms": tf * 1e3, "permute_ms": tp * 1e3,
-                          "total_ms": (time.perf_counter() - t0) * 1e3})
+            rec[:, t * RW:(t + 1) * RW] = sbd.pack_records(c[t], p[t], pairs, r, nd)
+        t3 = time.perf_counter()
+        if world > 1:
+            rec = sbd.gather_blocks(rec, G)
+        t4 = time.perf_counter()
+        checksum = 0.0
+        if rank == 0:
+            for t in range(T):
+                u = sbd.unpack_records(rec[:, t * RW:(t + 1) * RW])
+                order, bonf, bh = rank0_epilogue(e, u["p"], u["counts"])
+                checksum += float(bh[order[0]]) if len(order) else 0.0
+        t5 = time.perf_counter()
+        e2e_trace.append({"set_inputs_ms": (t1 - t0) * 1e3, "fisher_ms": (t2 - t1) * 1e3, "permute_ms": (t3 - t2) * 1e3,
+                          "gather_ms": (t4 - t3) * 1e3, "rank0_epilogue_ms": (t5 - t4) * 1e3,
+                          "total_ms": (t5 - t0) * 1e3})
         return h2d, d2h
 
     e.set_stream(0)
@@ -376,106 +408,68 @@ def run_ours(a):
     barrier()
     torch.cuda.synchronize()
     e0 = time.perf_counter()
-    n_e2e = max(1, min(a.steps, 3))
-    for _ in range(n_e2e):
+    for _ in range(a.steps):
         h2d_b, d2h_b = step_e2e()
     e.synchronize()
+    barrier()
     e2e_s = time.perf_counter() - e0
     if world > 1:
         tmax = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         e2e_s = float(tmax.item())
-    e2e_value = tests_per_step * n_e2e / e2e_s
+    e2e_value = tests_per_step * a.steps / e2e_s
 
-    # ---- reference-rule mode (second number): the reference's sequential early stop
-    # (methods.py:1360-1363) applied between growing slices of permutations
-    ref_rule = None
-    if P >= 32:
-        from scoary_b200.methods import early_stop_table
+    # ---- sub-measurements that explain the line: one GPU only (they would only repeat per rank)
+    ref_rule = fisher = c2 = c3 = None
+    if world == 1:
         e.set_stream(stream.cuda_stream)
-        e.set_genes_device(d_bits.data_ptr(), G, N, W)
+        e.set_genes_device(d_bits.data_ptr(), g_loc, N, W)
         for t in range(T):
             e.set_trait_vector(t, traits[t])
             e.set_tree(t, left, right, leaf_cols)
-        d_rmin = torch.from_numpy(early_stop_table(P)).to(dev)
-        def step_rule():
-            for t in range(T):
-                e.permute_device(t, G, P, seed, d_pairs[t].data_ptr(), d_r[t].data_ptr(), d_nd[t].data_ptr(),
-                                 early_stop=True, rmin_ptr=d_rmin.data_ptr())
-        step_rule()
-        torch.cuda.synchronize()
-        e.stats_reset()
-        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        r0.record()
-        step_rule()
-        r1.record()
-        torch.cuda.synchronize()
-        rule_ms = r0.elapsed_time(r1)
-        walks = e.stats()["tests_walks"]
-        nd = d_nd.cpu().numpy()
-        ref_rule = {"ms_per_step": rule_ms, "walks_executed": int(walks), "walks_exhaustive": int(G * T * (1 + P)),
-                    "genes_stopped_early": int((nd < P).sum()), "genes": int(G * T),
-                    "equivalent_tests_per_s": G * T * (1 + P) / (rule_ms * 1e-3),
-                    "note": "Permute's early stop on; pairwise walk + permutations only (no Fisher pass)"}
+        # reference-rule mode (second number): the reference's sequential early stop (methods.py:1360-1363)
+        if P >= 32:
+            from scoary_b200.methods import early_stop_table
+            d_rmin = torch.from_numpy(early_stop_table(P)).to(dev)
 
-    # ---- Fisher-only pass (BASELINE configs[1] shape of work), device resident
-    e.set_stream(stream.cuda_stream)
-    e.set_genes_device(d_bits.data_ptr(), G, N, W)
-    for t in range(T):
-        e.set_trait_vector(t, traits[t])
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e.contingency_fisher_device(0, d_counts[0].data_ptr(), d_p[0].data_ptr())
-    flush.zero_()
-    f0.record()
-    e.contingency_fisher_device(0, d_counts[0].data_ptr(), d_p[0].data_ptr())
-    f1.record()
-    torch.cuda.synchronize()
-    fisher_ms = f0.elapsed_time(f1)
-
-    # ---- BASELINE configs[1] itself (10k genes x 1k isolates, Fisher only, no tree): a second, small line
-    c2 = None
-    if rank == 0 and a.workload != "c2":
-        G2, N2, _, _, seed2 = synth.CONFIGS["c2"]
-        tr2 = synth.make_traits(N2, 1, seed2)
-        bits2 = synth.make_genes_packed(G2, N2, seed2, traits=tr2)
-        W2 = words_for(N2)
-        pin2 = torch.empty((G2, W2), dtype=torch.int64, pin_memory=True)
-        pin2.numpy().view(np.uint64)[:] = bits2
-        d_bits2 = pin2.to(dev)
-        e.set_stream(stream.cuda_stream)
-        e.set_genes_device(d_bits2.data_ptr(), G2, N2, W2)
-        e.set_trait_vector(0, tr2[0])
-        dc2 = torch.empty((G2, 4), dtype=torch.int32, device=dev)
-        dp2 = torch.empty(G2, dtype=torch.float64, device=dev)
-        for _ in range(3):
-            e.contingency_fisher_device(0, dc2.data_ptr(), dp2.data_ptr())
-        reps, tot = 20, 0.0
-        for _ in range(reps):
-            flush.zero_()
-            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            c0.record()
-            e.contingency_fisher_device(0, dc2.data_ptr(), dp2.data_ptr())
-            c1.record()
+            def step_rule():
+                for t in range(T):
+                    e.permute_device(t, g_loc, P, seed, d_pairs[t].data_ptr(), d_r[t].data_ptr(), d_nd[t].data_ptr(),
+                                     early_stop=True, rmin_ptr=d_rmin.data_ptr())
+            step_rule()
             torch.cuda.synchronize()
-            tot += c0.elapsed_time(c1)
-        ms2 = tot / reps
-        e.set_stream(0)
-        host2 = pin2.numpy().view(np.uint64)
-        e.set_genes(host2, N2); e.set_trait_vector(0, tr2[0]); e.contingency_fisher(0)
-        t0 = time.perf_counter()
-        for _ in range(reps):
-            e.set_genes(host2, N2)
-            e.set_trait_vector(0, tr2[0])
-            cc2, pp2, _ = e.contingency_fisher(0)
-        e2e2 = (time.perf_counter() - t0) / reps * 1e3
-        tested2 = int(((cc2[:, 0] + cc2[:, 1] > 0) & (cc2[:, 2] + cc2[:, 3] > 0)).sum())
-        bytes2 = G2 * (8 * W2 + 24)
-        c2 = {"workload": "c2: %d genes x %d isolates x 1 trait, Fisher only" % (G2, N2), "tests_per_step": tested2,
-              "value": tested2 / (ms2 * 1e-3), "unit": "tests/s", "ms_per_step": ms2,
-              "e2e": {"value": tested2 / (e2e2 * 1e-3), "ms_per_step": e2e2, "h2d_bytes_per_step": int(host2.nbytes + 16 * W2),
-                      "d2h_bytes_per_step": int(cc2.nbytes + pp2.nbytes)},
-              "roofline": {"bound": "hbm", "achieved": bytes2 / (ms2 * 1e-3) / 1e9, "unit": "GB/s",
-                           "note": "1.5 MB of input: launch-latency bound, not bandwidth bound"}}
+            e.stats_reset()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record()
+            step_rule()
+            r1.record()
+            torch.cuda.synchronize()
+            rule_ms = r0.elapsed_time(r1)
+            walks = e.stats()["tests_walks"]
+            nd = d_nd.cpu().numpy()
+            ref_rule = {"ms_per_step": rule_ms, "walks_executed": int(walks), "walks_exhaustive": int(g_loc * T * (1 + P)),
+                        "genes_stopped_early": int((nd < P).sum()), "genes": int(g_loc * T),
+                        "equivalent_tests_per_s": g_loc * T * (1 + P) / (rule_ms * 1e-3),
+                        "note": "Permute's early stop on; pairwise walk + permutations only (no Fisher pass)"}
+        # the Fisher pass alone (all T traits in one launch), device resident
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e.contingency_fisher_multi_device(0, T, d_counts.data_ptr(), d_p.data_ptr())
+        flush.zero_()
+        f0.record()
+        e.contingency_fisher_multi_device(0, T, d_counts.data_ptr(), d_p.data_ptr())
+        f1.record()
+        torch.cuda.synchronize()
+        fisher_ms = f0.elapsed_time(f1)
+        fisher_bytes = g_loc * (8 * W + 24 * T) + 16 * W * T      # each row once, 24 B out per (gene, trait)
+        peaks = _peaks()
+        fisher = {"kernel": "fisher_kernel (K2+K3), %d trait(s) per row read" % T, "ms": fisher_ms,
+                  "tests_per_s": g_loc * T / (fisher_ms * 1e-3), "bound": "hbm",
+                  "achieved": fisher_bytes / (fisher_ms * 1e-3) / 1e9, "peak": peaks[0], "unit": "GB/s",
+                  "frac": fisher_bytes / (fisher_ms * 1e-3) / 1e9 / peaks[0], "bytes_per_test": fisher_bytes / (g_loc * T)}
+        if a.workload != "c2":
+            c2 = small_fisher_line(e, torch, dev, stream, flush, synth, words_for)
+        if a.workload == "north_star":
+            c3 = c3_line(e, torch, dev, stream, flush, d_bits, g_loc, N, W, seed, d_counts, d_p, d_pairs, d_r, d_nd, g_tested)
 
     if rank != 0:
         if world > 1:
@@ -484,96 +478,76 @@ def run_ours(a):
         return
 
     # ---- roofline of the dominant kernel (K5)
-    peaks = {}
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
-            peaks = json.load(fh)
-    except Exception:
-        pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    hbm_peak, peak_src = _peaks()
     k5_launches = max(1, int(st["launches_permute"]))
     k5_ms = st["ms_permute"] / k5_launches                       # average launch duration (CUDA events, this run)
     launches_per_step = k5_launches / float(a.steps)
-    tests_per_launch = G * P / launches_per_step                 # (gene, labelling) walks one launch performs
-    n_leaves = N
+    tests_per_launch = g_loc * T * P / launches_per_step         # (gene, labelling) walks one launch performs
     bytes_per_test = (8 * W + 8) / float(1 + P) if P > 0 else 0  # compulsory HBM bytes per test
-    ops_per_test = (n_leaves - 1) * OPS_PER_NODE                 # int32 add/max ops per test
+    ops_per_test = (N - 1) * OPS_PER_NODE                        # int32 add/max ops per test
     alg_bytes = tests_per_launch * bytes_per_test
     alg_ops = tests_per_launch * ops_per_test
-    traffic = None
-    prof = os.path.join(ROOT, "profiles", "k5_dram_bytes.json")
-    if os.path.exists(prof):
-        try:
-            traffic = json.load(open(prof)).get(a.workload)
-        except Exception:
-            traffic = None
+    prof = _profile_json("k5_dram_bytes.json")
+    traffic = prof.get(a.workload) or prof.get("c3")
     roofline = {"kernel": "walk_permute_kernel (K5 permutation walks)", "bound": "hbm",
                 "achieved": alg_bytes / (k5_ms * 1e-3) / 1e9 if P > 0 else None, "peak": hbm_peak, "unit": "GB/s",
                 "frac": (alg_bytes / (k5_ms * 1e-3) / 1e9 / hbm_peak) if P > 0 else None, "traffic": traffic,
                 "peak_source": peak_src, "ms_per_launch": k5_ms, "launches_per_step": launches_per_step,
-                "note": "K5 is integer-issue bound by construction (%.2f algorithmic bytes per test): the meaningful "
-                        "bound is roofline_int32.  traffic = ncu dram bytes of ONE launch with caches flushed (the 32 MB "
-                        "walk-order gene matrix read once); within a step the %d launches find it in L2 (ncu "
-                        "lts hit rate 96 %%)" % (bytes_per_test, int(round(launches_per_step)))}
-    roofline_int = {"kernel": "walk_permute_kernel", "bound": "int32 add/max issue (DPX)",
-                    "achieved": alg_ops / (k5_ms * 1e-3) / 1e12 if P > 0 else None, "peak": int_peak / 1e12,
-                    "unit": "Top/s", "frac": (alg_ops / (k5_ms * 1e-3) / int_peak) if P > 0 else None,
-                    "peak_packed16": 2 * int_peak / 1e12,
-                    "frac_packed16": (alg_ops / (k5_ms * 1e-3) / (2 * int_peak)) if P > 0 else None,
-                    "ops_per_node": OPS_PER_NODE,
-                    "peak_source": "sb_int32_peak microbenchmark, this run: VIADDMNMX issue rate x (1 add + 1 max); "
-                                   "peak_packed16 = the .S16x2 forms the kernel uses below 128 leaves (2 genes per "
-                                   "instruction, same issue rate)",
-                    "note": "achieved counts the SURVEY 8(d) contract ops (76 per internal node); the kernel executes "
-                            "fewer (cheap leaf/cherry updates, two genes per instruction), so frac can exceed 1"}
-    # issue-slot view of the same kernel: warp instructions actually executed (ncu count, profiles/) per second
-    # against the SM's issue capacity (4 warp instructions per clock per SM) at the clock sampled above
-    try:
-        wi_file = json.load(open(os.path.join(ROOT, "profiles", "k5_warp_instructions.json")))
-        wi, wi_src = wi_file.get(a.workload), wi_file.get("source", "ncu")
-    except Exception:
-        wi = wi_src = None
+                "note": "K5 is integer-issue bound by construction (%.2f algorithmic bytes per test): this HBM fraction "
+                        "says nothing about it, `issue` below is the utilisation figure.  traffic = dram read + write "
+                        "bytes of one launch inside a running step (ncu --cache-control none, %s): the label vectors, "
+                        "the hit flags and what L2 evicts of the %d MB walk-order gene matrix and the threads' 32-bit "
+                        "DP stacks" % (bytes_per_test, prof.get("source", "profiles/"), int(g_loc * W * 8 / 1e6))}
+    # the utilisation figure of K5: warp instructions it executes (ncu smsp__inst_executed.sum, profiles/) per second
+    # against the SM's issue capacity (4 warp instructions per clock per SM) at the clock sampled in this run
+    wi_file = _profile_json("k5_warp_instructions.json")
+    key = a.workload if a.workload in wi_file else ("c3" if N == 5000 else None)
+    wi = wi_file.get(key) if key else None
+    issue = None
     if wi and P > 0 and clocks and clocks.get("sm_mhz"):
         issued = tests_per_launch / 64.0 * wi / (k5_ms * 1e-3)
         cap = 4.0 * st["sm_count"] * clocks["sm_mhz"] * 1e6
-        roofline_int["issue"] = {"warp_instr_per_s": issued, "peak": cap, "frac": issued / cap,
-                                 "warp_instr_per_64_walks": wi,
-                                 "source": "instruction count from profiles/k5_warp_instructions.json (%s); time and "
-                                           "clock from this run" % wi_src}
-        alu = (wi_file.get("by_pipe_c3") or {}).get("alu_class")
-        if alu:      # ALU-class instructions (DPX, LOP3, SHF, SEL ...) issue at 2 per clock per SM: the tighter pipe bound
-            roofline_int["issue"]["alu_class"] = {
-                "warp_instr_per_64_walks": alu, "peak_per_clock_per_sm": 2.0,
-                "frac": tests_per_launch / 64.0 * alu / (k5_ms * 1e-3) / (2.0 * st["sm_count"] * clocks["sm_mhz"] * 1e6),
-                "note": "upper estimate: assumes the DPX forms share the ALU pipe (ncu pipe_alu read 59.9 % where this "
-                        "count gave 77 % on the profiled kernel)"}
-    fisher_bytes = G * (8 * W + 24)
-    fisher = {"kernel": "fisher_kernel (K2+K3)", "ms": fisher_ms, "tests_per_s": G / (fisher_ms * 1e-3),
-              "bound": "hbm", "achieved": fisher_bytes / (fisher_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-              "frac": fisher_bytes / (fisher_ms * 1e-3) / 1e9 / hbm_peak}
+        issue = {"bound": "warp-instruction issue slots (4 per clock per SM)", "warp_instr_per_s": issued, "peak": cap,
+                 "frac": issued / cap, "warp_instr_per_64_walks": wi,
+                 "source": "%s; time and clock from this run" % wi_file.get("source", "ncu")}
+        alu = (wi_file.get("by_pipe_" + key) or {}).get("alu_pct_of_peak")
+        if alu:
+            issue["alu_pipe_pct_of_peak_ncu"] = alu
+    roofline["issue"] = issue
+    contract = {"what": "SURVEY 8(d) contract figure: (N - 1) x 76 int32 add/max ops per walk / the DPX rate measured by "
+                        "sb_int32_peak in this run.  NOT a bound for this kernel: it executes about 1/5.7 of those "
+                        "operations (one key pass, two genes per .S16x2 instruction, fused add-max, cheap leaf and cherry "
+                        "updates), so the ratio exceeds 1",
+                "contract_ops_per_s": alg_ops / (k5_ms * 1e-3) if P > 0 else None, "dpx_peak_ops_per_s": int_peak,
+                "ratio": (alg_ops / (k5_ms * 1e-3) / int_peak) if P > 0 else None, "ops_per_node": OPS_PER_NODE}
 
     cpu = None
     if not a.no_cpu_baseline and world == 1:      # rank 0 at N = 1 only
         run, rate, threads, sample = cpu_sample(G, N, T, P, seed, 6.0)
         x, y = run()
-        cpu = {"value": rate(x, y), "unit": "tests/s", "cores": threads, "kind": "port", "sample": sample}
+        cpu = {"value": rate(x, y), "unit": "tests/s", "cores": threads, "kind": "port", "sample": sample,
+               "python_reference": _profile_json("python_reference_timing.json") or None}
 
     line = {
         "metric": "gene-trait tests/sec (incl. permutations)", "value": value, "unit": "tests/s", "n_gpus": world,
         "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": dev_ms / a.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "int32 (walk DP) + f64 (Fisher)", "data": "synthetic",
-        "config": {"workload": "%s: %d genes/GPU x %d isolates x %d trait(s), %d permutations + pairwise, -p 1.0 "
-                               "exhaustive" % (a.workload, G, N, T, P),
-                   "parallelism": "gene-sharded x%d, one all-gather" % world if world > 1 else "single GPU",
-                   "l2": "256 MiB buffer written between timed steps (inputs ~65 MB < 126 MB L2)",
+        "scaling": "strong", "vs_baseline": None, "dtype": "int32 (walk DP) + f64 (Fisher)", "data": "synthetic",
+        "config": {"workload": workload_string(a.workload, G, N, T, P),
+                   "parallelism": ("the job's %d genes in %d contiguous shards (%d per GPU), traits and tree replicated, "
+                                   "one NCCL all-gather of %d-byte per-gene records (scoary_b200.distributed)"
+                                   % (G, world, bounds[0][1] - bounds[0][0], 4 * RW * T)) if world > 1 else "single GPU",
+                   "l2": "256 MiB buffer written between timed steps (inputs %d MB < 126 MB L2)" % (2 * g_loc * W * 8 // 1000000),
+                   "value_includes": "Fisher pass, pairwise walk, label shuffles, permutation walks, hit bookkeeping%s; the "
+                                     "gene matrix is already in walk order (K1 pack + host tree compile run once, in warm-up; "
+                                     "e2e repeats them every step)" % (", all-gather" if world > 1 else ""),
                    "tests_per_step": tests_per_step, "seed": seed},
         "e2e": {"value": e2e_value, "unit": "tests/s", "h2d_bytes_per_step": int(h2d_b), "d2h_bytes_per_step": int(d2h_b),
-                "ms_per_step": e2e_s / n_e2e * 1e3, "calls_ms": e2e_trace[-1]},
+                "ms_per_step": e2e_s / a.steps * 1e3, "steps": a.steps, "calls_ms": e2e_trace[-1],
+                "includes": "host bitsets in, host result arrays out, the gather and rank 0's adjusted p-values + sort"},
         "gpu_launches": int(st["kernel_launches"]),
         "clocks": clocks,
-        "roofline": roofline, "roofline_int32": roofline_int, "fisher_pass": fisher, "reference_rule_mode": ref_rule,
-        "config1_fisher_only": c2,
+        "roofline": roofline, "contract_int32": contract, "fisher_pass": fisher, "reference_rule_mode": ref_rule,
+        "config1_fisher_only": c2, "config2_c3": c3,
         "cpu_baseline": cpu,
         "kernel_ms": {k: st[k] for k in ("ms_fisher", "ms_shuffle", "ms_walk", "ms_permute", "ms_reduce")},
         "wall_s_timed_region": wall,
@@ -582,6 +556,98 @@ def run_ours(a):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def _profile_json(name):
+    try:
+        with open(os.path.join(ROOT, "profiles", name)) as fh:
+            return json.load(fh)
+    except Exception:
+        return {}
+
+
+def _peaks():
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            peaks = json.load(fh)
+    except Exception:
+        pass
+    return (float(peaks.get("hbm_gbs", 6650.0)),
+            "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)")
+
+
+def small_fisher_line(e, torch, dev, stream, flush, synth, words_for):
+    """BASELINE configs[1] itself (10k genes x 1k isolates, Fisher only, no tree): a second, small line."""
+    G2, N2, _, _, seed2 = synth.CONFIGS["c2"]
+    tr2 = synth.make_traits(N2, 1, seed2)
+    bits2 = synth.make_genes_packed(G2, N2, seed2, traits=tr2)
+    W2 = words_for(N2)
+    pin2 = torch.empty((G2, W2), dtype=torch.int64, pin_memory=True)
+    pin2.numpy().view(np.uint64)[:] = bits2
+    d_bits2 = pin2.to(dev)
+    e.set_stream(stream.cuda_stream)
+    e.set_genes_device(d_bits2.data_ptr(), G2, N2, W2)
+    e.set_trait_vector(0, tr2[0])
+    dc2 = torch.empty((G2, 4), dtype=torch.int32, device=dev)
+    dp2 = torch.empty(G2, dtype=torch.float64, device=dev)
+    for _ in range(3):
+        e.contingency_fisher_device(0, dc2.data_ptr(), dp2.data_ptr())
+    reps, tot = 20, 0.0
+    for _ in range(reps):
+        flush.zero_()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        e.contingency_fisher_device(0, dc2.data_ptr(), dp2.data_ptr())
+        c1.record()
+        torch.cuda.synchronize()
+        tot += c0.elapsed_time(c1)
+    ms2 = tot / reps
+    e.set_stream(0)
+    host2 = pin2.numpy().view(np.uint64)
+    e.set_genes(host2, N2)
+    e.set_trait_vector(0, tr2[0])
+    e.contingency_fisher(0)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        e.set_genes(host2, N2)
+        e.set_trait_vector(0, tr2[0])
+        cc2, pp2, _ = e.contingency_fisher(0)
+    e2e2 = (time.perf_counter() - t0) / reps * 1e3
+    tested2 = int(((cc2[:, 0] + cc2[:, 1] > 0) & (cc2[:, 2] + cc2[:, 3] > 0)).sum())
+    bytes2 = G2 * (8 * W2 + 24)
+    hbm_peak, _ = _peaks()
+    return {"workload": "c2: %d genes x %d isolates x 1 trait, Fisher only" % (G2, N2), "tests_per_step": tested2,
+            "value": tested2 / (ms2 * 1e-3), "unit": "tests/s", "ms_per_step": ms2,
+            "e2e": {"value": tested2 / (e2e2 * 1e-3), "ms_per_step": e2e2, "h2d_bytes_per_step": int(host2.nbytes + 16 * W2),
+                    "d2h_bytes_per_step": int(cc2.nbytes + pp2.nbytes)},
+            "roofline": {"bound": "hbm", "achieved": bytes2 / (ms2 * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": bytes2 / (ms2 * 1e-3) / 1e9 / hbm_peak,
+                         "note": "1.5 MB of input, one wave of one batch per warp: launch + FP64 latency, not bandwidth"}}
+
+
+def c3_line(e, torch, dev, stream, flush, d_bits, G, N, W, seed, d_counts, d_p, d_pairs, d_r, d_nd, g_tested):
+    """BASELINE configs[2] (the round-1 headline): the same matrix with 1 000 permutations, three timed steps."""
+    P3 = 1000
+    e.set_stream(stream.cuda_stream)
+
+    def step():
+        e.contingency_fisher_multi_device(0, 1, d_counts.data_ptr(), d_p.data_ptr())
+        e.permute_device(0, G, P3, seed, d_pairs[0].data_ptr(), d_r[0].data_ptr(), d_nd[0].data_ptr())
+    step()
+    torch.cuda.synchronize()
+    tot = 0.0
+    for _ in range(3):
+        flush.zero_()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        step()
+        c1.record()
+        torch.cuda.synchronize()
+        tot += c0.elapsed_time(c1)
+    ms = tot / 3
+    return {"workload": workload_string("c3", G, N, 1, P3), "ms_per_step": ms, "value": g_tested * (1 + P3) / (ms * 1e-3),
+            "unit": "tests/s", "steps": 3}
 
 
 _REAL_STDOUT = None

@@ -185,6 +185,27 @@ int sb_debug_shuffled_labels(sb_ctx *ctx, int32_t t, int32_t P, uint64_t seed, u
  * cluster[i] = [cluster[i], cluster[j]].  The merge order is identical to the reference's. */
 int sb_upgma(sb_ctx *ctx, int32_t *merges);
 
+/* ---- epilogue on the device ---- */
+/* What Setup_results does with the p-values of one trait after the gene loop (methods.py:900-925) and the sort
+ * every later step relies on (SortResultsAndSetKey, methods.py:1448-1454), for the 1M-row scale:
+ *   keep   uint8[n]   1 = the gene was tested (skip rule methods.py:804-814 applied by the caller); the _device
+ *                     variant derives it from counts int32[n][4] (tpgp+tngp > 0 and tpgn+tngn > 0)
+ *   n_tests           the reference's number_of_tests; <= 0: the number of tested genes
+ *   order  int32[n]   first *n_tested entries: tested genes by ascending p, ties in gene order (stable, as sorted())
+ *   bonferroni, bh    double[n] by gene: min(p m, 1) and the Benjamini-Hochberg step-up value with the reference's
+ *                     tie rule (a gene tied with its less significant neighbour inherits that neighbour's value,
+ *                     methods.py:908-919), min(., 1); NaN for untested genes.  Same operations in the same order as
+ *                     the reference (one multiplication, one division): bit-identical to it.
+ * Any output may be NULL. */
+int sb_adjust_pvalues(sb_ctx *ctx, const double *p, const uint8_t *keep, int64_t n, int64_t n_tests,
+                      int32_t *order, double *bonferroni, double *bh, int64_t *n_tested);
+int sb_adjust_pvalues_device(sb_ctx *ctx, const double *d_p, const int32_t *d_counts, int64_t n,
+                             int64_t n_tests, int32_t *d_order, double *d_bonferroni, double *d_bh,
+                             int64_t *n_tested);
+/* ss.binom_test(k, n, 0.5) of PairWiseComparisons (methods.py:1267-1275; SciPy binomtest, two-sided) for `count`
+ * (k, n) pairs: p = 1 if 2k == n, else min(1, 2 P[X <= min(k, n-k)]); NaN where n == 0.  <= 1e-13 relative. */
+int sb_binom_two_sided(sb_ctx *ctx, const int32_t *k, const int32_t *n, int64_t count, double *p);
+
 /* ---- input packing (host code, no GPU needed) ---- */
 /* The per-cell loop of Csv_to_dic_Roary (methods.py:445-497) done natively on the raw bytes of
  * the gene presence/absence file.  Dialect: csv.reader(skipinitialspace=True, delimiter=d) as

@@ -69,6 +69,12 @@ SIGNATURES = {
                                          ctypes.c_void_p, ctypes.c_void_p]),
     "sb_debug_shuffled_labels": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_uint64, ctypes.c_void_p]),
     "sb_upgma": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "sb_adjust_pvalues": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
+                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64)]),
+    "sb_adjust_pvalues_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                                ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                ctypes.POINTER(ctypes.c_int64)]),
+    "sb_binom_two_sided": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
     "sb_csv_row_starts": (ctypes.c_int64, [ctypes.c_char_p, ctypes.c_int64, ctypes.c_char, ctypes.c_void_p, ctypes.c_int64,
                                            ctypes.c_void_p]),
     "sb_csv_pack_rows": (ctypes.c_int64, [ctypes.c_char_p, ctypes.c_int64, ctypes.c_char, ctypes.c_void_p, ctypes.c_int64,

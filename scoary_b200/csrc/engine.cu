@@ -23,6 +23,7 @@
 #include "fisher.cuh"
 #include "walk.cuh"
 #include "tree_build.cuh"
+#include "epilogue.cuh"
 
 extern "C" void sb_build_logfact_dd(int32_t n, double *hi_lo);
 
@@ -30,7 +31,7 @@ namespace {
 
 std::string g_create_error;
 
-enum Cat { CAT_PACK = 0, CAT_FISHER, CAT_SHUFFLE, CAT_WALK, CAT_PERMUTE, CAT_REDUCE, CAT_TREE, CAT_N };
+enum Cat { CAT_PACK = 0, CAT_FISHER, CAT_SHUFFLE, CAT_WALK, CAT_PERMUTE, CAT_REDUCE, CAT_TREE, CAT_EPILOGUE, CAT_N };
 
 struct TimedEvent {
     cudaEvent_t start, stop;
@@ -79,8 +80,8 @@ struct sb_ctx {
     int32_t lut_n = -1;
     TraitSlot traits[SB_MAX_TRAITS];
     // scratch
-    void *d_scratch[12] = {nullptr};
-    size_t scratch_bytes[12] = {0};
+    void *d_scratch[16] = {nullptr};
+    size_t scratch_bytes[16] = {0};
     int32_t *h_pinned_counter = nullptr;
     unsigned long long *d_walks = nullptr;   // walks of rounds whose slot count lives on the device
     int permute_mode = 0;                    // 0 auto, 1 threads = genes, 2 threads = labellings (sb_set_permute_mode)
@@ -164,6 +165,7 @@ void resolve_events(sb_ctx *ctx)
             case CAT_PERMUTE: ctx->stats.ms_permute += ms; ctx->stats.launches_permute += 1; break;
             case CAT_REDUCE: ctx->stats.ms_reduce += ms; break;
             case CAT_TREE: ctx->stats.ms_pack += ms; break;   // tree construction is accounted with packing
+            case CAT_EPILOGUE: ctx->stats.ms_epilogue += ms; break;
         }
         ctx->free_events.push_back(e);
     }
@@ -658,6 +660,29 @@ double fill_fraction(int64_t threads_domain, int64_t blocks_y, int slots)
     return lanes * std::min(1.0, blocks / (double)slots);
 }
 
+// Labellings per launch (n <= cap) and per block (ppi) for `tiles` thread tiles on `slots` resident blocks.  Every block
+// of a launch does the same work (same program, ppi labellings), so a launch runs in whole waves of `slots` blocks and
+// a partly filled last wave costs as much as a full one: pick the (n, ppi) with the lowest cost per labelling,
+//     (waves x ppi + launch overhead) / n,       waves = ceil(tiles x n / ppi / slots).
+// 6 250 genes (C3 split over 8 GPUs: 13 tiles) on 740 slots: 56 labellings x 1 per block = 728 blocks, one wave at 98 %,
+// where the largest launch the constant pool allows (91) would run 1.6 waves at 80 %.
+void plan_launch(int64_t tiles, int cap, int slots, int ppi_min, int ppi_max, int *ppi_out, int *n_out)
+{
+    double best = 1e300;
+    int best_ppi = ppi_min, best_n = std::max(1, cap);
+    for (int ppi = ppi_max; ppi >= ppi_min; ppi /= 2) {
+        for (int n = cap / ppi * ppi; n >= ppi; n -= ppi) {
+            const int64_t blocks = tiles * (n / ppi);
+            const int64_t waves = (blocks + slots - 1) / slots;
+            const double cost = ((double)waves * ppi + 0.02) / n * (1.0 + 0.004 * (ppi_max / ppi - 1));
+            if (cost < best) { best = cost; best_ppi = ppi; best_n = n; }
+        }
+        if (ppi == 1) break;
+    }
+    *ppi_out = best_ppi;
+    *n_out = best_n;
+}
+
 // Transposed launches (walk.cuh): threads = labellings, constant rows = the genes of result slots list[e] / e.
 // Walks labellings [perm_lo, perm_hi) for n_rows genes; hit bytes go to d_hits [slot][Ps].
 int launch_rows(sb_ctx *ctx, const TraitSlot &s, const uint32_t *d_labelsT, int64_t Ps, int perm_lo, int perm_hi,
@@ -764,9 +789,13 @@ int launch_permute(sb_ctx *ctx, int32_t t, const int64_t *d_gene_idx, int64_t S,
     rc = upload_program(ctx, s);
     if (rc) return rc;
 
-    const int slots = 7 * ctx->sm_count;                   // resident K5 blocks, roughly (5-6 per SM)
-    int label_cap = label_capacity(s);
-    if (label_cap >= sb::PERMS_PER_ITEM_MAX) label_cap = label_cap / sb::PERMS_PER_ITEM_MAX * sb::PERMS_PER_ITEM_MAX;
+    const size_t smem = walk_smem_bytes(s, false);
+    if (smem > (size_t)ctx->max_smem_optin) return fail(ctx, SB_ERR_ARG, "tree too deep for shared memory");
+    SB_CUDA(ctx, cudaFuncSetAttribute(sb::walk_permute_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    SB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sb::walk_permute_kernel<false>, sb::WALK_THREADS, smem));
+    const int slots = std::max(1, per_sm) * ctx->sm_count;      // resident K5 blocks
+    const int label_cap = label_capacity(s);
     // threads = genes (the default) or threads = labellings: whichever shape fills the GPU better
     bool transposed = false;
     if (sb::WALK_NLAB == 1 && !sb::WALK_PADDED && ctx->permute_mode != 1) {
@@ -779,21 +808,16 @@ int launch_permute(sb_ctx *ctx, int32_t t, const int64_t *d_gene_idx, int64_t S,
     if (transposed)
         return launch_permute_transposed(ctx, s, d_gene_idx, S, P, early_stop, d_rmin, d_unperm, d_labelsW, d_r, d_n_done);
 
-    // labellings per block: as many as 4 (fewer hit bytes), but few enough that one launch still
-    // has a couple of blocks for every resident slot when only few genes are walked
-    const int64_t tiles_all = (S + (int64_t)sb::WALK_THREADS * sb::WALK_NP - 1) / ((int64_t)sb::WALK_THREADS * sb::WALK_NP);
-    int ppi = sb::PERMS_PER_ITEM_MAX;
-    while (ppi > sb::WALK_NLAB && tiles_all * ((std::min(label_cap, P) + ppi - 1) / ppi) < 2LL * slots) ppi /= 2;
-    if (early_stop) ppi = sb::WALK_NLAB;   // later rounds walk few genes: the fewest labellings per block keep every SM busy
-    const int rows_max = (std::min(label_cap, P) + ppi - 1) / ppi;
-    rc = ensure_scratch(ctx, 1, (size_t)rows_max * (size_t)S);
+    // labellings per launch and per block, in whole waves of resident blocks (plan_launch).  Reference-rule mode
+    // plans every round for the genes still running, one labelling per block (its hit rows hold one flag each).
+    const int64_t per_block = (int64_t)sb::WALK_THREADS * sb::WALK_NP;
+    const int64_t tiles_all = (S + per_block - 1) / per_block;
+    int ppi = sb::WALK_NLAB, n_launch = std::min(label_cap, P);
+    if (!early_stop) plan_launch(tiles_all, std::min(label_cap, P), slots, sb::WALK_NLAB, sb::PERMS_PER_ITEM_MAX, &ppi, &n_launch);
+    rc = ensure_scratch(ctx, 1, (size_t)((std::min(label_cap, P) + ppi - 1) / ppi) * (size_t)S);
     if (rc) return rc;
     uint8_t *d_hits = (uint8_t *)ctx->d_scratch[1];
 
-    const size_t smem = walk_smem_bytes(s, false);
-    if (smem > (size_t)ctx->max_smem_optin) return fail(ctx, SB_ERR_ARG, "tree too deep for shared memory");
-    SB_CUDA(ctx, cudaFuncSetAttribute(sb::walk_permute_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t per_block = (int64_t)sb::WALK_THREADS * sb::WALK_NP;
     // one slice: labellings [base, base + n_perms) for the slots of d_list (n_bound of them at most; the exact
     // count is n_bound itself or, for rounds enqueued without a host round trip, *d_count), then the bookkeeping
     auto slice = [&](int base, int n_perms, const int32_t *d_list, int64_t n_bound, const int32_t *d_count,
@@ -829,8 +853,8 @@ int launch_permute(sb_ctx *ctx, int32_t t, const int64_t *d_gene_idx, int64_t S,
         return SB_OK;
     };
     if (!early_stop) {
-        for (int base = 0; base < P; base += label_cap) {
-            rc = slice(base, std::min(label_cap, P - base), nullptr, S, nullptr, nullptr, nullptr);
+        for (int base = 0; base < P; base += n_launch) {
+            rc = slice(base, std::min(n_launch, P - base), nullptr, S, nullptr, nullptr, nullptr);
             if (rc) return rc;
         }
         return SB_OK;
@@ -851,7 +875,8 @@ int launch_permute(sb_ctx *ctx, int32_t t, const int64_t *d_gene_idx, int64_t S,
     const int32_t *cur = nullptr, *cur_count = nullptr;   // null = identity list of S slots
     int base = 0, round = 0;
     while (base < P && n_bound > 0) {
-        int n_perms = round == 0 ? 31 : (round == 1 ? 33 : label_cap);
+        int n_perms = round == 0 ? 31 : 33, one = 1;
+        if (round >= 2) plan_launch((n_bound + per_block - 1) / per_block, label_cap, slots, 1, 1, &one, &n_perms);
         n_perms = std::min(std::min(n_perms, label_cap), P - base);
         int32_t *out = d_list[round & 1];
         rc = slice(base, n_perms, cur, n_bound, cur_count, out, d_counters + round);
@@ -868,6 +893,67 @@ int launch_permute(sb_ctx *ctx, int32_t t, const int64_t *d_gene_idx, int64_t S,
         base += n_perms;
         ++round;
     }
+    return SB_OK;
+}
+
+// ---- device epilogue (epilogue.cuh) -----------------------------------------------
+// d_p [n], d_counts [n][4] or d_keep [n] (one of them) -> d_order [n] (first *m entries: tested genes by ascending p,
+// stable), d_bonf [n], d_bh [n].  n_tests <= 0: the number of tested genes.  Synchronises once (the count).
+int launch_adjust(sb_ctx *ctx, const double *d_p, const int32_t *d_counts, const uint8_t *d_keep, int64_t n,
+                  int64_t n_tests, int32_t *d_order, double *d_bonf, double *d_bh, int64_t *m_out)
+{
+    if (n <= 0) { if (m_out) *m_out = 0; return SB_OK; }
+    if (n > 0x7fffffffLL) return fail(ctx, SB_ERR_ARG, "sb_adjust_pvalues: at most 2^31 - 1 rows");
+    const int n_chunks = (int)((n + sb::SORT_CHUNK - 1) / sb::SORT_CHUNK);
+    const int64_t n_blocks = (n + 1023) / 1024;
+    const size_t b_keys = sizeof(uint64_t) * (size_t)n, b_idx = sizeof(int32_t) * (size_t)n;
+    const size_t b_hist = sizeof(uint32_t) * (size_t)sb::RADIX * n_chunks;
+    auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+    int rc = ensure_scratch(ctx, 11, 2 * up(b_keys) + 2 * up(b_idx) + up(b_hist) + up(b_keys) + up(sizeof(double) * n_blocks) + 256);
+    if (rc) return rc;
+    char *base = (char *)ctx->d_scratch[11];
+    uint64_t *keys[2] = {(uint64_t *)base, (uint64_t *)(base + up(b_keys))};
+    base += 2 * up(b_keys);
+    int32_t *idx[2] = {(int32_t *)base, (int32_t *)(base + up(b_idx))};
+    base += 2 * up(b_idx);
+    uint32_t *hist = (uint32_t *)base;
+    base += up(b_hist);
+    double *vals = (double *)base;
+    base += up(b_keys);
+    double *block_min = (double *)base;
+    base += up(sizeof(double) * n_blocks);
+    unsigned long long *d_kept = (unsigned long long *)base;
+    Timed tm(ctx, CAT_EPILOGUE);
+    SB_CUDA(ctx, cudaMemsetAsync(d_kept, 0, sizeof(unsigned long long), ctx->stream));
+    const unsigned g256 = (unsigned)((n + 255) / 256);
+    sb::epi_keys_kernel<<<g256, 256, 0, ctx->stream>>>(d_p, d_counts, d_keep, n, keys[0], idx[0], d_kept);
+    const unsigned gsort = (unsigned)((n_chunks + sb::SORT_WARPS - 1) / sb::SORT_WARPS);
+    int cur = 0;
+    for (int shift = 0; shift < 64; shift += sb::RADIX_BITS) {
+        sb::radix_hist_kernel<<<gsort, 32 * sb::SORT_WARPS, 0, ctx->stream>>>(keys[cur], n, shift, n_chunks, hist);
+        sb::radix_scan_kernel<<<1, 1024, 0, ctx->stream>>>(hist, (int64_t)sb::RADIX * n_chunks);
+        sb::radix_scatter_kernel<<<gsort, 32 * sb::SORT_WARPS, 0, ctx->stream>>>(keys[cur], idx[cur], n, shift, n_chunks, hist,
+                                                                                keys[cur ^ 1], idx[cur ^ 1]);
+        cur ^= 1;
+    }
+    ctx->stats.kernel_launches += 1 + 3 * (64 / sb::RADIX_BITS);
+    SB_CUDA(ctx, cudaGetLastError());
+    unsigned long long kept = 0;
+    SB_CUDA(ctx, cudaMemcpyAsync(&kept, d_kept, sizeof kept, cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const int64_t m = (int64_t)kept;
+    const double tests = (double)(n_tests > 0 ? n_tests : m);
+    if (m > 0) {
+        const int64_t mb = (m + 1023) / 1024;
+        sb::bh_values_kernel<<<(unsigned)((m + 255) / 256), 256, 0, ctx->stream>>>(keys[cur], m, tests, vals);
+        sb::suffix_min_block_kernel<<<(unsigned)mb, 1024, 0, ctx->stream>>>(vals, m, block_min);
+        sb::suffix_min_top_kernel<<<1, 1024, 0, ctx->stream>>>(block_min, mb);
+        ctx->stats.kernel_launches += 3;
+    }
+    sb::bh_finish_kernel<<<g256, 256, 0, ctx->stream>>>(keys[cur], idx[cur], n, m, tests, vals, block_min, d_order, d_bonf, d_bh);
+    ctx->stats.kernel_launches += 1;
+    SB_CUDA(ctx, cudaGetLastError());
+    if (m_out) *m_out = m;
     return SB_OK;
 }
 
@@ -1276,6 +1362,70 @@ int sb_permute(sb_ctx *ctx, int32_t t, const int64_t *gene_idx, int64_t S, int32
     SB_CUDA(ctx, cudaMemcpyAsync(n_done, d_nd, sizeof(int32_t) * (size_t)S, cudaMemcpyDeviceToHost, ctx->stream));
     SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->stats.d2h_bytes += (int64_t)sizeof(int32_t) * S * (pairs ? 5 : 2);
+    return SB_OK;
+}
+
+int sb_adjust_pvalues_device(sb_ctx *ctx, const double *d_p, const int32_t *d_counts, int64_t n, int64_t n_tests,
+                             int32_t *d_order, double *d_bonferroni, double *d_bh, int64_t *n_tested)
+{
+    if (!ctx || !d_p || !d_counts) return SB_ERR_ARG;
+    SB_CUDA(ctx, cudaSetDevice(ctx->device));
+    return launch_adjust(ctx, d_p, d_counts, nullptr, n, n_tests, d_order, d_bonferroni, d_bh, n_tested);
+}
+
+int sb_adjust_pvalues(sb_ctx *ctx, const double *p, const uint8_t *keep, int64_t n, int64_t n_tests, int32_t *order,
+                      double *bonferroni, double *bh, int64_t *n_tested)
+{
+    if (!ctx || !p || !keep) return SB_ERR_ARG;
+    SB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n <= 0) { if (n_tested) *n_tested = 0; return SB_OK; }
+    const size_t N = (size_t)n;
+    auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+    int rc = ensure_scratch(ctx, 12, 3 * up(8 * N) + up(4 * N) + up(N));
+    if (rc) return rc;
+    char *base = (char *)ctx->d_scratch[12];
+    double *d_p = (double *)base, *d_bonf = (double *)(base + up(8 * N)), *d_bh = (double *)(base + 2 * up(8 * N));
+    int32_t *d_order = (int32_t *)(base + 3 * up(8 * N));
+    uint8_t *d_keep = (uint8_t *)(base + 3 * up(8 * N) + up(4 * N));
+    SB_CUDA(ctx, cudaMemcpyAsync(d_p, p, 8 * N, cudaMemcpyHostToDevice, ctx->stream));
+    SB_CUDA(ctx, cudaMemcpyAsync(d_keep, keep, N, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->stats.h2d_bytes += (int64_t)(9 * N);
+    rc = launch_adjust(ctx, d_p, nullptr, d_keep, n, n_tests, d_order, d_bonf, d_bh, n_tested);
+    if (rc) return rc;
+    if (order) SB_CUDA(ctx, cudaMemcpyAsync(order, d_order, 4 * N, cudaMemcpyDeviceToHost, ctx->stream));
+    if (bonferroni) SB_CUDA(ctx, cudaMemcpyAsync(bonferroni, d_bonf, 8 * N, cudaMemcpyDeviceToHost, ctx->stream));
+    if (bh) SB_CUDA(ctx, cudaMemcpyAsync(bh, d_bh, 8 * N, cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stats.d2h_bytes += (int64_t)((order ? 4 : 0) + (bonferroni ? 8 : 0) + (bh ? 8 : 0)) * n;
+    return SB_OK;
+}
+
+int sb_binom_two_sided(sb_ctx *ctx, const int32_t *k, const int32_t *n, int64_t count, double *p)
+{
+    if (!ctx || !k || !n || !p) return SB_ERR_ARG;
+    SB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (count <= 0) return SB_OK;
+    int32_t n_max = 0;
+    for (int64_t i = 0; i < count; ++i) n_max = std::max(n_max, n[i]);
+    int rc = ensure_lut(ctx, n_max);
+    if (rc) return rc;
+    const size_t C = (size_t)count;
+    rc = ensure_scratch(ctx, 13, 16 * C + 512);
+    if (rc) return rc;
+    int32_t *d_k = (int32_t *)ctx->d_scratch[13], *d_n = d_k + C;
+    double *d_out = (double *)((char *)ctx->d_scratch[13] + (8 * C + 255) / 256 * 256);
+    SB_CUDA(ctx, cudaMemcpyAsync(d_k, k, 4 * C, cudaMemcpyHostToDevice, ctx->stream));
+    SB_CUDA(ctx, cudaMemcpyAsync(d_n, n, 4 * C, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        Timed tm(ctx, CAT_EPILOGUE);
+        sb::binom_two_sided_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(d_k, d_n, 1, count, ctx->d_lut, d_out);
+        ctx->stats.kernel_launches += 1;
+        SB_CUDA(ctx, cudaGetLastError());
+    }
+    SB_CUDA(ctx, cudaMemcpyAsync(p, d_out, 8 * C, cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stats.h2d_bytes += (int64_t)(8 * C);
+    ctx->stats.d2h_bytes += (int64_t)(8 * C);
     return SB_OK;
 }
 

@@ -113,7 +113,7 @@ __device__ __forceinline__ unsigned sb_sign_mask2(unsigned x)
 // next leaf sits in bit 15 / bit 31 and its half-word mask is ONE PRMT (sign replication) instead of
 // LOP3 + IMAD; a consumed leaf is a left shift.  Same results; verified through the host emulation.
 #ifndef SB_WALK_PRMT
-#define SB_WALK_PRMT 0
+#define SB_WALK_PRMT 1
 #endif
 // Experimental (tools/sweep_variants.py, not measured yet): the host compiler pads the leaf stream so that no op
 // ever crosses a 16-leaf window (pad positions carry gene bit 0 and no label; long leaf runs are split at the

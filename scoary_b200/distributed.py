@@ -31,18 +31,19 @@ def unpack_records(rec):
 
 
 def all_gather_records(rec_tensor, n_total, bounds):
-    """rec_tensor: torch int32 [g_local][RECORD_WORDS] on this rank's device (or CPU for gloo).
+    """rec_tensor: torch int32 [g_local][RECORD_WORDS x traits] on this rank's device (or CPU for gloo).
     Shards may differ in size by one row, so every rank pads to the largest shard; one
     collective.  Returns a torch tensor [n_total][RECORD_WORDS] in gene order."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size()
     gmax = max(hi - lo for lo, hi in bounds)
-    pad = torch.zeros((gmax, RECORD_WORDS), dtype=torch.int32, device=rec_tensor.device)
+    width = rec_tensor.shape[1]                     # RECORD_WORDS per trait
+    pad = torch.zeros((gmax, width), dtype=torch.int32, device=rec_tensor.device)
     pad[: rec_tensor.shape[0]] = rec_tensor
-    flat = torch.empty((world * gmax, RECORD_WORDS), dtype=torch.int32, device=rec_tensor.device)
+    flat = torch.empty((world * gmax, width), dtype=torch.int32, device=rec_tensor.device)
     dist.all_gather_into_tensor(flat, pad)          # output = rank-major concatenation along dim 0
-    out = flat.view(world, gmax, RECORD_WORDS)
+    out = flat.view(world, gmax, width)
     parts = [out[r, : bounds[r][1] - bounds[r][0]] for r in range(world)]
     full = torch.cat(parts, dim=0)
     assert full.shape[0] == n_total

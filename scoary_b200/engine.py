@@ -161,6 +161,37 @@ class Engine:
         self._check(self._lib.sb_upgma(self._ctx, _ptr(merges)))
         return merges
 
+    # -- epilogue
+    def adjust_pvalues(self, p, keep, n_tests=0):
+        """Setup_results' Bonferroni / Benjamini-Hochberg columns and the p-sort (methods.py:900-925, :1448-1454):
+        -> (order int32 [m] tested genes by ascending p, bonferroni f64 [n], bh f64 [n])."""
+        p = np.ascontiguousarray(p, dtype=np.float64)
+        keep = np.ascontiguousarray(keep, dtype=np.uint8)
+        n = len(p)
+        order = np.empty(n, dtype=np.int32)
+        bonf = np.empty(n, dtype=np.float64)
+        bh = np.empty(n, dtype=np.float64)
+        m = ctypes.c_int64()
+        self._check(self._lib.sb_adjust_pvalues(self._ctx, _ptr(p), _ptr(keep), n, int(n_tests), _ptr(order), _ptr(bonf),
+                                                _ptr(bh), ctypes.byref(m)))
+        return order[:m.value], bonf, bh
+
+    def adjust_pvalues_device(self, p_ptr, counts_ptr, n, order_ptr, bonf_ptr, bh_ptr, n_tests=0):
+        m = ctypes.c_int64()
+        self._check(self._lib.sb_adjust_pvalues_device(self._ctx, ctypes.c_void_p(int(p_ptr)), ctypes.c_void_p(int(counts_ptr)),
+                                                       int(n), int(n_tests), ctypes.c_void_p(int(order_ptr) or None),
+                                                       ctypes.c_void_p(int(bonf_ptr) or None),
+                                                       ctypes.c_void_p(int(bh_ptr) or None), ctypes.byref(m)))
+        return m.value
+
+    def binom_two_sided(self, k, n):
+        """ss.binom_test(k, n, 0.5) for arrays (methods.py:1267-1275)."""
+        k = np.ascontiguousarray(k, dtype=np.int32).reshape(-1)
+        n = np.ascontiguousarray(n, dtype=np.int32).reshape(-1)
+        out = np.empty(len(k), dtype=np.float64)
+        self._check(self._lib.sb_binom_two_sided(self._ctx, _ptr(k), _ptr(n), len(k), _ptr(out)))
+        return out
+
     # -- hot path, host buffers
     def contingency_fisher(self, t, want_p=True, want_hash=False):
         G = self.G

@@ -451,6 +451,29 @@ def benjamini_hochberg(p_sorted, number_of_tests):
     return np.minimum.accumulate(vals[::-1])[::-1]
 
 
+DEVICE_EPILOGUE_MIN = 100_000      # rows from which the adjusted p-values and the p-sort run on the GPU
+
+
+def adjust_pvalues(e, p, keep, n_tests=0, device_min=None):
+    """Bonferroni, Benjamini-Hochberg and the p-sort of one trait (scoary/methods.py:900-925, :1448-1454) for the genes
+    flagged in `keep`: -> (order: tested genes by ascending p, ties in gene order; bonferroni [n]; bh [n]; NaN where
+    not tested).  Large vectors go through the device epilogue (sb_adjust_pvalues, csrc/epilogue.cuh), small ones
+    through NumPy; the two are the same operations in the same order and agree bit for bit (tests/test_gpu_parity.py)."""
+    p = np.asarray(p, dtype=np.float64)
+    keep = np.asarray(keep, dtype=bool)
+    device_min = DEVICE_EPILOGUE_MIN if device_min is None else device_min
+    if len(p) >= device_min and hasattr(e, "adjust_pvalues"):
+        return e.adjust_pvalues(p, keep, n_tests)
+    idx = np.flatnonzero(keep)
+    m = n_tests or len(idx)
+    order = idx[np.argsort(p[idx], kind="stable")]
+    bonf = np.full(len(p), np.nan)
+    bh = np.full(len(p), np.nan)
+    bonf[idx] = np.minimum(p[idx] * m, 1.0)
+    bh[order] = np.minimum(benjamini_hochberg(p[order], m), 1.0)
+    return order, bonf, bh
+
+
 def Setup_results(genedic, traitsdic, collapse):
     """Counting, Fisher's exact test and multiple-testing adjustment for every trait
     (scoary/methods.py:757-928); the counting and Fisher part runs on the GPU
@@ -509,15 +532,11 @@ def Setup_results(genedic, traitsdic, collapse):
         cols = [x[idx].tolist() for x in (tpgp, tngp, tpgn, tngn, sens, spes, odds, np.asarray(pvals, np.float64))]
         if not collapse:
             # every tested gene is its own row: the adjusted p-values are array operations (methods.py:900-925)
-            pv = np.asarray(cols[7], dtype=np.float64)
-            order = np.argsort(pv, kind="stable")
-            bh = np.empty(len(pv), dtype=np.float64)
-            bh[order] = np.minimum(benjamini_hochberg(pv[order], number_of_tests), 1.0)
+            _, bonf_all, bh_all = adjust_pvalues(e, pvals, keep, number_of_tests)
             log.info("Adding p-values adjusted for testing multiple hypotheses")
             nugn, annotation = table.nugn, table.annotation
-            for i, a, b, c, d, se, sp, od, p_v, b_p, bh_p in zip(idx.tolist(), *cols,
-                                                                 np.minimum(pv * number_of_tests, 1.0).tolist(),
-                                                                 bh.tolist()):
+            for i, a, b, c, d, se, sp, od, p_v, b_p, bh_p in zip(idx.tolist(), *cols, bonf_all[idx].tolist(),
+                                                                 bh_all[idx].tolist()):
                 gene = names[i]
                 res[gene] = {"NUGN": nugn[i], "Annotation": annotation[i], "tpgp": a, "tngp": b, "tpgn": c, "tngn": d,
                              "sens": se, "spes": sp, "OR": od, "p_v": p_v, "B_p": b_p, "BH_p": bh_p}
@@ -965,10 +984,21 @@ def main(**kwargs):
     if args.citation:
         sys.exit(CITATION)
     if args.test:
-        ex = "/root/reference/scoary/exampledata"
+        # --test (scoary/methods.py:69-92): the reference's example data.  This repository carries it as test fixtures
+        # (tests/golden/inputs, the gene table gzipped); it is unpacked next to the results.
+        ex = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "inputs")
+        packed = os.path.join(ex, "Gene_presence_absence.csv.gz")
+        if not os.path.isfile(packed):
+            sys.exit("--test needs the example data of the source checkout (tests/golden/inputs); not found at %s" % ex)
+        import gzip
+        import shutil
+        import tempfile
+        unpacked = os.path.join(tempfile.mkdtemp(prefix="scoary_b200_test_"), "Gene_presence_absence.csv")
+        with gzip.open(packed, "rb") as fi, open(unpacked, "wb") as fo:
+            shutil.copyfileobj(fi, fo)
         args.correction, cutoffs = ["I", "EPW"], {"I": 0.05, "EPW": 0.05}
         args.delimiter, args.grabcols, args.max_hits, args.newicktree = ",", [], None, None
-        args.genes, args.traits = os.path.join(ex, "Gene_presence_absence.csv"), os.path.join(ex, "Tetracycline_resistance.csv")
+        args.genes, args.traits = unpacked, os.path.join(ex, "Tetracycline_resistance.csv")
         args.no_pairwise, args.outdir, args.permute, args.p_value_cutoff = False, "./", 0, [0.05, 0.05]
         args.restrict_to, args.start_col, args.upgma_tree, args.write_reduced = None, 15, True, False
         args.no_time, args.collapse = False, False
@@ -1093,9 +1123,26 @@ def main(**kwargs):
     except SystemExit:
         log.exception("CRITICAL:")
         _close_run(fileh, console, scratch, ok=False)
+        _abort_peers()
+        raise
+    except Exception:
+        # an engine / CUDA error on ONE rank of an N > 1 run would leave the others waiting in their next
+        # collective for ever: log it, close the files and take the whole job down
+        log.exception("CRITICAL:")
+        _close_run(fileh, console, scratch, ok=False)
+        _abort_peers()
         raise
     _close_run(fileh, console, scratch, ok=True)
     sys.exit(0)
+
+
+def _abort_peers():
+    """N > 1 only: a rank that fails leaves the process group the hard way, so that torchrun tears the other
+    ranks down instead of letting them block in a collective (exit status 1)."""
+    if dist.world_rank()[0] > 1:
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(1)
 
 
 if __name__ == "__main__":

@@ -38,22 +38,40 @@ def make_traits(n_isolates, n_traits, seed, missing_frac=0.0):
     return t
 
 
+def _gene_chunk(lo, hi, n_isolates, seed, traits, planted, gene_offset):
+    """uint8 [hi - lo][N]: rows lo .. hi - 1 of a shard; the random stream belongs to the chunk (seed, gene_offset + lo)."""
+    rng = np.random.default_rng([seed, 0x6E6E, gene_offset + lo])
+    f = rng.uniform(0.02, 0.98, size=(hi - lo, 1)).astype(np.float32)
+    m = (rng.random((hi - lo, n_isolates), dtype=np.float32) < f).astype(np.uint8)
+    if traits is not None and gene_offset == 0:
+        for k in range(traits.shape[0]):
+            for r in range(k * planted, (k + 1) * planted):
+                if lo <= r < hi:
+                    flip = (rng.random(n_isolates) < 0.1)
+                    m[r - lo] = ((traits[k] == 1) ^ flip).astype(np.uint8)
+    return m
+
+
 def make_genes_packed(n_genes, n_isolates, seed, traits=None, planted=10, chunk=4096, gene_offset=0):
     """uint64 [G][W] bitset rows; rows [k*planted, (k+1)*planted) of shard 0 are planted for trait k."""
     W = eng.words_for(n_isolates)
     out = np.empty((n_genes, W), dtype=np.uint64)
     for lo in range(0, n_genes, chunk):
         hi = min(n_genes, lo + chunk)
-        rng = np.random.default_rng([seed, 0x6E6E, gene_offset + lo])
-        f = rng.uniform(0.02, 0.98, size=(hi - lo, 1)).astype(np.float32)
-        m = (rng.random((hi - lo, n_isolates), dtype=np.float32) < f).astype(np.uint8)
-        if traits is not None and gene_offset == 0:
-            for k in range(traits.shape[0]):
-                for r in range(k * planted, (k + 1) * planted):
-                    if lo <= r < hi:
-                        flip = (rng.random(n_isolates) < 0.1)
-                        m[r - lo] = ((traits[k] == 1) ^ flip).astype(np.uint8)
-        out[lo:hi] = eng.pack_rows(m)
+        out[lo:hi] = eng.pack_rows(_gene_chunk(lo, hi, n_isolates, seed, traits, planted, gene_offset))
+    return out
+
+
+def make_genes_rows(lo, hi, n_genes, n_isolates, seed, traits=None, planted=10, chunk=4096):
+    """Rows lo .. hi - 1 of make_genes_packed(n_genes, ...): one GPU's shard of a FIXED job (strong scaling), generated
+    without the rest of the matrix (whole chunks are drawn, the shard is cut out of them)."""
+    W = eng.words_for(n_isolates)
+    out = np.empty((hi - lo, W), dtype=np.uint64)
+    for c_lo in range(lo // chunk * chunk, hi, chunk):
+        c_hi = min(n_genes, c_lo + chunk)
+        rows = eng.pack_rows(_gene_chunk(c_lo, c_hi, n_isolates, seed, traits, planted, 0))
+        a, b = max(lo, c_lo), min(hi, c_hi)
+        out[a - lo:b - lo] = rows[a - c_lo:b - c_lo]
     return out
 
 
