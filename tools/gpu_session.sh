@@ -27,12 +27,12 @@ step() {   # step <seconds> <log> <command...>
 step 900 pytest_gpu.log python -m pytest tests -m gpu -x -q
 step 1200 sweep.log python tools/sweep_variants.py run
 step 300 launches.log ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
-    --log-file "$out/launches.csv" python bench.py --steps 2 --warmup 3 --no-cpu-baseline
+    --log-file "$out/launches.csv" python bench.py --workload c3 --steps 2 --warmup 3 --no-cpu-baseline
 # the same command without ncu's cache flush between kernels: DRAM bytes and executed instructions of every launch as
 # they are inside a running step (the --set full capture below is cold-cache: its dram bytes re-read the gene matrix)
 step 300 step_dram.log ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum,gpu__time_duration.sum \
     --cache-control none --clock-control none -c 400 --csv \
-    --log-file "$out/step_dram.csv" python bench.py --steps 2 --warmup 3 --no-cpu-baseline
+    --log-file "$out/step_dram.csv" python bench.py --workload c3 --steps 2 --warmup 3 --no-cpu-baseline
 step 420 ncu_walk.log ncu --set full --clock-control none --import-source on -k regex:walk_permute -c 1 \
     -o "$out/prof_walk" -f python tools/probe.py --perms 60
 step 300 ncu_fisher.log ncu --set full --clock-control none --import-source on -k regex:fisher_kernel -c 1 \
@@ -43,6 +43,6 @@ for rep in "$out"/prof_walk.ncu-rep "$out"/prof_fisher.ncu-rep; do
     [ -f "$rep" ] && ncu -i "$rep" --page source --csv --print-source sass > "${rep%.ncu-rep}.source.csv" 2>/dev/null
 done
 step 600 bench.log python bench.py
-step 300 bench_north_star.log python bench.py --workload north_star --steps 2 --no-cpu-baseline
-grep -h '^{' "$out/bench.log" "$out/bench_north_star.log" > "$out/bench_lines.json" 2>/dev/null
+step 300 bench_c3.log python bench.py --workload c3 --steps 5 --no-cpu-baseline
+grep -h '^{' "$out/bench.log" "$out/bench_c3.log" > "$out/bench_lines.json" 2>/dev/null
 echo "== done" | tee -a "$out/session.log"

@@ -16,18 +16,18 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VDIR = os.path.join(ROOT, "variants")
 # name: compiler switches, or (git revision, switches) to build the kernels as they were at that revision
 VARIANTS = {
-    # round-2 session r2a (profiles/r2_sweep_a.txt): prmt 1.03x, minblocks6 1.03x, everything else <= 1.00x
-    # (two labellings in lockstep 0.88-0.97x despite -20 % instructions: 12 warps per SM do not hide the ALU latency)
-    "prmt": "-DSB_WALK_PRMT=1",               # gene-bit masks by PRMT sign replication
-    "minblocks6": "-DSB_WALK_MINBLOCKS=6",    # 80 registers: 24 warps per SM
-    "prmt_mb6": "-DSB_WALK_PRMT=1 -DSB_WALK_MINBLOCKS=6",
-    "prmt_mb7": "-DSB_WALK_PRMT=1 -DSB_WALK_MINBLOCKS=7",
-    "prmt_t96_mb8": "-DSB_WALK_PRMT=1 -DSB_WALK_THREADS=96 -DSB_WALK_MINBLOCKS=8",
-    "prmt_t160_mb5": "-DSB_WALK_PRMT=1 -DSB_WALK_THREADS=160 -DSB_WALK_MINBLOCKS=5",
-    "prmt_t192_mb4": "-DSB_WALK_PRMT=1 -DSB_WALK_THREADS=192 -DSB_WALK_MINBLOCKS=4",
-    "fisher512": "-DSB_FISHER_THREADS=512",
-    "fisher1024": "-DSB_FISHER_THREADS=1024",
-    "fisher640": "-DSB_FISHER_THREADS=640",
+    # round-2 sessions (profiles/r2_sweep.txt).  r2a: prmt 1.03x, minblocks6 1.03x, everything else <= 1.00x (two
+    # labellings in lockstep 0.88-0.97x despite -20 % instructions: 12 warps per SM do not hide the ALU latency).
+    # r2b: PRMT masks + block shapes, 1.07-1.10x -- but those launches ran 2.9 waves; with whole-wave launch planning
+    # (plan_launch, engine.cu) the shapes are compared again here.  PRMT masks are the default now.
+    "noprmt": "-DSB_WALK_PRMT=0",
+    "mb6": "-DSB_WALK_MINBLOCKS=6",
+    "mb7": "-DSB_WALK_MINBLOCKS=7",
+    "t96_mb8": "-DSB_WALK_THREADS=96 -DSB_WALK_MINBLOCKS=8",
+    "t160_mb5": "-DSB_WALK_THREADS=160 -DSB_WALK_MINBLOCKS=5",
+    "t192_mb4": "-DSB_WALK_THREADS=192 -DSB_WALK_MINBLOCKS=4",
+    "t224_mb3": "-DSB_WALK_THREADS=224 -DSB_WALK_MINBLOCKS=3",
+    "t256_mb3": "-DSB_WALK_THREADS=256 -DSB_WALK_MINBLOCKS=3",
 }
 
 
@@ -54,7 +54,7 @@ sys.path.insert(0, %(root)r)
 import numpy as np
 from scoary_b200 import synth
 from scoary_b200.engine import Engine
-G, N, P, seed = 50000, 5000, 240, 20260903
+G, N, P, seed = 50000, 5000, 360, 20260903
 traits = synth.make_traits(N, 1, seed)
 cache = "/tmp/sb_sweep_bits_{}_{}_{}.npy".format(G, N, seed)          # the same matrix for every variant: generate once
 if os.path.exists(cache):
