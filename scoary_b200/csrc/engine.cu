@@ -864,7 +864,7 @@ int launch_permute(sb_ctx *ctx, int32_t t, const int64_t *d_gene_idx, int64_t S,
     // stop right there, so the first slice is 31 labellings; the survivors of the first two slices (the host reads
     // their number, which bounds every later grid) then run slice after slice without a host round trip: each
     // round's list length stays on the device (S_dev) and blocks past the end exit at once.
-    const int n_rounds_max = 4 + (P + label_cap - 1) / label_cap;
+    const int n_rounds_max = P + 4;      // every round walks at least one labelling
     rc = ensure_scratch(ctx, 8, sizeof(int32_t) * (2 * (size_t)S + (size_t)n_rounds_max + 4));
     if (rc) return rc;
     int32_t *d_list[2] = {(int32_t *)ctx->d_scratch[8], (int32_t *)ctx->d_scratch[8] + S};
@@ -1488,7 +1488,8 @@ int sb_upgma(sb_ctx *ctx, int32_t *merges)
     SB_TRY(cudaMalloc(&S.size, sizeof(double) * N));
     SB_TRY(cudaMalloc(&S.alive, N));
     SB_TRY(cudaMalloc(&S.redo, N));
-    SB_TRY(cudaMalloc(&S.pick, sizeof(int) * 2));
+    SB_TRY(cudaMalloc(&S.pick, sizeof(int) * 4));
+    SB_TRY(cudaMemsetAsync(S.pick, 0, sizeof(int) * 4, ctx->stream));
     SB_TRY(cudaMalloc(&S.merges, sizeof(int) * 2 * (size_t)(N - 1)));
     SB_TRY(cudaMemcpyAsync(d_allowed, h_allowed.data(), sizeof(uint64_t) * W, cudaMemcpyHostToDevice, ctx->stream));
     SB_TRY(cudaMemsetAsync(d_nvar, 0, sizeof(unsigned long long), ctx->stream));
@@ -1503,12 +1504,33 @@ int sb_upgma(sb_ctx *ctx, int32_t *merges)
         sb::hamming_kernel<<<dim3(tiles, tiles, 1), dim3(32, 32, 1), 0, ctx->stream>>>(d_T, N, Gw, d_nvar, d_allowed, S.D);
         sb::upgma_rowmin_all_kernel<<<N, 256, 0, ctx->stream>>>(S);
         ctx->stats.kernel_launches += 3;
-        for (int step = 0; step < N - 1; ++step) {
-            sb::upgma_pick_kernel<<<1, 1024, 0, ctx->stream>>>(S, step);
+        // The N - 1 merge steps are four small kernels each (~20 000 launches at N = 5 000): one CUDA graph of
+        // UPGMA_GRAPH_STEPS steps is captured once and replayed; the kernels read the step counter from device
+        // memory and the steps past N - 1 in the last replay do nothing.
+        auto one_step = [&]() {
+            sb::upgma_pick_kernel<<<1, 1024, 0, ctx->stream>>>(S);
             sb::upgma_update_kernel<<<(N + 255) / 256, 256, 0, ctx->stream>>>(S);
             sb::upgma_redo_kernel<<<N, 256, 0, ctx->stream>>>(S);
             sb::upgma_finish_step_kernel<<<1, 1, 0, ctx->stream>>>(S);
+        };
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        bool graphed = false;
+        if (N - 1 > sb::UPGMA_GRAPH_STEPS &&
+            cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            for (int k = 0; k < sb::UPGMA_GRAPH_STEPS; ++k) one_step();
+            graphed = cudaStreamEndCapture(ctx->stream, &graph) == cudaSuccess && graph &&
+                      cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
         }
+        if (graphed) {
+            for (int step = 0; step < N - 1; step += sb::UPGMA_GRAPH_STEPS) SB_TRY(cudaGraphLaunch(exec, ctx->stream));
+        } else {
+            (void)cudaGetLastError();
+            for (int step = 0; step < N - 1; ++step) one_step();
+        }
+        SB_TRY(cudaStreamSynchronize(ctx->stream));
+        if (exec) cudaGraphExecDestroy(exec);
+        if (graph) cudaGraphDestroy(graph);
         ctx->stats.kernel_launches += 4LL * (N - 1);
     }
     SB_TRY(cudaGetLastError());

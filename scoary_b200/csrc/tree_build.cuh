@@ -114,10 +114,13 @@ struct UpgmaState {
     double *size;         // [N]
     unsigned char *alive; // [N]
     unsigned char *redo;  // [N] rows whose minimum must be recomputed
-    int *pick;            // [2] current (i, j)
+    int *pick;            // [2] current (i, j); [2] = the merge step the next pick kernel performs
     int *merges;          // [N-1][2]
     int N;
 };
+// The three kernels of a merge step read the step counter pick[2] from device memory and do nothing once N - 1 merges
+// are done, so a CUDA graph of UPGMA_GRAPH_STEPS steps can be replayed until the tree is complete (sb_upgma).
+constexpr int UPGMA_GRAPH_STEPS = 64;
 
 // minimum of row r by (value, column)
 __device__ __forceinline__ void row_min_block(const UpgmaState &S, int r, double *s_val, int *s_col)
@@ -155,8 +158,10 @@ __global__ void __launch_bounds__(256) upgma_rowmin_all_kernel(const UpgmaState 
 }
 
 // global argmin over the row minima by (value, morton(i, j)); one block
-__global__ void __launch_bounds__(1024) upgma_pick_kernel(const UpgmaState S, int step)
+__global__ void __launch_bounds__(1024) upgma_pick_kernel(const UpgmaState S)
 {
+    const int step = S.pick[2];
+    if (step >= S.N - 1) return;
     __shared__ double s_val[1024];
     __shared__ unsigned long long s_key[1024];
     __shared__ int s_row[1024];
@@ -191,7 +196,7 @@ __global__ void __launch_bounds__(1024) upgma_pick_kernel(const UpgmaState S, in
 __global__ void __launch_bounds__(256) upgma_update_kernel(const UpgmaState S)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= S.N) return;
+    if (k >= S.N || S.pick[2] >= S.N - 1) return;
     const int i = S.pick[0], j = S.pick[1], N = S.N;
     const double si = S.size[i], sj = S.size[j];
     const double ns = __dadd_rn(si, sj);
@@ -219,6 +224,7 @@ __global__ void __launch_bounds__(256) upgma_redo_kernel(const UpgmaState S)
     __shared__ double s_val[256];
     __shared__ int s_col[256];
     const int r = blockIdx.x;
+    if (S.pick[2] >= S.N - 1) return;
     if (!S.redo[r]) return;              // uniform per block
     row_min_block(S, r, s_val, s_col);
     if (threadIdx.x == 0) {
@@ -226,13 +232,16 @@ __global__ void __launch_bounds__(256) upgma_redo_kernel(const UpgmaState S)
     }
 }
 
+// End of a merge step (one thread): size / alive bookkeeping -- it must not race with upgma_update_kernel's reads, and
+// nothing in upgma_redo_kernel reads it -- and the step counter, which every kernel of the step has read by now.
 __global__ void upgma_finish_step_kernel(const UpgmaState S)
 {
-    // size/alive bookkeeping must not race with upgma_update_kernel's reads: done here, after it
+    if (S.pick[2] >= S.N - 1) return;
     const int i = S.pick[0], j = S.pick[1];
     S.size[i] = __dadd_rn(S.size[i], S.size[j]);
     S.size[j] = 0.0;
     S.alive[j] = 0;
+    S.pick[2] += 1;
 }
 
 }  // namespace sb

@@ -104,10 +104,10 @@ __device__ __forceinline__ unsigned sb_sign_mask2(unsigned x)
 #endif
 
 #ifndef SB_WALK_THREADS
-#define SB_WALK_THREADS 128
+#define SB_WALK_THREADS 192
 #endif
 #ifndef SB_WALK_MINBLOCKS
-#define SB_WALK_MINBLOCKS 5
+#define SB_WALK_MINBLOCKS 4
 #endif
 // Experimental (tools/sweep_variants.py, not measured yet): gene windows kept bit-reversed, so that the
 // next leaf sits in bit 15 / bit 31 and its half-word mask is ONE PRMT (sign replication) instead of

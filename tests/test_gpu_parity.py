@@ -497,4 +497,34 @@ def test_device_binomial_test_matches_scipy(engine):
     big = want > 1e-290
     rel = np.abs(got[ok][big] - want[big]) / want[big]
     assert rel.max() <= 1e-11, rel.max()
-    assert np.all(got[ok][~big] <= 1e-289)
+    tiny = ~(got[ok][~big] <= 1e-289)
+    assert not tiny.any(), (k[ok][~big][tiny][:5], n[ok][~big][tiny][:5], got[ok][~big][tiny][:5], want[~big][tiny][:5])
+
+
+def test_reference_rule_mode_many_rounds(engine):
+    """Reference-rule mode at the bench's shape in miniature: thousands of permutations, a tree large enough that the
+    constant pool holds few labellings, so the survivors run through > 100 device-paced rounds (each with its own
+    list-length counter).  r and n_done equal the oracle's sequential Permute."""
+    G, N, P = 700, 3000, 4000
+    bits, traits = _dataset(G, N, 515)
+    nested, col = _tree_for(N, 516, traits[0])
+    engine.set_genes(bits, N)
+    engine.set_trait_vector(0, traits[0])
+    names = engine.set_tree_nested(0, nested, col)
+    left, right, _ = O.flatten_tree(nested)
+    m = synth.unpack_rows(bits, N)
+    cols = np.asarray([col[n] for n in names])
+    labels = traits[0][cols].astype(np.uint8)
+    engine.set_permute_mode(1)
+    try:
+        engine.stats_reset()
+        pairs, r, nd = engine.permute(0, P, seed=31, early_stop=True, rmin=O.rmin_table(P))
+        walks = engine.stats()["tests_walks"]
+    finally:
+        engine.set_permute_mode(0)
+    pick = np.concatenate([np.arange(4), np.flatnonzero(nd == P)[:4], np.flatnonzero(nd < P)[:10]])
+    ref = O.permute(left, right, m[np.ix_(pick, cols)], labels, P=P, seed=31, trait=0, early_stop=True)
+    assert np.array_equal(pairs[pick], ref["pairs"])
+    assert np.array_equal(r[pick], ref["r"]) and np.array_equal(nd[pick], ref["n_done"])
+    assert (nd == P).sum() >= 5 and (nd == 31).sum() > G // 2
+    assert G + int(nd.sum()) <= walks <= G + int(nd.sum()) + 64 * G      # walks really done: n_done + slice overshoot

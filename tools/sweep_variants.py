@@ -18,16 +18,15 @@ VDIR = os.path.join(ROOT, "variants")
 VARIANTS = {
     # round-2 sessions (profiles/r2_sweep.txt).  r2a: prmt 1.03x, minblocks6 1.03x, everything else <= 1.00x (two
     # labellings in lockstep 0.88-0.97x despite -20 % instructions: 12 warps per SM do not hide the ALU latency).
-    # r2b: PRMT masks + block shapes, 1.07-1.10x -- but those launches ran 2.9 waves; with whole-wave launch planning
-    # (plan_launch, engine.cu) the shapes are compared again here.  PRMT masks are the default now.
-    "noprmt": "-DSB_WALK_PRMT=0",
-    "mb6": "-DSB_WALK_MINBLOCKS=6",
-    "mb7": "-DSB_WALK_MINBLOCKS=7",
-    "t96_mb8": "-DSB_WALK_THREADS=96 -DSB_WALK_MINBLOCKS=8",
-    "t160_mb5": "-DSB_WALK_THREADS=160 -DSB_WALK_MINBLOCKS=5",
-    "t192_mb4": "-DSB_WALK_THREADS=192 -DSB_WALK_MINBLOCKS=4",
-    "t224_mb3": "-DSB_WALK_THREADS=224 -DSB_WALK_MINBLOCKS=3",
-    "t256_mb3": "-DSB_WALK_THREADS=256 -DSB_WALK_MINBLOCKS=3",
+    # r2c (whole-wave launch planning in place, PRMT masks the default): 192 threads x 4 blocks per SM 1.09x,
+    # 128 x 7 1.05x, 256 x 3 1.05x, 128 x 6 1.04x, without PRMT 0.97x.  192 x 4 is the default now.
+    "t128_mb5": "-DSB_WALK_THREADS=128 -DSB_WALK_MINBLOCKS=5",     # the round-1 shape
+    "t192_mb5": "-DSB_WALK_THREADS=192 -DSB_WALK_MINBLOCKS=5",
+    "t160_mb6": "-DSB_WALK_THREADS=160 -DSB_WALK_MINBLOCKS=6",
+    "t224_mb4": "-DSB_WALK_THREADS=224 -DSB_WALK_MINBLOCKS=4",
+    "t256_mb4": "-DSB_WALK_THREADS=256 -DSB_WALK_MINBLOCKS=4",
+    "t384_mb2": "-DSB_WALK_THREADS=384 -DSB_WALK_MINBLOCKS=2",
+    "t192_mb4_npair3": "-DSB_WALK_NPAIR=3",
 }
 
 
