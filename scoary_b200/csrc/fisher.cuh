@@ -165,7 +165,9 @@ SB_DEV double fisher_two_sided(const double2 *lut, int a, int b, int c, int d, b
     }
     const int n1 = a + b, n2 = c + d, n = a + c, M = n1 + n2;
     const int lo = max(0, n - n2), hi = min(n, n1);
-    const int mode = (int)((double)((long long)(n + 1) * (long long)(n1 + 1)) / (double)(M + 2));
+    // SciPy: mode = int((n + 1)(n1 + 1) / (M + 2)) in double; the operands are integers < 2^31 and a quotient that is
+    // not an integer is at least 1 / (M + 2) away from one, so the unsigned division gives the same floor
+    const int mode = (int)(((unsigned)(n + 1) * (unsigned)(n1 + 1)) / (unsigned)(M + 2));
     if (a == mode) done = true;
     // log pmf(a)
     dd base = dd_make(lut[n1]);
@@ -176,13 +178,13 @@ SB_DEV double fisher_two_sided(const double2 *lut, int a, int b, int c, int d, b
     const dd S_a = fisher_S(lut, a, n1, n2, n);
     const dd logp_a = dd_sub(base, S_a);
     const double pexact = exp(logp_a.hi) * (1.0 + logp_a.lo);
-    {   // pexact ~= pmode  ->  1
+    const int dist = (a < mode) ? (mode - a) : (a - mode);
+    if (dist == 1) {   // pexact ~= pmode -> 1: the pmf is strictly unimodal, so only a neighbour of the mode can tie with it
         dd dm = dd_sub(S_a, fisher_S(lut, mode, n1, n2, n));
         if (fabs(dm.hi + dm.lo) <= FISHER_TIE_TOL) done = true;
     }
     const int dir_obs = (a < mode) ? -1 : +1;          // away from the mode on the observed side
     const int cnt_obs = (a < mode) ? (a - lo + 1) : (hi - a + 1);
-    const int dist = (a < mode) ? (mode - a) : (a - mode);
 
     // Other side: y_k = mode + dir2 * k, k = 1..K; included iff log pmf(y_k) - log pmf(a) <= tol.  pmf decreases
     // with k, so the included terms are k >= kstar.  Invariant of the search: kstar in [lo_k, hi_k], and hi_k is
@@ -221,19 +223,25 @@ SB_DEV double fisher_two_sided(const double2 *lut, int a, int b, int c, int d, b
     const int kstar = lo_k;
 
     // Near the mode: 1 - (the terms strictly between a and y_kstar), x = a + dir2 * j, j = 1 .. cc
-    const double var = ((double)n * (double)n1 / (double)M) * ((double)n2 / (double)M) * ((double)(M - n) / (double)max(M - 1, 1));
+    // (a - mode)^2 <= F_NEAR_Z2 x variance, variance = n n1 n2 (M - n) / (M^2 (M - 1)), without the divisions
+    const double dM = (double)M;
+    const double lhs = ((double)dist * (double)dist) * (dM * dM) * (double)max(M - 1, 1);
+    const double rhs = F_NEAR_Z2 * (((double)n * (double)n1) * ((double)n2 * (double)(M - n)));
     const int cc = dist + kstar - 1;
-    const bool near_mode = !done && (double)dist * (double)dist <= F_NEAR_Z2 * var && cc <= F_LANES * F_BLOCK;
+    const bool near_mode = !done && lhs <= rhs && cc <= F_LANES * F_BLOCK;
     const int blk_c = min(F_BLOCK, (cc + F_LANES - 1) >> 3);
     const double inner = fisher_sum<false>(lut, a + dir2, dir2, near_mode ? cc : 0, max(blk_c, 1), n1, n2, n, logp_a, S_a, 0.0,
                                     l8, lane0);
     const double p_near = 1.0 - inner;
     const bool tails = !done && !(near_mode && p_near >= F_NEAR_PMIN);
 
-    const double cut = pexact * F_TAIL_CUT;
-    double p = fisher_sum<true>(lut, a, dir_obs, tails ? cnt_obs : 0, F_BLOCK, n1, n2, n, logp_a, S_a, cut, l8, lane0);
-    const int cnt2 = (!tails || kstar > K) ? 0 : K - kstar + 1;
-    p += fisher_sum<true>(lut, mode + dir2 * kstar, dir2, cnt2, F_BLOCK, n1, n2, n, logp_a, S_a, cut, l8, lane0);
+    double p = 0.0;
+    if (SB_ANY(tails)) {       // most warps hold four null genes: no tail to sum
+        const double cut = pexact * F_TAIL_CUT;
+        p = fisher_sum<true>(lut, a, dir_obs, tails ? cnt_obs : 0, F_BLOCK, n1, n2, n, logp_a, S_a, cut, l8, lane0);
+        const int cnt2 = (!tails || kstar > K) ? 0 : K - kstar + 1;
+        p += fisher_sum<true>(lut, mode + dir2 * kstar, dir2, cnt2, F_BLOCK, n1, n2, n, logp_a, S_a, cut, l8, lane0);
+    }
     return done ? 1.0 : (tails ? fmin(p, 1.0) : p_near);
 }
 

@@ -497,7 +497,9 @@ def test_device_binomial_test_matches_scipy(engine):
     big = want > 1e-290
     rel = np.abs(got[ok][big] - want[big]) / want[big]
     assert rel.max() <= 1e-11, rel.max()
-    tiny = ~(got[ok][~big] <= 1e-289)
+    # SciPy itself degrades down there: for n > 1074 its two-sided sum underflows to exactly 0 where the true value
+    # (and the device's direct sum) is still a normal number, e.g. k = 29, n = 1077: 8.4e-268
+    tiny = ~(got[ok][~big] <= 1e-200)
     assert not tiny.any(), (k[ok][~big][tiny][:5], n[ok][~big][tiny][:5], got[ok][~big][tiny][:5], want[~big][tiny][:5])
 
 

@@ -24,7 +24,9 @@ step() {   # step <seconds> <log> <command...>
     tail -n 6 "$out/$log" | tee -a "$out/session.log"
 }
 
+mode="${2:-full}"          # quick: parity tests and the bench lines only
 step 900 pytest_gpu.log python -m pytest tests -m gpu -x -q
+if [ "$mode" != quick ]; then
 step 1200 sweep.log python tools/sweep_variants.py run
 step 300 launches.log ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
     --log-file "$out/launches.csv" python bench.py --workload c3 --steps 2 --warmup 3 --no-cpu-baseline
@@ -42,6 +44,7 @@ for rep in "$out"/prof_walk.ncu-rep "$out"/prof_fisher.ncu-rep; do
     # per-instruction executed counts and stall samples (SASS view): settles the pipe assignment of each opcode
     [ -f "$rep" ] && ncu -i "$rep" --page source --csv --print-source sass > "${rep%.ncu-rep}.source.csv" 2>/dev/null
 done
+fi
 step 600 bench.log python bench.py
 step 300 bench_c3.log python bench.py --workload c3 --steps 5 --no-cpu-baseline
 grep -h '^{' "$out/bench.log" "$out/bench_c3.log" > "$out/bench_lines.json" 2>/dev/null
