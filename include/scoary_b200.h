@@ -270,6 +270,9 @@ int sb_debug_compile_tree2(const int32_t *left, const int32_t *right, int32_t n_
  * runs `iters` rounds of dependent add/max chains on every SM and returns the
  * measured int32 add+max operations per second. */
 int sb_int32_peak(sb_ctx *ctx, int32_t iters, double *ops_per_s);
+/* Design probe (tools/pipes.py): warp instructions per second of eight instruction kinds the walk kernels are made of
+ * (VIADDMNMX, VIADDMNMX.S16x2, VIMNMX3.S16x2, VIADD.16x2, LOP3+SHF, VIMNMX3, ISETP+SEL, IMAD); out8 double[8]. */
+int sb_debug_pipe_rates(sb_ctx *ctx, int32_t iters, double *out8);
 
 #ifdef __cplusplus
 }

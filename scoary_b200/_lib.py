@@ -69,6 +69,7 @@ SIGNATURES = {
                                          ctypes.c_void_p, ctypes.c_void_p]),
     "sb_debug_shuffled_labels": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_uint64, ctypes.c_void_p]),
     "sb_upgma": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "sb_debug_pipe_rates": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p]),
     "sb_adjust_pvalues": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64)]),
     "sb_adjust_pvalues_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,

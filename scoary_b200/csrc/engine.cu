@@ -820,12 +820,16 @@ int launch_permute(sb_ctx *ctx, int32_t t, const int64_t *d_gene_idx, int64_t S,
 
     // one slice: labellings [base, base + n_perms) for the slots of d_list (n_bound of them at most; the exact
     // count is n_bound itself or, for rounds enqueued without a host round trip, *d_count), then the bookkeeping
+    const uint32_t *d_genesC = nullptr;     // reference-rule mode: compacted columns of the slots still running
+    const int32_t *d_col_of_slot = nullptr;
+    int64_t genesC_pad = 0;
     auto slice = [&](int base, int n_perms, const int32_t *d_list, int64_t n_bound, const int32_t *d_count,
                      int32_t *d_list_out, int32_t *d_count_out) -> int {
         int rc2 = upload_labels(ctx, s, d_labelsW + (size_t)base * s.W32p, n_perms);
         if (rc2) return rc2;
         sb::WalkArgs A;
         fill_walk_args(s, A, d_gene_idx, n_bound);
+        if (d_genesC) { A.genesT = d_genesC; A.Gs = genesC_pad; A.col_idx = d_col_of_slot; }
         A.S_total = S;
         A.S_dev = d_count;
         A.slot_idx = d_list;
@@ -889,6 +893,21 @@ int launch_permute(sb_ctx *ctx, int32_t t, const int64_t *d_gene_idx, int64_t S,
             SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             n_bound = *ctx->h_pinned_counter;
             cur_count = nullptr;     // exact on the host from here
+            if (round == 1 && n_bound > 0 && base + n_perms < P) {
+                // the slots that are left run all the remaining rounds: pack their gene columns side by side once
+                genesC_pad = (n_bound + 31) / 32 * 32;
+                rc = ensure_scratch(ctx, 14, sizeof(uint32_t) * (size_t)s.W32p * (size_t)genesC_pad + sizeof(int32_t) * (size_t)S);
+                if (rc) return rc;
+                uint32_t *gc = (uint32_t *)ctx->d_scratch[14];
+                int32_t *cs = (int32_t *)(gc + (size_t)s.W32p * (size_t)genesC_pad);
+                dim3 grid((unsigned)((n_bound + 255) / 256), (unsigned)std::min(s.W32p, 32), 1);
+                sb::compact_columns_kernel<<<grid, 256, 0, ctx->stream>>>(s.d_genesT, s.Gs, s.W32p, d_gene_idx, cur, (int)n_bound,
+                                                                         genesC_pad, gc, cs);
+                ctx->stats.kernel_launches += 1;
+                SB_CUDA(ctx, cudaGetLastError());
+                d_genesC = gc;
+                d_col_of_slot = cs;
+            }
         }
         base += n_perms;
         ++round;

@@ -527,6 +527,8 @@ struct WalkArgs {
                                // are enqueued without a host round trip; blocks past the end exit at once)
     int32_t lab_base;          // first word of the launch's label vectors in c_pool
     int32_t row_base;          // transposed launches: position (in slot_idx, or the slot itself) of constant row 0
+    const int32_t *col_idx;    // if set: column of genesT that holds result slot s (genesT is then the compacted matrix of
+                               // the slots still running in reference-rule mode; overrides gene_idx)
 };
 
 #ifndef SB_WALK_NPAIR
@@ -868,7 +870,7 @@ SB_DEV void walk_slots(const WalkArgs &A, const int32_t *list, int tile, int64_t
         const int64_t lc = active[k] ? li : (S - 1);   // idle lanes redo the last entry (no divergence)
         s_idx[k] = list ? (int64_t)list[lc] : lc;
         sc[k] = s_idx[k];
-        const int64_t gene = A.gene_idx ? A.gene_idx[sc[k]] : sc[k];
+        const int64_t gene = A.col_idx ? (int64_t)A.col_idx[sc[k]] : (A.gene_idx ? A.gene_idx[sc[k]] : sc[k]);
         gcol[k] = A.genesT + gene;
     }
 }
@@ -1022,29 +1024,48 @@ __global__ void __launch_bounds__(256) accumulate_hits_kernel(const uint8_t *__r
                                                               unsigned long long *__restrict__ walks)
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e == 0 && walks) atomicAdd(walks, (unsigned long long)(n_in_dev ? *n_in_dev : n_in) * (unsigned long long)n);
-    if (e >= (n_in_dev ? *n_in_dev : n_in)) return;
-    const int slot = list_in ? list_in[e] : e;
-    int r = (base == 0) ? 0 : r_arr[slot];
+    const int n_live = n_in_dev ? *n_in_dev : n_in;
+    if (e == 0 && walks) atomicAdd(walks, (unsigned long long)n_live * (unsigned long long)n);
+    const bool live = e < n_live;
+    const int slot = live ? (list_in ? list_in[e] : e) : 0;
     if (!early_stop) {
+        if (!live) return;
+        int r = (base == 0) ? 0 : r_arr[slot];
         for (int c = 0; c * ppi < n; ++c)
             r += __popc((uint32_t)hits[(int64_t)c * S_total + slot] & ((1u << min(ppi, n - c * ppi)) - 1u));
         r_arr[slot] = r;
         if (base + n >= P) n_done[slot] = P;
         return;
     }
-    for (int k = 0; k < n; ++k) {
-        const int i = base + k;
-        r += (hits[(int64_t)(k / ppi) * S_total + slot] >> (k % ppi)) & 1u;
-        if (i >= 30 && r >= rmin[i]) {
-            r_arr[slot] = r;
-            n_done[slot] = i + 1;
-            return;
+    bool survives = false;
+    if (live) {
+        int r = (base == 0) ? 0 : r_arr[slot];
+        bool stopped = false;
+        for (int k = 0; k < n; ++k) {
+            const int i = base + k;
+            r += (hits[(int64_t)(k / ppi) * S_total + slot] >> (k % ppi)) & 1u;
+            if (i >= 30 && r >= rmin[i]) {
+                n_done[slot] = i + 1;
+                stopped = true;
+                break;
+            }
+        }
+        r_arr[slot] = r;
+        if (!stopped) {
+            if (base + n >= P) n_done[slot] = P;
+            else survives = true;
         }
     }
-    r_arr[slot] = r;
-    if (base + n >= P) n_done[slot] = P;
-    else list_out[atomicAdd(counter, 1)] = slot;
+    // warp-aggregated append: one atomic per warp, and the slots of a warp keep their order, so the next round's
+    // threads read (nearly) consecutive columns
+    const unsigned m = __ballot_sync(0xffffffffu, survives);
+    if (m) {
+        const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+        int at = 0;
+        if (lane == leader) at = atomicAdd(counter, __popc(m));
+        at = __shfl_sync(0xffffffffu, at, leader);
+        if (survives) list_out[at + __popc(m & ((1u << lane) - 1u))] = slot;
+    }
 }
 
 // ---------------------------------------------------------------- transposed launches (few genes x many permutations)
@@ -1078,6 +1099,23 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const uint32_t *__rest
     const int64_t slot = list ? list[e] : e;
     const int64_t gene = gene_idx ? gene_idx[slot] : slot;
     rowsW[i] = genesT[(int64_t)w * Gs + gene];
+}
+
+// genesC [W32p][n_pad]: the columns of genesT that belong to the result slots list[e], e < *n (device count), packed
+// side by side, and col_of_slot[list[e]] = e.  Reference-rule mode walks the few slots that survive the first
+// rounds hundreds of times: out of the full matrix every thread would fetch its own 32-byte sector per word.
+__global__ void __launch_bounds__(256) compact_columns_kernel(const uint32_t *__restrict__ genesT, int64_t Gs, int W32p,
+                                                              const int64_t *__restrict__ gene_idx,
+                                                              const int32_t *__restrict__ list, int n, int64_t n_pad,
+                                                              uint32_t *__restrict__ genesC,
+                                                              int32_t *__restrict__ col_of_slot)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const int slot = list[e];
+    const int64_t gene = gene_idx ? gene_idx[slot] : slot;
+    if (blockIdx.y == 0) col_of_slot[slot] = e;
+    for (int w = blockIdx.y; w < W32p; w += gridDim.y) genesC[(int64_t)w * n_pad + e] = genesT[(int64_t)w * Gs + gene];
 }
 
 // Permute's bookkeeping (methods.py:1348-1365) on hit rows [slot][Pp] (one byte per labelling), one warp per gene.
