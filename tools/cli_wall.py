@@ -82,6 +82,10 @@ def main():
     argv = ["-g", gpath, "-t", tpath, "-o", os.path.join(d, "out"), "--no-time", "-p", "1.0", "-c", "I"]
     if P >= 10:
         argv += ["-e", str(P)]
+    try:
+        M.get_engine().set_profiling(True)
+    except Exception as ex:       # no GPU: main() will say so
+        print("engine:", ex, file=sys.stderr)
     t0 = time.perf_counter()
     try:
         M.main(argv=argv)

@@ -23,6 +23,10 @@ run() {    # run <n> <port> <args...>: bench.py on n GPUs the way the driver lau
     else python -m torch.distributed.run --nnodes=1 --nproc-per-node "$n" --master-addr 127.0.0.1 --master-port "$port" bench.py --gpus "$n" "$@"; fi
 }
 
+if [ "${SKIP_TESTS:-0}" != 1 ]; then
+    step 900 pytest_gpu.log python -m pytest tests -m gpu -x -q -rs
+    step 900 cli_wall_c3.log python tools/cli_wall.py --shape c3
+fi
 step 600 cli_two_gpus.log python -m pytest tests/test_gpu_cli_more.py -m gpu -q -k two_gpus -rs
 for n in 1 2 4 8; do
     [ "$n" -le "$ngpu" ] || continue
