@@ -17,12 +17,6 @@ step() {   # step <seconds> <log> <command...>
     echo "   exit $? ; tail:" | tee -a "$out/session.log"
     tail -n 4 "$out/$log" | cut -c1-600 | tee -a "$out/session.log"
 }
-run() {    # run <n> <port> <args...>: bench.py on n GPUs the way the driver launches it
-    local n="$1" port="$2"; shift 2
-    if [ "$n" = 1 ]; then python bench.py --gpus 1 "$@"
-    else python -m torch.distributed.run --nnodes=1 --nproc-per-node "$n" --master-addr 127.0.0.1 --master-port "$port" bench.py --gpus "$n" "$@"; fi
-}
-
 if [ "${SKIP_TESTS:-0}" != 1 ]; then
     step 900 pytest_gpu.log python -m pytest tests -m gpu -x -q -rs
     step 900 cli_wall_c3.log python tools/cli_wall.py --shape c3
@@ -30,12 +24,12 @@ fi
 step 600 cli_two_gpus.log python -m pytest tests/test_gpu_cli_more.py -m gpu -q -k two_gpus -rs
 for n in 1 2 4 8; do
     [ "$n" -le "$ngpu" ] || continue
-    step 400 "bench_north_star_n$n.log" run "$n" $((29500 + n)) --steps 5 --warmup 3 $([ "$n" = 1 ] || echo --no-cpu-baseline)
+    step 400 "bench_north_star_n$n.log" bash tools/run_bench_n.sh "$n" $((29500 + n)) --steps 5 --warmup 3 $([ "$n" = 1 ] || echo --no-cpu-baseline)
 done
 if [ "$ngpu" -ge 8 ]; then
-    step 400 bench_c4_n8.log run 8 29611 --workload c4 --steps 2 --warmup 3 --no-cpu-baseline
-    step 400 bench_c5_n8.log run 8 29612 --workload c5 --steps 3 --warmup 3 --no-cpu-baseline
-    step 400 bench_c3_n8.log run 8 29613 --workload c3 --steps 5 --warmup 3 --no-cpu-baseline
+    step 400 bench_c4_n8.log bash tools/run_bench_n.sh 8 29611 --workload c4 --steps 2 --warmup 3 --no-cpu-baseline
+    step 400 bench_c5_n8.log bash tools/run_bench_n.sh 8 29612 --workload c5 --steps 3 --warmup 3 --no-cpu-baseline
+    step 400 bench_c3_n8.log bash tools/run_bench_n.sh 8 29613 --workload c3 --steps 5 --warmup 3 --no-cpu-baseline
 fi
 grep -h '^{' "$out"/bench_*.log > "$out/bench_lines.json" 2>/dev/null
 echo "== done" | tee -a "$out/session.log"
