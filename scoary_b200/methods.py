@@ -452,6 +452,7 @@ def benjamini_hochberg(p_sorted, number_of_tests):
 
 
 DEVICE_EPILOGUE_MIN = 100_000      # rows from which the adjusted p-values and the p-sort run on the GPU
+DEVICE_BINOMIAL_MIN = 4096         # genes from which PairWiseComparisons' binomial tests run on the GPU
 
 
 def adjust_pvalues(e, p, keep, n_tests=0, device_min=None):
@@ -621,30 +622,39 @@ _RMIN_CACHE = {}
 
 def early_stop_table(P):
     """rmin[i] = least r for which the reference aborts after permutation i:
-    1 - ss.binom.cdf(r, i, 0.1) < 0.05 (scoary/methods.py:1360-1361).  Same SciPy expression as the
-    reference evaluates, but only around the boundary (started from the normal approximation and
-    walked down/up to the first r that satisfies it) and for all i at once."""
+    1 - ss.binom.cdf(r, i, 0.1) < 0.05 (scoary/methods.py:1360-1361), for all i at once.
+
+    The upper tail P[X > r], X ~ Binomial(i, 0.1), is summed directly from log-factorials (NumPy only: importing
+    scipy.stats costs more than a whole C3 run on the GPU) in a window around the normal approximation of the
+    threshold; an entry whose tail comes within 1e-9 of 0.05, or whose window does not bracket the threshold, is
+    decided by the reference's own SciPy expression instead (none does for P <= 100 000; tests/test_host_logic.py
+    compares the whole table with SciPy's)."""
     t = _RMIN_CACHE.get(P)
     if t is None:
-        from scipy import stats as ss
         t = np.full(max(P, 1), np.iinfo(np.int32).max, dtype=np.int32)
         if P > 30:
             i = np.arange(30, P, dtype=np.int64)
-
-            def stops(r):
-                return (1 - ss.binom.cdf(r, i, 0.1)) < 0.05
-
-            r = np.clip(np.floor(0.1 * i + 1.645 * np.sqrt(0.09 * i)).astype(np.int64), 0, i + 1)
-            for _ in range(64):                          # down while the smaller r already stops
-                down = (r > 0) & stops(np.maximum(r - 1, 0))
-                if not down.any():
-                    break
-                r[down] -= 1
-            for _ in range(64):                          # up to the first r that stops
-                up = ~stops(r)
-                if not up.any():
-                    break
-                r[up] += 1
+            lf = np.concatenate([[0.0], np.cumsum(np.log(np.arange(1, P + 1, dtype=np.float64)))])
+            sd = np.sqrt(0.09 * i)
+            r0 = np.clip(np.floor(0.1 * i + 1.645 * sd).astype(np.int64) - 4, 0, None)       # window start
+            K = int(8 + 12 * sd.max() + 8)
+            k = r0[:, None] + 1 + np.arange(K, dtype=np.int64)[None, :]                       # terms k = r0 + 1 ..
+            ok = k <= i[:, None]
+            kk = np.where(ok, k, 0)
+            logpmf = (lf[i][:, None] - lf[kk] - lf[i[:, None] - kk] + kk * np.log(0.1) + (i[:, None] - kk) * np.log(0.9))
+            pmf = np.where(ok, np.exp(logpmf), 0.0)
+            sf = np.cumsum(pmf[:, ::-1], axis=1)[:, ::-1]                                     # sf[:, j] = P[X > r0 + j]
+            stops = sf[:, :9] < 0.05
+            first = np.argmax(stops, axis=1)
+            r = r0 + first
+            doubt = (~stops.any(axis=1)) | (stops[:, 0] & (r0 > 0)) | (np.abs(sf[:, :9] - 0.05).min(axis=1) < 1e-9)
+            if doubt.any():
+                from scipy import stats as ss
+                for j in np.flatnonzero(doubt):
+                    rr = 0
+                    while not (1 - ss.binom.cdf(rr, int(i[j]), 0.1)) < 0.05:
+                        rr += 1
+                    r[j] = rr
             t[30:P] = r
         _RMIN_CACHE[P] = t
     return t
@@ -749,8 +759,14 @@ def PairWiseComparisons(nestedlist):
         rec = dist.gather_strided(rec, len(genes))
         pairs, r, nd = rec[:, 0:3], rec[:, 3], rec[:, 4]
     pairs = np.asarray(pairs, dtype=np.int64).reshape(-1, 3)
-    p_pro = _binom_two_sided_many(pairs[:, 1], pairs[:, 0]).tolist()
-    p_anti = _binom_two_sided_many(pairs[:, 0] - pairs[:, 2], pairs[:, 0]).tolist()
+    e = get_engine()
+    if len(pairs) >= DEVICE_BINOMIAL_MIN and hasattr(e, "binom_two_sided"):
+        # many genes: the binomial tests run on the GPU (sb_binom_two_sided, <= 1e-13 relative to SciPy's value)
+        both = e.binom_two_sided(np.concatenate([pairs[:, 1], pairs[:, 0] - pairs[:, 2]]), np.concatenate([pairs[:, 0]] * 2))
+        p_pro, p_anti = both[:len(pairs)].tolist(), both[len(pairs):].tolist()
+    else:   # few genes: SciPy itself, memoised -- the columns are then bit-identical to the reference's
+        p_pro = _binom_two_sided_many(pairs[:, 1], pairs[:, 0]).tolist()
+        p_anti = _binom_two_sided_many(pairs[:, 0] - pairs[:, 2], pairs[:, 0]).tolist()
     pairs = pairs.tolist()
     for k, g in enumerate(genes):
         total, pro, anti = pairs[k]
