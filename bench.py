@@ -446,10 +446,17 @@ def run_ours(a):
             torch.cuda.synchronize()
             rule_ms = r0.elapsed_time(r1)
             walks = e.stats()["tests_walks"]
+            e.stats_reset()
+            e.set_profiling(True)          # a third pass with per-kernel events: where the time of a pass goes
+            step_rule()
+            rst = e.stats()
+            e.set_profiling(False)
             nd = d_nd.cpu().numpy()
             ref_rule = {"ms_per_step": rule_ms, "walks_executed": int(walks), "walks_exhaustive": int(g_loc * T * (1 + P)),
                         "genes_stopped_early": int((nd < P).sum()), "genes": int(g_loc * T),
                         "equivalent_tests_per_s": g_loc * T * (1 + P) / (rule_ms * 1e-3),
+                        "kernel_ms": {k: rst[k] for k in ("ms_shuffle", "ms_walk", "ms_permute", "ms_reduce")},
+                        "k5_launches": int(rst["launches_permute"]),
                         "note": "Permute's early stop on; pairwise walk + permutations only (no Fisher pass)"}
         # the Fisher pass alone (all T traits in one launch), device resident
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -881,6 +881,7 @@ int launch_permute(sb_ctx *ctx, int32_t t, const int64_t *d_gene_idx, int64_t S,
     while (base < P && n_bound > 0) {
         int n_perms = round == 0 ? 31 : 33, one = 1;
         if (round >= 2) plan_launch((n_bound + per_block - 1) / per_block, label_cap, slots, 1, 1, &one, &n_perms);
+        if (round >= 2 && getenv("SB_RULE_ROUND_LABELLINGS")) n_perms = std::max(1, atoi(getenv("SB_RULE_ROUND_LABELLINGS")));   // tuning probe
         n_perms = std::min(std::min(n_perms, label_cap), P - base);
         int32_t *out = d_list[round & 1];
         rc = slice(base, n_perms, cur, n_bound, cur_count, out, d_counters + round);
