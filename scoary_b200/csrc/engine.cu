@@ -660,21 +660,20 @@ double fill_fraction(int64_t threads_domain, int64_t blocks_y, int slots)
     return lanes * std::min(1.0, blocks / (double)slots);
 }
 
-// Labellings per launch (n <= cap) and per block (ppi) for `tiles` thread tiles on `slots` resident blocks.  Every block
-// of a launch does the same work (same program, ppi labellings), so a launch runs in whole waves of `slots` blocks and
-// a partly filled last wave costs as much as a full one: pick the (n, ppi) with the lowest cost per labelling,
-//     (waves x ppi + launch overhead) / n,       waves = ceil(tiles x n / ppi / slots).
-// 6 250 genes (C3 split over 8 GPUs: 13 tiles) on 740 slots: 56 labellings x 1 per block = 728 blocks, one wave at 98 %,
-// where the largest launch the constant pool allows (91) would run 1.6 waves at 80 %.
+// Labellings per launch (n <= cap) and per block (ppi) for `tiles` thread tiles on `slots` resident blocks.  Measured
+// (tools/rule_probe.py, profiles/r2_rule_probe.txt): a launch of w = blocks / slots waves takes max(1, w) block times
+// -- below one wave the SMs that hold a full set of blocks set the time, above it blocks that start late run on
+// emptier SMs and the tail stays short -- plus ~0.05 block times of cold start (constant and instruction caches,
+// launch gap).  Pick the (n, ppi) with the lowest cost per labelling, (max(1, w) x ppi + 0.05) / n.
+// 6 250 genes (C3 split over 8 GPUs: 9 tiles) on 592 slots: one labelling per block and the largest launch the pool holds.
 void plan_launch(int64_t tiles, int cap, int slots, int ppi_min, int ppi_max, int *ppi_out, int *n_out)
 {
     double best = 1e300;
     int best_ppi = ppi_min, best_n = std::max(1, cap);
     for (int ppi = ppi_max; ppi >= ppi_min; ppi /= 2) {
         for (int n = cap / ppi * ppi; n >= ppi; n -= ppi) {
-            const int64_t blocks = tiles * (n / ppi);
-            const int64_t waves = (blocks + slots - 1) / slots;
-            const double cost = ((double)waves * ppi + 0.02) / n * (1.0 + 0.004 * (ppi_max / ppi - 1));
+            const double waves = std::max(1.0, (double)(tiles * (n / ppi)) / (double)slots);
+            const double cost = (waves * ppi + 0.05) / n * (1.0 + 0.004 * (ppi_max / ppi - 1));
             if (cost < best) { best = cost; best_ppi = ppi; best_n = n; }
         }
         if (ppi == 1) break;
@@ -888,13 +887,14 @@ int launch_permute(sb_ctx *ctx, int32_t t, const int64_t *d_gene_idx, int64_t S,
         if (rc) return rc;
         cur = out;
         cur_count = d_counters + round;
-        if (round < 2) {       // the two rounds that remove most genes: read the survivor count
+        if (round < 4 || round % 4 == 0) {   // the rounds that remove most genes, then every fourth: read the survivor
+                                             // count, so that the following rounds are sized for the genes really left
             SB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned_counter, cur_count, sizeof(int32_t), cudaMemcpyDeviceToHost,
                                          ctx->stream));
             SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             n_bound = *ctx->h_pinned_counter;
             cur_count = nullptr;     // exact on the host from here
-            if (round == 1 && n_bound > 0 && base + n_perms < P) {
+            if (round == 3 && n_bound > 0 && base + n_perms < P) {
                 // the slots that are left run all the remaining rounds: pack their gene columns side by side once
                 genesC_pad = (n_bound + 31) / 32 * 32;
                 rc = ensure_scratch(ctx, 14, sizeof(uint32_t) * (size_t)s.W32p * (size_t)genesC_pad + sizeof(int32_t) * (size_t)S);
