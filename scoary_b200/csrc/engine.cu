@@ -16,6 +16,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cmath>
 #include <string>
 #include <vector>
 
@@ -660,19 +661,22 @@ double fill_fraction(int64_t threads_domain, int64_t blocks_y, int slots)
     return lanes * std::min(1.0, blocks / (double)slots);
 }
 
-// Labellings per launch (n <= cap) and per block (ppi) for `tiles` thread tiles on `slots` resident blocks.  Measured
-// (tools/rule_probe.py, profiles/r2_rule_probe.txt): a launch of w = blocks / slots waves takes max(1, w) block times
-// -- below one wave the SMs that hold a full set of blocks set the time, above it blocks that start late run on
-// emptier SMs and the tail stays short -- plus ~0.05 block times of cold start (constant and instruction caches,
-// launch gap).  Pick the (n, ppi) with the lowest cost per labelling, (max(1, w) x ppi + 0.05) / n.
-// 6 250 genes (C3 split over 8 GPUs: 9 tiles) on 592 slots: one labelling per block and the largest launch the pool holds.
+// Labellings per launch (n <= cap) and per block (ppi) for `tiles` thread tiles on `slots` resident blocks.  Every block
+// of a launch does the same work, so a launch runs in waves of `slots` blocks.  Measured (tools/rule_probe.py,
+// profiles/r2_rule_probe.txt; 592 slots): a full wave takes 1.13 ms, a wave filled to a fraction f still takes
+// (0.25 + 0.75 f) of that -- blocks that share an SM with fewer others run faster, but not proportionally -- so whole
+// waves are cheapest per labelling: cost = (floor(w) + (0.25 + 0.75 frac(w) if frac(w) > 0) ) x ppi + 0.05, w = blocks / slots.
+// 5 700 genes (8 tiles of 768) on 592 slots: 74 labellings x 1 per block = 592 blocks, exactly one wave, 155 ms per
+// 10 000 permutations where the largest launch the constant pool allows (91: 1.23 waves) takes 168 ms.
 void plan_launch(int64_t tiles, int cap, int slots, int ppi_min, int ppi_max, int *ppi_out, int *n_out)
 {
     double best = 1e300;
     int best_ppi = ppi_min, best_n = std::max(1, cap);
     for (int ppi = ppi_max; ppi >= ppi_min; ppi /= 2) {
         for (int n = cap / ppi * ppi; n >= ppi; n -= ppi) {
-            const double waves = std::max(1.0, (double)(tiles * (n / ppi)) / (double)slots);
+            const double w = (double)(tiles * (n / ppi)) / (double)slots;
+            const double full = std::floor(w + 1e-9), frac = w - full;
+            const double waves = full + (frac > 1e-9 ? 0.25 + 0.75 * frac : 0.0);
             const double cost = (waves * ppi + 0.05) / n * (1.0 + 0.004 * (ppi_max / ppi - 1));
             if (cost < best) { best = cost; best_ppi = ppi; best_n = n; }
         }
