@@ -589,7 +589,7 @@ void fill_walk_args(const TraitSlot &s, sb::WalkArgs &A, const int64_t *d_gene_i
 {
     memset(&A, 0, sizeof A);
     A.genesT = s.d_genesT; A.Gs = s.Gs; A.gene_idx = d_gene_idx; A.S = S; A.S_total = S; A.slot_idx = nullptr;
-    A.W32p = s.W32p; A.shift = s.shift; A.lab_base = s.lab_base;
+    A.W32p = s.W32p; A.shift = s.shift; A.lab_base = s.lab_base; A.tile_threads = sb::WALK_THREADS;
 }
 
 // label vectors (or, in transposed launches, gene rows) that fit behind the program of slot s
@@ -716,7 +716,7 @@ int launch_rows(sb_ctx *ctx, const TraitSlot &s, const uint32_t *d_labelsT, int6
         memset(&A, 0, sizeof A);
         A.genesT = d_labelsT + perm_lo; A.Gs = Ps; A.S = Pn; A.S_total = Ps;
         A.slot_idx = d_list; A.row_base = (int32_t)base;
-        A.W32p = s.W32p; A.shift = s.shift; A.lab_base = s.lab_base;
+        A.W32p = s.W32p; A.shift = s.shift; A.lab_base = s.lab_base; A.tile_threads = sb::WALK_THREADS;
         A.n_perms = n; A.ppi = ppi; A.items_per_tile = (n + ppi - 1) / ppi;
         A.unperm = d_unperm; A.hits = d_hits + perm_lo;
         dim3 grid((unsigned)tiles, (unsigned)A.items_per_tile, 1);
@@ -795,8 +795,20 @@ int launch_permute(sb_ctx *ctx, int32_t t, const int64_t *d_gene_idx, int64_t S,
     const size_t smem = walk_smem_bytes(s, false);
     if (smem > (size_t)ctx->max_smem_optin) return fail(ctx, SB_ERR_ARG, "tree too deep for shared memory");
     SB_CUDA(ctx, cudaFuncSetAttribute(sb::walk_permute_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // Threads per block: WALK_THREADS, or fewer when that leaves the last tile of a SMALL work list nearly empty
+    // (6 250 genes -- the north_star job on 8 GPUs -- are 8.14 tiles of 192 x 4 but 9.77 tiles of 160 x 4: 98 % of the
+    // lanes carry a walk instead of 90 %).  Only exhaustive mode: reference-rule rounds shrink their lists anyway.
+    int tile_threads = sb::WALK_THREADS;
+    if (!early_stop && S < 24LL * sb::WALK_THREADS * sb::WALK_NP) {
+        double best = 0.0;
+        for (int tt = sb::WALK_THREADS; tt >= 96; tt -= 32) {
+            const int64_t per = (int64_t)tt * sb::WALK_NP, tl = (S + per - 1) / per;
+            const double util = (double)S / (double)(tl * per);
+            if (util > best + 0.02) { best = util; tile_threads = tt; }
+        }
+    }
     int per_sm = 0;
-    SB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sb::walk_permute_kernel<false>, sb::WALK_THREADS, smem));
+    SB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sb::walk_permute_kernel<false>, tile_threads, smem));
     const int slots = std::max(1, per_sm) * ctx->sm_count;      // resident K5 blocks
     const int label_cap = label_capacity(s);
     // threads = genes (the default) or threads = labellings: whichever shape fills the GPU better
@@ -813,7 +825,7 @@ int launch_permute(sb_ctx *ctx, int32_t t, const int64_t *d_gene_idx, int64_t S,
 
     // labellings per launch and per block, in whole waves of resident blocks (plan_launch).  Reference-rule mode
     // plans every round for the genes still running, one labelling per block (its hit rows hold one flag each).
-    const int64_t per_block = (int64_t)sb::WALK_THREADS * sb::WALK_NP;
+    const int64_t per_block = (int64_t)tile_threads * sb::WALK_NP;
     const int64_t tiles_all = (S + per_block - 1) / per_block;
     int ppi = sb::WALK_NLAB, n_launch = std::min(label_cap, P);
     if (!early_stop) plan_launch(tiles_all, std::min(label_cap, P), slots, sb::WALK_NLAB, sb::PERMS_PER_ITEM_MAX, &ppi, &n_launch);
@@ -835,6 +847,7 @@ int launch_permute(sb_ctx *ctx, int32_t t, const int64_t *d_gene_idx, int64_t S,
         if (d_genesC) { A.genesT = d_genesC; A.Gs = genesC_pad; A.col_idx = d_col_of_slot; }
         A.S_total = S;
         A.S_dev = d_count;
+        A.tile_threads = tile_threads;
         A.slot_idx = d_list;
         A.n_perms = n_perms;
         A.ppi = ppi;
@@ -846,7 +859,7 @@ int launch_permute(sb_ctx *ctx, int32_t t, const int64_t *d_gene_idx, int64_t S,
         dim3 grid((unsigned)tiles, (unsigned)A.items_per_tile, 1);
         {
             Timed tm(ctx, CAT_PERMUTE);
-            sb::walk_permute_kernel<false><<<grid, sb::WALK_THREADS, smem, ctx->stream>>>(A);
+            sb::walk_permute_kernel<false><<<grid, tile_threads, smem, ctx->stream>>>(A);
             ctx->stats.kernel_launches += 1;
             if (!d_count) ctx->stats.tests_walks += n_bound * (int64_t)n_perms;   // else the device counts (d_walks)
             SB_CUDA(ctx, cudaGetLastError());

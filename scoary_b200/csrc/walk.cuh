@@ -529,6 +529,8 @@ struct WalkArgs {
     int32_t row_base;          // transposed launches: position (in slot_idx, or the slot itself) of constant row 0
     const int32_t *col_idx;    // if set: column of genesT that holds result slot s (genesT is then the compacted matrix of
                                // the slots still running in reference-rule mode; overrides gene_idx)
+    int32_t tile_threads;      // threads per block of this launch (<= WALK_THREADS, a multiple of 32): a tile is
+                               // tile_threads x NP work-list entries, chosen so that the last tile is nearly full
 };
 
 #ifndef SB_WALK_NPAIR
@@ -857,7 +859,7 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR
 #undef SB_POP16
 }
 
-// gene slots of this thread: (tile * NP + k) * T + tid  (coalesced per k)
+// gene slots of this thread: (tile * NP + k) * tile_threads + tid  (coalesced per k)
 template <int NP>
 SB_DEV void walk_slots(const WalkArgs &A, const int32_t *list, int tile, int64_t (&s_idx)[NP], bool (&active)[NP],
                                            int64_t (&sc)[NP], const uint32_t *(&gcol)[NP])
@@ -865,7 +867,7 @@ SB_DEV void walk_slots(const WalkArgs &A, const int32_t *list, int tile, int64_t
     const int64_t S = A.S_dev ? (int64_t)*A.S_dev : A.S;
 #pragma unroll
     for (int k = 0; k < NP; ++k) {
-        const int64_t li = ((int64_t)tile * NP + k) * WALK_THREADS + threadIdx.x;   // position in the work list
+        const int64_t li = ((int64_t)tile * NP + k) * A.tile_threads + threadIdx.x;   // position in the work list
         active[k] = li < S;
         const int64_t lc = active[k] ? li : (S - 1);   // idle lanes redo the last entry (no divergence)
         s_idx[k] = list ? (int64_t)list[lc] : lc;
@@ -934,7 +936,7 @@ SB_KERNEL(__launch_bounds__(WALK_THREADS, SB_WALK_MINBLOCKS)) walk_permute_kerne
     const int chunk = blockIdx.y;
     const int perm0 = chunk * A.ppi;
     const int rows = min(A.ppi, A.n_perms - perm0);
-    if (A.S_dev && (int64_t)blockIdx.x * NP * WALK_THREADS >= (int64_t)*A.S_dev) return;   // grid sized for an upper bound
+    if (A.S_dev && (int64_t)blockIdx.x * NP * A.tile_threads >= (int64_t)*A.S_dev) return;   // grid sized for an upper bound
     int64_t s_idx[NP], sc[NP]; bool active[NP]; const uint32_t *gcol[NP];
     walk_slots<NP>(A, TRANSPOSED ? nullptr : A.slot_idx, blockIdx.x, s_idx, active, sc, gcol);   // transposed: slot_idx lists the rows
     const int K = 1 << A.shift;

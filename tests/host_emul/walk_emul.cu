@@ -24,7 +24,7 @@ void fill(sb::WalkArgs &A, const uint32_t *genesT, int64_t Gs, int64_t S, int W3
 {
     memset(&A, 0, sizeof A);
     A.genesT = genesT; A.Gs = Gs; A.gene_idx = nullptr; A.slot_idx = nullptr; A.S = S; A.S_total = S;
-    A.W32p = W32p; A.shift = shift;
+    A.W32p = W32p; A.shift = shift; A.tile_threads = sb::WALK_THREADS;
 }
 
 // the simulated shared memory is followed by guard words: a kernel that needs more stack than the compiler

@@ -141,3 +141,56 @@ def test_three_rank_cli_permutations_match_one_rank(tmp_path):
         a = _read(os.path.join(str(tmp_path / "two"), trait + ".results.csv"))
         assert a == _read(os.path.join(str(tmp_path / "one"), trait + ".results.csv"))
         assert "Empirical_p" in a.splitlines()[0]
+
+
+def _worker_wide_records(rank, world, port, q):
+    """records of T traits side by side (what bench.py gathers) and a rank that owns no genes"""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+    from scoary_b200 import distributed as D
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ok = True
+    for G, T in ((11, 3), (2, 2), (1, 1)):             # G < world: some ranks hold an empty shard
+        bounds = D.shard_bounds(G, world)
+        lo, hi = bounds[rank]
+        full = np.arange(G * T * D.RECORD_WORDS, dtype=np.int32).reshape(G, T * D.RECORD_WORDS)
+        got = D.all_gather_records(torch.from_numpy(full[lo:hi].copy()), G, bounds).numpy()
+        ok = ok and np.array_equal(got, full)
+        ok = ok and np.array_equal(D.gather_blocks(full[lo:hi], G), full)
+        ok = ok and np.array_equal(D.gather_strided(full[rank::world], G), full)
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put((rank, bool(ok)))
+
+
+def test_gathers_with_several_traits_per_record_and_empty_shards():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 400) + 7
+    procs = [ctx.Process(target=_worker_wide_records, args=(r, 3, port, q)) for r in range(3)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True), (2, True)]
+
+
+def test_cli_with_fewer_genes_than_ranks(tmp_path):
+    """G < world leaves a rank without genes; it must only take part in the gathers (no hang, no error),
+    and the files must equal a one-rank run."""
+    from scoary_b200.methods import ROARY_COLUMNS
+    g, t = str(tmp_path / "g.csv"), str(tmp_path / "t.csv")
+    iso = ["i%d" % k for k in range(10)]
+    with open(g, "w") as fh:
+        fh.write(",".join('"%s"' % c for c in ROARY_COLUMNS[:14]) + "," + ",".join(iso) + "\n")
+        fh.write('"gA","","x",1,1,1,1,,,,,,,,' + ",".join("1" if k % 2 else "" for k in range(10)) + "\n")
+        fh.write('"gB","","y",1,1,1,1,,,,,,,,' + ",".join("1" if k < 4 else "" for k in range(10)) + "\n")
+    with open(t, "w") as fh:
+        fh.write(",T\n" + "".join("%s,%d\n" % (n, k < 5) for k, n in enumerate(iso)))
+    argv = ["-g", g, "-t", t, "--no-time", "-p", "1.0", "-c", "I", "-e", "20"]
+    mp.spawn(_cli_worker, args=(3, 29900 + (os.getpid() % 90), argv, str(tmp_path / "three")), nprocs=3, join=True)
+    mp.spawn(_cli_worker, args=(1, 29990 - (os.getpid() % 90), argv, str(tmp_path / "one")), nprocs=1, join=True)
+    a = _read(os.path.join(str(tmp_path / "three"), "T.results.csv"))
+    assert a == _read(os.path.join(str(tmp_path / "one"), "T.results.csv")) and len(a.splitlines()) == 3

@@ -47,5 +47,7 @@ done
 fi
 step 600 bench.log python bench.py
 step 300 bench_c3.log python bench.py --workload c3 --steps 5 --no-cpu-baseline
-grep -h '^{' "$out/bench.log" "$out/bench_c3.log" > "$out/bench_lines.json" 2>/dev/null
+# one GPU's share of the north_star job on 8 GPUs (6 250 genes): what strong scaling asks of the launch planner
+step 300 bench_shard8.log python bench.py --genes 6250 --steps 3 --no-cpu-baseline
+grep -h '^{' "$out/bench.log" "$out/bench_c3.log" "$out/bench_shard8.log" > "$out/bench_lines.json" 2>/dev/null
 echo "== done" | tee -a "$out/session.log"
