@@ -8,9 +8,12 @@ for every (gene, trait) -- every gene row read once for all traits --, the unper
 label permutations for every gene (-p 1.0, exhaustive mode: no early stop), then -- for N > 1 -- the one NCCL
 all-gather of the per-gene records (scoary_b200.distributed).  tests = G_tested * T * (1 + P).
 
-The job is FIXED and N GPUs split its genes into contiguous shards ("scaling": "strong"): the default workload is
-BASELINE.json's north_star target, 50 000 genes x 5 000 isolates x 10 000 permutations, at 1 / 2 / 4 / 8 GPUs;
---workload c3 / c4 / c5 are configs[2..4] (c4 and c5 are the 8-GPU configurations; they also fit one GPU).
+The job is FIXED and N GPUs split it ("scaling": "strong"): by genes -- contiguous shards, one all-gather of per-gene
+records, the reference's own fan-out -- while a shard still fills a GPU, else by permutations -- every GPU walks all
+genes under its own range of the labellings and the hit counts are summed in one all-reduce
+(scoary_b200.distributed.split_for; --split forces one).  The default workload is BASELINE.json's north_star target,
+50 000 genes x 5 000 isolates x 10 000 permutations, at 1 / 2 / 4 / 8 GPUs; --workload c3 / c4 / c5 are configs[2..4]
+(c4 and c5 are the 8-GPU configurations; they also fit one GPU).
 
   value : whole-job tests/s with inputs resident in HBM when the clock starts (CUDA events, max over ranks)
   e2e   : the same through the host-buffer C-ABI calls (pinned host bitsets in, host result arrays out, H2D/D2H
@@ -49,6 +52,8 @@ def parse_args():
     ap.add_argument("--genes", type=int, default=0, help="override the job's gene count")
     ap.add_argument("--isolates", type=int, default=0)
     ap.add_argument("--perms", type=int, default=-1)
+    ap.add_argument("--split", default="auto", choices=["auto", "genes", "permutations"],
+                    help="how N GPUs divide the job (auto: scoary_b200.distributed.split_for)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -263,7 +268,15 @@ def run_ours(a):
 
     # ---- synthetic inputs: ONE fixed job (G genes), split into contiguous gene shards (strong scaling);
     # traits and tree are replicated
-    bounds = sbd.shard_bounds(G, world)
+    # N GPUs split the job by genes (the reference's own fan-out) while a shard still fills a GPU, else by
+    # permutations: every GPU walks all genes under its own range of the labellings and the hit counts are summed
+    split = sbd.split_for(G, P, world) if a.split == "auto" else a.split
+    if split == "permutations":
+        bounds = [(0, G)] * world
+        perm_first, perm_count = sbd.permutation_range(P, world, rank)
+    else:
+        bounds = sbd.shard_bounds(G, world)
+        perm_first, perm_count = 0, P
     lo, hi = bounds[rank]
     g_loc = hi - lo
     traits = synth.make_traits(N, T, seed)
@@ -306,6 +319,11 @@ def run_ours(a):
     def step_device():
         # every gene row is read ONCE for all T traits (sb_contingency_fisher_multi), then walks + permutations
         e.contingency_fisher_multi_device(0, T, d_counts.data_ptr(), d_p.data_ptr())
+        if split == "permutations":      # all genes, this rank's range of the labellings; one all-reduce of the hit counts
+            for t in range(T):
+                e.permute_range_device(t, g_loc, perm_first, perm_count, seed, d_pairs[t].data_ptr(), d_r[t].data_ptr())
+            dist.all_reduce(d_r, op=dist.ReduceOp.SUM)
+            return
         if P > 0:
             for t in range(T):
                 e.permute_device(t, g_loc, P, seed, d_pairs[t].data_ptr(), d_r[t].data_ptr(), d_nd[t].data_ptr())
@@ -328,7 +346,9 @@ def run_ours(a):
     counts_host = d_counts.cpu().numpy()
     g_tested = int(((counts_host[..., 0] + counts_host[..., 1] > 0) &
                     (counts_host[..., 2] + counts_host[..., 3] > 0)).sum())
-    tests_per_step_rank = g_tested * (1 + P)
+    # the job's tests are counted once: a rank that walks a range of the permutations repeats the (cheap) Fisher pass
+    # and the unpermuted walk of every gene, which are not counted again
+    tests_per_step_rank = g_tested * (1 + P) if split == "genes" else g_tested * perm_count + (g_tested if rank == 0 else 0)
 
     e.stats_reset()
     e.set_profiling(True)
@@ -381,14 +401,23 @@ def run_ours(a):
         d2h += c.nbytes + p.nbytes
         t2 = time.perf_counter()
         rec = np.zeros((g_loc, T * RW), dtype=np.int32)
+        r_all = np.zeros((T, g_loc), dtype=np.int32)
         for t in range(T):
             pairs = r = nd = 0
-            if P > 0:
+            if split == "permutations":
+                pairs, r = e.permute_range(t, perm_first, perm_count, seed=seed)
+                d2h += pairs.nbytes + r.nbytes
+                r_all[t], nd = r, P
+            elif P > 0:
                 pairs, r, nd = e.permute(t, P, seed=seed)
                 d2h += pairs.nbytes + r.nbytes + nd.nbytes
             rec[:, t * RW:(t + 1) * RW] = sbd.pack_records(c[t], p[t], pairs, r, nd)
         t3 = time.perf_counter()
-        if world > 1:
+        if split == "permutations":
+            r_all = sbd.all_reduce_sum(r_all)
+            for t in range(T):
+                rec[:, t * RW + 9] = r_all[t]
+        elif world > 1:
             rec = sbd.gather_blocks(rec, G)
         t4 = time.perf_counter()
         checksum = 0.0
@@ -489,7 +518,7 @@ def run_ours(a):
     k5_launches = max(1, int(st["launches_permute"]))
     k5_ms = st["ms_permute"] / k5_launches                       # average launch duration (CUDA events, this run)
     launches_per_step = k5_launches / float(a.steps)
-    tests_per_launch = g_loc * T * P / launches_per_step         # (gene, labelling) walks one launch performs
+    tests_per_launch = g_loc * T * perm_count / launches_per_step    # (gene, labelling) walks one launch performs
     bytes_per_test = (8 * W + 8) / float(1 + P) if P > 0 else 0  # compulsory HBM bytes per test
     ops_per_test = (N - 1) * OPS_PER_NODE                        # int32 add/max ops per test
     alg_bytes = tests_per_launch * bytes_per_test
@@ -540,13 +569,18 @@ def run_ours(a):
         "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": dev_ms / a.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "int32 (walk DP) + f64 (Fisher)", "data": "synthetic",
         "config": {"workload": workload_string(a.workload, G, N, T, P),
-                   "parallelism": ("the job's %d genes in %d contiguous shards (%d per GPU), traits and tree replicated, "
-                                   "one NCCL all-gather of %d-byte per-gene records (scoary_b200.distributed)"
-                                   % (G, world, bounds[0][1] - bounds[0][0], 4 * RW * T)) if world > 1 else "single GPU",
+                   "parallelism": "single GPU" if world == 1 else (
+                       "the job's %d genes in %d contiguous shards (%d per GPU), traits and tree replicated, one NCCL "
+                       "all-gather of %d-byte per-gene records (scoary_b200.distributed)"
+                       % (G, world, bounds[0][1] - bounds[0][0], 4 * RW * T) if split == "genes" else
+                       "the job's %d permutations in %d ranges (%d per GPU): every GPU walks all %d genes under its own "
+                       "labellings (gene shards of %d would not fill a GPU), Fisher pass and unpermuted walk replicated, "
+                       "one NCCL all-reduce of the %d-byte hit-count vector (scoary_b200.distributed.split_for)"
+                       % (P, world, perm_count, G, G // world, 4 * G * T)),
                    "l2": "256 MiB buffer written between timed steps (inputs %d MB < 126 MB L2)" % (2 * g_loc * W * 8 // 1000000),
                    "value_includes": "Fisher pass, pairwise walk, label shuffles, permutation walks, hit bookkeeping%s; the "
                                      "gene matrix is already in walk order (K1 pack + host tree compile run once, in warm-up; "
-                                     "e2e repeats them every step)" % (", all-gather" if world > 1 else ""),
+                                     "e2e repeats them every step)" % ((", all-gather" if split == "genes" else ", all-reduce") if world > 1 else ""),
                    "tests_per_step": tests_per_step, "seed": seed},
         "e2e": {"value": e2e_value, "unit": "tests/s", "h2d_bytes_per_step": int(h2d_b), "d2h_bytes_per_step": int(d2h_b),
                 "ms_per_step": e2e_s / a.steps * 1e3, "steps": a.steps, "calls_ms": e2e_trace[-1],

@@ -185,6 +185,16 @@ int sb_debug_shuffled_labels(sb_ctx *ctx, int32_t t, int32_t P, uint64_t seed, u
  * cluster[i] = [cluster[i], cluster[j]].  The merge order is identical to the reference's. */
 int sb_upgma(sb_ctx *ctx, int32_t *merges);
 
+/* Exhaustive Permute for the permutations perm_first .. perm_first + perm_count - 1 of a job: r[s] = hits among those
+ * labellings only (the labelling of permutation i depends on (seed, trait slot, i) alone, so the hit counts of
+ * disjoint ranges add up to sb_permute's r for the whole job).  This is how N GPUs split a job whose gene shards would
+ * be too small to fill them: every GPU walks all S genes under its own range of the permutations and the r vectors
+ * are summed (one all-reduce).  pairs (may be NULL) = the unpermuted Total, Pro, Anti as in sb_permute. */
+int sb_permute_range(sb_ctx *ctx, int32_t t, const int64_t *gene_idx, int64_t S, int32_t perm_first,
+                     int32_t perm_count, uint64_t seed, int32_t *pairs, int32_t *r);
+int sb_permute_range_device(sb_ctx *ctx, int32_t t, const int64_t *d_gene_idx, int64_t S, int32_t perm_first,
+                            int32_t perm_count, uint64_t seed, int32_t *d_pairs, int32_t *d_r);
+
 /* ---- epilogue on the device ---- */
 /* What Setup_results does with the p-values of one trait after the gene loop (methods.py:900-925) and the sort
  * every later step relies on (SortResultsAndSetKey, methods.py:1448-1454), for the 1M-row scale:

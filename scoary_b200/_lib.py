@@ -67,6 +67,11 @@ SIGNATURES = {
     "sb_permute_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32,
                                          ctypes.c_uint64, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
                                          ctypes.c_void_p, ctypes.c_void_p]),
+    "sb_permute_range": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32,
+                                        ctypes.c_int32, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p]),
+    "sb_permute_range_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64,
+                                               ctypes.c_int32, ctypes.c_int32, ctypes.c_uint64, ctypes.c_void_p,
+                                               ctypes.c_void_p]),
     "sb_debug_shuffled_labels": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_uint64, ctypes.c_void_p]),
     "sb_upgma": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "sb_debug_pipe_rates": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p]),

@@ -181,7 +181,8 @@ __global__ void __launch_bounds__(256) pack_walk_order_kernel(const uint64_t *__
 __global__ void __launch_bounds__(64) shuffle_labels_kernel(const uint32_t *__restrict__ labels_leaf /*[W32]*/,
                                                             int n_leaves, int W32, int W32p,
                                                             const int32_t *__restrict__ leaf_of_pos, uint64_t seed,
-                                                            int trait, int P, uint32_t *__restrict__ labelsW,
+                                                            int trait, int P, int perm_first,
+                                                            uint32_t *__restrict__ labelsW,
                                                             uint8_t *__restrict__ dbg_leaf /* [P][n_leaves] or null */)
 {
     extern __shared__ uint32_t s_lab[];   // [W32][T]
@@ -193,7 +194,9 @@ __global__ void __launch_bounds__(64) shuffle_labels_kernel(const uint32_t *__re
     uint32_t rnd[4] = {0, 0, 0, 0};
     for (int i = n_leaves - 1; i >= 1; --i) {
         const int s = n_leaves - 1 - i;
-        if ((s & 1) == 0) philox4x32_10((uint32_t)(s >> 1), (uint32_t)perm, (uint32_t)trait, SHUFFLE_DOMAIN, k0, k1, rnd);
+        // the stream belongs to the permutation's index in the whole job (perm_first + perm): a rank that walks a
+        // range of the permutations draws the same labellings a single GPU would
+        if ((s & 1) == 0) philox4x32_10((uint32_t)(s >> 1), (uint32_t)(perm_first + perm), (uint32_t)trait, SHUFFLE_DOMAIN, k0, k1, rnd);
         const uint64_t u = (s & 1) ? ((uint64_t)rnd[2] | ((uint64_t)rnd[3] << 32))
                                    : ((uint64_t)rnd[0] | ((uint64_t)rnd[1] << 32));
         const int j = (int)__umul64hi(u, (uint64_t)(i + 1));

@@ -126,6 +126,32 @@ def gather_blocks(rows, n_total):
     return np.concatenate([parts[r][: bounds[r][1] - bounds[r][0]] for r in range(world)], axis=0)
 
 
+def all_reduce_sum(values):
+    """Sum of an int32 array over the ranks (every rank gets the total): the hit counts of the permutation ranges the
+    ranks walked (Engine.permute_range) add up to the job's."""
+    import torch
+    import torch.distributed as dist
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.from_numpy(np.ascontiguousarray(values, dtype=np.int32)).to(dev)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.cpu().numpy()
+
+
+def permutation_range(P, world, rank):
+    """[first, first + count): rank's share of P permutations (contiguous, sizes differ by at most one)."""
+    lo, hi = shard_bounds(P, world)[rank]
+    return lo, hi - lo
+
+
+def split_for(G, P, world, per_tile=768, min_tiles=24, min_perms=64):
+    """How N GPUs split an EXHAUSTIVE job: by genes (the reference's own fan-out, methods.py:1076-1097) while a shard
+    still fills a GPU with whole waves of blocks, else by permutations -- every GPU walks all genes under its own range
+    of the labellings, so launches stay as large as on one GPU, and the hit counts are summed."""
+    if world > 1 and G / world < min_tiles * per_tile and P // world >= min_perms:
+        return "permutations"
+    return "genes"
+
+
 def gather_strided(rows, n_total):
     """Rank r holds rows r, r + world, r + 2 world, ... -> every rank gets all n_total rows in order."""
     world, _ = world_rank()

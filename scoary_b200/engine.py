@@ -243,6 +243,24 @@ class Engine:
                                          1 if early_stop else 0, _ptr(rm), _ptr(pairs), _ptr(r), _ptr(nd)))
         return pairs, r, nd
 
+    def permute_range(self, t, perm_first, perm_count, seed=0, gene_idx=None):
+        """Exhaustive Permute over permutations perm_first .. perm_first + perm_count - 1 of a job:
+        (pairs, r) with r = hits among those labellings (the ranges of a job add up to permute()'s r)."""
+        idx = None if gene_idx is None else np.ascontiguousarray(gene_idx, dtype=np.int64)
+        S = self.G if idx is None else len(idx)
+        pairs = np.empty((S, 3), dtype=np.int32)
+        r = np.empty(S, dtype=np.int32)
+        if S == 0:
+            return pairs, r
+        self._check(self._lib.sb_permute_range(self._ctx, int(t), _ptr(idx), S, int(perm_first), int(perm_count),
+                                               int(seed) & (2**64 - 1), _ptr(pairs), _ptr(r)))
+        return pairs, r
+
+    def permute_range_device(self, t, S, perm_first, perm_count, seed, pairs_ptr, r_ptr, gene_idx_ptr=0):
+        self._check(self._lib.sb_permute_range_device(self._ctx, int(t), ctypes.c_void_p(int(gene_idx_ptr) or None), int(S),
+                                                      int(perm_first), int(perm_count), int(seed) & (2**64 - 1),
+                                                      ctypes.c_void_p(int(pairs_ptr) or None), ctypes.c_void_p(int(r_ptr))))
+
     def shuffled_labels(self, t, P, seed, n_leaves):
         out = np.empty((P, n_leaves), dtype=np.uint8)
         self._check(self._lib.sb_debug_shuffled_labels(self._ctx, int(t), int(P), int(seed) & (2**64 - 1), _ptr(out)))

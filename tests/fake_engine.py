@@ -41,6 +41,11 @@ class FakeEngine:
     def set_permute_mode(self, mode):
         pass
 
+    def permute_range(self, t, perm_first, perm_count, seed=0, gene_idx=None):
+        left, right, g, lab = self._walk_inputs(t, gene_idx)
+        res = O.permute(left, right, g, lab, P=perm_first + perm_count, seed=seed & (2**64 - 1), trait=t, want_hits=True)
+        return res["pairs"], res["hits"][:, perm_first:perm_first + perm_count].sum(axis=1).astype(np.int32)
+
     def _walk_inputs(self, t, gene_idx):
         left, right, cols = self.trees[t]
         rows = np.arange(self.G) if gene_idx is None else np.asarray(gene_idx)

@@ -194,3 +194,48 @@ def test_cli_with_fewer_genes_than_ranks(tmp_path):
     mp.spawn(_cli_worker, args=(1, 29990 - (os.getpid() % 90), argv, str(tmp_path / "one")), nprocs=1, join=True)
     a = _read(os.path.join(str(tmp_path / "three"), "T.results.csv"))
     assert a == _read(os.path.join(str(tmp_path / "one"), "T.results.csv")) and len(a.splitlines()) == 3
+
+
+def _worker_perm_split(rank, world, port, q):
+    """the other way N GPUs split an exhaustive job: every rank walks all genes under its own range of the
+    permutations (Engine.permute_range), the hit counts are summed (distributed.all_reduce_sum)"""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    from fake_engine import FakeEngine
+    from scoary_b200 import distributed as D
+    from scoary_b200 import synth, tree as treemod
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    G, N, P, seed = 23, 50, 37, 9
+    traits = synth.make_traits(N, 1, seed)
+    bits = synth.make_genes_packed(G, N, seed, traits=traits)
+    left, right, names = treemod.flatten(synth.make_tree(N, seed))
+    col = {n: j for j, n in enumerate(synth.isolate_names(N))}
+    e = FakeEngine()
+    e.set_genes(bits, N)
+    e.set_trait_vector(0, traits[0])
+    e.set_tree(0, left, right, np.asarray([col[n] for n in names], dtype=np.int32))
+    first, count = D.permutation_range(P, world, rank)
+    pairs, r_part = e.permute_range(0, first, count, seed=seed)
+    r = D.all_reduce_sum(r_part)
+    want_pairs, want_r, _ = e.permute(0, P, seed=seed)
+    ok = np.array_equal(r, want_r) and np.array_equal(pairs, want_pairs)
+    ok = ok and D.split_for(50000, 10000, 8) == "permutations" and D.split_for(1000000, 1000, 8) == "genes"
+    ok = ok and D.split_for(50000, 10000, 1) == "genes" and D.split_for(50000, 100, 8) == "genes"
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put((rank, bool(ok)))
+
+
+def test_permutation_split_adds_up_under_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 400) + 11
+    procs = [ctx.Process(target=_worker_perm_split, args=(r, 3, port, q)) for r in range(3)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True), (2, True)]

@@ -530,3 +530,33 @@ def test_reference_rule_mode_many_rounds(engine):
     assert np.array_equal(r[pick], ref["r"]) and np.array_equal(nd[pick], ref["n_done"])
     assert (nd == P).sum() >= 5 and (nd == 31).sum() > G // 2
     assert G + int(nd.sum()) <= walks <= G + int(nd.sum()) + 64 * G      # walks really done: n_done + slice overshoot
+
+
+@pytest.mark.parametrize("G,N,P,parts", [(300, 200, 100, 3), (64, 1000, 257, 8), (700, 129, 64, 2)])
+def test_permutation_ranges_add_up_to_the_job(engine, G, N, P, parts):
+    """sb_permute_range: the labelling of permutation i depends on (seed, trait, i) alone, so disjoint ranges of the
+    permutations -- the way N GPUs split a job whose gene shards would be too small -- give hit counts that add up to
+    sb_permute's r, which equals the oracle's."""
+    from scoary_b200 import distributed as D
+    bits, traits = _dataset(G, N, 8000 + G + N, 0.01)
+    nested, col = _tree_for(N, 31 + N, traits[0])
+    engine.set_genes(bits, N)
+    engine.set_trait_vector(2, traits[0])
+    names = engine.set_tree_nested(2, nested, col)
+    left, right, _ = O.flatten_tree(nested)
+    m = synth.unpack_rows(bits, N)
+    cols = np.asarray([col[n] for n in names])
+    ref = O.permute(left, right, m[:, cols], traits[0][cols].astype(np.uint8), P=P, seed=77, trait=2)
+    pairs, r, nd = engine.permute(2, P, seed=77)
+    assert np.array_equal(r, ref["r"]) and np.array_equal(pairs, ref["pairs"])
+    total = np.zeros(G, dtype=np.int64)
+    for rank in range(parts):
+        first, count = D.permutation_range(P, parts, rank)
+        pr, rr = engine.permute_range(2, first, count, seed=77)
+        assert np.array_equal(pr, pairs)
+        total += rr
+    assert np.array_equal(total, r)
+    idx = np.asarray([3, 0, 17], dtype=np.int64)
+    _, r_sub = engine.permute_range(2, 5, P - 5, seed=77, gene_idx=idx)
+    _, r_head = engine.permute_range(2, 0, 5, seed=77, gene_idx=idx)
+    assert np.array_equal(r_sub + r_head, r[idx])
