@@ -112,7 +112,10 @@ int sb_set_trait(sb_ctx *ctx, int32_t t, const uint64_t *value, const uint64_t *
  * before parents, root last; child >= 0 is an internal node index, child < 0 is
  * leaf id ~child (0 .. n_internal); leaf_to_col[leaf id] = isolate column in
  * the gene bitset.  Replaces the nested-list `tree` argument of
- * ConvertUPGMAtoPhyloTree (methods.py:1386).  Host pointers. */
+ * ConvertUPGMAtoPhyloTree (methods.py:1386).  Host pointers.
+ * Limit: at most 32 766 leaves (the DP keys hold pairs and supporting pairs in 28 bits).  Every binary tree up to
+ * that size is accepted whatever its shape: the compiled walk program (<= 21 374 ops, a balanced tree) and at least
+ * five label vectors fit the 62 KB constant pool; sb_set_tree itself rejects anything larger (SB_ERR_ARG). */
 int sb_set_tree(sb_ctx *ctx, int32_t t, const int32_t *left, const int32_t *right,
                 int32_t n_internal, const int32_t *leaf_to_col);
 

@@ -864,8 +864,8 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR
 
 // gene slots of this thread: (tile * NP + k) * tile_threads + tid  (coalesced per k)
 template <int NP>
-SB_DEV void walk_slots(const WalkArgs &A, const int32_t *list, int tile, int64_t (&s_idx)[NP], bool (&active)[NP],
-                                           int64_t (&sc)[NP], const uint32_t *(&gcol)[NP])
+SB_DEV void walk_slots(const WalkArgs &A, const int32_t *list, int tile, int32_t (&s_idx)[NP], bool (&active)[NP],
+                                           const uint32_t *(&gcol)[NP])
 {
     const int64_t S = A.S_dev ? (int64_t)*A.S_dev : A.S;
 #pragma unroll
@@ -873,9 +873,8 @@ SB_DEV void walk_slots(const WalkArgs &A, const int32_t *list, int tile, int64_t
         const int64_t li = ((int64_t)tile * NP + k) * A.tile_threads + threadIdx.x;   // position in the work list
         active[k] = li < S;
         const int64_t lc = active[k] ? li : (S - 1);   // idle lanes redo the last entry (no divergence)
-        s_idx[k] = list ? (int64_t)list[lc] : lc;
-        sc[k] = s_idx[k];
-        const int64_t gene = A.col_idx ? (int64_t)A.col_idx[sc[k]] : (A.gene_idx ? A.gene_idx[sc[k]] : sc[k]);
+        s_idx[k] = list ? list[lc] : (int32_t)lc;         // result slots are counted in 32 bits throughout
+        const int64_t gene = A.col_idx ? (int64_t)A.col_idx[s_idx[k]] : (A.gene_idx ? A.gene_idx[s_idx[k]] : (int64_t)s_idx[k]);
         gcol[k] = A.genesT + gene;
     }
 }
@@ -887,8 +886,8 @@ SB_KERNEL(__launch_bounds__(WALK_THREADS)) walk_pairs_kernel(const WalkArgs A)
     SB_SHARED_STACK(smem_stack);
     int *stk = smem_stack + threadIdx.x;
     constexpr int NP = WALK_NP;
-    int64_t s_idx[NP], sc[NP]; bool active[NP]; const uint32_t *gcol[NP];
-    walk_slots<NP>(A, A.slot_idx, blockIdx.x, s_idx, active, sc, gcol);
+    int32_t s_idx[NP]; bool active[NP]; const uint32_t *gcol[NP];
+    walk_slots<NP>(A, A.slot_idx, blockIdx.x, s_idx, active, gcol);
     const int K = 1 << A.shift;
     Bonus32 b32[NP];
     Bonus16 b16[WALK_NPAIR];
@@ -910,9 +909,9 @@ SB_KERNEL(__launch_bounds__(WALK_THREADS)) walk_pairs_kernel(const WalkArgs A)
             if (acc[k].a[c] >= 0) anti = max(anti, acc[k].a[c] & mask);
         }
         if (active[k]) {
-            A.pairs[s_idx[k] * 3 + 0] = total;
-            A.pairs[s_idx[k] * 3 + 1] = pro;
-            A.pairs[s_idx[k] * 3 + 2] = anti;
+            A.pairs[(int64_t)s_idx[k] * 3 + 0] = total;
+            A.pairs[(int64_t)s_idx[k] * 3 + 1] = pro;
+            A.pairs[(int64_t)s_idx[k] * 3 + 2] = anti;
         }
     }
 }
@@ -940,11 +939,11 @@ SB_KERNEL(__launch_bounds__(WALK_THREADS, SB_WALK_MINBLOCKS)) walk_permute_kerne
     const int perm0 = chunk * A.ppi;
     const int rows = min(A.ppi, A.n_perms - perm0);
     if (A.S_dev && (int64_t)blockIdx.x * NP * A.tile_threads >= (int64_t)*A.S_dev) return;   // grid sized for an upper bound
-    int64_t s_idx[NP], sc[NP]; bool active[NP]; const uint32_t *gcol[NP];
-    walk_slots<NP>(A, TRANSPOSED ? nullptr : A.slot_idx, blockIdx.x, s_idx, active, sc, gcol);   // transposed: slot_idx lists the rows
+    int32_t s_idx[NP]; bool active[NP]; const uint32_t *gcol[NP];
+    walk_slots<NP>(A, TRANSPOSED ? nullptr : A.slot_idx, blockIdx.x, s_idx, active, gcol);   // transposed: slot_idx lists the rows
     const int K = 1 << A.shift;
     const int mask = K - 1;
-    long long u_total[NP], u_stat[NP]; bool use_pro[NP]; uint32_t hits[NP];
+    int u_total[NP], u_stat[NP]; bool use_pro[NP]; uint32_t hits[NP];      // unpermuted counts (<= 16 383)
     Bonus32 b32[NP];
     Bonus16 b16[WALK_NPAIR];
     // tested side and pair bonuses of "gene" k from the unpermuted counts at un: the statistic a gene is tested on
@@ -966,7 +965,7 @@ SB_KERNEL(__launch_bounds__(WALK_THREADS, SB_WALK_MINBLOCKS)) walk_permute_kerne
     for (int k = 0; k < NP; ++k) hits[k] = 0;
     if constexpr (!TRANSPOSED) {
 #pragma unroll
-        for (int k = 0; k < NP; ++k) side(k, A.unperm + sc[k] * 3);
+        for (int k = 0; k < NP; ++k) side(k, A.unperm + (int64_t)s_idx[k] * 3);
         pack_bonus();
     }
     for (int r = 0; r < rows; r += NLAB) {
@@ -990,14 +989,14 @@ SB_KERNEL(__launch_bounds__(WALK_THREADS, SB_WALK_MINBLOCKS)) walk_permute_kerne
 #pragma unroll
             for (int k = 0; k < NP; ++k) {
                 // root: Total and the statistic are independent maxima over the five states (classes.py:246-249)
-                const long long total = max5(acc[l * NP + k].p) >> A.shift;
+                const int total = max5(acc[l * NP + k].p) >> A.shift;
                 int stat = -1;
 #pragma unroll
                 for (int c = 0; c < 5; ++c)
                     if (acc[l * NP + k].p[c] >= 0) stat = max(stat, acc[l * NP + k].p[c] & mask);
-                const bool hit = (long long)stat * u_total[k] >= u_stat[k] * total;   // methods.py:1353-1355
+                const bool hit = (long long)stat * u_total[k] >= (long long)u_stat[k] * total;   // methods.py:1353-1355
                 if constexpr (TRANSPOSED) {
-                    if (active[k]) A.hits[row_slot * A.S_total + s_idx[k]] = (uint8_t)hit;
+                    if (active[k]) A.hits[row_slot * A.S_total + (int64_t)s_idx[k]] = (uint8_t)hit;
                 } else {
                     if (hit) hits[k] |= (1u << (r + l));
                 }
@@ -1007,7 +1006,7 @@ SB_KERNEL(__launch_bounds__(WALK_THREADS, SB_WALK_MINBLOCKS)) walk_permute_kerne
     if constexpr (!TRANSPOSED) {
 #pragma unroll
         for (int k = 0; k < NP; ++k)
-            if (active[k]) A.hits[(int64_t)(A.chunk_base + chunk) * A.S_total + s_idx[k]] = (uint8_t)hits[k];
+            if (active[k]) A.hits[(int64_t)(A.chunk_base + chunk) * A.S_total + (int64_t)s_idx[k]] = (uint8_t)hits[k];
     }
 }
 

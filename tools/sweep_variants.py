@@ -19,14 +19,14 @@ VARIANTS = {
     # round-2 sessions (profiles/r2_sweep.txt).  r2a: prmt 1.03x, minblocks6 1.03x, everything else <= 1.00x (two
     # labellings in lockstep 0.88-0.97x despite -20 % instructions: 12 warps per SM do not hide the ALU latency).
     # r2c (whole-wave launch planning in place, PRMT masks the default): 192 threads x 4 blocks per SM 1.09x,
-    # 128 x 7 1.05x, 256 x 3 1.05x, 128 x 6 1.04x, without PRMT 0.97x.  192 x 4 is the default now.
+    # 128 x 7 1.05x, 256 x 3 1.05x, 128 x 6 1.04x, without PRMT 0.97x.  r2d (192 x 4 the default): 192 x 5 0.97x,
+    # 160 x 6 0.97x, 224 x 4 0.93x, 384 x 2 1.01x, 6 genes per thread 0.77x.  Last check, after the prologue lost
+    # 12 registers of live state:
     "t128_mb5": "-DSB_WALK_THREADS=128 -DSB_WALK_MINBLOCKS=5",     # the round-1 shape
     "t192_mb5": "-DSB_WALK_THREADS=192 -DSB_WALK_MINBLOCKS=5",
     "t160_mb6": "-DSB_WALK_THREADS=160 -DSB_WALK_MINBLOCKS=6",
-    "t224_mb4": "-DSB_WALK_THREADS=224 -DSB_WALK_MINBLOCKS=4",
-    "t256_mb4": "-DSB_WALK_THREADS=256 -DSB_WALK_MINBLOCKS=4",
-    "t384_mb2": "-DSB_WALK_THREADS=384 -DSB_WALK_MINBLOCKS=2",
-    "t192_mb4_npair3": "-DSB_WALK_NPAIR=3",
+    "t160_mb5": "-DSB_WALK_THREADS=160 -DSB_WALK_MINBLOCKS=5",
+    "t224_mb3": "-DSB_WALK_THREADS=224 -DSB_WALK_MINBLOCKS=3",
 }
 
 
