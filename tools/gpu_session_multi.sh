@@ -30,6 +30,8 @@ if [ "$ngpu" -ge 8 ]; then
     step 400 bench_c4_n8.log bash tools/run_bench_n.sh 8 29611 --workload c4 --steps 2 --warmup 3 --no-cpu-baseline
     step 400 bench_c5_n8.log bash tools/run_bench_n.sh 8 29612 --workload c5 --steps 3 --warmup 3 --no-cpu-baseline
     step 400 bench_c3_n8.log bash tools/run_bench_n.sh 8 29613 --workload c3 --steps 5 --warmup 3 --no-cpu-baseline
+    # the split the planner did NOT choose for the north_star job (6 250-gene shards), for comparison
+    step 400 bench_north_star_n8_genes.log bash tools/run_bench_n.sh 8 29614 --split genes --steps 5 --warmup 3 --no-cpu-baseline
 fi
 grep -h '^{' "$out"/bench_*.log > "$out/bench_lines.json" 2>/dev/null
 echo "== done" | tee -a "$out/session.log"
