@@ -531,9 +531,12 @@ def run_ours(a):
                 "peak_source": peak_src, "ms_per_launch": k5_ms, "launches_per_step": launches_per_step,
                 "note": "K5 is integer-issue bound by construction (%.2f algorithmic bytes per test): this HBM fraction "
                         "says nothing about it, `issue` below is the utilisation figure.  traffic = dram read + write "
-                        "bytes of one launch inside a running step (ncu --cache-control none, %s): the label vectors, "
-                        "the hit flags and what L2 evicts of the %d MB walk-order gene matrix and the threads' 32-bit "
-                        "DP stacks" % (bytes_per_test, prof.get("source", "profiles/"), int(g_loc * W * 8 / 1e6))}
+                        "bytes of one full-size launch inside a running step (ncu --cache-control none, %s).  It is far "
+                        "above the algorithmic bytes and it is not re-reads of the input: the %d MB walk-order gene matrix "
+                        "stays in L2; what goes to DRAM is the threads' local-memory DP stack (32-bit entries of the "
+                        "tree's spine + register spills, 768 B per thread, rewritten by every block), which L1 / L2 write "
+                        "back.  At ~40 GB/s it is 0.6 %% of the HBM peak and costs the kernel nothing"
+                        % (bytes_per_test, prof.get("source", "profiles/"), int(g_loc * W * 8 / 1e6))}
     # the utilisation figure of K5: warp instructions it executes (ncu smsp__inst_executed.sum, profiles/) per second
     # against the SM's issue capacity (4 warp instructions per clock per SM) at the clock sampled in this run
     wi_file = _profile_json("k5_warp_instructions.json")
