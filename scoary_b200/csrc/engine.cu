@@ -815,10 +815,26 @@ int launch_permute(sb_ctx *ctx, int32_t t, const int64_t *d_gene_idx, int64_t S,
     // threads = genes (the default) or threads = labellings: whichever shape fills the GPU better
     bool transposed = false;
     if (sb::WALK_NLAB == 1 && !sb::WALK_PADDED && ctx->permute_mode != 1) {
-        const double f_genes = fill_fraction(S, std::min(label_cap, P), slots);
-        const double f_perms = fill_fraction(early_stop ? std::min<int64_t>(P, (int64_t)sb::WALK_THREADS * sb::WALK_NP) : P,
-                                             std::min<int64_t>(label_cap, S), slots);
-        transposed = ctx->permute_mode == 2 || f_perms > (early_stop ? 3.0 : 1.5) * f_genes;
+        if (!early_stop) {
+            const double f_genes = fill_fraction(S, std::min(label_cap, P), slots);
+            const double f_perms = fill_fraction(P, std::min<int64_t>(label_cap, S), slots);
+            transposed = f_perms > 1.5 * f_genes;
+        } else {
+            // Reference-rule mode, estimated times (profiles/r2_few_genes_probe.jsonl, r2_rule_probe.txt): threads = genes
+            // pays 64 labellings for every gene and then ~(P - 64) / 74 sequential rounds of at least one wave of blocks
+            // each; threads = labellings pays the first tile of labellings for every gene and the rest for the genes
+            // still running (unknown in advance: half of them assumed).
+            const double rate = 4.0e5 * 5000.0 / std::max(64, s.n_leaves);        // walks per ms at this tree size
+            const double per_tile = (double)sb::WALK_THREADS * sb::WALK_NP, frac = 0.5;
+            const int n_round = std::max(1, std::min(label_cap, 74));
+            const double t_wave = slots * per_tile / rate;
+            const double waves = std::max(1.0, std::ceil(frac * S / per_tile) * n_round / slots);
+            const double t_genes = S * 64.0 / rate + std::ceil(std::max(0, P - 64) / (double)n_round) * t_wave * waves;
+            const double first = std::min<double>(P, per_tile);
+            const double t_perms = S * first / rate + frac * S * (P - first) / rate + 0.5;
+            transposed = t_perms < t_genes;
+        }
+        transposed = transposed || ctx->permute_mode == 2;
     }
     ctx->stats.calls_transposed += transposed ? 1 : 0;
     if (transposed)
