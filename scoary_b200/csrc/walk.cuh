@@ -109,13 +109,13 @@ __device__ __forceinline__ unsigned sb_sign_mask2(unsigned x)
 #ifndef SB_WALK_MINBLOCKS
 #define SB_WALK_MINBLOCKS 4
 #endif
-// Experimental (tools/sweep_variants.py, not measured yet): gene windows kept bit-reversed, so that the
+// Gene windows are kept bit-reversed (measured 1.03x in round 2, profiles/r2_sweep.txt; 0 = the round-1 form), so that the
 // next leaf sits in bit 15 / bit 31 and its half-word mask is ONE PRMT (sign replication) instead of
 // LOP3 + IMAD; a consumed leaf is a left shift.  Same results; verified through the host emulation.
 #ifndef SB_WALK_PRMT
 #define SB_WALK_PRMT 1
 #endif
-// Experimental (tools/sweep_variants.py, not measured yet): the host compiler pads the leaf stream so that no op
+// Sweep variant (measured 0.98 - 1.01x in round 2, profiles/r2_sweep.txt: not adopted): the host compiler pads the leaf stream so that no op
 // ever crosses a 16-leaf window (pad positions carry gene bit 0 and no label; long leaf runs are split at the
 // boundaries).  The kernels then have no general path: an op that does not fit the rest of the window simply opens
 // the next one.  Changes the stream layout, so engine.cu (compile_tree, sb_set_tree) honours the same switch.
@@ -541,7 +541,8 @@ struct WalkArgs {
 #endif
 constexpr int WALK_NPAIR = SB_WALK_NPAIR;   // gene pairs per thread
 constexpr int WALK_NP = 2 * WALK_NPAIR;     // genes per thread
-// Experimental (tools/sweep_variants.py, not measured yet): K5 walks SB_WALK_NLAB labellings of its genes in
+// Sweep variant (measured 0.88 - 0.97x in round 2, profiles/r2_sweep.txt: 20 % fewer instructions, but 165 registers
+// leave 12 warps per SM -- not adopted): K5 walks SB_WALK_NLAB labellings of its genes in
 // lockstep.  The program decode, the leaf-stream bookkeeping and the gene-bit masks are then shared by the
 // labellings; only the DP arithmetic is per labelling (tools/k5_model.py counts the instructions).
 #ifndef SB_WALK_NLAB
