@@ -240,8 +240,12 @@ def Csv_to_dic_Roary(genefile, delimiter, grabcols, startcol=14, allowed_isolate
 
 
 def _popcount_rows(bits):
-    b = np.ascontiguousarray(bits).view(np.uint8)
-    return np.unpackbits(b, axis=1).sum(axis=1, dtype=np.int64) if b.size else np.zeros(bits.shape[0], np.int64)
+    b = np.ascontiguousarray(bits, dtype=np.uint64)
+    if not b.size:
+        return np.zeros(b.shape[0], np.int64)
+    if hasattr(np, "bitwise_count"):                       # NumPy >= 2.0
+        return np.bitwise_count(b).sum(axis=1, dtype=np.int64)
+    return np.unpackbits(b.view(np.uint8), axis=1).sum(axis=1, dtype=np.int64)
 
 
 def _native_gene_table(path, delimiter, roaryfile, genecol, nugcol, anncol, grabcols, header, src_cols, strains):
@@ -254,11 +258,13 @@ def _native_gene_table(path, delimiter, roaryfile, genecol, nugcol, anncol, grab
     with open(path, "rb") as fh:
         buf = fh.read()
     delim = delimiter.encode()[:1]
-    n = lib.sb_csv_row_starts(buf, len(buf), delim, None, 0, None)
+    # one scan: a row ends at a line terminator, so the terminators bound the number of rows (a memchr-speed count
+    # instead of a second pass of the quote-aware scanner over a multi-gigabyte buffer)
+    starts = np.empty(buf.count(b"\n") + buf.count(b"\r") + 2, dtype=np.int64)
+    n = lib.sb_csv_row_starts(buf, len(buf), delim, starts.ctypes.data_as(ctypes.c_void_p), len(starts), None)
     if n < 0:
         sys.exit("CRITICAL: Could not read gene presence absence file.")
-    starts = np.empty(max(n, 1), dtype=np.int64)
-    lib.sb_csv_row_starts(buf, len(buf), delim, starts.ctypes.data_as(ctypes.c_void_p), n, None)
+    starts = starts[:max(n, 1)]
     W = eng.words_for(len(src_cols))
     bits = np.empty((n, W), dtype=np.uint64)
     lead = sorted(set([genecol, nugcol, anncol] + list(grabcols)))
