@@ -1615,20 +1615,6 @@ int sb_upgma(sb_ctx *ctx, int32_t *merges)
         // The N - 1 merge steps are four small kernels each (~20 000 launches at N = 5 000): one CUDA graph of
         // UPGMA_GRAPH_STEPS steps is captured once and replayed; the kernels read the step counter from device
         // memory and the steps past N - 1 in the last replay do nothing.
-        // Preferred: the whole loop in one cooperative launch (three grid-wide barriers per merge step).
-        bool persistent = false;
-        {
-            int coop = 0, per_sm = 0;
-            cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
-            if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sb::upgma_persistent_kernel, 256, 0) == cudaSuccess &&
-                per_sm >= 1) {
-                const int blocks = ctx->sm_count * std::min(per_sm, 2);
-                void *args[] = {(void *)&S};
-                persistent = cudaLaunchCooperativeKernel((void *)sb::upgma_persistent_kernel, dim3(blocks), dim3(256), args, 0,
-                                                         ctx->stream) == cudaSuccess;
-                if (!persistent) (void)cudaGetLastError();
-            }
-        }
         auto one_step = [&]() {
             sb::upgma_pick_kernel<<<1, 1024, 0, ctx->stream>>>(S);
             sb::upgma_update_kernel<<<(N + 255) / 256, 256, 0, ctx->stream>>>(S);
@@ -1638,15 +1624,13 @@ int sb_upgma(sb_ctx *ctx, int32_t *merges)
         cudaGraph_t graph = nullptr;
         cudaGraphExec_t exec = nullptr;
         bool graphed = false;
-        if (!persistent && N - 1 > sb::UPGMA_GRAPH_STEPS &&
+        if (N - 1 > sb::UPGMA_GRAPH_STEPS &&
             cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
             for (int k = 0; k < sb::UPGMA_GRAPH_STEPS; ++k) one_step();
             graphed = cudaStreamEndCapture(ctx->stream, &graph) == cudaSuccess && graph &&
                       cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
         }
-        if (persistent) {
-            // done: one launch
-        } else if (graphed) {
+        if (graphed) {
             for (int step = 0; step < N - 1; step += sb::UPGMA_GRAPH_STEPS) SB_TRY(cudaGraphLaunch(exec, ctx->stream));
         } else {
             (void)cudaGetLastError();
@@ -1655,7 +1639,7 @@ int sb_upgma(sb_ctx *ctx, int32_t *merges)
         SB_TRY(cudaStreamSynchronize(ctx->stream));
         if (exec) cudaGraphExecDestroy(exec);
         if (graph) cudaGraphDestroy(graph);
-        ctx->stats.kernel_launches += persistent ? 1 : 4LL * (N - 1);
+        ctx->stats.kernel_launches += 4LL * (N - 1);
     }
     SB_TRY(cudaGetLastError());
     SB_TRY(cudaMemcpyAsync(merges, S.merges, sizeof(int) * 2 * (size_t)(N - 1), cudaMemcpyDeviceToHost, ctx->stream));

@@ -13,8 +13,6 @@
 // Arithmetic is IEEE double with explicit round-to-nearest intrinsics (no FMA contraction), in
 // the reference's operation order, so the merge order -- and therefore the tree -- is identical.
 #pragma once
-#include <cooperative_groups.h>
-
 #include "common.cuh"
 
 namespace sb {
@@ -244,85 +242,6 @@ __global__ void upgma_finish_step_kernel(const UpgmaState S)
     S.size[j] = 0.0;
     S.alive[j] = 0;
     S.pick[2] += 1;
-}
-
-// ---- 3b. the whole merge loop in ONE cooperative launch (grid-wide barriers instead of ~4 (N - 1) kernel launches):
-// per step  pick (block 0) | barrier | update (all threads, k strided) | barrier | recompute the flagged row minima
-// (rows strided over the blocks) + bookkeeping | barrier.  Same arithmetic and the same tie-breaks as the kernels above
-// (they remain the fallback where a cooperative launch is not possible).
-__global__ void __launch_bounds__(256) upgma_persistent_kernel(const UpgmaState S)
-{
-    namespace cg = cooperative_groups;
-    cg::grid_group grid = cg::this_grid();
-    __shared__ double s_val[256];
-    __shared__ unsigned long long s_key[256];
-    __shared__ int s_row[256];
-    __shared__ int s_col[256];
-    const int N = S.N, tid = threadIdx.x;
-    for (int step = 0; step < N - 1; ++step) {
-        if (blockIdx.x == 0) {       // global argmin over the row minima by (value, morton(i, j))
-            double bv = UPGMA_BIG * 4.0;
-            unsigned long long bk = ~0ULL;
-            int br = -1;
-            for (int r = tid; r < N; r += 256) {
-                const double v = S.rowmin_val[r];
-                const unsigned long long k = morton_key((unsigned)r, (unsigned)S.rowmin_col[r]);
-                if (v < bv || (v == bv && k < bk)) { bv = v; bk = k; br = r; }
-            }
-            s_val[tid] = bv; s_key[tid] = bk; s_row[tid] = br;
-            __syncthreads();
-            for (int o = 128; o > 0; o >>= 1) {
-                if (tid < o) {
-                    const double v = s_val[tid + o];
-                    const unsigned long long k = s_key[tid + o];
-                    if (v < s_val[tid] || (v == s_val[tid] && k < s_key[tid])) {
-                        s_val[tid] = v; s_key[tid] = k; s_row[tid] = s_row[tid + o];
-                    }
-                }
-                __syncthreads();
-            }
-            if (tid == 0) {
-                const int i = s_row[0], j = S.rowmin_col[i];
-                S.pick[0] = i; S.pick[1] = j;
-                S.merges[2 * step] = i; S.merges[2 * step + 1] = j;
-            }
-        }
-        grid.sync();
-        const int i = S.pick[0], j = S.pick[1];
-        {
-            const double si = S.size[i], sj = S.size[j];
-            const double ns = __dadd_rn(si, sj);
-            for (int k = blockIdx.x * 256 + tid; k < N; k += gridDim.x * 256) {
-                double nd;
-                if (k == i) nd = UPGMA_BIG;
-                else if (!S.alive[k]) nd = 1.0;      // retired clusters: methods.py:687-688
-                else nd = __ddiv_rn(__dadd_rn(__dmul_rn(S.D[(int64_t)i * N + k], si), __dmul_rn(S.D[(int64_t)j * N + k], sj)), ns);
-                const double vi = (k == j) ? UPGMA_BIG : nd;
-                S.D[(int64_t)i * N + k] = vi;
-                S.D[(int64_t)k * N + i] = vi;
-                S.D[(int64_t)j * N + k] = UPGMA_BIG;
-                S.D[(int64_t)k * N + j] = UPGMA_BIG;
-                if (k == i || k == j) { S.redo[k] = 1; continue; }
-                const int mc = S.rowmin_col[k];
-                if (mc == i || mc == j) { S.redo[k] = 1; continue; }
-                const double mv = S.rowmin_val[k];
-                if (vi < mv || (vi == mv && i < mc)) { S.rowmin_val[k] = vi; S.rowmin_col[k] = i; }
-            }
-        }
-        grid.sync();
-        for (int r = blockIdx.x; r < N; r += gridDim.x) {
-            if (!S.redo[r]) continue;                // uniform per block
-            __syncthreads();                         // s_val / s_col of the previous row are no longer read
-            row_min_block(S, r, s_val, s_col);
-            if (tid == 0) { S.rowmin_val[r] = s_val[0]; S.rowmin_col[r] = s_col[0]; S.redo[r] = 0; }
-        }
-        if (blockIdx.x == 0 && tid == 0) {           // nothing in this phase reads size / alive
-            S.size[i] = __dadd_rn(S.size[i], S.size[j]);
-            S.size[j] = 0.0;
-            S.alive[j] = 0;
-        }
-        grid.sync();
-    }
 }
 
 }  // namespace sb
