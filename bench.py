@@ -22,6 +22,7 @@ genes under its own range of the labellings and the hit counts are summed in one
           kernel that needs 0.07 bytes per test) and `issue`, its real utilisation (executed warp instructions from
           ncu / issue slots); contract_int32 is the SURVEY 8(d) op-count ratio, labelled as not a bound
   fisher_pass, config1_fisher_only, config2_c3, reference_rule_mode : the other kernels / configs, one GPU only
+  cli_wall : the whole command line, file in -> results.csv out, at the C3 shape (tools/cli_wall.py), one GPU only
   cpu_baseline : the oracle's C port on this box's host cores, bounded sample (+ the Python reference's own timing,
           measured in the build container: it cannot travel to the GPU box)
 """
@@ -55,6 +56,7 @@ def parse_args():
     ap.add_argument("--split", default="auto", choices=["auto", "genes", "permutations"],
                     help="how N GPUs divide the job (auto: scoary_b200.distributed.split_for)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cli-wall", action="store_true", help="skip the command-line wall-clock sub-line (N = 1 only)")
     return ap.parse_args()
 
 
@@ -567,6 +569,21 @@ def run_ours(a):
         cpu = {"value": rate(x, y), "unit": "tests/s", "cores": threads, "kind": "port", "sample": sample,
                "python_reference": _profile_json("python_reference_timing.json") or None}
 
+    # the whole command line, file in -> results.csv out, at the C3 shape (tools/cli_wall.py in its own process, after
+    # every timed region); the C5-shaped run (4 GB of input) is quoted from profiles/
+    cli_wall = None
+    if world == 1 and not a.no_cli_wall and not a.no_cpu_baseline:
+        try:
+            res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "cli_wall.py"), "--shape", "c3"],
+                                 capture_output=True, text=True, timeout=600)
+            cli_wall = {"c3": json.loads([ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1]),
+                        "c5": _profile_json("r2_cli_wall_c5.json") or None,
+                        "note": "scoary_b200.methods.main on a synthetic Roary table, -p 1.0 -c I -e 1000: parse + pack, "
+                                "UPGMA tree, statistics, pairwise + permutations (reference-rule mode), result file; c3 "
+                                "measured in this run, c5 (1 000 000 x 2 000, 4 GB of CSV) from profiles/"}
+        except Exception as ex:      # the sub-line is informative only
+            cli_wall = {"error": str(ex)[:200]}
+
     line = {
         "metric": "gene-trait tests/sec (incl. permutations)", "value": value, "unit": "tests/s", "n_gpus": world,
         "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": dev_ms / a.steps, "higher_is_better": True,
@@ -591,7 +608,7 @@ def run_ours(a):
         "gpu_launches": int(st["kernel_launches"]),
         "clocks": clocks,
         "roofline": roofline, "contract_int32": contract, "fisher_pass": fisher, "reference_rule_mode": ref_rule,
-        "config1_fisher_only": c2, "config2_c3": c3,
+        "config1_fisher_only": c2, "config2_c3": c3, "cli_wall": cli_wall,
         "cpu_baseline": cpu,
         "kernel_ms": {k: st[k] for k in ("ms_fisher", "ms_shuffle", "ms_walk", "ms_permute", "ms_reduce")},
         "wall_s_timed_region": wall,
