@@ -307,7 +307,8 @@ def run_ours(a):
     e.set_genes_device(d_bits.data_ptr(), g_loc, N, W)
     for t in range(T):
         e.set_trait_vector(t, traits[t])
-        e.set_tree(t, left, right, leaf_cols)
+        if P > 0:
+            e.set_tree(t, left, right, leaf_cols)
     d_counts = torch.empty((T, g_loc, 4), dtype=torch.int32, device=dev)
     d_p = torch.empty((T, g_loc), dtype=torch.float64, device=dev)
     d_pairs = torch.zeros((T, g_loc, 3), dtype=torch.int32, device=dev)
@@ -396,8 +397,11 @@ def run_ours(a):
         h2d += bits_host.nbytes
         for t in range(T):
             e.set_trait_vector(t, traits[t])
-            e.set_tree(t, left, right, leaf_cols)
-            h2d += 2 * W * 8 + left.nbytes + right.nbytes + leaf_cols.nbytes
+            if P > 0:
+            h2d += 2 * W * 8
+            if P > 0:          # a Fisher-only job (C2) has no tree
+                e.set_tree(t, left, right, leaf_cols)
+                h2d += left.nbytes + right.nbytes + leaf_cols.nbytes
         t1 = time.perf_counter()
         c, p, _ = e.contingency_fisher_multi(0, T)
         d2h += c.nbytes + p.nbytes
@@ -457,6 +461,7 @@ def run_ours(a):
         e.set_genes_device(d_bits.data_ptr(), g_loc, N, W)
         for t in range(T):
             e.set_trait_vector(t, traits[t])
+            if P > 0:
             e.set_tree(t, left, right, leaf_cols)
         # reference-rule mode (second number): the reference's sequential early stop (methods.py:1360-1363)
         if P >= 32:
