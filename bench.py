@@ -397,7 +397,6 @@ def run_ours(a):
         h2d += bits_host.nbytes
         for t in range(T):
             e.set_trait_vector(t, traits[t])
-            if P > 0:
             h2d += 2 * W * 8
             if P > 0:          # a Fisher-only job (C2) has no tree
                 e.set_tree(t, left, right, leaf_cols)
@@ -462,7 +461,7 @@ def run_ours(a):
         for t in range(T):
             e.set_trait_vector(t, traits[t])
             if P > 0:
-            e.set_tree(t, left, right, leaf_cols)
+                e.set_tree(t, left, right, leaf_cols)
         # reference-rule mode (second number): the reference's sequential early stop (methods.py:1360-1363)
         if P >= 32:
             from scoary_b200.methods import early_stop_table
