@@ -14,6 +14,7 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -115,20 +116,64 @@ int64_t sb_csv_row_starts(const char *buf, int64_t len, char delimiter, int64_t 
     };
     p = next_row(p);   // skip the header row
     if (header_end) *header_end = p - buf;
-    int64_t n = 0;
-    while (p < e) {
-        const char *q = next_row(p);
-        // ignore rows that are empty
-        const char *t = p;
-        while (t < q && (*t == '\n' || *t == '\r')) ++t;
-        if (t < q) {
-            if (row_starts) {
-                if (n >= max_rows) return -1;
-                row_starts[n] = p - buf;
+    // rows of [from, to): appends their starts to `out` (if given), returns where the last row ended
+    auto scan = [&](const char *from, const char *to, std::vector<int64_t> *out, int64_t *count) {
+        const char *r = from;
+        while (r < to) {
+            const char *q = next_row(r);
+            const char *t = r;
+            while (t < q && (*t == '\n' || *t == '\r')) ++t;      // rows that are empty are ignored
+            if (t < q) {
+                if (out) out->push_back(r - buf);
+                ++*count;
             }
-            ++n;
+            r = q;
         }
-        p = q;
+        return r;
+    };
+    // Large files: the scan is split at line feeds and the pieces are scanned in parallel, each ASSUMING that its first
+    // byte starts a row.  Piece 0 starts at a true row start; if every piece ends exactly where the next one begins, all
+    // the assumptions were true (induction).  A line feed inside a quoted field breaks the chain -- then, or for small
+    // files, the plain sequential scan below decides.
+    int n_pieces = 1;
+#ifdef _OPENMP
+    if (e - p > (4 << 20)) n_pieces = (int)std::min<int64_t>(4 * (int64_t)omp_get_max_threads(), (e - p) >> 20);
+#endif
+    if (n_pieces > 1) {
+        std::vector<const char *> cut(n_pieces + 1);
+        cut[0] = p;
+        cut[n_pieces] = e;
+        for (int k = 1; k < n_pieces; ++k) {
+            const char *nominal = p + (e - p) / n_pieces * k;
+            const char *nl = (const char *)memchr(nominal, '\n', (size_t)(e - nominal));
+            cut[k] = nl ? nl + 1 : e;
+        }
+        std::vector<std::vector<int64_t>> starts(n_pieces);
+        std::vector<int64_t> counts(n_pieces, 0);
+        std::vector<const char *> ended(n_pieces);
+#pragma omp parallel for schedule(dynamic, 1)
+        for (int k = 0; k < n_pieces; ++k)
+            ended[k] = cut[k] < cut[k + 1] ? scan(cut[k], cut[k + 1], row_starts ? &starts[k] : nullptr, &counts[k]) : cut[k];
+        bool chain = true;
+        for (int k = 0; k < n_pieces; ++k) chain = chain && (ended[k] == cut[k + 1] || cut[k] >= cut[k + 1]);
+        if (chain) {
+            int64_t n = 0;
+            for (int k = 0; k < n_pieces; ++k) {
+                if (row_starts) {
+                    if (n + counts[k] > max_rows) return -1;
+                    if (counts[k]) memcpy(row_starts + n, starts[k].data(), sizeof(int64_t) * (size_t)counts[k]);
+                }
+                n += counts[k];
+            }
+            return n;
+        }
+    }
+    std::vector<int64_t> all;
+    int64_t n = 0;
+    scan(p, e, row_starts ? &all : nullptr, &n);
+    if (row_starts) {
+        if (n > max_rows) return -1;
+        if (n) memcpy(row_starts, all.data(), sizeof(int64_t) * (size_t)n);
     }
     return n;
 }

@@ -255,16 +255,21 @@ def _native_gene_table(path, delimiter, roaryfile, genecol, nugcol, anncol, grab
     import ctypes
     from . import _lib
     lib = _lib.load()
+    import mmap
     with open(path, "rb") as fh:
-        buf = fh.read()
+        try:        # mapped, not read: the parallel scan below is then also what pulls the file in
+            buf = mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ)
+            view = np.frombuffer(buf, dtype=np.uint8)
+            pbuf = ctypes.c_char_p(view.ctypes.data)
+        except (ValueError, OSError):       # empty file, or a file system without mmap
+            buf = fh.read()
+            pbuf = buf
     delim = delimiter.encode()[:1]
-    # one scan: a row ends at a line terminator, so the terminators bound the number of rows (a memchr-speed count
-    # instead of a second pass of the quote-aware scanner over a multi-gigabyte buffer)
-    starts = np.empty(buf.count(b"\n") + buf.count(b"\r") + 2, dtype=np.int64)
-    n = lib.sb_csv_row_starts(buf, len(buf), delim, starts.ctypes.data_as(ctypes.c_void_p), len(starts), None)
+    n = lib.sb_csv_row_starts(pbuf, len(buf), delim, None, 0, None)        # count, then fill: the scan runs in parallel pieces
     if n < 0:
         sys.exit("CRITICAL: Could not read gene presence absence file.")
-    starts = starts[:max(n, 1)]
+    starts = np.empty(max(n, 1), dtype=np.int64)
+    lib.sb_csv_row_starts(pbuf, len(buf), delim, starts.ctypes.data_as(ctypes.c_void_p), n, None)
     W = eng.words_for(len(src_cols))
     bits = np.empty((n, W), dtype=np.uint64)
     lead = sorted(set([genecol, nugcol, anncol] + list(grabcols)))
@@ -272,7 +277,7 @@ def _native_gene_table(path, delimiter, roaryfile, genecol, nugcol, anncol, grab
     keep_arr = np.asarray(src_cols, dtype=np.int32)
     ranges = np.empty((n, len(lead), 2), dtype=np.int64)
     nfields = np.empty(max(n, 1), dtype=np.int32)
-    rc = lib.sb_csv_pack_rows(buf, len(buf), delim, starts.ctypes.data_as(ctypes.c_void_p), n,
+    rc = lib.sb_csv_pack_rows(pbuf, len(buf), delim, starts.ctypes.data_as(ctypes.c_void_p), n,
                               keep_arr.ctypes.data_as(ctypes.c_void_p), len(src_cols),
                               bits.ctypes.data_as(ctypes.c_void_p), W, lead_arr.ctypes.data_as(ctypes.c_void_p),
                               len(lead), ranges.ctypes.data_as(ctypes.c_void_p), nfields.ctypes.data_as(ctypes.c_void_p))

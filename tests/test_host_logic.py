@@ -264,6 +264,34 @@ def test_native_csv_packer_embedded_quotes_and_ragged_rows(tmp_path, monkeypatch
     monkeypatch.delenv("SCOARY_B200_PY_CSV", raising=False)
 
 
+def test_native_csv_row_scan_in_parallel_pieces(tmp_path, monkeypatch):
+    """Files above 4 MB are scanned in pieces cut at line feeds, each piece assuming that it starts a row; a line feed
+    inside a quoted cell breaks the chain of pieces and the sequential scan decides.  Both ways: the csv module's table."""
+    import csv as _csv
+    N, G = 1000, 3200                                              # ~6.5 MB
+    header = ",".join('"%s"' % c for c in M.ROARY_COLUMNS[:14]) + "," + ",".join("I%04d" % j for j in range(N))
+    rng = np.random.default_rng(8)
+    cells = np.where(rng.random((G, N)) < 0.4, "1", "0")
+    for variant in ("plain", "embedded"):
+        path = str(tmp_path / (variant + ".csv"))
+        with open(path, "w", newline="") as fh:
+            fh.write(header + "\n")
+            for g in range(G):
+                ann = "annot %d" % g
+                if variant == "embedded" and g % 97 == 5:
+                    ann = '"two\nlines, %d"' % g                   # every piece of the scan meets a few of these
+                fh.write('g%d,,%s,1,2,3,4,5,6,7,8,9,10,11,' % (g, ann) + ",".join(cells[g]) + "\n")
+        assert os.path.getsize(path) > (4 << 20)
+        monkeypatch.delenv("SCOARY_B200_PY_CSV", raising=False)
+        with open(path) as fh:
+            a = M.Csv_to_dic_Roary(fh, ",", [], startcol=14)["Roarydic"]
+        with open(path, newline="") as fh:
+            rows = list(_csv.reader(fh, skipinitialspace=True))[1:]
+        assert len(rows) == G and a.names == [r[0] for r in rows] and a.annotation == [r[2] for r in rows]
+        want = np.asarray([[c == "1" for c in r[14:]] for r in rows], dtype=np.uint8)
+        assert np.array_equal(a.matrix, want)
+
+
 @pytest.mark.parametrize("name,types", [("Example", None), ("generated", None), ("generated", "snp,del")])
 def test_vcf2scoary_matches_reference_converter(name, types, tmp_path):
     """same output file as scoary/vcf2scoary.py (goldens written by the reference),
