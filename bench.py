@@ -235,7 +235,7 @@ def run_reference(a):
 
 
 # ----------------------------------------------------------------------------- GPU arm
-def rank0_epilogue(e, p, counts, device_min=100000):
+def rank0_epilogue(e, p, counts, device_min=None):
     """What rank 0 does with the gathered vector before results can be written: skip rule, Bonferroni,
     Benjamini-Hochberg, p-sort (methods.py:804-814, :900-925, :1448-1454) -- the product's own code path
     (scoary_b200.methods.adjust_pvalues: device epilogue for large vectors, NumPy below)."""
