@@ -147,8 +147,8 @@ def split_for(G, P, world, per_tile=768, min_tiles=64, min_perms=64):
     """How N GPUs split an EXHAUSTIVE job: by genes (the reference's own fan-out, methods.py:1076-1097) while a shard is
     still many thread tiles (C5: 163 per GPU), else by permutations -- every GPU walks all genes under its own range of
     the labellings, so launches stay as large as on one GPU, and the hit counts are summed.  Measured on the north_star
-    job: gene shards of 25 000 / 6 250 genes scale 1.95x / 6.60x on 2 / 8 GPUs, permutation ranges 3.98x / 7.90x on
-    4 / 8 (profiles/r2_summary.md); what the permutation split repeats per GPU is one Fisher pass and one unpermuted
+    job: gene shards of 25 000 / 6 250 genes scale 1.95x / 6.60x on 2 / 8 GPUs, permutation ranges 2.00x / 3.98x / 7.90x on
+    2 / 4 / 8 (profiles/r2_summary.md); what the permutation split repeats per GPU is one Fisher pass and one unpermuted
     walk per gene, i.e. 1 / (P / N) of its work."""
     if world > 1 and G / world < min_tiles * per_tile and P // world >= min_perms:
         return "permutations"

@@ -206,9 +206,10 @@ def Csv_to_dic_Roary(genefile, delimiter, grabcols, startcol=14, allowed_isolate
             opened.close()
         s = _popcount_rows(table.bits)
         variable = (s > 0) & (s < len(strain_names_allowed))
-        zero_ones = None
+        # small tables: the matrix itself; large ones: the same cells, unpacked only if somebody asks for them
+        zero_ones = LazyZeroOnes(table, np.flatnonzero(variable))
         if int(variable.sum()) * len(strain_names_allowed) <= 200_000_000:
-            zero_ones = np.ascontiguousarray(table.rows_matrix(np.flatnonzero(variable)).T)
+            zero_ones = np.asarray(zero_ones)
         return {"Roarydic": table, "Zero_ones_matrix": zero_ones, "Strains": strain_names_allowed,
                 "Extracols": extracolstoprint, "Firstcolnames": firstcolnames}
     names, nugn, ann, rows = [], [], [], []
@@ -237,6 +238,35 @@ def Csv_to_dic_Roary(genefile, delimiter, grabcols, startcol=14, allowed_isolate
     zero_ones = np.ascontiguousarray(matrix[variable].T)              # isolates x variable genes
     return {"Roarydic": table, "Zero_ones_matrix": zero_ones, "Strains": strain_names_allowed,
             "Extracols": extracolstoprint, "Firstcolnames": firstcolnames}
+
+
+class LazyZeroOnes:
+    """The reference's Zero_ones_matrix (isolates x variable genes, uint8; scoary/methods.py:496-497, the input of
+    CreateTriangularDistanceMatrix) for tables too large to unpack up front: shape and len are known at once, the
+    cells are unpacked from the bitset rows on first use (np.asarray(m), m[i], iteration)."""
+
+    def __init__(self, table, rows):
+        self._table, self._rows, self._m = table, np.asarray(rows, dtype=np.int64), None
+        self.shape = (len(table.strains), len(self._rows))
+        self.dtype = np.dtype(np.uint8)
+
+    def _cells(self):
+        if self._m is None:
+            self._m = np.ascontiguousarray(self._table.rows_matrix(self._rows).T)
+        return self._m
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __array__(self, dtype=None, copy=None):
+        m = self._cells()
+        return m if dtype is None else m.astype(dtype)
+
+    def __getitem__(self, key):
+        return self._cells()[key]
+
+    def __iter__(self):
+        return iter(self._cells())
 
 
 def _popcount_rows(bits):
@@ -1100,7 +1130,10 @@ def main(**kwargs):
                 log.info("Reading variants from the VCF file")
                 from . import vcf2scoary
                 table = vcf2scoary.vcf_to_table(args.genes, "ALL", allowed)
-                parsed = {"Roarydic": table, "Zero_ones_matrix": None, "Strains": table.strains, "Extracols": [],
+                pc = _popcount_rows(table.bits)
+                parsed = {"Roarydic": table,
+                          "Zero_ones_matrix": LazyZeroOnes(table, np.flatnonzero((pc > 0) & (pc < len(table.strains)))),
+                          "Strains": table.strains, "Extracols": [],
                           "Firstcolnames": ["#CHROM", "POS", "ID"]}
             else:
                 log.info("Reading gene presence absence file")
