@@ -493,3 +493,16 @@ def test_cli_edge_cases_found_by_the_fuzzer(tmp_path, fake_engine):
     for f in ("perfect", "allzero", "withNA", "mixed"):
         assert _read(os.path.join(out, f + ".results.csv")) == _read(os.path.join(edir, f + ".results.csv")), f
     assert _read(os.path.join(out, "Tree.nwk")) == _read(os.path.join(edir, "Tree.nwk"))
+
+
+def test_lazy_zero_ones_matrix_matches_the_unpacked_cells():
+    """Zero_ones_matrix of large tables / VCF input (reference: methods.py:496-497) is unpacked on first use only."""
+    from scoary_b200 import methods as M
+    rng = np.random.default_rng(5)
+    cells = (rng.random((40, 70)) < 0.4).astype(np.uint8)                 # genes x isolates
+    table = M.GeneTable([f"g{i}" for i in range(40)], [""] * 40, [""] * 40, [f"s{j}" for j in range(70)], matrix=cells)
+    rows = [3, 7, 8, 30]
+    z = M.LazyZeroOnes(table, rows)
+    assert z.shape == (70, 4) and len(z) == 70 and z._m is None
+    assert np.array_equal(np.asarray(z), cells[rows].T)
+    assert np.array_equal(z[5], cells[rows, 5]) and np.array_equal(np.stack(list(z)), cells[rows].T)
