@@ -226,7 +226,7 @@ bool pad_stream(Program &prog, std::string &err)
         room -= n;
     };
     for (const uint16_t op : prog.ops) {
-        const int type = op & 15, cnt = op >> sb::OP_TYPE_BITS;
+        const int type = op & sb::OP_TYPE_MASK, cnt = op >> sb::OP_TYPE_BITS;
         const bool cherry = type == sb::OP_CHERRY_A16 || type == sb::OP_PUSH_CHERRY_A16 || type == sb::OP_CHERRY_B16 ||
                             type == sb::OP_CHERRY_B16_MERGE;
         if (cherry) {
@@ -452,6 +452,7 @@ int ensure_lut(sb_ctx *ctx, int32_t n)
 int set_genes_common(sb_ctx *ctx, int64_t G, int32_t N, int32_t W)
 {
     if (G <= 0 || N <= 0) return fail(ctx, SB_ERR_ARG, "sb_set_genes: G and N must be positive");
+    if (G > (int64_t)0x7fffff00) return fail(ctx, SB_ERR_ARG, "sb_set_genes: at most 2^31 - 256 gene rows per context");
     if (W < (N + 63) / 64 || (W & 1)) return fail(ctx, SB_ERR_ARG, "sb_set_genes: W must be even and >= ceil(N/64)");
     ctx->d_genes = nullptr;
     ctx->own_genes = false;

@@ -253,22 +253,25 @@ constexpr int walk_label_base(int n_ops) { return ((n_ops + 1) / 2 + 3) / 4 * 4;
 // per register, 16-bit keys), legal while the subtree has <= WALK_LIM16 leaves; "32" ops work
 // on the per-gene 32-bit accumulator A32.  The host compiler (engine.cu) switches mode with
 // WIDEN_A and the *W merge forms where a subtree outgrows 16 bits.
-// The most frequent ops of a typical tree are numbered so that the interpreter recognises each with
-// one bit test on the op word before it falls back to a jump table: B cherries = 2 | merge,
-// A pushes / cherries = 4 | push | 2 * cherry.
+// The ops are numbered so that the interpreter finds its way with ONE single-bit test per level (a uniform
+// LOP3 that sets the predicate, then the branch), most frequent first: bit 2 = B cherries (| 2: merge),
+// bit 3 = A pushes / cherries (| 32: push, | 2: cherry), bit 4 = the rare 32-bit ops (a jump table on bits 0, 1
+// and 5; bits 2 and 3 stay clear), else bit 5 = pops, bit 1 = single leaves.  (Compares of the whole type
+// field ended up in the compiler's jump table, 12 instructions before a pop or a leaf run started; and a test of
+// bit 0 compiles to LOP3 + ISETP + branch, so no frequent test uses it.)
 constexpr int OP_END = 0,
-              OP_LEAF_A16 = 1,
-              OP_CHERRY_B16 = 2,        // B16 <- cherry, then `count` leaf updates
-              OP_CHERRY_B16_MERGE = 3,  // as OP_CHERRY_B16, then A16 <- combine(A16, B16)
-              OP_PUSH16 = 5,            // spill A16 to the stack
-              OP_CHERRY_A16 = 6,        // A16 <- cherry, then `count` leaf updates
-              OP_PUSH_CHERRY_A16 = 7,   // push A16 first, then as OP_CHERRY_A16
-              OP_MERGE_POP16 = 8,
-              OP_WIDEN_A = 9, OP_LEAF_A32 = 10, OP_MERGE_A32_B16 = 11, OP_PUSH32 = 12, OP_MERGE_POP32 = 13,
-              OP_MERGE_POPW = 14;
+              OP_MERGE_POP16 = 32,
+              OP_LEAF_A16 = 2,
+              OP_CHERRY_B16 = 4,        // B16 <- cherry, then `count` leaf updates
+              OP_CHERRY_B16_MERGE = 6,  // as OP_CHERRY_B16, then A16 <- combine(A16, B16)
+              OP_PUSH16 = 40,           // spill A16 to the stack
+              OP_CHERRY_A16 = 10,       // A16 <- cherry, then `count` leaf updates
+              OP_PUSH_CHERRY_A16 = 42,  // push A16 first, then as OP_CHERRY_A16
+              OP_WIDEN_A = 16, OP_LEAF_A32 = 17, OP_MERGE_A32_B16 = 18, OP_PUSH32 = 19, OP_MERGE_POP32 = 48,
+              OP_MERGE_POPW = 49;
 // raw (pre-fusion) steps used only by the host compiler (never stored in a program)
-constexpr int RAW_LEAF_B16 = 16, RAW_MERGE_AB16 = 17;
-constexpr int OP_TYPE_BITS = 4, OP_MAX_COUNT = 4095;
+constexpr int RAW_LEAF_B16 = 64, RAW_MERGE_AB16 = 65;
+constexpr int OP_TYPE_BITS = 6, OP_TYPE_MASK = (1 << OP_TYPE_BITS) - 1, OP_MAX_COUNT = 1023;
 constexpr int PERMS_PER_ITEM_MAX = 4;      // labellings walked per block: 4, 2 or 1 (one byte of hit flags per gene)
 // 16-bit keys: (pairs << 6) + x with pairs, x <= 63  ->  subtrees of at most 127 leaves.
 // Unreachable = -16384 (+ drift < 4096), so valid + unreachable < 0 and unreachable + unreachable
@@ -509,6 +512,31 @@ SB_DEV void walk_widen(const WalkState16 &s, WalkState &g0, WalkState &g1, int s
     }
 }
 
+// The packed accumulator A16 and the 32-bit accumulator of a pair's first gene are never live at the same time
+// (WIDEN_A turns one into the other), so they share their registers: in 32-bit mode a16[s] holds the keys of gene 2s
+// bit for bit and only the second gene needs registers of its own (10 fewer live registers in the interpreter loop).
+template <bool DUAL>
+SB_DEV WalkState as_state32(const WalkState16 &h)
+{
+    WalkState w;
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+        w.p[c] = (int)h.p[c];
+        if constexpr (DUAL) w.a[c] = (int)h.a[c];
+    }
+    return w;
+}
+
+template <bool DUAL>
+SB_DEV void put_state32(WalkState16 &h, const WalkState &w)
+{
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+        h.p[c] = (unsigned)w.p[c];
+        if constexpr (DUAL) h.a[c] = (unsigned)w.a[c];
+    }
+}
+
 struct WalkArgs {
     const uint32_t *genesT;    // [W32p][Gs]
     int64_t Gs;
@@ -551,13 +579,13 @@ constexpr int WALK_NP = 2 * WALK_NPAIR;     // genes per thread
 constexpr int WALK_NLAB = SB_WALK_NLAB;
 
 // NP = 2 * NPAIR genes x NLAB labellings: simultaneous tree walks of this thread's genes under the
-// labellings at c_pool[lab_off[l] ..].  gcol[k] points at gene k's column of genesT; genes 2q and 2q+1
+// labellings at c_pool[lab_off[l] ..].  gcol[k] is gene k's column of genesT (an index: four 64-bit pointers were 8 registers); genes 2q and 2q+1
 // share the packed accumulators of pair q; state index s = l * NPAIR + q (32-bit: l * NP + k).  Every branch is on block-uniform data (the program and
 // the label bits); per-gene data only feeds selects.  The program always ends in 32-bit mode.
 // Stack entries take EW = 10 (DUAL) or 5 words: per gene pair in the packed shared-memory stack, per gene in the
 // 32-bit local-memory stack (WALK_STACK32).
 template <int NPAIR, int NLAB, bool DUAL>
-SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR], const int (&lab_off)[NLAB],
+SB_DEV void walk_tree(const WalkArgs &A, const uint32_t (&gcol)[2 * NPAIR], const int (&lab_off)[NLAB],
                                           int *stk, WalkState (&acc)[NLAB * 2 * NPAIR],
                                           const Bonus32 (&b32)[2 * NPAIR], const Bonus16 (&b16c)[NPAIR])
 {
@@ -567,8 +595,10 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR
     constexpr int EW = DUAL ? 10 : 5;
     const int K = 1 << A.shift;
     const int scale = K - (1 << WALK_SH16);
-    WalkState16 a16[NS], b16[NS];
-    int sp = 0, pc = 0;                // sp counts 32-bit words per thread; pc is a BYTE offset into c_pool
+    WalkState16 a16[NS], b16[NS];      // a16[s]: packed A of pair s, or (32-bit mode) the keys of gene 2s
+    WalkState hi[NS];                  // 32-bit mode: the keys of gene 2s + 1
+    int *top = stk;                    // the thread's next free word of the packed stack (entries are T words apart)
+    int pc = 0;                        // a BYTE offset into c_pool
     int sp32 = 0;                      // 32-bit entries held in stk32
     int stk32[WALK_STACK32 * EW * NLAB * NP];   // local memory: touched by PUSH32 / MERGE_POP32 only
     int room = 0, win = 0;             // leaves left in the current 16-leaf window; windows opened so far
@@ -578,7 +608,7 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR
 #pragma unroll
     for (int l = 0; l < NLAB; ++l) lw[l] = 0;
 #pragma unroll
-    for (int k = 0; k < NP; ++k) gnext[k] = SB_LDG(gcol[k]);
+    for (int k = 0; k < NP; ++k) gnext[k] = SB_LDG(A.genesT + gcol[k]);
 #pragma unroll
     for (int q = 0; q < NPAIR; ++q) { gx[q] = 0; gy[q] = 0; }
     const int W32p = A.W32p;
@@ -600,7 +630,7 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR
             }                                                                                  \
             if (w_ + 1 < W32p) {                                                               \
                 _Pragma("unroll") for (int k_ = 0; k_ < NP; ++k_)                              \
-                    gnext[k_] = SB_LDG(gcol[k_] + (int64_t)(w_ + 1) * Gs);                    \
+                    gnext[k_] = SB_LDG(A.genesT + (int64_t)(w_ + 1) * Gs + gcol[k_]);        \
             }                                                                                  \
         } else {                                                                               \
             _Pragma("unroll") for (int q_ = 0; q_ < NPAIR; ++q_) gx[q_] = gy[q_];              \
@@ -650,12 +680,16 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR
         _Pragma("unroll") for (int l = 0; l < NLAB; ++l) {                                     \
             const uint32_t t_ = lw[l] & 1u;                                                    \
             lw[l] >>= 1;                                                                       \
-            if (t_) {                                                                          \
-                _Pragma("unroll") for (int k = 0; k < NP; ++k)                                 \
-                    walk_leaf<1, DUAL>(acc[l * NP + k], SB_GENE_BIT(k), b32[k]);               \
-            } else {                                                                           \
-                _Pragma("unroll") for (int k = 0; k < NP; ++k)                                 \
-                    walk_leaf<0, DUAL>(acc[l * NP + k], SB_GENE_BIT(k), b32[k]);               \
+            _Pragma("unroll") for (int q = 0; q < NPAIR; ++q) {                                \
+                WalkState g0_ = as_state32<DUAL>(a16[l * NPAIR + q]);                          \
+                if (t_) {                                                                      \
+                    walk_leaf<1, DUAL>(g0_, SB_GENE_BIT(2 * q), b32[2 * q]);                   \
+                    walk_leaf<1, DUAL>(hi[l * NPAIR + q], SB_GENE_BIT(2 * q + 1), b32[2 * q + 1]); \
+                } else {                                                                       \
+                    walk_leaf<0, DUAL>(g0_, SB_GENE_BIT(2 * q), b32[2 * q]);                   \
+                    walk_leaf<0, DUAL>(hi[l * NPAIR + q], SB_GENE_BIT(2 * q + 1), b32[2 * q + 1]); \
+                }                                                                              \
+                put_state32<DUAL>(a16[l * NPAIR + q], g0_);                                    \
             }                                                                                  \
         }                                                                                      \
         _Pragma("unroll") for (int q = 0; q < NPAIR; ++q) SB_CONSUME(q, 1);                    \
@@ -733,7 +767,7 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR
     } while (0)
 #define SB_POP16(L, q)                                                                         \
     do {                                                                                       \
-        const int *s_ = stk + (sp + (q) * EW) * T;                                             \
+        const int *s_ = top + (q) * EW * T;                                                    \
         _Pragma("unroll") for (int c = 0; c < 5; ++c) {                                        \
             L.p[c] = (unsigned)s_[c * T];                                                      \
             if constexpr (DUAL) L.a[c] = (unsigned)s_[(5 + c) * T];                            \
@@ -742,52 +776,59 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR
     for (;;) {
         const uint32_t op = *reinterpret_cast<const uint16_t *>(reinterpret_cast<const char *>(c_pool) + pc);
         pc += 2;
-        const int type = op & 15, cnt = op >> OP_TYPE_BITS;
-        if (((op ^ (uint32_t)OP_CHERRY_B16) & 14u) == 0) {
+        const int cnt = op >> OP_TYPE_BITS;
+        if (op & 4u) {
             SB_CHERRY_RUN16(b16);
-            if (op & 1u) {
+            if (op & 2u) {
 #pragma unroll
                 for (int s = 0; s < NS; ++s) walk_merge16<DUAL>(b16[s], a16[s], b16c[s % NPAIR]);
             }
             continue;
         }
-        if ((op & 12u) == 4u) {
-            if (op & 1u) {
+        if (op & 8u) {
+            if (op & 32u) {
 #pragma unroll
                 for (int q = 0; q < NS; ++q) {
-                    int *s = stk + (sp + q * EW) * T;
+                    int *s = top + q * EW * T;
 #pragma unroll
                     for (int c = 0; c < 5; ++c) {
                         s[c * T] = (int)a16[q].p[c];
                         if constexpr (DUAL) s[(5 + c) * T] = (int)a16[q].a[c];
                     }
                 }
-                sp += EW * NS;
+                top += EW * NS * T;
             }
             if (op & 2u) SB_CHERRY_RUN16(a16);
             continue;
         }
-        if (type == OP_MERGE_POP16) {
+        if ((op & 16u) == 0) {
+            if (op & 32u) {         // OP_MERGE_POP16
 #pragma unroll 1
-            for (int i = 0; i < cnt; ++i) {
-                sp -= EW * NS;
+                for (int i = 0; i < cnt; ++i) {
+                    top -= EW * NS * T;
 #pragma unroll
-                for (int q = 0; q < NS; ++q) {
-                    WalkState16 L;
-                    SB_POP16(L, q);
-                    walk_merge16<DUAL>(L, a16[q], b16c[q % NPAIR]);
+                    for (int q = 0; q < NS; ++q) {
+                        WalkState16 L;
+                        SB_POP16(L, q);
+                        walk_merge16<DUAL>(L, a16[q], b16c[q % NPAIR]);
+                    }
                 }
+                continue;
             }
-            continue;
+            if (op & 2u) {          // OP_LEAF_A16
+                SB_LEAF_RUN(SB_LEAF_STEP16(a16));
+                continue;
+            }
+            break;                  // OP_END
         }
-        if (type == OP_LEAF_A16) {
-            SB_LEAF_RUN(SB_LEAF_STEP16(a16));
-            continue;
-        }
-        switch (type) {
+        switch (op & OP_TYPE_MASK) {
         case OP_WIDEN_A:
 #pragma unroll
-            for (int q = 0; q < NS; ++q) walk_widen<DUAL>(a16[q], acc[2 * q], acc[2 * q + 1], scale);
+            for (int q = 0; q < NS; ++q) {
+                WalkState g0;
+                walk_widen<DUAL>(a16[q], g0, hi[q], scale);
+                put_state32<DUAL>(a16[q], g0);
+            }
             break;
         case OP_LEAF_A32:
             SB_LEAF_RUN(SB_LEAF_STEP32());
@@ -795,20 +836,25 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR
         case OP_MERGE_A32_B16:
 #pragma unroll
             for (int q = 0; q < NS; ++q) {
-                WalkState r0, r1;
+                WalkState r0, r1, g0 = as_state32<DUAL>(a16[q]);
                 walk_widen<DUAL>(b16[q], r0, r1, scale);
-                walk_merge<DUAL>(r0, acc[2 * q], b32[(2 * q) % NP]);
-                walk_merge<DUAL>(r1, acc[2 * q + 1], b32[(2 * q + 1) % NP]);
+                walk_merge<DUAL>(r0, g0, b32[(2 * q) % NP]);
+                walk_merge<DUAL>(r1, hi[q], b32[(2 * q + 1) % NP]);
+                put_state32<DUAL>(a16[q], g0);
             }
             break;
         case OP_PUSH32: {
             int *s = stk32 + sp32 * (EW * NLAB * NP);
 #pragma unroll
-            for (int k = 0; k < NLAB * NP; ++k) {
+            for (int q = 0; q < NS; ++q) {
 #pragma unroll
                 for (int c = 0; c < 5; ++c) {
-                    s[k * EW + c] = acc[k].p[c];
-                    if constexpr (DUAL) s[k * EW + 5 + c] = acc[k].a[c];
+                    s[2 * q * EW + c] = (int)a16[q].p[c];
+                    s[(2 * q + 1) * EW + c] = hi[q].p[c];
+                    if constexpr (DUAL) {
+                        s[2 * q * EW + 5 + c] = (int)a16[q].a[c];
+                        s[(2 * q + 1) * EW + 5 + c] = hi[q].a[c];
+                    }
                 }
             }
             ++sp32;
@@ -820,35 +866,47 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR
                 --sp32;
                 const int *s = stk32 + sp32 * (EW * NLAB * NP);
 #pragma unroll
-                for (int k = 0; k < NLAB * NP; ++k) {
-                    WalkState L;
+                for (int q = 0; q < NS; ++q) {
+                    WalkState L0, L1, g0 = as_state32<DUAL>(a16[q]);
 #pragma unroll
                     for (int c = 0; c < 5; ++c) {
-                        L.p[c] = s[k * EW + c];
-                        if constexpr (DUAL) L.a[c] = s[k * EW + 5 + c];
+                        L0.p[c] = s[2 * q * EW + c];
+                        L1.p[c] = s[(2 * q + 1) * EW + c];
+                        if constexpr (DUAL) {
+                            L0.a[c] = s[2 * q * EW + 5 + c];
+                            L1.a[c] = s[(2 * q + 1) * EW + 5 + c];
+                        }
                     }
-                    walk_merge<DUAL>(L, acc[k], b32[k % NP]);
+                    walk_merge<DUAL>(L0, g0, b32[(2 * q) % NP]);
+                    walk_merge<DUAL>(L1, hi[q], b32[(2 * q + 1) % NP]);
+                    put_state32<DUAL>(a16[q], g0);
                 }
             }
             break;
         case OP_MERGE_POPW:
 #pragma unroll 1
             for (int i = 0; i < cnt; ++i) {
-                sp -= EW * NS;
+                top -= EW * NS * T;
 #pragma unroll
                 for (int q = 0; q < NS; ++q) {
                     WalkState16 L;
                     SB_POP16(L, q);
-                    WalkState r0, r1;
+                    WalkState r0, r1, g0 = as_state32<DUAL>(a16[q]);
                     walk_widen<DUAL>(L, r0, r1, scale);
-                    walk_merge<DUAL>(r0, acc[2 * q], b32[(2 * q) % NP]);
-                    walk_merge<DUAL>(r1, acc[2 * q + 1], b32[(2 * q + 1) % NP]);
+                    walk_merge<DUAL>(r0, g0, b32[(2 * q) % NP]);
+                    walk_merge<DUAL>(r1, hi[q], b32[(2 * q + 1) % NP]);
+                    put_state32<DUAL>(a16[q], g0);
                 }
             }
             break;
-        default:   // OP_END
-            return;
+        default:
+            break;
         }
+    }
+#pragma unroll
+    for (int q = 0; q < NS; ++q) {     // the program always ends in 32-bit mode
+        acc[2 * q] = as_state32<DUAL>(a16[q]);
+        acc[2 * q + 1] = hi[q];
     }
 #undef SB_OPEN_WINDOW
 #undef SB_WINDOW_X
@@ -866,7 +924,7 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t *const (&gcol)[2 * NPAIR
 // gene slots of this thread: (tile * NP + k) * tile_threads + tid  (coalesced per k)
 template <int NP>
 SB_DEV void walk_slots(const WalkArgs &A, const int32_t *list, int tile, int32_t (&s_idx)[NP], bool (&active)[NP],
-                                           const uint32_t *(&gcol)[NP])
+                                           uint32_t (&gcol)[NP])
 {
     const int64_t S = A.S_dev ? (int64_t)*A.S_dev : A.S;
 #pragma unroll
@@ -876,7 +934,7 @@ SB_DEV void walk_slots(const WalkArgs &A, const int32_t *list, int tile, int32_t
         const int64_t lc = active[k] ? li : (S - 1);   // idle lanes redo the last entry (no divergence)
         s_idx[k] = list ? list[lc] : (int32_t)lc;         // result slots are counted in 32 bits throughout
         const int64_t gene = A.col_idx ? (int64_t)A.col_idx[s_idx[k]] : (A.gene_idx ? A.gene_idx[s_idx[k]] : (int64_t)s_idx[k]);
-        gcol[k] = A.genesT + gene;
+        gcol[k] = (uint32_t)gene;   // columns are counted in 32 bits (sb_set_genes checks)
     }
 }
 
@@ -887,7 +945,7 @@ SB_KERNEL(__launch_bounds__(WALK_THREADS)) walk_pairs_kernel(const WalkArgs A)
     SB_SHARED_STACK(smem_stack);
     int *stk = smem_stack + threadIdx.x;
     constexpr int NP = WALK_NP;
-    int32_t s_idx[NP]; bool active[NP]; const uint32_t *gcol[NP];
+    int32_t s_idx[NP]; bool active[NP]; uint32_t gcol[NP];
     walk_slots<NP>(A, A.slot_idx, blockIdx.x, s_idx, active, gcol);
     const int K = 1 << A.shift;
     Bonus32 b32[NP];
@@ -940,7 +998,7 @@ SB_KERNEL(__launch_bounds__(WALK_THREADS, SB_WALK_MINBLOCKS)) walk_permute_kerne
     const int perm0 = chunk * A.ppi;
     const int rows = min(A.ppi, A.n_perms - perm0);
     if (A.S_dev && (int64_t)blockIdx.x * NP * A.tile_threads >= (int64_t)*A.S_dev) return;   // grid sized for an upper bound
-    int32_t s_idx[NP]; bool active[NP]; const uint32_t *gcol[NP];
+    int32_t s_idx[NP]; bool active[NP]; uint32_t gcol[NP];
     walk_slots<NP>(A, TRANSPOSED ? nullptr : A.slot_idx, blockIdx.x, s_idx, active, gcol);   // transposed: slot_idx lists the rows
     const int K = 1 << A.shift;
     const int mask = K - 1;

@@ -311,8 +311,8 @@ def test_padded_stream_program_never_crosses_a_window(padded):
         assert len(order) <= 1.25 * n + 16
         room, pos = 0, 0
         for op in ops:
-            kind, cnt = int(op) & 15, int(op) >> 4
-            leaves = cnt + 2 if kind in (2, 3, 6, 7) else cnt if kind in (1, 10) else 0      # csrc/walk.cuh op numbers
+            kind, cnt = int(op) & 63, int(op) >> 6
+            leaves = cnt + 2 if kind in (4, 6, 10, 42) else cnt if kind in (2, 17) else 0    # csrc/walk.cuh op numbers
             if leaves == 0:
                 continue
             assert leaves <= 16

@@ -11,9 +11,9 @@ from oracle import oracle as O
 from scoary_b200 import _lib, synth
 from scoary_b200 import tree as treemod
 
-OPS = {0: "END", 1: "LEAF_A16", 2: "CHERRY_B16", 3: "CHERRY_B16_MERGE", 5: "PUSH16", 6: "CHERRY_A16",
-       7: "PUSH_CHERRY_A16", 8: "MERGE_POP16", 9: "WIDEN_A", 10: "LEAF_A32", 11: "MERGE_A32_B16", 12: "PUSH32",
-       13: "MERGE_POP32", 14: "MERGE_POPW"}      # csrc/walk.cuh
+OPS = {0: "END", 32: "MERGE_POP16", 2: "LEAF_A16", 4: "CHERRY_B16", 6: "CHERRY_B16_MERGE", 40: "PUSH16", 10: "CHERRY_A16",
+       42: "PUSH_CHERRY_A16", 16: "WIDEN_A", 17: "LEAF_A32", 18: "MERGE_A32_B16", 19: "PUSH32",
+       48: "MERGE_POP32", 49: "MERGE_POPW"}      # csrc/walk.cuh
 NEG = -(1 << 30)
 
 
@@ -69,7 +69,7 @@ def run_program(ops, order, gene_bits, labels, n_leaves):
         return leaf_state(int(gene_bits[leaf]), int(labels[leaf]), K, 0, 0)
 
     for op in ops.tolist():
-        kind, cnt = OPS[op & 15], op >> 4
+        kind, cnt = OPS[op & 63], op >> 6
         if kind == "END":
             break
         if kind in ("CHERRY_A16", "PUSH_CHERRY_A16", "PUSH16"):

@@ -22,11 +22,19 @@ VARIANTS = {
     # 128 x 7 1.05x, 256 x 3 1.05x, 128 x 6 1.04x, without PRMT 0.97x.  r2d (192 x 4 the default): 192 x 5 0.97x,
     # 160 x 6 0.97x, 224 x 4 0.93x, 384 x 2 1.01x, 6 genes per thread 0.77x.  Last check, after the prologue lost
     # 12 registers of live state:
-    "t128_mb5": "-DSB_WALK_THREADS=128 -DSB_WALK_MINBLOCKS=5",     # the round-1 shape
-    "t192_mb5": "-DSB_WALK_THREADS=192 -DSB_WALK_MINBLOCKS=5",
-    "t160_mb6": "-DSB_WALK_THREADS=160 -DSB_WALK_MINBLOCKS=6",
-    "t160_mb5": "-DSB_WALK_THREADS=160 -DSB_WALK_MINBLOCKS=5",
-    "t224_mb3": "-DSB_WALK_THREADS=224 -DSB_WALK_MINBLOCKS=3",
+    # r2i: after the interpreter lost its whole-field compares and 10 live registers (a16 doubles as the 32-bit
+    # accumulator of a pair's first gene): the kernels of the previous commit, more resident blocks, two labellings
+    "before_875ceed": ("875ceed", ""),
+    "t256_mb3": "-DSB_WALK_THREADS=256 -DSB_WALK_MINBLOCKS=3",
+    # r2i, first pass: the new interpreter 1.055x over 875ceed; 192 x 5 1.01x, 160 x 6 1.01x, 256 x 3 1.02x; two
+    # labellings at 128 registers (16 warps) 0.99 - 1.01x with 18 % fewer instructions, at 96 registers 0.57x.
+    # Second pass: six genes per thread now fit 96 registers (12 % fewer instructions, 20 warps per SM)
+    "np3_t128_mb5": "-DSB_WALK_NPAIR=3 -DSB_WALK_THREADS=128 -DSB_WALK_MINBLOCKS=5",
+    "np3_t160_mb4": "-DSB_WALK_NPAIR=3 -DSB_WALK_THREADS=160 -DSB_WALK_MINBLOCKS=4",
+    "np3_t192_mb3": "-DSB_WALK_NPAIR=3 -DSB_WALK_THREADS=192 -DSB_WALK_MINBLOCKS=3",
+    "np3_t128_mb6": "-DSB_WALK_NPAIR=3 -DSB_WALK_THREADS=128 -DSB_WALK_MINBLOCKS=6",
+    "np3_t96_mb7": "-DSB_WALK_NPAIR=3 -DSB_WALK_THREADS=96 -DSB_WALK_MINBLOCKS=7",
+    "np3_t64_mb10": "-DSB_WALK_NPAIR=3 -DSB_WALK_THREADS=64 -DSB_WALK_MINBLOCKS=10",
 }
 
 
