@@ -228,7 +228,7 @@ bool pad_stream(Program &prog, std::string &err)
     for (const uint16_t op : prog.ops) {
         const int type = op & sb::OP_TYPE_MASK, cnt = op >> sb::OP_TYPE_BITS;
         const bool cherry = type == sb::OP_CHERRY_A16 || type == sb::OP_PUSH_CHERRY_A16 || type == sb::OP_CHERRY_B16 ||
-                            type == sb::OP_CHERRY_B16_MERGE;
+                            type == sb::OP_CHERRY_B16_MERGE || type == (sb::OP_CHERRY_B16_MERGE | sb::OP_FLAG_BARE);
         if (cherry) {
             const int n = cnt + 2;
             if (n > W) { err = "internal error: cherry op longer than a leaf window"; return false; }
@@ -402,7 +402,7 @@ bool compile_tree(const int32_t *left, const int32_t *right, int32_t n_internal,
             while (j < n_raw && raw[j] == sb::RAW_LEAF_B16 && leaves < (size_t)sb::OP_MAX_COUNT) { ++j; ++leaves; }
             if (j < n_raw && raw[j] == sb::RAW_LEAF_B16) { err = "caterpillar too long for one op"; return false; }
             const bool merge = j < n_raw && raw[j] == sb::RAW_MERGE_AB16;
-            emit(merge ? sb::OP_CHERRY_B16_MERGE : sb::OP_CHERRY_B16, leaves);
+            emit(merge ? (sb::OP_CHERRY_B16_MERGE | (leaves == 0 ? sb::OP_FLAG_BARE : 0)) : sb::OP_CHERRY_B16, leaves);
             i = j + (merge ? 1 : 0);
         } else if (kind == sb::RAW_LEAF_B16 || kind == sb::RAW_MERGE_AB16) {
             err = "internal error: B-accumulator step outside a B evaluation";

@@ -312,7 +312,7 @@ def test_padded_stream_program_never_crosses_a_window(padded):
         room, pos = 0, 0
         for op in ops:
             kind, cnt = int(op) & 63, int(op) >> 6
-            leaves = cnt + 2 if kind in (4, 6, 10, 42) else cnt if kind in (2, 17) else 0    # csrc/walk.cuh op numbers
+            leaves = cnt + 2 if kind in (4, 6, 38, 10, 42) else cnt if kind in (2, 17) else 0    # csrc/walk.cuh op numbers
             if leaves == 0:
                 continue
             assert leaves <= 16

@@ -11,7 +11,7 @@ from oracle import oracle as O
 from scoary_b200 import _lib, synth
 from scoary_b200 import tree as treemod
 
-OPS = {0: "END", 32: "MERGE_POP16", 2: "LEAF_A16", 4: "CHERRY_B16", 6: "CHERRY_B16_MERGE", 40: "PUSH16", 10: "CHERRY_A16",
+OPS = {0: "END", 32: "MERGE_POP16", 2: "LEAF_A16", 4: "CHERRY_B16", 6: "CHERRY_B16_MERGE", 38: "CHERRY_B16_MERGE", 40: "PUSH16", 10: "CHERRY_A16",
        42: "PUSH_CHERRY_A16", 16: "WIDEN_A", 17: "LEAF_A32", 18: "MERGE_A32_B16", 19: "PUSH32",
        48: "MERGE_POP32", 49: "MERGE_POPW"}      # csrc/walk.cuh
 NEG = -(1 << 30)

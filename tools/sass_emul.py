@@ -445,7 +445,7 @@ class Machine:
             c = self.pred(a[3])
             need(c)
             self.setr(a[0], x if c else y)
-        elif op == "PLOP3":
+        elif op in ("PLOP3", "UPLOP3"):
             x, y, z = need(self.pred(a[2]), self.pred(a[3]), self.pred(a[4]))
             lut = int(a[5], 16)
             self.setp(a[0], bool(lut >> ((4 if x else 0) | (2 if y else 0) | (1 if z else 0)) & 1))
@@ -463,6 +463,17 @@ class Machine:
             self.setr(a[0], min(x, y) if self.pred(a[5]) else max(x, y))
         elif op == "R2UR":
             self.setr(a[0], V(a[1]))
+        elif op in ("UPRMT", "PRMT") and not mods:                           # PRMT d, a, selector, b (generic mode)
+            x, sel, y = need(V(a[1]), V(a[2]), V(a[3]))
+            src = (x & M32) | ((y & M32) << 32)
+            out = 0
+            for i in range(4):
+                nib = (sel >> (4 * i)) & 0xF
+                byte = (src >> (8 * (nib & 7))) & 0xFF
+                if nib & 8:
+                    byte = 0xFF if byte & 0x80 else 0
+                out |= byte << (8 * i)
+            self.setr(a[0], out)
         elif op == "VIADD" and not mods:
             x, y = need(V(a[1]), V(a[2]))
             self.setr(a[0], x + y)
