@@ -409,8 +409,9 @@ bool compile_tree(const int32_t *left, const int32_t *right, int32_t n_internal,
             return false;
         } else {
             size_t j = i + 1;
-            const bool runs = (kind == sb::OP_LEAF_A16 || kind == sb::OP_LEAF_A32 || kind == sb::OP_MERGE_POP16 ||
-                               kind == sb::OP_MERGE_POP32 || kind == sb::OP_MERGE_POPW);
+            // (a packed pop is one op each: as a counted loop the kernel shuffled 16 registers around every merge)
+            const bool runs = (kind == sb::OP_LEAF_A16 || kind == sb::OP_LEAF_A32 || kind == sb::OP_MERGE_POP32 ||
+                               kind == sb::OP_MERGE_POPW);
             if (runs) while (j < n_raw && raw[j] == kind) ++j;
             size_t cnt = j - i;
             if (kind == sb::OP_PUSH32) { sp32 += 1; depth32 = std::max(depth32, sp32); }

@@ -19,7 +19,7 @@
 //   LEAF_A xN / LEAF_B xN A (or B) <- combine(A (or B), next leaf)      N times
 //   MERGE_AB              A <- combine(A, B)
 //   PUSH                  spill A to the DP stack (packed entries: shared memory; 32-bit entries: local memory)
-//   MERGE_POP xN          A <- combine(pop(), A)                         N times
+//   MERGE_POP             A <- combine(pop(), A)          (xN for the 32-bit forms)
 // (each in a packed 16-bit form for subtrees of <= 127 leaves -- two genes per register,
 // .S16x2 DPX instructions -- and a 32-bit form above that, with WIDEN steps in between)
 // A and B are two register-resident accumulators: a second child that is a
@@ -468,13 +468,14 @@ SB_DEV void merge_pass16(const unsigned L[5], const unsigned R[5], unsigned out[
                                              unsigned bopp)
 {
     const unsigned ML = max5_16(L), MR = max5_16(R);
-#pragma unroll
-    for (int c = 0; c < 4; ++c) out[c] = __viaddmax_s16x2(L[c], MR, SB_ADD2_NC(ML, R[c]));   // ML is reachable
-    // out[4] as in merge_pass: clamp and pair bonuses ride on fused add-max steps
+    // out[4] as in merge_pass: clamp and pair bonuses ride on fused add-max steps.  It comes first in the source
+    // because it needs the old R[0..3], which out[0..3] may then overwrite in place (callers pass acc as R).
     const unsigned nf = __viaddmax_s16x2(L[4], R[4], NEG16x2);
     const unsigned pp = __viaddmax_s16x2(L[0], R[3], SB_VADD2(L[3], R[0]));
     const unsigned ap = __viaddmax_s16x2(L[1], R[2], SB_VADD2(L[2], R[1]));
     out[4] = __viaddmax_s16x2(ap, bopp, __viaddmax_s16x2(pp, bsup, nf));
+#pragma unroll
+    for (int c = 0; c < 4; ++c) out[c] = __viaddmax_s16x2(L[c], MR, SB_ADD2_NC(ML, R[c]));   // ML is reachable
 }
 
 // acc <- combine(L, acc)
@@ -846,16 +847,13 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t (&gcol)[2 * NPAIR], cons
             continue;
         }
         if ((op & 16u) == 0) {
-            if (op & 32u) {         // OP_MERGE_POP16
-#pragma unroll 1
-                for (int i = 0; i < cnt; ++i) {
-                    top -= EW * NS * T;
+            if (op & 32u) {         // OP_MERGE_POP16 (always a single pop)
+                top -= EW * NS * T;
 #pragma unroll
-                    for (int q = 0; q < NS; ++q) {
-                        WalkState16 L;
-                        SB_POP16(L, q);
-                        walk_merge16<DUAL>(L, a16[q], b16c[q % NPAIR]);
-                    }
+                for (int q = 0; q < NS; ++q) {
+                    WalkState16 L;
+                    SB_POP16(L, q);
+                    walk_merge16<DUAL>(L, a16[q], b16c[q % NPAIR]);
                 }
                 continue;
             }
