@@ -579,12 +579,12 @@ int launch_fisher(sb_ctx *ctx, int32_t t0, int32_t nT, int32_t *d_counts, double
     return SB_OK;
 }
 
-// DP stack: s.depth units per gene pair (and per labelling walked in lockstep, K5 only); a unit is 10 words
-// with both passes (K4), 5 with one (K5)
+// DP stack: s.depth pushes per thread; a push holds all packed states of the thread (10 words each with both
+// passes, K4; 5 with one, K5), padded to whole 128-bit chunks (sb::walk_push_words)
 size_t walk_smem_bytes(const TraitSlot &s, bool dual)
 {
-    return sizeof(int) * (dual ? 10 : 5) * (size_t)std::max(1, s.depth) * sb::WALK_THREADS * sb::WALK_NPAIR *
-           (dual ? 1 : sb::WALK_NLAB);
+    return sizeof(int) * (size_t)sb::walk_push_words(dual, dual ? 1 : sb::WALK_NLAB) * (size_t)std::max(1, s.depth) *
+           sb::WALK_THREADS;
 }
 
 void fill_walk_args(const TraitSlot &s, sb::WalkArgs &A, const int64_t *d_gene_idx, int64_t S)
@@ -708,7 +708,7 @@ int launch_rows(sb_ctx *ctx, const TraitSlot &s, const uint32_t *d_labelsT, int6
     const int64_t tiles = (Pn + per_block - 1) / per_block;
     int ppi = sb::PERMS_PER_ITEM_MAX;      // rows per block: fewer when that is what it takes to give every SM work
     while (ppi > 1 && tiles * ((std::min<int64_t>(cap, n_rows) + ppi - 1) / ppi) < 2LL * 7 * ctx->sm_count) ppi /= 2;
-    const size_t smem = sizeof(int) * 5 * (size_t)std::max(1, s.depth) * sb::WALK_THREADS * sb::WALK_NPAIR;
+    const size_t smem = sizeof(int) * (size_t)sb::walk_push_words(false, 1) * (size_t)std::max(1, s.depth) * sb::WALK_THREADS;
     SB_CUDA(ctx, cudaFuncSetAttribute(sb::walk_permute_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int64_t base = 0; base < n_rows; base += cap) {
         const int n = (int)std::min<int64_t>(cap, n_rows - base);
@@ -804,7 +804,7 @@ int launch_permute(sb_ctx *ctx, int32_t t, const int64_t *d_gene_idx, int64_t S,
     int tile_threads = sb::WALK_THREADS;
     if (!early_stop && S < 24LL * sb::WALK_THREADS * sb::WALK_NP) {
         double best = 0.0;
-        for (int tt = sb::WALK_THREADS; tt >= 96; tt -= 32) {
+        for (int tt = sb::WALK_THREADS; tt >= 64; tt -= 32) {
             const int64_t per = (int64_t)tt * sb::WALK_NP, tl = (S + per - 1) / per;
             const double util = (double)S / (double)(tl * per);
             if (util > best + 0.02) { best = util; tile_threads = tt; }

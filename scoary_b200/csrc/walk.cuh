@@ -103,11 +103,14 @@ __device__ __forceinline__ unsigned sb_sign_mask2(unsigned x)
 #define SB_SIGN_MASK2(x) sb_sign_mask2(x)
 #endif
 
+// Block shape: 768 threads per SM at 80 registers either way; after the interpreter changes of session r2i
+// 128 x 6 measured 1.02x over 192 x 4 (as do 256 x 3 and 192 x 5 at 64 registers; profiles/r2_sweep.txt), and
+// its finer tiles suit the short work lists of reference-rule rounds.
 #ifndef SB_WALK_THREADS
-#define SB_WALK_THREADS 192
+#define SB_WALK_THREADS 128
 #endif
 #ifndef SB_WALK_MINBLOCKS
-#define SB_WALK_MINBLOCKS 4
+#define SB_WALK_MINBLOCKS 6
 #endif
 // Gene windows are kept bit-reversed (measured 1.03x in round 2, profiles/r2_sweep.txt; 0 = the round-1 form), so that the
 // next leaf sits in bit 15 / bit 31 and its half-word mask is ONE PRMT (sign replication) instead of
@@ -600,6 +603,15 @@ struct WalkArgs {
 #endif
 constexpr int WALK_NPAIR = SB_WALK_NPAIR;   // gene pairs per thread
 constexpr int WALK_NP = 2 * WALK_NPAIR;     // genes per thread
+// Words one packed push takes per thread: 5 (one pass) or 10 (both) per packed state, padded to whole 128-bit
+// chunks -- an entry is stored as [chunk][thread] uint4, so a push / pop is 3 LDS.128 / STS.128 (K5: 10 words + 2 of
+// padding) instead of 10 32-bit accesses.
+#ifdef SB_HOST_EMUL
+#define SB_HOST_DEVICE
+#else
+#define SB_HOST_DEVICE __host__ __device__
+#endif
+SB_HOST_DEVICE constexpr int walk_push_words(bool dual, int nlab) { return ((dual ? 10 : 5) * WALK_NPAIR * nlab + 3) / 4 * 4; }
 // Sweep variant (measured 0.88 - 0.97x in round 2, profiles/r2_sweep.txt: 20 % fewer instructions, but 165 registers
 // leave 12 warps per SM -- not adopted): K5 walks SB_WALK_NLAB labellings of its genes in
 // lockstep.  The program decode, the leaf-stream bookkeeping and the gene-bit masks are then shared by the
@@ -613,8 +625,9 @@ constexpr int WALK_NLAB = SB_WALK_NLAB;
 // labellings at c_pool[lab_off[l] ..].  gcol[k] is gene k's column of genesT (an index: four 64-bit pointers were 8 registers); genes 2q and 2q+1
 // share the packed accumulators of pair q; state index s = l * NPAIR + q (32-bit: l * NP + k).  Every branch is on block-uniform data (the program and
 // the label bits); per-gene data only feeds selects.  The program always ends in 32-bit mode.
-// Stack entries take EW = 10 (DUAL) or 5 words: per gene pair in the packed shared-memory stack, per gene in the
-// 32-bit local-memory stack (WALK_STACK32).
+// Stack entries take EW = 10 (DUAL) or 5 words: per gene pair in the packed shared-memory stack (all pairs of a
+// push together, walk_push_words), per gene in the 32-bit local-memory stack (WALK_STACK32).  stk: the thread's first
+// 128-bit chunk of the block's stack.
 template <int NPAIR, int NLAB, bool DUAL>
 SB_DEV void walk_tree(const WalkArgs &A, const uint32_t (&gcol)[2 * NPAIR], const int (&lab_off)[NLAB],
                                           int *stk, WalkState (&acc)[NLAB * 2 * NPAIR],
@@ -628,7 +641,8 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t (&gcol)[2 * NPAIR], cons
     const int scale = K - (1 << WALK_SH16);
     WalkState16 a16[NS], b16[NS];      // a16[s]: packed A of pair s, or (32-bit mode) the keys of gene 2s
     WalkState hi[NS];                  // 32-bit mode: the keys of gene 2s + 1
-    int *top = stk;                    // the thread's next free word of the packed stack (entries are T words apart)
+    constexpr int PW4 = walk_push_words(DUAL, NLAB) / 4;   // 128-bit chunks per push
+    uint4 *top = reinterpret_cast<uint4 *>(stk);           // the thread's next free chunk (chunks are T apart)
     int pc = 0;                        // a BYTE offset into c_pool
     int sp32 = 0;                      // 32-bit entries held in stk32
     int stk32[WALK_STACK32 * EW * NLAB * NP];   // local memory: touched by PUSH32 / MERGE_POP32 only
@@ -810,12 +824,20 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t (&gcol)[2 * NPAIR], cons
             }                                                                                  \
         }                                                                                      \
     }
-#define SB_POP16(L, q)                                                                         \
+    // pop one entry into Ls[NS]; word q * EW + c (+ 5 for the second pass) of a push belongs to state q
+#define SB_POP16_ALL(Ls)                                                                       \
     do {                                                                                       \
-        const int *s_ = top + (q) * EW * T;                                                    \
-        _Pragma("unroll") for (int c = 0; c < 5; ++c) {                                        \
-            L.p[c] = (unsigned)s_[c * T];                                                      \
-            if constexpr (DUAL) L.a[c] = (unsigned)s_[(5 + c) * T];                            \
+        unsigned w_[PW4 * 4];                                                                  \
+        top -= PW4 * T;                                                                        \
+        _Pragma("unroll") for (int j = 0; j < PW4; ++j) {                                      \
+            const uint4 v_ = top[j * T];                                                       \
+            w_[4 * j] = v_.x; w_[4 * j + 1] = v_.y; w_[4 * j + 2] = v_.z; w_[4 * j + 3] = v_.w; \
+        }                                                                                      \
+        _Pragma("unroll") for (int q = 0; q < NS; ++q) {                                       \
+            _Pragma("unroll") for (int c = 0; c < 5; ++c) {                                    \
+                Ls[q].p[c] = w_[q * EW + c];                                                   \
+                if constexpr (DUAL) Ls[q].a[c] = w_[q * EW + 5 + c];                           \
+            }                                                                                  \
         }                                                                                      \
     } while (0)
     for (;;) {
@@ -832,29 +854,30 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t (&gcol)[2 * NPAIR], cons
         }
         if (op & 8u) {
             if (op & 32u) {
+                unsigned w[PW4 * 4];
+#pragma unroll
+                for (int k = EW * NS; k < PW4 * 4; ++k) w[k] = 0u;
 #pragma unroll
                 for (int q = 0; q < NS; ++q) {
-                    int *s = top + q * EW * T;
 #pragma unroll
                     for (int c = 0; c < 5; ++c) {
-                        s[c * T] = (int)a16[q].p[c];
-                        if constexpr (DUAL) s[(5 + c) * T] = (int)a16[q].a[c];
+                        w[q * EW + c] = a16[q].p[c];
+                        if constexpr (DUAL) w[q * EW + 5 + c] = a16[q].a[c];
                     }
                 }
-                top += EW * NS * T;
+#pragma unroll
+                for (int j = 0; j < PW4; ++j) top[j * T] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+                top += PW4 * T;
             }
             if (op & 2u) SB_CHERRY_RUN16(a16, false);
             continue;
         }
         if ((op & 16u) == 0) {
             if (op & 32u) {         // OP_MERGE_POP16 (always a single pop)
-                top -= EW * NS * T;
+                WalkState16 L[NS];
+                SB_POP16_ALL(L);
 #pragma unroll
-                for (int q = 0; q < NS; ++q) {
-                    WalkState16 L;
-                    SB_POP16(L, q);
-                    walk_merge16<DUAL>(L, a16[q], b16c[q % NPAIR]);
-                }
+                for (int q = 0; q < NS; ++q) walk_merge16<DUAL>(L[q], a16[q], b16c[q % NPAIR]);
                 continue;
             }
             if (op & 2u) {          // OP_LEAF_A16
@@ -928,11 +951,11 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t (&gcol)[2 * NPAIR], cons
         case OP_MERGE_POPW:
 #pragma unroll 1
             for (int i = 0; i < cnt; ++i) {
-                top -= EW * NS * T;
+                WalkState16 Ls[NS];
+                SB_POP16_ALL(Ls);
 #pragma unroll
                 for (int q = 0; q < NS; ++q) {
-                    WalkState16 L;
-                    SB_POP16(L, q);
+                    const WalkState16 &L = Ls[q];
                     WalkState r0, r1, g0 = as_state32<DUAL>(a16[q]);
                     walk_widen<DUAL>(L, r0, r1, scale);
                     walk_merge<DUAL>(r0, g0, b32[(2 * q) % NP]);
@@ -960,7 +983,7 @@ SB_DEV void walk_tree(const WalkArgs &A, const uint32_t (&gcol)[2 * NPAIR], cons
 #undef SB_LEAF_STEP32
 #undef SB_LEAF_RUN
 #undef SB_CHERRY_RUN16
-#undef SB_POP16
+#undef SB_POP16_ALL
 }
 
 // gene slots of this thread: (tile * NP + k) * tile_threads + tid  (coalesced per k)
@@ -985,7 +1008,7 @@ SB_DEV void walk_slots(const WalkArgs &A, const int32_t *list, int tile, int32_t
 SB_KERNEL(__launch_bounds__(WALK_THREADS)) walk_pairs_kernel(const WalkArgs A)
 {
     SB_SHARED_STACK(smem_stack);
-    int *stk = smem_stack + threadIdx.x;
+    int *stk = smem_stack + 4 * threadIdx.x;
     constexpr int NP = WALK_NP;
     int32_t s_idx[NP]; bool active[NP]; uint32_t gcol[NP];
     walk_slots<NP>(A, A.slot_idx, blockIdx.x, s_idx, active, gcol);
@@ -1033,7 +1056,7 @@ template <bool TRANSPOSED>
 SB_KERNEL(__launch_bounds__(WALK_THREADS, SB_WALK_MINBLOCKS)) walk_permute_kernel(const WalkArgs A)
 {
     SB_SHARED_STACK(smem_stack);
-    int *stk = smem_stack + threadIdx.x;
+    int *stk = smem_stack + 4 * threadIdx.x;
     constexpr int NP = WALK_NP;
     constexpr int NLAB = TRANSPOSED ? 1 : WALK_NLAB;
     const int chunk = blockIdx.y;

@@ -68,7 +68,7 @@ int emul_pairs(const uint16_t *ops, int n_ops, const uint32_t *labels, const uin
     fill(A, genesT, Gs, S, W32p, shift);
     A.pairs = pairs; A.lab_base = base;
     const int T = sb::WALK_THREADS;
-    const size_t words = (size_t)10 * (stack_units > 0 ? stack_units : 1) * T * sb::WALK_NPAIR;
+    const size_t words = (size_t)sb::walk_push_words(true, 1) * (stack_units > 0 ? stack_units : 1) * T;
     std::vector<int> smem(words + GUARD, CANARY);
     const int64_t per_block = (int64_t)T * sb::WALK_NP;
     for (int64_t tile = 0; tile < (S + per_block - 1) / per_block; ++tile)
@@ -93,7 +93,7 @@ int emul_permute(const uint16_t *ops, int n_ops, const uint32_t *labelsW, int P,
     A.n_perms = P; A.ppi = ppi; A.items_per_tile = (P + ppi - 1) / ppi; A.chunk_base = 0;
     A.unperm = unperm; A.hits = hits;
     const int T = sb::WALK_THREADS;
-    const size_t words = (size_t)5 * (stack_units > 0 ? stack_units : 1) * T * sb::WALK_NPAIR * sb::WALK_NLAB;
+    const size_t words = (size_t)sb::walk_push_words(false, sb::WALK_NLAB) * (stack_units > 0 ? stack_units : 1) * T;
     std::vector<int> smem(words + GUARD, CANARY);
     const int64_t per_block = (int64_t)T * sb::WALK_NP;
     for (int64_t tile = 0; tile < (S + per_block - 1) / per_block; ++tile)
@@ -121,7 +121,7 @@ int emul_permute_transposed(const uint16_t *ops, int n_ops, const uint32_t *rows
     A.n_perms = n_rows; A.ppi = ppi; A.items_per_tile = (n_rows + ppi - 1) / ppi;
     A.unperm = unperm; A.hits = hits;
     const int T = sb::WALK_THREADS;
-    const size_t words = (size_t)5 * (stack_units > 0 ? stack_units : 1) * T * sb::WALK_NPAIR;
+    const size_t words = (size_t)sb::walk_push_words(false, 1) * (stack_units > 0 ? stack_units : 1) * T;
     std::vector<int> smem(words + GUARD, CANARY);
     const int64_t per_block = (int64_t)T * sb::WALK_NP;
     for (int64_t tile = 0; tile < (P + per_block - 1) / per_block; ++tile)

@@ -25,16 +25,13 @@ VARIANTS = {
     # r2i: after the interpreter lost its whole-field compares and 10 live registers (a16 doubles as the 32-bit
     # accumulator of a pair's first gene): the kernels of the previous commit, more resident blocks, two labellings
     "before_875ceed": ("875ceed", ""),
-    "t256_mb3": "-DSB_WALK_THREADS=256 -DSB_WALK_MINBLOCKS=3",
     # r2i, first pass: the new interpreter 1.055x over 875ceed; 192 x 5 1.01x, 160 x 6 1.01x, 256 x 3 1.02x; two
     # labellings at 128 registers (16 warps) 0.99 - 1.01x with 18 % fewer instructions, at 96 registers 0.57x.
-    # Second pass: six genes per thread now fit 96 registers (12 % fewer instructions, 20 warps per SM)
-    "np3_t128_mb5": "-DSB_WALK_NPAIR=3 -DSB_WALK_THREADS=128 -DSB_WALK_MINBLOCKS=5",
-    "np3_t160_mb4": "-DSB_WALK_NPAIR=3 -DSB_WALK_THREADS=160 -DSB_WALK_MINBLOCKS=4",
-    "np3_t192_mb3": "-DSB_WALK_NPAIR=3 -DSB_WALK_THREADS=192 -DSB_WALK_MINBLOCKS=3",
-    "np3_t128_mb6": "-DSB_WALK_NPAIR=3 -DSB_WALK_THREADS=128 -DSB_WALK_MINBLOCKS=6",
-    "np3_t96_mb7": "-DSB_WALK_NPAIR=3 -DSB_WALK_THREADS=96 -DSB_WALK_MINBLOCKS=7",
-    "np3_t64_mb10": "-DSB_WALK_NPAIR=3 -DSB_WALK_THREADS=64 -DSB_WALK_MINBLOCKS=10",
+    # Second pass: six genes per thread at 96 registers (12 % fewer instructions, 18 - 20 warps per SM) 0.86 - 0.91x.
+    # Third pass: fused bare cherries, single pops, in-place merges (-13 % instructions in all)
+    "t256_mb3": "-DSB_WALK_THREADS=256 -DSB_WALK_MINBLOCKS=3",
+    "t192_mb5": "-DSB_WALK_THREADS=192 -DSB_WALK_MINBLOCKS=5",
+    "t128_mb6": "-DSB_WALK_THREADS=128 -DSB_WALK_MINBLOCKS=6",
 }
 
 
