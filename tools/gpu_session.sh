@@ -24,7 +24,7 @@ step() {   # step <seconds> <log> <command...>
     tail -n 6 "$out/$log" | tee -a "$out/session.log"
 }
 
-mode="${2:-full}"          # quick: parity tests and the bench lines only
+mode="${2:-full}"          # quick: parity tests and the bench lines only; walk: everything but the Fisher capture
 step 900 pytest_gpu.log python -m pytest tests -m gpu -x -q
 if [ "$mode" != quick ]; then
 step 1200 sweep.log python tools/sweep_variants.py run
@@ -37,8 +37,10 @@ step 300 step_dram.log ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,
     --log-file "$out/step_dram.csv" python bench.py --workload c3 --steps 2 --warmup 3 --no-cpu-baseline
 step 420 ncu_walk.log ncu --set full --clock-control none --import-source on -k regex:walk_permute -c 1 \
     -o "$out/prof_walk" -f python tools/probe.py --perms 60
+if [ "$mode" != walk ]; then     # walk: the Fisher kernel did not change, keep its capture
 step 300 ncu_fisher.log ncu --set full --clock-control none --import-source on -k regex:fisher_kernel -c 1 \
     -o "$out/prof_fisher" -f python tools/probe.py --perms 4
+fi
 for rep in "$out"/prof_walk.ncu-rep "$out"/prof_fisher.ncu-rep; do
     [ -f "$rep" ] && ncu -i "$rep" --page raw --csv > "${rep%.ncu-rep}.raw.csv" 2>/dev/null
     # per-instruction executed counts and stall samples (SASS view): settles the pipe assignment of each opcode
@@ -47,7 +49,9 @@ done
 fi
 step 600 bench.log python bench.py
 step 300 bench_c3.log python bench.py --workload c3 --steps 5 --no-cpu-baseline
+if [ "$mode" != walk ]; then
 # one GPU's share of the north_star job on 8 GPUs (6 250 genes): what strong scaling asks of the launch planner
 step 300 bench_shard8.log python bench.py --genes 6250 --steps 3 --no-cpu-baseline
+fi
 grep -h '^{' "$out/bench.log" "$out/bench_c3.log" "$out/bench_shard8.log" > "$out/bench_lines.json" 2>/dev/null
 echo "== done" | tee -a "$out/session.log"

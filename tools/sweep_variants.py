@@ -28,10 +28,10 @@ VARIANTS = {
     # r2i, first pass: the new interpreter 1.055x over 875ceed; 192 x 5 1.01x, 160 x 6 1.01x, 256 x 3 1.02x; two
     # labellings at 128 registers (16 warps) 0.99 - 1.01x with 18 % fewer instructions, at 96 registers 0.57x.
     # Second pass: six genes per thread at 96 registers (12 % fewer instructions, 18 - 20 warps per SM) 0.86 - 0.91x.
-    # Third pass: fused bare cherries, single pops, in-place merges (-13 % instructions in all)
+    # Third pass (fused bare cherries, single pops, in-place merges): 1.11x over 875ceed; 256 x 3, 192 x 5 and
+    # 128 x 6 each 1.02x over 192 x 4 -> 128 x 6 adopted.  Fourth pass: 128-bit stack chunks in place
+    "t192_mb4": "-DSB_WALK_THREADS=192 -DSB_WALK_MINBLOCKS=4",
     "t256_mb3": "-DSB_WALK_THREADS=256 -DSB_WALK_MINBLOCKS=3",
-    "t192_mb5": "-DSB_WALK_THREADS=192 -DSB_WALK_MINBLOCKS=5",
-    "t128_mb6": "-DSB_WALK_THREADS=128 -DSB_WALK_MINBLOCKS=6",
 }
 
 

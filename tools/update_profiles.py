@@ -70,6 +70,8 @@ def main():
             "cold_cache_single_launch": round((float(w["dram__bytes_read.sum"]) + float(w["dram__bytes_write.sum"])) * 1e6)}
     json.dump(dram, open(os.path.join(ROOT, "profiles", "k5_dram_bytes.json"), "w"), indent=1)
     for k, name in (("walk", "walk_permute"), ("fisher", "fisher")):
+        if not os.path.exists(os.path.join(sess, "prof_%s.raw.csv" % k)):
+            continue
         out = os.path.join(ROOT, "profiles", "%s_ncu_%s_%s.txt" % (tag, name, commit))
         txt = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"),
                               os.path.join(sess, "prof_%s.raw.csv" % k), os.path.join(sess, "prof_%s.source.csv" % k)],
