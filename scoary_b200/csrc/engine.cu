@@ -816,7 +816,7 @@ int launch_permute(sb_ctx *ctx, int32_t t, const int64_t *d_gene_idx, int64_t S,
     const int label_cap = label_capacity(s);
     // threads = genes (the default) or threads = labellings: whichever shape fills the GPU better
     bool transposed = false;
-    if (sb::WALK_NLAB == 1 && !sb::WALK_PADDED && ctx->permute_mode != 1) {
+    if (sb::WALK_NLAB == 1 && ctx->permute_mode != 1) {
         if (!early_stop) {
             const double f_genes = fill_fraction(S, std::min(label_cap, P), slots);
             const double f_perms = fill_fraction(P, std::min<int64_t>(label_cap, S), slots);

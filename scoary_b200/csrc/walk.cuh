@@ -118,12 +118,16 @@ __device__ __forceinline__ unsigned sb_sign_mask2(unsigned x)
 #ifndef SB_WALK_PRMT
 #define SB_WALK_PRMT 1
 #endif
-// Sweep variant (measured 0.98 - 1.01x in round 2, profiles/r2_sweep.txt: not adopted): the host compiler pads the leaf stream so that no op
-// ever crosses a 16-leaf window (pad positions carry gene bit 0 and no label; long leaf runs are split at the
-// boundaries).  The kernels then have no general path: an op that does not fit the rest of the window simply opens
-// the next one.  Changes the stream layout, so engine.cu (compile_tree, sb_set_tree) honours the same switch.
+// The host compiler pads the leaf stream so that no op ever crosses a 16-leaf window (pad positions carry gene bit 0
+// and no label; long leaf runs are split at the boundaries).  The kernels then have no general path: an op that does
+// not fit the rest of the window simply opens the next one.  Without padding (0) every fifth cherry of a typical tree
+// took a second, window-crossing copy of its handler: 10 % of the executed instructions came out of code that is
+// otherwise cold.  Measured 0.98 - 1.01x early in round 2, 1.023x (sweep) / 1.027x (north_star step) after the
+// interpreter changes of sessions r2i - r2k (profiles/r2_sweep.txt), when instruction fetch had become the second
+// largest stall; the stream grows by ~12 %.  Changes the stream layout, so engine.cu (compile_tree, sb_set_tree)
+// honours the same switch.
 #ifndef SB_WALK_PADDED
-#define SB_WALK_PADDED 0
+#define SB_WALK_PADDED 1
 #endif
 constexpr int WALK_THREADS = SB_WALK_THREADS;
 constexpr bool WALK_PADDED = SB_WALK_PADDED != 0;

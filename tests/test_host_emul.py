@@ -62,8 +62,14 @@ def _ptr(a):
 def _pack_walk_order(bits_by_leaf, order, W32p):
     """uint8 [R][n_leaves] (leaf-id order) -> uint32 [R][W32p], bit b of word w = the leaf consumed at position 32w+b"""
     walk = np.zeros((bits_by_leaf.shape[0], W32p * 32), dtype=np.uint8)
-    walk[:, :len(order)] = bits_by_leaf[:, order]
+    real = order >= 0                                     # pad positions (leaf id -1) carry bit 0
+    walk[:, np.nonzero(real)[0]] = bits_by_leaf[:, order[real]]
     return np.ascontiguousarray(np.packbits(walk, axis=1, bitorder="little")).view(np.uint32).reshape(-1, W32p)
+
+
+def _stream_words(order):
+    """W32p of a leaf stream: 32-bit words, padded to a multiple of four (engine.cu sb_set_tree)"""
+    return ((len(order) + 31) // 32 + 3) // 4 * 4
 
 
 def _setup(n, G, seed, comb=False):
@@ -83,8 +89,7 @@ def _setup(n, G, seed, comb=False):
     m[0] = lab                                            # a perfectly associated gene
     if G > 1:
         m[1] = 1 - lab
-    W32 = (n + 31) // 32
-    W32p = (W32 + 3) // 4 * 4
+    W32p = _stream_words(order)
     shift = 1
     while (1 << shift) <= n // 2:
         shift += 1
@@ -203,7 +208,7 @@ def test_extreme_keys_stay_inside_their_16_bit_lane(emul, n, comb):
     Results must equal the oracle's and SB_ADD2_NC must never see a low-lane carry."""
     c = _setup(n, 8, 900 + n, comb)
     pos_of_leaf = np.empty(n, dtype=np.int64)
-    pos_of_leaf[c["order"][:n]] = np.arange(n)
+    pos_of_leaf[c["order"][c["order"] >= 0]] = np.arange(n)        # rank in walk order (pad positions do not count)
     lab = (pos_of_leaf % 2).astype(np.uint8)                      # by leaf id: alternating in walk order
     m = np.stack([lab, 1 - lab, (pos_of_leaf // 2 % 2).astype(np.uint8), 1 - (pos_of_leaf // 2 % 2).astype(np.uint8),
                   np.ones(n, np.uint8), np.zeros(n, np.uint8), (pos_of_leaf % 3 == 0).astype(np.uint8),
@@ -257,21 +262,25 @@ def test_lockstep_variant_of_the_permutation_kernel_on_the_host(emul_nlab2, n, G
     _check_permute(emul_nlab2, n, G, comb, ppi)
 
 
-# ---------------------------------------------------------------------------- padded leaf stream (-DSB_WALK_PADDED=1)
-@pytest.fixture(scope="module")
-def padded():
-    """(tree compiler of a -DSB_WALK_PADDED=1 build of the product library, walk kernels of the same build on the host)"""
-    so = os.path.join(HERE, "libscoary_b200_padded.so")
+# ---------------------------------------------------------------------------- the two leaf-stream layouts
+# -DSB_WALK_PADDED=1 (the default: no op crosses a 16-leaf window, the stream holds pad positions) and =0 (ops may
+# cross, the kernels keep a window-crossing path), each as an explicit build of the tree compiler and of the kernels
+@pytest.fixture(scope="module", params=["1", "0"], ids=["padded", "crossing"])
+def padded(request):
+    """(tree compiler of a -DSB_WALK_PADDED=<flag> build of the product library, walk kernels of the same build on the
+    host, flag)"""
+    flag = request.param
+    so = os.path.join(HERE, "libscoary_b200_padded%s.so" % flag)
     deps = [os.path.join(CSRC, f) for f in ("engine.cu", "walk.cuh", "common.cuh")]
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
         env = dict(os.environ)
         env.pop("CC", None)
-        subprocess.run(["make", "-B", "-C", CSRC, "OUT=" + so, "EXTRA=-DSB_WALK_PADDED=1"], check=True, env=env,
+        subprocess.run(["make", "-B", "-C", CSRC, "OUT=" + so, "EXTRA=-DSB_WALK_PADDED=" + flag], check=True, env=env,
                        stdout=subprocess.DEVNULL)
     lib = ctypes.CDLL(so)
     lib.sb_debug_compile_tree2.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int32,
                                            ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]
-    return lib, _build_walk_emul(os.path.join(HERE, "libwalk_emul_padded.so"), ("-DSB_WALK_PADDED=1",))
+    return lib, _build_walk_emul(os.path.join(HERE, "libwalk_emul_padded%s.so" % flag), ("-DSB_WALK_PADDED=" + flag,)), flag
 
 
 def _compile_padded(lib, nested):
@@ -297,7 +306,9 @@ def _pack_stream(bits_by_leaf, order, W32p):
 def test_padded_stream_program_never_crosses_a_window(padded):
     """Every leaf-consuming op of a padded program lies inside one 16-leaf window under the kernels' rule (an op
     that does not fit opens the next window), every leaf appears exactly once, pads cost at most ~25 % positions."""
-    lib, _ = padded
+    lib, _, flag = padded
+    if flag == "0":
+        pytest.skip("the crossing layout has no pad positions")
     for n, comb in ((2, False), (17, False), (127, True), (300, True), (1000, False), (5000, False)):
         names = synth.isolate_names(n)
         nested = names[0]
@@ -329,7 +340,7 @@ def test_padded_stream_program_never_crosses_a_window(padded):
 @pytest.mark.parametrize("n,G,comb", [(5, 40, False), (33, 9, False), (129, 300, False), (150, 260, True), (1000, 20, False),
                                       (5000, 12, False)])
 def test_padded_variant_of_the_walk_kernels_on_the_host(padded, n, G, comb):
-    lib, emul_p = padded
+    lib, emul_p, _ = padded
     rng = np.random.default_rng(700 + n)
     names = synth.isolate_names(n)
     nested = names[0]
@@ -397,7 +408,7 @@ def test_random_campaign_over_tree_shapes_and_window_offsets(emul, emul_prmt, em
         m = (rng.random((G, n)) < rng.uniform(0.0, 1.0, size=G)[:, None]).astype(np.uint8)
         lab = (rng.random(n) < rng.uniform(0.05, 0.95)).astype(np.uint8)
         m[0] = lab
-        W32p = ((n + 31) // 32 + 3) // 4 * 4
+        W32p = _stream_words(order)
         shift = 1
         while (1 << shift) <= n // 2:
             shift += 1

@@ -17,18 +17,23 @@ OPS = {0: "END", 32: "MERGE_POP16", 2: "LEAF_A16", 4: "CHERRY_B16", 6: "CHERRY_B
 NEG = -(1 << 30)
 
 
-def compile_tree(nested):
+WINDOW = 16      # csrc/walk.cuh WALK_WINDOW
+
+
+def compile_tree(nested, lib=None):
+    """(ops, stream, stack units, leaf names): stream[pos] = the leaf consumed at position pos, or -1 for a pad
+    position (the default build pads the stream so that no op crosses a 16-leaf window, csrc/walk.cuh SB_WALK_PADDED)"""
     left, right, names = treemod.flatten(nested)
-    lib = _lib.load()
+    lib = lib or _lib.load()
     n = len(left)
-    ops = np.zeros(4 * n + 16, dtype=np.uint16)
-    order = np.zeros(n + 1, dtype=np.int32)
-    depth = ctypes.c_int32()
-    k = lib.sb_debug_compile_tree(left.ctypes.data_as(ctypes.c_void_p), right.ctypes.data_as(ctypes.c_void_p), n,
-                                  ops.ctypes.data_as(ctypes.c_void_p), len(ops), order.ctypes.data_as(ctypes.c_void_p),
-                                  ctypes.byref(depth))
+    ops = np.zeros(6 * n + 64, dtype=np.uint16)
+    order = np.full(3 * n + 64, -9, dtype=np.int32)
+    n_pos, depth = ctypes.c_int32(), ctypes.c_int32()
+    ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p)      # noqa: E731
+    k = lib.sb_debug_compile_tree2(ptr(left), ptr(right), n, ptr(ops), len(ops), ptr(order), len(order),
+                                   ctypes.byref(n_pos), ctypes.byref(depth))
     assert k > 0, lib.sb_last_error(None)
-    return ops[:k], order, depth.value, names
+    return ops[:k].copy(), order[:n_pos.value].copy(), depth.value, names
 
 
 def leaf_state(g, t, K, ps, po):
@@ -57,6 +62,8 @@ def run_program(ops, order, gene_bits, labels, n_leaves):
         shift += 1
     K = 1 << shift
     pos = 0
+    room = 0               # leaves left in the current window, as the kernels count them
+    padded = len(order) != n_leaves or bool((order < 0).any())
     A = B = None
     mode_a = None          # 16 or 32: which accumulator form A is in
     stack = []
@@ -65,6 +72,7 @@ def run_program(ops, order, gene_bits, labels, n_leaves):
     def next_leaf():
         nonlocal pos
         leaf = order[pos]
+        assert leaf >= 0, "an op consumed a pad position"
         pos += 1
         return leaf_state(int(gene_bits[leaf]), int(labels[leaf]), K, 0, 0)
 
@@ -72,6 +80,19 @@ def run_program(ops, order, gene_bits, labels, n_leaves):
         kind, cnt = OPS[op & 63], op >> 6
         if kind == "END":
             break
+        need = cnt + 2 if "CHERRY" in kind else cnt if kind in ("LEAF_A16", "LEAF_A32") else 0
+        if need:
+            # the kernels' window rule: an op that does not fit what is left of the 16-leaf window opens the next
+            # one; in a padded stream what it skips is padding, and no op is longer than a window
+            if padded:
+                assert need <= WINDOW
+                if need > room:
+                    assert np.all(order[pos:pos + room] == -1)
+                    pos += room
+                    room = WINDOW
+                room -= need
+            else:
+                room = (room - need) % WINDOW
         if kind in ("CHERRY_A16", "PUSH_CHERRY_A16", "PUSH16"):
             if kind != "CHERRY_A16":
                 assert mode_a == 16
@@ -136,7 +157,7 @@ def run_program(ops, order, gene_bits, labels, n_leaves):
         # the packed 16-bit form is only legal up to 127 leaves (keys < 4096)
         if mode_a == 16:
             assert sizes["A"] <= 127, (kind, sizes["A"])
-    assert pos == n_leaves and not stack and mode_a == 32 and sizes["A"] == n_leaves
+    assert np.all(order[pos:] == -1) and not stack and mode_a == 32 and sizes["A"] == n_leaves
     p, a = A
     mask = K - 1
     total = max(p) >> shift
@@ -165,7 +186,7 @@ def test_compiled_program_reproduces_the_oracle(n):
     rng = np.random.default_rng(n)
     for nested in shapes:
         ops, order, depth, leaf_names = compile_tree(nested)
-        assert sorted(order.tolist()) == list(range(n))
+        assert sorted(order[order >= 0].tolist()) == list(range(n))
         left, right, onames = O.flatten_tree(nested)
         assert onames == leaf_names
         for _ in range(3):

@@ -30,8 +30,9 @@ VARIANTS = {
     # Second pass: six genes per thread at 96 registers (12 % fewer instructions, 18 - 20 warps per SM) 0.86 - 0.91x.
     # Third pass (fused bare cherries, single pops, in-place merges): 1.11x over 875ceed; 256 x 3, 192 x 5 and
     # 128 x 6 each 1.02x over 192 x 4 -> 128 x 6 adopted.  Fourth pass: 128-bit stack chunks in place
-    "t192_mb4": "-DSB_WALK_THREADS=192 -DSB_WALK_MINBLOCKS=4",
-    "t256_mb3": "-DSB_WALK_THREADS=256 -DSB_WALK_MINBLOCKS=3",
+    # r2j (128-bit stack chunks in place): 192 x 4 0.98x, 256 x 3 1.00x.  r2k: the padded leaf stream 1.023x (no
+    # window-crossing copies of the handlers: instruction fetch stalls) -> adopted; padded at 192 x 4 1.00x
+    "crossing": "-DSB_WALK_PADDED=0",
 }
 
 

@@ -44,7 +44,8 @@ def main():
                          "fma_pct_of_peak": float(w["sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"]),
                          "uniform_pct_of_peak": float(w["sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active"]),
                          "lsu_pct_of_peak": float(w["sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"])},
-          "history": {"5af1521 (round 1, profiled)": 152363, "630daac (round 1 HEAD, ncu in round 2)": 133854}}
+          "history": {"5af1521 (round 1, profiled)": 152363, "630daac (round 1 HEAD, ncu in round 2)": 133854,
+                      "d0be99b (round 2, session r2h)": 131749}}
     wi["by_pipe_north_star"] = wi["by_pipe_c3"]
     json.dump(wi, open(os.path.join(ROOT, "profiles", "k5_warp_instructions.json"), "w"), indent=1)
     # DRAM traffic of the full-size exhaustive launches inside running steps
