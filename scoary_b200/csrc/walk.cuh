@@ -393,9 +393,10 @@ SB_DEV void walk_cherry16_mixed(WalkState16 &o, unsigned mB, unsigned mb, const 
     o.p[1] = N & ~mb;               // Ab
     o.p[2] = N & mB;                // aB
     o.p[3] = N & mb;                // ab
-    const unsigned pm = mB & ~mb, am = ~mB & mb;   // AB+ab supports, aB+Ab opposes
-    o.p[4] = sel2(pm, b.ps, sel2(am, b.po, N));
-    if constexpr (DUAL) o.a[4] = sel2(pm, b.as_, sel2(am, b.ao, N));
+    // a pair exists where the genes differ: AB+ab (mB set) supports, aB+Ab opposes -- three LOP3 per key set
+    const unsigned d = mB ^ mb;
+    o.p[4] = sel2(d, sel2(mB, b.ps, b.po), N);
+    if constexpr (DUAL) o.a[4] = sel2(d, sel2(mB, b.as_, b.ao), N);
 }
 
 // o[q] <- node of two leaves, for every gene pair q of the thread.  m1, m2: half-word masks of the two
