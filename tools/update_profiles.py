@@ -45,9 +45,19 @@ def main():
                          "uniform_pct_of_peak": float(w["sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active"]),
                          "lsu_pct_of_peak": float(w["sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"])},
           "history": {"5af1521 (round 1, profiled)": 152363, "630daac (round 1 HEAD, ncu in round 2)": 133854,
-                      "d0be99b (round 2, session r2h)": 131749}}
+                      "d0be99b (round 2, session r2h)": 131749, "8d63fcb (round 2, session r2j)": 110681,
+                      "3a850a5 (round 2, session r2l)": 108611}}
     wi["by_pipe_north_star"] = wi["by_pipe_c3"]
     json.dump(wi, open(os.path.join(ROOT, "profiles", "k5_warp_instructions.json"), "w"), indent=1)
+    if not os.path.exists(os.path.join(sess, "step_dram.csv")):      # a tools/final_check.sh session: K5 capture only
+        out = os.path.join(ROOT, "profiles", "%s_ncu_walk_permute_%s.txt" % (tag, commit))
+        txt = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"),
+                              os.path.join(sess, "prof_walk.raw.csv"), os.path.join(sess, "prof_walk.source.csv")],
+                             capture_output=True, text=True, check=True).stdout
+        open(out, "w").write("# ncu --set full --clock-control none --import-source on, one launch of tools/probe.py (C3 shape), "
+                             "kernels of commit %s, session %s\n" % (commit, os.path.basename(sess)) + txt)
+        print(json.dumps(wi["launch"]), per64)
+        return
     # DRAM traffic of the full-size exhaustive launches inside running steps
     rows = list(csv.reader(l for l in open(os.path.join(sess, "step_dram.csv")) if not l.startswith("==")))
     hdr = rows[0]
