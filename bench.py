@@ -540,7 +540,7 @@ def run_ours(a):
                         "bytes of one full-size launch inside a running step (ncu --cache-control none, %s).  It is far "
                         "above the algorithmic bytes and it is not re-reads of the input: the %d MB walk-order gene matrix "
                         "stays in L2; what goes to DRAM is the threads' local-memory DP stack (32-bit entries of the "
-                        "tree's spine + register spills, 768 B per thread, rewritten by every block), which L1 / L2 write "
+                        "tree's spine + register spills, ~0.7 KB per thread, rewritten by every block), which L1 / L2 write "
                         "back.  At ~40 GB/s it is 0.6 %% of the HBM peak and costs the kernel nothing"
                         % (bytes_per_test, prof.get("source", "profiles/"), int(g_loc * W * 8 / 1e6))}
     # the utilisation figure of K5: warp instructions it executes (ncu smsp__inst_executed.sum, profiles/) per second

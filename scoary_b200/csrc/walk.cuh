@@ -603,6 +603,8 @@ struct WalkArgs {
                                // tile_threads x NP work-list entries, chosen so that the last tile is nearly full
 };
 
+// Sweep variant: 3 = six genes per thread (12 % fewer instructions, but 96 registers leave 18 - 20 warps per SM:
+// measured 0.86 - 0.91x in session r2i, 0.77x earlier in round 2; profiles/r2_sweep.txt -- not adopted)
 #ifndef SB_WALK_NPAIR
 #define SB_WALK_NPAIR 2
 #endif
@@ -617,8 +619,8 @@ constexpr int WALK_NP = 2 * WALK_NPAIR;     // genes per thread
 #define SB_HOST_DEVICE __host__ __device__
 #endif
 SB_HOST_DEVICE constexpr int walk_push_words(bool dual, int nlab) { return ((dual ? 10 : 5) * WALK_NPAIR * nlab + 3) / 4 * 4; }
-// Sweep variant (measured 0.88 - 0.97x in round 2, profiles/r2_sweep.txt: 20 % fewer instructions, but 165 registers
-// leave 12 warps per SM -- not adopted): K5 walks SB_WALK_NLAB labellings of its genes in
+// Sweep variant (18 - 20 % fewer instructions, but 128 registers leave 16 warps per SM: measured 0.99 - 1.01x in
+// session r2i, 0.88 - 0.97x at 165 registers earlier in round 2, profiles/r2_sweep.txt -- not adopted): K5 walks SB_WALK_NLAB labellings of its genes in
 // lockstep.  The program decode, the leaf-stream bookkeeping and the gene-bit masks are then shared by the
 // labellings; only the DP arithmetic is per labelling (tools/k5_model.py counts the instructions).
 #ifndef SB_WALK_NLAB

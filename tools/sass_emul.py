@@ -511,7 +511,7 @@ class Machine:
         return n
 
 
-def walk_args(Gs, S, S_total, W32p, shift, n_perms, ppi, chunk_base=0, gene_idx=0, slot_idx=0, lab_base=0, threads=192):
+def walk_args(Gs, S, S_total, W32p, shift, n_perms, ppi, chunk_base=0, gene_idx=0, slot_idx=0, lab_base=0, threads=128):
     """struct WalkArgs (csrc/walk.cuh) as the kernel-parameter bytes; pointers only need to be non-null"""
     return struct.pack("<QqQQqqiiiiiiQQQQiiQii", 0x7000_0000_0000, Gs, gene_idx, slot_idx, S, S_total, W32p, shift, n_perms, ppi,
                        (n_perms + ppi - 1) // ppi, chunk_base, 0x7100_0000_0000, 0x7200_0000_0000, 0x7300_0000_0000,
