@@ -669,7 +669,8 @@ double fill_fraction(int64_t threads_domain, int64_t blocks_y, int slots)
 // (0.25 + 0.75 f) of that -- blocks that share an SM with fewer others run faster, but not proportionally -- so whole
 // waves are cheapest per labelling: cost = (floor(w) + (0.25 + 0.75 frac(w) if frac(w) > 0) ) x ppi + 0.05, w = blocks / slots.
 // 5 700 genes (8 tiles of 768) on 592 slots: 74 labellings x 1 per block = 592 blocks, exactly one wave, 155 ms per
-// 10 000 permutations where the largest launch the constant pool allows (91: 1.23 waves) takes 168 ms.
+// 10 000 permutations where the largest launch the constant pool allows (91: 1.23 waves) takes 168 ms.  (Figures of
+// the 192 x 4 block shape the model was measured with; the rule itself does not depend on the shape.)
 void plan_launch(int64_t tiles, int cap, int slots, int ppi_min, int ppi_max, int *ppi_out, int *n_out)
 {
     double best = 1e300;
@@ -799,8 +800,8 @@ int launch_permute(sb_ctx *ctx, int32_t t, const int64_t *d_gene_idx, int64_t S,
     if (smem > (size_t)ctx->max_smem_optin) return fail(ctx, SB_ERR_ARG, "tree too deep for shared memory");
     SB_CUDA(ctx, cudaFuncSetAttribute(sb::walk_permute_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // Threads per block: WALK_THREADS, or fewer when that leaves the last tile of a SMALL work list nearly empty
-    // (6 250 genes -- the north_star job on 8 GPUs -- are 8.14 tiles of 192 x 4 but 9.77 tiles of 160 x 4: 98 % of the
-    // lanes carry a walk instead of 90 %).  Only exhaustive mode: reference-rule rounds shrink their lists anyway.
+    // (6 250 genes -- the north_star job on 8 GPUs -- are 12.2 tiles of 128 x 4 but 16.3 tiles of 96 x 4: 96 % of the
+    // lanes carry a walk instead of 94 %).  Only exhaustive mode: reference-rule rounds shrink their lists anyway.
     int tile_threads = sb::WALK_THREADS;
     if (!early_stop && S < 24LL * sb::WALK_THREADS * sb::WALK_NP) {
         double best = 0.0;

@@ -249,8 +249,8 @@ struct WalkState {
 // the branching on them in the uniform datapath (ULDC / UISETP / BRA.U) and the
 // vector pipes only see the DP arithmetic.
 // One 62 KB pool, split per tree: the uint16 program at the start, the label vectors of the current launch
-// from word WalkArgs::lab_base on.  A 5 000-leaf tree (~2 500 ops, 5 KB) leaves room for 91 labellings per launch;
-// a balanced 32 766-leaf tree (21 374 ops, 43 KB) still fits with 5.
+// from word WalkArgs::lab_base on.  A 5 000-leaf tree (~2 700 ops, 5 KB) leaves room for 81 labellings per launch;
+// a balanced 32 766-leaf tree (24 952 ops, 50 KB) still fits with 3.
 constexpr int C_POOL_WORDS = 15872;
 SB_CONST uint32_t c_pool[C_POOL_WORDS];
 // first label word behind a program of n_ops ops (16-byte aligned)
