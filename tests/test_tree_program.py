@@ -216,3 +216,19 @@ def compile_tree_bad():
     k = lib.sb_debug_compile_tree(left.ctypes.data_as(ctypes.c_void_p), right.ctypes.data_as(ctypes.c_void_p), 2,
                                   ops.ctypes.data_as(ctypes.c_void_p), 16, order.ctypes.data_as(ctypes.c_void_p), None)
     assert k > 0, lib.sb_last_error(None)
+
+
+def test_largest_trees_fit_the_constant_pool():
+    """sb_set_tree's limit (include/scoary_b200.h: <= 32 766 isolates): program + at least one label vector of the
+    padded stream must fit the 15 872-word constant pool (csrc/walk.cuh C_POOL_WORDS) for every tree shape; the
+    balanced tree has the longest program (one op per cherry, push and pop), the random-join tree the longest stream."""
+    import sys
+    sys.setrecursionlimit(1_000_000)
+    n = 32766
+    names, shapes = _shapes(n, 5)
+    for nested in shapes[:3]:
+        ops, order, depth, _ = compile_tree(nested)
+        w32p = ((len(order) + 31) // 32 + 3) // 4 * 4
+        label_base = ((len(ops) + 1) // 2 + 3) // 4 * 4              # walk_label_base
+        assert label_base + w32p <= 15872, (len(ops), len(order))
+        assert len(order) <= 1.25 * n + 16 and depth <= 8
