@@ -231,13 +231,17 @@ int sb_binom_two_sided(sb_ctx *ctx, const int32_t *k, const int32_t *n, int64_t 
  *   [n_rows][n_lead][2] receives the byte range of the fields lead_cols[] (identifier,
  *   annotation, ...); begin < 0 marks a field with escaped quotes that the host must unescape
  *   (its range starts at -begin - 1).  row_fields[n_rows] = number of fields in the row.
- *   Returns 0, or -(row + 1) of the first row too short for the requested columns. */
+ *   Returns 0, or -(row + 1) of the first row too short for the requested columns.
+ * sb_csv_gather_fields: the text of lead field k of every row copied back to back into out (offsets[n_rows + 1];
+ *   fields with begin < 0 contribute nothing); out = NULL only fills the offsets.  Returns the byte count or -1. */
 int64_t sb_csv_row_starts(const char *buf, int64_t len, char delimiter, int64_t *row_starts,
                           int64_t max_rows, int64_t *header_end);
 int64_t sb_csv_pack_rows(const char *buf, int64_t len, char delimiter, const int64_t *row_starts,
                          int64_t n_rows, const int32_t *keep_cols, int32_t n_keep, uint64_t *bits,
                          int32_t W, const int32_t *lead_cols, int32_t n_lead, int64_t *lead_ranges,
                          int32_t *row_fields);
+int64_t sb_csv_gather_fields(const char *buf, const int64_t *lead_ranges, int64_t n_rows, int32_t n_lead,
+                             int32_t k, char *out, int64_t out_cap, int64_t *offsets);
 
 /* ---- VCF input (host code, no GPU needed) ---- */
 /* scoary/vcf2scoary.py:50-218 followed by the cell loop of Csv_to_dic_Roary (methods.py:445-497),

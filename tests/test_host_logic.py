@@ -237,28 +237,32 @@ def test_native_csv_packer_embedded_quotes_and_ragged_rows(tmp_path, monkeypatch
     header = ",".join('"%s"' % c for c in M.ROARY_COLUMNS[:14]) + "," + ",".join("I%d" % j for j in range(N))
     tricky_ann = ['5" nuclease', 'x "quoted" y', '"starts quoted" tail"', '"a ""b"" c"', 'odd " count', '"multi\nline, cell"',
                   ' "after space"', 'plain', '3\'-5" exo"nuclease"', '""']
-    for trial, wide_row in [(0, None), (1, 3)]:
+    for trial, wide_row in [(0, None), (1, 3), (2, None)]:
         lines = [header]
+        if trial == 2:      # text that is not ASCII (byte offsets are not character offsets) and repeated identifiers
+            tricky_ann = tricky_ann + ['na\u00efve "prot\u00e9ine" \u03b2', '"\u00e5 ""\u00f8"" \u00e6"']
         for g in range(40):
             ann = tricky_ann[g % len(tricky_ann)] if g % 2 == 0 else rnd.choice(tricky_ann)
             cells = [rnd.choice(['"l_%d"' % g, "l%d" % g, '', '0', '-', '""', 'a"b', '"-"']) for _ in range(N)]
-            row = 'g%d,nug %d"x,%s,1,2,3,4,5,6,7,8,9,10,11,%s' % (g, g, ann, ",".join(cells))
+            gid = g if trial < 2 or g % 9 else g // 18
+            row = 'g%d,nug %d"x,%s,1,2,3,4,5,6,7,8,9,10,11,%s' % (gid, g, ann, ",".join(cells))
             if wide_row is not None and g == wide_row:
                 row += ",extra"
             lines.append(row)
         path = str(tmp_path / ("quotes%d.csv" % trial))
-        with open(path, "w", newline="") as fh:
+        with open(path, "w", newline="", encoding="utf-8") as fh:
             fh.write("\r\n".join(lines[:20]) + "\n" + "\n".join(lines[20:]) + "\n")
         monkeypatch.delenv("SCOARY_B200_PY_CSV", raising=False)
-        with open(path) as fh:
+        with open(path, encoding="utf-8") as fh:
             a = M.Csv_to_dic_Roary(fh, ",", [3], startcol=14)
         monkeypatch.setenv("SCOARY_B200_PY_CSV", "1")
-        with open(path, newline="") as fh:
+        with open(path, newline="", encoding="utf-8") as fh:
             b = M.Csv_to_dic_Roary(fh, ",", [3], startcol=14)
-        with open(path, newline="") as fh:
+        with open(path, newline="", encoding="utf-8") as fh:
             want = [r[0] for r in __import__("csv").reader(fh, skipinitialspace=True)][1:]
         ta, tb = a["Roarydic"], b["Roarydic"]
         assert len(want) == 40 and tb.names == [w for w in dict.fromkeys(want)]
+        assert trial < 2 or (len(tb.names) < 40 and any(not x.isascii() for x in tb.annotation))
         assert ta.names == tb.names and ta.nugn == tb.nugn and ta.annotation == tb.annotation
         assert np.array_equal(ta.bits, tb.bits) and ta.extra == tb.extra
     monkeypatch.delenv("SCOARY_B200_PY_CSV", raising=False)
