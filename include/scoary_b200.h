@@ -236,6 +236,11 @@ int sb_binom_two_sided(sb_ctx *ctx, const int32_t *k, const int32_t *n, int64_t 
  *   fields with begin < 0 contribute nothing); out = NULL only fills the offsets.  Returns the byte count or -1. */
 int64_t sb_csv_row_starts(const char *buf, int64_t len, char delimiter, int64_t *row_starts,
                           int64_t max_rows, int64_t *header_end);
+/* sb_csv_scan_rows: the same in one pass -- *row_starts_out receives a malloc'ed array (NULL without rows) that
+ * sb_csv_free releases; returns the number of data rows or -1. */
+int64_t sb_csv_scan_rows(const char *buf, int64_t len, char delimiter, int64_t **row_starts_out,
+                         int64_t *header_end);
+void sb_csv_free(void *p);
 int64_t sb_csv_pack_rows(const char *buf, int64_t len, char delimiter, const int64_t *row_starts,
                          int64_t n_rows, const int32_t *keep_cols, int32_t n_keep, uint64_t *bits,
                          int32_t W, const int32_t *lead_cols, int32_t n_lead, int64_t *lead_ranges,

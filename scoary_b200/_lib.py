@@ -86,6 +86,9 @@ SIGNATURES = {
     "sb_csv_pack_rows": (ctypes.c_int64, [ctypes.c_char_p, ctypes.c_int64, ctypes.c_char, ctypes.c_void_p, ctypes.c_int64,
                                           ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p,
                                           ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]),
+    "sb_csv_scan_rows": (ctypes.c_int64, [ctypes.c_char_p, ctypes.c_int64, ctypes.c_char, ctypes.POINTER(ctypes.c_void_p),
+                                          ctypes.c_void_p]),
+    "sb_csv_free": (None, [ctypes.c_void_p]),
     "sb_csv_gather_fields": (ctypes.c_int64, [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
                                               ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
     "sb_vcf_line_starts": (ctypes.c_int64, [ctypes.c_char_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),

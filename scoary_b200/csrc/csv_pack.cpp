@@ -12,6 +12,7 @@
 // Host code only (no CUDA); rows are parsed in parallel with OpenMP after a sequential scan for
 // the row starts.
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -36,6 +37,23 @@ inline const char *parse_row(const char *base, const char *p, const char *e, cha
 {
     int col = 0;
     for (;;) {
+        // the two shapes nearly every presence cell has -- one plain character, or nothing, before the delimiter --
+        // without the general scan (same result: no space to skip, no quote to open, the field ends at the delimiter)
+        if (p + 1 < e && p[1] == delim && p[0] != ' ' && p[0] != '"' && p[0] != delim && p[0] != '\n' && p[0] != '\r') {
+            f(col, p - base, p + 1 - base, false, false);
+            ++col;
+            p += 2;
+            continue;
+        }
+        if (p < e && p[0] == '"') {                 // "text" + delimiter, no quote inside: what Roary writes
+            const char *q = (const char *)memchr(p + 1, '"', (size_t)(e - (p + 1)));
+            if (q && q + 1 < e && q[1] == delim) {
+                f(col, p + 1 - base, q - base, true, false);
+                ++col;
+                p = q + 2;
+                continue;
+            }
+        }
         while (p < e && *p == ' ') ++p;             // skipinitialspace
         const char *fb = p;
         bool quoted = false, esc = false;
@@ -84,10 +102,43 @@ extern "C" {
 
 // Row starts of the data rows (everything after the first row).  row_starts may be NULL to count.
 // Returns the number of data rows (empty trailing lines are ignored), or -1 on error.
+// (The work is in scan_rows below; with grow != NULL the starts go to a malloc'ed array of the right size instead:
+// sb_csv_scan_rows, one pass over the file where count-then-fill takes two.)
+static int64_t scan_rows(const char *buf, int64_t len, char delimiter, int64_t *row_starts, int64_t max_rows,
+                         int64_t *header_end, int64_t **grow);
+
 int64_t sb_csv_row_starts(const char *buf, int64_t len, char delimiter, int64_t *row_starts, int64_t max_rows,
                           int64_t *header_end)
 {
+    return scan_rows(buf, len, delimiter, row_starts, max_rows, header_end, nullptr);
+}
+
+// As sb_csv_row_starts in ONE pass: *row_starts_out receives a malloc'ed array of the row starts (release it with
+// sb_csv_free; NULL when there are no rows).  Returns the number of data rows or -1.
+int64_t sb_csv_scan_rows(const char *buf, int64_t len, char delimiter, int64_t **row_starts_out, int64_t *header_end)
+{
+    if (!row_starts_out) return -1;
+    *row_starts_out = nullptr;
+    return scan_rows(buf, len, delimiter, nullptr, 0, header_end, row_starts_out);
+}
+
+void sb_csv_free(void *p) { free(p); }
+
+static int64_t scan_rows(const char *buf, int64_t len, char delimiter, int64_t *row_starts, int64_t max_rows,
+                         int64_t *header_end, int64_t **grow)
+{
     if (!buf || len < 0) return -1;
+    const bool collect = row_starts != nullptr || grow != nullptr;
+    auto deliver = [&](int64_t n) -> bool {          // where n starts go: the caller's array, or a new one
+        if (grow) {
+            if (n == 0) return true;
+            *grow = (int64_t *)malloc(sizeof(int64_t) * (size_t)n);
+            if (!*grow) return false;
+            row_starts = *grow;
+            return true;
+        }
+        return !row_starts || n <= max_rows;
+    };
     const char *p = buf, *e = buf + len;
     // The reader's state machine (Python's _csv.c, excel dialect, skipinitialspace, non-strict): a '"' opens a quoted
     // field only as the first character of a field (after the skipped spaces); anywhere else it is a literal, so an
@@ -153,16 +204,16 @@ int64_t sb_csv_row_starts(const char *buf, int64_t len, char delimiter, int64_t 
         std::vector<const char *> ended(n_pieces);
 #pragma omp parallel for schedule(dynamic, 1)
         for (int k = 0; k < n_pieces; ++k)
-            ended[k] = cut[k] < cut[k + 1] ? scan(cut[k], cut[k + 1], row_starts ? &starts[k] : nullptr, &counts[k]) : cut[k];
+            ended[k] = cut[k] < cut[k + 1] ? scan(cut[k], cut[k + 1], collect ? &starts[k] : nullptr, &counts[k]) : cut[k];
         bool chain = true;
         for (int k = 0; k < n_pieces; ++k) chain = chain && (ended[k] == cut[k + 1] || cut[k] >= cut[k + 1]);
         if (chain) {
+            int64_t total = 0;
+            for (int k = 0; k < n_pieces; ++k) total += counts[k];
+            if (!deliver(total)) return -1;
             int64_t n = 0;
             for (int k = 0; k < n_pieces; ++k) {
-                if (row_starts) {
-                    if (n + counts[k] > max_rows) return -1;
-                    if (counts[k]) memcpy(row_starts + n, starts[k].data(), sizeof(int64_t) * (size_t)counts[k]);
-                }
+                if (row_starts && counts[k]) memcpy(row_starts + n, starts[k].data(), sizeof(int64_t) * (size_t)counts[k]);
                 n += counts[k];
             }
             return n;
@@ -170,11 +221,9 @@ int64_t sb_csv_row_starts(const char *buf, int64_t len, char delimiter, int64_t 
     }
     std::vector<int64_t> all;
     int64_t n = 0;
-    scan(p, e, row_starts ? &all : nullptr, &n);
-    if (row_starts) {
-        if (n > max_rows) return -1;
-        if (n) memcpy(row_starts, all.data(), sizeof(int64_t) * (size_t)n);
-    }
+    scan(p, e, collect ? &all : nullptr, &n);
+    if (!deliver(n)) return -1;
+    if (row_starts && n) memcpy(row_starts, all.data(), sizeof(int64_t) * (size_t)n);
     return n;
 }
 

@@ -294,11 +294,14 @@ def _native_gene_table(path, delimiter, roaryfile, genecol, nugcol, anncol, grab
             buf = fh.read()
             pbuf = buf
     delim = delimiter.encode()[:1]
-    n = lib.sb_csv_row_starts(pbuf, len(buf), delim, None, 0, None)        # count, then fill: the scan runs in parallel pieces
+    found = ctypes.c_void_p()
+    n = lib.sb_csv_scan_rows(pbuf, len(buf), delim, ctypes.byref(found), None)      # one pass, in parallel pieces
     if n < 0:
         sys.exit("CRITICAL: Could not read gene presence absence file.")
     starts = np.empty(max(n, 1), dtype=np.int64)
-    lib.sb_csv_row_starts(pbuf, len(buf), delim, starts.ctypes.data_as(ctypes.c_void_p), n, None)
+    if n:
+        ctypes.memmove(starts.ctypes.data, found.value, 8 * n)
+    lib.sb_csv_free(found)
     W = eng.words_for(len(src_cols))
     bits = np.empty((n, W), dtype=np.uint64)
     lead = sorted(set([genecol, nugcol, anncol] + list(grabcols)))

@@ -294,6 +294,19 @@ def test_native_csv_row_scan_in_parallel_pieces(tmp_path, monkeypatch):
         assert len(rows) == G and a.names == [r[0] for r in rows] and a.annotation == [r[2] for r in rows]
         want = np.asarray([[c == "1" for c in r[14:]] for r in rows], dtype=np.uint8)
         assert np.array_equal(a.matrix, want)
+        # the two-pass form of the scan (count, then fill) and the one-pass form give the same row starts
+        import ctypes
+        from scoary_b200 import _lib
+        lib = _lib.load()
+        raw = open(path, "rb").read()
+        n = lib.sb_csv_row_starts(raw, len(raw), b",", None, 0, None)
+        two = np.empty(n, dtype=np.int64)
+        assert lib.sb_csv_row_starts(raw, len(raw), b",", two.ctypes.data_as(ctypes.c_void_p), n, None) == n == G
+        found = ctypes.c_void_p()
+        assert lib.sb_csv_scan_rows(raw, len(raw), b",", ctypes.byref(found), None) == n
+        one = np.ctypeslib.as_array(ctypes.cast(found, ctypes.POINTER(ctypes.c_int64)), shape=(n,)).copy()
+        lib.sb_csv_free(found)
+        assert np.array_equal(one, two) and raw[one[0]:one[0] + 3] == b"g0,"
 
 
 @pytest.mark.parametrize("name,types", [("Example", None), ("generated", None), ("generated", "snp,del")])
