@@ -37,8 +37,11 @@ inline bool is_word(unsigned char c)
 // end of the line starting at p (position of the terminator or e)
 inline const char *line_end(const char *p, const char *e)
 {
-    while (p < e && !is_eol(*p)) ++p;
-    return p;
+    // the next '\n', unless a '\r' comes first (memchr twice: the second one only looks at this line)
+    const char *nl = (const char *)memchr(p, '\n', (size_t)(e - p));
+    const char *le = nl ? nl : e;
+    const char *cr = (const char *)memchr(p, '\r', (size_t)(le - p));
+    return cr ? cr : le;
 }
 
 inline const char *field_end(const char *p, const char *le)
@@ -120,7 +123,17 @@ int64_t sb_vcf_line_starts(const char *buf, int64_t len, int64_t *line_starts, i
     }
     if (needs_python) {
         // the "##" block is parsed by the host's csv module (Description="..." is normal there)
-        for (int64_t i = first; i < len && !odd; ++i) odd = (buf[i] == '"') || ((unsigned char)buf[i] >= 0x80);
+        const int64_t block = 1 << 16, n_blocks = (len - first + block - 1) / block;
+        int any = 0;
+#pragma omp parallel for schedule(static) reduction(| : any)
+        for (int64_t b = 0; b < n_blocks; ++b) {
+            const unsigned char *q = (const unsigned char *)buf + first + b * block;
+            const int64_t m = std::min<int64_t>(block, len - first - b * block);
+            unsigned acc = 0;
+            for (int64_t i = 0; i < m; ++i) acc |= (unsigned)(q[i] == '"') | (unsigned)(q[i] >> 7);
+            any |= (int)acc;
+        }
+        odd = any != 0;
         *needs_python = odd ? 1 : 0;
     }
     return n;

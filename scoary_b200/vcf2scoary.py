@@ -141,10 +141,19 @@ def _native_table(vcf_path, types, keep):
                               bits.ctypes.data_as(ctypes.c_void_p), W, ranges.ctypes.data_as(ctypes.c_void_p), None)
     if rc != 0:
         return None
-    rg = ranges[:total].tolist()
-    chrom = [buf[b:e].decode("ascii") for (b, e), _, _ in rg]
-    pos = [buf[b:e].decode("ascii") for _, (b, e), _ in rg]
-    vid = [buf[b:e].decode("ascii") for _, _, (b, e) in rg]
+    def column(k):
+        """CHROM / POS / ID of every output row: gathered natively into one blob, decoded once, sliced `total` times"""
+        offs = np.empty(total + 1, dtype=np.int64)
+        rp, op = ranges.ctypes.data_as(ctypes.c_void_p), offs.ctypes.data_as(ctypes.c_void_p)
+        size = lib.sb_csv_gather_fields(buf, rp, total, 3, k, None, 0, op)
+        blob = np.empty(max(int(size), 1), dtype=np.uint8)
+        if size < 0 or lib.sb_csv_gather_fields(buf, rp, total, 3, k, blob.ctypes.data_as(ctypes.c_void_p), int(size),
+                                                op) != size:
+            return [buf[b:e].decode("ascii") for b, e in ranges[:total, k].tolist()]
+        text, o = blob[:size].tobytes().decode("ascii"), offs.tolist()      # the native parser only accepts ASCII files
+        return [text[o[r]:o[r + 1]] for r in range(total)]
+
+    chrom, pos, vid = column(0), column(1), column(2)
     names = [c + "_|_" + p + "_|_" + i for c, p, i in zip(chrom, pos, vid)]
     return GeneTable(names, pos, vid, kept_names, bits=bits)
 
