@@ -1580,11 +1580,7 @@ int sb_upgma(sb_ctx *ctx, int32_t *merges)
     auto cleanup = [&]() {
         cudaFree(d_T); cudaFree(d_allowed); cudaFree(d_nvar); cudaFree(S.D); cudaFree(S.rowmin_val); cudaFree(S.rowmin_col);
         cudaFree(S.size); cudaFree(S.alive); cudaFree(S.redo); cudaFree(S.pick); cudaFree(S.merges);
-        cudaFree(S.redo_list); cudaFree(S.redo_count); cudaFree(S.done);
     };
-    // SB_UPGMA_FUSED=1: two kernels per merge step (update + redo / finish / next pick) instead of four
-    const char *fused_env = getenv("SB_UPGMA_FUSED");
-    const bool fused = fused_env && atoi(fused_env) != 0;
 #define SB_TRY(call)                                                \
     do {                                                            \
         cudaError_t e__ = (call);                                   \
@@ -1606,11 +1602,6 @@ int sb_upgma(sb_ctx *ctx, int32_t *merges)
     SB_TRY(cudaMalloc(&S.pick, sizeof(int) * 4));
     SB_TRY(cudaMemsetAsync(S.pick, 0, sizeof(int) * 4, ctx->stream));
     SB_TRY(cudaMalloc(&S.merges, sizeof(int) * 2 * (size_t)(N - 1)));
-    SB_TRY(cudaMalloc(&S.redo_list, sizeof(int) * N));
-    SB_TRY(cudaMalloc(&S.redo_count, sizeof(int)));
-    SB_TRY(cudaMalloc(&S.done, sizeof(unsigned int)));
-    SB_TRY(cudaMemsetAsync(S.redo_count, 0, sizeof(int), ctx->stream));
-    SB_TRY(cudaMemsetAsync(S.done, 0, sizeof(unsigned int), ctx->stream));
     SB_TRY(cudaMemcpyAsync(d_allowed, h_allowed.data(), sizeof(uint64_t) * W, cudaMemcpyHostToDevice, ctx->stream));
     SB_TRY(cudaMemsetAsync(d_nvar, 0, sizeof(unsigned long long), ctx->stream));
     std::vector<double> ones(N, 1.0);
@@ -1627,18 +1618,9 @@ int sb_upgma(sb_ctx *ctx, int32_t *merges)
         // The N - 1 merge steps are four small kernels each (~20 000 launches at N = 5 000): one CUDA graph of
         // UPGMA_GRAPH_STEPS steps is captured once and replayed; the kernels read the step counter from device
         // memory and the steps past N - 1 in the last replay do nothing.
-        if (fused) {                     // the first pair; every later one is picked at the end of the step before
-            sb::upgma_pick_kernel<<<1, 1024, 0, ctx->stream>>>(S);
-            ctx->stats.kernel_launches += 1;
-        }
         auto one_step = [&]() {
-            if (fused) {
-                sb::upgma_update_kernel<true><<<(N + 255) / 256, 256, 0, ctx->stream>>>(S);
-                sb::upgma_redo_pick_kernel<<<sb::UPGMA_REDO_BLOCKS, 256, 0, ctx->stream>>>(S);
-                return;
-            }
             sb::upgma_pick_kernel<<<1, 1024, 0, ctx->stream>>>(S);
-            sb::upgma_update_kernel<false><<<(N + 255) / 256, 256, 0, ctx->stream>>>(S);
+            sb::upgma_update_kernel<<<(N + 255) / 256, 256, 0, ctx->stream>>>(S);
             sb::upgma_redo_kernel<<<N, 256, 0, ctx->stream>>>(S);
             sb::upgma_finish_step_kernel<<<1, 1, 0, ctx->stream>>>(S);
         };
@@ -1660,7 +1642,7 @@ int sb_upgma(sb_ctx *ctx, int32_t *merges)
         SB_TRY(cudaStreamSynchronize(ctx->stream));
         if (exec) cudaGraphExecDestroy(exec);
         if (graph) cudaGraphDestroy(graph);
-        ctx->stats.kernel_launches += (fused ? 2LL : 4LL) * (N - 1);
+        ctx->stats.kernel_launches += 4LL * (N - 1);
     }
     SB_TRY(cudaGetLastError());
     SB_TRY(cudaMemcpyAsync(merges, S.merges, sizeof(int) * 2 * (size_t)(N - 1), cudaMemcpyDeviceToHost, ctx->stream));

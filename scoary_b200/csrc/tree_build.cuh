@@ -117,10 +117,6 @@ struct UpgmaState {
     int *pick;            // [2] current (i, j); [2] = the merge step the next pick kernel performs
     int *merges;          // [N-1][2]
     int N;
-    // two-kernel steps (upgma_update_kernel<true> + upgma_redo_pick_kernel):
-    int *redo_list;       // [N] rows whose minimum must be recomputed, appended by the update kernel
-    int *redo_count;      // [1]
-    unsigned int *done;   // [1] blocks of the redo kernel that have finished their rows
 };
 // The three kernels of a merge step read the step counter pick[2] from device memory and do nothing once N - 1 merges
 // are done, so a CUDA graph of UPGMA_GRAPH_STEPS steps can be replayed until the tree is complete (sb_upgma).
@@ -196,10 +192,7 @@ __global__ void __launch_bounds__(1024) upgma_pick_kernel(const UpgmaState S)
     }
 }
 
-// new row/column of cluster i, retire j, incremental row-minimum maintenance (grid over k).
-// LIST: rows to recompute are appended to redo_list instead of flagged (the redo kernel then needs a handful of
-// blocks instead of one per row).
-template <bool LIST>
+// new row/column of cluster i, retire j, incremental row-minimum maintenance (grid over k)
 __global__ void __launch_bounds__(256) upgma_update_kernel(const UpgmaState S)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -219,12 +212,9 @@ __global__ void __launch_bounds__(256) upgma_update_kernel(const UpgmaState S)
     S.D[(int64_t)j * N + k] = UPGMA_BIG; // row j
     S.D[(int64_t)k * N + j] = UPGMA_BIG; // column j
     // row-minimum maintenance for row k (rows i and j are recomputed in full)
+    if (k == i || k == j) { S.redo[k] = 1; return; }
     const int mc = S.rowmin_col[k];
-    if (k == i || k == j || mc == i || mc == j) {
-        if (LIST) S.redo_list[atomicAdd(S.redo_count, 1)] = k;
-        else S.redo[k] = 1;
-        return;
-    }
+    if (mc == i || mc == j) { S.redo[k] = 1; return; }
     const double mv = S.rowmin_val[k];
     if (vi < mv || (vi == mv && i < mc)) { S.rowmin_val[k] = vi; S.rowmin_col[k] = i; }
 }
@@ -239,70 +229,6 @@ __global__ void __launch_bounds__(256) upgma_redo_kernel(const UpgmaState S)
     row_min_block(S, r, s_val, s_col);
     if (threadIdx.x == 0) {
         S.rowmin_val[r] = s_val[0]; S.rowmin_col[r] = s_col[0]; S.redo[r] = 0;
-    }
-}
-
-// Two-kernel step, second half: the listed rows are recomputed by a few blocks; the LAST block to finish (fence +
-// counter) closes the step (size / alive bookkeeping, step counter) and picks the next pair, so a step is
-// update + this kernel instead of pick + update + redo (one block per row) + finish.  Same arithmetic, same tie rules.
-constexpr int UPGMA_REDO_BLOCKS = 8;
-__global__ void __launch_bounds__(256) upgma_redo_pick_kernel(const UpgmaState S)
-{
-    __shared__ double s_val[256];
-    __shared__ int s_col[256];
-    __shared__ unsigned long long s_key[256];
-    __shared__ int s_row[256];
-    __shared__ int s_last;
-    const int step = S.pick[2];          // changes only after every block has arrived at the counter below
-    if (step >= S.N - 1) return;
-    const int n_redo = *S.redo_count;
-    for (int e = blockIdx.x; e < n_redo; e += gridDim.x) {
-        const int r = S.redo_list[e];
-        row_min_block(S, r, s_val, s_col);
-        if (threadIdx.x == 0) { S.rowmin_val[r] = s_val[0]; S.rowmin_col[r] = s_col[0]; }
-        __syncthreads();                 // s_val / s_col are reused by the next row
-    }
-    if (threadIdx.x == 0) {
-        __threadfence();
-        s_last = atomicInc(S.done, gridDim.x - 1) == gridDim.x - 1;      // wraps to 0 for the next step
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    if (threadIdx.x == 0) {              // what upgma_finish_step_kernel does
-        const int i = S.pick[0], j = S.pick[1];
-        S.size[i] = __dadd_rn(S.size[i], S.size[j]);
-        S.size[j] = 0.0;
-        S.alive[j] = 0;
-        *S.redo_count = 0;
-        S.pick[2] = step + 1;
-    }
-    if (step + 1 >= S.N - 1) return;
-    // the next pick, as upgma_pick_kernel; the row minima were written by other blocks: read them past L1
-    double bv = UPGMA_BIG * 4.0;
-    unsigned long long bk = ~0ULL;
-    int br = -1;
-    for (int r = threadIdx.x; r < S.N; r += 256) {
-        const double v = __ldcg(&S.rowmin_val[r]);
-        const unsigned long long k = morton_key((unsigned)r, (unsigned)__ldcg(&S.rowmin_col[r]));
-        if (v < bv || (v == bv && k < bk)) { bv = v; bk = k; br = r; }
-    }
-    s_val[threadIdx.x] = bv; s_key[threadIdx.x] = bk; s_row[threadIdx.x] = br;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-        if (threadIdx.x < o) {
-            const double v = s_val[threadIdx.x + o];
-            const unsigned long long k = s_key[threadIdx.x + o];
-            if (v < s_val[threadIdx.x] || (v == s_val[threadIdx.x] && k < s_key[threadIdx.x])) {
-                s_val[threadIdx.x] = v; s_key[threadIdx.x] = k; s_row[threadIdx.x] = s_row[threadIdx.x + o];
-            }
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        const int i = s_row[0], j = __ldcg(&S.rowmin_col[i]);
-        S.pick[0] = i; S.pick[1] = j;
-        S.merges[2 * (step + 1)] = i; S.merges[2 * (step + 1) + 1] = j;
     }
 }
 
